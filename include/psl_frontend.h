@@ -1,0 +1,104 @@
+/*
+ * psl_frontend.h — C-ABI of the B200-native PSL-SLAM feature front end.
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference
+ * interface it replaces (file:line relative to the PSL-SLAM tree).  The
+ * library (libpsl_frontend.so) is CUDA-only: there is no CPU fallback; every
+ * call fails with PSL_E_CUDA when no sm_100 device is usable.
+ *
+ * Conventions
+ *   - all functions return 0 (PSL_OK) or a negative PSL_E_* code and never throw;
+ *     psl_last_error(ctx) returns a human-readable reason for the last failure.
+ *   - the caller owns every buffer and passes capacities; the callee writes counts.
+ *   - a psl_ctx is bound to one GPU and one stream and is NOT re-entrant — the same
+ *     rule as the reference extractors (stateful mvImagePyramid member,
+ *     include/ORBextractor.h:85; one extractor per thread, src/Frame.cc:92-93).
+ *   - "_dev" variants take device pointers (inputs already resident in HBM) and
+ *     enqueue on the ctx stream; the non-_dev variants take HOST pointers and
+ *     include the H2D/D2H copies.
+ */
+#ifndef PSL_FRONTEND_H
+#define PSL_FRONTEND_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSL_OK 0
+#define PSL_E_INVALID (-1)   /* bad argument (null, size, stride, aspect) */
+#define PSL_E_CUDA (-2)      /* CUDA runtime failure / no device */
+#define PSL_E_CAPACITY (-3)  /* caller buffer or ctx limit too small */
+#define PSL_E_INTERNAL (-4)
+
+typedef struct psl_ctx psl_ctx;
+
+/* Same field order and size (28 B) as cv::KeyPoint, the element type of
+ * ORBextractor::operator()'s `keypoints` (include/ORBextractor.h:59-61). */
+typedef struct psl_keypoint {
+  float x, y;     /* pt, level-0 pixel coordinates (ORBextractor.cc:1095-1101) */
+  float size;     /* 31*scale[octave] truncated (ORBextractor.cc:837) */
+  float angle;    /* degrees, IC_Angle (ORBextractor.cc:77-104) */
+  float response; /* FAST score */
+  int32_t octave;
+  int32_t class_id; /* always -1 */
+} psl_keypoint;
+
+/* Mirrors the YAML keys read in src/Tracking.cc:113-127
+ * (ORBextractor.* / LINEextractor.*; Examples/RGB-D/TUM1.yaml:42-63). */
+typedef struct psl_config {
+  int32_t device;          /* CUDA ordinal */
+  int32_t max_width;       /* largest frame the ctx must accept */
+  int32_t max_height;
+  int32_t max_batch;       /* frames in flight per *_batch call */
+  int32_t orb_nfeatures;   /* ORBextractor.nFeatures   (1000) */
+  float orb_scale_factor;  /* ORBextractor.scaleFactor (1.2)  */
+  int32_t orb_nlevels;     /* ORBextractor.nLevels     (8)    */
+  int32_t orb_ini_th_fast; /* ORBextractor.iniThFAST   (20)   */
+  int32_t orb_min_th_fast; /* ORBextractor.minThFAST   (7)    */
+  int32_t line_nfeatures;  /* LINEextractor.nFeatures  (200)  */
+  float line_scale_factor; /* LINEextractor.scaleFactor (1.2; truncated to int 1 by the reference) */
+  int32_t line_nlevels;    /* LINEextractor.nLevels    (1)    */
+  float line_min_length;   /* LINEextractor.min_line_length (0) */
+} psl_config;
+
+void psl_default_config(psl_config* cfg);
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:410-470) + LINEextractor ctor
+ * (add_src/LineExtractor.cpp:6-25): tables, device buffers, stream. */
+int psl_create(const psl_config* cfg, psl_ctx** out);
+void psl_destroy(psl_ctx* ctx);
+const char* psl_last_error(const psl_ctx* ctx);
+/* cudaStream_t of the ctx, as void* (for callers that order their own work after ours). */
+void* psl_stream(psl_ctx* ctx);
+int psl_sync(psl_ctx* ctx);
+
+/* ORBextractor::GetLevels/GetScaleFactors/GetInverseScaleFactors/GetScaleSigmaSquares/
+ * GetInverseScaleSigmaSquares (include/ORBextractor.h:63-83); each array nlevels long (may be NULL). */
+int psl_orb_tables(const psl_ctx* ctx, int32_t* nlevels, float* scale, float* inv_scale, float* sigma2,
+                   float* inv_sigma2, int32_t* features_per_level);
+
+/* ORBextractor::operator()(image, mask, keypoints, descriptors)
+ * (src/ORBextractor.cc:1043-1105; called from Frame::ExtractORB, src/Frame.cc:311-317).
+ * gray: HOST CV_8UC1, `stride` bytes per row.  mask is ignored by the reference and absent here.
+ * kps[cap], desc[cap*32]; *n = number written (≤ nfeatures + 3*nlevels).
+ * Empty image (w==0||h==0) → *n = 0, PSL_OK (the reference returns silently, :1046-1047). */
+int psl_orb_extract(psl_ctx* ctx, const uint8_t* gray, int32_t w, int32_t h, int32_t stride, psl_keypoint* kps,
+                    uint8_t* desc, int32_t cap, int32_t* n);
+
+/* Batched form of the same call: B frames of identical size, frame b at gray + b*frame_stride
+ * (HOST).  Outputs are [B][cap] row blocks; n[b] = count of frame b. */
+int psl_orb_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t w, int32_t h, int32_t stride,
+                          int64_t frame_stride, psl_keypoint* kps, uint8_t* desc, int32_t cap, int32_t* n);
+
+/* Same, all pointers DEVICE memory; asynchronous on psl_stream(ctx). */
+int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, int32_t w, int32_t h, int32_t stride,
+                              int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
+                              int32_t* d_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSL_FRONTEND_H */

@@ -1,0 +1,53 @@
+/*
+ * psl_oracle.h — TEST INFRASTRUCTURE.  CPU restatement of the reference's
+ * front-end algorithms; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product
+ * (libpsl_frontend.so) never links or calls anything declared here.
+ *
+ * Parity status: the reference cannot be compiled here (needs OpenCV 3.x +
+ * contrib headers) and holds no tests or golden vectors for this path
+ * (SURVEY.md §4, §8c).  The oracle is pinned against goldens produced by
+ * oracle/pyref/ (the reference's control flow over the real cv2 4.13
+ * primitives) — "pinned to cv2-primitive goldens, unpinned by the reference".
+ */
+#ifndef PSL_ORACLE_H
+#define PSL_ORACLE_H
+#include <stdint.h>
+
+#include "../../include/psl_frontend.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_orb_params {
+  int32_t nfeatures;
+  float scale_factor;
+  int32_t nlevels, ini_th, min_th;
+} orc_orb_params;
+
+/* primitives */
+void orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+void orc_gauss_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize);
+float orc_fast_atan2(float y, float x);
+/* FAST-9/16 score of every pixel of a w×h image (0 where not evaluable / not a corner at `th`) */
+void orc_fast_score(const uint8_t* img, int w, int h, int stride, int th, uint8_t* score);
+
+/* ctor tables, ORBextractor.cc:410-470; arrays nlevels long */
+void orc_orb_tables(const orc_orb_params* p, float* scale, float* inv_scale, int32_t* quota, int32_t* umax16);
+void orc_orb_level_size(const orc_orb_params* p, int w, int h, int level, int* lw, int* lh);
+
+/* stage functions; coordinates of candidates/selected are relative to minBorder (16) as in the reference */
+int orc_fast_cells(const uint8_t* img, int w, int h, int stride, int ini_th, int min_th, float* xyr, int cap);
+int orc_octree(const float* xyr, int n, int min_x, int max_x, int min_y, int max_y, int N, float* out_xyr, int cap);
+float orc_ic_angle(const uint8_t* img, int stride, int x, int y);
+void orc_brief(const uint8_t* blur, int stride, float x, float y, float angle_deg, uint8_t* desc32);
+
+/* ORBextractor::operator(), ORBextractor.cc:1043-1105.  Returns 0 or <0. */
+int orc_orb_extract(const orc_orb_params* p, const uint8_t* gray, int w, int h, int stride, psl_keypoint* kps,
+                    uint8_t* desc, int cap, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
