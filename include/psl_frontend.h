@@ -58,6 +58,9 @@ typedef struct psl_config {
   int32_t orb_nlevels;     /* ORBextractor.nLevels     (8)    */
   int32_t orb_ini_th_fast; /* ORBextractor.iniThFAST   (20)   */
   int32_t orb_min_th_fast; /* ORBextractor.minThFAST   (7)    */
+  int32_t orb_max_candidates; /* FAST candidate pool per frame; 0 = auto (the reference only
+                                 reserves nfeatures*10 as a hint, ORBextractor.cc:779) */
+  int32_t chunk_frames;    /* frames processed together so a chunk's pyramid stays in L2; 0 = auto */
   int32_t line_nfeatures;  /* LINEextractor.nFeatures  (200)  */
   float line_scale_factor; /* LINEextractor.scaleFactor (1.2; truncated to int 1 by the reference) */
   int32_t line_nlevels;    /* LINEextractor.nLevels    (1)    */
@@ -97,6 +100,17 @@ int psl_orb_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t 
 int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, int32_t w, int32_t h, int32_t stride,
                               int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
                               int32_t* d_n);
+
+/* Diagnostic: copy an intermediate of the LAST ORB call (chunk-local frame index) to the host, so the
+ * stage-level parity tests can compare with ComputePyramid (ORBextractor.cc:1107-1132), the FAST cell
+ * loop (:789-829) and DistributeOctTree (:539-763) separately.
+ *   what = 0: pyramid level image, tightly packed w*h bytes (level >= 1)
+ *          1: blurred level image, tightly packed
+ *          2: FAST candidates of the level in reference order, packed u32 (x-16)<<20 | (y-16)<<8 | score
+ *          3: octree-selected keys of the level in list order, same packing
+ * *n = number of bytes (0,1) or entries (2,3) written. */
+int psl_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, int32_t level, void* out, int64_t cap_bytes,
+                    int64_t* n);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,7 @@
+"""psl_slam_b200 — B200-native feature front end of PSL-SLAM (ORB + lines + matching).
+
+Host-side mirrors of the reference's extractor / matcher classes over the C-ABI in
+include/psl_frontend.h (libpsl_frontend.so, hand-written sm_100a CUDA).  No CPU fallback.
+"""
+from ._lib import KP_DTYPE, PslError, default_config  # noqa: F401
+from .orb import Context, ORBextractor  # noqa: F401

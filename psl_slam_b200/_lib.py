@@ -1,0 +1,70 @@
+"""ctypes binding of libpsl_frontend.so (the CUDA product library, include/psl_frontend.h).
+
+There is no fallback: if the library is missing or no B200 is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpsl_frontend.so")
+
+PSL_OK, PSL_E_INVALID, PSL_E_CUDA, PSL_E_CAPACITY, PSL_E_INTERNAL = 0, -1, -2, -3, -4
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+class PslError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"psl error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
+                ("max_batch", C.c_int32), ("orb_nfeatures", C.c_int32), ("orb_scale_factor", C.c_float),
+                ("orb_nlevels", C.c_int32), ("orb_ini_th_fast", C.c_int32), ("orb_min_th_fast", C.c_int32),
+                ("orb_max_candidates", C.c_int32), ("chunk_frames", C.c_int32), ("line_nfeatures", C.c_int32),
+                ("line_scale_factor", C.c_float), ("line_nlevels", C.c_int32), ("line_min_length", C.c_float)]
+
+
+# every symbol include/psl_frontend.h declares (checked by tests/test_abi.py)
+EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", "psl_stream", "psl_sync",
+           "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(f"{SO_PATH} not built — run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                              "there is no CPU fallback")
+        L = C.CDLL(SO_PATH)
+        L.psl_last_error.restype = C.c_char_p
+        L.psl_last_error.argtypes = [C.c_void_p]
+        L.psl_stream.restype = C.c_void_p
+        L.psl_stream.argtypes = [C.c_void_p]
+        L.psl_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        L.psl_destroy.argtypes = [C.c_void_p]
+        L.psl_destroy.restype = None
+        L.psl_sync.argtypes = [C.c_void_p]
+        L.psl_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        _i, _p, _l = C.c_int32, C.c_void_p, C.c_int64
+        L.psl_orb_extract.argtypes = [_p, _p, _i, _i, _i, _p, _p, _i, _p]
+        L.psl_orb_extract_batch.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _i, _p]
+        L.psl_orb_extract_batch_dev.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _i, _p]
+        L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
+        _lib = L
+    return _lib
+
+
+def default_config() -> Config:
+    cfg = Config()
+    lib().psl_default_config(C.byref(cfg))
+    return cfg

@@ -1,0 +1,36 @@
+// Launchers of the ORB extractor kernels (all asynchronous on `st`).
+#pragma once
+#include "psl_common.cuh"
+
+namespace psl {
+
+// per-axis resize tables of one level (built on the host)
+struct ResizeTables {
+  const short4* xt;  // [dw]  (sx, sx+1 clamped, a0, a1)
+  const short4* yt;  // [dh]  (sy, sy+1 clamped, b0, b1)
+};
+
+// K1: level l from level l-1 (ORBextractor.cc:1120)
+void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTables& t, int B, cudaStream_t st);
+
+// K2: per-cell FAST + NMS + threshold fallback + ordered compaction (ORBextractor.cc:789-829)
+void launch_fast_cells(const OrbGeometry* d_geo, const OrbGeometry& geo, ImgBatch in0, int ini_th, int min_th,
+                       uint32_t* pool, int pool_cap, uint32_t* pool_count, uint2* cell_tab, uint32_t* status, int B,
+                       cudaStream_t st);
+
+// K3: DistributeOctTree per (frame, level) (ORBextractor.cc:539-763)
+void launch_octree(const OrbGeometry* d_geo, const OrbGeometry& geo, const uint32_t* pool, int pool_cap,
+                   const uint2* cell_tab, uint32_t* key_scratch, uint16_t* node_scratch, uint32_t* sel,
+                   int32_t* sel_count, uint32_t* status, int B, cudaStream_t st);
+
+// K5: 7x7 sigma-2 Gaussian blur of every level (ORBextractor.cc:1085-1086)
+void launch_gauss7(const OrbGeometry& geo, ImgBatch in0, int B, cudaStream_t st);
+
+// K4+K6: orientation, rBRIEF, final keypoint records (ORBextractor.cc:77-147,837-852,1095-1103)
+void launch_describe(const OrbGeometry* d_geo, const OrbGeometry& geo, ImgBatch in0, const uint32_t* sel,
+                     const int32_t* sel_count, psl_keypoint* kps, uint8_t* desc, int cap, int32_t* n_out,
+                     uint32_t* status, int B, cudaStream_t st);
+
+size_t octree_smem_bytes(int node_cap);
+
+}  // namespace psl

@@ -1,0 +1,54 @@
+// Host-side context shared by the C-ABI translation units.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "orb_kernels.cuh"
+
+struct psl_ctx {
+  psl_config cfg{};
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int chunk = 0;
+  int pool_cap = 0;
+
+  // ORBextractor ctor tables (ORBextractor.cc:410-446)
+  std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+  std::vector<int32_t> quota;
+
+  // geometry of the current frame size
+  int geo_w = 0, geo_h = 0;
+  psl::OrbGeometry geo{};
+  psl::OrbGeometry* d_geo = nullptr;
+  std::vector<psl::ResizeTables> rtab;
+  void* d_tables = nullptr;       // resize tables of all levels
+  uint8_t* d_levels = nullptr;    // pyramid levels 1.. and blurred levels 0.. of one chunk
+  uint32_t* d_pool = nullptr;     // [chunk][pool_cap] FAST candidates
+  uint32_t* d_pool_count = nullptr;
+  uint2* d_cell_tab = nullptr;    // [chunk][total_cells] (offset,count)
+  uint32_t* d_key_scratch = nullptr;   // [chunk][2][pool_cap]
+  uint16_t* d_node_scratch = nullptr;  // [chunk][2][pool_cap]
+  uint32_t* d_sel = nullptr;      // [chunk][total_sel]
+  int32_t* d_sel_count = nullptr; // [chunk][nlevels]
+  uint32_t* d_status = nullptr;
+  uint32_t* h_status = nullptr;   // pinned mirror
+
+  // staging for the host-pointer entry points (grown on demand)
+  uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
+  psl_keypoint* d_kps = nullptr; size_t d_kps_bytes = 0;
+  uint8_t* d_desc = nullptr; size_t d_desc_bytes = 0;
+  int32_t* d_n = nullptr; size_t d_n_bytes = 0;
+};
+
+namespace psl {
+int fail(psl_ctx* c, int code, const std::string& msg);
+int cuda_fail(psl_ctx* c, cudaError_t e, const char* what);
+int ensure_bytes(psl_ctx* c, void** p, size_t* have, size_t need);
+int check_status(psl_ctx* c);  // sync + translate the device status word
+}  // namespace psl
+
+#define PSL_CK(call)                                                     \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return psl::cuda_fail(ctx, e__, #call);      \
+  } while (0)

@@ -3,7 +3,7 @@
 A planar colour "poster" of random filled rectangles is viewed by a pinhole
 camera (ICL intrinsics, Examples/RGB-D/ICL.yaml:8-11 in the reference) moving
 on a smooth 6-DoF trajectory.  Everything is numpy float64 + PCG64, so the same
-seed gives the same bytes on every box.  Not an oracle: it only makes inputs.
+seed gives the same bytes on every box.  It only makes inputs; it checks nothing.
 """
 from __future__ import annotations
 

@@ -1,0 +1,124 @@
+"""GPU: the CUDA ORB extractor through the C-ABI against the oracle and the committed goldens."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+ORB = golden_names("orb_")
+
+
+def _extractor(g):
+    from psl_slam_b200 import ORBextractor
+    nf, nl, ini, mn = [int(v) for v in g["params"]]
+    h, w = g["image"].shape
+    return ORBextractor(nf, float(g["scale_factor"]), nl, ini, mn, max_width=w, max_height=h)
+
+
+def _same(kps, desc, okps, odesc):
+    assert len(kps) == len(okps)
+    for f in kps.dtype.names:
+        assert np.array_equal(kps[f], okps[f]), f
+    assert np.array_equal(desc, odesc)
+
+
+@pytest.mark.parametrize("name", ORB)
+def test_orb_vs_golden(name):
+    g = load_golden(name)
+    ex = _extractor(g)
+    kps, desc = ex(g["image"])
+    gk = g["kps"]
+    assert len(kps) == len(gk)
+    for i, f in enumerate(["x", "y", "size", "angle", "response"]):
+        assert np.array_equal(kps[f], gk[:, i]), f
+    assert np.array_equal(kps["octave"], g["octave"])
+    assert np.all(kps["class_id"] == -1)
+    assert np.array_equal(desc, g["desc"])
+
+
+def test_getters_match_oracle(orc):
+    from psl_slam_b200 import ORBextractor
+    ex = ORBextractor()
+    scale, inv, quota, _ = orc.orb_tables(orc.params())
+    assert np.array_equal(ex.GetScaleFactors(), scale)
+    assert np.array_equal(ex.GetInverseScaleFactors(), inv)
+    assert np.array_equal(ex.features_per_level(), quota)
+    assert ex.GetLevels() == 8
+
+
+def test_batch_sequence_vs_oracle(orc):
+    """cfg-4 shaped: a batch of consecutive frames, more frames than one chunk."""
+    from psl_slam_b200 import ORBextractor, synth
+    gray, _, _ = synth.sequence(4, 5)
+    ex = ORBextractor(chunk_frames=2)
+    kps, desc, n = ex.extract_batch(gray)
+    for b in range(len(gray)):
+        okps, odesc = orc.orb_extract(gray[b])
+        _same(kps[b, : n[b]], desc[b, : n[b]], okps, odesc)
+
+
+def test_strided_input_and_repeatability(orc):
+    from psl_slam_b200 import ORBextractor, synth
+    gray, _, _ = synth.sequence(6, 1)
+    big = np.zeros((480, 1000), np.uint8)
+    big[:, 100:740] = gray[0]
+    ex = ORBextractor()
+    a = ex(big[:, 100:740])
+    b = ex(gray[0])
+    _same(a[0], a[1], b[0], b[1])
+    okps, odesc = orc.orb_extract(gray[0])
+    _same(a[0], a[1], okps, odesc)
+
+
+def test_random_noise_sizes(orc):
+    """Dense-corner stress (every cell full, octree phase 2 everywhere) at odd sizes."""
+    from psl_slam_b200 import ORBextractor
+    rng = np.random.default_rng(3)
+    for (w, h, nf, nl) in [(231, 187, 700, 4), (402, 150, 300, 3), (640, 480, 2000, 8)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        ex = ORBextractor(nf, 1.2, nl, 20, 7, max_width=w, max_height=h, max_candidates=131072)
+        kps, desc = ex(img)
+        okps, odesc = orc.orb_extract(img, orc.params(nf, 1.2, nl, 20, 7))
+        _same(kps, desc, okps, odesc)
+
+
+def test_empty_and_errors():
+    from psl_slam_b200 import ORBextractor, PslError
+    ex = ORBextractor()
+    kps, desc = ex(np.zeros((0, 0), np.uint8))
+    assert len(kps) == 0 and desc.shape == (0, 32)
+    with pytest.raises(PslError):
+        ex(np.zeros((600, 800), np.uint8))  # larger than max_width/max_height
+    with pytest.raises(PslError):
+        ORBextractor(1000, 1.2, 8, 20, 7, max_width=64, max_height=64)(np.zeros((64, 64), np.uint8))
+
+
+def test_candidate_pool_overflow_is_loud():
+    from psl_slam_b200 import ORBextractor, PslError
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    ex = ORBextractor(max_candidates=1024)
+    with pytest.raises(PslError) as e:
+        ex(img)
+    assert e.value.code == -3
+    ex2 = ORBextractor(max_candidates=131072)
+    assert len(ex2(img)[0]) >= 1000
+
+
+@pytest.mark.parametrize("name", ORB)
+def test_stages_vs_golden(name):
+    """Pyramid level, blur, FAST candidates and octree selection, stage by stage."""
+    g = load_golden(name)
+    ex = _extractor(g)
+    ex(g["image"])
+    lvl = int(g["level_idx"])
+    li = g["level_img"]
+    if lvl > 0:
+        assert np.array_equal(ex.debug_fetch(0, 0, lvl).reshape(li.shape), li)
+    if "level_blur" in g:
+        assert np.array_equal(ex.debug_fetch(1, 0, lvl).reshape(li.shape), g["level_blur"])
+    for l in range(ex.GetLevels()):
+        assert np.array_equal(ex.debug_fetch(2, 0, l), g[f"cands_{l}"]), f"candidates level {l}"
+        sel = ex.debug_fetch(3, 0, l)
+        gs = g[f"sel_{l}"]
+        assert np.array_equal(sel[:, :2] + 16, gs[:, :2]) and np.array_equal(sel[:, 2], gs[:, 2]), f"octree level {l}"
