@@ -101,6 +101,16 @@ int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, in
                               int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
                               int32_t* d_n);
 
+/* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).
+ * Stages: 0 pyramid resize, 1 FAST cells, 2 octree selection, 3 Gaussian blur, 4 orientation+rBRIEF,
+ * 5.. reserved for matching / line stages.  psl_profile_read synchronises, writes the accumulated
+ * milliseconds and kernel-launch counts per stage since the last read (arrays of PSL_N_STAGES) and resets. */
+#define PSL_N_STAGES 16
+int psl_profile_enable(psl_ctx* ctx, int32_t on);
+int psl_profile_read(psl_ctx* ctx, float* ms, int64_t* launches);
+/* Kernel launches issued by this ctx since creation (all stages). */
+int64_t psl_launch_count(const psl_ctx* ctx);
+
 /* Diagnostic: copy an intermediate of the LAST ORB call (chunk-local frame index) to the host, so the
  * stage-level parity tests can compare with ComputePyramid (ORBextractor.cc:1107-1132), the FAST cell
  * loop (:789-829) and DistributeOctTree (:539-763) separately.

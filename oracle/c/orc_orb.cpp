@@ -79,22 +79,48 @@ void orc_gauss_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* d
   static const int k7[7] = {18, 34, 48, 56, 48, 34, 18};  // sigma 2
   static const int k5[5] = {14, 62, 104, 62, 14};         // sigma 1
   const int* k = ksize == 7 ? k7 : k5;
-  int r = ksize / 2;
-  std::vector<uint16_t> H((size_t)w * h);
+  const int r = ksize / 2;
+  static thread_local std::vector<uint16_t> H;
+  H.resize((size_t)w * h);
   for (int y = 0; y < h; ++y) {
     const uint8_t* S = src + (size_t)y * sstride;
-    for (int x = 0; x < w; ++x) {
+    uint16_t* Hr = &H[(size_t)y * w];
+    const int xa = std::min(r, w), xb = std::max(w - r, xa);
+    for (int x = 0; x < xa; ++x) {
       int acc = 0;
       for (int i = -r; i <= r; ++i) acc += k[i + r] * S[reflect101(x + i, w)];
-      H[(size_t)y * w + x] = (uint16_t)acc;
+      Hr[x] = (uint16_t)acc;
+    }
+    if (ksize == 7)
+      for (int x = xa; x < xb; ++x)
+        Hr[x] = (uint16_t)(18 * (S[x - 3] + S[x + 3]) + 34 * (S[x - 2] + S[x + 2]) + 48 * (S[x - 1] + S[x + 1]) + 56 * S[x]);
+    else
+      for (int x = xa; x < xb; ++x)
+        Hr[x] = (uint16_t)(14 * (S[x - 2] + S[x + 2]) + 62 * (S[x - 1] + S[x + 1]) + 104 * S[x]);
+    for (int x = xb; x < w; ++x) {
+      int acc = 0;
+      for (int i = -r; i <= r; ++i) acc += k[i + r] * S[reflect101(x + i, w)];
+      Hr[x] = (uint16_t)acc;
     }
   }
-  for (int y = 0; y < h; ++y)
-    for (int x = 0; x < w; ++x) {
-      uint32_t acc = 0;
-      for (int j = -r; j <= r; ++j) acc += (uint32_t)k[j + r] * H[(size_t)reflect101(y + j, h) * w + x];
-      dst[(size_t)y * dstride + x] = (uint8_t)((acc + 32768u) >> 16);
+  for (int y = 0; y < h; ++y) {
+    const uint16_t* rows[7];
+    for (int j = -r; j <= r; ++j) rows[j + r] = &H[(size_t)reflect101(y + j, h) * w];
+    uint8_t* D = dst + (size_t)y * dstride;
+    if (ksize == 7) {
+      const uint16_t *r0 = rows[0], *r1 = rows[1], *r2 = rows[2], *r3 = rows[3], *r4 = rows[4], *r5 = rows[5], *r6 = rows[6];
+      for (int x = 0; x < w; ++x) {
+        uint32_t acc = 18u * ((uint32_t)r0[x] + r6[x]) + 34u * ((uint32_t)r1[x] + r5[x]) + 48u * ((uint32_t)r2[x] + r4[x]) + 56u * r3[x];
+        D[x] = (uint8_t)((acc + 32768u) >> 16);
+      }
+    } else {
+      for (int x = 0; x < w; ++x) {
+        uint32_t acc = 0;
+        for (int j = 0; j < ksize; ++j) acc += (uint32_t)k[j] * rows[j][x];
+        D[x] = (uint8_t)((acc + 32768u) >> 16);
+      }
     }
+  }
 }
 
 // cv::fastAtan2 scalar (App. A4), degrees.
@@ -135,7 +161,20 @@ void orc_fast_score(const uint8_t* img, int w, int h, int stride, int th, uint8_
       int d4 = c - p[off[4]], d12 = c - p[off[12]];
       if (std::abs(d4) <= th && std::abs(d12) <= th) continue;
       int d[25];
-      for (int k = 0; k < 16; ++k) d[k] = c - p[off[k]];
+      unsigned mb = 0, md = 0;
+      for (int k = 0; k < 16; ++k) {
+        d[k] = c - p[off[k]];
+        mb |= (unsigned)(d[k] > th) << k;
+        md |= (unsigned)(d[k] < -th) << k;
+      }
+      auto run9 = [](unsigned m16) {
+        unsigned m = m16 | (m16 << 16), r = m & (m >> 1);
+        r &= r >> 2;
+        r &= r >> 4;
+        r &= m >> 8;
+        return (r & 0xFFFFu) != 0;
+      };
+      if (!run9(mb) && !run9(md)) continue;  // not a corner at th: its score would be < th
       for (int k = 16; k < 25; ++k) d[k] = d[k - 16];
       int best = 0;
       for (int s = 0; s < 16; ++s) {
@@ -200,9 +239,11 @@ int orc_fast_cells(const uint8_t* img, int w, int h, int stride, int ini_th, int
   const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
   if (nCols <= 0 || nRows <= 0) return 0;
   const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
-  std::vector<uint8_t> s_ini((size_t)w * h), s_min((size_t)w * h);
-  orc_fast_score(img, w, h, stride, ini_th, s_ini.data());
-  orc_fast_score(img, w, h, stride, min_th, s_min.data());
+  // The score is threshold independent (App. A3), so cv::FAST(th)'s score image is the raw
+  // score map with values below th zeroed: one map at the lower threshold serves both passes.
+  static thread_local std::vector<uint8_t> raw;
+  raw.resize((size_t)w * h);
+  orc_fast_score(img, w, h, stride, std::min(ini_th, min_th), raw.data());
   int n = 0;
   for (int i = 0; i < nRows; ++i) {
     int iniY = minBY + i * hCell, maxY = iniY + hCell + 6;
@@ -216,16 +257,18 @@ int orc_fast_cells(const uint8_t* img, int w, int h, int stride, int ini_th, int
       int x0 = iniX + 3, x1 = maxX - 3, y0 = iniY + 3, y1 = maxY - 3;
       int start = n;
       for (int pass = 0; pass < 2 && n == start; ++pass) {
-        const uint8_t* S = pass == 0 ? s_ini.data() : s_min.data();
+        const uint8_t* S = raw.data();
+        const int th = pass == 0 ? ini_th : min_th;
         for (int y = y0; y < y1; ++y)
           for (int x = x0; x < x1; ++x) {
             int sc = S[(size_t)y * w + x];
-            if (!sc) continue;
+            if (sc < th) continue;
             bool ok = true;
             for (int yy = y - 1; yy <= y + 1 && ok; ++yy)
               for (int xx = x - 1; xx <= x + 1; ++xx) {
                 if ((xx == x && yy == y) || xx < x0 || xx >= x1 || yy < y0 || yy >= y1) continue;
-                if (S[(size_t)yy * w + xx] >= sc) { ok = false; break; }
+                const int sn = S[(size_t)yy * w + xx];
+                if (sn >= th && sn >= sc) { ok = false; break; }
               }
             if (!ok) continue;
             if (n < cap) {
@@ -416,7 +459,8 @@ int orc_orb_extract(const orc_orb_params* p, const uint8_t* gray, int w, int h, 
   std::vector<float> scale(L), inv(L);
   std::vector<int32_t> quota(L);
   orc_orb_tables(p, scale.data(), inv.data(), quota.data(), nullptr);
-  std::vector<std::vector<uint8_t>> pyr(L);
+  static thread_local std::vector<std::vector<uint8_t>> pyr;
+  pyr.resize(L);
   std::vector<int> lw(L), lh(L);
   for (int l = 0; l < L; ++l) {  // ComputePyramid :1107-1132 (border never read → not built)
     lw[l] = cv_round((float)w * inv[l]);
@@ -429,8 +473,8 @@ int orc_orb_extract(const orc_orb_params* p, const uint8_t* gray, int w, int h, 
       orc_resize_linear_u8(pyr[l - 1].data(), lw[l - 1], lh[l - 1], lw[l - 1], pyr[l].data(), lw[l], lh[l], lw[l]);
   }
   int n = 0;
-  std::vector<float> cand, sel;
-  std::vector<uint8_t> blur;
+  static thread_local std::vector<float> cand, sel;
+  static thread_local std::vector<uint8_t> blur;
   for (int l = 0; l < L; ++l) {
     int ccap = (lw[l] * lh[l]) / 4 + 16;
     cand.resize((size_t)3 * ccap);
@@ -464,3 +508,33 @@ int orc_orb_extract(const orc_orb_params* p, const uint8_t* gray, int w, int h, 
 }
 
 }  // extern "C"
+
+// ---- throughput harness for the CPU baseline: one frame per task, `nthreads` workers --------
+#include <atomic>
+#include <thread>
+extern "C" int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
+                                        int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor) {
+  std::atomic<int> next(0), err(0);
+  std::atomic<uint32_t> acc(0);
+  auto work = [&]() {
+    const int cap = p->nfeatures + 4 * p->nlevels + 16;
+    std::vector<psl_keypoint> kps(cap);
+    std::vector<uint8_t> desc((size_t)cap * 32);
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= B) break;
+      int n = 0;
+      if (orc_orb_extract(p, gray + (size_t)b * frame_stride, w, h, stride, kps.data(), desc.data(), cap, &n)) err = 1;
+      n_out[b] = n;
+      uint32_t x = 0;
+      for (int i = 0; i < n * 8; ++i) x ^= reinterpret_cast<const uint32_t*>(desc.data())[i];
+      acc.fetch_xor(x);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  if (desc_xor) *desc_xor = acc.load();
+  return err.load() ? -1 : 0;
+}

@@ -47,6 +47,10 @@ void orc_brief(const uint8_t* blur, int stride, float x, float y, float angle_de
 int orc_orb_extract(const orc_orb_params* p, const uint8_t* gray, int w, int h, int stride, psl_keypoint* kps,
                     uint8_t* desc, int cap, int* n);
 
+/* CPU-baseline harness: B frames, one frame per task on `nthreads` std::threads. */
+int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
+                             int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor);
+
 #ifdef __cplusplus
 }
 #endif

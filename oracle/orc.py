@@ -119,3 +119,17 @@ def orb_extract(img: np.ndarray, p: OrbParams | None = None, cap: int | None = N
     if rc != 0:
         raise RuntimeError(f"orc_orb_extract rc={rc}")
     return kps[: n.value].copy(), desc[: n.value].copy()
+
+
+def orb_extract_batch_mt(frames: np.ndarray, p: OrbParams | None = None, nthreads: int = 1) -> np.ndarray:
+    """CPU-baseline harness: extract every frame of [B,H,W] on `nthreads` threads; returns counts."""
+    p = p or params()
+    frames = np.ascontiguousarray(frames, np.uint8)
+    B, H, W = frames.shape
+    n = np.zeros(B, np.int32)
+    x = C.c_uint32(0)
+    rc = lib().orc_orb_extract_batch_mt(C.byref(p), _p(frames), B, W, H, frames.strides[1],
+                                        C.c_int64(frames.strides[0]), nthreads, _p(n), C.byref(x))
+    if rc != 0:
+        raise RuntimeError("orc_orb_extract_batch_mt failed")
+    return n

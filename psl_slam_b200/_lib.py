@@ -34,7 +34,8 @@ class Config(C.Structure):
 
 # every symbol include/psl_frontend.h declares (checked by tests/test_abi.py)
 EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", "psl_stream", "psl_sync",
-           "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch"]
+           "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch", "psl_profile_enable",
+           "psl_profile_read", "psl_launch_count"]
 
 _lib = None
 
@@ -59,6 +60,10 @@ def lib():
         L.psl_orb_extract.argtypes = [_p, _p, _i, _i, _i, _p, _p, _i, _p]
         L.psl_orb_extract_batch.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _i, _p]
         L.psl_orb_extract_batch_dev.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _i, _p]
+        L.psl_profile_enable.argtypes = [_p, _i]
+        L.psl_profile_read.argtypes = [_p, _p, _p]
+        L.psl_launch_count.argtypes = [_p]
+        L.psl_launch_count.restype = C.c_int64
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

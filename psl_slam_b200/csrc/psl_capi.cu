@@ -39,6 +39,24 @@ int check_status(psl_ctx* ctx) {
   return fail(ctx, PSL_E_INTERNAL, "unknown device status");
 }
 
+size_t prof_mark(psl_ctx* c) {
+  if (!c->prof) return 0;
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+  return c->ev_used++;
+}
+void prof_span(psl_ctx* c, int stage, size_t e0, int nlaunch) {
+  c->launches += nlaunch;
+  c->stage_launches[stage] += nlaunch;
+  if (!c->prof) return;
+  const size_t e1 = prof_mark(c);
+  c->spans.push_back({stage, e0, e1});
+}
+
 static inline int cv_round(float v) { return (int)lrintf(v); }  // cvRound: half-to-even
 
 // One axis of cv::resize(INTER_LINEAR) for CV_8U: tap indices and Q11 weights.
@@ -166,18 +184,28 @@ static int run_chunk(psl_ctx* ctx, ImgBatch in0, int nb, psl_keypoint* d_kps, ui
   const OrbGeometry& g = ctx->geo;
   cudaStream_t st = ctx->stream;
   PSL_CK(cudaMemsetAsync(ctx->d_pool_count, 0, nb * sizeof(uint32_t), st));
+  size_t e = prof_mark(ctx);
   for (int l = 1; l < g.nlevels; ++l) {  // ComputePyramid :1107-1132
     ImgBatch src = l == 1 ? in0
                           : ImgBatch{g.level[l - 1].ptr, g.level[l - 1].pitch, g.level[l - 1].frame_stride,
                                      g.level[l - 1].w, g.level[l - 1].h};
     launch_resize(src, g.level[l], ctx->rtab[l], nb, st);
   }
+  prof_span(ctx, 0, e, g.nlevels - 1);
+  e = prof_mark(ctx);
   launch_fast_cells(ctx->d_geo, g, in0, ctx->cfg.orb_ini_th_fast, ctx->cfg.orb_min_th_fast, ctx->d_pool,
                     ctx->pool_cap, ctx->d_pool_count, ctx->d_cell_tab, ctx->d_status, nb, st);
+  prof_span(ctx, 1, e, 1);
+  e = prof_mark(ctx);
   launch_octree(ctx->d_geo, g, ctx->d_pool, ctx->pool_cap, ctx->d_cell_tab, ctx->d_key_scratch, ctx->d_node_scratch,
                 ctx->d_sel, ctx->d_sel_count, ctx->d_status, nb, st);
+  prof_span(ctx, 2, e, 1);
+  e = prof_mark(ctx);
   launch_gauss7(g, in0, nb, st);
+  prof_span(ctx, 3, e, g.nlevels);
+  e = prof_mark(ctx);
   launch_describe(ctx->d_geo, g, in0, ctx->d_sel, ctx->d_sel_count, d_kps, d_desc, cap, d_n, ctx->d_status, nb, st);
+  prof_span(ctx, 4, e, 1);
   PSL_CK(cudaGetLastError());
   return PSL_OK;
 }
@@ -273,6 +301,7 @@ void psl_destroy(psl_ctx* ctx) {
   cudaFree(ctx->d_kps);
   cudaFree(ctx->d_desc);
   cudaFree(ctx->d_n);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -354,6 +383,29 @@ int psl_orb_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t 
   PSL_CK(cudaMemcpyAsync(desc, ctx->d_desc, (size_t)32 * cap * B, cudaMemcpyDeviceToHost, ctx->stream));
   return check_status(ctx);
 }
+
+int psl_profile_enable(psl_ctx* ctx, int32_t on) {
+  if (!ctx) return PSL_E_INVALID;
+  ctx->prof = on != 0;
+  return PSL_OK;
+}
+
+int psl_profile_read(psl_ctx* ctx, float* ms, int64_t* launches) {
+  if (!ctx || !ms || !launches) return PSL_E_INVALID;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  PSL_CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < PSL_N_STAGES; ++i) { ms[i] = 0.f; launches[i] = ctx->stage_launches[i]; ctx->stage_launches[i] = 0; }
+  for (const auto& sp : ctx->spans) {
+    float t = 0.f;
+    PSL_CK(cudaEventElapsedTime(&t, ctx->ev_pool[sp.e0], ctx->ev_pool[sp.e1]));
+    ms[sp.stage] += t;
+  }
+  ctx->spans.clear();
+  ctx->ev_used = 0;
+  return PSL_OK;
+}
+
+int64_t psl_launch_count(const psl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int psl_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, int32_t level, void* out, int64_t cap_bytes,
                     int64_t* n) {

@@ -33,6 +33,15 @@ struct psl_ctx {
   uint32_t* d_status = nullptr;
   uint32_t* h_status = nullptr;   // pinned mirror
 
+  // per-stage profiling (psl_profile_*)
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int stage; size_t e0, e1; };
+  std::vector<Span> spans;
+  int64_t stage_launches[PSL_N_STAGES] = {0};
+  int64_t launches = 0;
+
   // staging for the host-pointer entry points (grown on demand)
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
   psl_keypoint* d_kps = nullptr; size_t d_kps_bytes = 0;
@@ -45,6 +54,9 @@ int fail(psl_ctx* c, int code, const std::string& msg);
 int cuda_fail(psl_ctx* c, cudaError_t e, const char* what);
 int ensure_bytes(psl_ctx* c, void** p, size_t* have, size_t need);
 int check_status(psl_ctx* c);  // sync + translate the device status word
+// RAII-free stage bracket: begin/end record events when profiling is on and count launches.
+size_t prof_mark(psl_ctx* c);
+void prof_span(psl_ctx* c, int stage, size_t e0, int nlaunch);
 }  // namespace psl
 
 #define PSL_CK(call)                                                     \

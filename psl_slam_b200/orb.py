@@ -41,6 +41,21 @@ class Context:
     def stream(self) -> int:
         return int(_lib.lib().psl_stream(self._h) or 0)
 
+    STAGES = ["pyramid", "fast", "octree", "blur", "describe"]
+
+    def profile(self, on: bool):
+        self.check(_lib.lib().psl_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """(ms per stage, launches per stage) accumulated since the last read."""
+        ms = np.zeros(16, np.float32)
+        ln = np.zeros(16, np.int64)
+        self.check(_lib.lib().psl_profile_read(self._h, _ptr(ms), _ptr(ln)))
+        return ms, ln
+
+    def launch_count(self) -> int:
+        return int(_lib.lib().psl_launch_count(self._h))
+
     def close(self):
         if self._h:
             _lib.lib().psl_destroy(self._h)
