@@ -101,6 +101,83 @@ int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, in
                               int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
                               int32_t* d_n);
 
+/* ------------------------------------------------------------------------------------------------
+ * Matching.  Only plain arrays cross the boundary: the caller (Frame / Tracking) keeps the MapPoint
+ * objects and passes what the matchers read from them.
+ * ------------------------------------------------------------------------------------------------ */
+
+#define PSL_GRID_COLS 64 /* FRAME_GRID_COLS, include/Frame.h:46 */
+#define PSL_GRID_ROWS 48 /* FRAME_GRID_ROWS, include/Frame.h:45 */
+
+/* What the matchers read from the searched Frame (include/Frame.h:150-290): undistorted keypoints
+ * (mvKeysUn), right coordinates (mvuRight; <=0 = none; may be NULL), descriptors (mDescriptors) and the
+ * image bounds that define the 64x48 feature grid (mnMinX.., mfGridElementWidthInv..; Frame.cc:160-166).
+ * The grid itself (Frame::AssignFeaturesToGrid, Frame.cc:269-284) is rebuilt by the library. */
+typedef struct psl_frame_view {
+  int32_t n;
+  const psl_keypoint* kps_un;
+  const float* u_right;
+  const uint8_t* desc; /* n x 32 */
+  float min_x, min_y, max_x, max_y;
+  float grid_w_inv, grid_h_inv;
+} psl_frame_view;
+
+#define PSL_Q_VALID 1u  /* query takes part (MapPoint exists, not outlier, in frustum ...) */
+#define PSL_Q_CLAIMS 2u /* its MapPoint has Observations()>0: a kp assigned to it is skipped by later queries
+                           (ORBmatcher.cc:87-89, 1403-1405) */
+
+/* One projected point to be matched: what SearchByProjection computes per MapPoint before calling
+ * Frame::GetFeaturesInArea (ORBmatcher.cc:62-71 and :1365-1393). */
+typedef struct psl_proj_query {
+  float u, v;        /* projection in the searched frame */
+  float radius;      /* window half-size, already scaled (th*scale[octave], r*scale[level]) */
+  int32_t min_level; /* GetFeaturesInArea(minLevel,maxLevel): -1/-1 = no gating (Frame.cc:1006) */
+  int32_t max_level;
+  float u_right;     /* predicted right coordinate (u - bf/z, mTrackProjXR) */
+  float angle;       /* keypoint angle used by the rotation histogram */
+  uint32_t flags;    /* PSL_Q_* */
+} psl_proj_query;
+
+typedef struct psl_match_params {
+  int32_t mode;              /* 0: best only, rotation histogram (ORBmatcher.cc:1328-1470)
+                                1: best + second with same-level ratio test (ORBmatcher.cc:45-129) */
+  int32_t th_dist;           /* TH_HIGH = 100 (ORBmatcher.cc:37) */
+  float nn_ratio;            /* mfNNratio */
+  int32_t check_orientation; /* mbCheckOrientation */
+} psl_match_params;
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1647-1663) for n pairs a[i], b[i] of 32-byte descriptors. */
+int psl_descriptor_distance(psl_ctx* ctx, const uint8_t* a, const uint8_t* b, int32_t n, int32_t* dist);
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) as used by LSDmatcher::matchNNR / FrameBFMatch
+ * (add_src/LSDmatcher.cpp:354-376, 492-516): idx/dist are nq x 2, sorted by distance, earliest train
+ * index wins ties; missing neighbours (nt < 2) are -1. */
+int psl_hamming_knn2(psl_ctx* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx,
+                     int32_t* dist);
+
+/* ORBmatcher::SearchByProjection, both the Frame<-LastFrame form (ORBmatcher.cc:1328-1470, mode 0) and the
+ * Frame<-local-map-points form (:45-129, mode 1).  claimed_in[n] (may be NULL) marks keypoints whose current
+ * MapPoint has Observations()>0 before the call.  assign[n] = index of the query whose point ends up in
+ * mvpMapPoints[i], or -1; *nmatches = the function's return value. */
+int psl_match_projection(psl_ctx* ctx, const psl_frame_view* frame, const psl_proj_query* queries,
+                         const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in,
+                         const psl_match_params* params, int32_t* assign, int32_t* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (ORBmatcher.cc:159-288).  The two FeatureVectors
+ * (DBoW2 std::map<NodeId, vector<uint>>) are passed as CSR: node ids ascending, offs[n_nodes+1], indices.
+ * kf_valid[i] != 0 iff the keyframe keypoint has a good MapPoint.  match_f[nf] = keyframe keypoint index
+ * matched to frame keypoint i, or -1. */
+typedef struct psl_feature_vector {
+  int32_t n_nodes;
+  const uint32_t* node_id;
+  const int32_t* offs;
+  const uint32_t* idx;
+} psl_feature_vector;
+int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, int32_t nkf,
+                  const psl_feature_vector* kf_fv, const uint8_t* f_desc, const float* f_angle, int32_t nf,
+                  const psl_feature_vector* f_fv, float nn_ratio, int32_t th_low, int32_t check_orientation,
+                  int32_t* match_f, int32_t* nmatches);
+
 /* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).
  * Stages: 0 pyramid resize, 1 FAST cells, 2 octree selection, 3 Gaussian blur, 4 orientation+rBRIEF,
  * 5.. reserved for matching / line stages.  psl_profile_read synchronises, writes the accumulated

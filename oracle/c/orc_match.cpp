@@ -1,0 +1,223 @@
+// TEST INFRASTRUCTURE — CPU oracle for the point matchers (see psl_oracle.h).
+// Sequential restatement of /root/reference/src/ORBmatcher.cc and the Frame helpers it calls
+// (src/Frame.cc:269-284, 985-1050) on plain arrays.  Nothing here is used by the product.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "psl_oracle.h"
+
+namespace {
+
+const int HISTO_LENGTH = 30;  // ORBmatcher.cc:38
+
+// ORBmatcher::DescriptorDistance, ORBmatcher.cc:1647-1663 (SWAR popcount over 8 words)
+int desc_dist(const uint8_t* a, const uint8_t* b) {
+  int dist = 0;
+  for (int i = 0; i < 8; ++i) {
+    uint32_t x, y;
+    std::memcpy(&x, a + 4 * i, 4);
+    std::memcpy(&y, b + 4 * i, 4);
+    uint32_t v = x ^ y;
+    v = v - ((v >> 1) & 0x55555555u);
+    v = (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+    dist += (int)((((v + (v >> 4)) & 0xF0F0F0Fu) * 0x1010101u) >> 24);
+  }
+  return dist;
+}
+
+// Frame::AssignFeaturesToGrid + PosInGrid, Frame.cc:269-284,1040-1050
+struct Grid {
+  std::vector<int> cell[PSL_GRID_COLS][PSL_GRID_ROWS];
+  explicit Grid(const psl_frame_view& f) {
+    for (int i = 0; i < f.n; ++i) {
+      const int px = (int)roundf((f.kps_un[i].x - f.min_x) * f.grid_w_inv);
+      const int py = (int)roundf((f.kps_un[i].y - f.min_y) * f.grid_h_inv);
+      if (px < 0 || px >= PSL_GRID_COLS || py < 0 || py >= PSL_GRID_ROWS) continue;
+      cell[px][py].push_back(i);
+    }
+  }
+};
+
+// Frame::GetFeaturesInArea, Frame.cc:985-1038
+void features_in_area(const psl_frame_view& f, const Grid& g, float x, float y, float r, int minLevel, int maxLevel,
+                      std::vector<int>& out) {
+  out.clear();
+  const int nMinCellX = std::max(0, (int)floorf((x - f.min_x - r) * f.grid_w_inv));
+  if (nMinCellX >= PSL_GRID_COLS) return;
+  const int nMaxCellX = std::min(PSL_GRID_COLS - 1, (int)ceilf((x - f.min_x + r) * f.grid_w_inv));
+  if (nMaxCellX < 0) return;
+  const int nMinCellY = std::max(0, (int)floorf((y - f.min_y - r) * f.grid_h_inv));
+  if (nMinCellY >= PSL_GRID_ROWS) return;
+  const int nMaxCellY = std::min(PSL_GRID_ROWS - 1, (int)ceilf((y - f.min_y + r) * f.grid_h_inv));
+  if (nMaxCellY < 0) return;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+    for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+      for (int i : g.cell[ix][iy]) {
+        const psl_keypoint& kp = f.kps_un[i];
+        if (bCheckLevels) {
+          if (kp.octave < minLevel) continue;
+          if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+        }
+        const float dx = kp.x - x, dy = kp.y - y;
+        if (fabsf(dx) < r && fabsf(dy) < r) out.push_back(i);
+      }
+}
+
+// ORBmatcher::ComputeThreeMaxima, ORBmatcher.cc:1601-1642
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; ++i) {
+    const int s = (int)histo[i].size();
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+    else if (s > max3) { max3 = s; ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+int rot_bin(float a1, float a2) {
+  const float factor = 1.0f / HISTO_LENGTH;  // the reference's quirk: only bins 0..12 are ever hit
+  float rot = a1 - a2;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)roundf(rot * factor);
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+}  // namespace
+
+extern "C" {
+
+void orc_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+  for (int i = 0; i < n; ++i) dist[i] = desc_dist(a + 32 * (size_t)i, b + 32 * (size_t)i);
+}
+
+// cv::BFMatcher(NORM_HAMMING).knnMatch(k=2): ascending distance, earliest index on ties
+void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist) {
+  for (int i = 0; i < nq; ++i) {
+    int b0 = -1, b1 = -1, d0 = 1 << 30, d1 = 1 << 30;
+    for (int j = 0; j < nt; ++j) {
+      const int d = desc_dist(q + 32 * (size_t)i, t + 32 * (size_t)j);
+      if (d < d0) { d1 = d0; b1 = b0; d0 = d; b0 = j; }
+      else if (d < d1) { d1 = d; b1 = j; }
+    }
+    idx[2 * i] = b0; idx[2 * i + 1] = b1;
+    dist[2 * i] = b0 < 0 ? -1 : d0;
+    dist[2 * i + 1] = b1 < 0 ? -1 : d1;
+  }
+}
+
+// Candidate list of one query in the reference's enumeration order (for stage tests)
+int orc_features_in_area(const psl_frame_view* f, float x, float y, float r, int minLevel, int maxLevel, int32_t* out,
+                         int cap) {
+  Grid g(*f);
+  std::vector<int> v;
+  features_in_area(*f, g, x, y, r, minLevel, maxLevel, v);
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+
+// ORBmatcher::SearchByProjection — mode 0: (Frame&, const Frame& LastFrame, th, bMono) ORBmatcher.cc:1328-1470
+//                                  mode 1: (Frame&, vector<MapPoint*>&, th)            ORBmatcher.cc:45-129
+int orc_match_projection(const psl_frame_view* f, const psl_proj_query* qs, const uint8_t* qdesc, int nq,
+                         const uint8_t* claimed_in, const psl_match_params* p, int32_t* assign, int32_t* nmatches) {
+  Grid g(*f);
+  std::vector<uint8_t> claimed(f->n, 0);
+  if (claimed_in) std::memcpy(claimed.data(), claimed_in, f->n);
+  for (int i = 0; i < f->n; ++i) assign[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> cand;
+  int nm = 0;
+  for (int q = 0; q < nq; ++q) {
+    const psl_proj_query& Q = qs[q];
+    if (!(Q.flags & PSL_Q_VALID)) continue;
+    features_in_area(*f, g, Q.u, Q.v, Q.radius, Q.min_level, Q.max_level, cand);
+    if (cand.empty()) continue;
+    const uint8_t* dq = qdesc + 32 * (size_t)q;
+    int bestDist = 256, bestIdx = -1, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1;
+    for (int i2 : cand) {
+      if (claimed[i2]) continue;  // mvpMapPoints[i2] && Observations()>0
+      if (f->u_right && f->u_right[i2] > 0) {
+        const float er = fabsf(Q.u_right - f->u_right[i2]);
+        if (er > Q.radius) continue;
+      }
+      const int dist = desc_dist(dq, f->desc + 32 * (size_t)i2);
+      if (dist < bestDist) {
+        bestDist2 = bestDist; bestLevel2 = bestLevel;
+        bestDist = dist; bestLevel = f->kps_un[i2].octave; bestIdx = i2;
+      } else if (p->mode == 1 && dist < bestDist2) {
+        bestLevel2 = f->kps_un[i2].octave; bestDist2 = dist;
+      }
+    }
+    if (bestDist <= p->th_dist) {
+      if (p->mode == 1 && bestLevel == bestLevel2 && bestDist > p->nn_ratio * bestDist2) continue;
+      assign[bestIdx] = q;
+      claimed[bestIdx] = (Q.flags & PSL_Q_CLAIMS) ? 1 : 0;
+      ++nm;
+      if (p->mode == 0 && p->check_orientation) rotHist[rot_bin(Q.angle, f->kps_un[bestIdx].angle)].push_back(bestIdx);
+    }
+  }
+  if (p->mode == 0 && p->check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int idx : rotHist[i]) { assign[idx] = -1; --nm; }
+  }
+  *nmatches = nm;
+  return 0;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), ORBmatcher.cc:159-288
+int orc_match_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, int nkf,
+                  const psl_feature_vector* kfv, const uint8_t* f_desc, const float* f_angle, int nf,
+                  const psl_feature_vector* ffv, float nn_ratio, int th_low, int check_orientation, int32_t* match_f,
+                  int32_t* nmatches) {
+  (void)nkf;
+  for (int i = 0; i < nf; ++i) match_f[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nm = 0, a = 0, b = 0;
+  while (a < kfv->n_nodes && b < ffv->n_nodes) {
+    if (kfv->node_id[a] == ffv->node_id[b]) {
+      for (int ik = kfv->offs[a]; ik < kfv->offs[a + 1]; ++ik) {
+        const int realIdxKF = (int)kfv->idx[ik];
+        if (!kf_valid[realIdxKF]) continue;
+        const uint8_t* dKF = kf_desc + 32 * (size_t)realIdxKF;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int jf = ffv->offs[b]; jf < ffv->offs[b + 1]; ++jf) {
+          const int realIdxF = (int)ffv->idx[jf];
+          if (match_f[realIdxF] >= 0) continue;
+          const int dist = desc_dist(dKF, f_desc + 32 * (size_t)realIdxF);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= th_low && (float)bestDist1 < nn_ratio * (float)bestDist2) {
+          match_f[bestIdxF] = realIdxKF;
+          if (check_orientation) rotHist[rot_bin(kf_angle[realIdxKF], f_angle[bestIdxF])].push_back(bestIdxF);
+          ++nm;
+        }
+      }
+      ++a; ++b;
+    } else if (kfv->node_id[a] < ffv->node_id[b]) {
+      while (a < kfv->n_nodes && kfv->node_id[a] < ffv->node_id[b]) ++a;  // lower_bound
+    } else {
+      while (b < ffv->n_nodes && ffv->node_id[b] < kfv->node_id[a]) ++b;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { match_f[idx] = -1; --nm; }
+    }
+  }
+  *nmatches = nm;
+  return 0;
+}
+
+}  // extern "C"

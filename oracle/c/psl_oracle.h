@@ -47,6 +47,18 @@ void orc_brief(const uint8_t* blur, int stride, float x, float y, float angle_de
 int orc_orb_extract(const orc_orb_params* p, const uint8_t* gray, int w, int h, int stride, psl_keypoint* kps,
                     uint8_t* desc, int cap, int* n);
 
+/* ---- matchers (orc_match.cpp): ORBmatcher.cc + Frame.cc grid helpers ---- */
+void orc_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+void orc_hamming_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist);
+int orc_features_in_area(const psl_frame_view* f, float x, float y, float r, int minLevel, int maxLevel, int32_t* out,
+                         int cap);
+int orc_match_projection(const psl_frame_view* f, const psl_proj_query* qs, const uint8_t* qdesc, int nq,
+                         const uint8_t* claimed_in, const psl_match_params* p, int32_t* assign, int32_t* nmatches);
+int orc_match_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, int nkf,
+                  const psl_feature_vector* kfv, const uint8_t* f_desc, const float* f_angle, int nf,
+                  const psl_feature_vector* ffv, float nn_ratio, int th_low, int check_orientation, int32_t* match_f,
+                  int32_t* nmatches);
+
 /* CPU-baseline harness: B frames, one frame per task on `nthreads` std::threads. */
 int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
                              int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor);

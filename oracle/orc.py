@@ -133,3 +133,60 @@ def orb_extract_batch_mt(frames: np.ndarray, p: OrbParams | None = None, nthread
     if rc != 0:
         raise RuntimeError("orc_orb_extract_batch_mt failed")
     return n
+
+
+# ---- matchers (oracle/c/orc_match.cpp) --------------------------------------------------------
+from psl_slam_b200._lib import (MatchParams, QUERY_DTYPE, make_feature_vector,  # noqa: E402  (ABI structs only)
+                                make_frame_view)
+
+
+def descriptor_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    out = np.empty(len(a), np.int32)
+    lib().orc_descriptor_distance(_p(a), _p(b), len(a), _p(out))
+    return out
+
+
+def hamming_knn2(q: np.ndarray, t: np.ndarray):
+    q, t = np.ascontiguousarray(q, np.uint8), np.ascontiguousarray(t, np.uint8)
+    idx = np.empty((len(q), 2), np.int32)
+    dist = np.empty((len(q), 2), np.int32)
+    lib().orc_hamming_knn2(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
+    return idx, dist
+
+
+def features_in_area(kps_un, desc, bounds, x, y, r, min_level=-1, max_level=-1):
+    fv, keep = make_frame_view(kps_un, None, desc, bounds)
+    out = np.empty(len(desc) + 1, np.int32)
+    n = lib().orc_features_in_area(C.byref(fv), C.c_float(x), C.c_float(y), C.c_float(r), min_level, max_level,
+                                   _p(out), len(out))
+    return out[:n].copy()
+
+
+def match_projection(kps_un, u_right, desc, bounds, queries, qdesc, claimed_in, mode, th_dist=100, nn_ratio=0.6,
+                     check_orientation=True):
+    fv, keep = make_frame_view(kps_un, u_right, desc, bounds)
+    queries = np.ascontiguousarray(queries, QUERY_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    cl = None if claimed_in is None else np.ascontiguousarray(claimed_in, np.uint8)
+    prm = MatchParams(mode, th_dist, nn_ratio, int(check_orientation))
+    assign = np.empty(len(desc), np.int32)
+    nm = C.c_int32()
+    lib().orc_match_projection(C.byref(fv), _p(queries), _p(qdesc), len(queries), None if cl is None else _p(cl),
+                               C.byref(prm), _p(assign), C.byref(nm))
+    return assign, nm.value
+
+
+def match_bow(kf_desc, kf_angle, kf_valid, kf_csr, f_desc, f_angle, f_csr, nn_ratio=0.7, th_low=50,
+              check_orientation=True):
+    kf_desc, f_desc = np.ascontiguousarray(kf_desc, np.uint8), np.ascontiguousarray(f_desc, np.uint8)
+    kf_angle, f_angle = np.ascontiguousarray(kf_angle, np.float32), np.ascontiguousarray(f_angle, np.float32)
+    kf_valid = np.ascontiguousarray(kf_valid, np.uint8)
+    kfv, k1 = make_feature_vector(*kf_csr)
+    ffv, k2 = make_feature_vector(*f_csr)
+    match = np.empty(len(f_desc), np.int32)
+    nm = C.c_int32()
+    lib().orc_match_bow(_p(kf_desc), _p(kf_angle), _p(kf_valid), len(kf_desc), C.byref(kfv), _p(f_desc), _p(f_angle),
+                        len(f_desc), C.byref(ffv), C.c_float(nn_ratio), th_low, int(check_orientation), _p(match),
+                        C.byref(nm))
+    return match, nm.value

@@ -60,8 +60,75 @@ def make_orb():
         print(name, img.shape, "n =", len(kps), "per-level", np.bincount(octv, minlength=P.nlevels).tolist())
 
 
+def make_match():
+    """cfg-2 shaped fixtures: consecutive RGB-D frames, projection queries, BoW groups, knn2."""
+    from oracle import orc
+    from oracle.pyref import frame_py, match_py
+    K = synth.ICL
+    gray, depth, T = synth.sequence(2, 3)
+    P = orb_cv2.OrbParams()
+    ext = [orc.orb_extract(g) for g in gray]  # bit-identical to orb_cv2 (tests/test_oracle_orb.py)
+    bounds = (np.float32(0), np.float32(0), np.float32(640), np.float32(480))  # zero distortion: Frame.cc:155-158
+    scale = np.array(P.scale, np.float32)
+    views, world = [], []
+    for i in range(3):
+        kps, desc = ext[i]
+        xy = np.stack([kps["x"], kps["y"]], 1)
+        ur, dep = frame_py.stereo_from_rgbd(xy, frame_py.depth_to_float(depth[i]), K["bf"])
+        Twc = np.linalg.inv(T[i])
+        world.append(frame_py.unproject(xy, dep, K, Twc))
+        views.append((kps, desc, ur))
+    rng = np.random.default_rng(22)
+    for pair, (a, b) in enumerate([(0, 1), (1, 2)]):
+        kl, dl, _ = views[a]
+        kc, dc, urc = views[b]
+        n = len(kl)
+        outlier = rng.random(n) < 0.05
+        has_mp = rng.random(n) < 0.9
+        claims = rng.random(n) < 0.8  # temporal points (Observations()==0) do not claim
+        # pose prior = true pose perturbed a little (the motion model is never exact)
+        Tcur = T[b].copy()
+        Tcur[:3, 3] += rng.normal(0, 0.002, 3)
+        q = frame_py.projection_queries(world[a], kl["octave"], kl["angle"], has_mp & ~outlier, claims, Tcur, T[a], K,
+                                        scale, 15.0 if pair == 0 else 30.0, bounds)
+        kun = np.stack([kc["x"], kc["y"], kc["size"], kc["angle"], kc["response"]], 1).astype(np.float32)
+        fv = match_py.FrameView(kun, kc["octave"], urc, dc, *bounds)
+        assign, nm = match_py.search_by_projection(fv, q, dl, None, 0, 100, 0.9, True)
+        # mode 1: same queries read as local-map points (levels pred-1..pred), some keypoints pre-claimed
+        q1 = q.copy()
+        q1["min_level"] = kl["octave"] - 1
+        q1["max_level"] = kl["octave"]
+        pre = rng.random(len(dc)) < 0.3
+        assign1, nm1 = match_py.search_by_projection(fv, q1, dl, pre, 1, 100, 0.8, False)
+        # BoW: fake vocabulary = 6 descriptor bits -> 64 nodes, a few nodes missing on either side
+        def fvec(desc, drop):
+            node = (desc[:, 0] & 0x3F).astype(np.uint32)
+            d = {}
+            for i, nd in enumerate(node):
+                if nd % 7 != drop:
+                    d.setdefault(int(nd), []).append(i)
+            return d
+        kf_fv, f_fv = fvec(dl, 3), fvec(dc, 5)
+        match, nmb = match_py.search_by_bow(dl, kl["angle"], has_mp, kf_fv, dc, kc["angle"], f_fv, 0.7, 50, True)
+        idx2, dist2 = match_py.knn2_cv2(dl[:200], dc[:200])
+        def csr(d):
+            ids = sorted(d)
+            offs = np.cumsum([0] + [len(d[k]) for k in ids]).astype(np.int32)
+            return np.array(ids, np.uint32), offs, np.array([i for k in ids for i in d[k]], np.uint32)
+        kcsr, fcsr = csr(kf_fv), csr(f_fv)
+        np.savez_compressed(os.path.join(OUT, f"match_pair{pair}.npz"), kps_cur=kc, desc_cur=dc, u_right_cur=urc,
+                            desc_last=dl, angle_last=kl["angle"], bounds=np.array(bounds, np.float32), queries=q,
+                            assign0=assign, nmatches0=np.int32(nm), queries1=q1, claimed1=pre.astype(np.uint8),
+                            assign1=assign1, nmatches1=np.int32(nm1), kf_valid=has_mp.astype(np.uint8),
+                            kf_nodes=kcsr[0], kf_offs=kcsr[1], kf_idx=kcsr[2], f_nodes=fcsr[0], f_offs=fcsr[1],
+                            f_idx=fcsr[2], bow_match=match, bow_nmatches=np.int32(nmb), knn_idx=idx2, knn_dist=dist2)
+        print(f"match_pair{pair}: queries {int((q['flags'] & 1).sum())} proj-matches {nm} / mode1 {nm1} / bow {nmb}")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(OUT, exist_ok=True)
     if what in ("orb", "all"):
         make_orb()
+    if what in ("match", "all"):
+        make_match()

@@ -1,0 +1,191 @@
+"""TEST INFRASTRUCTURE — golden-vector generator for the point matchers.
+
+Independent Python restatement (written from the reference source, not from oracle/c) of
+ORBmatcher::SearchByProjection (src/ORBmatcher.cc:45-129 and :1328-1470), SearchByBoW (:159-288),
+ComputeThreeMaxima (:1601-1642), DescriptorDistance (:1647-1663) and Frame::AssignFeaturesToGrid /
+GetFeaturesInArea / PosInGrid (src/Frame.cc:269-284, 985-1050).  cv2.BFMatcher supplies the real
+knnMatch used by LSDmatcher::matchNNR (add_src/LSDmatcher.cpp:354-376).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+F32 = np.float32
+COLS, ROWS = 64, 48
+HISTO = 30
+
+
+def c_round(x) -> int:
+    """C round(): half away from zero."""
+    x = float(x)
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def popcount_dist(a: np.ndarray, b: np.ndarray) -> int:
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+class FrameView:
+    def __init__(self, kps_un, octave, u_right, desc, min_x, min_y, max_x, max_y):
+        self.x = kps_un[:, 0].astype(F32)
+        self.y = kps_un[:, 1].astype(F32)
+        self.angle = kps_un[:, 3].astype(F32)
+        self.octave = octave.astype(np.int32)
+        self.u_right = None if u_right is None else u_right.astype(F32)
+        self.desc = desc
+        self.n = len(desc)
+        self.min_x, self.min_y, self.max_x, self.max_y = F32(min_x), F32(min_y), F32(max_x), F32(max_y)
+        self.w_inv = F32(COLS) / F32(self.max_x - self.min_x)  # Frame.cc:163-164
+        self.h_inv = F32(ROWS) / F32(self.max_y - self.min_y)
+        self.grid = [[[] for _ in range(ROWS)] for _ in range(COLS)]
+        for i in range(self.n):  # AssignFeaturesToGrid
+            px = c_round(F32(self.x[i] - self.min_x) * self.w_inv)
+            py = c_round(F32(self.y[i] - self.min_y) * self.h_inv)
+            if 0 <= px < COLS and 0 <= py < ROWS:
+                self.grid[px][py].append(i)
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        x, y, r = F32(x), F32(y), F32(r)
+        out = []
+        c0 = max(0, int(math.floor(F32(F32(x - self.min_x) - r) * self.w_inv)))
+        if c0 >= COLS:
+            return out
+        c1 = min(COLS - 1, int(math.ceil(F32(F32(x - self.min_x) + r) * self.w_inv)))
+        if c1 < 0:
+            return out
+        r0 = max(0, int(math.floor(F32(F32(y - self.min_y) - r) * self.h_inv)))
+        if r0 >= ROWS:
+            return out
+        r1 = min(ROWS - 1, int(math.ceil(F32(F32(y - self.min_y) + r) * self.h_inv)))
+        if r1 < 0:
+            return out
+        check = (min_level > 0) or (max_level >= 0)
+        for ix in range(c0, c1 + 1):
+            for iy in range(r0, r1 + 1):
+                for i in self.grid[ix][iy]:
+                    if check:
+                        if self.octave[i] < min_level:
+                            continue
+                        if max_level >= 0 and self.octave[i] > max_level:
+                            continue
+                    if abs(F32(self.x[i] - x)) < r and abs(F32(self.y[i] - y)) < r:
+                        out.append(i)
+        return out
+
+
+def three_maxima(sizes):
+    m1 = m2 = m3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > m1:
+            m3, m2, m1 = m2, m1, s
+            i3, i2, i1 = i2, i1, i
+        elif s > m2:
+            m3, m2 = m2, s
+            i3, i2 = i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    if m2 < F32(0.1) * F32(m1):
+        i2 = i3 = -1
+    elif m3 < F32(0.1) * F32(m1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def rot_bin(a1, a2):
+    factor = F32(1.0) / F32(HISTO)
+    rot = F32(F32(a1) - F32(a2))
+    if rot < 0.0:
+        rot = F32(rot + F32(360.0))
+    b = c_round(F32(rot * factor))
+    return 0 if b == HISTO else b
+
+
+def search_by_projection(fv: FrameView, queries, qdesc, claimed_in, mode, th_dist=100, nn_ratio=0.6, check_ori=True):
+    """queries: structured array (u,v,radius,min_level,max_level,u_right,angle,flags)."""
+    assign = np.full(fv.n, -1, np.int32)
+    claimed = np.zeros(fv.n, bool) if claimed_in is None else claimed_in.astype(bool).copy()
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for qi, q in enumerate(queries):
+        if not (q["flags"] & 1):
+            continue
+        cand = fv.features_in_area(q["u"], q["v"], q["radius"], int(q["min_level"]), int(q["max_level"]))
+        if not cand:
+            continue
+        best, best_i, best_l, best2, best2_l = 256, -1, -1, 256, -1
+        for i2 in cand:
+            if claimed[i2]:
+                continue
+            if fv.u_right is not None and fv.u_right[i2] > 0:
+                if abs(F32(F32(q["u_right"]) - fv.u_right[i2])) > F32(q["radius"]):
+                    continue
+            d = popcount_dist(qdesc[qi], fv.desc[i2])
+            if d < best:
+                best2, best2_l = best, best_l
+                best, best_l, best_i = d, int(fv.octave[i2]), i2
+            elif mode == 1 and d < best2:
+                best2, best2_l = d, int(fv.octave[i2])
+        if best <= th_dist:
+            if mode == 1 and best_l == best2_l and F32(best) > F32(nn_ratio) * F32(best2):
+                continue
+            assign[best_i] = qi
+            claimed[best_i] = bool(q["flags"] & 2)
+            nm += 1
+            if mode == 0 and check_ori:
+                hist[rot_bin(q["angle"], fv.angle[best_i])].append(best_i)
+    if mode == 0 and check_ori:
+        keep = three_maxima([len(h) for h in hist])
+        for b in range(HISTO):
+            if b not in keep:
+                for i in hist[b]:
+                    assign[i] = -1
+                    nm -= 1
+    return assign, nm
+
+
+def search_by_bow(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv, nn_ratio=0.7, th_low=50, check_ori=True):
+    """kf_fv / f_fv: dict node_id -> list of indices (DBoW2::FeatureVector)."""
+    nf = len(f_desc)
+    match = np.full(nf, -1, np.int32)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for node in sorted(set(kf_fv) & set(f_fv)):
+        for ikf in kf_fv[node]:
+            if not kf_valid[ikf]:
+                continue
+            b1, bi, b2 = 256, -1, 256
+            for jf in f_fv[node]:
+                if match[jf] >= 0:
+                    continue
+                d = popcount_dist(kf_desc[ikf], f_desc[jf])
+                if d < b1:
+                    b2, b1, bi = b1, d, jf
+                elif d < b2:
+                    b2 = d
+            if b1 <= th_low and F32(b1) < F32(nn_ratio) * F32(b2):
+                match[bi] = ikf
+                if check_ori:
+                    hist[rot_bin(kf_angle[ikf], f_angle[bi])].append(bi)
+                nm += 1
+    if check_ori:
+        keep = three_maxima([len(h) for h in hist])
+        for b in range(HISTO):
+            if b not in keep:
+                for i in hist[b]:
+                    match[i] = -1
+                    nm -= 1
+    return match, nm
+
+
+def knn2_cv2(q, t):
+    import cv2
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(q, t, 2)
+    idx = np.full((len(q), 2), -1, np.int32)
+    dist = np.full((len(q), 2), -1, np.int32)
+    for i, row in enumerate(m):
+        for k, e in enumerate(row):
+            idx[i, k], dist[i, k] = e.trainIdx, int(e.distance)
+    return idx, dist

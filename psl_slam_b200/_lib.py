@@ -32,10 +32,50 @@ class Config(C.Structure):
                 ("line_scale_factor", C.c_float), ("line_nlevels", C.c_int32), ("line_min_length", C.c_float)]
 
 
+QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
+                        ("u_right", "<f4"), ("angle", "<f4"), ("flags", "<u4")])  # psl_proj_query
+Q_VALID, Q_CLAIMS = 1, 2
+
+
+class FrameView(C.Structure):  # psl_frame_view
+    _fields_ = [("n", C.c_int32), ("kps_un", C.c_void_p), ("u_right", C.c_void_p), ("desc", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float)]
+
+
+class MatchParams(C.Structure):  # psl_match_params
+    _fields_ = [("mode", C.c_int32), ("th_dist", C.c_int32), ("nn_ratio", C.c_float),
+                ("check_orientation", C.c_int32)]
+
+
+class FeatureVector(C.Structure):  # psl_feature_vector
+    _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("offs", C.c_void_p), ("idx", C.c_void_p)]
+
+
+def make_frame_view(kps_un: np.ndarray, u_right, desc: np.ndarray, bounds):
+    """Build a psl_frame_view over numpy arrays (kept alive by the returned tuple)."""
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    min_x, min_y, max_x, max_y = (np.float32(b) for b in bounds)
+    fv = FrameView(len(kps_un), kps_un.ctypes.data, None if ur is None else ur.ctypes.data, desc.ctypes.data,
+                   min_x, min_y, max_x, max_y, np.float32(64) / np.float32(max_x - min_x),
+                   np.float32(48) / np.float32(max_y - min_y))  # Frame.cc:163-164
+    return fv, (kps_un, ur, desc)
+
+
+def make_feature_vector(node_id, offs, idx):
+    node_id = np.ascontiguousarray(node_id, np.uint32)
+    offs = np.ascontiguousarray(offs, np.int32)
+    idx = np.ascontiguousarray(idx, np.uint32)
+    return FeatureVector(len(node_id), node_id.ctypes.data, offs.ctypes.data, idx.ctypes.data), (node_id, offs, idx)
+
+
 # every symbol include/psl_frontend.h declares (checked by tests/test_abi.py)
 EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", "psl_stream", "psl_sync",
            "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch", "psl_profile_enable",
-           "psl_profile_read", "psl_launch_count"]
+           "psl_profile_read", "psl_launch_count", "psl_descriptor_distance", "psl_hamming_knn2",
+           "psl_match_projection", "psl_match_bow"]
 
 _lib = None
 
@@ -64,6 +104,10 @@ def lib():
         L.psl_profile_read.argtypes = [_p, _p, _p]
         L.psl_launch_count.argtypes = [_p]
         L.psl_launch_count.restype = C.c_int64
+        L.psl_descriptor_distance.argtypes = [_p, _p, _p, _i, _p]
+        L.psl_hamming_knn2.argtypes = [_p, _p, _i, _p, _i, _p, _p]
+        L.psl_match_projection.argtypes = [_p, _p, _p, _p, _i, _p, _p, _p, _p]
+        L.psl_match_bow.argtypes = [_p, _p, _p, _p, _i, _p, _p, _p, _i, _p, C.c_float, _i, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

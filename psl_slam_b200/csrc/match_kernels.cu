@@ -1,0 +1,439 @@
+// K7/K8/K9: Hamming matchers of ORBmatcher / LSDmatcher on CUDA cores (__popc; nothing here is a
+// dense contraction).  The reference matchers are greedy and sequential: a keypoint already given to
+// an earlier query is skipped by later ones (ORBmatcher.cc:87-89, 209-210, 1403-1405), and distance
+// ties go to the first candidate in Frame::GetFeaturesInArea's enumeration order.  The work is split
+// into an embarrassingly parallel stage (ordered candidate lists with distances, one warp per query)
+// and an ordered resolve stage (one warp per frame walks the queries in order; the 32 lanes scan a
+// query's candidates together and pick the lexicographic minimum of (distance, position)).
+#include "match_kernels.cuh"
+
+namespace psl {
+
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__device__ __forceinline__ unsigned warp_min_u32(unsigned v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// rotation-histogram bin, ORBmatcher.cc:1431-1438 (factor = 1.0f/HISTO_LENGTH quirk kept)
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+  float rot = __fsub_rn(a1, a2);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, 1.0f / 30));
+  return bin == 30 ? 0 : bin;
+}
+
+// ComputeThreeMaxima, ORBmatcher.cc:1601-1642
+__device__ void three_maxima(const int* h, int& i1, int& i2, int& i3) {
+  int m1 = 0, m2 = 0, m3 = 0;
+  i1 = i2 = i3 = -1;
+  for (int i = 0; i < 30; ++i) {
+    const int s = h[i];
+    if (s > m1) { m3 = m2; m2 = m1; m1 = s; i3 = i2; i2 = i1; i1 = i; }
+    else if (s > m2) { m3 = m2; m2 = s; i3 = i2; i2 = i; }
+    else if (s > m3) { m3 = s; i3 = i; }
+  }
+  if ((float)m2 < __fmul_rn(0.1f, (float)m1)) { i2 = -1; i3 = -1; }
+  else if ((float)m3 < __fmul_rn(0.1f, (float)m1)) { i3 = -1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame::AssignFeaturesToGrid / PosInGrid (Frame.cc:269-284, 1040-1050): CSR over 64x48 cells,
+// items inside a cell in ascending keypoint index (= push_back order).  One CTA per frame.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGridThreads = 256;
+
+__global__ void __launch_bounds__(kGridThreads)
+    grid_build_kernel(MatchFrames f, int32_t* __restrict__ cell_start, uint16_t* __restrict__ cell_items) {
+  __shared__ int s_cnt[kGridCells];
+  __shared__ int s_warp[kGridThreads / 32];
+  __shared__ int s_carry;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = f.n[b];
+  const psl_keypoint* kps = f.kps + (size_t)b * f.cap;
+  int32_t* start = cell_start + (size_t)b * (kGridCells + 1);
+  uint16_t* items = cell_items + (size_t)b * f.cap;
+  for (int c = tid; c < kGridCells; c += kGridThreads) s_cnt[c] = 0;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  auto cell_of = [&](int i) {
+    const int px = (int)roundf(__fmul_rn(__fsub_rn(kps[i].x, f.min_x), f.grid_w_inv));
+    const int py = (int)roundf(__fmul_rn(__fsub_rn(kps[i].y, f.min_y), f.grid_h_inv));
+    if (px < 0 || px >= PSL_GRID_COLS || py < 0 || py >= PSL_GRID_ROWS) return -1;
+    return px * PSL_GRID_ROWS + py;
+  };
+  for (int i = tid; i < n; i += kGridThreads) {
+    const int c = cell_of(i);
+    if (c >= 0) atomicAdd(&s_cnt[c], 1);
+  }
+  __syncthreads();
+  // exclusive scan of the 3072 counts, 256 at a time
+  for (int base = 0; base < kGridCells; base += kGridThreads) {
+    const int v = s_cnt[base + tid];
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if ((tid & 31) >= d) inc += o;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kGridThreads / 32; ++w) {
+      if (w < (tid >> 5)) wbase += s_warp[w];
+      tot += s_warp[w];
+    }
+    const int excl = s_carry + wbase + inc - v;
+    start[base + tid] = excl;
+    s_cnt[base + tid] = excl;  // becomes the fill cursor
+    __syncthreads();
+    if (tid == 0) s_carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0) start[kGridCells] = s_carry;
+  for (int i = tid; i < n; i += kGridThreads) {
+    const int c = cell_of(i);
+    if (c >= 0) items[atomicAdd(&s_cnt[c], 1)] = (uint16_t)i;
+  }
+  __syncthreads();
+  // restore push_back order inside every cell (cells hold a handful of items)
+  for (int c = tid; c < kGridCells; c += kGridThreads) {
+    const int s = start[c], e = s_cnt[c];
+    for (int i = s + 1; i < e; ++i) {
+      const uint16_t v = items[i];
+      int j = i - 1;
+      while (j >= s && items[j] > v) { items[j + 1] = items[j]; --j; }
+      items[j + 1] = v;
+    }
+  }
+}
+
+void launch_grid_build(const MatchFrames& f, int32_t* cell_start, uint16_t* cell_items, int B, cudaStream_t st) {
+  grid_build_kernel<<<B, kGridThreads, 0, st>>>(f, cell_start, cell_items);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate lists: Frame::GetFeaturesInArea (Frame.cc:985-1038) + the static gates of
+// SearchByProjection (right-coordinate test, ORBmatcher.cc:91-96 / 1407-1413) + Hamming distance.
+// One warp per query; 32 grid cells are examined per step in the reference's (ix outer, iy inner)
+// order, and a warp prefix sum keeps the output in enumeration order.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCandWarps = 8;
+
+__global__ void __launch_bounds__(kCandWarps * 32)
+    proj_candidates_kernel(MatchFrames f, MatchQueries qs, const int32_t* __restrict__ cell_start,
+                           const uint16_t* __restrict__ cell_items, uint32_t* __restrict__ cand,
+                           int32_t* __restrict__ cand_count, uint32_t* __restrict__ status) {
+  const int lane = threadIdx.x & 31, b = blockIdx.y;
+  const int qi = blockIdx.x * kCandWarps + (threadIdx.x >> 5);
+  if (qi >= qs.nq[b]) return;
+  const psl_proj_query Q = qs.q[(size_t)b * qs.cap + qi];
+  int32_t* out_count = cand_count + (size_t)b * qs.cap + qi;
+  if (!(Q.flags & PSL_Q_VALID)) {
+    if (lane == 0) *out_count = 0;
+    return;
+  }
+  const float x = Q.u, y = Q.v, r = Q.radius;
+  const float dxm = __fsub_rn(x, f.min_x), dym = __fsub_rn(y, f.min_y);
+  const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dxm, r), f.grid_w_inv)));
+  const int c1 = min(PSL_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(dxm, r), f.grid_w_inv)));
+  const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dym, r), f.grid_h_inv)));
+  const int r1 = min(PSL_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.grid_h_inv)));
+  if (c0 >= PSL_GRID_COLS || c1 < 0 || r0 >= PSL_GRID_ROWS || r1 < 0) {
+    if (lane == 0) *out_count = 0;
+    return;
+  }
+  const bool check_levels = (Q.min_level > 0) || (Q.max_level >= 0);
+  const psl_keypoint* kps = f.kps + (size_t)b * f.cap;
+  const float* ur = f.u_right ? f.u_right + (size_t)b * f.cap : nullptr;
+  const uint4* fdesc = reinterpret_cast<const uint4*>(f.desc + (size_t)b * f.cap * 32);
+  const uint4* qd = reinterpret_cast<const uint4*>(qs.desc + ((size_t)b * qs.cap + qi) * 32);
+  const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+  const int32_t* start = cell_start + (size_t)b * (kGridCells + 1);
+  const uint16_t* items = cell_items + (size_t)b * f.cap;
+  uint32_t* out = cand + ((size_t)b * qs.cap + qi) * kCandCap;
+
+  auto passes = [&](int i) {
+    const psl_keypoint kp = kps[i];
+    if (check_levels) {
+      if (kp.octave < Q.min_level) return false;
+      if (Q.max_level >= 0 && kp.octave > Q.max_level) return false;
+    }
+    if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) return false;
+    if (ur) {
+      const float u2 = ur[i];
+      if (u2 > 0.f && fabsf(__fsub_rn(Q.u_right, u2)) > r) return false;
+    }
+    return true;
+  };
+
+  const int ncy = r1 - r0 + 1, ncells = (c1 - c0 + 1) * ncy;
+  int total = 0;
+  for (int base = 0; base < ncells; base += 32) {
+    const int c = base + lane;
+    int s = 0, e = 0;
+    if (c < ncells) {
+      const int ix = c0 + c / ncy, iy = r0 + c % ncy;
+      s = start[ix * PSL_GRID_ROWS + iy];
+      e = start[ix * PSL_GRID_ROWS + iy + 1];
+    }
+    int cnt = 0;
+    for (int k = s; k < e; ++k) cnt += passes(items[k]) ? 1 : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    int pos = total + inc - cnt;
+    for (int k = s; k < e && cnt; ++k) {
+      const int i = items[k];
+      if (!passes(i)) continue;
+      if (pos < kCandCap) {
+        const uint4 d0 = __ldg(fdesc + 2 * i), d1 = __ldg(fdesc + 2 * i + 1);
+        out[pos] = ((uint32_t)i << 16) | (uint32_t)hamming256(q0, q1, d0, d1);
+      }
+      ++pos;
+    }
+    total += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) {
+    *out_count = min(total, kCandCap);
+    if (total > kCandCap) atomicOr(status, kStatCandOverflow);
+  }
+}
+
+void launch_proj_candidates(const MatchFrames& f, const MatchQueries& q, const int32_t* cell_start,
+                            const uint16_t* cell_items, uint32_t* cand, int32_t* cand_count, uint32_t* status, int B,
+                            cudaStream_t st) {
+  dim3 grid((q.cap + kCandWarps - 1) / kCandWarps, B);
+  proj_candidates_kernel<<<grid, kCandWarps * 32, 0, st>>>(f, q, cell_start, cell_items, cand, cand_count, status);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered resolve: the loops of SearchByProjection (ORBmatcher.cc:64-124 / 1353-1444) with the
+// dynamic "already claimed" test, then the rotation-consistency filter (:1447-1467).
+// One warp per frame; dynamic shared memory: claimed[cap] bytes.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+    proj_resolve_kernel(MatchFrames f, MatchQueries qs, const uint32_t* __restrict__ cand,
+                        const int32_t* __restrict__ cand_count, const uint8_t* __restrict__ claimed_in,
+                        psl_match_params prm, uint32_t* __restrict__ accepted_scratch, int32_t* __restrict__ assign_out,
+                        int32_t* __restrict__ nmatches) {
+  extern __shared__ uint8_t s_claimed[];
+  __shared__ int s_hist[32];
+  const int lane = threadIdx.x, b = blockIdx.x;
+  const int n = f.n[b], nq = qs.nq[b];
+  int32_t* assign = assign_out + (size_t)b * f.cap;
+  const psl_keypoint* kps = f.kps + (size_t)b * f.cap;
+  uint32_t* accepted = accepted_scratch + (size_t)b * qs.cap;
+  for (int i = lane; i < n; i += 32) {
+    s_claimed[i] = claimed_in ? claimed_in[(size_t)b * f.cap + i] : 0;
+    assign[i] = -1;
+  }
+  s_hist[lane] = 0;
+  __syncwarp();
+  int nm = 0, nacc = 0;
+  const bool hist_on = prm.mode == 0 && prm.check_orientation;
+  for (int q = 0; q < nq; ++q) {
+    const int cnt = cand_count[(size_t)b * qs.cap + q];
+    if (cnt == 0) continue;
+    const uint32_t* cl = cand + ((size_t)b * qs.cap + q) * kCandCap;
+    // two lexicographically smallest (dist, position) among unclaimed candidates
+    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    for (int k = lane; k < cnt; k += 32) {
+      const uint32_t e = cl[k];
+      if (s_claimed[e >> 16]) continue;
+      const unsigned key = ((e & 0xFFFFu) << 16) | (unsigned)k;
+      if (key < k1) { k2 = k1; k1 = key; }
+      else if (key < k2) k2 = key;
+    }
+    const unsigned best = warp_min_u32(k1);
+    if (best == 0xFFFFFFFFu) continue;
+    const int bestDist = (int)(best >> 16);
+    if (bestDist > prm.th_dist) continue;
+    const int bestIdx = (int)(cl[best & 0xFFFFu] >> 16);
+    if (prm.mode == 1) {
+      const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
+      if (second != 0xFFFFFFFFu) {
+        const int d2 = (int)(second >> 16);
+        const int l1 = kps[bestIdx].octave, l2 = kps[cl[second & 0xFFFFu] >> 16].octave;
+        if (l1 == l2 && (float)bestDist > __fmul_rn(prm.nn_ratio, (float)d2)) continue;  // :118-119
+      }
+      // no second candidate: bestLevel2 = -1 never equals a real level, bestDist2 = 256 (:76-79)
+    }
+    const psl_proj_query Q = qs.q[(size_t)b * qs.cap + q];
+    if (lane == 0) {
+      assign[bestIdx] = q;
+      s_claimed[bestIdx] = (Q.flags & PSL_Q_CLAIMS) ? 1 : 0;
+      if (hist_on) {
+        const int bin = rot_bin(Q.angle, kps[bestIdx].angle);
+        s_hist[bin]++;
+        accepted[nacc] = ((uint32_t)bestIdx << 8) | (uint32_t)bin;
+      }
+    }
+    ++nm;
+    ++nacc;
+    __syncwarp();
+  }
+  if (hist_on) {
+    int i1, i2, i3;
+    three_maxima(s_hist, i1, i2, i3);
+    int dropped = 0;
+    for (int k = lane; k < nacc; k += 32) {
+      const uint32_t e = accepted[k];
+      const int bin = (int)(e & 0xFFu);
+      if (bin != i1 && bin != i2 && bin != i3) {
+        assign[e >> 8] = -1;
+        ++dropped;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, d);
+    nm -= dropped;
+  }
+  if (lane == 0) nmatches[b] = nm;
+}
+
+void launch_proj_resolve(const MatchFrames& f, const MatchQueries& q, const uint32_t* cand, const int32_t* cand_count,
+                         const uint8_t* claimed_in, psl_match_params prm, uint32_t* accepted_scratch, int32_t* assign,
+                         int32_t* nmatches, int B, cudaStream_t st) {
+  proj_resolve_kernel<<<B, 32, (size_t)f.cap, st>>>(f, q, cand, cand_count, claimed_in, prm, accepted_scratch, assign,
+                                                    nmatches);
+}
+
+// ---------------------------------------------------------------------------------------------
+// DescriptorDistance (ORBmatcher.cc:1647-1663) and BFMatcher knn2 (LSDmatcher.cpp:354-376)
+// ---------------------------------------------------------------------------------------------
+__global__ void descriptor_distance_kernel(const uint4* a, const uint4* b, int n, int32_t* dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dist[i] = hamming256(a[2 * i], a[2 * i + 1], b[2 * i], b[2 * i + 1]);
+}
+
+void launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, cudaStream_t st) {
+  if (n <= 0) return;
+  descriptor_distance_kernel<<<(n + 127) / 128, 128, 0, st>>>((const uint4*)a, (const uint4*)b, n, dist);
+}
+
+constexpr int kKnnWarps = 4;
+
+__global__ void __launch_bounds__(kKnnWarps * 32)
+    knn2_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int32_t* __restrict__ idx,
+                int32_t* __restrict__ dist) {
+  const int lane = threadIdx.x & 31, qi = blockIdx.x * kKnnWarps + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  const uint4 q0 = __ldg(q + 2 * qi), q1 = __ldg(q + 2 * qi + 1);
+  unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;  // (dist << 16) | train index: earliest index wins ties
+  for (int j = lane; j < nt; j += 32) {
+    const unsigned key = ((unsigned)hamming256(q0, q1, __ldg(t + 2 * j), __ldg(t + 2 * j + 1)) << 16) | (unsigned)j;
+    if (key < k1) { k2 = k1; k1 = key; }
+    else if (key < k2) k2 = key;
+  }
+  const unsigned best = warp_min_u32(k1);
+  const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
+  if (lane == 0) {
+    idx[2 * qi] = best == 0xFFFFFFFFu ? -1 : (int)(best & 0xFFFFu);
+    dist[2 * qi] = best == 0xFFFFFFFFu ? -1 : (int)(best >> 16);
+    idx[2 * qi + 1] = second == 0xFFFFFFFFu ? -1 : (int)(second & 0xFFFFu);
+    dist[2 * qi + 1] = second == 0xFFFFFFFFu ? -1 : (int)(second >> 16);
+  }
+}
+
+void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist, cudaStream_t st) {
+  if (nq <= 0) return;
+  knn2_kernel<<<(nq + kKnnWarps - 1) / kKnnWarps, kKnnWarps * 32, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt,
+                                                                           idx, dist);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SearchByBoW (ORBmatcher.cc:159-288): one warp per pair of equal vocabulary nodes.  A frame
+// keypoint belongs to exactly one node, so the greedy "already matched" test never crosses warps.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    bow_kernel(const uint4* __restrict__ kf_desc, const float* __restrict__ kf_angle,
+               const uint8_t* __restrict__ kf_valid, const int32_t* __restrict__ kf_offs,
+               const uint32_t* __restrict__ kf_idx, const uint4* __restrict__ f_desc, const float* __restrict__ f_angle,
+               const int32_t* __restrict__ f_offs, const uint32_t* __restrict__ f_idx, const int2* __restrict__ pairs,
+               int npairs, float nn_ratio, int th_low, int check_ori, int32_t* match_f, int32_t* hist,
+               uint32_t* accepted, int32_t* n_accepted) {
+  const int lane = threadIdx.x & 31, g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= npairs) return;
+  const int2 pr = pairs[g];
+  const int ks = kf_offs[pr.x], ke = kf_offs[pr.x + 1], fs = f_offs[pr.y], fe = f_offs[pr.y + 1];
+  for (int ik = ks; ik < ke; ++ik) {
+    const int rk = (int)kf_idx[ik];
+    if (!kf_valid[rk]) continue;
+    const uint4 q0 = __ldg(kf_desc + 2 * rk), q1 = __ldg(kf_desc + 2 * rk + 1);
+    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+    for (int j = fs + lane; j < fe; j += 32) {
+      const int rf = (int)f_idx[j];
+      if (match_f[rf] >= 0) continue;  // :209-210
+      const unsigned key = ((unsigned)hamming256(q0, q1, __ldg(f_desc + 2 * rf), __ldg(f_desc + 2 * rf + 1)) << 16) |
+                           (unsigned)(j - fs);
+      if (key < k1) { k2 = k1; k1 = key; }
+      else if (key < k2) k2 = key;
+    }
+    const unsigned best = warp_min_u32(k1);
+    if (best == 0xFFFFFFFFu) continue;
+    const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
+    const int d1 = (int)(best >> 16), d2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
+    if (d1 <= th_low && (float)d1 < __fmul_rn(nn_ratio, (float)d2)) {
+      const int rf = (int)f_idx[fs + (int)(best & 0xFFFFu)];
+      if (lane == 0) {
+        match_f[rf] = rk;
+        if (check_ori) {
+          const int bin = rot_bin(kf_angle[rk], f_angle[rf]);
+          atomicAdd(&hist[bin], 1);
+          accepted[atomicAdd(n_accepted, 1)] = ((uint32_t)rf << 8) | (uint32_t)bin;
+        } else {
+          atomicAdd(n_accepted, 1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void bow_finalize_kernel(int check_ori, int32_t* match_f, const int32_t* hist, const uint32_t* accepted,
+                                    const int32_t* n_accepted, int32_t* nmatches) {
+  __shared__ int s_drop;
+  if (threadIdx.x == 0) s_drop = 0;
+  __syncthreads();
+  const int n = *n_accepted;
+  if (check_ori) {
+    int i1, i2, i3;
+    three_maxima(hist, i1, i2, i3);
+    int d = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const uint32_t e = accepted[k];
+      const int bin = (int)(e & 0xFFu);
+      if (bin != i1 && bin != i2 && bin != i3) { match_f[e >> 8] = -1; ++d; }
+    }
+    atomicAdd(&s_drop, d);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *nmatches = n - s_drop;
+}
+
+void launch_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, const int32_t* kf_offs,
+                const uint32_t* kf_idx, const uint8_t* f_desc, const float* f_angle, const int32_t* f_offs,
+                const uint32_t* f_idx, const int2* pairs, int npairs, float nn_ratio, int th_low, int check_ori, int nf,
+                int32_t* match_f, int32_t* hist, uint32_t* accepted, int32_t* n_accepted, int32_t* nmatches,
+                cudaStream_t st) {
+  cudaMemsetAsync(match_f, 0xFF, (size_t)nf * sizeof(int32_t), st);
+  cudaMemsetAsync(hist, 0, 32 * sizeof(int32_t), st);
+  cudaMemsetAsync(n_accepted, 0, sizeof(int32_t), st);
+  if (npairs > 0)
+    bow_kernel<<<(npairs + 3) / 4, 128, 0, st>>>((const uint4*)kf_desc, kf_angle, kf_valid, kf_offs, kf_idx,
+                                                 (const uint4*)f_desc, f_angle, f_offs, f_idx, pairs, npairs, nn_ratio,
+                                                 th_low, check_ori, match_f, hist, accepted, n_accepted);
+  bow_finalize_kernel<<<1, 128, 0, st>>>(check_ori, match_f, hist, accepted, n_accepted, nmatches);
+}
+
+}  // namespace psl

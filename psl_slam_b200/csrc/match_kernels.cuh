@@ -1,0 +1,51 @@
+// Launchers of the Hamming matchers (all asynchronous on `st`).  Batch-first: every launcher
+// works on B independent (frame, query-set) pairs laid out as [B][cap] row blocks.
+#pragma once
+#include "psl_common.cuh"
+
+namespace psl {
+
+constexpr int kGridCells = PSL_GRID_COLS * PSL_GRID_ROWS;  // 3072
+constexpr int kCandCap = 256;                              // candidates kept per projected query
+
+// The searched frames of a batch: frame b owns rows [b*cap, b*cap + n[b]).
+struct MatchFrames {
+  const psl_keypoint* kps;  // undistorted keypoints (mvKeysUn)
+  const float* u_right;     // may be null
+  const uint8_t* desc;
+  const int32_t* n;         // device array [B]
+  int32_t cap;
+  float min_x, min_y, grid_w_inv, grid_h_inv;
+};
+
+struct MatchQueries {
+  const psl_proj_query* q;
+  const uint8_t* desc;
+  const int32_t* nq;  // device array [B]
+  int32_t cap;
+};
+
+// per-frame CSR of the 64x48 feature grid: start[B][3073], items[B][cap]
+void launch_grid_build(const MatchFrames& f, int32_t* cell_start, uint16_t* cell_items, int B, cudaStream_t st);
+
+// ordered candidate lists with distances: cand[B][qcap][kCandCap] = idx<<16 | dist, count[B][qcap]
+void launch_proj_candidates(const MatchFrames& f, const MatchQueries& q, const int32_t* cell_start,
+                            const uint16_t* cell_items, uint32_t* cand, int32_t* cand_count, uint32_t* status, int B,
+                            cudaStream_t st);
+
+// ordered greedy resolve + rotation-histogram filter; claimed_in may be null
+void launch_proj_resolve(const MatchFrames& f, const MatchQueries& q, const uint32_t* cand, const int32_t* cand_count,
+                         const uint8_t* claimed_in, psl_match_params prm, uint32_t* accepted_scratch, int32_t* assign,
+                         int32_t* nmatches, int B, cudaStream_t st);
+
+void launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, cudaStream_t st);
+void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist, cudaStream_t st);
+
+// SearchByBoW: `pairs` = (kf node slot, frame node slot) of equal node ids
+void launch_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, const int32_t* kf_offs,
+                const uint32_t* kf_idx, const uint8_t* f_desc, const float* f_angle, const int32_t* f_offs,
+                const uint32_t* f_idx, const int2* pairs, int npairs, float nn_ratio, int th_low, int check_ori, int nf,
+                int32_t* match_f, int32_t* hist /*[32]*/, uint32_t* accepted, int32_t* n_accepted, int32_t* nmatches,
+                cudaStream_t st);
+
+}  // namespace psl

@@ -5,6 +5,13 @@
 
 #include "orb_kernels.cuh"
 
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct psl_ctx {
   psl_config cfg{};
   cudaStream_t stream = nullptr;
@@ -42,6 +49,10 @@ struct psl_ctx {
   int64_t stage_launches[PSL_N_STAGES] = {0};
   int64_t launches = 0;
 
+  // matcher scratch (single-pair host API and the batched pipeline)
+  DevBuf m_kps, m_ur, m_desc, m_q, m_qdesc, m_claimed, m_n, m_cell_start, m_cell_items, m_cand, m_cand_count,
+      m_accepted, m_assign, m_nm, m_misc[12];
+
   // staging for the host-pointer entry points (grown on demand)
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
   psl_keypoint* d_kps = nullptr; size_t d_kps_bytes = 0;
@@ -53,6 +64,7 @@ namespace psl {
 int fail(psl_ctx* c, int code, const std::string& msg);
 int cuda_fail(psl_ctx* c, cudaError_t e, const char* what);
 int ensure_bytes(psl_ctx* c, void** p, size_t* have, size_t need);
+inline int ensure(psl_ctx* c, DevBuf& b, size_t need) { return ensure_bytes(c, &b.p, &b.bytes, need ? need : 16); }
 int check_status(psl_ctx* c);  // sync + translate the device status word
 // RAII-free stage bracket: begin/end record events when profiling is on and count launches.
 size_t prof_mark(psl_ctx* c);

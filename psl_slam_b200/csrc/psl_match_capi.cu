@@ -1,0 +1,153 @@
+// C-ABI of the matchers (include/psl_frontend.h): host-pointer, single-pair entry points that
+// stage the plain arrays in HBM, run the batch kernels with B = 1 and copy the result back.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "match_kernels.cuh"
+#include "psl_ctx.cuh"
+
+using namespace psl;
+
+#define PSL_UP(buf, src, nbytes)                                                                    \
+  do {                                                                                              \
+    int rc__ = ensure(ctx, buf, (nbytes));                                                          \
+    if (rc__) return rc__;                                                                          \
+    if ((nbytes) > 0) PSL_CK(cudaMemcpyAsync((buf).p, (src), (nbytes), cudaMemcpyHostToDevice, ctx->stream)); \
+  } while (0)
+
+extern "C" {
+
+int psl_descriptor_distance(psl_ctx* ctx, const uint8_t* a, const uint8_t* b, int32_t n, int32_t* dist) {
+  if (!ctx) return PSL_E_INVALID;
+  if (n < 0 || (n > 0 && (!a || !b || !dist))) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (n == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  PSL_UP(ctx->m_desc, a, (size_t)n * 32);
+  PSL_UP(ctx->m_qdesc, b, (size_t)n * 32);
+  int rc = ensure(ctx, ctx->m_assign, (size_t)n * 4);
+  if (rc) return rc;
+  launch_descriptor_distance(ctx->m_desc.as<uint8_t>(), ctx->m_qdesc.as<uint8_t>(), n, ctx->m_assign.as<int32_t>(),
+                             ctx->stream);
+  prof_span(ctx, 5, prof_mark(ctx), 1);
+  PSL_CK(cudaMemcpyAsync(dist, ctx->m_assign.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+int psl_hamming_knn2(psl_ctx* ctx, const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx,
+                     int32_t* dist) {
+  if (!ctx) return PSL_E_INVALID;
+  if (nq < 0 || nt < 0 || nt > 65535 || (nq > 0 && (!q || !idx || !dist)) || (nt > 0 && !t))
+    return fail(ctx, PSL_E_INVALID, "bad argument (nt <= 65535)");
+  if (nq == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  PSL_UP(ctx->m_qdesc, q, (size_t)nq * 32);
+  PSL_UP(ctx->m_desc, t, (size_t)nt * 32);
+  int rc = ensure(ctx, ctx->m_assign, (size_t)nq * 8);
+  if (rc) return rc;
+  if ((rc = ensure(ctx, ctx->m_cand_count, (size_t)nq * 8))) return rc;
+  launch_knn2(ctx->m_qdesc.as<uint8_t>(), nq, ctx->m_desc.as<uint8_t>(), nt, ctx->m_assign.as<int32_t>(),
+              ctx->m_cand_count.as<int32_t>(), ctx->stream);
+  prof_span(ctx, 5, prof_mark(ctx), 1);
+  PSL_CK(cudaMemcpyAsync(idx, ctx->m_assign.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(dist, ctx->m_cand_count.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+int psl_match_projection(psl_ctx* ctx, const psl_frame_view* fv, const psl_proj_query* queries,
+                         const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in,
+                         const psl_match_params* prm, int32_t* assign, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!fv || !prm || !nmatches || nq < 0 || fv->n < 0 || fv->n > 65535 || (fv->n > 0 && (!fv->kps_un || !fv->desc || !assign)) ||
+      (nq > 0 && (!queries || !query_desc)) || (prm->mode != 0 && prm->mode != 1))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  const int n = fv->n;
+  if (n == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const int ncap = std::max(n, 1), qcap = std::max(nq, 1);
+  PSL_UP(ctx->m_kps, fv->kps_un, (size_t)n * sizeof(psl_keypoint));
+  if (fv->u_right) PSL_UP(ctx->m_ur, fv->u_right, (size_t)n * 4);
+  PSL_UP(ctx->m_desc, fv->desc, (size_t)n * 32);
+  PSL_UP(ctx->m_q, queries, (size_t)nq * sizeof(psl_proj_query));
+  PSL_UP(ctx->m_qdesc, query_desc, (size_t)nq * 32);
+  if (claimed_in) PSL_UP(ctx->m_claimed, claimed_in, (size_t)n);
+  const int32_t nn[2] = {n, nq};
+  PSL_UP(ctx->m_n, nn, sizeof(nn));
+  int rc;
+  if ((rc = ensure(ctx, ctx->m_cell_start, (size_t)(kGridCells + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cell_items, (size_t)ncap * 2))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cand, (size_t)qcap * kCandCap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cand_count, (size_t)qcap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_accepted, (size_t)qcap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_assign, (size_t)ncap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_nm, 4))) return rc;
+  MatchFrames F{ctx->m_kps.as<psl_keypoint>(), fv->u_right ? ctx->m_ur.as<float>() : nullptr, ctx->m_desc.as<uint8_t>(),
+                ctx->m_n.as<int32_t>(), ncap, fv->min_x, fv->min_y, fv->grid_w_inv, fv->grid_h_inv};
+  MatchQueries Q{ctx->m_q.as<psl_proj_query>(), ctx->m_qdesc.as<uint8_t>(), ctx->m_n.as<int32_t>() + 1, qcap};
+  size_t e = prof_mark(ctx);
+  launch_grid_build(F, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(), 1, ctx->stream);
+  launch_proj_candidates(F, Q, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(),
+                         ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->d_status, 1, ctx->stream);
+  launch_proj_resolve(F, Q, ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(),
+                      claimed_in ? ctx->m_claimed.as<uint8_t>() : nullptr, *prm, ctx->m_accepted.as<uint32_t>(),
+                      ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, ctx->stream);
+  prof_span(ctx, 5, e, 3);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(assign, ctx->m_assign.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = check_status(ctx);
+  if (rc == PSL_E_CAPACITY) return fail(ctx, rc, "more than 256 candidates in one search window");
+  return rc;
+}
+
+int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, int32_t nkf,
+                  const psl_feature_vector* kfv, const uint8_t* f_desc, const float* f_angle, int32_t nf,
+                  const psl_feature_vector* ffv, float nn_ratio, int32_t th_low, int32_t check_orientation,
+                  int32_t* match_f, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!kfv || !ffv || !nmatches || nkf < 0 || nf < 0 || (nf > 0 && (!f_desc || !f_angle || !match_f)) ||
+      (nkf > 0 && (!kf_desc || !kf_angle || !kf_valid)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  for (int i = 0; i < nf; ++i) match_f[i] = -1;
+  if (nf == 0 || nkf == 0) return PSL_OK;
+  // merge walk over the two sorted node lists (std::map iteration + lower_bound, ORBmatcher.cc:180-262)
+  std::vector<int2> pairs;
+  for (int a = 0, b = 0; a < kfv->n_nodes && b < ffv->n_nodes;) {
+    if (kfv->node_id[a] == ffv->node_id[b]) pairs.push_back(make_int2(a++, b++));
+    else if (kfv->node_id[a] < ffv->node_id[b]) ++a;
+    else ++b;
+  }
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const size_t nki = kfv->n_nodes ? (size_t)kfv->offs[kfv->n_nodes] : 0, nfi = ffv->n_nodes ? (size_t)ffv->offs[ffv->n_nodes] : 0;
+  for (size_t i = 0; i < nki; ++i) if ((int)kfv->idx[i] >= nkf) return fail(ctx, PSL_E_INVALID, "kf feature index out of range");
+  for (size_t i = 0; i < nfi; ++i) if ((int)ffv->idx[i] >= nf) return fail(ctx, PSL_E_INVALID, "frame feature index out of range");
+  DevBuf* M = ctx->m_misc;
+  PSL_UP(M[0], kf_desc, (size_t)nkf * 32);
+  PSL_UP(M[1], kf_angle, (size_t)nkf * 4);
+  PSL_UP(M[2], kf_valid, (size_t)nkf);
+  PSL_UP(M[3], kfv->offs, (size_t)(kfv->n_nodes + 1) * 4);
+  PSL_UP(M[4], kfv->idx, nki * 4);
+  PSL_UP(M[5], f_desc, (size_t)nf * 32);
+  PSL_UP(M[6], f_angle, (size_t)nf * 4);
+  PSL_UP(M[7], ffv->offs, (size_t)(ffv->n_nodes + 1) * 4);
+  PSL_UP(M[8], ffv->idx, nfi * 4);
+  PSL_UP(M[9], pairs.data(), pairs.size() * sizeof(int2));
+  int rc;
+  if ((rc = ensure(ctx, M[10], (size_t)nf * 4 + 34 * 4))) return rc;      // match_f | hist[32] | n_accepted | nmatches
+  if ((rc = ensure(ctx, M[11], (size_t)std::max(nkf, 1) * 4))) return rc;  // accepted list
+  int32_t* d_match = M[10].as<int32_t>();
+  int32_t* d_hist = d_match + nf;
+  launch_bow(M[0].as<uint8_t>(), M[1].as<float>(), M[2].as<uint8_t>(), M[3].as<int32_t>(), M[4].as<uint32_t>(),
+             M[5].as<uint8_t>(), M[6].as<float>(), M[7].as<int32_t>(), M[8].as<uint32_t>(), M[9].as<int2>(),
+             (int)pairs.size(), nn_ratio, th_low, check_orientation, nf, d_match, d_hist, M[11].as<uint32_t>(),
+             d_hist + 32, d_hist + 33, ctx->stream);
+  prof_span(ctx, 5, prof_mark(ctx), 2);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(match_f, d_match, (size_t)nf * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, d_hist + 33, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+}  // extern "C"

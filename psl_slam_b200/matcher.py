@@ -1,0 +1,99 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:41-83 in the reference) over the
+C-ABI.  The reference methods take Frame / KeyFrame / MapPoint objects; here the caller passes the plain
+arrays those objects hold (a FrameData view and projected queries) — exactly what crosses the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view
+from .orb import Context, _ptr
+
+
+@dataclass
+class FrameData:
+    """What the matchers read from a Frame: mvKeysUn, mvuRight, mDescriptors and the image bounds
+    (include/Frame.h:150-290)."""
+    kps_un: np.ndarray            # KP_DTYPE [n]
+    desc: np.ndarray              # u8 [n,32]
+    u_right: np.ndarray | None    # f32 [n] (<=0: none)
+    bounds: tuple                 # (mnMinX, mnMinY, mnMaxX, mnMaxY)
+
+
+class ORBmatcher:
+    TH_HIGH = 100  # ORBmatcher.cc:37
+    TH_LOW = 50    # ORBmatcher.cc:38
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, *, ctx: Context | None = None, device: int = 0):
+        """ORBmatcher(float nnratio=0.6, bool checkOri=true) — ORBmatcher.cc:41-43."""
+        if ctx is None:
+            cfg = _lib.default_config()
+            cfg.device = device
+            ctx = Context(cfg)
+        self.ctx = ctx
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+
+    def DescriptorDistance(self, a: np.ndarray, b: np.ndarray):
+        """ORBmatcher.cc:1647-1663; accepts one pair [32] or n pairs [n,32]."""
+        a2 = np.ascontiguousarray(np.atleast_2d(a), np.uint8)
+        b2 = np.ascontiguousarray(np.atleast_2d(b), np.uint8)
+        out = np.zeros(len(a2), np.int32)
+        self.ctx.check(_lib.lib().psl_descriptor_distance(self.ctx.handle, _ptr(a2), _ptr(b2), len(a2), _ptr(out)))
+        return int(out[0]) if np.ndim(a) == 1 else out
+
+    def _project(self, frame: FrameData, queries, qdesc, claimed, mode, th_dist, ratio, ori):
+        fv, keep = make_frame_view(frame.kps_un, frame.u_right, frame.desc, frame.bounds)
+        queries = np.ascontiguousarray(queries, QUERY_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        cl = None if claimed is None else np.ascontiguousarray(claimed, np.uint8)
+        prm = MatchParams(mode, th_dist, ratio, int(ori))
+        assign = np.full(fv.n, -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_match_projection(self.ctx.handle, C.byref(fv), _ptr(queries), _ptr(qdesc),
+                                                       len(queries), None if cl is None else _ptr(cl), C.byref(prm),
+                                                       _ptr(assign), C.byref(nm)))
+        return assign, nm.value
+
+    def SearchByProjectionLastFrame(self, cur: FrameData, queries, last_desc, claimed=None):
+        """SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono) — ORBmatcher.cc:1328-1470.
+        `queries` carry what the per-point prologue (:1353-1393) computes."""
+        return self._project(cur, queries, last_desc, claimed, 0, self.TH_HIGH, self.mfNNratio,
+                             self.mbCheckOrientation)
+
+    def SearchByProjectionMapPoints(self, frame: FrameData, queries, mp_desc, claimed=None):
+        """SearchByProjection(Frame &F, const vector<MapPoint*>&, th) — ORBmatcher.cc:45-129."""
+        return self._project(frame, queries, mp_desc, claimed, 1, self.TH_HIGH, self.mfNNratio, False)
+
+    def SearchByBoW(self, kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv):
+        """SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — ORBmatcher.cc:159-288.
+        kf_fv / f_fv: (node_ids ascending, offs, indices) CSR of DBoW2::FeatureVector."""
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8)
+        f_desc = np.ascontiguousarray(f_desc, np.uint8)
+        kf_angle = np.ascontiguousarray(kf_angle, np.float32)
+        f_angle = np.ascontiguousarray(f_angle, np.float32)
+        kf_valid = np.ascontiguousarray(kf_valid, np.uint8)
+        a, k1 = make_feature_vector(*kf_fv)
+        b, k2 = make_feature_vector(*f_fv)
+        match = np.full(len(f_desc), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_match_bow(self.ctx.handle, _ptr(kf_desc), _ptr(kf_angle), _ptr(kf_valid),
+                                                len(kf_desc), C.byref(a), _ptr(f_desc), _ptr(f_angle), len(f_desc),
+                                                C.byref(b), C.c_float(self.mfNNratio), self.TH_LOW,
+                                                int(self.mbCheckOrientation), _ptr(match), C.byref(nm)))
+        return match, nm.value
+
+
+def hamming_knn2(ctx: Context, q: np.ndarray, t: np.ndarray):
+    """cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, 2) — LSDmatcher.cpp:361-362."""
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    idx = np.full((len(q), 2), -1, np.int32)
+    dist = np.full((len(q), 2), -1, np.int32)
+    ctx.check(_lib.lib().psl_hamming_knn2(ctx.handle, _ptr(q), len(q), _ptr(t), len(t), _ptr(idx), _ptr(dist)))
+    return idx, dist

@@ -1,0 +1,60 @@
+"""CPU: the matcher oracle (oracle/c/orc_match.cpp) against the goldens written by the independent
+Python restatement + cv2.BFMatcher (oracle/pyref/match_py.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+PAIRS = golden_names("match_pair")
+
+
+def test_descriptor_distance_known_answers(orc):
+    a = np.zeros((3, 32), np.uint8)
+    b = np.zeros((3, 32), np.uint8)
+    b[1] = 0xFF
+    b[2, 5] = 0b10110000
+    assert orc.descriptor_distance(a, b).tolist() == [0, 256, 3]
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_knn2_vs_cv2(orc, name):
+    g = load_golden(name)
+    idx, dist = orc.hamming_knn2(g["desc_last"][:200], g["desc_cur"][:200])
+    assert np.array_equal(idx, g["knn_idx"]) and np.array_equal(dist, g["knn_dist"])
+
+
+def test_knn2_fewer_than_two_train_rows(orc):
+    q = np.arange(64, dtype=np.uint8).reshape(2, 32)
+    idx, dist = orc.hamming_knn2(q, q[:1])
+    assert idx[:, 1].tolist() == [-1, -1] and idx[:, 0].tolist() == [0, 0] and dist[0, 0] == 0
+    idx, dist = orc.hamming_knn2(q, q[:0])
+    assert (idx == -1).all()
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_search_by_projection_modes(orc, name):
+    g = load_golden(name)
+    a0, n0 = orc.match_projection(g["kps_cur"], g["u_right_cur"], g["desc_cur"], g["bounds"], g["queries"],
+                                  g["desc_last"], None, 0, 100, 0.9, True)
+    assert np.array_equal(a0, g["assign0"]) and n0 == int(g["nmatches0"])
+    a1, n1 = orc.match_projection(g["kps_cur"], g["u_right_cur"], g["desc_cur"], g["bounds"], g["queries1"],
+                                  g["desc_last"], g["claimed1"], 1, 100, 0.8, False)
+    assert np.array_equal(a1, g["assign1"]) and n1 == int(g["nmatches1"])
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_search_by_bow(orc, name):
+    g = load_golden(name)
+    m, n = orc.match_bow(g["desc_last"], g["angle_last"], g["kf_valid"], (g["kf_nodes"], g["kf_offs"], g["kf_idx"]),
+                         g["desc_cur"], g["kps_cur"]["angle"], (g["f_nodes"], g["f_offs"], g["f_idx"]), 0.7, 50, True)
+    assert np.array_equal(m, g["bow_match"]) and n == int(g["bow_nmatches"])
+
+
+def test_empty_inputs(orc):
+    g = load_golden(PAIRS[0])
+    a, n = orc.match_projection(g["kps_cur"], None, g["desc_cur"], g["bounds"], g["queries"][:0], g["desc_last"][:0],
+                                None, 0)
+    assert n == 0 and (a == -1).all()
+    a, n = orc.match_projection(g["kps_cur"][:0], None, g["desc_cur"][:0], g["bounds"], g["queries"], g["desc_last"],
+                                None, 0)
+    assert n == 0 and len(a) == 0
