@@ -178,9 +178,51 @@ int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, c
                   const psl_feature_vector* f_fv, float nn_ratio, int32_t th_low, int32_t check_orientation,
                   int32_t* match_f, int32_t* nmatches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched point front end of one tracking step (BASELINE config 2/4), everything resident in HBM.
+ * For a batch of B consecutive RGB-D frames it does what the reference does per frame:
+ *   Frame::Frame(gray, depth, ...)      ExtractORB (src/Frame.cc:179 -> ORBextractor::operator())
+ *                                        ComputeStereoFromRGBD (src/Frame.cc:192, :1342-1363)
+ *   Tracking::TrackWithMotionModel      ORBmatcher::SearchByProjection(Cur, Last, th, false)
+ *                                        (src/Tracking.cc:1193 -> src/ORBmatcher.cc:1328-1470)
+ * with frame b-1 of the batch playing LastFrame for frame b (every keypoint of the last frame that has depth
+ * carries a MapPoint, as after Tracking::UpdateLastFrame), and Tcw[b] the pose prior of frame b.
+ * Distortion must be zero (mvKeysUn == mvKeys, bounds = image; Frame.cc:155-158).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct psl_camera {
+  float fx, fy, cx, cy; /* Camera.fx .. (Examples/RGB-D/ICL.yaml:8-11) */
+  float bf;             /* Camera.bf */
+  float depth_factor;   /* 1/DepthMapFactor as float (Tracking.cc:142-145) */
+} psl_camera;
+
+typedef struct psl_track_params {
+  float th;                  /* window factor: 15 (Tracking.cc:1189) */
+  float nn_ratio;            /* ORBmatcher(0.9, true) at Tracking.cc:1166 */
+  int32_t check_orientation;
+  int32_t th_dist;           /* TH_HIGH = 100 */
+} psl_track_params;
+
+/* DEVICE pointers, asynchronous on psl_stream(ctx).  gray: [B] frames of h rows, `gray_stride` bytes per row,
+ * frames `gray_frame_stride` bytes apart; depth: u16, strides in PIXELS; Tcw: [B][12] row-major 3x4 float.
+ * Outputs are [B][cap] blocks: kps, desc (x32), u_right, z (mvDepth), assign (index into frame b-1's
+ * keypoints whose point landed on keypoint i of frame b, or -1), and n[B], nmatches[B] (nmatches[0] = 0). */
+int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                            const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                            int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                            const psl_track_params* prm, psl_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n,
+                            float* d_u_right, float* d_z, int32_t* d_assign, int32_t* d_nmatches, int32_t cap);
+
+/* Same with HOST pointers (tightly packed frames: gray [B][h][w] u8, depth [B][h][w] u16, Tcw [B][12]);
+ * H2D and D2H copies are part of the call. */
+int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
+                        const float* Tcw, const psl_camera* cam, const psl_track_params* prm, psl_keypoint* kps,
+                        uint8_t* desc, int32_t* n, float* u_right, float* z, int32_t* assign, int32_t* nmatches,
+                        int32_t cap);
+
 /* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).
  * Stages: 0 pyramid resize, 1 FAST cells, 2 octree selection, 3 Gaussian blur, 4 orientation+rBRIEF,
- * 5.. reserved for matching / line stages.  psl_profile_read synchronises, writes the accumulated
+ * 5 single-pair matcher calls, 6 stereo + projection queries, 7 feature grid, 8 candidate lists,
+ * 9 ordered resolve; 10.. reserved for the line stages.  psl_profile_read synchronises, writes the accumulated
  * milliseconds and kernel-launch counts per stage since the last read (arrays of PSL_N_STAGES) and resets. */
 #define PSL_N_STAGES 16
 int psl_profile_enable(psl_ctx* ctx, int32_t on);

@@ -59,6 +59,14 @@ int orc_match_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* 
                   const psl_feature_vector* ffv, float nn_ratio, int th_low, int check_orientation, int32_t* match_f,
                   int32_t* nmatches);
 
+/* ---- Frame bookkeeping (orc_frame.cpp): Frame.cc:1342-1381, ORBmatcher.cc:1339-1393 ---- */
+void orc_stereo_from_rgbd(const psl_keypoint* kps, int n, const uint16_t* depth, int w, int h, int stride_px,
+                          float depth_factor, float bf, float* u_right, float* z);
+void orc_queries_from_last_frame(const psl_keypoint* kps_last, const float* z_last, const uint8_t* valid_in,
+                                 const uint8_t* claims_in, int n, const float* Tcw_last, const float* Tcw_cur,
+                                 const float* cam, const float* scale_factors, float th, int mono, float min_x,
+                                 float min_y, float max_x, float max_y, psl_proj_query* q);
+
 /* CPU-baseline harness: B frames, one frame per task on `nthreads` std::threads. */
 int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
                              int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor);

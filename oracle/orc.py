@@ -190,3 +190,32 @@ def match_bow(kf_desc, kf_angle, kf_valid, kf_csr, f_desc, f_angle, f_csr, nn_ra
                         len(f_desc), C.byref(ffv), C.c_float(nn_ratio), th_low, int(check_orientation), _p(match),
                         C.byref(nm))
     return match, nm.value
+
+
+# ---- Frame bookkeeping (oracle/c/orc_frame.cpp) -------------------------------------------------
+def stereo_from_rgbd(kps, depth_u16, depth_factor, bf):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+    ur = np.empty(len(kps), np.float32)
+    z = np.empty(len(kps), np.float32)
+    lib().orc_stereo_from_rgbd(_p(kps), len(kps), _p(depth_u16), depth_u16.shape[1], depth_u16.shape[0],
+                               depth_u16.shape[1], C.c_float(depth_factor), C.c_float(bf), _p(ur), _p(z))
+    return ur, z
+
+
+def queries_from_last_frame(kps_last, z_last, Tcw_last, Tcw_cur, cam, scale_factors, th, bounds, valid=None,
+                            claims=None, mono=False):
+    kps_last = np.ascontiguousarray(kps_last, KP_DTYPE)
+    z_last = np.ascontiguousarray(z_last, np.float32)
+    Tl = np.ascontiguousarray(np.asarray(Tcw_last, np.float32)[:3, :4])
+    Tc = np.ascontiguousarray(np.asarray(Tcw_cur, np.float32)[:3, :4])
+    cam = np.ascontiguousarray(cam, np.float32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    va = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    cl = None if claims is None else np.ascontiguousarray(claims, np.uint8)
+    q = np.zeros(len(kps_last), QUERY_DTYPE)
+    lib().orc_queries_from_last_frame(_p(kps_last), _p(z_last), None if va is None else _p(va),
+                                      None if cl is None else _p(cl), len(kps_last), _p(Tl), _p(Tc), _p(cam), _p(sf),
+                                      C.c_float(th), int(mono), C.c_float(bounds[0]), C.c_float(bounds[1]),
+                                      C.c_float(bounds[2]), C.c_float(bounds[3]), _p(q))
+    return q

@@ -48,6 +48,16 @@ class MatchParams(C.Structure):  # psl_match_params
                 ("check_orientation", C.c_int32)]
 
 
+class Camera(C.Structure):  # psl_camera
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("depth_factor", C.c_float)]
+
+
+class TrackParams(C.Structure):  # psl_track_params
+    _fields_ = [("th", C.c_float), ("nn_ratio", C.c_float), ("check_orientation", C.c_int32),
+                ("th_dist", C.c_int32)]
+
+
 class FeatureVector(C.Structure):  # psl_feature_vector
     _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("offs", C.c_void_p), ("idx", C.c_void_p)]
 
@@ -75,7 +85,7 @@ def make_feature_vector(node_id, offs, idx):
 EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", "psl_stream", "psl_sync",
            "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch", "psl_profile_enable",
            "psl_profile_read", "psl_launch_count", "psl_descriptor_distance", "psl_hamming_knn2",
-           "psl_match_projection", "psl_match_bow"]
+           "psl_match_projection", "psl_match_bow", "psl_track_orb_batch", "psl_track_orb_batch_dev"]
 
 _lib = None
 
@@ -108,6 +118,9 @@ def lib():
         L.psl_hamming_knn2.argtypes = [_p, _p, _i, _p, _i, _p, _p]
         L.psl_match_projection.argtypes = [_p, _p, _p, _p, _i, _p, _p, _p, _p]
         L.psl_match_bow.argtypes = [_p, _p, _p, _p, _i, _p, _p, _p, _i, _p, C.c_float, _i, _i, _p, _p]
+        L.psl_track_orb_batch_dev.argtypes = [_p, _p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
+                                              _p, _p, _i]
+        L.psl_track_orb_batch.argtypes = [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

@@ -1,0 +1,118 @@
+// Frame bookkeeping between extraction and matching on the RGB-D path, kept on the device so the
+// batched pipeline never leaves HBM: depth scaling (Tracking.cc:234-235), ComputeStereoFromRGBD and
+// UnprojectStereo (Frame.cc:1342-1381), UpdatePoseMatrices, and the per-point prologue of
+// SearchByProjection(Current, Last, th, bMono) (ORBmatcher.cc:1339-1393).
+// Arithmetic: fp32 with explicit round-to-nearest ops; 3x3 products accumulate in fp64 and round once,
+// as cv::Mat (CV_32F) products do.
+#include "frame_kernels.cuh"
+
+namespace psl {
+
+__global__ void stereo_kernel(const psl_keypoint* __restrict__ kps, const int32_t* __restrict__ n, int cap,
+                              const uint16_t* __restrict__ depth, int stride_px, int64_t frame_stride_px,
+                              float depth_factor, float bf, float* __restrict__ u_right, float* __restrict__ z) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n[b]) return;
+  const psl_keypoint kp = kps[(size_t)b * cap + i];
+  const float d = __fmul_rn((float)depth[(size_t)b * frame_stride_px + (size_t)(int)kp.y * stride_px + (int)kp.x],
+                            depth_factor);
+  float ur = -1.f, zz = -1.f;
+  if (d > 0.f) {
+    zz = d;
+    ur = __fsub_rn(kp.x, __fdiv_rn(bf, d));
+  }
+  u_right[(size_t)b * cap + i] = ur;
+  z[(size_t)b * cap + i] = zz;
+}
+
+void launch_stereo(const psl_keypoint* kps, const int32_t* n, int cap, const uint16_t* depth, int stride_px,
+                   int64_t frame_stride_px, float depth_factor, float bf, float* u_right, float* z, int B,
+                   cudaStream_t st) {
+  dim3 grid((cap + 255) / 256, B);
+  stereo_kernel<<<grid, 256, 0, st>>>(kps, n, cap, depth, stride_px, frame_stride_px, depth_factor, bf, u_right, z);
+}
+
+// float( sum_k R[i][k]*x[k] in double + t[i] )
+__device__ __forceinline__ void affine(const float* R, int rs, const float* x, const float* t, float* out) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double s = __dadd_rn(__dadd_rn(__dmul_rn((double)R[i * rs], (double)x[0]),
+                                         __dmul_rn((double)R[i * rs + 1], (double)x[1])),
+                               __dmul_rn((double)R[i * rs + 2], (double)x[2]));
+    out[i] = (float)__dadd_rn(s, t ? (double)t[i] : 0.0);
+  }
+}
+
+// Queries of frame gb = first + blockIdx.y from the keypoints of frame gb-1 (same [B][cap] arrays).
+__global__ void query_build_kernel(const psl_keypoint* __restrict__ kps, const float* __restrict__ z,
+                                   const int32_t* __restrict__ n, int cap, const float* __restrict__ Tcw, int first,
+                                   psl_camera cam, QueryBuildParams prm, psl_proj_query* __restrict__ q,
+                                   int32_t* __restrict__ nq) {
+  const int b = blockIdx.y, gb = first + b, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb == 0) {
+    if (i == 0) nq[b] = 0;
+    return;
+  }
+  const int nl = n[gb - 1];
+  if (i == 0) nq[b] = nl;
+  if (i >= nl) return;
+  const float* Tl = Tcw + (size_t)(gb - 1) * 12;
+  const float* Tc = Tcw + (size_t)gb * 12;
+  const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, bf = cam.bf;
+  const float invfx = __fdiv_rn(1.0f, fx), invfy = __fdiv_rn(1.0f, fy), mb = __fdiv_rn(bf, fx);
+  float Rwc[9], nRwc[9], Ow[3], nRcT[9], twc[3], tlc[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      Rwc[r * 3 + k] = Tl[k * 4 + r];
+      nRwc[r * 3 + k] = -Tl[k * 4 + r];
+      nRcT[r * 3 + k] = -Tc[k * 4 + r];
+    }
+  const float tl[3] = {Tl[3], Tl[7], Tl[11]}, tc[3] = {Tc[3], Tc[7], Tc[11]};
+  affine(nRwc, 3, tl, nullptr, Ow);   // mOw = -Rcw^T tcw (Frame::UpdatePoseMatrices)
+  affine(nRcT, 3, tc, nullptr, twc);  // :1345
+  affine(Tl, 4, twc, tl, tlc);        // :1350
+  const bool fwd = tlc[2] > mb && !prm.mono, bwd = -tlc[2] > mb && !prm.mono;
+
+  psl_proj_query Q;
+  Q.u = Q.v = Q.radius = Q.u_right = Q.angle = 0.f;
+  Q.min_level = Q.max_level = 0;
+  Q.flags = 0;
+  const psl_keypoint kp = kps[(size_t)(gb - 1) * cap + i];
+  const float zz = z[(size_t)(gb - 1) * cap + i];
+  if (zz > 0.f) {
+    const float xc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(kp.x, cx), zz), invfx),
+                         __fmul_rn(__fmul_rn(__fsub_rn(kp.y, cy), zz), invfy), zz};
+    float pw[3], pc[3];
+    affine(Rwc, 3, xc, Ow, pw);  // UnprojectStereo
+    affine(Tc, 4, pw, tc, pc);   // :1363
+    const float invz = (float)__ddiv_rn(1.0, (double)pc[2]);
+    if (!(invz < 0.f)) {
+      const float u = __fadd_rn(__fmul_rn(__fmul_rn(fx, pc[0]), invz), cx);
+      const float v = __fadd_rn(__fmul_rn(__fmul_rn(fy, pc[1]), invz), cy);
+      if (!(u < prm.min_x || u > prm.max_x || v < prm.min_y || v > prm.max_y)) {
+        const int o = kp.octave;
+        Q.u = u;
+        Q.v = v;
+        Q.radius = __fmul_rn(prm.th, prm.scale[o]);
+        if (fwd) { Q.min_level = o; Q.max_level = -1; }
+        else if (bwd) { Q.min_level = 0; Q.max_level = o; }
+        else { Q.min_level = o - 1; Q.max_level = o + 1; }
+        Q.u_right = __fsub_rn(u, __fmul_rn(bf, invz));
+        Q.angle = kp.angle;
+        Q.flags = PSL_Q_VALID | PSL_Q_CLAIMS;
+      }
+    }
+  }
+  q[(size_t)b * cap + i] = Q;
+}
+
+void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* n, int cap, const float* Tcw, int first,
+                        const psl_camera& cam, const QueryBuildParams& prm, psl_proj_query* q, int32_t* nq, int B,
+                        cudaStream_t st) {
+  dim3 grid((cap + 127) / 128, B);
+  query_build_kernel<<<grid, 128, 0, st>>>(kps, z, n, cap, Tcw, first, cam, prm, q, nq);
+}
+
+}  // namespace psl

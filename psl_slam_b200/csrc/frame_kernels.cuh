@@ -1,0 +1,20 @@
+#pragma once
+#include "psl_common.cuh"
+
+namespace psl {
+
+struct QueryBuildParams {
+  float th;  // SearchByProjection window factor (15 / 7 in Tracking.cc:1189-1193)
+  int32_t mono;
+  float min_x, min_y, max_x, max_y;
+  float scale[kMaxLevels];  // mvScaleFactors
+};
+
+void launch_stereo(const psl_keypoint* kps, const int32_t* n, int cap, const uint16_t* depth, int stride_px,
+                   int64_t frame_stride_px, float depth_factor, float bf, float* u_right, float* z, int B,
+                   cudaStream_t st);
+void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* n, int cap, const float* Tcw, int first,
+                        const psl_camera& cam, const QueryBuildParams& prm, psl_proj_query* q, int32_t* nq, int B,
+                        cudaStream_t st);
+
+}  // namespace psl

@@ -1,0 +1,120 @@
+// C-ABI of the batched point front end (psl_track_orb_batch[_dev]): ORB extraction, RGB-D stereo
+// bookkeeping and SearchByProjection against the previous frame, chunk by chunk, all in HBM.
+#include <algorithm>
+#include <cstring>
+
+#include "frame_kernels.cuh"
+#include "match_kernels.cuh"
+#include "psl_ctx.cuh"
+
+using namespace psl;
+
+extern "C" {
+
+int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                            const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                            int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                            const psl_track_params* prm, psl_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n,
+                            float* d_u_right, float* d_z, int32_t* d_assign, int32_t* d_nmatches, int32_t cap) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!d_gray || !d_depth || !d_Tcw || !cam || !prm || !d_kps || !d_desc || !d_n || !d_u_right || !d_z || !d_assign ||
+      !d_nmatches || B < 0 || w <= 0 || h <= 0 || cap < 1 || cap > 65535 || depth_stride_px < w)
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  int rc = psl_orb_extract_batch_dev(ctx, d_gray, B, w, h, gray_stride, gray_frame_stride, d_kps, d_desc, cap, d_n);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  size_t e = prof_mark(ctx);
+  launch_stereo(d_kps, d_n, cap, d_depth, depth_stride_px, depth_frame_stride_px, cam->depth_factor, cam->bf, d_u_right,
+                d_z, B, st);
+  prof_span(ctx, 6, e, 1);
+
+  const int C = ctx->chunk;
+  if ((rc = ensure(ctx, ctx->m_q, (size_t)C * cap * sizeof(psl_proj_query)))) return rc;
+  if ((rc = ensure(ctx, ctx->m_n, (size_t)C * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cell_start, (size_t)C * (kGridCells + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cell_items, (size_t)C * cap * 2))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cand, (size_t)C * cap * kCandCap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cand_count, (size_t)C * cap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_accepted, (size_t)C * cap * 4))) return rc;
+
+  QueryBuildParams qp{};
+  qp.th = prm->th;
+  qp.mono = 0;
+  qp.min_x = 0.f;  // zero distortion: mnMinX = 0, mnMaxX = cols (Frame.cc:155-158)
+  qp.min_y = 0.f;
+  qp.max_x = (float)w;
+  qp.max_y = (float)h;
+  for (int l = 0; l < ctx->cfg.orb_nlevels; ++l) qp.scale[l] = ctx->scale[l];
+  const float gw = (float)PSL_GRID_COLS / (qp.max_x - qp.min_x), gh = (float)PSL_GRID_ROWS / (qp.max_y - qp.min_y);
+  psl_match_params mp{0, prm->th_dist, prm->nn_ratio, prm->check_orientation};
+
+  for (int c0 = 0; c0 < B; c0 += C) {
+    const int nb = std::min(C, B - c0);
+    const size_t off = (size_t)c0 * cap;
+    e = prof_mark(ctx);
+    launch_query_build(d_kps, d_z, d_n, cap, d_Tcw, c0, *cam, qp, ctx->m_q.as<psl_proj_query>(), ctx->m_n.as<int32_t>(),
+                       nb, st);
+    prof_span(ctx, 6, e, 1);
+    MatchFrames F{d_kps + off, d_u_right + off, d_desc + off * 32, d_n + c0, cap, qp.min_x, qp.min_y, gw, gh};
+    // descriptors of the query side are those of frame b-1 in the same [B][cap] array
+    const uint8_t* qdesc = d_desc + ((ptrdiff_t)c0 - 1) * (ptrdiff_t)cap * 32;
+    MatchQueries Q{ctx->m_q.as<psl_proj_query>(), qdesc, ctx->m_n.as<int32_t>(), cap};
+    e = prof_mark(ctx);
+    launch_grid_build(F, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(), nb, st);
+    prof_span(ctx, 7, e, 1);
+    e = prof_mark(ctx);
+    launch_proj_candidates(F, Q, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(),
+                           ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->d_status, nb, st);
+    prof_span(ctx, 8, e, 1);
+    e = prof_mark(ctx);
+    launch_proj_resolve(F, Q, ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), nullptr, mp,
+                        ctx->m_accepted.as<uint32_t>(), d_assign + off, d_nmatches + c0, nb, st);
+    prof_span(ctx, 9, e, 1);
+  }
+  PSL_CK(cudaGetLastError());
+  return PSL_OK;
+}
+
+int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
+                        const float* Tcw, const psl_camera* cam, const psl_track_params* prm, psl_keypoint* kps,
+                        uint8_t* desc, int32_t* n, float* u_right, float* z, int32_t* assign, int32_t* nmatches,
+                        int32_t cap) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!gray || !depth || !Tcw || !kps || !desc || !n || !u_right || !z || !assign || !nmatches || B < 0 || w <= 0 ||
+      h <= 0 || cap < 1)
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const size_t px = (size_t)w * h, nk = (size_t)B * cap;
+  DevBuf* M = ctx->m_misc;
+  int rc;
+  if ((rc = ensure(ctx, M[0], px * B))) return rc;
+  if ((rc = ensure(ctx, M[1], px * B * 2))) return rc;
+  if ((rc = ensure(ctx, M[2], (size_t)B * 12 * 4))) return rc;
+  if ((rc = ensure(ctx, M[3], nk * sizeof(psl_keypoint)))) return rc;
+  if ((rc = ensure(ctx, M[4], nk * 32))) return rc;
+  if ((rc = ensure(ctx, M[5], (size_t)B * 8))) return rc;  // n | nmatches
+  if ((rc = ensure(ctx, M[6], nk * 4))) return rc;
+  if ((rc = ensure(ctx, M[7], nk * 4))) return rc;
+  if ((rc = ensure(ctx, M[8], nk * 4))) return rc;
+  cudaStream_t st = ctx->stream;
+  PSL_CK(cudaMemcpyAsync(M[0].p, gray, px * B, cudaMemcpyHostToDevice, st));
+  PSL_CK(cudaMemcpyAsync(M[1].p, depth, px * B * 2, cudaMemcpyHostToDevice, st));
+  PSL_CK(cudaMemcpyAsync(M[2].p, Tcw, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+  int32_t* d_n = M[5].as<int32_t>();
+  rc = psl_track_orb_batch_dev(ctx, M[0].as<uint8_t>(), w, (int64_t)px, M[1].as<uint16_t>(), w, (int64_t)px, B, w, h,
+                               M[2].as<float>(), cam, prm, M[3].as<psl_keypoint>(), M[4].as<uint8_t>(), d_n,
+                               M[6].as<float>(), M[7].as<float>(), M[8].as<int32_t>(), d_n + B, cap);
+  if (rc) return rc;
+  PSL_CK(cudaMemcpyAsync(kps, M[3].p, nk * sizeof(psl_keypoint), cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(desc, M[4].p, nk * 32, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(n, d_n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(nmatches, d_n + B, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(u_right, M[6].p, nk * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(z, M[7].p, nk * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(assign, M[8].p, nk * 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
+}  // extern "C"

@@ -41,7 +41,8 @@ class Context:
     def stream(self) -> int:
         return int(_lib.lib().psl_stream(self._h) or 0)
 
-    STAGES = ["pyramid", "fast", "octree", "blur", "describe"]
+    STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match_single", "stereo_queries", "grid",
+              "candidates", "resolve"]
 
     def profile(self, on: bool):
         self.check(_lib.lib().psl_profile_enable(self._h, int(on)))

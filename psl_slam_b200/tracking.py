@@ -1,0 +1,55 @@
+"""Batched point front end of one tracking step (psl_track_orb_batch): what Frame::Frame (ExtractORB +
+ComputeStereoFromRGBD, src/Frame.cc:133-210) and the SearchByProjection call of
+Tracking::TrackWithMotionModel (src/Tracking.cc:1193) do per frame, for a batch of consecutive RGB-D frames."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import KP_DTYPE, Camera, TrackParams
+from .orb import ORBextractor, _ptr
+
+
+def make_camera(fx, fy, cx, cy, bf, depth_map_factor=5000.0) -> Camera:
+    f = np.float32(1.0) / np.float32(depth_map_factor)  # Tracking.cc:142-145
+    return Camera(fx, fy, cx, cy, bf, float(f))
+
+
+def make_track_params(th=15.0, nn_ratio=0.9, check_orientation=True, th_dist=100) -> TrackParams:
+    return TrackParams(th, nn_ratio, int(check_orientation), th_dist)
+
+
+def pose_rows(Tcw: np.ndarray) -> np.ndarray:
+    """[B,4,4] or [B,3,4] poses -> contiguous float32 [B,12]."""
+    T = np.asarray(Tcw, np.float32)
+    return np.ascontiguousarray(T[:, :3, :4].reshape(len(T), 12))
+
+
+def track_orb_batch(ex: ORBextractor, gray: np.ndarray, depth: np.ndarray, Tcw: np.ndarray, cam: Camera,
+                    prm: TrackParams | None = None):
+    """HOST arrays in, host arrays out.  Returns dict(kps, desc, n, u_right, z, assign, nmatches)."""
+    prm = prm or make_track_params()
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    B, H, W = gray.shape
+    T = pose_rows(Tcw)
+    cap = ex.cap
+    out = dict(kps=np.zeros((B, cap), KP_DTYPE), desc=np.zeros((B, cap, 32), np.uint8), n=np.zeros(B, np.int32),
+               u_right=np.zeros((B, cap), np.float32), z=np.zeros((B, cap), np.float32),
+               assign=np.full((B, cap), -1, np.int32), nmatches=np.zeros(B, np.int32))
+    ex.ctx.check(_lib.lib().psl_track_orb_batch(ex.ctx.handle, _ptr(gray), _ptr(depth), B, W, H, _ptr(T),
+                                                C.addressof(cam), C.addressof(prm), _ptr(out["kps"]),
+                                                _ptr(out["desc"]), _ptr(out["n"]), _ptr(out["u_right"]),
+                                                _ptr(out["z"]), _ptr(out["assign"]), _ptr(out["nmatches"]), cap))
+    return out
+
+
+def track_orb_batch_dev(ex: ORBextractor, d_gray: int, d_depth: int, B: int, W: int, H: int, d_Tcw: int, cam: Camera,
+                        prm: TrackParams, d_kps: int, d_desc: int, d_n: int, d_u_right: int, d_z: int, d_assign: int,
+                        d_nmatches: int, cap: int):
+    """DEVICE pointers (tightly packed frames), asynchronous on the ctx stream."""
+    ex.ctx.check(_lib.lib().psl_track_orb_batch_dev(ex.ctx.handle, d_gray, W, W * H, d_depth, W, W * H, B, W, H,
+                                                    d_Tcw, C.addressof(cam), C.addressof(prm), d_kps, d_desc, d_n,
+                                                    d_u_right, d_z, d_assign, d_nmatches, cap))
