@@ -49,13 +49,33 @@ def algorithmic_bytes(w, h, nlevels, scale, nfeat):
         "octree": 2 * 4 * 10_000,                     # candidate keys in, selected keys out (L2)
         "blur": 2 * sum(P),                           # read + write every level
         "describe": 2 * nfeat * 961 + nfeat * 60,     # 31x31 patches (x2 images) + records
+        "match_single": 0,
+        "stereo_queries": nfeat * (28 + 2 + 8 + 28 + 4 + 32),  # kp + depth px + (uRight,z) ; kp + z -> query
+        "grid": nfeat * (28 + 2) + 3073 * 4,          # keypoints in, CSR out
+        "candidates": nfeat * 20 * 32 + nfeat * 64,   # ~20 candidate descriptors per query
+        "resolve": nfeat * 20 * 4 + nfeat * 4,        # candidate lists in, assignment out
     }
 
 
 def synth_frames(n_distinct, seed=4):
+    """n consecutive synthetic RGB-D frames (gray u8, depth u16) + world->camera poses [n,12] f32."""
     from psl_slam_b200 import synth
     gray, depth, T = synth.sequence(seed, n_distinct, W, H)
-    return gray
+    return gray, depth, np.ascontiguousarray(T.astype(np.float32)[:, :3, :4].reshape(n_distinct, 12))
+
+
+def cam6():
+    from psl_slam_b200 import synth
+    K = synth.ICL
+    return np.array([K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], np.float32(1.0) / np.float32(K["depth_factor"])],
+                    np.float32)
+
+
+def ping_pong(n_distinct, total):
+    """Index pattern 0,1,..,n-1,n-2,..,1,0,1,.. : every consecutive pair of the long batch is a real
+    consecutive pair of the short synthetic sequence (so SearchByProjection always has a valid prior)."""
+    period = list(range(n_distinct)) + list(range(n_distinct - 2, 0, -1))
+    return np.array([period[i % len(period)] for i in range(total)], np.int64)
 
 
 class ClockSampler(threading.Thread):
@@ -93,28 +113,34 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline(frames_u8: np.ndarray, budget_s: float = 12.0):
-    """The oracle (CPU port of the reference path) on a bounded sample, 1 thread and all threads."""
+def cpu_run(gray, depth, T12, nthreads):
+    from oracle import orc
+    p = orc.params(ORB["nfeatures"], ORB["scale"], ORB["nlevels"], ORB["ini"], ORB["mn"])
+    return orc.track_batch_mt(gray, depth, T12, cam6(), p, TRACK["th"], TRACK["nn_ratio"], TRACK["ori"], nthreads)
+
+
+def cpu_baseline(gray, depth, T12, budget_s: float = 14.0):
+    """The oracle (CPU port of the reference path: extract + stereo + SearchByProjection) on a bounded
+    sample of the same workload, 1 thread (how the reference runs, Frame.cc:179-180) and all threads."""
     from oracle import orc
     orc.build()
-    p = orc.params(ORB["nfeatures"], ORB["scale"], ORB["nlevels"], ORB["ini"], ORB["mn"])
     cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    orc.orb_extract_batch_mt(frames_u8[:2], p, 1)
-    t1 = (time.perf_counter() - t0) / 2
-    n1 = max(2, min(len(frames_u8), int(budget_s * 0.3 / t1)))
+    cpu_run(gray[:3], depth[:3], T12[:3], 1)
+    t1 = (time.perf_counter() - t0) / 3
+    n1 = max(3, min(len(gray), int(budget_s * 0.3 / t1)))
     t0 = time.perf_counter()
-    orc.orb_extract_batch_mt(frames_u8[:n1], p, 1)
+    cpu_run(gray[:n1], depth[:n1], T12[:n1], 1)
     fps1 = n1 / (time.perf_counter() - t0)
-    reps = max(1, int(budget_s * 0.7 * fps1 * cores * 0.7 / len(frames_u8)))
-    sample = np.concatenate([frames_u8] * reps) if reps > 1 else frames_u8
+    total = max(len(gray), int(budget_s * 0.7 * fps1 * cores * 0.6))
+    idx = ping_pong(len(gray), total)
+    g, d, t = gray[idx], depth[idx], T12[idx]
     t0 = time.perf_counter()
-    orc.orb_extract_batch_mt(sample, p, cores)
-    fpsN = len(sample) / (time.perf_counter() - t0)
-    return {"value": fpsN, "unit": "frames/s", "cores": cores, "kind": "port",
-            "value_1_thread": fps1,
-            "sample": f"{len(sample)} frames ORB extract on {cores} threads (one frame per task); "
-                      f"{n1} frames on 1 thread"}
+    cpu_run(g, d, t, cores)
+    fpsN = total / (time.perf_counter() - t0)
+    return {"value": fpsN, "unit": "frames/s", "cores": cores, "kind": "port", "value_1_thread": fps1,
+            "sample": f"{total} frames (extract + stereo + SearchByProjection vs previous frame) on {cores} threads, "
+                      f"one frame per task; {n1} frames on 1 thread"}
 
 
 def run_reference(args, rank, world):
@@ -123,16 +149,16 @@ def run_reference(args, rank, world):
         return
     from oracle import orc
     orc.build()
-    frames = synth_frames(8)
-    p = orc.params(ORB["nfeatures"], ORB["scale"], ORB["nlevels"], ORB["ini"], ORB["mn"])
+    gray, depth, T12 = synth_frames(8)
     cores = os.cpu_count() or 1
-    per_step = max(cores, 2 * cores)
-    batch = np.concatenate([frames] * ((per_step + len(frames) - 1) // len(frames)))[:per_step]
+    per_step = 4 * cores
+    idx = ping_pong(len(gray), per_step)
+    g, d, t = gray[idx], depth[idx], T12[idx]
     for _ in range(args.warmup):
-        orc.orb_extract_batch_mt(batch, p, cores)
+        cpu_run(g, d, t, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.orb_extract_batch_mt(batch, p, cores)
+        cpu_run(g, d, t, cores)
     dt = time.perf_counter() - t0
     fps = per_step * args.steps / dt
     out = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
@@ -147,11 +173,14 @@ def run_reference(args, rank, world):
 
 
 METRIC = "frames/s ORB+LSD/LBD extract+match @640x480"
+TRACK = dict(th=15.0, nn_ratio=0.9, ori=True)  # Tracking.cc:1166,1189
 
 
 def workload_config(frames_per_gpu):
-    return {"workload": "cfg1-batched: ORBextractor on synthetic 640x480 frames, TUM1.yaml settings "
-                        "(1000 features, 8 levels, 1.2, FAST 20/7); matching and line stages join as they land",
+    return {"workload": "cfg2-batched: full point front end per frame — ORBextractor (TUM1.yaml: 1000 features, "
+                        "8 levels, 1.2, FAST 20/7) + ComputeStereoFromRGBD + SearchByProjection(Cur, Last, th=15) "
+                        "between consecutive synthetic 640x480 RGB-D frames (ICL intrinsics); line stages "
+                        "(LSD/LBD) are not in the timed path yet",
             "frames_per_step_per_gpu": frames_per_gpu, "width": W, "height": H,
             "l2_policy": "inputs larger than L2 (frames_per_step x 307 KB >> 126 MB), no flush",
             "parallelism": "frames sharded across GPUs, no collective"}
@@ -190,19 +219,29 @@ def main():
     ex = ORBextractor(ORB["nfeatures"], ORB["scale"], ORB["nlevels"], ORB["ini"], ORB["mn"], device=local,
                       max_width=W, max_height=H, chunk_frames=args.chunk)
     cap = ex.cap
-    base = synth_frames(16, seed=4 + rank)                       # distinct synthetic frames per rank
-    d_base = torch.from_numpy(base).cuda()
-    idx = torch.arange(F, device="cuda") % d_base.shape[0]
-    d_gray = d_base[idx].contiguous()                            # [F,H,W] u8 resident in HBM
+    from psl_slam_b200 import make_camera, make_track_params, synth, track_orb_batch_dev
+    K = synth.ICL
+    cam = make_camera(K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], K["depth_factor"])
+    tprm = make_track_params(TRACK["th"], TRACK["nn_ratio"], TRACK["ori"])
+    base_g, base_d, base_T = synth_frames(16, seed=4 + rank)      # distinct synthetic sequence per rank
+    idx = torch.from_numpy(ping_pong(16, F)).cuda()
+    d_gray = torch.from_numpy(base_g).cuda()[idx].contiguous()    # [F,H,W] u8 resident in HBM
+    d_depth = torch.from_numpy(base_d.view(np.int16)).cuda()[idx].contiguous()  # u16 bits
+    d_T = torch.from_numpy(base_T).cuda()[idx].contiguous()
     d_kps = torch.empty((F, cap, 28), dtype=torch.uint8, device="cuda")
     d_desc = torch.empty((F, cap, 32), dtype=torch.uint8, device="cuda")
     d_n = torch.zeros(F, dtype=torch.int32, device="cuda")
+    d_ur = torch.empty((F, cap), dtype=torch.float32, device="cuda")
+    d_z = torch.empty((F, cap), dtype=torch.float32, device="cuda")
+    d_assign = torch.empty((F, cap), dtype=torch.int32, device="cuda")
+    d_nm = torch.zeros(F, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ex.ctx.stream(), device=local)
 
     def step_dev():
-        ex.extract_batch_dev(d_gray.data_ptr(), F, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(),
-                             d_n.data_ptr(), cap)
+        track_orb_batch_dev(ex, d_gray.data_ptr(), d_depth.data_ptr(), F, W, H, d_T.data_ptr(), cam, tprm,
+                            d_kps.data_ptr(), d_desc.data_ptr(), d_n.data_ptr(), d_ur.data_ptr(), d_z.data_ptr(),
+                            d_assign.data_ptr(), d_nm.data_ptr(), cap)
 
     def barrier():
         if world > 1:
@@ -215,6 +254,8 @@ def main():
     ex.ctx.sync()
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(2):  # keep the GPU under load while nvidia-smi starts sampling
+        step_dev()
     barrier()
     l0 = ex.ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,6 +273,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     n_kp = int(d_n.sum().item())
+    n_match = int(d_nm.sum().item())
     value = world * F * args.steps / (ms * 1e-3)
 
     # ---- per-stage pass (same steps, events between stages) -> roofline ----------------------
@@ -270,15 +312,27 @@ def main():
     import ctypes as C
 
     from psl_slam_b200 import _lib
-    h_gray = torch.empty((F, H, W), dtype=torch.uint8, pin_memory=True)
+    pin = dict(pin_memory=True)
+    h_gray = torch.empty((F, H, W), dtype=torch.uint8, **pin)
     h_gray.copy_(d_gray.cpu())
-    h_kps = torch.empty((F, cap, 28), dtype=torch.uint8, pin_memory=True)
-    h_desc = torch.empty((F, cap, 32), dtype=torch.uint8, pin_memory=True)
-    h_n = torch.empty(F, dtype=torch.int32, pin_memory=True)
+    h_depth = torch.empty((F, H, W), dtype=torch.int16, **pin)
+    h_depth.copy_(d_depth.cpu())
+    h_T = torch.empty((F, 12), dtype=torch.float32, **pin)
+    h_T.copy_(d_T.cpu())
+    h_kps = torch.empty((F, cap, 28), dtype=torch.uint8, **pin)
+    h_desc = torch.empty((F, cap, 32), dtype=torch.uint8, **pin)
+    h_n = torch.empty(F, dtype=torch.int32, **pin)
+    h_nm = torch.empty(F, dtype=torch.int32, **pin)
+    h_ur = torch.empty((F, cap), dtype=torch.float32, **pin)
+    h_z = torch.empty((F, cap), dtype=torch.float32, **pin)
+    h_assign = torch.empty((F, cap), dtype=torch.int32, **pin)
 
     def step_host():
-        ex.ctx.check(_lib.lib().psl_orb_extract_batch(ex.ctx.handle, h_gray.data_ptr(), F, W, H, W, W * H,
-                                                      h_kps.data_ptr(), h_desc.data_ptr(), cap, h_n.data_ptr()))
+        ex.ctx.check(_lib.lib().psl_track_orb_batch(ex.ctx.handle, h_gray.data_ptr(), h_depth.data_ptr(), F, W, H,
+                                                    h_T.data_ptr(), C.addressof(cam), C.addressof(tprm),
+                                                    h_kps.data_ptr(), h_desc.data_ptr(), h_n.data_ptr(),
+                                                    h_ur.data_ptr(), h_z.data_ptr(), h_assign.data_ptr(),
+                                                    h_nm.data_ptr(), cap))
 
     for _ in range(2):
         step_host()
@@ -293,13 +347,13 @@ def main():
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    e2e = {"value": world * F * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": F * W * H,
-           "d2h_bytes_per_step": F * (cap * 60 + 4), "steps": e2e_steps,
-           "keypoints_checked": int(h_n.sum().item()) == n_kp}
+    e2e = {"value": world * F * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": F * (W * H * 3 + 48),
+           "d2h_bytes_per_step": F * (cap * (28 + 32 + 12) + 8), "steps": e2e_steps,
+           "results_equal_device_path": int(h_n.sum().item()) == n_kp and int(h_nm.sum().item()) == n_match}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(base)
+        cpu = cpu_baseline(base_g, base_d, base_T)
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -307,7 +361,7 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": workload_config(F), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
-               "keypoints_per_frame": n_kp / F}
+               "keypoints_per_frame": n_kp / F, "matches_per_frame": n_match / max(F - 1, 1)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

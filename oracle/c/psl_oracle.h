@@ -71,6 +71,10 @@ void orc_queries_from_last_frame(const psl_keypoint* kps_last, const float* z_la
 int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
                              int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor);
 
+int orc_track_batch_mt(const orc_orb_params* p, const uint8_t* gray, const uint16_t* depth, int B, int w, int h,
+                       const float* Tcw, const float* cam, float th, float nn_ratio, int check_ori, int nthreads,
+                       int32_t* n_out, int32_t* nmatches_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,3 +219,21 @@ def queries_from_last_frame(kps_last, z_last, Tcw_last, Tcw_cur, cam, scale_fact
                                       C.c_float(th), int(mono), C.c_float(bounds[0]), C.c_float(bounds[1]),
                                       C.c_float(bounds[2]), C.c_float(bounds[3]), _p(q))
     return q
+
+
+def track_batch_mt(gray, depth, Tcw12, cam6, p: OrbParams | None = None, th=15.0, nn_ratio=0.9, check_ori=True,
+                   nthreads=1):
+    """CPU-baseline harness for the point front end (extract + stereo + SearchByProjection vs previous frame)."""
+    p = p or params()
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    T = np.ascontiguousarray(Tcw12, np.float32)
+    cam = np.ascontiguousarray(cam6, np.float32)
+    B, H, W = gray.shape
+    n = np.zeros(B, np.int32)
+    nm = np.zeros(B, np.int32)
+    rc = lib().orc_track_batch_mt(C.byref(p), _p(gray), _p(depth), B, W, H, _p(T), _p(cam), C.c_float(th),
+                                  C.c_float(nn_ratio), int(check_ori), nthreads, _p(n), _p(nm))
+    if rc != 0:
+        raise RuntimeError("orc_track_batch_mt failed")
+    return n, nm

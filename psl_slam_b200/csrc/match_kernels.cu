@@ -129,14 +129,16 @@ constexpr int kCandWarps = 8;
 __global__ void __launch_bounds__(kCandWarps * 32)
     proj_candidates_kernel(MatchFrames f, MatchQueries qs, const int32_t* __restrict__ cell_start,
                            const uint16_t* __restrict__ cell_items, uint32_t* __restrict__ cand,
-                           int32_t* __restrict__ cand_count, uint32_t* __restrict__ status) {
+                           int32_t* __restrict__ cand_count, uint2* __restrict__ cand_best,
+                           uint32_t* __restrict__ status) {
   const int lane = threadIdx.x & 31, b = blockIdx.y;
   const int qi = blockIdx.x * kCandWarps + (threadIdx.x >> 5);
   if (qi >= qs.nq[b]) return;
   const psl_proj_query Q = qs.q[(size_t)b * qs.cap + qi];
   int32_t* out_count = cand_count + (size_t)b * qs.cap + qi;
+  uint2* out_best = cand_best + (size_t)b * qs.cap + qi;
   if (!(Q.flags & PSL_Q_VALID)) {
-    if (lane == 0) *out_count = 0;
+    if (lane == 0) { *out_count = 0; *out_best = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
     return;
   }
   const float x = Q.u, y = Q.v, r = Q.radius;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(kCandWarps * 32)
   const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dym, r), f.grid_h_inv)));
   const int r1 = min(PSL_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.grid_h_inv)));
   if (c0 >= PSL_GRID_COLS || c1 < 0 || r0 >= PSL_GRID_ROWS || r1 < 0) {
-    if (lane == 0) *out_count = 0;
+    if (lane == 0) { *out_count = 0; *out_best = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); }
     return;
   }
   const bool check_levels = (Q.min_level > 0) || (Q.max_level >= 0);
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(kCandWarps * 32)
 
   const int ncy = r1 - r0 + 1, ncells = (c1 - c0 + 1) * ncy;
   int total = 0;
+  unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;  // two smallest (dist << 16 | position) seen by this lane
   for (int base = 0; base < ncells; base += 32) {
     const int c = base + lane;
     int s = 0, e = 0;
@@ -197,23 +200,31 @@ __global__ void __launch_bounds__(kCandWarps * 32)
       if (!passes(i)) continue;
       if (pos < kCandCap) {
         const uint4 d0 = __ldg(fdesc + 2 * i), d1 = __ldg(fdesc + 2 * i + 1);
-        out[pos] = ((uint32_t)i << 16) | (uint32_t)hamming256(q0, q1, d0, d1);
+        const unsigned dist = (unsigned)hamming256(q0, q1, d0, d1);
+        out[pos] = ((uint32_t)i << 16) | dist;
+        const unsigned key = (dist << 16) | (unsigned)pos;
+        if (key < k1) { k2 = k1; k1 = key; }
+        else if (key < k2) k2 = key;
       }
       ++pos;
     }
     total += __shfl_sync(0xffffffffu, inc, 31);
   }
+  const unsigned best = warp_min_u32(k1);
+  const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
   if (lane == 0) {
     *out_count = min(total, kCandCap);
+    *out_best = make_uint2(best, second);
     if (total > kCandCap) atomicOr(status, kStatCandOverflow);
   }
 }
 
 void launch_proj_candidates(const MatchFrames& f, const MatchQueries& q, const int32_t* cell_start,
-                            const uint16_t* cell_items, uint32_t* cand, int32_t* cand_count, uint32_t* status, int B,
-                            cudaStream_t st) {
+                            const uint16_t* cell_items, uint32_t* cand, int32_t* cand_count, uint2* cand_best,
+                            uint32_t* status, int B, cudaStream_t st) {
   dim3 grid((q.cap + kCandWarps - 1) / kCandWarps, B);
-  proj_candidates_kernel<<<grid, kCandWarps * 32, 0, st>>>(f, q, cell_start, cell_items, cand, cand_count, status);
+  proj_candidates_kernel<<<grid, kCandWarps * 32, 0, st>>>(f, q, cell_start, cell_items, cand, cand_count, cand_best,
+                                                           status);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,8 +234,9 @@ void launch_proj_candidates(const MatchFrames& f, const MatchQueries& q, const i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
     proj_resolve_kernel(MatchFrames f, MatchQueries qs, const uint32_t* __restrict__ cand,
-                        const int32_t* __restrict__ cand_count, const uint8_t* __restrict__ claimed_in,
-                        psl_match_params prm, uint32_t* __restrict__ accepted_scratch, int32_t* __restrict__ assign_out,
+                        const int32_t* __restrict__ cand_count, const uint2* __restrict__ cand_best,
+                        const uint8_t* __restrict__ claimed_in, psl_match_params prm,
+                        uint32_t* __restrict__ accepted_scratch, int32_t* __restrict__ assign_out,
                         int32_t* __restrict__ nmatches) {
   extern __shared__ uint8_t s_claimed[];
   __shared__ int s_hist[32];
@@ -232,57 +244,81 @@ __global__ void __launch_bounds__(32)
   const int n = f.n[b], nq = qs.nq[b];
   int32_t* assign = assign_out + (size_t)b * f.cap;
   const psl_keypoint* kps = f.kps + (size_t)b * f.cap;
-  uint32_t* accepted = accepted_scratch + (size_t)b * qs.cap;
+  uint32_t* accepted = accepted_scratch + (size_t)b * qs.cap;  // (query << 16 | keypoint) of accepted matches
   for (int i = lane; i < n; i += 32) {
     s_claimed[i] = claimed_in ? claimed_in[(size_t)b * f.cap + i] : 0;
     assign[i] = -1;
   }
   s_hist[lane] = 0;
   __syncwarp();
-  int nm = 0, nacc = 0;
-  const bool hist_on = prm.mode == 0 && prm.check_orientation;
-  for (int q = 0; q < nq; ++q) {
-    const int cnt = cand_count[(size_t)b * qs.cap + q];
-    if (cnt == 0) continue;
-    const uint32_t* cl = cand + ((size_t)b * qs.cap + q) * kCandCap;
-    // two lexicographically smallest (dist, position) among unclaimed candidates
-    unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-    for (int k = lane; k < cnt; k += 32) {
-      const uint32_t e = cl[k];
-      if (s_claimed[e >> 16]) continue;
-      const unsigned key = ((e & 0xFFFFu) << 16) | (unsigned)k;
-      if (key < k1) { k2 = k1; k1 = key; }
-      else if (key < k2) k2 = key;
+  int nacc = 0;
+  for (int base = 0; base < nq; base += 32) {
+    // 32 queries at a time: every lane preloads one query's unconstrained best/second and its flags
+    const int ql = base + lane;
+    uint2 bs = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    unsigned bidx = 0, sidx = 0, claims = 0;
+    if (ql < nq) {
+      bs = cand_best[(size_t)b * qs.cap + ql];
+      const uint32_t* cl = cand + ((size_t)b * qs.cap + ql) * kCandCap;
+      if (bs.x != 0xFFFFFFFFu) bidx = cl[bs.x & 0xFFFFu] >> 16;
+      if (bs.y != 0xFFFFFFFFu) sidx = cl[bs.y & 0xFFFFu] >> 16;
+      claims = (qs.q[(size_t)b * qs.cap + ql].flags & PSL_Q_CLAIMS) ? 1u : 0u;
     }
-    const unsigned best = warp_min_u32(k1);
-    if (best == 0xFFFFFFFFu) continue;
-    const int bestDist = (int)(best >> 16);
-    if (bestDist > prm.th_dist) continue;
-    const int bestIdx = (int)(cl[best & 0xFFFFu] >> 16);
-    if (prm.mode == 1) {
-      const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
-      if (second != 0xFFFFFFFFu) {
+    const int lim = min(32, nq - base);
+    for (int j = 0; j < lim; ++j) {
+      unsigned best = __shfl_sync(0xffffffffu, bs.x, j);
+      if (best == 0xFFFFFFFFu) continue;  // invalid query or empty window
+      unsigned second = __shfl_sync(0xffffffffu, bs.y, j);
+      unsigned bi = __shfl_sync(0xffffffffu, bidx, j), si = __shfl_sync(0xffffffffu, sidx, j);
+      const unsigned cf = __shfl_sync(0xffffffffu, claims, j);
+      const int q = base + j;
+      const uint32_t* cl = cand + ((size_t)b * qs.cap + q) * kCandCap;
+      // the precomputed pair is still right unless one of the two keypoints was claimed meanwhile
+      const bool stale = s_claimed[bi] || (prm.mode == 1 && second != 0xFFFFFFFFu && s_claimed[si]);
+      if (stale) {
+        const int cnt = cand_count[(size_t)b * qs.cap + q];
+        unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        for (int k = lane; k < cnt; k += 32) {
+          const uint32_t e = cl[k];
+          if (s_claimed[e >> 16]) continue;
+          const unsigned key = ((e & 0xFFFFu) << 16) | (unsigned)k;
+          if (key < k1) { k2 = k1; k1 = key; }
+          else if (key < k2) k2 = key;
+        }
+        best = warp_min_u32(k1);
+        if (best == 0xFFFFFFFFu) continue;
+        second = warp_min_u32(k1 == best ? k2 : k1);
+        bi = cl[best & 0xFFFFu] >> 16;
+        if (second != 0xFFFFFFFFu) si = cl[second & 0xFFFFu] >> 16;
+      }
+      const int bestDist = (int)(best >> 16);
+      if (bestDist > prm.th_dist) continue;
+      if (prm.mode == 1 && second != 0xFFFFFFFFu) {
+        // ratio test only when best and second live on the same pyramid level (:118-119); with no second
+        // candidate bestLevel2 = -1 never equals a real level (:76-79)
         const int d2 = (int)(second >> 16);
-        const int l1 = kps[bestIdx].octave, l2 = kps[cl[second & 0xFFFFu] >> 16].octave;
-        if (l1 == l2 && (float)bestDist > __fmul_rn(prm.nn_ratio, (float)d2)) continue;  // :118-119
+        if (kps[bi].octave == kps[si].octave && (float)bestDist > __fmul_rn(prm.nn_ratio, (float)d2)) continue;
       }
-      // no second candidate: bestLevel2 = -1 never equals a real level, bestDist2 = 256 (:76-79)
-    }
-    const psl_proj_query Q = qs.q[(size_t)b * qs.cap + q];
-    if (lane == 0) {
-      assign[bestIdx] = q;
-      s_claimed[bestIdx] = (Q.flags & PSL_Q_CLAIMS) ? 1 : 0;
-      if (hist_on) {
-        const int bin = rot_bin(Q.angle, kps[bestIdx].angle);
-        s_hist[bin]++;
-        accepted[nacc] = ((uint32_t)bestIdx << 8) | (uint32_t)bin;
+      if (lane == 0) {
+        assign[bi] = q;
+        s_claimed[bi] = (uint8_t)cf;
+        accepted[nacc] = ((uint32_t)q << 16) | bi;
       }
+      ++nacc;
+      __syncwarp();
     }
-    ++nm;
-    ++nacc;
-    __syncwarp();
   }
-  if (hist_on) {
+  int nm = nacc;
+  if (prm.mode == 0 && prm.check_orientation) {
+    // rotation histogram of the accepted matches (:1431-1441), then keep the three best bins (:1447-1467)
+    __syncwarp();
+    for (int k = lane; k < nacc; k += 32) {
+      const uint32_t e = accepted[k];
+      const int bin = rot_bin(qs.q[(size_t)b * qs.cap + (e >> 16)].angle, kps[e & 0xFFFFu].angle);
+      atomicAdd(&s_hist[bin], 1);
+      accepted[k] = ((e & 0xFFFFu) << 8) | (uint32_t)bin;
+    }
+    __syncwarp();
     int i1, i2, i3;
     three_maxima(s_hist, i1, i2, i3);
     int dropped = 0;
@@ -302,10 +338,10 @@ __global__ void __launch_bounds__(32)
 }
 
 void launch_proj_resolve(const MatchFrames& f, const MatchQueries& q, const uint32_t* cand, const int32_t* cand_count,
-                         const uint8_t* claimed_in, psl_match_params prm, uint32_t* accepted_scratch, int32_t* assign,
-                         int32_t* nmatches, int B, cudaStream_t st) {
-  proj_resolve_kernel<<<B, 32, (size_t)f.cap, st>>>(f, q, cand, cand_count, claimed_in, prm, accepted_scratch, assign,
-                                                    nmatches);
+                         const uint2* cand_best, const uint8_t* claimed_in, psl_match_params prm,
+                         uint32_t* accepted_scratch, int32_t* assign, int32_t* nmatches, int B, cudaStream_t st) {
+  proj_resolve_kernel<<<B, 32, (size_t)f.cap, st>>>(f, q, cand, cand_count, cand_best, claimed_in, prm,
+                                                    accepted_scratch, assign, nmatches);
 }
 
 // ---------------------------------------------------------------------------------------------

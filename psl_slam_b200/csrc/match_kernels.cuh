@@ -28,15 +28,16 @@ struct MatchQueries {
 // per-frame CSR of the 64x48 feature grid: start[B][3073], items[B][cap]
 void launch_grid_build(const MatchFrames& f, int32_t* cell_start, uint16_t* cell_items, int B, cudaStream_t st);
 
-// ordered candidate lists with distances: cand[B][qcap][kCandCap] = idx<<16 | dist, count[B][qcap]
+// ordered candidate lists with distances: cand[B][qcap][kCandCap] = idx<<16 | dist, count[B][qcap];
+// best[B][qcap] = the two lexicographically smallest (dist<<16 | position) of each list (0xFFFFFFFF = none)
 void launch_proj_candidates(const MatchFrames& f, const MatchQueries& q, const int32_t* cell_start,
-                            const uint16_t* cell_items, uint32_t* cand, int32_t* cand_count, uint32_t* status, int B,
-                            cudaStream_t st);
+                            const uint16_t* cell_items, uint32_t* cand, int32_t* cand_count, uint2* cand_best,
+                            uint32_t* status, int B, cudaStream_t st);
 
 // ordered greedy resolve + rotation-histogram filter; claimed_in may be null
 void launch_proj_resolve(const MatchFrames& f, const MatchQueries& q, const uint32_t* cand, const int32_t* cand_count,
-                         const uint8_t* claimed_in, psl_match_params prm, uint32_t* accepted_scratch, int32_t* assign,
-                         int32_t* nmatches, int B, cudaStream_t st);
+                         const uint2* cand_best, const uint8_t* claimed_in, psl_match_params prm,
+                         uint32_t* accepted_scratch, int32_t* assign, int32_t* nmatches, int B, cudaStream_t st);
 
 void launch_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int32_t* dist, cudaStream_t st);
 void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx, int32_t* dist, cudaStream_t st);

@@ -302,7 +302,7 @@ void psl_destroy(psl_ctx* ctx) {
   cudaFree(ctx->d_desc);
   cudaFree(ctx->d_n);
   for (DevBuf* b : {&ctx->m_kps, &ctx->m_ur, &ctx->m_desc, &ctx->m_q, &ctx->m_qdesc, &ctx->m_claimed, &ctx->m_n,
-                    &ctx->m_cell_start, &ctx->m_cell_items, &ctx->m_cand, &ctx->m_cand_count, &ctx->m_accepted,
+                    &ctx->m_cell_start, &ctx->m_cell_items, &ctx->m_cand, &ctx->m_cand_count, &ctx->m_best, &ctx->m_accepted,
                     &ctx->m_assign, &ctx->m_nm})
     cudaFree(b->p);
   for (DevBuf& b : ctx->m_misc) cudaFree(b.p);

@@ -79,6 +79,7 @@ int psl_match_projection(psl_ctx* ctx, const psl_frame_view* fv, const psl_proj_
   if ((rc = ensure(ctx, ctx->m_cell_items, (size_t)ncap * 2))) return rc;
   if ((rc = ensure(ctx, ctx->m_cand, (size_t)qcap * kCandCap * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_cand_count, (size_t)qcap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_best, (size_t)qcap * 8))) return rc;
   if ((rc = ensure(ctx, ctx->m_accepted, (size_t)qcap * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_assign, (size_t)ncap * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_nm, 4))) return rc;
@@ -88,8 +89,9 @@ int psl_match_projection(psl_ctx* ctx, const psl_frame_view* fv, const psl_proj_
   size_t e = prof_mark(ctx);
   launch_grid_build(F, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(), 1, ctx->stream);
   launch_proj_candidates(F, Q, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(),
-                         ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->d_status, 1, ctx->stream);
-  launch_proj_resolve(F, Q, ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(),
+                         ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->m_best.as<uint2>(),
+                         ctx->d_status, 1, ctx->stream);
+  launch_proj_resolve(F, Q, ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->m_best.as<uint2>(),
                       claimed_in ? ctx->m_claimed.as<uint8_t>() : nullptr, *prm, ctx->m_accepted.as<uint32_t>(),
                       ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, ctx->stream);
   prof_span(ctx, 5, e, 3);

@@ -29,13 +29,16 @@ int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_st
                 d_z, B, st);
   prof_span(ctx, 6, e, 1);
 
-  const int C = ctx->chunk;
+  // The matching kernels are latency-bound per frame (one warp walks a frame's queries in order), so they
+  // run over many more frames per launch than the L2-sized extraction chunks.
+  const int C = std::min(B, 1024);
   if ((rc = ensure(ctx, ctx->m_q, (size_t)C * cap * sizeof(psl_proj_query)))) return rc;
   if ((rc = ensure(ctx, ctx->m_n, (size_t)C * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_cell_start, (size_t)C * (kGridCells + 1) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_cell_items, (size_t)C * cap * 2))) return rc;
   if ((rc = ensure(ctx, ctx->m_cand, (size_t)C * cap * kCandCap * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_cand_count, (size_t)C * cap * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_best, (size_t)C * cap * 8))) return rc;
   if ((rc = ensure(ctx, ctx->m_accepted, (size_t)C * cap * 4))) return rc;
 
   QueryBuildParams qp{};
@@ -65,10 +68,12 @@ int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_st
     prof_span(ctx, 7, e, 1);
     e = prof_mark(ctx);
     launch_proj_candidates(F, Q, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(),
-                           ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->d_status, nb, st);
+                           ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->m_best.as<uint2>(),
+                         ctx->d_status, nb, st);
     prof_span(ctx, 8, e, 1);
     e = prof_mark(ctx);
-    launch_proj_resolve(F, Q, ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), nullptr, mp,
+    launch_proj_resolve(F, Q, ctx->m_cand.as<uint32_t>(), ctx->m_cand_count.as<int32_t>(), ctx->m_best.as<uint2>(),
+                        nullptr, mp,
                         ctx->m_accepted.as<uint32_t>(), d_assign + off, d_nmatches + c0, nb, st);
     prof_span(ctx, 9, e, 1);
   }
