@@ -10,27 +10,23 @@
 //   * NMS keeps p iff score(p) > score(q) for the 8 neighbours q inside the interior that are
 //     corners; since sub-threshold neighbours have score < t <= score(p), the NMS verdict does
 //     not depend on t either.
-// So one CTA per cell computes the score map once, takes the NMS verdict once, and applies the
-// ini/min fallback by counting.  Output order is raster inside the cell (prefix sum, no
-// atomics inside a cell); cells are stitched in row-major order later by K3.
+// One CTA per cell: (A) a two-pair compass reject compacts the pixels that can be corners,
+// (B) their exact scores are computed two pixels per thread on packed u16x2 min/max,
+// (C) NMS runs over the survivors only and marks two bitmaps (>= iniTh, >= minTh), and
+// (D) the ini/min fallback is a count, the raster-ordered output a popc prefix sum over the
+// bitmap words.  Cells are stitched in row-major order later by K3.
 #include "orb_fast_score.cuh"
 #include "orb_kernels.cuh"
 
 namespace psl {
 
 constexpr int kFastThreads = 128;
-constexpr int kTilePitch = 72;      // >= kMaxCellDim, multiple of 4
-constexpr int kInteriorMax = 60;    // kMaxCellDim - 6
+constexpr int kTilePitch = 72;     // bytes per tile row (>= kMaxCellDim + 3 alignment slack, multiple of 4)
+constexpr int kTileWords = kTilePitch / 4;
+constexpr int kInteriorMax = 60;   // kMaxCellDim - 6
+constexpr int kMaxWords = (kInteriorMax * kInteriorMax + 31) / 32;  // bitmap words (113 <= threads)
 
-__device__ __forceinline__ bool has_run9(uint32_t m16) {
-  uint32_t m = m16 | (m16 << 16);
-  uint32_t r = m & (m >> 1);
-  r &= r >> 2;
-  r &= r >> 4;       // runs of 8
-  r &= m >> 8;       // runs of 9
-  return (r & 0xFFFFu) != 0;
-}
-
+template <bool ALIGNED>
 __global__ void __launch_bounds__(kFastThreads)
     fast_cells_kernel(const OrbGeometry* __restrict__ geo, ImgBatch in0, int ini_th, int min_th,
                       uint32_t* __restrict__ pool, int pool_cap, uint32_t* __restrict__ pool_count,
@@ -38,12 +34,12 @@ __global__ void __launch_bounds__(kFastThreads)
   __shared__ __align__(16) uint8_t s_tile[kMaxCellDim][kTilePitch];
   __shared__ __align__(16) uint8_t s_score[kInteriorMax + 2][kInteriorMax + 4];  // 1-px zero rim for the NMS
   __shared__ uint16_t s_list[kInteriorMax * kInteriorMax];
+  __shared__ uint32_t s_keep[2][kMaxWords];
   __shared__ int s_nlist;
   __shared__ int s_warp[2][kFastThreads / 32];
   __shared__ uint32_t s_base;
 
   const int cell = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  // locate the level of this cell
   int lvl = 0;
   const int nl = geo->nlevels;
   for (int l = 1; l < nl; ++l)
@@ -68,6 +64,11 @@ __global__ void __launch_bounds__(kFastThreads)
     if (tid == 0) *tab = make_uint2(0u, 0u);
     return;
   }
+  const int npx = iw * ih;
+  // i / d for i < 2^13, d <= 72 without an integer divide: the true quotient (i + 0.5) / d is at least
+  // 0.5 / d away from an integer, far more than the fp32 rounding error of the product.
+  const float rcp_iw = __frcp_rn((float)iw);
+#define PSL_DIV(i, rcp) ((int)(((float)(i) + 0.5f) * (rcp)))
 
   const uint8_t* __restrict__ img;
   int pitch;
@@ -78,80 +79,82 @@ __global__ void __launch_bounds__(kFastThreads)
     img = geo->level[lvl].ptr + (size_t)b * geo->level[lvl].frame_stride;
     pitch = geo->level[lvl].pitch;
   }
-
-  for (int i = tid; i < tw * th; i += kFastThreads) {
-    const int y = i / tw, x = i - y * tw;
-    s_tile[y][x] = __ldg(img + (size_t)(iniY + y) * pitch + iniX + x);
+  // Tile load.  ALIGNED: rows are 4-byte aligned -> whole words starting at iniX rounded down; the tile
+  // keeps that left slack (ax) so that shared and global addresses stay word-congruent.
+  const int ax = ALIGNED ? (iniX & 3) : 0;
+  if (ALIGNED) {
+    const int nw = (tw + ax + 3) >> 2;
+    const float rcp_nw = __frcp_rn((float)nw);
+    const uint8_t* src = img + (size_t)iniY * pitch + (iniX - ax);
+    for (int i = tid; i < nw * th; i += kFastThreads) {
+      const int y = PSL_DIV(i, rcp_nw), x = i - y * nw;
+      reinterpret_cast<uint32_t*>(&s_tile[y][0])[x] = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)y * pitch) + x);
+    }
+  } else {
+    const float rcp_tw = __frcp_rn((float)tw);
+    for (int i = tid; i < tw * th; i += kFastThreads) {
+      const int y = PSL_DIV(i, rcp_tw), x = i - y * tw;
+      s_tile[y][x] = __ldg(img + (size_t)(iniY + y) * pitch + iniX + x);
+    }
   }
   for (int i = tid; i < (kInteriorMax + 2) * (kInteriorMax + 4) / 4; i += kFastThreads)
     reinterpret_cast<uint32_t*>(&s_score[0][0])[i] = 0u;
+  if (tid < kMaxWords) { s_keep[0][tid] = 0u; s_keep[1][tid] = 0u; }
   if (tid == 0) s_nlist = 0;
   __syncthreads();
 
-  // ---- pass A: corner test at the lower threshold, compact the few survivors ----------------
+  // ---- A: compass reject.  Any 9-arc contains one pixel of each antipodal pair, so a corner needs
+  // (p0 or p8) and (p4 or p12) outside [v-t, v+t].  Compared on pixel values, never on differences
+  // (nvcc 12.9 mis-packs min/max/abs of u8 differences for sm_100a).
   const int t_lo = min(ini_th, min_th);
-  for (int i = tid; i < iw * ih; i += kFastThreads) {
-    const int y = i / iw, x = i - y * iw;
-    const uint8_t* c = &s_tile[y + 3][x + 3];
-    const int v = *c;
-    // Any 9-arc contains one pixel of each antipodal pair: two cheap rejects.  (Compared on the
-    // pixel values, not on differences: nvcc 12.9 packs min/max/abs of u8 differences into
-    // unsigned 16-bit SIMD for sm_100a and gets negative differences wrong — see DESIGN.md.)
-    const int hi = v + t_lo, lo = v - t_lo;
+  for (int i = tid; i < npx; i += kFastThreads) {
+    const int y = PSL_DIV(i, rcp_iw), x = i - y * iw;
+    const uint8_t* c = &s_tile[y + 3][x + 3 + ax];
+    const int v = *c, hi = v + t_lo, lo = v - t_lo;
     const int q0 = c[3 * kTilePitch], q8 = c[-3 * kTilePitch];
     if (q0 >= lo && q0 <= hi && q8 >= lo && q8 <= hi) continue;
     const int q4 = c[3], q12 = c[-3];
     if (q4 >= lo && q4 <= hi && q12 >= lo && q12 <= hi) continue;
-    uint32_t mb = 0, md = 0;  // circle pixels darker than v - t (d > t)  /  brighter than v + t
-#define PSL_CIRC(k, dx, dy)                                  \
-  {                                                          \
-    const int pv = c[(dy) * kTilePitch + (dx)];              \
-    mb |= (pv < lo ? 1u : 0u) << (k);                        \
-    md |= (pv > hi ? 1u : 0u) << (k);                        \
-  }
-    PSL_CIRC(0, 0, 3) PSL_CIRC(1, 1, 3) PSL_CIRC(2, 2, 2) PSL_CIRC(3, 3, 1) PSL_CIRC(4, 3, 0) PSL_CIRC(5, 3, -1)
-    PSL_CIRC(6, 2, -2) PSL_CIRC(7, 1, -3) PSL_CIRC(8, 0, -3) PSL_CIRC(9, -1, -3) PSL_CIRC(10, -2, -2)
-    PSL_CIRC(11, -3, -1) PSL_CIRC(12, -3, 0) PSL_CIRC(13, -3, 1) PSL_CIRC(14, -2, 2) PSL_CIRC(15, -1, 3)
-#undef PSL_CIRC
-    if (has_run9(mb) || has_run9(md)) s_list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
+    s_list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
   }
   __syncthreads();
 
-  // ---- pass B: exact scores of the survivors (dense, no divergence) -------------------------
+  // ---- B: exact scores, two survivors per thread on u16x2 lanes -----------------------------------
   const int nlist = s_nlist;
+  for (int k = 2 * tid; k < nlist; k += 2 * kFastThreads) {
+    const int ia = s_list[k], ib = s_list[min(k + 1, nlist - 1)];
+    const int ya = PSL_DIV(ia, rcp_iw), xa = ia - ya * iw;
+    const int yb = PSL_DIV(ib, rcp_iw), xb = ib - yb * iw;
+    const unsigned sc = fast_score_pair<kTilePitch>(&s_tile[ya + 3][xa + 3 + ax], &s_tile[yb + 3][xb + 3 + ax]);
+    const unsigned sa = sc & 0xFFFFu, sb = sc >> 16;
+    s_score[ya + 1][xa + 1] = (uint8_t)(sa >= (unsigned)t_lo ? sa : 0u);
+    s_score[yb + 1][xb + 1] = (uint8_t)(sb >= (unsigned)t_lo ? sb : 0u);
+  }
+  __syncthreads();
+
+  // ---- C: NMS over the survivors, two keep-bitmaps ----------------------------------------------------
   for (int k = tid; k < nlist; k += kFastThreads) {
     const int i = s_list[k];
-    const int y = i / iw, x = i - y * iw;
-    const uint8_t* c = &s_tile[y + 3][x + 3];
-    s_score[y + 1][x + 1] = (uint8_t)fast_score_at<kTilePitch>(c);
+    const int y = PSL_DIV(i, rcp_iw), x = i - y * iw;
+    const unsigned s = s_score[y + 1][x + 1];
+    if (!s) continue;
+    const uint8_t* r0 = &s_score[y][x];
+    const uint8_t* r1 = &s_score[y + 1][x];
+    const uint8_t* r2 = &s_score[y + 2][x];
+    const unsigned m = max(max(max((unsigned)r0[0], (unsigned)r0[1]), max((unsigned)r0[2], (unsigned)r1[0])),
+                           max(max((unsigned)r1[2], (unsigned)r2[0]), max((unsigned)r2[1], (unsigned)r2[2])));
+    if (s > m) {
+      if (s >= (unsigned)ini_th) atomicOr(&s_keep[0][i >> 5], 1u << (i & 31));
+      if (s >= (unsigned)min_th) atomicOr(&s_keep[1][i >> 5], 1u << (i & 31));
+    }
   }
   __syncthreads();
 
-  // ---- NMS + threshold fallback + raster-ordered compaction ---------------------------------
-  const int npx = iw * ih;
-  const int run = (npx + kFastThreads - 1) / kFastThreads;  // <= 29
-  const int p0 = tid * run, p1 = min(p0 + run, npx);
-  uint32_t keep_ini = 0, keep_lo = 0;
-  {
-    int y = p0 / iw, x = p0 - y * iw;
-    for (int p = p0; p < p1; ++p) {
-      const int s = s_score[y + 1][x + 1];
-      if (s) {
-        const uint8_t* r0 = &s_score[y][x];
-        const uint8_t* r1 = &s_score[y + 1][x];
-        const uint8_t* r2 = &s_score[y + 2][x];
-        const int m = max(max(max(r0[0], r0[1]), max(r0[2], r1[0])), max(max(r1[2], r2[0]), max(r2[1], r2[2])));
-        if (s > m) {
-          if (s >= ini_th) keep_ini |= 1u << (p - p0);
-          if (s >= min_th) keep_lo |= 1u << (p - p0);
-        }
-      }
-      if (++x == iw) { x = 0; ++y; }
-    }
-  }
-  // block exclusive scan of both counts
+  // ---- D: threshold fallback + raster-ordered compaction (thread t owns bitmap word t) -----------
+  const int nwords = (npx + 31) >> 5;
+  const uint32_t w_ini = tid < nwords ? s_keep[0][tid] : 0u, w_lo = tid < nwords ? s_keep[1][tid] : 0u;
   const int lane = tid & 31, wid = tid >> 5;
-  int c_ini = __popc(keep_ini), c_lo = __popc(keep_lo);
+  const int c_ini = __popc(w_ini), c_lo = __popc(w_lo);
   int i_ini = c_ini, i_lo = c_lo;
 #pragma unroll
   for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(kFastThreads)
   }
   const bool use_ini = tot_ini > 0;  // :812-816 retry with minThFAST only when the cell is empty
   const int total = use_ini ? tot_ini : tot_lo;
-  uint32_t keep = use_ini ? keep_ini : keep_lo;
+  uint32_t keep = use_ini ? w_ini : w_lo;
   int pos = use_ini ? base_ini + i_ini - c_ini : base_lo + i_lo - c_lo;
   if (tid == 0) {
     uint32_t base = 0;
@@ -185,19 +188,27 @@ __global__ void __launch_bounds__(kFastThreads)
   while (keep) {
     const int bit = __ffs(keep) - 1;
     keep &= keep - 1;
-    const int p = p0 + bit;
-    const int y = p / iw, x = p - y * iw;
+    const int p = tid * 32 + bit;
+    const int y = PSL_DIV(p, rcp_iw), x = p - y * iw;
     // cell-local + (j*wCell, i*hCell) (:820-825) == level coordinate - minBorder
     out[pos++] = pack_cand(x + 3 + cj * g.w_cell, y + 3 + ci * g.h_cell, s_score[y + 1][x + 1]);
   }
 }
 
+#undef PSL_DIV
+
 void launch_fast_cells(const OrbGeometry* d_geo, const OrbGeometry& geo, ImgBatch in0, int ini_th, int min_th,
                        uint32_t* pool, int pool_cap, uint32_t* pool_count, uint2* cell_tab, uint32_t* status, int B,
                        cudaStream_t st) {
   dim3 grid(geo.total_cells, B);
-  fast_cells_kernel<<<grid, kFastThreads, 0, st>>>(d_geo, in0, ini_th, min_th, pool, pool_cap, pool_count, cell_tab,
-                                                   status);
+  // levels >= 1 are ours (128-byte pitch); level 0 is the caller's image
+  const bool aligned = ((uintptr_t)in0.ptr & 3) == 0 && (in0.pitch & 3) == 0 && (in0.frame_stride & 3) == 0;
+  if (aligned)
+    fast_cells_kernel<true><<<grid, kFastThreads, 0, st>>>(d_geo, in0, ini_th, min_th, pool, pool_cap, pool_count,
+                                                           cell_tab, status);
+  else
+    fast_cells_kernel<false><<<grid, kFastThreads, 0, st>>>(d_geo, in0, ini_th, min_th, pool, pool_cap, pool_count,
+                                                            cell_tab, status);
 }
 
 }  // namespace psl

@@ -33,4 +33,34 @@ __device__ __forceinline__ int fast_score_at(const uint8_t* c) {
   return best - 1;
 }
 
+// Two pixels at once on packed u16x2 lanes (VIMNMX3.U16x2 on sm_100a): `ca`, `cb` point at the two
+// centres.  3-input max/min give the 9-wide sliding windows in two steps (3, then 3 of 3).
+// Returns score(a) | score(b) << 16 with scores clamped at 0 (a score <= 0 is never a corner).
+template <int PITCH>
+__device__ __forceinline__ unsigned fast_score_pair(const uint8_t* ca, const uint8_t* cb) {
+  unsigned p[16];
+#define PSL_P2(k, off) p[k] = (unsigned)ca[off] | ((unsigned)cb[off] << 16);
+  PSL_P2(0, 3 * PITCH) PSL_P2(1, 3 * PITCH + 1) PSL_P2(2, 2 * PITCH + 2) PSL_P2(3, PITCH + 3)
+  PSL_P2(4, 3) PSL_P2(5, -PITCH + 3) PSL_P2(6, -2 * PITCH + 2) PSL_P2(7, -3 * PITCH + 1)
+  PSL_P2(8, -3 * PITCH) PSL_P2(9, -3 * PITCH - 1) PSL_P2(10, -2 * PITCH - 2) PSL_P2(11, -PITCH - 3)
+  PSL_P2(12, -3) PSL_P2(13, PITCH - 3) PSL_P2(14, 2 * PITCH - 2) PSL_P2(15, 3 * PITCH - 1)
+#undef PSL_P2
+  unsigned h3[16], l3[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    h3[i] = __vimax3_u16x2(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+    l3[i] = __vimin3_u16x2(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+  }
+  unsigned H = 0xFFFFFFFFu, L = 0u;  // min over arcs of the arc's brightest pixel / max of the darkest
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    H = __vminu2(H, __vimax3_u16x2(h3[i], h3[(i + 3) & 15], h3[(i + 6) & 15]));
+    L = __vmaxu2(L, __vimin3_u16x2(l3[i], l3[(i + 3) & 15], l3[(i + 6) & 15]));
+  }
+  const int va = ca[0], vb = cb[0];
+  const int sa = max(va - (int)(H & 0xFFFFu), (int)(L & 0xFFFFu) - va) - 1;
+  const int sb = max(vb - (int)(H >> 16), (int)(L >> 16) - vb) - 1;
+  return (unsigned)max(sa, 0) | ((unsigned)max(sb, 0) << 16);
+}
+
 }  // namespace psl
