@@ -42,10 +42,12 @@ void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTabl
 
 // ---------------------------------------------------------------------------------------------
 // K5: 7x7 sigma=2 blur, Q8 taps [18,34,48,56,48,34,18], REFLECT_101, dst = (v + 2^15) >> 16.
-// Tile 128x16 outputs per CTA; input tile with 3-px halo staged in shared memory, row pass to
-// u16 in shared memory, column pass straight to a uchar4 store.
+// No shared memory: a thread owns 4 adjacent columns (one output word) and walks down a band of
+// rows with the seven row-pass sums of its columns in a register ring.  Per input row it loads
+// three aligned words (coalesced across the warp, neighbours hit L1), makes the 4 horizontal
+// sums, and emits one uchar4 of the row 3 above.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGTW = 128, kGTH = 16, kGR = 3;
+constexpr int kGBand = 28;  // output rows per warp (4 ring turns of 7)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   // valid for -n < i < 2n-1, which holds for a 3-px halo on any level the extractor accepts
@@ -53,39 +55,74 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i >= n ? 2 * (n - 1) - i : i;
 }
 
-__global__ void __launch_bounds__(256) gauss7_kernel(ImgBatch src, ImgBatchMut dst) {
-  __shared__ uint8_t s_in[kGTH + 2 * kGR][kGTW + 2 * kGR + 2];
-  __shared__ uint16_t s_row[kGTH + 2 * kGR][kGTW];
-  const int b = blockIdx.z;
-  const int x0 = blockIdx.x * kGTW, y0 = blockIdx.y * kGTH;
+template <bool ALIGNED>
+__global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut dst) {
+  const int lane = threadIdx.x, b = blockIdx.z;
+  const int xw = blockIdx.x * 32 + lane;              // output word (4 pixels)
+  const int y0 = (blockIdx.y * 4 + threadIdx.y) * kGBand;
+  const int w = src.w, h = src.h;
+  if (y0 >= h || xw * 4 >= w) return;
+  const int x = xw * 4;
+  const bool interior = ALIGNED && xw >= 1 && x + 7 < w;
   const uint8_t* __restrict__ S = src.ptr + (size_t)b * src.frame_stride;
-  constexpr int IW = kGTW + 2 * kGR, IH = kGTH + 2 * kGR;
-  for (int i = threadIdx.x; i < IW * IH; i += 256) {
-    const int ty = i / IW, tx = i - ty * IW;
-    const int gx = reflect101(x0 + tx - kGR, src.w), gy = reflect101(y0 + ty - kGR, src.h);
-    // tiles hanging over the right/bottom edge read (harmless) reflected pixels
-    s_in[ty][tx] = __ldg(S + (size_t)min(max(gy, 0), src.h - 1) * src.pitch + min(max(gx, 0), src.w - 1));
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < IH * kGTW; i += 256) {
-    const int ty = i / kGTW, tx = i - ty * kGTW;
-    const uint8_t* p = &s_in[ty][tx];
-    s_row[ty][tx] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kGTH * (kGTW / 4); i += 256) {
-    const int ty = i / (kGTW / 4), tx = (i - ty * (kGTW / 4)) * 4;
-    const int gy = y0 + ty, gx = x0 + tx;
-    if (gy >= src.h || gx >= src.w) continue;
-    uint32_t packed = 0;
+  uint8_t* __restrict__ D = dst.ptr + (size_t)b * dst.frame_stride;
+  int xi[10];
+  if (!interior) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t v = 18u * (s_row[ty][tx + k] + s_row[ty + 6][tx + k]) +
-                         34u * (s_row[ty + 1][tx + k] + s_row[ty + 5][tx + k]) +
-                         48u * (s_row[ty + 2][tx + k] + s_row[ty + 4][tx + k]) + 56u * s_row[ty + 3][tx + k];
-      packed |= ((v + 32768u) >> 16) << (8 * k);
+    for (int k = 0; k < 10; ++k) xi[k] = min(reflect101(x - 3 + k, w), w - 1);
+  }
+  int ring[7][4];
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ring[j][k] = 0;
+  const int y_end = min(y0 + kGBand, h);
+  for (int yb = y0 - 3; yb < y_end + 3; yb += 7) {
+    // issue the loads of seven rows before touching any of them (memory-level parallelism)
+    uint32_t ld[7][3];
+    if (interior) {
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int yy = min(yb + j, y_end + 2);
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(S + (size_t)reflect101(yy, h) * src.pitch) + xw;
+        ld[j][0] = __ldg(rw - 1);
+        ld[j][1] = __ldg(rw);
+        ld[j][2] = __ldg(rw + 1);
+      }
     }
-    *reinterpret_cast<uint32_t*>(dst.ptr + (size_t)b * dst.frame_stride + (size_t)gy * dst.pitch + gx) = packed;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int yy = yb + j;
+      if (yy >= y_end + 3) break;
+      int p[10];
+      if (interior) {
+        const uint32_t w0 = ld[j][0], w1 = ld[j][1], w2 = ld[j][2];
+        p[0] = (w0 >> 8) & 0xFF; p[1] = (w0 >> 16) & 0xFF; p[2] = w0 >> 24;
+        p[3] = w1 & 0xFF; p[4] = (w1 >> 8) & 0xFF; p[5] = (w1 >> 16) & 0xFF; p[6] = w1 >> 24;
+        p[7] = w2 & 0xFF; p[8] = (w2 >> 8) & 0xFF; p[9] = (w2 >> 16) & 0xFF;
+      } else {
+        const uint8_t* row = S + (size_t)reflect101(yy, h) * src.pitch;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) p[k] = __ldg(row + xi[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        ring[j][k] = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
+      const int yo = yy - 3;
+      if (yo >= y0) {
+        // newest row is slot j; the 7 rows yo-3..yo+3 sit in slots (j+1)%7 .. j
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t v = 18u * (uint32_t)(ring[(j + 1) % 7][k] + ring[j][k]) +
+                             34u * (uint32_t)(ring[(j + 2) % 7][k] + ring[(j + 6) % 7][k]) +
+                             48u * (uint32_t)(ring[(j + 3) % 7][k] + ring[(j + 5) % 7][k]) +
+                             56u * (uint32_t)ring[(j + 4) % 7][k];
+          packed |= ((v + 32768u) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(D + (size_t)yo * dst.pitch + x) = packed;
+      }
+    }
   }
 }
 
@@ -95,8 +132,10 @@ void launch_gauss7(const OrbGeometry& geo, ImgBatch in0, int B, cudaStream_t st)
                           : ImgBatch{geo.level[l].ptr, geo.level[l].pitch, geo.level[l].frame_stride, geo.level[l].w,
                                      geo.level[l].h};
     const ImgBatchMut& dst = geo.blur[l];
-    dim3 grid((dst.w + kGTW - 1) / kGTW, (dst.h + kGTH - 1) / kGTH, B);
-    gauss7_kernel<<<grid, 256, 0, st>>>(src, dst);
+    dim3 grid(((dst.w + 3) / 4 + 31) / 32, (dst.h + 4 * kGBand - 1) / (4 * kGBand), B), block(32, 4);
+    const bool aligned = ((uintptr_t)src.ptr & 3) == 0 && (src.pitch & 3) == 0 && (src.frame_stride & 3) == 0;
+    if (aligned) gauss7_kernel<true><<<grid, block, 0, st>>>(src, dst);
+    else gauss7_kernel<false><<<grid, block, 0, st>>>(src, dst);
   }
 }
 
