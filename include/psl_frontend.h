@@ -46,6 +46,22 @@ typedef struct psl_keypoint {
   int32_t class_id; /* always -1 */
 } psl_keypoint;
 
+/* Same field order and size (68 B) as cv::line_descriptor::KeyLine
+ * (Thirdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:107-146), the element type of
+ * LINEextractor::operator()'s `keylines` (add_inc/LineExtractor.h:167). */
+typedef struct psl_keyline {
+  float angle;      /* atan2(dy, dx) of the segment */
+  int32_t class_id; /* index of the line after the top-N filter (LineExtractor.cpp:346-347) */
+  int32_t octave;   /* always 0 (uselongline.cpp:419) */
+  float pt_x, pt_y; /* midpoint */
+  float response;   /* length / max(cols, rows) */
+  float size;       /* (ex-sx)*(ey-sy) */
+  float start_x, start_y, end_x, end_y;             /* extremes in the original image */
+  float s_oct_x, s_oct_y, e_oct_x, e_oct_y;         /* extremes in the octave image (same: octave 0) */
+  float line_length;
+  int32_t num_pixels; /* cv::LineIterator(img, start, end).count */
+} psl_keyline;
+
 /* Mirrors the YAML keys read in src/Tracking.cc:113-127
  * (ORBextractor.* / LINEextractor.*; Examples/RGB-D/TUM1.yaml:42-63). */
 typedef struct psl_config {

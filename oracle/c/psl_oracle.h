@@ -67,6 +67,18 @@ void orc_queries_from_last_frame(const psl_keypoint* kps_last, const float* z_la
                                  const float* cam, const float* scale_factors, float th, int mono, float min_x,
                                  float min_y, float max_x, float max_y, psl_proj_query* q);
 
+/* ---- lines (orc_lsd.cpp ...): cv::LineSegmentDetector(LSD_REFINE_STD) behind LineExtractor.cpp:336-337 ---- */
+int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int order_mode, float* lines, int cap);
+int orc_line_iterator_count(int w, int h, float x1, float y1, float x2, float y2);
+int orc_merge_lines_lsd(const float* lines, int n, float* out, int cap);
+void orc_clamp_segments(float* lines, int n, int w, int h);
+int orc_make_keylines(const float* lines, int n, int w, int h, int nfeatures, psl_keyline* kl);
+void orc_lbd_gradients(const uint8_t* img, int w, int h, int stride, int16_t* dx, int16_t* dy);
+void orc_lbd_one(const int16_t* dx, const int16_t* dy, int w, int h, const psl_keyline* kl, float* des72);
+void orc_lbd_binarise(const float* des72, uint8_t* out32);
+int orc_line_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, psl_keyline* kl, uint8_t* ldesc,
+                     double* lineeq, float* lbd72, int cap, int* n_out);
+
 /* CPU-baseline harness: B frames, one frame per task on `nthreads` std::threads. */
 int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
                              int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor);

@@ -237,3 +237,78 @@ def track_batch_mt(gray, depth, Tcw12, cam6, p: OrbParams | None = None, th=15.0
     if rc != 0:
         raise RuntimeError("orc_track_batch_mt failed")
     return n, nm
+
+
+# ---- lines ------------------------------------------------------------------------------------------
+from psl_slam_b200._lib import KEYLINE_DTYPE  # noqa: E402  (ABI struct only)
+
+
+def lsd_detect(img: np.ndarray, order_mode: int = 1) -> np.ndarray:
+    """cv::LineSegmentDetector(REFINE_STD).detect -> float32 [n,4] (x1,y1,x2,y2).
+    order_mode 1 = bins descending, raster order inside a bin (matches cv2 4.13 and OpenCV 3.x);
+    0 = unstable std::sort (kept only to show the sensitivity)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = 8192
+    out = np.empty((cap, 4), np.float32)
+    n = lib().orc_lsd_detect(_p(img), img.shape[1], img.shape[0], img.strides[0], order_mode, _p(out), cap)
+    return out[:n].copy()
+
+
+def line_iterator_count(w, h, x1, y1, x2, y2) -> int:
+    return int(lib().orc_line_iterator_count(w, h, C.c_float(x1), C.c_float(y1), C.c_float(x2), C.c_float(y2)))
+
+
+def merge_lines_lsd(lines: np.ndarray) -> np.ndarray:
+    lines = np.ascontiguousarray(lines, np.float32).reshape(-1, 4)
+    out = np.empty((max(len(lines), 1), 4), np.float32)
+    n = lib().orc_merge_lines_lsd(_p(lines), len(lines), _p(out), len(out))
+    return out[:n].copy()
+
+
+def clamp_segments(lines: np.ndarray, w: int, h: int) -> np.ndarray:
+    lines = np.ascontiguousarray(lines, np.float32).reshape(-1, 4).copy()
+    lib().orc_clamp_segments(_p(lines), len(lines), w, h)
+    return lines
+
+
+def make_keylines(lines: np.ndarray, w: int, h: int, nfeatures: int = 200) -> np.ndarray:
+    lines = np.ascontiguousarray(lines, np.float32).reshape(-1, 4)
+    kl = np.zeros(max(len(lines), 1), KEYLINE_DTYPE)
+    n = lib().orc_make_keylines(_p(lines), len(lines), w, h, nfeatures, _p(kl))
+    return kl[:n].copy()
+
+
+def lbd_gradients(img: np.ndarray):
+    img = np.ascontiguousarray(img, np.uint8)
+    dx = np.empty(img.shape, np.int16)
+    dy = np.empty(img.shape, np.int16)
+    lib().orc_lbd_gradients(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(dx), _p(dy))
+    return dx, dy
+
+
+def lbd_descriptors(dx: np.ndarray, dy: np.ndarray, kl: np.ndarray):
+    """(float [n,72], binary u8 [n,32])"""
+    kl = np.ascontiguousarray(kl, KEYLINE_DTYPE)
+    des = np.zeros((len(kl), 72), np.float32)
+    out = np.zeros((len(kl), 32), np.uint8)
+    for i in range(len(kl)):
+        lib().orc_lbd_one(_p(dx), _p(dy), dx.shape[1], dx.shape[0], C.c_void_p(kl.ctypes.data + 68 * i),
+                          C.c_void_p(des.ctypes.data + 288 * i))
+        lib().orc_lbd_binarise(C.c_void_p(des.ctypes.data + 288 * i), C.c_void_p(out.ctypes.data + 32 * i))
+    return des, out
+
+
+def line_extract(img: np.ndarray, nfeatures: int = 200, cap: int = 1024):
+    """LINEextractor::operator(): (keylines [n], ldesc u8 [n,32], lineeq f64 [n,3], lbd f32 [n,72])."""
+    img = np.ascontiguousarray(img, np.uint8)
+    kl = np.zeros(cap, KEYLINE_DTYPE)
+    ld = np.zeros((cap, 32), np.uint8)
+    eq = np.zeros((cap, 3), np.float64)
+    lbd = np.zeros((cap, 72), np.float32)
+    n = C.c_int(0)
+    rc = lib().orc_line_extract(_p(img), img.shape[1], img.shape[0], img.strides[0], nfeatures, _p(kl), _p(ld), _p(eq),
+                                _p(lbd), cap, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"orc_line_extract rc={rc}")
+    n = n.value
+    return kl[:n].copy(), ld[:n].copy(), eq[:n].copy(), lbd[:n].copy()

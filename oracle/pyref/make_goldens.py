@@ -125,6 +125,25 @@ def make_match():
         print(f"match_pair{pair}: queries {int((q['flags'] & 1).sum())} proj-matches {nm} / mode1 {nm1} / bow {nmb}")
 
 
+def make_line():
+    """cfg-3 shaped fixtures: LSD (real cv2) -> merge -> top-N -> LBD (real cv2 blur/Sobel) -> line equations."""
+    from oracle.pyref import line_py
+    from psl_slam_b200._lib import KEYLINE_DTYPE
+    cases = [("line_lowtex3", synth.make_lowtex(3), 200), ("line_lowtex5", synth.make_lowtex(5), 200),
+             ("line_lowtex7_320x240", synth.make_lowtex(7, 320, 240), 200),
+             ("line_textured_top60", synth.sequence(1, 1)[0][0], 60),
+             ("line_flat", np.full((240, 320), 90, np.uint8), 200)]
+    for name, img, nfeat in cases:
+        raw, merged, kls, des, bits, eq = line_py.line_extract(img, nfeat)
+        kl = np.zeros(len(kls), KEYLINE_DTYPE)
+        for i, k in enumerate(kls):
+            for f in KEYLINE_DTYPE.names:
+                kl[i][f] = k[f]
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), image=img, nfeatures=np.int32(nfeat), lsd_raw=raw,
+                            merged=merged, keylines=kl, lbd=des, ldesc=bits, lineeq=eq)
+        print(name, img.shape, "raw", len(raw), "merged", len(merged), "kept", len(kl))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(OUT, exist_ok=True)
@@ -132,3 +151,5 @@ if __name__ == "__main__":
         make_orb()
     if what in ("match", "all"):
         make_match()
+    if what in ("line", "all"):
+        make_line()

@@ -32,6 +32,11 @@ class Config(C.Structure):
                 ("line_scale_factor", C.c_float), ("line_nlevels", C.c_int32), ("line_min_length", C.c_float)]
 
 
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                          ("response", "<f4"), ("size", "<f4"), ("start_x", "<f4"), ("start_y", "<f4"),
+                          ("end_x", "<f4"), ("end_y", "<f4"), ("s_oct_x", "<f4"), ("s_oct_y", "<f4"),
+                          ("e_oct_x", "<f4"), ("e_oct_y", "<f4"), ("line_length", "<f4"),
+                          ("num_pixels", "<i4")])  # psl_keyline, 68 B
 QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
                         ("u_right", "<f4"), ("angle", "<f4"), ("flags", "<u4")])  # psl_proj_query
 Q_VALID, Q_CLAIMS = 1, 2
