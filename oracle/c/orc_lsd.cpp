@@ -292,6 +292,16 @@ struct Lsd {
 
 }  // namespace
 
+// stage accessor: the blurred + 0.8x-resized 8-bit image LSD works on (for the prologue parity tests)
+extern "C" int orc_lsd_scaled_image(const uint8_t* img, int w, int h, int stride, uint8_t* out, int* W, int* H) {
+  Lsd L;
+  L.prologue(img, w, h, stride);
+  *W = L.W;
+  *H = L.H;
+  if (out) std::memcpy(out, L.img.data(), L.img.size());
+  return 0;
+}
+
 extern "C" int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int order_mode, float* lines, int cap) {
   if (w <= 0 || h <= 0) return 0;
   static thread_local Lsd L;

@@ -69,6 +69,7 @@ void orc_queries_from_last_frame(const psl_keypoint* kps_last, const float* z_la
 
 /* ---- lines (orc_lsd.cpp ...): cv::LineSegmentDetector(LSD_REFINE_STD) behind LineExtractor.cpp:336-337 ---- */
 int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int order_mode, float* lines, int cap);
+int orc_lsd_scaled_image(const uint8_t* img, int w, int h, int stride, uint8_t* out, int* W, int* H);
 int orc_line_iterator_count(int w, int h, float x1, float y1, float x2, float y2);
 int orc_merge_lines_lsd(const float* lines, int n, float* out, int cap);
 void orc_clamp_segments(float* lines, int n, int w, int h);

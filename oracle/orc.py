@@ -312,3 +312,12 @@ def line_extract(img: np.ndarray, nfeatures: int = 200, cap: int = 1024):
         raise RuntimeError(f"orc_line_extract rc={rc}")
     n = n.value
     return kl[:n].copy(), ld[:n].copy(), eq[:n].copy(), lbd[:n].copy()
+
+
+def lsd_scaled_image(img: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    W, H = C.c_int(), C.c_int()
+    lib().orc_lsd_scaled_image(_p(img), img.shape[1], img.shape[0], img.strides[0], None, C.byref(W), C.byref(H))
+    out = np.empty((H.value, W.value), np.uint8)
+    lib().orc_lsd_scaled_image(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), C.byref(W), C.byref(H))
+    return out

@@ -1,0 +1,64 @@
+// Launchers of the line front end (LSD + merge + LBD); all asynchronous on `st`, batch-first.
+#pragma once
+#include "line_core.cuh"
+#include "psl_common.cuh"
+
+namespace psl {
+
+// geometry + per-chunk device buffers of the line path for one frame size
+struct LineBuffers {
+  int w, h, pitch;     // input size; pitch of the u8 work images (multiple of 128)
+  int Ws, Hs;          // LSD working size (0.8x)
+  int min_reg_size;    // LSD minimal region size (-logNT / log10(p))
+  int raw_cap;         // raw LSD segments kept per frame
+  int kl_cap;          // keylines per frame (>= nfeatures)
+  const short2* xtab;  // [Ws] exact-resize taps (src index, Q8 weight of the right tap or -1)
+  const short2* ytab;  // [Hs]
+  uint8_t* blur;       // [C][h][pitch]   7x7 sigma 0.75 (LSD) and, later, 5x5 sigma 1 (LBD)
+  uint8_t* scaled;     // [C][Hs][Ws]
+  float* deg;          // [C][Hs*Ws]
+  int32_t* n2;         // [C][Hs*Ws]
+  uint8_t* used;       // [C][Hs*Ws]
+  uint32_t* reg;       // [C][Hs*Ws]
+  int32_t* max_n2;     // [C]
+  int32_t* row_cnt;    // [C][Hs]  defined pixels per row -> exclusive offsets
+  int32_t* n_def;      // [C]
+  uint16_t* key_in;    // [C][Hs*Ws]
+  uint16_t* key_out;
+  uint32_t* val_in;    // [C][Hs*Ws]
+  uint32_t* val_out;
+  int32_t* seg_begin;  // [C] segment offsets for the segmented sort
+  int32_t* seg_end;    // [C]
+  void* sort_tmp;
+  size_t sort_tmp_bytes;
+  float* raw;          // [C][raw_cap][4]
+  int32_t* n_raw;      // [C]
+  line::Seg* t1;       // [C][raw_cap]
+  line::Seg* t2;       // [C][raw_cap]
+  float* m_angles;     // merge scratch, [C][raw_cap] each
+  float* m_length;
+  uint16_t* m_order;
+  uint16_t* m_tmp16;
+  uint16_t* m_nb;      // [C][raw_cap][kNbCap]
+  uint16_t* m_nb_cnt;
+  int16_t* m_code;
+  uint16_t* m_check;
+  uint16_t* m_loc;
+  uint8_t* m_flag;
+  int16_t* gdx;        // [C][h][w] Sobel of the sigma-1 blurred image
+  int16_t* gdy;
+  float* lbd_rows;     // [C][kl_cap][63][4]
+};
+
+size_t lsd_sort_temp_bytes(int items_per_frame, int frames);
+
+// LSD for `nb` frames: fills raw segments + counts
+void launch_lsd(const LineBuffers& L, ImgBatch in, int nb, uint32_t* status, cudaStream_t st);
+// clamp + merge + top-N + keylines + line equations
+void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int32_t* n_out,
+                      uint32_t* status, cudaStream_t st);
+// LBD descriptors of the keylines (float 72 optional)
+void launch_lbd(const LineBuffers& L, ImgBatch in, int nb, const psl_keyline* kl, const int32_t* n_kl, uint8_t* ldesc,
+                float* lbd72, cudaStream_t st);
+
+}  // namespace psl

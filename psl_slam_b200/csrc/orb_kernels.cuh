@@ -23,6 +23,9 @@ void launch_octree(const OrbGeometry* d_geo, const OrbGeometry& geo, const uint3
                    const uint2* cell_tab, uint32_t* key_scratch, uint16_t* node_scratch, uint32_t* sel,
                    int32_t* sel_count, uint32_t* status, int B, cudaStream_t st);
 
+// generic separable 7-tap Q8 blur of one image batch (taps t0,t1,t2,t3=centre; dst pitch multiple of 4)
+void launch_blur7(const ImgBatch& src, const ImgBatchMut& dst, int t0, int t1, int t2, int t3, int B, cudaStream_t st);
+
 // K5: 7x7 sigma-2 Gaussian blur of every level (ORBextractor.cc:1085-1086)
 void launch_gauss7(const OrbGeometry& geo, ImgBatch in0, int B, cudaStream_t st);
 

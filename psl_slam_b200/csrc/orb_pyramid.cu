@@ -41,7 +41,9 @@ void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTabl
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5: 7x7 sigma=2 blur, Q8 taps [18,34,48,56,48,34,18], REFLECT_101, dst = (v + 2^15) >> 16.
+// K5: separable 7-tap Q8 blur of CV_8U (cv::GaussianBlur bit-exact path), REFLECT_101, dst = (v + 2^15) >> 16.
+// Taps (t0,t1,t2,t3 = centre): [18,34,48,56] = 7x7 sigma 2 (ORB), [0,4,56,136] = 7x7 sigma 0.75 (LSD prologue),
+// [0,14,62,104] = 5x5 sigma 1 (LBD).
 // No shared memory: a thread owns 4 adjacent columns (one output word) and walks down a band of
 // rows with the seven row-pass sums of its columns in a register ring.  Per input row it loads
 // three aligned words (coalesced across the warp, neighbours hit L1), makes the 4 horizontal
@@ -56,7 +58,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut dst) {
+__global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut dst, int t0, int t1, int t2, int t3) {
   const int lane = threadIdx.x, b = blockIdx.z;
   const int xw = blockIdx.x * 32 + lane;              // output word (4 pixels)
   const int y0 = (blockIdx.y * 4 + threadIdx.y) * kGBand;
@@ -107,17 +109,17 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        ring[j][k] = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
+        ring[j][k] = t0 * (p[k] + p[k + 6]) + t1 * (p[k + 1] + p[k + 5]) + t2 * (p[k + 2] + p[k + 4]) + t3 * p[k + 3];
       const int yo = yy - 3;
       if (yo >= y0) {
         // newest row is slot j; the 7 rows yo-3..yo+3 sit in slots (j+1)%7 .. j
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t v = 18u * (uint32_t)(ring[(j + 1) % 7][k] + ring[j][k]) +
-                             34u * (uint32_t)(ring[(j + 2) % 7][k] + ring[(j + 6) % 7][k]) +
-                             48u * (uint32_t)(ring[(j + 3) % 7][k] + ring[(j + 5) % 7][k]) +
-                             56u * (uint32_t)ring[(j + 4) % 7][k];
+          const uint32_t v = (uint32_t)t0 * (uint32_t)(ring[(j + 1) % 7][k] + ring[j][k]) +
+                             (uint32_t)t1 * (uint32_t)(ring[(j + 2) % 7][k] + ring[(j + 6) % 7][k]) +
+                             (uint32_t)t2 * (uint32_t)(ring[(j + 3) % 7][k] + ring[(j + 5) % 7][k]) +
+                             (uint32_t)t3 * (uint32_t)ring[(j + 4) % 7][k];
           packed |= ((v + 32768u) >> 16) << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(D + (size_t)yo * dst.pitch + x) = packed;
@@ -126,16 +128,19 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
   }
 }
 
+void launch_blur7(const ImgBatch& src, const ImgBatchMut& dst, int t0, int t1, int t2, int t3, int B, cudaStream_t st) {
+  dim3 grid(((dst.w + 3) / 4 + 31) / 32, (dst.h + 4 * kGBand - 1) / (4 * kGBand), B), block(32, 4);
+  const bool aligned = ((uintptr_t)src.ptr & 3) == 0 && (src.pitch & 3) == 0 && (src.frame_stride & 3) == 0;
+  if (aligned) gauss7_kernel<true><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3);
+  else gauss7_kernel<false><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3);
+}
+
 void launch_gauss7(const OrbGeometry& geo, ImgBatch in0, int B, cudaStream_t st) {
   for (int l = 0; l < geo.nlevels; ++l) {
     ImgBatch src = l == 0 ? in0
                           : ImgBatch{geo.level[l].ptr, geo.level[l].pitch, geo.level[l].frame_stride, geo.level[l].w,
                                      geo.level[l].h};
-    const ImgBatchMut& dst = geo.blur[l];
-    dim3 grid(((dst.w + 3) / 4 + 31) / 32, (dst.h + 4 * kGBand - 1) / (4 * kGBand), B), block(32, 4);
-    const bool aligned = ((uintptr_t)src.ptr & 3) == 0 && (src.pitch & 3) == 0 && (src.frame_stride & 3) == 0;
-    if (aligned) gauss7_kernel<true><<<grid, block, 0, st>>>(src, dst);
-    else gauss7_kernel<false><<<grid, block, 0, st>>>(src, dst);
+    launch_blur7(src, geo.blur[l], 18, 34, 48, 56, B, st);
   }
 }
 
