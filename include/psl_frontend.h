@@ -80,7 +80,11 @@ typedef struct psl_config {
   int32_t line_nfeatures;  /* LINEextractor.nFeatures  (200)  */
   float line_scale_factor; /* LINEextractor.scaleFactor (1.2; truncated to int 1 by the reference) */
   int32_t line_nlevels;    /* LINEextractor.nLevels    (1)    */
-  float line_min_length;   /* LINEextractor.min_line_length (0) */
+  float line_min_length;   /* LINEextractor.min_line_length (0; read by Tracking.cc:126 but never used by
+                              LINEextractor::operator(), add_src/LineExtractor.cpp:325-366 -> ignored here too) */
+  int32_t line_chunk_frames; /* frames per launch of the line stages; 0 = auto (1024).  The sequential LSD core
+                                runs one frame per warp, so the batch is its only parallel axis */
+  int32_t line_max_raw;    /* raw LSD segments kept per frame before the merge; 0 = auto (4096) */
 } psl_config;
 
 void psl_default_config(psl_config* cfg);
@@ -116,6 +120,29 @@ int psl_orb_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t 
 int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, int32_t w, int32_t h, int32_t stride,
                               int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
                               int32_t* d_n);
+
+/* LINEextractor::operator()(image, mask, keylines, descriptors, lineVec2d)
+ * (add_src/LineExtractor.cpp:325-366; called from Frame::ExtractLSD, src/Frame.cc:494):
+ *   LSDDetector::detect(img, kl, scale -> int 1, numOctaves 1)   :336-337  (cv::LineSegmentDetector, REFINE_STD)
+ *   optimizeAndMergeLines_lsd                                      :338      (add_src/uselongline.cpp:449-485)
+ *   sort by response, keep line_nfeatures, class_id = i            :342-348
+ *   BinaryDescriptor::compute (LBD, 32 bytes per line)             :349-350
+ *   2-D line equations sp x ep / |(l0, l1)|                        :352-363
+ * gray: HOST CV_8UC1.  mask must be empty in the reference's only call (Frame.cc:493) and is absent here.
+ * kl[cap], ldesc[cap*32], lineeq[cap*3] (fp64, lineVec2d), lbd72[cap*72] (optional, may be NULL: the float
+ * descriptor before binarisation).  *n = number of lines.  Empty image -> *n = 0, PSL_OK (:327-328). */
+int psl_line_extract(psl_ctx* ctx, const uint8_t* gray, int32_t w, int32_t h, int32_t stride, psl_keyline* kl,
+                     uint8_t* ldesc, double* lineeq, float* lbd72, int32_t cap, int32_t* n);
+
+/* Batched form: B frames of identical size, frame b at gray + b*frame_stride (HOST); outputs are [B][cap] blocks. */
+int psl_line_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t w, int32_t h, int32_t stride,
+                           int64_t frame_stride, psl_keyline* kl, uint8_t* ldesc, double* lineeq, float* lbd72,
+                           int32_t cap, int32_t* n);
+
+/* Same, all pointers DEVICE memory; asynchronous on psl_stream(ctx). */
+int psl_line_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, int32_t w, int32_t h, int32_t stride,
+                               int64_t frame_stride, psl_keyline* d_kl, uint8_t* d_ldesc, double* d_lineeq,
+                               float* d_lbd72, int32_t cap, int32_t* d_n);
 
 /* ------------------------------------------------------------------------------------------------
  * Matching.  Only plain arrays cross the boundary: the caller (Frame / Tracking) keeps the MapPoint
@@ -238,7 +265,8 @@ int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth
 /* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).
  * Stages: 0 pyramid resize, 1 FAST cells, 2 octree selection, 3 Gaussian blur, 4 orientation+rBRIEF,
  * 5 single-pair matcher calls, 6 stereo + projection queries, 7 feature grid, 8 candidate lists,
- * 9 ordered resolve; 10.. reserved for the line stages.  psl_profile_read synchronises, writes the accumulated
+ * 9 ordered resolve, 10 LSD prologue (blur, 0.8x resize, gradient, seed keys), 11 LSD seed ordering,
+ * 12 LSD region growing, 13 line merge + KeyLines, 14 LBD, 15 line matching.  psl_profile_read synchronises, writes the accumulated
  * milliseconds and kernel-launch counts per stage since the last read (arrays of PSL_N_STAGES) and resets. */
 #define PSL_N_STAGES 16
 int psl_profile_enable(psl_ctx* ctx, int32_t on);
@@ -253,7 +281,9 @@ int64_t psl_launch_count(const psl_ctx* ctx);
  *          1: blurred level image, tightly packed
  *          2: FAST candidates of the level in reference order, packed u32 (x-16)<<20 | (y-16)<<8 | score
  *          3: octree-selected keys of the level in list order, same packing
- * *n = number of bytes (0,1) or entries (2,3) written. */
+ *          4: (last LINE call) the 0.8x image LSD works on, tightly packed
+ *          5: (last LINE call) raw LSD segments of the frame, float x1,y1,x2,y2 each
+ * *n = number of bytes (0,1,4) or entries (2,3,5) written. */
 int psl_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, int32_t level, void* out, int64_t cap_bytes,
                     int64_t* n);
 

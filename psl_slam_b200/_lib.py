@@ -29,7 +29,8 @@ class Config(C.Structure):
                 ("max_batch", C.c_int32), ("orb_nfeatures", C.c_int32), ("orb_scale_factor", C.c_float),
                 ("orb_nlevels", C.c_int32), ("orb_ini_th_fast", C.c_int32), ("orb_min_th_fast", C.c_int32),
                 ("orb_max_candidates", C.c_int32), ("chunk_frames", C.c_int32), ("line_nfeatures", C.c_int32),
-                ("line_scale_factor", C.c_float), ("line_nlevels", C.c_int32), ("line_min_length", C.c_float)]
+                ("line_scale_factor", C.c_float), ("line_nlevels", C.c_int32), ("line_min_length", C.c_float),
+                ("line_chunk_frames", C.c_int32), ("line_max_raw", C.c_int32)]
 
 
 KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
@@ -90,7 +91,8 @@ def make_feature_vector(node_id, offs, idx):
 EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", "psl_stream", "psl_sync",
            "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch", "psl_profile_enable",
            "psl_profile_read", "psl_launch_count", "psl_descriptor_distance", "psl_hamming_knn2",
-           "psl_match_projection", "psl_match_bow", "psl_track_orb_batch", "psl_track_orb_batch_dev"]
+           "psl_match_projection", "psl_match_bow", "psl_track_orb_batch", "psl_track_orb_batch_dev",
+           "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev"]
 
 _lib = None
 
@@ -126,6 +128,9 @@ def lib():
         L.psl_track_orb_batch_dev.argtypes = [_p, _p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p,
                                               _p, _p, _i]
         L.psl_track_orb_batch.argtypes = [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i]
+        L.psl_line_extract.argtypes = [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p]
+        L.psl_line_extract_batch.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _p, _p, _i, _p]
+        L.psl_line_extract_batch_dev.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _p, _p, _i, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

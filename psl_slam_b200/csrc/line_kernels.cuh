@@ -11,7 +11,6 @@ struct LineBuffers {
   int Ws, Hs;          // LSD working size (0.8x)
   int min_reg_size;    // LSD minimal region size (-logNT / log10(p))
   int raw_cap;         // raw LSD segments kept per frame
-  int kl_cap;          // keylines per frame (>= nfeatures)
   const short2* xtab;  // [Ws] exact-resize taps (src index, Q8 weight of the right tap or -1)
   const short2* ytab;  // [Hs]
   uint8_t* blur;       // [C][h][pitch]   7x7 sigma 0.75 (LSD) and, later, 5x5 sigma 1 (LBD)
@@ -45,20 +44,25 @@ struct LineBuffers {
   uint16_t* m_check;
   uint16_t* m_loc;
   uint8_t* m_flag;
-  int16_t* gdx;        // [C][h][w] Sobel of the sigma-1 blurred image
-  int16_t* gdy;
-  float* lbd_rows;     // [C][kl_cap][63][4]
+  short2* gxy;         // [C][h][w] Sobel (dx, dy) of the sigma-1 blurred image
 };
 
 size_t lsd_sort_temp_bytes(int items_per_frame, int frames);
 
-// LSD for `nb` frames: fills raw segments + counts
-void launch_lsd(const LineBuffers& L, ImgBatch in, int nb, uint32_t* status, cudaStream_t st);
-// clamp + merge + top-N + keylines + line equations
-void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int32_t* n_out,
-                      uint32_t* status, cudaStream_t st);
-// LBD descriptors of the keylines (float 72 optional)
-void launch_lbd(const LineBuffers& L, ImgBatch in, int nb, const psl_keyline* kl, const int32_t* n_kl, uint8_t* ldesc,
-                float* lbd72, cudaStream_t st);
+// LSD for `nb` frames (cv::LineSegmentDetector behind LineExtractor.cpp:336-337), three stages:
+// blur + 0.8x resize + gradient + seed keys (6 launches); stable seed ordering (cub segmented radix sort, counted as 1);
+// the sequential region-growing core -> raw segments + counts (1 launch)
+void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t st);
+void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st);
+void launch_lsd_core(const LineBuffers& L, int nb, uint32_t* status, cudaStream_t st);
+// clamp + merge + top-N + keylines + line equations (LineExtractor.cpp:338-363); outputs are [nb][cap] blocks
+void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int cap,
+                      int32_t* n_out, uint32_t* status, cudaStream_t st);
+// LBD descriptors of the keylines (BinaryDescriptor::compute, LineExtractor.cpp:349-350); lbd72 optional.
+// 3 launches: 5x5 sigma-1 blur, Sobel, descriptor.
+void launch_lbd(const LineBuffers& L, ImgBatch in, int nb, int nfeatures, const psl_keyline* kl, const int32_t* n_kl,
+                int cap, uint8_t* ldesc, float* lbd72, cudaStream_t st);
+// LBD weight tables (BinaryDescriptor ctor, binary_descriptor_custom.cpp:219-261), computed once on the host
+void upload_lbd_tables();
 
 }  // namespace psl

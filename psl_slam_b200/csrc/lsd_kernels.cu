@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(32)
   f.cap = L.raw_cap;
   const int n = lsd::detect(f);
   L.n_raw[b] = n < L.raw_cap ? n : L.raw_cap;
-  if (n > L.raw_cap) atomicOr(status, kStatCandOverflow);
+  if (n > L.raw_cap) atomicOr(status, kStatLineRaw);
 }
 
 size_t lsd_sort_temp_bytes(int items_per_frame, int frames) {
@@ -151,7 +151,7 @@ size_t lsd_sort_temp_bytes(int items_per_frame, int frames) {
   return bytes;
 }
 
-void launch_lsd(const LineBuffers& L, ImgBatch in, int nb, uint32_t* status, cudaStream_t st) {
+void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t st) {
   const int npx = L.Ws * L.Hs;
   ImgBatchMut bl{L.blur, L.pitch, (int64_t)L.pitch * L.h, L.w, L.h};
   launch_blur7(in, bl, 0, 4, 56, 136, nb, st);  // GaussianBlur(7x7, sigma = 0.6 / 0.8)
@@ -166,10 +166,17 @@ void launch_lsd(const LineBuffers& L, ImgBatch in, int nb, uint32_t* status, cud
   lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.deg, L.n2, L.used, L.max_n2, L.row_cnt, rho);
   lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, npx, L.n_def, L.seg_begin, L.seg_end);
   lsd_keys_kernel<<<rows, 128, 0, st>>>(L.deg, L.n2, L.Ws, L.Hs, L.max_n2, L.row_cnt, L.key_in, L.val_in);
+}
+
+// stable: bins descending, raster order inside a bin (identical to cv2 4.13 on every golden)
+void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st) {
+  const int npx = L.Ws * L.Hs;
   size_t tmp = L.sort_tmp_bytes;
-  // stable: bins descending, raster order inside a bin (what cv2 4.13 and OpenCV 3.x both produce)
   cub::DeviceSegmentedRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.key_in, L.key_out, L.val_in, L.val_out,
                                                      (int64_t)npx * nb, nb, L.seg_begin, L.seg_end, 0, 10, st);
+}
+
+void launch_lsd_core(const LineBuffers& L, int nb, uint32_t* status, cudaStream_t st) {
   lsd_core_kernel<<<nb, 32, 0, st>>>(L, status);
 }
 

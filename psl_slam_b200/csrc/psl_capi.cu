@@ -35,7 +35,9 @@ int check_status(psl_ctx* ctx) {
   if (s & kStatNodeOverflow) return fail(ctx, PSL_E_INTERNAL, "octree: node table bound violated");
   if (s & kStatCandOverflow)
     return fail(ctx, PSL_E_CAPACITY, "FAST candidate pool overflow: raise psl_config.orb_max_candidates");
-  if (s & kStatOutOverflow) return fail(ctx, PSL_E_CAPACITY, "keypoint capacity `cap` too small");
+  if (s & kStatOutOverflow) return fail(ctx, PSL_E_CAPACITY, "output capacity `cap` too small");
+  if (s & kStatLineRaw) return fail(ctx, PSL_E_CAPACITY, "LSD raw segment overflow: raise psl_config.line_max_raw");
+  if (s & kStatLineNeighbours) return fail(ctx, PSL_E_CAPACITY, "line merge: neighbour list bound violated");
   return fail(ctx, PSL_E_INTERNAL, "unknown device status");
 }
 
@@ -233,6 +235,8 @@ void psl_default_config(psl_config* cfg) {
   cfg->line_scale_factor = 1.2f;
   cfg->line_nlevels = 1;
   cfg->line_min_length = 0.f;
+  cfg->line_chunk_frames = 0;
+  cfg->line_max_raw = 0;
 }
 
 int psl_create(const psl_config* cfg, psl_ctx** out) {
@@ -275,6 +279,7 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
     ctx->quota[L - 1] = std::max(cfg->orb_nfeatures - sum, 0);
   }
   ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 256;
+  ctx->line_chunk = cfg->line_chunk_frames > 0 ? cfg->line_chunk_frames : 1024;
   ctx->pool_cap = cfg->orb_max_candidates > 0 ? cfg->orb_max_candidates : std::max(16384, 32 * cfg->orb_nfeatures);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc(&ctx->d_geo, sizeof(OrbGeometry)) == cudaSuccess &&
@@ -294,6 +299,7 @@ void psl_destroy(psl_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_geometry(ctx);
+  free_line_geometry(ctx);
   cudaFree(ctx->d_geo);
   cudaFree(ctx->d_status);
   cudaFreeHost(ctx->h_status);
@@ -415,6 +421,11 @@ int64_t psl_launch_count(const psl_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int psl_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, int32_t level, void* out, int64_t cap_bytes,
                     int64_t* n) {
   if (!ctx || !out || !n) return PSL_E_INVALID;
+  if (what == 4 || what == 5) {
+    PSL_CK(cudaSetDevice(ctx->cfg.device));
+    *n = 0;
+    return psl_line_debug_fetch(ctx, what, frame, out, cap_bytes, n);
+  }
   const OrbGeometry& g = ctx->geo;
   if (!ctx->geo_w || frame < 0 || frame >= ctx->chunk || level < 0 || level >= g.nlevels)
     return fail(ctx, PSL_E_INVALID, "debug_fetch: no geometry / bad frame or level");

@@ -68,6 +68,8 @@ enum : uint32_t {
   kStatOutOverflow = 2u,    // caller's kps/desc capacity too small
   kStatNodeOverflow = 4u,   // octree node table too small (internal bound violated)
   kStatBadRoot = 8u,        // candidate outside every octree root (aspect not supported)
+  kStatLineNeighbours = 16u,  // a segment has more merge neighbours than line::kNbCap
+  kStatLineRaw = 32u,       // more raw LSD segments than psl_config.line_max_raw
 };
 
 }  // namespace psl

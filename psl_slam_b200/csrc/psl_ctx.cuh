@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 
+#include "line_kernels.cuh"
 #include "orb_kernels.cuh"
 
 // grow-only device buffer
@@ -40,6 +41,14 @@ struct psl_ctx {
   uint32_t* d_status = nullptr;
   uint32_t* h_status = nullptr;   // pinned mirror
 
+  // line front end (allocated on first use): geometry + per-chunk buffers for frames of lgeo_w x lgeo_h
+  int line_chunk = 0;
+  int lgeo_w = 0, lgeo_h = 0;
+  psl::LineBuffers lb{};
+  std::vector<void*> line_allocs;
+  // staging of the host-pointer line entry points
+  DevBuf l_in, l_kl, l_desc, l_eq, l_lbd, l_n;
+
   // per-stage profiling (psl_profile_*)
   bool prof = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -65,11 +74,14 @@ int fail(psl_ctx* c, int code, const std::string& msg);
 int cuda_fail(psl_ctx* c, cudaError_t e, const char* what);
 int ensure_bytes(psl_ctx* c, void** p, size_t* have, size_t need);
 inline int ensure(psl_ctx* c, DevBuf& b, size_t need) { return ensure_bytes(c, &b.p, &b.bytes, need ? need : 16); }
+void free_line_geometry(psl_ctx* c);
 int check_status(psl_ctx* c);  // sync + translate the device status word
 // RAII-free stage bracket: begin/end record events when profiling is on and count launches.
 size_t prof_mark(psl_ctx* c);
 void prof_span(psl_ctx* c, int stage, size_t e0, int nlaunch);
 }  // namespace psl
+
+int psl_line_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, void* out, int64_t cap_bytes, int64_t* n);
 
 #define PSL_CK(call)                                                     \
   do {                                                                   \

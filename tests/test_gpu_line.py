@@ -1,0 +1,82 @@
+"""GPU: the CUDA line extractor (LSD + merge + LBD) through the C-ABI against the oracle and the committed
+cv2 goldens.  Integer / byte results and every float field are compared bit-exactly."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+LINES = golden_names("line_")
+
+
+def _same(got, want):
+    kl, ld, eq, lbd = got
+    okl, old, oeq, olbd = want
+    assert len(kl) == len(okl)
+    for f in kl.dtype.names:
+        assert np.array_equal(kl[f], okl[f]), f
+    assert np.array_equal(ld, old)
+    assert np.array_equal(eq, oeq)
+    assert np.array_equal(lbd, olbd, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", LINES)
+def test_line_vs_golden_and_stages(orc, name):
+    from psl_slam_b200 import LINEextractor
+    g = load_golden(name)
+    img = g["image"]
+    h, w = img.shape
+    ex = LINEextractor(1, 1.2, int(g["nfeatures"]), 0.0, max_width=w, max_height=h, chunk_frames=2)
+    got = ex(img, with_lbd_floats=True)
+    _same(got, (g["keylines"], g["ldesc"], g["lineeq"], g["lbd"]))
+    # stages: the 0.8x working image and the raw LSD segments (cv2.createLineSegmentDetector output)
+    scaled = orc.lsd_scaled_image(img)
+    assert np.array_equal(ex.debug_fetch(4).reshape(scaled.shape), scaled)
+    assert np.array_equal(ex.debug_fetch(5), orc.clamp_segments(g["lsd_raw"], w, h))
+
+
+def test_lsd_known_answers():
+    """SURVEY App. B.5 (measured with cv2 4.13): a vertical step edge gives exactly one segment."""
+    from psl_slam_b200 import LINEextractor
+    ex = LINEextractor(chunk_frames=1)
+    im = np.full((480, 640), 60, np.uint8)
+    im[:, 200:] = 180
+    kl, ld, eq = ex(im)
+    assert np.array_equal(ex.debug_fetch(5), np.array([[199.375, 0.625, 199.375, 478.125]], np.float32))
+    assert len(kl) == 1 and kl["num_pixels"][0] == 478 and ld.shape == (1, 32)
+    assert np.allclose(np.abs(eq[0]), [1.0, 0.0, 199.375])
+    kl, ld, eq = ex(np.full((480, 640), 7, np.uint8))
+    assert len(kl) == 0 and ld.shape == (0, 32) and eq.shape == (0, 3)
+    kl, ld, eq = ex(np.zeros((0, 0), np.uint8))  # empty image: silent return (LineExtractor.cpp:327-328)
+    assert len(kl) == 0
+
+
+def test_batch_mixed_frames_vs_oracle(orc):
+    """A batch spanning several chunks: textured, low-texture and flat frames side by side."""
+    from psl_slam_b200 import LINEextractor, synth
+    gray, _, _ = synth.sequence(6, 3)
+    frames = np.stack([gray[0], synth.make_lowtex(11), np.full((480, 640), 100, np.uint8), gray[1],
+                       synth.make_lowtex(12), gray[2], synth.make_lowtex(13)])
+    ex = LINEextractor(chunk_frames=3)
+    kl, ld, eq, lbd, n = ex.extract_batch(frames, with_lbd_floats=True)
+    assert n[2] == 0 and n.max() > 20
+    for b in range(len(frames)):
+        want = orc.line_extract(frames[b], 200)
+        _same((kl[b, : n[b]], ld[b, : n[b]], eq[b, : n[b]], lbd[b, : n[b]]), want)
+    # same frames, one chunk, strided rows: identical bytes
+    padded = np.zeros((len(frames), 480, 704), np.uint8)
+    padded[:, :, :640] = frames
+    ex2 = LINEextractor(chunk_frames=16)
+    kl2, ld2, eq2, n2 = ex2.extract_batch(padded[:, :, :640])
+    assert np.array_equal(n, n2) and kl.tobytes() == kl2.tobytes() and np.array_equal(ld, ld2)
+
+
+def test_capacity_errors_are_loud():
+    from psl_slam_b200 import LINEextractor, PslError, synth
+    gray, _, _ = synth.sequence(6, 1)
+    ex = LINEextractor(max_raw=64, chunk_frames=1)
+    with pytest.raises(PslError) as e:
+        ex(gray[0])
+    assert e.value.code == -3
+    with pytest.raises(PslError):
+        LINEextractor(max_width=320, max_height=240)(gray[0])
