@@ -222,6 +222,84 @@ int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, c
                   int32_t* match_f, int32_t* nmatches);
 
 /* ------------------------------------------------------------------------------------------------
+ * Line matching (add_src/LSDmatcher.cpp, add_src/InsectlineMatch.cpp).  As for points, MapLine / InsectLine
+ * objects stay with the caller; plain arrays cross the boundary.  All pointers HOST.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* LSDmatcher::match -> matchNNR (LSDmatcher.cpp:354-413): BFMatcher(NORM_HAMMING).knnMatch(desc1, desc2, 2), keep
+ * best if d0 < d1 * nnr.  matches12[n1] = index into desc2 or -1; *nmatches = return value.  With n2 < 2 the
+ * reference indexes out of bounds (:369); here every query is unmatched. */
+int psl_line_match_nnr(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2, float nnr,
+                       int32_t* matches12, int32_t* nmatches);
+
+/* LSDmatcher::SearchByGeomNApearance(CurrentFrame, LastFrame, desc_th) (LSDmatcher.cpp:36-110, called at
+ * Tracking.cc:1183): matchNNR(last, cur, desc_th), then per last line with a MapLine (has_mapline_last[i] != 0):
+ * reject if the matched current line has startPointX == 0, if |cos| of the 2-D directions < cos 20 deg, or if both
+ * endpoints moved by more than 10 % of the image bounds.  assign_cur[n_cur] = last-frame line whose MapLine ends up
+ * in CurrentFrame.mvpMapLines[i] (the last writer wins, as in the reference) or -1; *nmatches = return value.
+ * bounds = mnMinX, mnMinY, mnMaxX, mnMaxY of the current frame. */
+int psl_line_search_geom(psl_ctx* ctx, const psl_keyline* kl_last, const uint8_t* desc_last,
+                         const uint8_t* has_mapline_last, int32_t n_last, const psl_keyline* kl_cur,
+                         const uint8_t* desc_cur, int32_t n_cur, const float* bounds, float desc_th,
+                         int32_t* assign_cur, int32_t* nmatches);
+
+/* LSDmatcher::FrameBFMatch (LSDmatcher.cpp:492-516) with lineDescriptorMAD (:660-685): knn2, MAD-adaptive gap
+ * threshold, d0 < th and d0 < nn_ratio * d1.  matches[n1] = index into desc2 or -1.  n1 == 0 or n2 < 2: all -1. */
+int psl_line_frame_bf_match(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
+                            float nn_ratio, float th, int32_t* matches);
+
+/* LSDmatcher::SearchDouble(InitialFrame, CurrentFrame, LineMatches) (LSDmatcher.cpp:462-490): FrameBFMatch in both
+ * directions (TH_LOW = 50) and mutual consistency.  matches12[n1]; *nmatches = return value.  The KeyFrame form
+ * (:415-460) is the same call with the roles swapped plus the caller's MapLine lookup. */
+int psl_line_search_double(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
+                           float nn_ratio, float th, int32_t* matches12, int32_t* nmatches);
+
+/* What LSDmatcher::SearchByProjection reads from the searched Frame (include/Frame.h): mvKeylinesUn, mLdesc,
+ * mvKeyLineFunctions, mvLines3D (first/second endpoints, n x 6 doubles; only the map-line form needs it) and the
+ * bounds of the 64x48 line grid (Frame::AssignFeaturesToGridForLine, Frame.cc:286-309; rebuilt by the library). */
+typedef struct psl_line_frame_view {
+  int32_t n;
+  const psl_keyline* kl_un;
+  const uint8_t* ldesc;
+  const double* lineeq;
+  const double* lines3d;
+  float min_x, min_y, max_x, max_y;
+  float grid_w_inv, grid_h_inv;
+} psl_line_frame_view;
+
+/* One projected MapLine: what Frame::isInFrustum(MapLine*, ...) leaves in mTrackProjX1.. (Frame.cc:828-898). */
+typedef struct psl_line_query {
+  float x1, y1, x2, y2;     /* mTrackProjX1, Y1, X2, Y2 */
+  float radius;             /* th (LSDmatcher.cpp:152) or RadiusByViewingCos(viewCos)*th (:282-285) */
+  float sx, sy, ex, ey;     /* mode 0: LastFrame.mvKeylinesUn[i] s/ePointInOctave (orientation gate :175-185) */
+  float length;             /* mode 0: LastFrame.mvKeylinesUn[i].lineLength (:189-193) */
+  double normal[3];         /* mode 1: pML->GetNormal() (:294, :312-322) */
+  uint32_t flags;           /* PSL_Q_VALID | PSL_Q_CLAIMS */
+  uint32_t pad_;
+} psl_line_query;
+
+/* LSDmatcher::SearchByProjection, mode 0 = (CurrentFrame, LastFrame, th) (LSDmatcher.cpp:112-215; window test with
+ * TH 0.96, 2-D direction gate cos 10 deg, length ratio >= 0.75, best <= 95), mode 1 = (F, vpMapLines, eval_orient, th)
+ * (:260-352; TH 0.998, 3-D direction gate cos 15 deg, best/second with same-level ratio test nn_ratio, best <= 95).
+ * Candidates come from Frame::GetFeaturesInAreaForLine (Frame.cc:752-826) in its enumeration order.
+ * claimed_in[n] (may be NULL) marks lines whose MapLine has Observations() > 0 before the call.
+ * assign[n] = query whose MapLine ends up in mvpMapLines[i], or -1; *nmatches = return value. */
+int psl_line_match_projection(psl_ctx* ctx, const psl_line_frame_view* frame, const psl_line_query* queries, const uint8_t* query_desc,
+                              int32_t nq, const uint8_t* claimed_in, int32_t mode, float nn_ratio, int32_t* assign,
+                              int32_t* nmatches);
+
+/* InsectLineMatch::SearchMapInsectline (add_src/InsectlineMatch.cpp:9-60; mode 0) and its live twin
+ * Map::AssociatePlanesByBoundary (src/Map.cc:204-272; mode 1: map planes flipped to d >= 0, the distance
+ * threshold carried across structural lines, one match counted per assignment).
+ * planes_cam[n_ljl*4]: Frame::mvPlanes; Tcw[16] row-major 4x4 float (Frame::ComputeWorldPlane, Frame.cc:918-925);
+ * pts[n_ljl*15]: the four 3-D endpoints of the two lines and the junction (mvLines3D[..].first/second, CrossPoint_3D),
+ * doubles; map_planes[n_map*4] float (InsectLine::GetWorldPos_plane); map_bad[n_map] (isBad, mode 0 only, may be
+ * NULL).  assign[n_ljl] = map index in mvpMapInsecs[i] or -1. */
+int psl_plane_assoc(psl_ctx* ctx, const float* planes_cam, const double* pts, int32_t n_ljl, const float* Tcw,
+                    const float* map_planes, const uint8_t* map_bad, int32_t n_map, float d_th, float a_th,
+                    int32_t mode, int32_t* assign, int32_t* nmatches);
+
+/* ------------------------------------------------------------------------------------------------
  * Batched point front end of one tracking step (BASELINE config 2/4), everything resident in HBM.
  * For a batch of B consecutive RGB-D frames it does what the reference does per frame:
  *   Frame::Frame(gray, depth, ...)      ExtractORB (src/Frame.cc:179 -> ORBextractor::operator())

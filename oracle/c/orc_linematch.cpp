@@ -1,0 +1,326 @@
+// TEST INFRASTRUCTURE — CPU oracle for the line matchers (see psl_oracle.h): a sequential restatement of
+// add_src/LSDmatcher.cpp (match/matchNNR :354-413, SearchByGeomNApearance :36-110, SearchByProjection :112-215 and
+// :260-352, FrameBFMatch :492-516, SearchDouble :462-490, lineDescriptorMAD :660-685), the Frame helpers they call
+// (src/Frame.cc:286-309 AssignFeaturesToGridForLine, :752-826 GetFeaturesInAreaForLine, add_src/lineIterator.cpp:33-77)
+// and the structural-line association (add_src/InsectlineMatch.cpp:9-60, src/Map.cc:204-272) on plain arrays.
+// cv::BFMatcher::knnMatch is orc_hamming_knn2 (pinned against cv2.BFMatcher, tests/test_oracle_match.py).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_set>
+#include <vector>
+
+#include "psl_oracle.h"
+
+namespace {
+
+int desc_dist(const uint8_t* a, const uint8_t* b) {  // LSDmatcher::DescriptorDistance, LSDmatcher.cpp:687-703
+  int d = 0;
+  orc_descriptor_distance(a, b, 1, &d);
+  return d;
+}
+
+// ORB_SLAM2::LineIterator (add_src/lineIterator.cpp:33-77): Bresenham over grid coordinates
+struct LineIt {
+  double x1, y1, x2, y2, dx, dy, error;
+  bool steep;
+  int ystep, x, y, maxX;
+  LineIt(double x1_, double y1_, double x2_, double y2_)
+      : x1(x1_), y1(y1_), x2(x2_), y2(y2_), steep(std::abs(y2_ - y1_) > std::abs(x2_ - x1_)) {
+    if (steep) { std::swap(x1, y1); std::swap(x2, y2); }
+    if (x1 > x2) { std::swap(x1, x2); std::swap(y1, y2); }
+    dx = x2 - x1;
+    dy = std::abs(y2 - y1);
+    error = dx / 2.0;
+    ystep = (y1 < y2) ? 1 : -1;
+    x = static_cast<int>(x1);
+    y = static_cast<int>(y1);
+    maxX = static_cast<int>(x2);
+  }
+  bool next(int& px, int& py) {
+    if (x > maxX) return false;
+    if (steep) { px = y; py = x; } else { px = x; py = y; }
+    error -= dy;
+    if (error < 0) { y += ystep; error += dx; }
+    x++;
+    return true;
+  }
+};
+
+struct LineGrid {  // Frame::AssignFeaturesToGridForLine, Frame.cc:286-309
+  std::vector<int> cell[PSL_GRID_COLS][PSL_GRID_ROWS];
+  explicit LineGrid(const psl_line_frame_view& f) {
+    for (int i = 0; i < f.n; ++i) {
+      const psl_keyline& kl = f.kl_un[i];
+      LineIt it(kl.start_x * f.grid_w_inv, kl.start_y * f.grid_h_inv, kl.end_x * f.grid_w_inv, kl.end_y * f.grid_h_inv);
+      int px, py;
+      while (it.next(px, py))
+        if (px >= 0 && px < PSL_GRID_COLS && py >= 0 && py < PSL_GRID_ROWS) cell[px][py].push_back(i);
+    }
+  }
+};
+
+// Frame::GetFeaturesInAreaForLine, Frame.cc:752-826 (minLevel / maxLevel are ignored by the reference)
+void lines_in_area(const psl_line_frame_view& f, const LineGrid& g, float x1, float y1, float x2, float y2, float r,
+                   float TH, std::vector<int>& out) {
+  out.clear();
+  std::unordered_set<int> seen;
+  const float x[3] = {x1, (float)((x1 + x2) / 2.0), x2};
+  const float y[3] = {y1, (float)((y1 + y2) / 2.0), y2};
+  float d1x = x1 - x2, d1y = y1 - y2;
+  const float n1 = (float)sqrt((double)(d1x * d1x + d1y * d1y));
+  d1x /= n1;
+  d1y /= n1;
+  for (int i = 0; i < 3; ++i) {
+    const int nMinCellX = std::max(0, (int)floor((double)((x[i] - f.min_x - r) * f.grid_w_inv)));
+    if (nMinCellX >= PSL_GRID_COLS) continue;
+    const int nMaxCellX = std::min(PSL_GRID_COLS - 1, (int)ceil((double)((x[i] - f.min_x + r) * f.grid_w_inv)));
+    if (nMaxCellX < 0) continue;
+    const int nMinCellY = std::max(0, (int)floor((double)((y[i] - f.min_y - r) * f.grid_h_inv)));
+    if (nMinCellY >= PSL_GRID_ROWS) continue;
+    const int nMaxCellY = std::min(PSL_GRID_ROWS - 1, (int)ceil((double)((y[i] - f.min_y + r) * f.grid_h_inv)));
+    if (nMaxCellY < 0) continue;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+      for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+        for (int j : g.cell[ix][iy]) {
+          if (seen.count(j)) continue;
+          const psl_keyline& kl = f.kl_un[j];
+          float d2x = kl.start_x - kl.end_x, d2y = kl.start_y - kl.end_y;
+          const float n2 = (float)sqrt((double)(d2x * d2x + d2y * d2y));
+          d2x /= n2;
+          d2y /= n2;
+          const float cs = std::abs(d1x * d2x + d1y * d2y);
+          if (cs < TH) continue;
+          const double* L = f.lineeq + 3 * j;
+          const float dist = (float)(L[0] * x[i] + L[1] * y[i] + L[2]);
+          if (fabs(dist) < r) {
+            out.push_back(j);
+            seen.insert(j);
+          }
+        }
+  }
+}
+
+// LSDmatcher::computeAngle2D, LSDmatcher.cpp:19-34 on (e - s) float differences stored as doubles
+double angle2d(double ax, double ay, double bx, double by) {
+  const double dot = ax * bx + ay * by;
+  const double ma = std::sqrt(ax * ax + ay * ay), mb = std::sqrt(bx * bx + by * by);
+  return std::abs(dot / (ma * mb));
+}
+
+// lineDescriptorMAD, LSDmatcher.cpp:660-685 (only the two medians are used by the caller)
+void mad(const std::vector<float>& d0, const std::vector<float>& d1, double& nn_mad, double& nn12_mad) {
+  const size_t n = d0.size();
+  std::vector<float> a(d0);
+  std::sort(a.begin(), a.end());
+  const double med = a[n / 2];
+  for (size_t i = 0; i < n; ++i) a[i] = fabsf((float)(d0[i] - med));
+  std::sort(a.begin(), a.end());
+  nn_mad = 1.4826 * a[n / 2];
+  std::vector<float> g(n);
+  for (size_t i = 0; i < n; ++i) g[i] = d1[i] - d0[i];
+  std::sort(g.begin(), g.end());
+  const double med12 = g[n / 2];
+  for (size_t i = 0; i < n; ++i) a[i] = fabsf((float)(d1[i] - d0[i] - med12));
+  std::sort(a.begin(), a.end());
+  nn12_mad = 1.4826 * a[n / 2];
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_line_grid_cells(const psl_line_frame_view* f, int line, int32_t* cells, int cap) {
+  const psl_keyline& kl = f->kl_un[line];
+  LineIt it(kl.start_x * f->grid_w_inv, kl.start_y * f->grid_h_inv, kl.end_x * f->grid_w_inv, kl.end_y * f->grid_h_inv);
+  int px, py, n = 0;
+  while (it.next(px, py))
+    if (px >= 0 && px < PSL_GRID_COLS && py >= 0 && py < PSL_GRID_ROWS) {
+      if (n < cap) cells[n] = px * PSL_GRID_ROWS + py;
+      ++n;
+    }
+  return n;
+}
+
+int orc_lines_in_area(const psl_line_frame_view* f, float x1, float y1, float x2, float y2, float r, float TH,
+                      int32_t* out, int cap) {
+  LineGrid g(*f);
+  std::vector<int> v;
+  lines_in_area(*f, g, x1, y1, x2, y2, r, TH, v);
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+
+int orc_line_match_nnr(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, float nnr, int32_t* matches12) {
+  int matches = 0;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  if (n1 <= 0 || n2 < 2) return 0;
+  std::vector<int32_t> idx(2 * (size_t)n1), dist(2 * (size_t)n1);
+  orc_hamming_knn2(desc1, n1, desc2, n2, idx.data(), dist.data());
+  for (int i = 0; i < n1; ++i)
+    if ((float)dist[2 * i] < (float)dist[2 * i + 1] * nnr) {
+      matches12[i] = idx[2 * i];
+      ++matches;
+    }
+  return matches;
+}
+
+int orc_line_search_geom(const psl_keyline* kl_last, const uint8_t* desc_last, const uint8_t* has_ml, int n_last,
+                         const psl_keyline* kl_cur, const uint8_t* desc_cur, int n_cur, const float* bounds,
+                         float desc_th, int32_t* assign_cur) {
+  for (int i = 0; i < n_cur; ++i) assign_cur[i] = -1;
+  if (n_cur == 0) return 0;  // CurrentFrame.mLdesc.empty()
+  std::vector<int32_t> m12(std::max(n_last, 1));
+  orc_line_match_nnr(desc_last, n_last, desc_cur, n_cur, desc_th, m12.data());
+  const double deltaWidth = (bounds[2] - bounds[0]) * 0.1, deltaHeight = (bounds[3] - bounds[1]) * 0.1;
+  const double cos_th = std::cos(20.0 / 180.0 * M_PI);
+  int lmatches = 0;
+  for (int i1 = 0; i1 < n_last; ++i1) {
+    if (!has_ml[i1]) continue;
+    const int i2 = m12[i1];
+    if (i2 < 0) continue;
+    const psl_keyline& c = kl_cur[i2];
+    const psl_keyline& l = kl_last[i1];
+    if (c.start_x == 0) continue;
+    const double ang = angle2d((double)(c.e_oct_x - c.s_oct_x), (double)(c.e_oct_y - c.s_oct_y),
+                               (double)(l.e_oct_x - l.s_oct_x), (double)(l.e_oct_y - l.s_oct_y));
+    if (ang < cos_th) continue;
+    if ((fabs(c.s_oct_x - l.s_oct_x) > deltaWidth || fabs(c.s_oct_y - l.s_oct_y) > deltaHeight) &&
+        (fabs(c.e_oct_x - l.e_oct_x) > deltaWidth || fabs(c.e_oct_y - l.e_oct_y) > deltaHeight))
+      continue;
+    assign_cur[i2] = i1;
+    ++lmatches;
+  }
+  return lmatches;
+}
+
+void orc_line_frame_bf_match(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, float nn_ratio, float th,
+                             int32_t* matches) {
+  for (int i = 0; i < n1; ++i) matches[i] = -1;
+  if (n1 <= 0 || n2 < 2) return;
+  std::vector<int32_t> idx(2 * (size_t)n1), dist(2 * (size_t)n1);
+  orc_hamming_knn2(desc1, n1, desc2, n2, idx.data(), dist.data());
+  std::vector<float> d0(n1), d1(n1);
+  for (int i = 0; i < n1; ++i) { d0[i] = (float)dist[2 * i]; d1[i] = (float)dist[2 * i + 1]; }
+  double nn_th, nn12_th;
+  mad(d0, d1, nn_th, nn12_th);
+  nn12_th = nn12_th * 0.5;
+  for (int i = 0; i < n1; ++i) {
+    const double dist_12 = d1[i] - d0[i];
+    if (dist_12 > nn12_th && d0[i] < th && d0[i] < nn_ratio * d1[i]) matches[i] = idx[2 * i];
+  }
+}
+
+int orc_line_search_double(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, float nn_ratio, float th,
+                           int32_t* matches12) {
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<int32_t> m21(n2);
+  orc_line_frame_bf_match(desc1, n1, desc2, n2, nn_ratio, th, matches12);
+  orc_line_frame_bf_match(desc2, n2, desc1, n1, nn_ratio, th, m21.data());
+  int nm = 0;
+  for (int i = 0; i < n1; ++i) {
+    const int j = matches12[i];
+    if (j >= 0) {
+      if (m21[j] != i) matches12[i] = -1;
+      else ++nm;
+    }
+  }
+  return nm;
+}
+
+int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,
+                              const uint8_t* claimed_in, int mode, float nn_ratio, int32_t* assign) {
+  LineGrid g(*f);
+  std::vector<uint8_t> claimed(std::max(f->n, 1), 0);
+  for (int i = 0; i < f->n; ++i) {
+    assign[i] = -1;
+    if (claimed_in) claimed[i] = claimed_in[i];
+  }
+  const double cos10 = std::cos(10.0 / 180.0 * M_PI), cos15 = std::cos(15.0 / 180.0 * M_PI);
+  int nmatches = 0;
+  std::vector<int> cand;
+  for (int q = 0; q < nq; ++q) {
+    const psl_line_query& Q = qs[q];
+    if (!(Q.flags & PSL_Q_VALID)) continue;
+    lines_in_area(*f, g, Q.x1, Q.y1, Q.x2, Q.y2, Q.radius, mode == 0 ? 0.96f : 0.998f, cand);
+    if (cand.empty()) continue;
+    const uint8_t* dq = qdesc + 32 * (size_t)q;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int i2 : cand) {
+      if (claimed[i2]) continue;
+      const psl_keyline& c = f->kl_un[i2];
+      if (mode == 0) {
+        const double ang = angle2d((double)(c.e_oct_x - c.s_oct_x), (double)(c.e_oct_y - c.s_oct_y),
+                                   (double)(Q.ex - Q.sx), (double)(Q.ey - Q.sy));
+        if (ang < cos10) continue;
+        const int dist = desc_dist(dq, f->ldesc + 32 * (size_t)i2);
+        const float mx = std::max(Q.length, c.line_length), mn = std::min(Q.length, c.line_length);
+        if (mn / mx < 0.75) continue;
+        if (dist < bestDist) { bestDist = dist; bestIdx = i2; }
+      } else {
+        const double* p = f->lines3d + 6 * (size_t)i2;
+        const double vx = p[0] - p[3], vy = p[1] - p[4], vz = p[2] - p[5];
+        const float dot = (float)(vx * Q.normal[0] + vy * Q.normal[1] + vz * Q.normal[2]);
+        const float mag_f = (float)std::sqrt(vx * vx + vy * vy + vz * vz);
+        const float mag_ml = (float)std::sqrt(Q.normal[0] * Q.normal[0] + Q.normal[1] * Q.normal[1] + Q.normal[2] * Q.normal[2]);
+        const float angle = std::abs(dot / (mag_f * mag_ml));
+        if (angle < cos15) continue;
+        const int dist = desc_dist(dq, f->ldesc + 32 * (size_t)i2);
+        if (dist < bestDist) {
+          bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = c.octave; bestIdx = i2;
+        } else if (dist < bestDist2) {
+          bestLevel2 = c.octave; bestDist2 = dist;
+        }
+      }
+    }
+    if (bestDist <= 95) {
+      if (mode == 1 && bestLevel == bestLevel2 && bestDist > nn_ratio * bestDist2) continue;
+      assign[bestIdx] = q;
+      if (Q.flags & PSL_Q_CLAIMS) claimed[bestIdx] = 1;
+      ++nmatches;
+    }
+  }
+  return nmatches;
+}
+
+int orc_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
+                    const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign) {
+  int nmatches = 0;
+  float dTh = d_th;  // Map.cc:251 overwrites the function-level threshold (mode 1)
+  for (int i = 0; i < n_ljl; ++i) {
+    assign[i] = -1;
+    float pM[4];  // Frame::ComputeWorldPlane: Tcw^T * plane, cv::Mat CV_32F product (double accumulation, one rounding)
+    for (int k = 0; k < 4; ++k) {
+      double acc = 0;
+      for (int r = 0; r < 4; ++r) acc += (double)Tcw[4 * r + k] * (double)planes_cam[4 * i + r];
+      pM[k] = (float)acc;
+    }
+    const double* P = pts + 15 * (size_t)i;
+    float ldTh = d_th;
+    bool found = false;
+    for (int m = 0; m < n_map; ++m) {
+      if (mode == 0 && map_bad && map_bad[m]) continue;
+      float pW[4] = {map_planes[4 * m], map_planes[4 * m + 1], map_planes[4 * m + 2], map_planes[4 * m + 3]};
+      if (mode == 1 && pW[3] < 0)
+        for (float& v : pW) v = -v;
+      const float angle = pM[0] * pW[0] + pM[1] * pW[1] + pM[2] * pW[2];
+      if (angle > a_th || angle < -a_th) {
+        float d[5];
+        for (int k = 0; k < 5; ++k) d[k] = (float)(pW[0] * P[3 * k] + pW[1] * P[3 * k + 1] + pW[2] * P[3 * k + 2] + pW[3]);
+        const float dis = (d[0] + d[1] + d[2] + d[3] + d[4]) / 5;
+        float& thr = mode == 0 ? ldTh : dTh;
+        if (std::abs(dis) < thr) {
+          thr = dis;  // signed: the reference's quirk (InsectlineMatch.cpp:46-47, Map.cc:250-251)
+          assign[i] = m;
+          found = true;
+          if (mode == 1) ++nmatches;
+        }
+      }
+    }
+    if (mode == 0 && found) ++nmatches;
+  }
+  return nmatches;
+}
+
+}  // extern "C"

@@ -80,6 +80,23 @@ void orc_lbd_binarise(const float* des72, uint8_t* out32);
 int orc_line_extract(const uint8_t* gray, int w, int h, int stride, int nfeatures, psl_keyline* kl, uint8_t* ldesc,
                      double* lineeq, float* lbd72, int cap, int* n_out);
 
+/* ---- line matchers (orc_linematch.cpp): LSDmatcher.cpp, Frame.cc line grid, InsectlineMatch.cpp, Map.cc:204-272 ---- */
+int orc_line_grid_cells(const psl_line_frame_view* f, int line, int32_t* cells, int cap);
+int orc_lines_in_area(const psl_line_frame_view* f, float x1, float y1, float x2, float y2, float r, float TH,
+                      int32_t* out, int cap);
+int orc_line_match_nnr(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, float nnr, int32_t* matches12);
+int orc_line_search_geom(const psl_keyline* kl_last, const uint8_t* desc_last, const uint8_t* has_ml, int n_last,
+                         const psl_keyline* kl_cur, const uint8_t* desc_cur, int n_cur, const float* bounds,
+                         float desc_th, int32_t* assign_cur);
+void orc_line_frame_bf_match(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, float nn_ratio, float th,
+                             int32_t* matches);
+int orc_line_search_double(const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, float nn_ratio, float th,
+                           int32_t* matches12);
+int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,
+                              const uint8_t* claimed_in, int mode, float nn_ratio, int32_t* assign);
+int orc_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
+                    const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign);
+
 /* CPU-baseline harness: B frames, one frame per task on `nthreads` std::threads. */
 int orc_orb_extract_batch_mt(const orc_orb_params* p, const uint8_t* gray, int B, int w, int h, int stride,
                              int64_t frame_stride, int nthreads, int32_t* n_out, uint32_t* desc_xor);

@@ -321,3 +321,72 @@ def lsd_scaled_image(img: np.ndarray) -> np.ndarray:
     out = np.empty((H.value, W.value), np.uint8)
     lib().orc_lsd_scaled_image(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), C.byref(W), C.byref(H))
     return out
+
+
+# ---- line matchers --------------------------------------------------------------------------------
+from psl_slam_b200._lib import LINE_QUERY_DTYPE, make_line_frame_view  # noqa: E402  (ABI structs only)
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, np.uint8)
+
+
+def line_match_nnr(d1, d2, nnr):
+    d1, d2 = _u8(d1), _u8(d2)
+    out = np.zeros(len(d1), np.int32)
+    n = lib().orc_line_match_nnr(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nnr), _p(out))
+    return out, int(n)
+
+
+def line_search_geom(kl_last, d_last, has_ml, kl_cur, d_cur, bounds, desc_th):
+    kl_last, kl_cur = np.ascontiguousarray(kl_last, KEYLINE_DTYPE), np.ascontiguousarray(kl_cur, KEYLINE_DTYPE)
+    d_last, d_cur, has_ml = _u8(d_last), _u8(d_cur), _u8(has_ml)
+    bounds = np.ascontiguousarray(bounds, np.float32)
+    out = np.zeros(len(kl_cur), np.int32)
+    n = lib().orc_line_search_geom(_p(kl_last), _p(d_last), _p(has_ml), len(kl_last), _p(kl_cur), _p(d_cur),
+                                   len(kl_cur), _p(bounds), C.c_float(desc_th), _p(out))
+    return out, int(n)
+
+
+def line_frame_bf_match(d1, d2, nn_ratio, th):
+    d1, d2 = _u8(d1), _u8(d2)
+    out = np.zeros(len(d1), np.int32)
+    lib().orc_line_frame_bf_match(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nn_ratio), C.c_float(th), _p(out))
+    return out
+
+
+def line_search_double(d1, d2, nn_ratio, th):
+    d1, d2 = _u8(d1), _u8(d2)
+    out = np.zeros(len(d1), np.int32)
+    n = lib().orc_line_search_double(_p(d1), len(d1), _p(d2), len(d2), C.c_float(nn_ratio), C.c_float(th), _p(out))
+    return out, int(n)
+
+
+def lines_in_area(view, x1, y1, x2, y2, r, TH):
+    out = np.zeros(max(view.n, 1), np.int32)
+    n = lib().orc_lines_in_area(C.byref(view), C.c_float(x1), C.c_float(y1), C.c_float(x2), C.c_float(y2),
+                                C.c_float(r), C.c_float(TH), _p(out), len(out))
+    return out[:n].copy()
+
+
+def line_match_projection(view, queries, qdesc, claimed_in, mode, nn_ratio):
+    queries = np.ascontiguousarray(queries, LINE_QUERY_DTYPE)
+    qdesc, claimed_in = _u8(qdesc), _u8(claimed_in)
+    out = np.zeros(max(view.n, 1), np.int32)
+    n = lib().orc_line_match_projection(C.byref(view), _p(queries), _p(qdesc), len(queries),
+                                        None if claimed_in is None else _p(claimed_in), mode, C.c_float(nn_ratio),
+                                        _p(out))
+    return out[: view.n].copy(), int(n)
+
+
+def plane_assoc(planes_cam, pts, Tcw, map_planes, map_bad, d_th, a_th, mode):
+    planes_cam = np.ascontiguousarray(planes_cam, np.float32).reshape(-1, 4)
+    pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 15)
+    Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(4, 4)
+    map_planes = np.ascontiguousarray(map_planes, np.float32).reshape(-1, 4)
+    map_bad = _u8(map_bad)
+    out = np.zeros(max(len(planes_cam), 1), np.int32)
+    n = lib().orc_plane_assoc(_p(planes_cam), _p(pts), len(planes_cam), _p(Tcw), _p(map_planes),
+                              None if map_bad is None else _p(map_bad), len(map_planes), C.c_float(d_th),
+                              C.c_float(a_th), mode, _p(out))
+    return out[: len(planes_cam)].copy(), int(n)

@@ -1,0 +1,269 @@
+"""TEST INFRASTRUCTURE — golden-vector generator for the line matchers.
+
+Independent Python restatement (written from the reference source, not from oracle/c) of
+LSDmatcher::matchNNR / match (add_src/LSDmatcher.cpp:354-413), SearchByGeomNApearance (:36-110),
+SearchByProjection (:112-215 and :260-352), FrameBFMatch + lineDescriptorMAD (:492-516, :660-685),
+SearchDouble (:462-490), Frame::AssignFeaturesToGridForLine / GetFeaturesInAreaForLine
+(src/Frame.cc:286-309, 752-826), ORB_SLAM2::LineIterator (add_src/lineIterator.cpp:33-77),
+InsectLineMatch::SearchMapInsectline (add_src/InsectlineMatch.cpp:9-60) and Map::AssociatePlanesByBoundary
+(src/Map.cc:204-272).  cv2.BFMatcher supplies the real knnMatch.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+F32 = np.float32
+COLS, ROWS = 64, 48
+
+
+def knn2_cv2(q, t):
+    import cv2
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, False).knnMatch(np.ascontiguousarray(q), np.ascontiguousarray(t), 2)
+    idx = np.full((len(q), 2), -1, np.int32)
+    dist = np.full((len(q), 2), -1.0, np.float32)
+    for i, r in enumerate(m):
+        for k, d in enumerate(r):
+            idx[i, k] = d.trainIdx
+            dist[i, k] = d.distance
+    return idx, dist
+
+
+def match_nnr(d1, d2, nnr):
+    out = np.full(len(d1), -1, np.int32)
+    if len(d1) == 0 or len(d2) < 2:
+        return out, 0
+    idx, dist = knn2_cv2(d1, d2)
+    ok = dist[:, 0] < dist[:, 1] * F32(nnr)
+    out[ok] = idx[ok, 0]
+    return out, int(ok.sum())
+
+
+def angle2d(ax, ay, bx, by):
+    ax, ay, bx, by = float(ax), float(ay), float(bx), float(by)
+    dot = ax * bx + ay * by
+    return abs(dot / (math.sqrt(ax * ax + ay * ay) * math.sqrt(bx * bx + by * by)))
+
+
+def search_geom(kl_last, d_last, has_ml, kl_cur, d_cur, bounds, desc_th):
+    assign = np.full(len(kl_cur), -1, np.int32)
+    if len(kl_cur) == 0:
+        return assign, 0
+    m12, _ = match_nnr(d_last, d_cur, desc_th)
+    dW = float(F32(bounds[2]) - F32(bounds[0])) * 0.1
+    dH = float(F32(bounds[3]) - F32(bounds[1])) * 0.1
+    cth = math.cos(20.0 / 180.0 * math.pi)
+    n = 0
+    for i1 in range(len(kl_last)):
+        if not has_ml[i1] or m12[i1] < 0:
+            continue
+        c, l = kl_cur[m12[i1]], kl_last[i1]
+        if c["start_x"] == 0:
+            continue
+        a = angle2d(F32(c["e_oct_x"] - c["s_oct_x"]), F32(c["e_oct_y"] - c["s_oct_y"]),
+                    F32(l["e_oct_x"] - l["s_oct_x"]), F32(l["e_oct_y"] - l["s_oct_y"]))
+        if a < cth:
+            continue
+        far_s = abs(float(F32(c["s_oct_x"] - l["s_oct_x"]))) > dW or abs(float(F32(c["s_oct_y"] - l["s_oct_y"]))) > dH
+        far_e = abs(float(F32(c["e_oct_x"] - l["e_oct_x"]))) > dW or abs(float(F32(c["e_oct_y"] - l["e_oct_y"]))) > dH
+        if far_s and far_e:
+            continue
+        assign[m12[i1]] = i1
+        n += 1
+    return assign, n
+
+
+def frame_bf_match(d1, d2, nn_ratio, th):
+    out = np.full(len(d1), -1, np.int32)
+    if len(d1) == 0 or len(d2) < 2:
+        return out
+    idx, dist = knn2_cv2(d1, d2)
+    d0, dd1 = dist[:, 0], dist[:, 1]
+    n = len(d0)
+    med12 = float(np.sort(dd1 - d0)[n // 2])
+    dev = np.abs((dd1 - d0 - F32(0)).astype(np.float64) - med12).astype(np.float32)  # fabsf(float - float - double)
+    nn12 = 1.4826 * float(np.sort(dev)[n // 2]) * 0.5
+    for i in range(n):
+        if float(dd1[i] - d0[i]) > nn12 and d0[i] < F32(th) and d0[i] < F32(nn_ratio) * dd1[i]:
+            out[i] = idx[i, 0]
+    return out
+
+
+def search_double(d1, d2, nn_ratio, th):
+    out = np.full(len(d1), -1, np.int32)
+    if len(d1) == 0 or len(d2) == 0:
+        return out, 0
+    m12 = frame_bf_match(d1, d2, nn_ratio, th)
+    m21 = frame_bf_match(d2, d1, nn_ratio, th)
+    n = 0
+    for i, j in enumerate(m12):
+        if j >= 0 and m21[j] == i:
+            out[i] = j
+            n += 1
+    return out, n
+
+
+def bresenham_cells(x1, y1, x2, y2):
+    """ORB_SLAM2::LineIterator over doubles."""
+    steep = abs(y2 - y1) > abs(x2 - x1)
+    if steep:
+        x1, y1, x2, y2 = y1, x1, y2, x2
+    if x1 > x2:
+        x1, x2, y1, y2 = x2, x1, y2, y1
+    dx, dy = x2 - x1, abs(y2 - y1)
+    err = dx / 2.0
+    ystep = 1 if y1 < y2 else -1
+    x, y, mx = int(x1), int(y1), int(x2)
+    out = []
+    while x <= mx:
+        out.append((y, x) if steep else (x, y))
+        err -= dy
+        if err < 0:
+            y += ystep
+            err += dx
+        x += 1
+    return out
+
+
+class LineFrame:
+    def __init__(self, kl, desc, lineeq, lines3d, bounds):
+        self.kl, self.desc, self.eq, self.l3d = kl, desc, lineeq, lines3d
+        self.min_x, self.min_y, self.max_x, self.max_y = (F32(b) for b in bounds)
+        self.w_inv = F32(COLS) / F32(self.max_x - self.min_x)
+        self.h_inv = F32(ROWS) / F32(self.max_y - self.min_y)
+        self.grid = {}
+        for i, k in enumerate(kl):
+            for (px, py) in bresenham_cells(float(F32(k["start_x"]) * self.w_inv), float(F32(k["start_y"]) * self.h_inv),
+                                            float(F32(k["end_x"]) * self.w_inv), float(F32(k["end_y"]) * self.h_inv)):
+                if 0 <= px < COLS and 0 <= py < ROWS:
+                    self.grid.setdefault((px, py), []).append(i)
+
+    def in_area(self, x1, y1, x2, y2, r, TH):
+        x1, y1, x2, y2, r, TH = F32(x1), F32(y1), F32(x2), F32(y2), F32(r), F32(TH)
+        xs = [x1, F32(float(F32(x1 + x2)) / 2.0), x2]
+        ys = [y1, F32(float(F32(y1 + y2)) / 2.0), y2]
+        d1x, d1y = F32(x1 - x2), F32(y1 - y2)
+        n1 = F32(math.sqrt(float(F32(F32(d1x * d1x) + F32(d1y * d1y)))))
+        d1x, d1y = F32(d1x / n1), F32(d1y / n1)
+        out, seen = [], set()
+        for x, y in zip(xs, ys):
+            cx0 = max(0, math.floor(float(F32(F32(F32(x - self.min_x) - r) * self.w_inv))))
+            if cx0 >= COLS:
+                continue
+            cx1 = min(COLS - 1, math.ceil(float(F32(F32(F32(x - self.min_x) + r) * self.w_inv))))
+            if cx1 < 0:
+                continue
+            cy0 = max(0, math.floor(float(F32(F32(F32(y - self.min_y) - r) * self.h_inv))))
+            if cy0 >= ROWS:
+                continue
+            cy1 = min(ROWS - 1, math.ceil(float(F32(F32(F32(y - self.min_y) + r) * self.h_inv))))
+            if cy1 < 0:
+                continue
+            for ix in range(cx0, cx1 + 1):
+                for iy in range(cy0, cy1 + 1):
+                    for j in self.grid.get((ix, iy), []):
+                        if j in seen:
+                            continue
+                        k = self.kl[j]
+                        d2x, d2y = F32(k["start_x"] - k["end_x"]), F32(k["start_y"] - k["end_y"])
+                        n2 = F32(math.sqrt(float(F32(F32(d2x * d2x) + F32(d2y * d2y)))))
+                        d2x, d2y = F32(d2x / n2), F32(d2y / n2)
+                        cs = abs(F32(F32(d1x * d2x) + F32(d1y * d2y)))
+                        if cs < TH:
+                            continue
+                        L = self.eq[j]
+                        dist = F32(float(L[0]) * float(x) + float(L[1]) * float(y) + float(L[2]))
+                        if abs(float(dist)) < float(r):
+                            out.append(j)
+                            seen.add(j)
+        return out
+
+
+def popcount_dist(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def search_by_projection(fr: LineFrame, q, qdesc, claimed_in, mode, nn_ratio):
+    n = len(fr.kl)
+    assign = np.full(n, -1, np.int32)
+    claimed = np.zeros(n, bool) if claimed_in is None else claimed_in.astype(bool).copy()
+    c10, c15 = math.cos(10.0 / 180.0 * math.pi), math.cos(15.0 / 180.0 * math.pi)
+    nm = 0
+    for qi in range(len(q)):
+        Q = q[qi]
+        if not (Q["flags"] & 1):
+            continue
+        cand = fr.in_area(Q["x1"], Q["y1"], Q["x2"], Q["y2"], Q["radius"], 0.96 if mode == 0 else 0.998)
+        best, best2, lvl, lvl2, bidx = 256, 256, -1, -1, -1
+        for i2 in cand:
+            if claimed[i2]:
+                continue
+            c = fr.kl[i2]
+            if mode == 0:
+                a = angle2d(F32(c["e_oct_x"] - c["s_oct_x"]), F32(c["e_oct_y"] - c["s_oct_y"]),
+                            F32(Q["ex"] - Q["sx"]), F32(Q["ey"] - Q["sy"]))
+                if a < c10:
+                    continue
+                d = popcount_dist(qdesc[qi], fr.desc[i2])
+                mx, mn = max(F32(Q["length"]), F32(c["line_length"])), min(F32(Q["length"]), F32(c["line_length"]))
+                if float(F32(mn / mx)) < 0.75:
+                    continue
+                if d < best:
+                    best, bidx = d, i2
+            else:
+                v = fr.l3d[i2, :3] - fr.l3d[i2, 3:]
+                nrm = Q["normal"]
+                dot = F32(v[0] * nrm[0] + v[1] * nrm[1] + v[2] * nrm[2])
+                mf = F32(math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]))
+                mm = F32(math.sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]))
+                ang = abs(F32(dot / F32(mf * mm)))
+                if float(ang) < c15:
+                    continue
+                d = popcount_dist(qdesc[qi], fr.desc[i2])
+                if d < best:
+                    best2, best, lvl2, lvl, bidx = best, d, lvl, int(c["octave"]), i2
+                elif d < best2:
+                    lvl2, best2 = int(c["octave"]), d
+        if best <= 95:
+            if mode == 1 and lvl == lvl2 and F32(best) > F32(nn_ratio) * F32(best2):
+                continue
+            assign[bidx] = qi
+            if Q["flags"] & 2:
+                claimed[bidx] = True
+            nm += 1
+    return assign, nm
+
+
+def plane_assoc(planes_cam, pts, Tcw, map_planes, map_bad, d_th, a_th, mode):
+    n = len(planes_cam)
+    assign = np.full(n, -1, np.int32)
+    nm = 0
+    dTh = F32(d_th)
+    for i in range(n):
+        pM = (Tcw.astype(np.float64).T @ planes_cam[i].astype(np.float64)).astype(np.float32)
+        ldTh = F32(d_th)
+        found = False
+        for m in range(len(map_planes)):
+            if mode == 0 and map_bad is not None and map_bad[m]:
+                continue
+            pW = map_planes[m].astype(np.float32)
+            if mode == 1 and pW[3] < 0:
+                pW = -pW
+            ang = F32(F32(F32(pM[0] * pW[0]) + F32(pM[1] * pW[1])) + F32(pM[2] * pW[2]))
+            if ang > F32(a_th) or ang < -F32(a_th):
+                d = [F32(float(pW[0]) * pts[i, 3 * k] + float(pW[1]) * pts[i, 3 * k + 1] + float(pW[2]) * pts[i, 3 * k + 2]
+                         + float(pW[3])) for k in range(5)]
+                dis = F32(F32(F32(F32(F32(d[0] + d[1]) + d[2]) + d[3]) + d[4]) / F32(5))
+                thr = ldTh if mode == 0 else dTh
+                if abs(dis) < thr:
+                    if mode == 0:
+                        ldTh = dis
+                    else:
+                        dTh = dis
+                        nm += 1
+                    assign[i] = m
+                    found = True
+        if mode == 0 and found:
+            nm += 1
+    return assign, nm

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|line|all]
+    python -m oracle.pyref.make_goldens [orb|match|line|linematch|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -144,6 +144,92 @@ def make_line():
         print(name, img.shape, "raw", len(raw), "merged", len(merged), "kept", len(kl))
 
 
+def make_linematch():
+    """Line matcher fixtures: real extracted lines of frame pairs (oracle extraction, pinned above) and the
+    independent Python restatement of the matchers over cv2.BFMatcher."""
+    from oracle import orc
+    from oracle.pyref import linematch_py as lm
+    from psl_slam_b200._lib import LINE_QUERY_DTYPE
+    g, _, _ = synth.sequence(2, 2)
+    low = synth.make_lowtex(21)
+    low2 = np.roll(np.roll(low, 3, axis=1), -2, axis=0)
+    low2 = np.clip(low2.astype(np.int32) + np.rint(np.random.default_rng(5).normal(0, 1.0, low.shape)).astype(np.int32),
+                   0, 255).astype(np.uint8)
+    for pair, (a, b) in enumerate([(g[0], g[1]), (low, low2)]):
+        rng = np.random.default_rng(100 + pair)
+        kl_l, d_l, eq_l, _ = orc.line_extract(a, 200)
+        kl_c, d_c, eq_c, _ = orc.line_extract(b, 200)
+        bounds = np.array([0, 0, 640, 480], np.float32)
+        has_ml = (rng.random(len(kl_l)) < 0.85).astype(np.uint8)
+        nnr12, nnr_n = lm.match_nnr(d_l, d_c, 0.95)
+        geom, geom_n = lm.search_geom(kl_l, d_l, has_ml, kl_c, d_c, bounds, 0.95)
+        bf = lm.frame_bf_match(d_l, d_c, 0.95, 50)
+        dbl, dbl_n = lm.search_double(d_l, d_c, 0.95, 50)
+        # projection queries: last-frame lines "projected" with a small displacement
+        nq = len(kl_l)
+        q = np.zeros(nq, LINE_QUERY_DTYPE)
+        jit = rng.normal(0, 1.5, (nq, 4)).astype(np.float32)
+        q["x1"], q["y1"] = kl_l["start_x"] + jit[:, 0], kl_l["start_y"] + jit[:, 1]
+        q["x2"], q["y2"] = kl_l["end_x"] + jit[:, 2], kl_l["end_y"] + jit[:, 3]
+        q["radius"] = 6.0
+        q["sx"], q["sy"], q["ex"], q["ey"] = kl_l["s_oct_x"], kl_l["s_oct_y"], kl_l["e_oct_x"], kl_l["e_oct_y"]
+        q["length"] = kl_l["line_length"]
+        q["flags"] = (has_ml.astype(np.uint32)) | (2 * (rng.random(nq) < 0.8)).astype(np.uint32)
+        # synthetic 3-D lines of the current frame (z = 2 plane + noise) and map-line normals
+        l3d = np.zeros((len(kl_c), 6))
+        for i, k in enumerate(kl_c):
+            l3d[i] = [(k["start_x"] - 320) / 240.0, (k["start_y"] - 240) / 240.0, 2.0 + rng.normal(0, .02),
+                      (k["end_x"] - 320) / 240.0, (k["end_y"] - 240) / 240.0, 2.0 + rng.normal(0, .02)]
+        for i, k in enumerate(kl_l):
+            v = np.array([k["start_x"] - k["end_x"], k["start_y"] - k["end_y"], 0.0]) / 240.0
+            q["normal"][i] = v + rng.normal(0, 0.02, 3) * np.linalg.norm(v)
+        fr = lm.LineFrame(kl_c, d_c, eq_c, l3d, bounds)
+        claimed = (rng.random(len(kl_c)) < 0.2).astype(np.uint8)
+        a0, n0 = lm.search_by_projection(fr, q, d_l, claimed, 0, 0.95)
+        q1 = q.copy()
+        q1["radius"] = np.where(rng.random(nq) < 0.5, 5.0, 8.0).astype(np.float32) * np.float32(3.0)
+        a1, n1 = lm.search_by_projection(fr, q1, d_l, claimed, 1, 0.8)
+        area = [np.array(fr.in_area(q["x1"][i], q["y1"][i], q["x2"][i], q["y2"][i], 6.0, 0.96), np.int32)
+                for i in range(min(nq, 12))]
+        np.savez_compressed(os.path.join(OUT, f"linematch_pair{pair}.npz"), kl_last=kl_l, desc_last=d_l, kl_cur=kl_c,
+                            desc_cur=d_c, eq_cur=eq_c, lines3d_cur=l3d, bounds=bounds, has_ml=has_ml, nnr12=nnr12,
+                            nnr_n=np.int32(nnr_n), geom=geom, geom_n=np.int32(geom_n), bf=bf, dbl=dbl,
+                            dbl_n=np.int32(dbl_n), queries0=q, queries1=q1, claimed=claimed, proj0=a0,
+                            proj0_n=np.int32(n0), proj1=a1, proj1_n=np.int32(n1),
+                            area_cat=np.concatenate(area) if area else np.zeros(0, np.int32),
+                            area_len=np.array([len(x) for x in area], np.int32))
+        print(f"linematch_pair{pair}: lines {len(kl_l)}/{len(kl_c)} nnr {nnr_n} geom {geom_n} bf {(bf >= 0).sum()} "
+              f"double {dbl_n} proj0 {n0} proj1 {n1}")
+    # structural-line / plane association
+    rng = np.random.default_rng(77)
+    n_ljl, n_map = 14, 40
+    Tcw = np.eye(4, dtype=np.float32)
+    Tcw[:3, :3] = synth.trajectory(3, 9)[2][:3, :3].astype(np.float32)
+    Tcw[:3, 3] = [0.1, -0.05, 0.3]
+    nrm = rng.normal(0, 1, (n_map, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    map_planes = np.concatenate([nrm, rng.uniform(-3, 3, (n_map, 1))], 1).astype(np.float32)
+    planes_cam = np.zeros((n_ljl, 4), np.float32)
+    pts = np.zeros((n_ljl, 15))
+    Twc = np.linalg.inv(Tcw.astype(np.float64))
+    for i in range(n_ljl):
+        m = int(rng.integers(0, n_map))
+        pw = map_planes[m].astype(np.float64) * (1 if i % 3 else -1)
+        pw[3] += rng.normal(0, 0.03)
+        planes_cam[i] = (Twc.T @ pw).astype(np.float32)  # pi_c = Twc^T pi_w
+        # 5 world points near the plane
+        for k in range(5):
+            p = rng.normal(0, 1, 3)
+            p -= (pw[:3] @ p + pw[3]) * pw[:3]
+            pts[i, 3 * k:3 * k + 3] = p + rng.normal(0, 0.02, 3)
+    bad = (rng.random(n_map) < 0.15).astype(np.uint8)
+    a_0, n_0 = lm.plane_assoc(planes_cam, pts, Tcw, map_planes, bad, 0.1, 0.86, 0)
+    a_1, n_1 = lm.plane_assoc(planes_cam, pts, Tcw, map_planes, None, 0.1, 0.86, 1)
+    np.savez_compressed(os.path.join(OUT, "plane_assoc.npz"), planes_cam=planes_cam, pts=pts, Tcw=Tcw,
+                        map_planes=map_planes, map_bad=bad, assign0=a_0, n0=np.int32(n_0), assign1=a_1, n1=np.int32(n_1))
+    print("plane_assoc: mode0", n_0, a_0.tolist(), "mode1", n_1, a_1.tolist())
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(OUT, exist_ok=True)
@@ -153,3 +239,5 @@ if __name__ == "__main__":
         make_match()
     if what in ("line", "all"):
         make_line()
+    if what in ("linematch", "all"):
+        make_linematch()

@@ -40,6 +40,9 @@ KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4
                           ("num_pixels", "<i4")])  # psl_keyline, 68 B
 QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
                         ("u_right", "<f4"), ("angle", "<f4"), ("flags", "<u4")])  # psl_proj_query
+LINE_QUERY_DTYPE = np.dtype([("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4"), ("radius", "<f4"),
+                             ("sx", "<f4"), ("sy", "<f4"), ("ex", "<f4"), ("ey", "<f4"), ("length", "<f4"),
+                             ("normal", "<f8", (3,)), ("flags", "<u4"), ("pad_", "<u4")])  # psl_line_query, 72 B
 Q_VALID, Q_CLAIMS = 1, 2
 
 
@@ -47,6 +50,25 @@ class FrameView(C.Structure):  # psl_frame_view
     _fields_ = [("n", C.c_int32), ("kps_un", C.c_void_p), ("u_right", C.c_void_p), ("desc", C.c_void_p),
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
                 ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float)]
+
+
+class LineFrameView(C.Structure):  # psl_line_frame_view
+    _fields_ = [("n", C.c_int32), ("kl_un", C.c_void_p), ("ldesc", C.c_void_p), ("lineeq", C.c_void_p),
+                ("lines3d", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float),
+                ("max_y", C.c_float), ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float)]
+
+
+def make_line_frame_view(kl_un, ldesc, lineeq, lines3d, bounds):
+    """Build a psl_line_frame_view over numpy arrays (kept alive by the returned tuple)."""
+    kl_un = np.ascontiguousarray(kl_un, KEYLINE_DTYPE)
+    ldesc = np.ascontiguousarray(ldesc, np.uint8)
+    lineeq = np.ascontiguousarray(lineeq, np.float64)
+    l3 = None if lines3d is None else np.ascontiguousarray(lines3d, np.float64)
+    min_x, min_y, max_x, max_y = (np.float32(b) for b in bounds)
+    fv = LineFrameView(len(kl_un), kl_un.ctypes.data, ldesc.ctypes.data, lineeq.ctypes.data,
+                       None if l3 is None else l3.ctypes.data, min_x, min_y, max_x, max_y,
+                       np.float32(64) / np.float32(max_x - min_x), np.float32(48) / np.float32(max_y - min_y))
+    return fv, (kl_un, ldesc, lineeq, l3)
 
 
 class MatchParams(C.Structure):  # psl_match_params

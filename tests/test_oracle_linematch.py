@@ -1,0 +1,62 @@
+"""CPU: the line-matcher oracle (oracle/c/orc_linematch.cpp) against goldens made by the independent Python
+restatement over the real cv2.BFMatcher (oracle/pyref/linematch_py.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+PAIRS = golden_names("linematch_")
+
+
+def view_of(g):
+    from psl_slam_b200._lib import make_line_frame_view
+    return make_line_frame_view(g["kl_cur"], g["desc_cur"], g["eq_cur"], g["lines3d_cur"], g["bounds"])
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_descriptor_matchers(orc, name):
+    g = load_golden(name)
+    m, n = orc.line_match_nnr(g["desc_last"], g["desc_cur"], 0.95)
+    assert np.array_equal(m, g["nnr12"]) and n == int(g["nnr_n"])
+    a, n = orc.line_search_geom(g["kl_last"], g["desc_last"], g["has_ml"], g["kl_cur"], g["desc_cur"], g["bounds"], 0.95)
+    assert np.array_equal(a, g["geom"]) and n == int(g["geom_n"])
+    assert np.array_equal(orc.line_frame_bf_match(g["desc_last"], g["desc_cur"], 0.95, 50), g["bf"])
+    m, n = orc.line_search_double(g["desc_last"], g["desc_cur"], 0.95, 50)
+    assert np.array_equal(m, g["dbl"]) and n == int(g["dbl_n"])
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_line_grid_and_projection(orc, name):
+    g = load_golden(name)
+    view, keep = view_of(g)
+    q = g["queries0"]
+    off = 0
+    for i, ln in enumerate(g["area_len"]):
+        got = orc.lines_in_area(view, q["x1"][i], q["y1"][i], q["x2"][i], q["y2"][i], 6.0, 0.96)
+        assert np.array_equal(got, g["area_cat"][off:off + ln])
+        off += ln
+    a, n = orc.line_match_projection(view, q, g["desc_last"], g["claimed"], 0, 0.95)
+    assert np.array_equal(a, g["proj0"]) and n == int(g["proj0_n"])
+    a, n = orc.line_match_projection(view, g["queries1"], g["desc_last"], g["claimed"], 1, 0.8)
+    assert np.array_equal(a, g["proj1"]) and n == int(g["proj1_n"])
+
+
+def test_plane_assoc(orc):
+    g = load_golden("plane_assoc")
+    a, n = orc.plane_assoc(g["planes_cam"], g["pts"], g["Tcw"], g["map_planes"], g["map_bad"], 0.1, 0.86, 0)
+    assert np.array_equal(a, g["assign0"]) and n == int(g["n0"])
+    a, n = orc.plane_assoc(g["planes_cam"], g["pts"], g["Tcw"], g["map_planes"], None, 0.1, 0.86, 1)
+    assert np.array_equal(a, g["assign1"]) and n == int(g["n1"])
+
+
+def test_degenerate_inputs(orc):
+    d = np.zeros((0, 32), np.uint8)
+    one = np.full((1, 32), 7, np.uint8)
+    three = np.arange(96, dtype=np.uint8).reshape(3, 32)
+    assert orc.line_match_nnr(d, three, 0.95)[1] == 0
+    m, n = orc.line_match_nnr(three, one, 0.95)  # < 2 train rows: the reference reads out of bounds; pinned: no match
+    assert n == 0 and np.all(m == -1)
+    assert np.all(orc.line_frame_bf_match(three, one, 0.95, 50) == -1)
+    assert orc.line_search_double(d, three, 0.95, 50)[1] == 0
+    a, n = orc.plane_assoc(np.zeros((0, 4)), np.zeros((0, 15)), np.eye(4), np.zeros((3, 4)), None, 0.1, 0.86, 0)
+    assert n == 0 and len(a) == 0
