@@ -6,5 +6,6 @@ include/psl_frontend.h (libpsl_frontend.so, hand-written sm_100a CUDA).  No CPU 
 from ._lib import KEYLINE_DTYPE, KP_DTYPE, PslError, default_config  # noqa: F401
 from .orb import Context, ORBextractor  # noqa: F401
 from .line import LINEextractor  # noqa: F401
+from .line_matcher import InsectLineMatch, LineFrameData, LSDmatcher  # noqa: F401
 from .matcher import FrameData, ORBmatcher, hamming_knn2  # noqa: F401
 from .tracking import make_camera, make_track_params, track_orb_batch, track_orb_batch_dev  # noqa: F401

@@ -114,7 +114,9 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_orb_tables", "psl_orb_extract", "psl_orb_extract_batch", "psl_orb_extract_batch_dev", "psl_debug_fetch", "psl_profile_enable",
            "psl_profile_read", "psl_launch_count", "psl_descriptor_distance", "psl_hamming_knn2",
            "psl_match_projection", "psl_match_bow", "psl_track_orb_batch", "psl_track_orb_batch_dev",
-           "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev"]
+           "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
+           "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
+           "psl_plane_assoc"]
 
 _lib = None
 
@@ -153,6 +155,13 @@ def lib():
         L.psl_line_extract.argtypes = [_p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p]
         L.psl_line_extract_batch.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _p, _p, _i, _p]
         L.psl_line_extract_batch_dev.argtypes = [_p, _p, _i, _i, _i, _i, _l, _p, _p, _p, _p, _i, _p]
+        _f = C.c_float
+        L.psl_line_match_nnr.argtypes = [_p, _p, _i, _p, _i, _f, _p, _p]
+        L.psl_line_search_geom.argtypes = [_p, _p, _p, _p, _i, _p, _p, _i, _p, _f, _p, _p]
+        L.psl_line_frame_bf_match.argtypes = [_p, _p, _i, _p, _i, _f, _f, _p]
+        L.psl_line_search_double.argtypes = [_p, _p, _i, _p, _i, _f, _f, _p, _p]
+        L.psl_line_match_projection.argtypes = [_p, _p, _p, _p, _i, _p, _i, _f, _p, _p]
+        L.psl_plane_assoc.argtypes = [_p, _p, _p, _i, _p, _p, _p, _i, _f, _f, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

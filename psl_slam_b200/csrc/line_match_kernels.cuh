@@ -1,0 +1,37 @@
+// Launchers of the line matchers (all asynchronous on `st`), batch-first: B independent pairs, [B][cap] blocks.
+#pragma once
+#include "psl_common.cuh"
+
+namespace psl {
+
+constexpr int kLineCells = 80;     // grid cells one line can cross (Bresenham over a 64x48 grid: <= 66 in-grid steps)
+constexpr int kMaxLinesPerFrame = 4096;  // line index field of the projection keys
+
+// the lines of a batch of frames: frame b owns rows [b*cap, b*cap + n[b])
+struct LineSet {
+  const psl_keyline* kl;  // may be null for descriptor-only matchers
+  const uint8_t* desc;
+  const int32_t* n;       // device array [B]
+  int32_t cap;
+};
+
+void launch_line_knn2(const LineSet& Q, const LineSet& T, uint2* knn, int B, cudaStream_t st);
+void launch_line_nnr(const LineSet& Q, const uint2* knn, float nnr, int32_t* m12, int32_t* nmatches, int B,
+                     cudaStream_t st);
+void launch_line_geom(const LineSet& Last, const uint8_t* has_ml, const LineSet& Cur, const uint2* knn, float desc_th,
+                      float bounds_w, float bounds_h, int32_t* assign_cur, int32_t* nmatches, int B, cudaStream_t st);
+void launch_line_bfmatch(const LineSet& Q, const LineSet& T, const uint2* knn, float nn_ratio, float th,
+                         int32_t* matches, int B, cudaStream_t st);
+void launch_line_mutual(const LineSet& A, const int32_t* m21, int cap2, int32_t* m12, int32_t* nmatches, int B,
+                        cudaStream_t st);
+// 3 launches: line grid cells, static keys, ordered resolve
+void launch_line_projection(const LineSet& F, const double* lineeq, const double* lines3d, const psl_line_query* queries,
+                            const uint8_t* qdesc, const int32_t* nq, int qcap, int max_nq, float min_x, float min_y,
+                            float w_inv, float h_inv, int mode, float nn_ratio, const uint8_t* claimed_in,
+                            uint16_t* cells, uint8_t* ncell, unsigned long long* keys, uint8_t* claimed, int32_t* assign,
+                            int32_t* nmatches, int B, cudaStream_t st);
+void launch_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
+                        const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign,
+                        int32_t* nmatches, cudaStream_t st);
+
+}  // namespace psl

@@ -1,0 +1,215 @@
+// C-ABI of the line matchers (include/psl_frontend.h): host-pointer, single-pair entry points that stage the
+// plain arrays in HBM, run the batch kernels with B = 1 and copy the result back.
+#include <algorithm>
+#include <cstring>
+
+#include "line_match_kernels.cuh"
+#include "psl_ctx.cuh"
+
+using namespace psl;
+
+#define PSL_UP(buf, src, nbytes)                                                                    \
+  do {                                                                                              \
+    int rc__ = ensure(ctx, buf, (nbytes));                                                          \
+    if (rc__) return rc__;                                                                          \
+    if ((nbytes) > 0) PSL_CK(cudaMemcpyAsync((buf).p, (src), (nbytes), cudaMemcpyHostToDevice, ctx->stream)); \
+  } while (0)
+#define PSL_ENS(buf, nbytes)                    \
+  do {                                          \
+    int rc__ = ensure(ctx, buf, (nbytes));      \
+    if (rc__) return rc__;                      \
+  } while (0)
+
+namespace {
+// uploads desc1 -> m_qdesc, desc2 -> m_desc, (n1, n2) -> m_n and returns the two LineSets (cap = n, B = 1)
+int stage_desc_pair(psl_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, LineSet& A, LineSet& Bs) {
+  PSL_UP(ctx->m_qdesc, d1, (size_t)n1 * 32);
+  PSL_UP(ctx->m_desc, d2, (size_t)n2 * 32);
+  const int32_t nn[2] = {n1, n2};
+  PSL_UP(ctx->m_n, nn, sizeof(nn));
+  A = LineSet{nullptr, ctx->m_qdesc.as<uint8_t>(), ctx->m_n.as<int32_t>(), std::max(n1, 1)};
+  Bs = LineSet{nullptr, ctx->m_desc.as<uint8_t>(), ctx->m_n.as<int32_t>() + 1, std::max(n2, 1)};
+  return PSL_OK;
+}
+bool bad_desc_args(const uint8_t* d1, int n1, const uint8_t* d2, int n2) {
+  return n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535 || (n1 > 0 && !d1) || (n2 > 0 && !d2);
+}
+}  // namespace
+
+extern "C" {
+
+int psl_line_match_nnr(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2, float nnr,
+                       int32_t* matches12, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (bad_desc_args(desc1, n1, desc2, n2) || !nmatches || (n1 > 0 && !matches12)) return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  if (n1 == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  LineSet A, T;
+  int rc = stage_desc_pair(ctx, desc1, n1, desc2, n2, A, T);
+  if (rc) return rc;
+  PSL_ENS(ctx->m_best, (size_t)n1 * 8);
+  PSL_ENS(ctx->m_assign, (size_t)n1 * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(A, T, ctx->m_best.as<uint2>(), 1, ctx->stream);
+  launch_line_nnr(A, ctx->m_best.as<uint2>(), nnr, ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, ctx->stream);
+  prof_span(ctx, 15, e, 2);
+  PSL_CK(cudaMemcpyAsync(matches12, ctx->m_assign.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+int psl_line_search_geom(psl_ctx* ctx, const psl_keyline* kl_last, const uint8_t* desc_last,
+                         const uint8_t* has_mapline_last, int32_t n_last, const psl_keyline* kl_cur,
+                         const uint8_t* desc_cur, int32_t n_cur, const float* bounds, float desc_th,
+                         int32_t* assign_cur, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (bad_desc_args(desc_last, n_last, desc_cur, n_cur) || !nmatches || !bounds || (n_last > 0 && (!kl_last || !has_mapline_last)) ||
+      (n_cur > 0 && (!kl_cur || !assign_cur)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  if (n_cur == 0) return PSL_OK;  // CurrentFrame.mLdesc.empty(), LSDmatcher.cpp:40-43
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  LineSet L, Cn;
+  int rc = stage_desc_pair(ctx, desc_last, n_last, desc_cur, n_cur, L, Cn);
+  if (rc) return rc;
+  PSL_UP(ctx->m_misc[0], kl_last, (size_t)n_last * sizeof(psl_keyline));
+  PSL_UP(ctx->m_misc[1], kl_cur, (size_t)n_cur * sizeof(psl_keyline));
+  PSL_UP(ctx->m_claimed, has_mapline_last, (size_t)n_last);
+  L.kl = ctx->m_misc[0].as<psl_keyline>();
+  Cn.kl = ctx->m_misc[1].as<psl_keyline>();
+  PSL_ENS(ctx->m_best, (size_t)std::max(n_last, 1) * 8);
+  PSL_ENS(ctx->m_assign, (size_t)n_cur * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(L, Cn, ctx->m_best.as<uint2>(), 1, ctx->stream);
+  launch_line_geom(L, ctx->m_claimed.as<uint8_t>(), Cn, ctx->m_best.as<uint2>(), desc_th, bounds[2] - bounds[0],
+                   bounds[3] - bounds[1], ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, ctx->stream);
+  prof_span(ctx, 15, e, 2);
+  PSL_CK(cudaMemcpyAsync(assign_cur, ctx->m_assign.p, (size_t)n_cur * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+int psl_line_frame_bf_match(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
+                            float nn_ratio, float th, int32_t* matches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (bad_desc_args(desc1, n1, desc2, n2) || (n1 > 0 && !matches)) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (n1 == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  LineSet A, T;
+  int rc = stage_desc_pair(ctx, desc1, n1, desc2, n2, A, T);
+  if (rc) return rc;
+  PSL_ENS(ctx->m_best, (size_t)n1 * 8);
+  PSL_ENS(ctx->m_assign, (size_t)n1 * 4);
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(A, T, ctx->m_best.as<uint2>(), 1, ctx->stream);
+  launch_line_bfmatch(A, T, ctx->m_best.as<uint2>(), nn_ratio, th, ctx->m_assign.as<int32_t>(), 1, ctx->stream);
+  prof_span(ctx, 15, e, 2);
+  PSL_CK(cudaMemcpyAsync(matches, ctx->m_assign.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+int psl_line_search_double(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
+                           float nn_ratio, float th, int32_t* matches12, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (bad_desc_args(desc1, n1, desc2, n2) || !nmatches || (n1 > 0 && !matches12)) return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  if (n1 == 0) return PSL_OK;
+  if (n2 == 0) {  // LSDmatcher.cpp:469-470
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    return PSL_OK;
+  }
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  LineSet A, T;
+  int rc = stage_desc_pair(ctx, desc1, n1, desc2, n2, A, T);
+  if (rc) return rc;
+  PSL_ENS(ctx->m_best, (size_t)n1 * 8);
+  PSL_ENS(ctx->m_cand_count, (size_t)n2 * 8);
+  PSL_ENS(ctx->m_assign, (size_t)n1 * 4);
+  PSL_ENS(ctx->m_accepted, (size_t)n2 * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  cudaStream_t st = ctx->stream;
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(A, T, ctx->m_best.as<uint2>(), 1, st);
+  launch_line_bfmatch(A, T, ctx->m_best.as<uint2>(), nn_ratio, th, ctx->m_assign.as<int32_t>(), 1, st);
+  launch_line_knn2(T, A, ctx->m_cand_count.as<uint2>(), 1, st);
+  launch_line_bfmatch(T, A, ctx->m_cand_count.as<uint2>(), nn_ratio, th, ctx->m_accepted.as<int32_t>(), 1, st);
+  launch_line_mutual(A, ctx->m_accepted.as<int32_t>(), T.cap, ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, st);
+  prof_span(ctx, 15, e, 5);
+  PSL_CK(cudaMemcpyAsync(matches12, ctx->m_assign.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
+int psl_line_match_projection(psl_ctx* ctx, const psl_line_frame_view* fv, const psl_line_query* queries,
+                              const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in, int32_t mode,
+                              float nn_ratio, int32_t* assign, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!fv || !nmatches || nq < 0 || fv->n < 0 || fv->n > kMaxLinesPerFrame || (mode != 0 && mode != 1) ||
+      (fv->n > 0 && (!fv->kl_un || !fv->ldesc || !fv->lineeq || !assign || (mode == 1 && !fv->lines3d))) ||
+      (nq > 0 && (!queries || !query_desc)))
+    return fail(ctx, PSL_E_INVALID, "bad argument (at most 4096 lines per frame)");
+  *nmatches = 0;
+  const int n = fv->n;
+  if (n == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const int qcap = std::max(nq, 1);
+  PSL_UP(ctx->m_misc[0], fv->kl_un, (size_t)n * sizeof(psl_keyline));
+  PSL_UP(ctx->m_desc, fv->ldesc, (size_t)n * 32);
+  PSL_UP(ctx->m_misc[1], fv->lineeq, (size_t)n * 24);
+  if (mode == 1) PSL_UP(ctx->m_misc[2], fv->lines3d, (size_t)n * 48);
+  PSL_UP(ctx->m_misc[3], queries, (size_t)nq * sizeof(psl_line_query));
+  PSL_UP(ctx->m_qdesc, query_desc, (size_t)nq * 32);
+  if (claimed_in) PSL_UP(ctx->m_claimed, claimed_in, (size_t)n);
+  const int32_t nn[2] = {n, nq};
+  PSL_UP(ctx->m_n, nn, sizeof(nn));
+  PSL_ENS(ctx->m_misc[4], (size_t)n * kLineCells * 2);
+  PSL_ENS(ctx->m_misc[5], (size_t)n);
+  PSL_ENS(ctx->m_misc[6], (size_t)qcap * n * 8);
+  PSL_ENS(ctx->m_misc[7], (size_t)n);
+  PSL_ENS(ctx->m_assign, (size_t)n * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  LineSet F{ctx->m_misc[0].as<psl_keyline>(), ctx->m_desc.as<uint8_t>(), ctx->m_n.as<int32_t>(), n};
+  size_t e = prof_mark(ctx);
+  launch_line_projection(F, ctx->m_misc[1].as<double>(), mode == 1 ? ctx->m_misc[2].as<double>() : nullptr,
+                         ctx->m_misc[3].as<psl_line_query>(), ctx->m_qdesc.as<uint8_t>(), ctx->m_n.as<int32_t>() + 1, qcap,
+                         nq, fv->min_x, fv->min_y, fv->grid_w_inv, fv->grid_h_inv, mode, nn_ratio,
+                         claimed_in ? ctx->m_claimed.as<uint8_t>() : nullptr, ctx->m_misc[4].as<uint16_t>(),
+                         ctx->m_misc[5].as<uint8_t>(), ctx->m_misc[6].as<unsigned long long>(), ctx->m_misc[7].as<uint8_t>(),
+                         ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, ctx->stream);
+  prof_span(ctx, 15, e, 3);
+  PSL_CK(cudaMemcpyAsync(assign, ctx->m_assign.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+int psl_plane_assoc(psl_ctx* ctx, const float* planes_cam, const double* pts, int32_t n_ljl, const float* Tcw,
+                    const float* map_planes, const uint8_t* map_bad, int32_t n_map, float d_th, float a_th,
+                    int32_t mode, int32_t* assign, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!nmatches || n_ljl < 0 || n_map < 0 || (mode != 0 && mode != 1) || !Tcw ||
+      (n_ljl > 0 && (!planes_cam || !pts || !assign)) || (n_map > 0 && !map_planes))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  if (n_ljl == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  PSL_UP(ctx->m_misc[0], planes_cam, (size_t)n_ljl * 16);
+  PSL_UP(ctx->m_misc[1], pts, (size_t)n_ljl * 120);
+  PSL_UP(ctx->m_misc[2], Tcw, 64);
+  PSL_UP(ctx->m_misc[3], map_planes, (size_t)n_map * 16);
+  if (map_bad) PSL_UP(ctx->m_claimed, map_bad, (size_t)n_map);
+  PSL_ENS(ctx->m_assign, (size_t)n_ljl * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  size_t e = prof_mark(ctx);
+  launch_plane_assoc(ctx->m_misc[0].as<float>(), ctx->m_misc[1].as<double>(), n_ljl, ctx->m_misc[2].as<float>(),
+                     ctx->m_misc[3].as<float>(), map_bad ? ctx->m_claimed.as<uint8_t>() : nullptr, n_map, d_th, a_th, mode,
+                     ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), ctx->stream);
+  prof_span(ctx, 15, e, 1);
+  PSL_CK(cudaMemcpyAsync(assign, ctx->m_assign.p, (size_t)n_ljl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+"""Host-side mirrors of ORB_SLAM2::LSDmatcher (add_inc/LSDmatcher.h:20-75 in the reference) and
+ORB_SLAM2::InsectLineMatch (add_inc/InsectlineMatch.h:9-17) over the C-ABI.  The reference methods take
+Frame / KeyFrame / MapLine / InsectLine objects; here the caller passes the plain arrays those objects hold —
+exactly what crosses the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import KEYLINE_DTYPE, LINE_QUERY_DTYPE, make_line_frame_view
+from .orb import Context, _ptr
+
+
+@dataclass
+class LineFrameData:
+    """What the line matchers read from a Frame: mvKeylinesUn, mLdesc, mvKeyLineFunctions, mvLines3D and the
+    image bounds (include/Frame.h)."""
+    kl_un: np.ndarray             # KEYLINE_DTYPE [n]
+    ldesc: np.ndarray             # u8 [n,32]
+    lineeq: np.ndarray            # f64 [n,3]
+    lines3d: np.ndarray | None    # f64 [n,6] (first xyz, second xyz)
+    bounds: tuple                 # (mnMinX, mnMinY, mnMaxX, mnMaxY)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+class LSDmatcher:
+    TH_HIGH = 80  # LSDmatcher.cpp:12-14
+    TH_LOW = 50
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio: float = 0.95, checkOri: bool = True, *, ctx: Context | None = None, device: int = 0):
+        """LSDmatcher(float nnratio=0.95, bool checkOri=true) — LSDmatcher.cpp:16-18."""
+        if ctx is None:
+            cfg = _lib.default_config()
+            cfg.device = device
+            ctx = Context(cfg)
+        self.ctx = ctx
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+
+    def match(self, desc1, desc2, nnr):
+        """match / matchNNR — LSDmatcher.cpp:354-413.  Returns (matches_12, count)."""
+        d1, d2 = _u8(desc1), _u8(desc2)
+        out = np.full(len(d1), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_line_match_nnr(self.ctx.handle, _ptr(d1), len(d1), _ptr(d2), len(d2),
+                                                     C.c_float(nnr), _ptr(out), C.byref(nm)))
+        return out, nm.value
+
+    matchNNR = match
+
+    def SearchByGeomNApearance(self, cur: LineFrameData, last: LineFrameData, has_mapline_last, desc_th):
+        """SearchByGeomNApearance(CurrentFrame, LastFrame, desc_th) — LSDmatcher.cpp:36-110.
+        Returns (assign_cur [n_cur] = last-frame line index or -1, count)."""
+        kl_l, kl_c = np.ascontiguousarray(last.kl_un, KEYLINE_DTYPE), np.ascontiguousarray(cur.kl_un, KEYLINE_DTYPE)
+        d_l, d_c, has = _u8(last.ldesc), _u8(cur.ldesc), _u8(has_mapline_last)
+        b = np.ascontiguousarray(cur.bounds, np.float32)
+        out = np.full(len(kl_c), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_line_search_geom(self.ctx.handle, _ptr(kl_l), _ptr(d_l), _ptr(has), len(kl_l),
+                                                       _ptr(kl_c), _ptr(d_c), len(kl_c), _ptr(b), C.c_float(desc_th),
+                                                       _ptr(out), C.byref(nm)))
+        return out, nm.value
+
+    def FrameBFMatch(self, ldesc1, ldesc2, TH):
+        """FrameBFMatch(ldesc1, ldesc2, LineMatches, TH) — LSDmatcher.cpp:492-516."""
+        d1, d2 = _u8(ldesc1), _u8(ldesc2)
+        out = np.full(len(d1), -1, np.int32)
+        self.ctx.check(_lib.lib().psl_line_frame_bf_match(self.ctx.handle, _ptr(d1), len(d1), _ptr(d2), len(d2),
+                                                          C.c_float(self.mfNNratio), C.c_float(TH), _ptr(out)))
+        return out
+
+    def SearchDouble(self, ldesc1, ldesc2):
+        """SearchDouble(InitialFrame, CurrentFrame, LineMatches) — LSDmatcher.cpp:462-490."""
+        d1, d2 = _u8(ldesc1), _u8(ldesc2)
+        out = np.full(len(d1), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_line_search_double(self.ctx.handle, _ptr(d1), len(d1), _ptr(d2), len(d2),
+                                                         C.c_float(self.mfNNratio), C.c_float(self.TH_LOW), _ptr(out),
+                                                         C.byref(nm)))
+        return out, nm.value
+
+    def _project(self, frame: LineFrameData, queries, qdesc, claimed, mode):
+        fv, keep = make_line_frame_view(frame.kl_un, frame.ldesc, frame.lineeq, frame.lines3d, frame.bounds)
+        queries = np.ascontiguousarray(queries, LINE_QUERY_DTYPE)
+        qdesc = _u8(qdesc)
+        cl = None if claimed is None else _u8(claimed)
+        assign = np.full(fv.n, -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_line_match_projection(self.ctx.handle, C.byref(fv), _ptr(queries), _ptr(qdesc),
+                                                            len(queries), None if cl is None else _ptr(cl), mode,
+                                                            C.c_float(self.mfNNratio), _ptr(assign), C.byref(nm)))
+        return assign, nm.value
+
+    def SearchByProjectionLastFrame(self, cur: LineFrameData, queries, last_desc, claimed=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th) — LSDmatcher.cpp:112-215."""
+        return self._project(cur, queries, last_desc, claimed, 0)
+
+    def SearchByProjectionMapLines(self, frame: LineFrameData, queries, ml_desc, claimed=None):
+        """SearchByProjection(F, vpMapLines, eval_orient, th) — LSDmatcher.cpp:260-352."""
+        return self._project(frame, queries, ml_desc, claimed, 1)
+
+
+class InsectLineMatch:
+    def __init__(self, dTh: float = 0.1, aTh: float = 0.86, *, ctx: Context | None = None, device: int = 0):
+        """InsectLineMatch(float dTh=0.1, float aTh=0.86) — InsectlineMatch.cpp:8."""
+        if ctx is None:
+            cfg = _lib.default_config()
+            cfg.device = device
+            ctx = Context(cfg)
+        self.ctx, self.dTh, self.aTh = ctx, float(dTh), float(aTh)
+
+    def _run(self, planes_cam, pts, Tcw, map_planes, map_bad, mode):
+        planes_cam = np.ascontiguousarray(planes_cam, np.float32).reshape(-1, 4)
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 15)
+        Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(4, 4)
+        map_planes = np.ascontiguousarray(map_planes, np.float32).reshape(-1, 4)
+        bad = None if map_bad is None else _u8(map_bad)
+        out = np.full(len(planes_cam), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_plane_assoc(self.ctx.handle, _ptr(planes_cam), _ptr(pts), len(planes_cam), _ptr(Tcw),
+                                                  _ptr(map_planes), None if bad is None else _ptr(bad), len(map_planes),
+                                                  C.c_float(self.dTh), C.c_float(self.aTh), mode, _ptr(out), C.byref(nm)))
+        return out, nm.value
+
+    def SearchMapInsectline(self, planes_cam, pts, Tcw, map_planes, map_bad=None):
+        """SearchMapInsectline(Frame&, vpMapInsectline) — InsectlineMatch.cpp:9-60."""
+        return self._run(planes_cam, pts, Tcw, map_planes, map_bad, 0)
+
+    def AssociatePlanesByBoundary(self, planes_cam, pts, Tcw, map_planes):
+        """Map::AssociatePlanesByBoundary(Frame&, dTh, aTh) — src/Map.cc:204-272 (the live twin)."""
+        return self._run(planes_cam, pts, Tcw, map_planes, None, 1)

@@ -68,7 +68,10 @@ def test_batch_mixed_frames_vs_oracle(orc):
     padded[:, :, :640] = frames
     ex2 = LINEextractor(chunk_frames=16)
     kl2, ld2, eq2, n2 = ex2.extract_batch(padded[:, :, :640])
-    assert np.array_equal(n, n2) and kl.tobytes() == kl2.tobytes() and np.array_equal(ld, ld2)
+    assert np.array_equal(n, n2)
+    for b in range(len(frames)):  # rows past n[b] are unspecified
+        assert kl[b, : n[b]].tobytes() == kl2[b, : n[b]].tobytes() and np.array_equal(ld[b, : n[b]], ld2[b, : n[b]])
+        assert np.array_equal(eq[b, : n[b]], eq2[b, : n[b]])
 
 
 def test_capacity_errors_are_loud():

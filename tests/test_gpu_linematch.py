@@ -1,0 +1,124 @@
+"""GPU: the CUDA line matchers through the C-ABI against the oracle and the committed goldens (bit-exact
+indices and counts)."""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+PAIRS = golden_names("linematch_")
+
+
+def _frames(g):
+    from psl_slam_b200 import LineFrameData
+    b = tuple(g["bounds"])
+    cur = LineFrameData(g["kl_cur"], g["desc_cur"], g["eq_cur"], g["lines3d_cur"], b)
+    last = LineFrameData(g["kl_last"], g["desc_last"], None, None, b)
+    return cur, last
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_descriptor_matchers_vs_golden(name):
+    from psl_slam_b200 import LSDmatcher
+    g = load_golden(name)
+    cur, last = _frames(g)
+    m = LSDmatcher(0.95, True)
+    m12, n = m.match(g["desc_last"], g["desc_cur"], 0.95)
+    assert np.array_equal(m12, g["nnr12"]) and n == int(g["nnr_n"])
+    a, n = m.SearchByGeomNApearance(cur, last, g["has_ml"], 0.95)
+    assert np.array_equal(a, g["geom"]) and n == int(g["geom_n"])
+    assert np.array_equal(m.FrameBFMatch(g["desc_last"], g["desc_cur"], 50), g["bf"])
+    d, n = m.SearchDouble(g["desc_last"], g["desc_cur"])
+    assert np.array_equal(d, g["dbl"]) and n == int(g["dbl_n"])
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_projection_vs_golden(name):
+    from psl_slam_b200 import LSDmatcher
+    g = load_golden(name)
+    cur, _ = _frames(g)
+    a, n = LSDmatcher(0.95).SearchByProjectionLastFrame(cur, g["queries0"], g["desc_last"], g["claimed"])
+    assert np.array_equal(a, g["proj0"]) and n == int(g["proj0_n"])
+    a, n = LSDmatcher(0.8).SearchByProjectionMapLines(cur, g["queries1"], g["desc_last"], g["claimed"])
+    assert np.array_equal(a, g["proj1"]) and n == int(g["proj1_n"])
+
+
+def test_random_sweep_vs_oracle(orc):
+    """Random descriptors / geometry at several sizes, including the degenerate ones."""
+    from psl_slam_b200 import LineFrameData, LSDmatcher
+    from psl_slam_b200._lib import KEYLINE_DTYPE, LINE_QUERY_DTYPE, make_line_frame_view
+    rng = np.random.default_rng(3)
+    m = LSDmatcher(0.9)
+    for n1, n2 in [(0, 5), (5, 0), (1, 1), (3, 1), (2, 2), (40, 57), (200, 200), (333, 150)]:
+        base = rng.integers(0, 256, (max(n1, n2, 1), 32), dtype=np.uint8)
+        d1 = base[:n1] ^ (rng.random((n1, 32)) < 0.08).astype(np.uint8) * rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+        d2 = base[rng.permutation(len(base))[:n2]] if n2 else np.zeros((0, 32), np.uint8)
+        want, wn = orc.line_match_nnr(d1, d2, 0.9)
+        got, gn = m.match(d1, d2, 0.9)
+        assert np.array_equal(got, want) and gn == wn
+        assert np.array_equal(m.FrameBFMatch(d1, d2, 50), orc.line_frame_bf_match(d1, d2, 0.9, 50))
+        want, wn = orc.line_search_double(d1, d2, 0.9, 50)
+        got, gn = m.SearchDouble(d1, d2)
+        assert np.array_equal(got, want) and gn == wn
+        if n1 == 0 or n2 == 0:
+            continue
+        # random segments in a 640x480 image, queries near them
+        def rand_kl(n):
+            kl = np.zeros(n, KEYLINE_DTYPE)
+            kl["start_x"], kl["start_y"] = rng.uniform(0, 639, n), rng.uniform(0, 479, n)
+            ang, ln = rng.uniform(0, np.pi, n), rng.uniform(50, 300, n)
+            kl["end_x"] = np.clip(kl["start_x"] + ln * np.cos(ang), 0, 639)
+            kl["end_y"] = np.clip(kl["start_y"] + ln * np.sin(ang), 0, 479)
+            for a, b in (("s_oct_x", "start_x"), ("s_oct_y", "start_y"), ("e_oct_x", "end_x"), ("e_oct_y", "end_y")):
+                kl[a] = kl[b]
+            kl["line_length"] = np.hypot(kl["end_x"] - kl["start_x"], kl["end_y"] - kl["start_y"])
+            return kl
+        klc = rand_kl(n2)
+        eq = np.zeros((n2, 3))
+        for i, k in enumerate(klc):
+            l = np.cross([k["start_x"], k["start_y"], 1.0], [k["end_x"], k["end_y"], 1.0])
+            eq[i] = l / np.hypot(l[0], l[1])
+        l3d = rng.normal(0, 1, (n2, 6))
+        q = np.zeros(n1, LINE_QUERY_DTYPE)
+        src = klc[rng.integers(0, n2, n1)]
+        q["x1"], q["y1"] = src["start_x"] + rng.normal(0, 2, n1), src["start_y"] + rng.normal(0, 2, n1)
+        q["x2"], q["y2"] = src["end_x"] + rng.normal(0, 2, n1), src["end_y"] + rng.normal(0, 2, n1)
+        q["radius"] = rng.choice([3.0, 6.0, 15.0, 24.0], n1)
+        q["sx"], q["sy"], q["ex"], q["ey"] = q["x1"], q["y1"], q["x2"], q["y2"]
+        q["length"] = src["line_length"] * rng.uniform(0.6, 1.2, n1)
+        q["normal"] = rng.normal(0, 1, (n1, 3))
+        q["flags"] = rng.integers(0, 4, n1)
+        claimed = (rng.random(n2) < 0.1).astype(np.uint8)
+        bounds = (0.0, 0.0, 640.0, 480.0)
+        view, keep = make_line_frame_view(klc, d2, eq, l3d, bounds)
+        fd = LineFrameData(klc, d2, eq, l3d, bounds)
+        for mode in (0, 1):
+            want, wn = orc.line_match_projection(view, q, d1, claimed, mode, 0.9)
+            got, gn = (m.SearchByProjectionLastFrame if mode == 0 else m.SearchByProjectionMapLines)(fd, q, d1, claimed)
+            assert np.array_equal(got, want) and gn == wn, (n1, n2, mode)
+        kll = rand_kl(n1)
+        has = (rng.random(n1) < 0.8).astype(np.uint8)
+        want, wn = orc.line_search_geom(kll, d1, has, klc, d2, bounds, 0.95)
+        got, gn = m.SearchByGeomNApearance(fd, LineFrameData(kll, d1, None, None, bounds), has, 0.95)
+        assert np.array_equal(got, want) and gn == wn
+
+
+def test_plane_assoc_vs_golden_and_oracle(orc):
+    from psl_slam_b200 import InsectLineMatch
+    g = load_golden("plane_assoc")
+    m = InsectLineMatch(0.1, 0.86)
+    a, n = m.SearchMapInsectline(g["planes_cam"], g["pts"], g["Tcw"], g["map_planes"], g["map_bad"])
+    assert np.array_equal(a, g["assign0"]) and n == int(g["n0"])
+    a, n = m.AssociatePlanesByBoundary(g["planes_cam"], g["pts"], g["Tcw"], g["map_planes"])
+    assert np.array_equal(a, g["assign1"]) and n == int(g["n1"])
+    rng = np.random.default_rng(8)
+    for n_ljl, n_map in [(0, 4), (3, 0), (25, 300)]:
+        pc = rng.normal(0, 1, (n_ljl, 4)).astype(np.float32)
+        pts = rng.normal(0, 1, (n_ljl, 15))
+        mp = rng.normal(0, 1, (n_map, 4)).astype(np.float32)
+        mp[:, :3] /= np.linalg.norm(mp[:, :3], axis=1, keepdims=True) + 1e-9
+        pc[:, :3] /= np.linalg.norm(pc[:, :3], axis=1, keepdims=True) + 1e-9
+        for mode in (0, 1):
+            want, wn = orc.plane_assoc(pc, pts, np.eye(4), mp, None, 1.5, 0.5, mode)
+            got, gn = m.__class__(1.5, 0.5, ctx=m.ctx)._run(pc, pts, np.eye(4), mp, None, mode)
+            assert np.array_equal(got, want) and gn == wn
