@@ -54,7 +54,19 @@ def algorithmic_bytes(w, h, nlevels, scale, nfeat):
         "grid": nfeat * (28 + 2) + 3073 * 4,          # keypoints in, CSR out
         "candidates": nfeat * 20 * 32 + nfeat * 64,   # ~20 candidate descriptors per query
         "resolve": nfeat * 20 * 4 + nfeat * 4,        # candidate lists in, assignment out
+        # line stages (LSD works on the 0.8x image, Ws x Hs = lrint(.8 w) x lrint(.8 h))
+        "lsd_prologue": 2 * w * h + (w * h + LS(w, h)) + LS(w, h) * (1 + 4 + 4 + 1) + LS(w, h) * (8 + 6),
+        #                 blur R+W    resize R + W        gradient R u8, W deg/n2/used   seed keys R, W (key, idx)
+        "lsd_order": 2 * LS(w, h) * 6 * 2,            # two radix passes over (u16 key, u32 idx) pairs, R + W
+        "lsd_grow": LS(w, h) * (4 + 4 + 1 + 1) + LS(w, h) * 4,  # deg, n2, used R+W once each + the seed list
+        "line_merge": 4096 * 16 * 4,                  # raw segments through two merge passes (bound by the raw cap)
+        "lbd": 2 * w * h + w * h + w * h * 4 + 200 * 63 * 120 * 4,  # blur R+W, Sobel R + W short2, 63 x len gathers/line
+        "line_match": 2 * 200 * 32 + 200 * 68 * 2,    # two descriptor sets + keylines
     }
+
+
+def LS(w, h):
+    return int(round(w * 0.8)) * int(round(h * 0.8))
 
 
 def synth_frames(n_distinct, seed=4):
@@ -116,18 +128,20 @@ class ClockSampler(threading.Thread):
 def cpu_run(gray, depth, T12, nthreads):
     from oracle import orc
     p = orc.params(ORB["nfeatures"], ORB["scale"], ORB["nlevels"], ORB["ini"], ORB["mn"])
-    return orc.track_batch_mt(gray, depth, T12, cam6(), p, TRACK["th"], TRACK["nn_ratio"], TRACK["ori"], nthreads)
+    return orc.frontend_batch_mt(gray, depth, T12, cam6(), p, TRACK["th"], TRACK["nn_ratio"], TRACK["ori"],
+                                 LINE["nfeatures"], LINE["desc_th"], nthreads)
 
 
 def cpu_baseline(gray, depth, T12, budget_s: float = 14.0):
-    """The oracle (CPU port of the reference path: extract + stereo + SearchByProjection) on a bounded
-    sample of the same workload, 1 thread (how the reference runs, Frame.cc:179-180) and all threads."""
+    """The oracle (CPU port of the reference path: ORB + LSD/LBD extraction + stereo + both frame-to-frame
+    matchers) on a bounded sample of the same workload, 1 thread (how the reference runs, Frame.cc:179-180)
+    and all threads."""
     from oracle import orc
     orc.build()
     cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    cpu_run(gray[:3], depth[:3], T12[:3], 1)
-    t1 = (time.perf_counter() - t0) / 3
+    cpu_run(gray[:2], depth[:2], T12[:2], 1)
+    t1 = (time.perf_counter() - t0) / 2
     n1 = max(3, min(len(gray), int(budget_s * 0.3 / t1)))
     t0 = time.perf_counter()
     cpu_run(gray[:n1], depth[:n1], T12[:n1], 1)
@@ -139,8 +153,8 @@ def cpu_baseline(gray, depth, T12, budget_s: float = 14.0):
     cpu_run(g, d, t, cores)
     fpsN = total / (time.perf_counter() - t0)
     return {"value": fpsN, "unit": "frames/s", "cores": cores, "kind": "port", "value_1_thread": fps1,
-            "sample": f"{total} frames (extract + stereo + SearchByProjection vs previous frame) on {cores} threads, "
-                      f"one frame per task; {n1} frames on 1 thread"}
+            "sample": f"{total} frames (ORB + LSD/LBD extract + stereo + SearchByProjection + SearchByGeomNApearance vs "
+                      f"previous frame) on {cores} threads, one frame per task; {n1} frames on 1 thread"}
 
 
 def run_reference(args, rank, world):
@@ -151,7 +165,7 @@ def run_reference(args, rank, world):
     orc.build()
     gray, depth, T12 = synth_frames(8)
     cores = os.cpu_count() or 1
-    per_step = 4 * cores
+    per_step = 2 * cores
     idx = ping_pong(len(gray), per_step)
     g, d, t = gray[idx], depth[idx], T12[idx]
     for _ in range(args.warmup):
@@ -174,13 +188,14 @@ def run_reference(args, rank, world):
 
 METRIC = "frames/s ORB+LSD/LBD extract+match @640x480"
 TRACK = dict(th=15.0, nn_ratio=0.9, ori=True)  # Tracking.cc:1166,1189
+LINE = dict(nfeatures=200, desc_th=0.95)        # TUM1.yaml:60-63, Tracking.cc:1182
 
 
 def workload_config(frames_per_gpu):
-    return {"workload": "cfg2-batched: full point front end per frame — ORBextractor (TUM1.yaml: 1000 features, "
-                        "8 levels, 1.2, FAST 20/7) + ComputeStereoFromRGBD + SearchByProjection(Cur, Last, th=15) "
-                        "between consecutive synthetic 640x480 RGB-D frames (ICL intrinsics); line stages "
-                        "(LSD/LBD) are not in the timed path yet",
+    return {"workload": "cfg4: batched combined front end per frame — ORBextractor (TUM1.yaml: 1000 features, 8 levels, "
+                        "1.2, FAST 20/7) + LINEextractor (LSD, long-line merge, top 200, LBD) + ComputeStereoFromRGBD + "
+                        "SearchByProjection(Cur, Last, th=15) + SearchByGeomNApearance(Cur, Last, 0.95) between "
+                        "consecutive synthetic textured 640x480 RGB-D frames (ICL intrinsics)",
             "frames_per_step_per_gpu": frames_per_gpu, "width": W, "height": H,
             "l2_policy": "inputs larger than L2 (frames_per_step x 307 KB >> 126 MB), no flush",
             "parallelism": "frames sharded across GPUs, no collective"}
@@ -194,6 +209,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=2048, help="frames per step per GPU")
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--line-chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -213,13 +229,18 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from psl_slam_b200 import ORBextractor
+    from psl_slam_b200 import Context, ORBextractor, default_config
+    from psl_slam_b200._lib import FrontendOut
 
     F = args.frames
-    ex = ORBextractor(ORB["nfeatures"], ORB["scale"], ORB["nlevels"], ORB["ini"], ORB["mn"], device=local,
-                      max_width=W, max_height=H, chunk_frames=args.chunk)
-    cap = ex.cap
-    from psl_slam_b200 import make_camera, make_track_params, synth, track_orb_batch_dev
+    cfg = default_config()
+    cfg.device, cfg.max_width, cfg.max_height = local, W, H
+    cfg.orb_nfeatures, cfg.orb_scale_factor, cfg.orb_nlevels = ORB["nfeatures"], ORB["scale"], ORB["nlevels"]
+    cfg.orb_ini_th_fast, cfg.orb_min_th_fast = ORB["ini"], ORB["mn"]
+    cfg.chunk_frames, cfg.line_chunk_frames, cfg.line_nfeatures = args.chunk, args.line_chunk, LINE["nfeatures"]
+    ex = ORBextractor(ctx=Context(cfg))
+    cap, lcap = ex.cap, LINE["nfeatures"]
+    from psl_slam_b200 import make_camera, make_track_params, synth, track_frontend_batch_dev
     K = synth.ICL
     cam = make_camera(K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], K["depth_factor"])
     tprm = make_track_params(TRACK["th"], TRACK["nn_ratio"], TRACK["ori"])
@@ -235,13 +256,21 @@ def main():
     d_z = torch.empty((F, cap), dtype=torch.float32, device="cuda")
     d_assign = torch.empty((F, cap), dtype=torch.int32, device="cuda")
     d_nm = torch.zeros(F, dtype=torch.int32, device="cuda")
+    d_kl = torch.empty((F, lcap, 68), dtype=torch.uint8, device="cuda")
+    d_ld = torch.empty((F, lcap, 32), dtype=torch.uint8, device="cuda")
+    d_eq = torch.empty((F, lcap, 3), dtype=torch.float64, device="cuda")
+    d_nl = torch.zeros(F, dtype=torch.int32, device="cuda")
+    d_la = torch.empty((F, lcap), dtype=torch.int32, device="cuda")
+    d_lnm = torch.zeros(F, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(ex.ctx.stream(), device=local)
+    fo_dev = FrontendOut(d_kps.data_ptr(), d_desc.data_ptr(), d_n.data_ptr(), d_ur.data_ptr(), d_z.data_ptr(),
+                         d_assign.data_ptr(), d_nm.data_ptr(), cap, lcap, d_kl.data_ptr(), d_ld.data_ptr(),
+                         d_eq.data_ptr(), d_nl.data_ptr(), d_la.data_ptr(), d_lnm.data_ptr())
 
     def step_dev():
-        track_orb_batch_dev(ex, d_gray.data_ptr(), d_depth.data_ptr(), F, W, H, d_T.data_ptr(), cam, tprm,
-                            d_kps.data_ptr(), d_desc.data_ptr(), d_n.data_ptr(), d_ur.data_ptr(), d_z.data_ptr(),
-                            d_assign.data_ptr(), d_nm.data_ptr(), cap)
+        track_frontend_batch_dev(ex, d_gray.data_ptr(), d_depth.data_ptr(), F, W, H, d_T.data_ptr(), cam, tprm,
+                                 LINE["desc_th"], fo_dev)
 
     def barrier():
         if world > 1:
@@ -274,6 +303,7 @@ def main():
         ms = float(t.item())
     n_kp = int(d_n.sum().item())
     n_match = int(d_nm.sum().item())
+    n_lines, n_lmatch = int(d_nl.sum().item()), int(d_lnm.sum().item())
     value = world * F * args.steps / (ms * 1e-3)
 
     # ---- per-stage pass (same steps, events between stages) -> roofline ----------------------
@@ -326,16 +356,22 @@ def main():
     h_ur = torch.empty((F, cap), dtype=torch.float32, **pin)
     h_z = torch.empty((F, cap), dtype=torch.float32, **pin)
     h_assign = torch.empty((F, cap), dtype=torch.int32, **pin)
+    h_kl = torch.empty((F, lcap, 68), dtype=torch.uint8, **pin)
+    h_ld = torch.empty((F, lcap, 32), dtype=torch.uint8, **pin)
+    h_eq = torch.empty((F, lcap, 3), dtype=torch.float64, **pin)
+    h_nl = torch.empty(F, dtype=torch.int32, **pin)
+    h_la = torch.empty((F, lcap), dtype=torch.int32, **pin)
+    h_lnm = torch.empty(F, dtype=torch.int32, **pin)
+    fo_host = FrontendOut(h_kps.data_ptr(), h_desc.data_ptr(), h_n.data_ptr(), h_ur.data_ptr(), h_z.data_ptr(),
+                          h_assign.data_ptr(), h_nm.data_ptr(), cap, lcap, h_kl.data_ptr(), h_ld.data_ptr(),
+                          h_eq.data_ptr(), h_nl.data_ptr(), h_la.data_ptr(), h_lnm.data_ptr())
 
     def step_host():
-        ex.ctx.check(_lib.lib().psl_track_orb_batch(ex.ctx.handle, h_gray.data_ptr(), h_depth.data_ptr(), F, W, H,
-                                                    h_T.data_ptr(), C.addressof(cam), C.addressof(tprm),
-                                                    h_kps.data_ptr(), h_desc.data_ptr(), h_n.data_ptr(),
-                                                    h_ur.data_ptr(), h_z.data_ptr(), h_assign.data_ptr(),
-                                                    h_nm.data_ptr(), cap))
+        ex.ctx.check(_lib.lib().psl_track_frontend_batch(ex.ctx.handle, h_gray.data_ptr(), h_depth.data_ptr(), F, W, H,
+                                                         h_T.data_ptr(), C.addressof(cam), C.addressof(tprm),
+                                                         C.c_float(LINE["desc_th"]), C.byref(fo_host)))
 
-    for _ in range(2):
-        step_host()
+    step_host()
     barrier()
     e2e_steps = max(2, args.steps // 2)
     t0 = time.perf_counter()
@@ -348,8 +384,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     e2e = {"value": world * F * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": F * (W * H * 3 + 48),
-           "d2h_bytes_per_step": F * (cap * (28 + 32 + 12) + 8), "steps": e2e_steps,
-           "results_equal_device_path": int(h_n.sum().item()) == n_kp and int(h_nm.sum().item()) == n_match}
+           "d2h_bytes_per_step": F * (cap * (28 + 32 + 12) + lcap * (68 + 32 + 24 + 4) + 16), "steps": e2e_steps,
+           "results_equal_device_path": int(h_n.sum().item()) == n_kp and int(h_nm.sum().item()) == n_match and
+           int(h_nl.sum().item()) == n_lines and int(h_lnm.sum().item()) == n_lmatch}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -361,7 +398,8 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": workload_config(F), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
-               "keypoints_per_frame": n_kp / F, "matches_per_frame": n_match / max(F - 1, 1)}
+               "keypoints_per_frame": n_kp / F, "matches_per_frame": n_match / max(F - 1, 1),
+               "lines_per_frame": n_lines / F, "line_matches_per_frame": n_lmatch / max(F - 1, 1)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -340,6 +340,36 @@ int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth
                         uint8_t* desc, int32_t* n, float* u_right, float* z, int32_t* assign, int32_t* nmatches,
                         int32_t cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched combined front end of one tracking step (BASELINE config 4): per frame b of a batch of consecutive
+ * RGB-D frames, everything the reference does between Tracking::GrabImageRGBD and Optimizer::PoseOptimization
+ * on the feature side:
+ *   Frame::Frame            ExtractORB + ExtractLSD (LINEextractor::operator()) + ComputeStereoFromRGBD
+ *                           (src/Frame.cc:179-192)
+ *   TrackWithMotionModel    LSDmatcher::SearchByGeomNApearance(Cur, Last, 0.95)   (src/Tracking.cc:1182-1183)
+ *                           ORBmatcher::SearchByProjection(Cur, Last, th)         (src/Tracking.cc:1193)
+ * with frame b-1 playing LastFrame (all of its lines / depth-valid points carrying map features).
+ * Outputs are [B][cap] (points) and [B][line_cap] (lines) blocks; line_assign[b][i] = index of the line of
+ * frame b-1 whose MapLine lands on line i of frame b, or -1; line_nmatches[0] = 0.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct psl_frontend_out {
+  psl_keypoint* kps; uint8_t* desc; int32_t* n; float* u_right; float* z; int32_t* assign; int32_t* nmatches;
+  int32_t cap;
+  int32_t line_cap;
+  psl_keyline* kl; uint8_t* ldesc; double* lineeq; int32_t* nl; int32_t* line_assign; int32_t* line_nmatches;
+} psl_frontend_out;
+
+/* DEVICE pointers (inputs as psl_track_orb_batch_dev, every psl_frontend_out pointer in HBM); asynchronous. */
+int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                                 const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                                 int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                                 const psl_track_params* prm, float line_desc_th, const psl_frontend_out* out);
+
+/* HOST pointers (tightly packed frames); H2D and D2H copies are part of the call. */
+int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
+                             const float* Tcw, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* out);
+
 /* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).
  * Stages: 0 pyramid resize, 1 FAST cells, 2 octree selection, 3 Gaussian blur, 4 orientation+rBRIEF,
  * 5 single-pair matcher calls, 6 stereo + projection queries, 7 feature grid, 8 candidate lists,

@@ -57,3 +57,50 @@ extern "C" int orc_track_batch_mt(const orc_orb_params* p, const uint8_t* gray, 
   });
   return err.load() ? -1 : 0;
 }
+
+// Combined front end (cfg 4): the point chain above plus, per frame, LINEextractor::operator() and, per
+// consecutive pair, LSDmatcher::SearchByGeomNApearance(Cur, Last, desc_th) (Tracking.cc:1182-1183).
+extern "C" int orc_frontend_batch_mt(const orc_orb_params* p, const uint8_t* gray, const uint16_t* depth, int B, int w,
+                                     int h, const float* Tcw, const float* cam, float th, float nn_ratio, int check_ori,
+                                     int line_nfeatures, float line_desc_th, int nthreads, int32_t* n_out,
+                                     int32_t* nmatches_out, int32_t* nl_out, int32_t* line_nmatches_out) {
+  int rc = orc_track_batch_mt(p, gray, depth, B, w, h, Tcw, cam, th, nn_ratio, check_ori, nthreads, n_out, nmatches_out);
+  if (rc) return rc;
+  const int cap = line_nfeatures;
+  std::vector<psl_keyline> kl((size_t)B * cap);
+  std::vector<uint8_t> ld((size_t)B * cap * 32);
+  std::vector<double> eq((size_t)B * cap * 3);
+  std::atomic<int> next(0), err(0);
+  auto run = [&](auto&& fn) {
+    next = 0;
+    std::vector<std::thread> th_;
+    for (int t = 1; t < nthreads; ++t) th_.emplace_back(fn);
+    fn();
+    for (auto& t : th_) t.join();
+  };
+  run([&]() {
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= B) break;
+      int n = 0;
+      if (orc_line_extract(gray + (size_t)b * w * h, w, h, w, line_nfeatures, &kl[(size_t)b * cap], &ld[(size_t)b * cap * 32],
+                           &eq[(size_t)b * cap * 3], nullptr, cap, &n))
+        err = 1;
+      nl_out[b] = n;
+    }
+  });
+  line_nmatches_out[0] = 0;
+  const float bounds[4] = {0.f, 0.f, (float)w, (float)h};
+  run([&]() {
+    std::vector<int32_t> assign(cap);
+    std::vector<uint8_t> has(cap, 1);
+    for (;;) {
+      const int b = 1 + next.fetch_add(1);
+      if (b >= B) break;
+      const size_t o0 = (size_t)(b - 1) * cap, o1 = (size_t)b * cap;
+      line_nmatches_out[b] = orc_line_search_geom(&kl[o0], &ld[o0 * 32], has.data(), nl_out[b - 1], &kl[o1], &ld[o1 * 32],
+                                                  nl_out[b], bounds, line_desc_th, assign.data());
+    }
+  });
+  return err.load() ? -1 : 0;
+}

@@ -105,6 +105,11 @@ int orc_track_batch_mt(const orc_orb_params* p, const uint8_t* gray, const uint1
                        const float* Tcw, const float* cam, float th, float nn_ratio, int check_ori, int nthreads,
                        int32_t* n_out, int32_t* nmatches_out);
 
+int orc_frontend_batch_mt(const orc_orb_params* p, const uint8_t* gray, const uint16_t* depth, int B, int w, int h,
+                          const float* Tcw, const float* cam, float th, float nn_ratio, int check_ori,
+                          int line_nfeatures, float line_desc_th, int nthreads, int32_t* n_out, int32_t* nmatches_out,
+                          int32_t* nl_out, int32_t* line_nmatches_out);
+
 #ifdef __cplusplus
 }
 #endif

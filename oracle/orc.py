@@ -239,6 +239,25 @@ def track_batch_mt(gray, depth, Tcw12, cam6, p: OrbParams | None = None, th=15.0
     return n, nm
 
 
+def frontend_batch_mt(gray, depth, Tcw12, cam6, p: OrbParams | None = None, th=15.0, nn_ratio=0.9, check_ori=True,
+                      line_nfeatures=200, line_desc_th=0.95, nthreads=1):
+    """CPU-baseline harness for the combined front end (points as track_batch_mt + LINEextractor per frame +
+    SearchByGeomNApearance per consecutive pair).  Returns (n, nmatches, nl, line_nmatches)."""
+    p = p or params()
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    T = np.ascontiguousarray(Tcw12, np.float32)
+    cam = np.ascontiguousarray(cam6, np.float32)
+    B, H, W = gray.shape
+    n, nm, nl, lnm = (np.zeros(B, np.int32) for _ in range(4))
+    rc = lib().orc_frontend_batch_mt(C.byref(p), _p(gray), _p(depth), B, W, H, _p(T), _p(cam), C.c_float(th),
+                                     C.c_float(nn_ratio), int(check_ori), line_nfeatures, C.c_float(line_desc_th),
+                                     nthreads, _p(n), _p(nm), _p(nl), _p(lnm))
+    if rc != 0:
+        raise RuntimeError("orc_frontend_batch_mt failed")
+    return n, nm, nl, lnm
+
+
 # ---- lines ------------------------------------------------------------------------------------------
 from psl_slam_b200._lib import KEYLINE_DTYPE  # noqa: E402  (ABI struct only)
 

@@ -86,6 +86,13 @@ class TrackParams(C.Structure):  # psl_track_params
                 ("th_dist", C.c_int32)]
 
 
+class FrontendOut(C.Structure):  # psl_frontend_out
+    _fields_ = [("kps", C.c_void_p), ("desc", C.c_void_p), ("n", C.c_void_p), ("u_right", C.c_void_p),
+                ("z", C.c_void_p), ("assign", C.c_void_p), ("nmatches", C.c_void_p), ("cap", C.c_int32),
+                ("line_cap", C.c_int32), ("kl", C.c_void_p), ("ldesc", C.c_void_p), ("lineeq", C.c_void_p),
+                ("nl", C.c_void_p), ("line_assign", C.c_void_p), ("line_nmatches", C.c_void_p)]
+
+
 class FeatureVector(C.Structure):  # psl_feature_vector
     _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("offs", C.c_void_p), ("idx", C.c_void_p)]
 
@@ -116,7 +123,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_match_projection", "psl_match_bow", "psl_track_orb_batch", "psl_track_orb_batch_dev",
            "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
-           "psl_plane_assoc"]
+           "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev"]
 
 _lib = None
 
@@ -162,6 +169,8 @@ def lib():
         L.psl_line_search_double.argtypes = [_p, _p, _i, _p, _i, _f, _f, _p, _p]
         L.psl_line_match_projection.argtypes = [_p, _p, _p, _p, _i, _p, _i, _f, _p, _p]
         L.psl_plane_assoc.argtypes = [_p, _p, _p, _i, _p, _p, _p, _i, _f, _f, _i, _p, _p]
+        L.psl_track_frontend_batch_dev.argtypes = [_p, _p, _i, _l, _p, _i, _l, _i, _i, _i, _p, _p, _p, _f, _p]
+        L.psl_track_frontend_batch.argtypes = [_p, _p, _p, _i, _i, _i, _p, _p, _p, _f, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "frame_kernels.cuh"
+#include "line_match_kernels.cuh"
 #include "match_kernels.cuh"
 #include "psl_ctx.cuh"
 
@@ -119,6 +120,97 @@ int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth
   PSL_CK(cudaMemcpyAsync(u_right, M[6].p, nk * 4, cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(z, M[7].p, nk * 4, cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(assign, M[8].p, nk * 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
+
+int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                                 const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                                 int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                                 const psl_track_params* prm, float line_desc_th, const psl_frontend_out* o) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!o || !o->kl || !o->ldesc || !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || o->line_cap < 1 ||
+      o->line_cap > kMaxLinesPerFrame)
+    return fail(ctx, PSL_E_INVALID, "bad line output block");
+  if (B <= 0) return B == 0 ? PSL_OK : fail(ctx, PSL_E_INVALID, "bad argument");
+  int rc = psl_track_orb_batch_dev(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px,
+                                   depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, o->kps, o->desc, o->n, o->u_right, o->z,
+                                   o->assign, o->nmatches, o->cap);
+  if (rc) return rc;
+  const int lc = o->line_cap;
+  rc = psl_line_extract_batch_dev(ctx, d_gray, B, w, h, gray_stride, gray_frame_stride, o->kl, o->ldesc, o->lineeq, nullptr,
+                                  lc, o->nl);
+  if (rc) return rc;
+  // SearchByGeomNApearance(frame b, frame b-1): the Last set is the same [B][line_cap] block shifted by one frame
+  cudaStream_t st = ctx->stream;
+  if ((rc = ensure(ctx, ctx->m_misc[9], (size_t)B * lc * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->m_misc[10], (size_t)B * 4))) return rc;
+  int32_t* n_last = ctx->m_misc[10].as<int32_t>();
+  PSL_CK(cudaMemsetAsync(n_last, 0, 4, st));
+  if (B > 1) PSL_CK(cudaMemcpyAsync(n_last + 1, o->nl, (size_t)(B - 1) * 4, cudaMemcpyDeviceToDevice, st));
+  LineSet Cur{o->kl, o->ldesc, o->nl, lc};
+  LineSet Last{o->kl - lc, o->ldesc - (ptrdiff_t)lc * 32, n_last, lc};
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(Last, Cur, ctx->m_misc[9].as<uint2>(), B, st);
+  launch_line_geom(Last, nullptr, Cur, ctx->m_misc[9].as<uint2>(), line_desc_th, (float)w, (float)h, o->line_assign,
+                   o->line_nmatches, B, st);
+  prof_span(ctx, 15, e, 2);
+  PSL_CK(cudaGetLastError());
+  return PSL_OK;
+}
+
+int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
+                             const float* Tcw, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* o) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!gray || !depth || !Tcw || !o || !o->kps || !o->desc || !o->n || !o->u_right || !o->z || !o->assign || !o->nmatches ||
+      !o->kl || !o->ldesc || !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || B < 0 || w <= 0 || h <= 0 ||
+      o->cap < 1 || o->line_cap < 1)
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const size_t px = (size_t)w * h, nk = (size_t)B * o->cap, nl = (size_t)B * o->line_cap;
+  DevBuf* M = ctx->m_misc;
+  int rc;
+  if ((rc = ensure(ctx, M[0], px * B))) return rc;
+  if ((rc = ensure(ctx, M[1], px * B * 2))) return rc;
+  if ((rc = ensure(ctx, M[2], (size_t)B * 12 * 4))) return rc;
+  if ((rc = ensure(ctx, M[3], nk * sizeof(psl_keypoint)))) return rc;
+  if ((rc = ensure(ctx, M[4], nk * 32))) return rc;
+  if ((rc = ensure(ctx, M[5], (size_t)B * 16))) return rc;  // n | nmatches | nl | line_nmatches
+  if ((rc = ensure(ctx, M[6], nk * 4))) return rc;
+  if ((rc = ensure(ctx, M[7], nk * 4))) return rc;
+  if ((rc = ensure(ctx, M[8], nk * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->l_kl, nl * sizeof(psl_keyline)))) return rc;
+  if ((rc = ensure(ctx, ctx->l_desc, nl * 32))) return rc;
+  if ((rc = ensure(ctx, ctx->l_eq, nl * 24))) return rc;
+  if ((rc = ensure(ctx, ctx->l_n, nl * 4))) return rc;  // line_assign
+  cudaStream_t st = ctx->stream;
+  PSL_CK(cudaMemcpyAsync(M[0].p, gray, px * B, cudaMemcpyHostToDevice, st));
+  PSL_CK(cudaMemcpyAsync(M[1].p, depth, px * B * 2, cudaMemcpyHostToDevice, st));
+  PSL_CK(cudaMemcpyAsync(M[2].p, Tcw, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+  int32_t* d_n = M[5].as<int32_t>();
+  psl_frontend_out d = *o;
+  d.kps = M[3].as<psl_keypoint>(); d.desc = M[4].as<uint8_t>(); d.n = d_n; d.nmatches = d_n + B;
+  d.u_right = M[6].as<float>(); d.z = M[7].as<float>(); d.assign = M[8].as<int32_t>();
+  d.kl = ctx->l_kl.as<psl_keyline>(); d.ldesc = ctx->l_desc.as<uint8_t>(); d.lineeq = ctx->l_eq.as<double>();
+  d.nl = d_n + 2 * B; d.line_nmatches = d_n + 3 * B; d.line_assign = ctx->l_n.as<int32_t>();
+  rc = psl_track_frontend_batch_dev(ctx, M[0].as<uint8_t>(), w, (int64_t)px, M[1].as<uint16_t>(), w, (int64_t)px, B, w, h,
+                                    M[2].as<float>(), cam, prm, line_desc_th, &d);
+  if (rc) return rc;
+  PSL_CK(cudaMemcpyAsync(o->kps, d.kps, nk * sizeof(psl_keypoint), cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->desc, d.desc, nk * 32, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->n, d.n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->nmatches, d.nmatches, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->u_right, d.u_right, nk * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->z, d.z, nk * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->assign, d.assign, nk * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->kl, d.kl, nl * sizeof(psl_keyline), cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->ldesc, d.ldesc, nl * 32, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->lineeq, d.lineeq, nl * 24, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->nl, d.nl, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->line_nmatches, d.line_nmatches, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(o->line_assign, d.line_assign, nl * 4, cudaMemcpyDeviceToHost, st));
   return check_status(ctx);
 }
 

@@ -42,7 +42,7 @@ class Context:
         return int(_lib.lib().psl_stream(self._h) or 0)
 
     STAGES = ["pyramid", "fast", "octree", "blur", "describe", "match_single", "stereo_queries", "grid",
-              "candidates", "resolve"]
+              "candidates", "resolve", "lsd_prologue", "lsd_order", "lsd_grow", "line_merge", "lbd", "line_match"]
 
     def profile(self, on: bool):
         self.check(_lib.lib().psl_profile_enable(self._h, int(on)))

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, Camera, TrackParams
+from ._lib import KEYLINE_DTYPE, KP_DTYPE, Camera, FrontendOut, TrackParams
 from .orb import ORBextractor, _ptr
 
 
@@ -53,3 +53,36 @@ def track_orb_batch_dev(ex: ORBextractor, d_gray: int, d_depth: int, B: int, W: 
     ex.ctx.check(_lib.lib().psl_track_orb_batch_dev(ex.ctx.handle, d_gray, W, W * H, d_depth, W, W * H, B, W, H,
                                                     d_Tcw, C.addressof(cam), C.addressof(prm), d_kps, d_desc, d_n,
                                                     d_u_right, d_z, d_assign, d_nmatches, cap))
+
+
+def track_frontend_batch(ex: ORBextractor, gray: np.ndarray, depth: np.ndarray, Tcw: np.ndarray, cam: Camera,
+                         prm: TrackParams | None = None, line_desc_th: float = 0.95):
+    """Combined front end (psl_track_frontend_batch): points as track_orb_batch plus LINEextractor per frame and
+    LSDmatcher::SearchByGeomNApearance against the previous frame (Tracking.cc:1182-1183).  HOST arrays in/out.
+    `ex.ctx` must be configured for the line path too (default config is)."""
+    prm = prm or make_track_params()
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    B, H, W = gray.shape
+    T = pose_rows(Tcw)
+    cap, lc = ex.cap, int(ex.ctx.cfg.line_nfeatures)
+    out = dict(kps=np.zeros((B, cap), KP_DTYPE), desc=np.zeros((B, cap, 32), np.uint8), n=np.zeros(B, np.int32),
+               u_right=np.zeros((B, cap), np.float32), z=np.zeros((B, cap), np.float32),
+               assign=np.full((B, cap), -1, np.int32), nmatches=np.zeros(B, np.int32),
+               kl=np.zeros((B, lc), KEYLINE_DTYPE), ldesc=np.zeros((B, lc, 32), np.uint8),
+               lineeq=np.zeros((B, lc, 3), np.float64), nl=np.zeros(B, np.int32),
+               line_assign=np.full((B, lc), -1, np.int32), line_nmatches=np.zeros(B, np.int32))
+    fo = FrontendOut(*[out[k].ctypes.data for k in ("kps", "desc", "n", "u_right", "z", "assign", "nmatches")], cap, lc,
+                     *[out[k].ctypes.data for k in ("kl", "ldesc", "lineeq", "nl", "line_assign", "line_nmatches")])
+    ex.ctx.check(_lib.lib().psl_track_frontend_batch(ex.ctx.handle, _ptr(gray), _ptr(depth), B, W, H, _ptr(T),
+                                                     C.addressof(cam), C.addressof(prm), C.c_float(line_desc_th),
+                                                     C.byref(fo)))
+    return out
+
+
+def track_frontend_batch_dev(ex: ORBextractor, d_gray: int, d_depth: int, B: int, W: int, H: int, d_Tcw: int,
+                             cam: Camera, prm: TrackParams, line_desc_th: float, fo: FrontendOut):
+    """DEVICE pointers (tightly packed frames; every FrontendOut pointer in HBM), asynchronous on the ctx stream."""
+    ex.ctx.check(_lib.lib().psl_track_frontend_batch_dev(ex.ctx.handle, d_gray, W, W * H, d_depth, W, W * H, B, W, H,
+                                                         d_Tcw, C.addressof(cam), C.addressof(prm),
+                                                         C.c_float(line_desc_th), C.byref(fo)))

@@ -60,3 +60,40 @@ def test_track_wide_window_and_no_orientation(orc):
     for b, (kps, desc, ur, z, assign, nm) in enumerate(ref):
         n = out["n"][b]
         assert np.array_equal(out["assign"][b, :n], assign) and out["nmatches"][b] == nm
+
+
+def test_combined_frontend_vs_oracle_chain(orc):
+    """cfg 4 shaped: ORB + lines + both frame-to-frame matchers for a batch spanning several chunks."""
+    from psl_slam_b200 import Context, ORBextractor, default_config, make_camera, make_track_params, synth, \
+        track_frontend_batch
+    K = synth.ICL
+    gray, depth, T = synth.sequence(9, 4)
+    T = T.astype(np.float32)
+    cfg = default_config()
+    cfg.chunk_frames, cfg.line_chunk_frames = 3, 2
+    ex = ORBextractor(ctx=Context(cfg))
+    cam = make_camera(K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], K["depth_factor"])
+    out = track_frontend_batch(ex, gray, depth, T, cam, make_track_params(15.0, 0.9, True), 0.95)
+    ref = oracle_chain(orc, gray, depth, T, K)
+    bounds = np.array([0, 0, gray.shape[2], gray.shape[1]], np.float32)
+    prev = None
+    for b, (kps, desc, ur, z, assign, nm) in enumerate(ref):
+        n = out["n"][b]
+        assert n == len(kps) and np.array_equal(out["desc"][b, :n], desc)
+        assert np.array_equal(out["assign"][b, :n], assign) and out["nmatches"][b] == nm
+        kl, ld, eq, _ = orc.line_extract(gray[b], 200)
+        nl = out["nl"][b]
+        assert nl == len(kl) and nl > 30
+        assert out["kl"][b, :nl].tobytes() == kl.tobytes() and np.array_equal(out["ldesc"][b, :nl], ld)
+        assert np.array_equal(out["lineeq"][b, :nl], eq)
+        if prev is None:
+            assert out["line_nmatches"][b] == 0 and np.all(out["line_assign"][b, :nl] == -1)
+        else:
+            la, ln = orc.line_search_geom(prev[0], prev[1], np.ones(len(prev[0]), np.uint8), kl, ld, bounds, 0.95)
+            assert np.array_equal(out["line_assign"][b, :nl], la) and out["line_nmatches"][b] == ln and ln > 10
+        prev = (kl, ld)
+    # the CPU-baseline harness computes the same counts
+    cam6 = np.array([K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], np.float32(1.0) / np.float32(K["depth_factor"])], np.float32)
+    n2, nm2, nl2, lnm2 = orc.frontend_batch_mt(gray, depth, T[:, :3, :4].reshape(len(T), 12), cam6, nthreads=2)
+    assert np.array_equal(n2, out["n"]) and np.array_equal(nm2, out["nmatches"])
+    assert np.array_equal(nl2, out["nl"]) and np.array_equal(lnm2, out["line_nmatches"])
