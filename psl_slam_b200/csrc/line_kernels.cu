@@ -9,23 +9,241 @@
 namespace psl {
 
 // ---------------------------------------------------------------------------------------------------
-// clamp + optimizeAndMergeLines_lsd + top-N + KeyLines + line equations: one frame per warp, lane 0
-// walks the reference's control flow (line_core.cuh explains why); the batch is the parallel axis.
+// clamp + optimizeAndMergeLines_lsd + top-N + KeyLines + line equations, one frame per warp.
+// line_core.cuh holds the scalar statement of this stage (what the CPU suite checks against the oracle);
+// here the warp runs the same decisions with the data-parallel parts spread over the lanes:
+//   * the angle-sorted pair scan of MergeLines (uselongline.cpp:61-151) tests 32 partners of one segment at a
+//     time; the early `break` is the first lane whose angle gap exceeds the threshold, neighbour lists are
+//     appended in lane (= scan) order;
+//   * connected components / sub-clusters (:153-229) stay on lane 0 (index bookkeeping only) and emit the
+//     list of sub-cluster heads: every output line is fold(MergeTwoLines, head, neighbours(head)), so the
+//     fp64-heavy folds (:231-262) run one sub-cluster per lane;
+//   * stable index sorts are rank computations (position = number of elements that sort before).
 // ---------------------------------------------------------------------------------------------------
+namespace linew {
+
+using line::kNbCap;
+using line::MergeScratch;
+using line::Seg;
+constexpr unsigned kFull = 0xffffffffu;
+
+// stable rank sort of idx[0..n) by key[idx] ascending (desc = false) or descending; result in out[]
+__device__ void rank_sort(const uint16_t* idx, uint16_t* out, int n, const float* key, bool desc, int lane) {
+  for (int a = lane; a < n; a += 32) {
+    const float ka = key[idx[a]];
+    int r = 0;
+    for (int b = 0; b < n; ++b) {
+      const float kb = key[idx[b]];
+      const bool before = desc ? (kb > ka) : (kb < ka);
+      r += (before || (!(desc ? (ka > kb) : (ka < kb)) && b < a)) ? 1 : 0;
+    }
+    out[r] = idx[a];
+  }
+  __syncwarp();
+}
+
+__device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, float distance_thr, float endpoint_threshold,
+                           MergeScratch& S, int lane) {
+  if (n <= 0) return 0;
+  for (int i = lane; i < n; i += 32) {
+    const float dx = __fsub_rn(src[i].v[2], src[i].v[0]), dy = __fsub_rn(src[i].v[3], src[i].v[1]);
+    S.angles[i] = (float)atan((double)__fdiv_rn(dy, dx));
+    S.length[i] = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    S.tmp16[i] = (uint16_t)i;
+    S.nb_cnt[i] = 0;
+    S.code[i] = -1;
+  }
+  __syncwarp();
+  rank_sort(S.tmp16, S.order, n, S.angles, false, lane);
+  const float ep_thr = __fmul_rn(endpoint_threshold, endpoint_threshold);
+  const float quater_PI = (float)(line::kPi / 4.0);
+  for (int i = 0; i < n; ++i) {
+    const int idx1 = S.order[i];
+    const Seg s1 = src[idx1];
+    float x11 = s1.v[0], y11 = s1.v[1], x12 = s1.v[2], y12 = s1.v[3];
+    const float angle1 = S.angles[idx1];
+    const bool sx = fabsf(angle1) < quater_PI;
+    if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
+    const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
+    const float mx1 = (float)(0.5 * (double)__fadd_rn(s1.v[0], s1.v[2])), my1 = (float)(0.5 * (double)__fadd_rn(s1.v[1], s1.v[3]));
+    int cnt1 = S.nb_cnt[idx1];
+    for (int j0 = i + 1; j0 < n; j0 += 32) {
+      const int j = j0 + lane;
+      bool far = false, to_merge = false;
+      int idx2 = 0;
+      if (j < n) {
+        idx2 = S.order[j];
+        const Seg s2 = src[idx2];
+        float x21 = s2.v[0], y21 = s2.v[1], x22 = s2.v[2], y22 = s2.v[3];
+        if ((sx && (x22 < x21)) || ((!sx) && y22 < y21)) { float t = x21; x21 = x22; x22 = t; t = y21; y21 = y22; y22 = t; }
+        far = line::angle_diff(angle1, S.angles[idx2]) > angle_thr;
+        if (!far) {
+          const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
+          if (!(line::point_line_distance(s2, mx1, my1) > distance_thr && line::point_line_distance(s1, mx2, my2) > distance_thr)) {
+            float cx12, cy12, cx21, cy21;
+            if ((sx && x12 > x22) || (!sx && y12 > y22)) { cx12 = x22; cy12 = y22; cx21 = x11; cy21 = y11; }
+            else { cx12 = x12; cy12 = y12; cx21 = x21; cy21 = y21; }
+            to_merge = ((sx && cx12 >= cx21) || (!sx && cy12 >= cy21));
+            if (!to_merge) {
+              const float ex = __fsub_rn(cx21, cx12), ey = __fsub_rn(cy21, cy12);
+              to_merge = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < ep_thr;
+            }
+          }
+        }
+      }
+      // the scalar loop stops at the first partner whose angle gap is too large (unless near-vertical)
+      const unsigned brk = can_break ? __ballot_sync(kFull, far) : 0u;
+      const unsigned live = brk ? ((1u << (__ffs(brk) - 1)) - 1u) : kFull;
+      const unsigned mm = __ballot_sync(kFull, to_merge) & live;
+      if (mm >> lane & 1u) {
+        const int pos = cnt1 + __popc(mm & ((1u << lane) - 1u));
+        const int c2 = S.nb_cnt[idx2];
+        if (pos < kNbCap && c2 < kNbCap) {
+          S.nb[idx1 * kNbCap + pos] = (uint16_t)idx2;
+          S.nb[idx2 * kNbCap + c2] = (uint16_t)idx1;
+          S.nb_cnt[idx2] = (uint16_t)(c2 + 1);
+        } else {
+          S.overflow = 1;
+        }
+      }
+      cnt1 = min(cnt1 + __popc(mm), kNbCap);
+      __syncwarp();
+      if (brk) break;
+    }
+    if (lane == 0) S.nb_cnt[idx1] = (uint16_t)cnt1;
+    __syncwarp();
+  }
+  S.overflow = __any_sync(kFull, S.overflow) ? 1 : 0;
+  // connected components (:153-190) and sub-clusters (:193-229): heads of the output lines, in output order
+  uint16_t* heads = S.order;  // the angle order is no longer needed
+  int nd = 0;
+  if (lane == 0) {
+    for (int i = 0; i < n; ++i) {
+      if (S.code[i] >= 0) continue;
+      S.code[i] = 1;
+      uint16_t* cl = S.tmp16;
+      int cs = 0, ncheck = 0;
+      cl[cs++] = (uint16_t)i;
+      for (int k = 0; k < S.nb_cnt[i]; ++k) S.check[ncheck++] = S.nb[i * kNbCap + k];
+      while (ncheck > 0) {
+        int lo = n, hi = -1;
+        for (int c = 0; c < ncheck; ++c) {
+          const int j = S.check[c];
+          if (S.code[j] < 0) { S.code[j] = 1; cl[cs++] = (uint16_t)j; }
+          for (int k = 0; k < S.nb_cnt[j]; ++k) {
+            const int q = S.nb[j * kNbCap + k];
+            if (S.code[q] < 0) { S.flag[q] = 1; lo = q < lo ? q : lo; hi = q > hi ? q : hi; }
+          }
+        }
+        ncheck = 0;
+        for (int q = lo; q <= hi; ++q)
+          if (S.flag[q]) {
+            S.flag[q] = 0;
+            if (S.code[q] < 0) S.check[ncheck++] = (uint16_t)q;
+          }
+      }
+      if (cs <= 2) {  // fold(cluster) == fold(head, neighbours(head)): the only possible neighbour is the other member
+        heads[nd++] = cl[0];
+        continue;
+      }
+      line::stable_sort_idx(cl, S.check, cs, S.length, true);
+      for (int k = 0; k < cs; ++k) { S.loc[cl[k]] = (uint16_t)k; S.flag[k] = 0; }
+      for (int j = 0; j < cs; ++j) {
+        if (S.flag[j]) continue;
+        const int li = cl[j];
+        for (int k = 0; k < S.nb_cnt[li]; ++k) S.flag[S.loc[S.nb[li * kNbCap + k]]] = 1;
+        heads[nd++] = (uint16_t)li;
+      }
+      for (int k = 0; k < cs; ++k) S.flag[k] = 0;
+    }
+  }
+  nd = __shfl_sync(kFull, nd, 0);
+  __syncwarp();
+  for (int o = lane; o < nd; o += 32) {  // folded MergeTwoLines (:243-255), one sub-cluster per lane
+    const int li = heads[o];
+    Seg nl = line::merge_two(src[li], src[li]);
+    for (int k = 0; k < S.nb_cnt[li]; ++k) nl = line::merge_two(nl, src[S.nb[li * kNbCap + k]]);
+    dst[o] = nl;
+  }
+  __syncwarp();
+  return nd;
+}
+
+// FilterShortLines (:338-351): order-preserving compaction in place
+__device__ int filter_short(Seg* lines, int n, float length_thr, int lane) {
+  const float thr2 = __fmul_rn(length_thr, length_thr);
+  int m = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    Seg s{};
+    bool keep = false;
+    if (i < n) {
+      s = lines[i];
+      const float dx = __fsub_rn(s.v[2], s.v[0]), dy = __fsub_rn(s.v[3], s.v[1]);
+      keep = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) > thr2;
+    }
+    const unsigned bal = __ballot_sync(kFull, keep);
+    __syncwarp();
+    if (keep) lines[m + __popc(bal & ((1u << lane) - 1u))] = s;  // m + rank <= i: never overtakes unread input
+    m += __popc(bal);
+    __syncwarp();
+  }
+  return m;
+}
+
+__device__ int frame_lines(Seg* raw, int n_raw, Seg* t1, Seg* t2, int w, int h, int nfeatures, MergeScratch& S,
+                           psl_keyline* kl, double* lineeq, int kl_cap, int lane) {
+  for (int i = lane; i < n_raw; i += 32) line::clamp_segment(raw[i], w, h);
+  __syncwarp();
+  int n1 = merge_lines(raw, n_raw, t1, 0.05f, 5.f, 15.f, S, lane);   // uselongline.cpp:458
+  n1 = filter_short(t1, n1, 30.f, lane);
+  int n2 = merge_lines(t1, n1, t2, 0.03f, 3.f, 30.f, S, lane);       // :464
+  n2 = filter_short(t2, n2, 50.f, lane);
+  int n = n2;
+  if (n2 > nfeatures) {  // LineExtractor.cpp:342-348 (stable by response, descending)
+    for (int i = lane; i < n2; i += 32) {
+      const double ddx = (double)__fsub_rn(t2[i].v[0], t2[i].v[2]), ddy = (double)__fsub_rn(t2[i].v[1], t2[i].v[3]);
+      S.length[i] = __fdiv_rn((float)sqrt(ddx * ddx + ddy * ddy), (float)(w > h ? w : h));  // response
+      S.tmp16[i] = (uint16_t)i;
+    }
+    __syncwarp();
+    rank_sort(S.tmp16, S.order, n2, S.length, true, lane);
+    n = nfeatures;
+  } else {
+    for (int i = lane; i < n2; i += 32) S.order[i] = (uint16_t)i;
+    __syncwarp();
+  }
+  if (n > kl_cap) return -1;
+  for (int i = lane; i < n; i += 32) {
+    psl_keyline k;
+    line::make_keyline(t2[S.order[i]], n2 > nfeatures ? i : (int)S.order[i], w, h, k);
+    kl[i] = k;
+    // sp x ep normalised by its first two components (LineExtractor.cpp:352-363), fp64
+    const double sx = k.start_x, sy = k.start_y, ex = k.end_x, ey = k.end_y;
+    const double l0 = sy * 1.0 - 1.0 * ey, l1 = 1.0 * ex - sx * 1.0, l2 = sx * ey - sy * ex;
+    const double nrm = sqrt(l0 * l0 + l1 * l1);
+    lineeq[3 * i] = l0 / nrm; lineeq[3 * i + 1] = l1 / nrm; lineeq[3 * i + 2] = l2 / nrm;
+  }
+  return n;
+}
+
+}  // namespace linew
+
 __global__ void __launch_bounds__(32)
     line_post_kernel(LineBuffers L, int nfeatures, psl_keyline* __restrict__ kl, double* __restrict__ lineeq, int cap,
                      int32_t* __restrict__ n_out, uint32_t* __restrict__ status) {
-  if (threadIdx.x != 0) return;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, lane = threadIdx.x;
   const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
   line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
                        L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0};
   line::Seg* raw = reinterpret_cast<line::Seg*>(L.raw) + o;
-  const int n = line::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,
-                                  lineeq + (size_t)b * cap * 3, cap);
-  if (S.overflow) atomicOr(status, kStatLineNeighbours);
-  if (n < 0) atomicOr(status, kStatOutOverflow);
-  n_out[b] = n < 0 ? 0 : n;
+  const int n = linew::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,
+                                   lineeq + (size_t)b * cap * 3, cap, lane);
+  if (lane == 0) {
+    if (S.overflow) atomicOr(status, kStatLineNeighbours);
+    if (n < 0) atomicOr(status, kStatOutOverflow);
+    n_out[b] = n < 0 ? 0 : n;
+  }
 }
 
 void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int cap,

@@ -30,11 +30,15 @@ __global__ void __launch_bounds__(256)
 }
 
 // ll_angle: gradient on the 2x2 stencil, angle in degrees (fastAtan2), squared norm, per-frame maximum
-// and the number of seed-capable pixels per row.  One warp per row.
+// and the number of seed-capable pixels per row.  One warp per row.  Each pixel gets one 16-byte record
+// (angle in degrees | cos | sin | squared gradient norm) so that region growing needs a single LDG.128 per
+// neighbour: cos / sin are the fp32 values region_grow adds to its running sums, (float)cos((double)(float)angle)
+// (the reference calls cos(float) -> pinned to fp64 evaluation), computed here in parallel instead
+// of inside the sequential loop.
 __global__ void __launch_bounds__(128)
-    lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, float* __restrict__ deg,
-                        int32_t* __restrict__ n2, uint8_t* __restrict__ used, int32_t* __restrict__ max_n2,
-                        int32_t* __restrict__ row_cnt, double rho) {
+    lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, float4* __restrict__ pix,
+                        uint8_t* __restrict__ used, int32_t* __restrict__ max_n2, int32_t* __restrict__ row_cnt,
+                        double rho) {
   const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
   if (y >= Hs) return;
   const uint8_t* r0 = scaled + ((size_t)b * Hs + y) * Ws;
@@ -42,20 +46,22 @@ __global__ void __launch_bounds__(128)
   const size_t base = ((size_t)b * Hs + y) * Ws;
   int cnt = 0, mx = -1;
   for (int x = lane; x < Ws; x += 32) {
-    float d = lsd::kNotDefDeg;
-    int q = 0;
+    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(0));
     if (y < Hs - 1 && x < Ws - 1) {
       const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
       const int gx = DA + BC, gy = DA - BC;
-      q = gx * gx + gy * gy;
+      const int q = gx * gx + gy * gy;
+      rec.w = __int_as_float(q);
       if (!(sqrt((double)q / 4.0) <= rho)) {
-        d = lsd::fast_atan2((float)gx, (float)-gy);
+        rec.x = lsd::fast_atan2((float)gx, (float)-gy);
+        const double a = (double)(float)((double)rec.x * lsd::kDegToRad);
+        rec.y = (float)cos(a);
+        rec.z = (float)sin(a);
         ++cnt;
         mx = max(mx, q);
       }
     }
-    deg[base + x] = d;
-    n2[base + x] = q;
+    pix[base + x] = rec;
     used[base + x] = 0;
   }
 #pragma unroll
@@ -96,9 +102,8 @@ __global__ void __launch_bounds__(32)
 
 // (bin, pixel) pairs of the seed-capable pixels in raster order (ordered compaction, one warp per row)
 __global__ void __launch_bounds__(128)
-    lsd_keys_kernel(const float* __restrict__ deg, const int32_t* __restrict__ n2, int Ws, int Hs,
-                    const int32_t* __restrict__ max_n2, const int32_t* __restrict__ row_off,
-                    uint16_t* __restrict__ key, uint32_t* __restrict__ val) {
+    lsd_keys_kernel(const float4* __restrict__ pix, int Ws, int Hs, const int32_t* __restrict__ max_n2,
+                    const int32_t* __restrict__ row_off, uint16_t* __restrict__ key, uint32_t* __restrict__ val) {
   const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
   if (y >= Hs - 1) return;
   const size_t npx = (size_t)Ws * Hs, base = (size_t)b * npx + (size_t)y * Ws;
@@ -108,38 +113,316 @@ __global__ void __launch_bounds__(128)
   int pos = row_off[(size_t)b * Hs + y];
   for (int x0 = 0; x0 < Ws - 1; x0 += 32) {
     const int x = x0 + lane;
-    const bool def = x < Ws - 1 && deg[base + x] != lsd::kNotDefDeg;
+    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, 0.f);
+    if (x < Ws - 1) rec = pix[base + x];
+    const bool def = rec.x != lsd::kNotDefDeg;
     const unsigned bal = __ballot_sync(0xffffffffu, def);
     if (def) {
       const int p = pos + __popc(bal & ((1u << lane) - 1u));
-      key[(size_t)b * npx + p] = (uint16_t)(int)(sqrt((double)n2[base + x] / 4.0) * bin_coef);
+      key[(size_t)b * npx + p] = (uint16_t)(int)(sqrt((double)__float_as_int(rec.w) / 4.0) * bin_coef);
       val[(size_t)b * npx + p] = (uint32_t)(y * Ws + x);
     }
     pos += __popc(bal);
   }
 }
 
-// the sequential core: one frame per warp, lane 0 walks the seed list
+// ---------------------------------------------------------------------------------------------------
+// The sequential core, one frame per warp.  Region growing is order dependent (every accepted pixel moves
+// the region angle the next neighbour is tested against), so the warp does not split the region; it
+// evaluates the next <= 27 neighbour tests of the reference's loop at once (the 3x3 neighbourhoods of up to
+// three consecutive region points, lane order = loop order), accepts the first aligned one, updates the
+// angle, and re-evaluates only the lanes after it — exactly the sequence of decisions of the scalar loop
+// (lsd_core.cuh, which the CPU suite checks against the oracle) with the loads and the per-pixel arithmetic
+// done 27-wide.  The fp64 running sums of region2rect / refine are added in the reference's order
+// (one lane-ordered shuffle chain), the extents are exact min/max reductions.
+// ---------------------------------------------------------------------------------------------------
+namespace lsdw {
+
+using lsd::kDegToRad;
+using lsd::kM2Pi;
+using lsd::kM32Pi;
+using lsd::kNotDefDeg;
+using lsd::kPi;
+
+struct Frame {
+  int W, H;
+  const float4* pix;
+  uint8_t* used;
+  uint32_t* reg;
+};
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+__device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec) {
+  double n_theta = theta - (double)deg * kDegToRad;
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > kM32Pi) {
+    n_theta -= kM2Pi;
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+// region_grow; returns the region size, reg_angle out
+__device__ int region_grow(const Frame& f, int seed, double& reg_angle, double prec, int lane) {
+  const int W = f.W, H = f.H;
+  reg_angle = (double)f.pix[seed].x * kDegToRad;
+  float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+  const int sy = seed / W, sx = seed - sy * W;
+  if (lane == 0) {
+    f.reg[0] = ((uint32_t)sy << 16) | (uint32_t)sx;
+    f.used[seed] = 1;
+  }
+  __syncwarp();
+  int n = 1;
+  const int p = lane / 9, k = lane - 9 * p;
+  const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
+  for (int i = 0; i < n;) {
+    const int m = min(3, n - i);
+    bool cand = false;
+    int nidx = -1;
+    float4 rec = make_float4(kNotDefDeg, 0.f, 0.f, 0.f);
+    uint32_t npk = 0;
+    if (p < m) {
+      const uint32_t c = f.reg[i + p];
+      const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
+      if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
+        nidx = yy * W + xx;
+        npk = ((uint32_t)yy << 16) | (uint32_t)xx;
+        if (f.used[nidx] != 1) {
+          rec = f.pix[nidx];
+          cand = rec.x != kNotDefDeg;
+        }
+      }
+    }
+    unsigned mask = __ballot_sync(kFull, cand);
+    while (mask) {
+      const bool ok = cand && aligned_deg(rec.x, reg_angle, prec);
+      const unsigned am = __ballot_sync(kFull, ok) & mask;
+      if (!am) break;
+      const int j = __ffs(am) - 1;
+      const int aidx = __shfl_sync(kFull, nidx, j);
+      const uint32_t apk = __shfl_sync(kFull, npk, j);
+      sumdx += __shfl_sync(kFull, rec.y, j);
+      sumdy += __shfl_sync(kFull, rec.z, j);
+      if (lane == 0) {
+        f.used[aidx] = 1;
+        f.reg[n] = apk;
+      }
+      ++n;
+      reg_angle = (double)lsd::fast_atan2(sumdy, sumdx) * kDegToRad;
+      if (nidx == aidx) cand = false;           // the same pixel seen from another centre is now USED
+      mask &= ~((2u << j) - 1u);                // tests before j were made (and failed) with the older angle
+      mask &= __ballot_sync(kFull, cand);
+    }
+    i += m;
+    __syncwarp();
+  }
+  return n;
+}
+
+struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy; };
+
+__device__ __forceinline__ double modgrad(const Frame& f, int idx) {
+  return sqrt((double)__float_as_int(f.pix[idx].w) / 4.0);
+}
+
+__device__ void region2rect(const Frame& f, int n, double reg_angle, double prec, Rect& rec, int lane) {
+  // weighted centroid: x += px * w ... in list order
+  double x = 0, y = 0, sum = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    double tx = 0, ty = 0, w = 0;
+    if (i < n) {
+      const uint32_t c = f.reg[i];
+      const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
+      w = modgrad(f, py * f.W + px);
+      tx = (double)px * w;
+      ty = (double)py * w;
+    }
+    const int cnt = min(32, n - base);
+    for (int k = 0; k < cnt; ++k) {
+      x += shfl_d(tx, k);
+      y += shfl_d(ty, k);
+      sum += shfl_d(w, k);
+    }
+  }
+  x /= sum;
+  y /= sum;
+  // get_theta: inertia matrix in list order
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    double t1 = 0, t2 = 0, t3 = 0;
+    if (i < n) {
+      const uint32_t c = f.reg[i];
+      const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
+      const double w = modgrad(f, py * f.W + px), dx = (double)px - x, dy = (double)py - y;
+      t1 = dy * dy * w;
+      t2 = dx * dx * w;
+      t3 = dx * dy * w;
+    }
+    const int cnt = min(32, n - base);
+    for (int k = 0; k < cnt; ++k) {
+      Ixx += shfl_d(t1, k);
+      Iyy += shfl_d(t2, k);
+      Ixy -= shfl_d(t3, k);
+    }
+  }
+  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lsd::fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)lsd::fast_atan2((float)Ixy, (float)(lambda - Iyy));
+  theta *= kDegToRad;
+  double d = lsd::angle_diff_signed(theta, reg_angle);
+  if (d < 0) d = -d;
+  if (d > prec) theta += kPi;
+  const double dx = cos(theta), dy = sin(theta);
+  // extents: `if (l > l_max) l_max = l; else if (l < l_min) l_min = l;` with both starting at 0 is an
+  // independent max and min (a value above the running max is positive, so it cannot lower the min)
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t c = f.reg[i];
+    const double rdx = (double)(int)(c & 0xFFFFu) - x, rdy = (double)(int)(c >> 16) - y;
+    const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
+    l_max = l > l_max ? l : l_max;
+    l_min = l < l_min ? l : l_min;
+    w_max = w > w_max ? w : w_max;
+    w_min = w < w_min ? w : w_min;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    double v = __shfl_xor_sync(kFull, l_max, o); l_max = v > l_max ? v : l_max;
+    v = __shfl_xor_sync(kFull, l_min, o); l_min = v < l_min ? v : l_min;
+    v = __shfl_xor_sync(kFull, w_max, o); w_max = v > w_max ? v : w_max;
+    v = __shfl_xor_sync(kFull, w_min, o); w_min = v < w_min ? v : w_min;
+  }
+  rec.x1 = x + l_min * dx; rec.y1 = y + l_min * dy;
+  rec.x2 = x + l_max * dx; rec.y2 = y + l_max * dy;
+  rec.width = w_max - w_min;
+  rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+
+__device__ __forceinline__ double density_of(int n, const Rect& rec) {
+  return (double)n / (sqrt(lsd::dist_sq(rec.x1, rec.y1, rec.x2, rec.y2)) * rec.width);
+}
+
+// reduce_region_radius: the swap-with-last removal defines the order of the surviving points (and with it
+// the rounding of the next region2rect), so lane 0 replays it; the rectangle fits stay cooperative.
+__device__ bool reduce_region_radius(const Frame& f, int& n, double reg_angle, double prec, Rect& rec, double density,
+                                     int lane) {
+  const uint32_t c0 = f.reg[0];
+  const double xc = (double)(int)(c0 & 0xFFFFu), yc = (double)(int)(c0 >> 16);
+  const double r1 = lsd::dist_sq(xc, yc, rec.x1, rec.y1), r2 = lsd::dist_sq(xc, yc, rec.x2, rec.y2);
+  double radSq = r1 > r2 ? r1 : r2;
+  while (density < lsd::kDensityTh) {
+    radSq *= 0.75 * 0.75;
+    if (lane == 0) {
+      int m = n;
+      for (int i = 0; i < m; ++i) {
+        const uint32_t c = f.reg[i];
+        const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
+        if (lsd::dist_sq(xc, yc, (double)px, (double)py) > radSq) {
+          f.used[py * f.W + px] = 0;
+          f.reg[i] = f.reg[m - 1];
+          f.reg[m - 1] = c;
+          --m;
+          --i;
+        }
+      }
+      n = m;
+    }
+    n = __shfl_sync(kFull, n, 0);
+    __syncwarp();
+    if (n < 2) return false;
+    region2rect(f, n, reg_angle, prec, rec, lane);
+    density = density_of(n, rec);
+  }
+  return true;
+}
+
+__device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Rect& rec, int lane) {
+  double density = density_of(n, rec);
+  if (density >= lsd::kDensityTh) return true;
+  const uint32_t c0 = f.reg[0];
+  const int sx = (int)(c0 & 0xFFFFu), sy = (int)(c0 >> 16);
+  const double xc = (double)sx, yc = (double)sy, ang_c = (double)f.pix[sy * f.W + sx].x * kDegToRad;
+  double sum = 0, s_sum = 0;
+  int cnt = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    double a = 0, a2 = 0;   // points outside the radius add +0.0, which leaves the sums unchanged
+    bool in = false;
+    if (i < n) {
+      const uint32_t c = f.reg[i];
+      const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
+      f.used[py * f.W + px] = 0;
+      if (sqrt(lsd::dist_sq(xc, yc, (double)px, (double)py)) < rec.width) {
+        a = lsd::angle_diff_signed((double)f.pix[py * f.W + px].x * kDegToRad, ang_c);
+        a2 = a * a;
+        in = true;
+      }
+    }
+    cnt += __popc(__ballot_sync(kFull, in));
+    const int c32 = min(32, n - base);
+    for (int k = 0; k < c32; ++k) {
+      sum += shfl_d(a, k);
+      s_sum += shfl_d(a2, k);
+    }
+  }
+  __syncwarp();
+  const double mean_angle = sum / (double)cnt;
+  const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+  n = region_grow(f, sy * f.W + sx, reg_angle, tau, lane);
+  if (n < 2) return false;
+  region2rect(f, n, reg_angle, prec, rec, lane);
+  density = density_of(n, rec);
+  if (density < lsd::kDensityTh) return reduce_region_radius(f, n, reg_angle, prec, rec, density, lane);
+  return true;
+}
+
+}  // namespace lsdw
+
 __global__ void __launch_bounds__(32)
     lsd_core_kernel(LineBuffers L, uint32_t* __restrict__ status) {
-  if (threadIdx.x != 0) return;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, lane = threadIdx.x;
   const size_t npx = (size_t)L.Ws * L.Hs;
-  lsd::Frame f;
-  f.W = L.Ws;
-  f.H = L.Hs;
-  f.deg = L.deg + b * npx;
-  f.n2 = L.n2 + b * npx;
-  f.used = L.used + b * npx;
-  f.reg = L.reg + b * npx;
-  f.seeds = L.val_out + b * npx;
-  f.n_seeds = L.n_def[b];
-  f.min_reg_size = L.min_reg_size;
-  f.out = L.raw + (size_t)b * L.raw_cap * 4;
-  f.cap = L.raw_cap;
-  const int n = lsd::detect(f);
-  L.n_raw[b] = n < L.raw_cap ? n : L.raw_cap;
-  if (n > L.raw_cap) atomicOr(status, kStatLineRaw);
+  lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.used + b * npx, L.reg + b * npx};
+  const uint32_t* seeds = L.val_out + b * npx;
+  const int n_seeds = L.n_def[b];
+  float* out = L.raw + (size_t)b * L.raw_cap * 4;
+  const double prec = lsd::kPi * lsd::kAngTh / 180;
+  int nseg = 0;
+  for (int s0 = 0; s0 < n_seeds; s0 += 32) {
+    const int my = s0 + lane < n_seeds ? (int)seeds[s0 + lane] : -1;
+    // a pixel that is USED now stays USED (only the pixels of the region being refined are ever released)
+    unsigned todo = __ballot_sync(lsdw::kFull, my >= 0 && f.used[my] == 0);
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int seed = __shfl_sync(lsdw::kFull, my, l);
+      if (f.used[seed] != 0) continue;
+      double reg_angle;
+      int n = lsdw::region_grow(f, seed, reg_angle, prec, lane);
+      if (n < L.min_reg_size) continue;
+      lsdw::Rect rec;
+      lsdw::region2rect(f, n, reg_angle, prec, rec, lane);
+      if (!lsdw::refine(f, n, reg_angle, prec, rec, lane)) continue;
+      rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+      rec.x1 /= lsd::kScale; rec.y1 /= lsd::kScale; rec.x2 /= lsd::kScale; rec.y2 /= lsd::kScale;
+      if (lane == 0 && nseg < L.raw_cap) {
+        out[4 * nseg] = (float)rec.x1; out[4 * nseg + 1] = (float)rec.y1;
+        out[4 * nseg + 2] = (float)rec.x2; out[4 * nseg + 3] = (float)rec.y2;
+      }
+      ++nseg;
+    }
+  }
+  if (lane == 0) {
+    L.n_raw[b] = nseg < L.raw_cap ? nseg : L.raw_cap;
+    if (nseg > L.raw_cap) atomicOr(status, kStatLineRaw);
+  }
 }
 
 size_t lsd_sort_temp_bytes(int items_per_frame, int frames) {
@@ -163,9 +446,9 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
   cudaMemsetAsync(L.max_n2, 0xFF, (size_t)nb * sizeof(int32_t), st);  // -1
   const double rho = 2.0 / sin(lsd::kPi * lsd::kAngTh / 180);
   dim3 rows((L.Hs + 3) / 4, nb);
-  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.deg, L.n2, L.used, L.max_n2, L.row_cnt, rho);
+  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.pix, L.used, L.max_n2, L.row_cnt, rho);
   lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, npx, L.n_def, L.seg_begin, L.seg_end);
-  lsd_keys_kernel<<<rows, 128, 0, st>>>(L.deg, L.n2, L.Ws, L.Hs, L.max_n2, L.row_cnt, L.key_in, L.val_in);
+  lsd_keys_kernel<<<rows, 128, 0, st>>>(L.pix, L.Ws, L.Hs, L.max_n2, L.row_cnt, L.key_in, L.val_in);
 }
 
 // stable: bins descending, raster order inside a bin (identical to cv2 4.13 on every golden)
