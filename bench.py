@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=2048, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=4096, help="frames per step per GPU")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--line-chunk", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -234,7 +234,7 @@ def main():
 
     F = args.frames
     cfg = default_config()
-    cfg.device, cfg.max_width, cfg.max_height = local, W, H
+    cfg.device, cfg.max_width, cfg.max_height, cfg.max_batch = local, W, H, F
     cfg.orb_nfeatures, cfg.orb_scale_factor, cfg.orb_nlevels = ORB["nfeatures"], ORB["scale"], ORB["nlevels"]
     cfg.orb_ini_th_fast, cfg.orb_min_th_fast = ORB["ini"], ORB["mn"]
     cfg.chunk_frames, cfg.line_chunk_frames, cfg.line_nfeatures = args.chunk, args.line_chunk, LINE["nfeatures"]

@@ -82,8 +82,9 @@ typedef struct psl_config {
   int32_t line_nlevels;    /* LINEextractor.nLevels    (1)    */
   float line_min_length;   /* LINEextractor.min_line_length (0; read by Tracking.cc:126 but never used by
                               LINEextractor::operator(), add_src/LineExtractor.cpp:325-366 -> ignored here too) */
-  int32_t line_chunk_frames; /* frames per launch of the line stages; 0 = auto (1024).  The sequential LSD core
-                                runs one frame per warp, so the batch is its only parallel axis */
+  int32_t line_chunk_frames; /* frames per launch of the line stages; 0 = auto (max_batch clamped to [64, 4096]).
+                                The LSD core runs one frame per warp, so the batch is its parallel axis;
+                                the line buffers take about 7.5 MB of HBM per frame of the chunk at 640x480 */
   int32_t line_max_raw;    /* raw LSD segments kept per frame before the merge; 0 = auto (4096) */
 } psl_config;
 

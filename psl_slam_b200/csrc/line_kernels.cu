@@ -229,10 +229,13 @@ __device__ int frame_lines(Seg* raw, int n_raw, Seg* t1, Seg* t2, int w, int h, 
 
 }  // namespace linew
 
-__global__ void __launch_bounds__(32)
-    line_post_kernel(LineBuffers L, int nfeatures, psl_keyline* __restrict__ kl, double* __restrict__ lineeq, int cap,
-                     int32_t* __restrict__ n_out, uint32_t* __restrict__ status) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+constexpr int kPostWarps = 4;  // frames per CTA (one per warp)
+
+__global__ void __launch_bounds__(kPostWarps * 32)
+    line_post_kernel(LineBuffers L, int nb, int nfeatures, psl_keyline* __restrict__ kl, double* __restrict__ lineeq,
+                     int cap, int32_t* __restrict__ n_out, uint32_t* __restrict__ status) {
+  const int b = blockIdx.x * kPostWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= nb) return;
   const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
   line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
                        L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0};
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(32)
 
 void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int cap,
                       int32_t* n_out, uint32_t* status, cudaStream_t st) {
-  line_post_kernel<<<nb, 32, 0, st>>>(L, nfeatures, kl, lineeq, cap, n_out, status);
+  line_post_kernel<<<(nb + kPostWarps - 1) / kPostWarps, kPostWarps * 32, 0, st>>>(L, nb, nfeatures, kl, lineeq, cap, n_out, status);
 }
 
 // ---------------------------------------------------------------------------------------------------

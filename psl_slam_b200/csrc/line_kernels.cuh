@@ -15,8 +15,7 @@ struct LineBuffers {
   const short2* ytab;  // [Hs]
   uint8_t* blur;       // [C][h][pitch]   7x7 sigma 0.75 (LSD) and, later, 5x5 sigma 1 (LBD)
   uint8_t* scaled;     // [C][Hs][Ws]
-  float4* pix;         // [C][Hs*Ws]  (angle in degrees | cos | sin | squared gradient norm as int bits)
-  uint8_t* used;       // [C][Hs*Ws]
+  float4* pix;         // [C][Hs*Ws]  (angle in degrees | cos | sin | int bits: squared gradient norm + USED flag)
   uint32_t* reg;       // [C][Hs*Ws]
   int32_t* max_n2;     // [C]
   int32_t* row_cnt;    // [C][Hs]  defined pixels per row -> exclusive offsets

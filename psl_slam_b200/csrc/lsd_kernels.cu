@@ -29,16 +29,18 @@ __global__ void __launch_bounds__(256)
   dst[((size_t)b * Hs + y) * Ws + x] = (uint8_t)((v + 32768u) >> 16);
 }
 
+constexpr int lsdw_kN2Mask = 0x000FFFFF;  // gx^2 + gy^2 <= 2 * 510^2 < 2^20
+constexpr int lsdw_kUsed = 0x40000000;    // region membership flag, kept in the same word
+
 // ll_angle: gradient on the 2x2 stencil, angle in degrees (fastAtan2), squared norm, per-frame maximum
 // and the number of seed-capable pixels per row.  One warp per row.  Each pixel gets one 16-byte record
-// (angle in degrees | cos | sin | squared gradient norm) so that region growing needs a single LDG.128 per
+// (angle in degrees | cos | sin | squared gradient norm + USED flag) so that region growing needs a single LDG.128 per
 // neighbour: cos / sin are the fp32 values region_grow adds to its running sums, (float)cos((double)(float)angle)
 // (the reference calls cos(float) -> pinned to fp64 evaluation), computed here in parallel instead
 // of inside the sequential loop.
 __global__ void __launch_bounds__(128)
     lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, float4* __restrict__ pix,
-                        uint8_t* __restrict__ used, int32_t* __restrict__ max_n2, int32_t* __restrict__ row_cnt,
-                        double rho) {
+                        int32_t* __restrict__ max_n2, int32_t* __restrict__ row_cnt, double rho) {
   const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
   if (y >= Hs) return;
   const uint8_t* r0 = scaled + ((size_t)b * Hs + y) * Ws;
@@ -62,7 +64,6 @@ __global__ void __launch_bounds__(128)
       }
     }
     pix[base + x] = rec;
-    used[base + x] = 0;
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(128)
     const unsigned bal = __ballot_sync(0xffffffffu, def);
     if (def) {
       const int p = pos + __popc(bal & ((1u << lane) - 1u));
-      key[(size_t)b * npx + p] = (uint16_t)(int)(sqrt((double)__float_as_int(rec.w) / 4.0) * bin_coef);
+      key[(size_t)b * npx + p] = (uint16_t)(int)(sqrt((double)(__float_as_int(rec.w) & lsdw_kN2Mask) / 4.0) * bin_coef);
       val[(size_t)b * npx + p] = (uint32_t)(y * Ws + x);
     }
     pos += __popc(bal);
@@ -144,16 +145,23 @@ using lsd::kM32Pi;
 using lsd::kNotDefDeg;
 using lsd::kPi;
 
+constexpr int kRing = 1024;  // region points kept in shared memory (the BFS frontier and small regions)
+
 struct Frame {
   int W, H;
-  const float4* pix;
-  uint8_t* used;
-  uint32_t* reg;
+  float4* pix;
+  uint32_t* reg;    // region points in HBM, packed y << 16 | x
+  uint32_t* ring;   // the last kRing of them in shared memory
 };
 
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+__device__ __forceinline__ int* flags_of(const Frame& f, int idx) { return reinterpret_cast<int*>(f.pix + idx) + 3; }
+// region point i of a region of (current) size n
+__device__ __forceinline__ uint32_t reg_at(const Frame& f, int i, int n) {
+  return (n - i <= kRing) ? f.ring[i & (kRing - 1)] : f.reg[i];
+}
 
 __device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec) {
   double n_theta = theta - (double)deg * kDegToRad;
@@ -165,68 +173,126 @@ __device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec
   return n_theta <= prec;
 }
 
-// region_grow; returns the region size, reg_angle out
+// the <= 27 neighbour tests of up to three consecutive region points, one per lane in loop order
+struct Nbr {
+  int nidx;       // pixel index, -1 = outside the image / idle lane
+  uint32_t npk;   // packed y << 16 | x
+  float4 rec;     // pixel record
+  bool cand;      // unused and with a defined angle when it was loaded
+};
+
+__device__ __forceinline__ Nbr load_nbr(const Frame& f, int first, int m, int n, int p, int ox, int oy) {
+  Nbr b{-1, 0u, make_float4(kNotDefDeg, 0.f, 0.f, 0.f), false};
+  if (p < m) {
+    const uint32_t c = reg_at(f, first + p, n);
+    const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
+    if (xx >= 0 && xx < f.W && yy >= 0 && yy < f.H) {
+      b.nidx = yy * f.W + xx;
+      b.npk = ((uint32_t)yy << 16) | (uint32_t)xx;
+      b.rec = f.pix[b.nidx];
+      b.cand = !(__float_as_int(b.rec.w) & lsdw_kUsed) && b.rec.x != kNotDefDeg;
+    }
+  }
+  return b;
+}
+
+// region_grow; returns the region size, reg_angle out.
+//
+// The serial chain of the reference is  accept -> sums -> reg_angle = fastAtan2(sums) -> test next neighbour.
+// Two things shorten it without changing a single decision:
+//  * the alignment test |angle_i - reg_angle| <= prec is first made on the sums themselves
+//    (cos_i * sumdx + sin_i * sumdy against cos(prec -/+ 0.5 deg) * |sum|): fastAtan2 is within 0.01 deg of the
+//    true angle and the fp32 dot product within 1e-6, so outside the +/- 0.5 deg band the outcome is certain;
+//    only a neighbour inside the band takes the exact path (fastAtan2 of the sums + the fp64 comparison);
+//  * the records of the next region points are loaded while the current ones are being decided; a pixel
+//    accepted in between is struck from the prefetched set by index.
 __device__ int region_grow(const Frame& f, int seed, double& reg_angle, double prec, int lane) {
-  const int W = f.W, H = f.H;
-  reg_angle = (double)f.pix[seed].x * kDegToRad;
-  float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+  const int W = f.W;
+  const float4 srec = f.pix[seed];
+  reg_angle = (double)srec.x * kDegToRad;
+  // The reference seeds the sums with (float)cos(reg_angle) of the fp64 angle; that value only matters once a
+  // second pixel joins (most seeds grow nothing), so it is evaluated at the first accept.  Until then the
+  // quick test runs on the record's cos / sin (same direction to 1e-7) and the exact test on reg_angle itself.
+  float sumdx = srec.y, sumdy = srec.z;
   const int sy = seed / W, sx = seed - sy * W;
   if (lane == 0) {
-    f.reg[0] = ((uint32_t)sy << 16) | (uint32_t)sx;
-    f.used[seed] = 1;
+    const uint32_t c = ((uint32_t)sy << 16) | (uint32_t)sx;
+    f.reg[0] = c;
+    f.ring[0] = c;
+    *flags_of(f, seed) = __float_as_int(srec.w) | lsdw_kUsed;
   }
   __syncwarp();
+  const double band = 0.5 * kDegToRad;
+  const bool quick = prec + band < 1.5 && prec > band;   // both cosines positive: the test can be made on squares
+  const float chi = quick ? (float)cos(prec - band) : 2.f;   // dot >= chi * |sum|: aligned for sure
+  const float clo = quick ? (float)cos(prec + band) : 0.f;   // dot <= clo * |sum|: not aligned for sure
+  const float chi2 = chi * chi, clo2 = clo * clo;
+  float s2 = sumdx * sumdx + sumdy * sumdy;
+  bool angle_valid = true;
   int n = 1;
   const int p = lane / 9, k = lane - 9 * p;
   const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
-  for (int i = 0; i < n;) {
-    const int m = min(3, n - i);
-    bool cand = false;
-    int nidx = -1;
-    float4 rec = make_float4(kNotDefDeg, 0.f, 0.f, 0.f);
-    uint32_t npk = 0;
-    if (p < m) {
-      const uint32_t c = f.reg[i + p];
-      const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
-      if (xx >= 0 && xx < W && yy >= 0 && yy < H) {
-        nidx = yy * W + xx;
-        npk = ((uint32_t)yy << 16) | (uint32_t)xx;
-        if (f.used[nidx] != 1) {
-          rec = f.pix[nidx];
-          cand = rec.x != kNotDefDeg;
-        }
-      }
-    }
-    unsigned mask = __ballot_sync(kFull, cand);
+  int i = 0, m = 1;
+  Nbr cur = load_nbr(f, 0, 1, 1, p, ox, oy);
+  while (true) {
+    // prefetch the neighbours of the region points that already exist beyond the current ones
+    const int m2 = min(3, n - (i + m));
+    Nbr nxt = load_nbr(f, i + m, m2, n, p, ox, oy);
+    unsigned mask = __ballot_sync(kFull, cur.cand);
     while (mask) {
-      const bool ok = cand && aligned_deg(rec.x, reg_angle, prec);
+      const float dot = cur.rec.y * sumdx + cur.rec.z * sumdy, dot2 = dot * dot;
+      const bool sure = quick && s2 > 1e-6f;   // opposing gradients cancelled: no direction to test against
+      bool ok = cur.cand && sure && dot > 0.f && dot2 >= chi2 * s2;
+      const bool maybe = cur.cand && !ok && (!sure || (dot > 0.f && dot2 > clo2 * s2));
+      if (__ballot_sync(kFull, maybe) & mask) {
+        if (!angle_valid) {
+          reg_angle = (double)lsd::fast_atan2(sumdy, sumdx) * kDegToRad;
+          angle_valid = true;
+        }
+        if (maybe) ok = aligned_deg(cur.rec.x, reg_angle, prec);
+      }
       const unsigned am = __ballot_sync(kFull, ok) & mask;
       if (!am) break;
       const int j = __ffs(am) - 1;
-      const int aidx = __shfl_sync(kFull, nidx, j);
-      const uint32_t apk = __shfl_sync(kFull, npk, j);
-      sumdx += __shfl_sync(kFull, rec.y, j);
-      sumdy += __shfl_sync(kFull, rec.z, j);
-      if (lane == 0) {
-        f.used[aidx] = 1;
-        f.reg[n] = apk;
+      const int aidx = __shfl_sync(kFull, cur.nidx, j);
+      if (n == 1) {  // first accept: the exact seed terms
+        sumdx = (float)cos(reg_angle);
+        sumdy = (float)sin(reg_angle);
+      }
+      sumdx += __shfl_sync(kFull, cur.rec.y, j);
+      sumdy += __shfl_sync(kFull, cur.rec.z, j);
+      if (lane == j) {
+        *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
+        f.reg[n] = cur.npk;
+        f.ring[n & (kRing - 1)] = cur.npk;
       }
       ++n;
-      reg_angle = (double)lsd::fast_atan2(sumdy, sumdx) * kDegToRad;
-      if (nidx == aidx) cand = false;           // the same pixel seen from another centre is now USED
-      mask &= ~((2u << j) - 1u);                // tests before j were made (and failed) with the older angle
-      mask &= __ballot_sync(kFull, cand);
+      s2 = sumdx * sumdx + sumdy * sumdy;
+      angle_valid = false;
+      if (cur.nidx == aidx) cur.cand = false;   // the same pixel seen from another centre is now USED
+      if (nxt.nidx == aidx) nxt.cand = false;
+      mask &= ~((2u << j) - 1u);                // tests before j were made (and failed) with the older sums
     }
     i += m;
+    if (i >= n) break;
     __syncwarp();
+    if (m2 > 0) {
+      cur = nxt;
+      m = m2;
+    } else {  // the next points were appended during this step
+      m = min(3, n - i);
+      cur = load_nbr(f, i, m, n, p, ox, oy);
+    }
   }
+  if (!angle_valid) reg_angle = (double)lsd::fast_atan2(sumdy, sumdx) * kDegToRad;
+  __syncwarp();
   return n;
 }
 
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy; };
 
 __device__ __forceinline__ double modgrad(const Frame& f, int idx) {
-  return sqrt((double)__float_as_int(f.pix[idx].w) / 4.0);
+  return sqrt((double)(*flags_of(f, idx) & lsdw_kN2Mask) / 4.0);
 }
 
 __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec, Rect& rec, int lane) {
@@ -236,7 +302,7 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
     const int i = base + lane;
     double tx = 0, ty = 0, w = 0;
     if (i < n) {
-      const uint32_t c = f.reg[i];
+      const uint32_t c = reg_at(f, i, n);
       const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
       w = modgrad(f, py * f.W + px);
       tx = (double)px * w;
@@ -257,7 +323,7 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
     const int i = base + lane;
     double t1 = 0, t2 = 0, t3 = 0;
     if (i < n) {
-      const uint32_t c = f.reg[i];
+      const uint32_t c = reg_at(f, i, n);
       const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
       const double w = modgrad(f, py * f.W + px), dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * w;
@@ -283,7 +349,7 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
   // independent max and min (a value above the running max is positive, so it cannot lower the min)
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = lane; i < n; i += 32) {
-    const uint32_t c = f.reg[i];
+    const uint32_t c = reg_at(f, i, n);
     const double rdx = (double)(int)(c & 0xFFFFu) - x, rdy = (double)(int)(c >> 16) - y;
     const double l = rdx * dx + rdy * dy, w = -rdx * dy + rdy * dx;
     l_max = l > l_max ? l : l_max;
@@ -310,7 +376,8 @@ __device__ __forceinline__ double density_of(int n, const Rect& rec) {
 }
 
 // reduce_region_radius: the swap-with-last removal defines the order of the surviving points (and with it
-// the rounding of the next region2rect), so lane 0 replays it; the rectangle fits stay cooperative.
+// the rounding of the next region2rect), so lane 0 replays it on the HBM list; the rectangle fits stay
+// cooperative.
 __device__ bool reduce_region_radius(const Frame& f, int& n, double reg_angle, double prec, Rect& rec, double density,
                                      int lane) {
   const uint32_t c0 = f.reg[0];
@@ -325,7 +392,7 @@ __device__ bool reduce_region_radius(const Frame& f, int& n, double reg_angle, d
         const uint32_t c = f.reg[i];
         const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
         if (lsd::dist_sq(xc, yc, (double)px, (double)py) > radSq) {
-          f.used[py * f.W + px] = 0;
+          *flags_of(f, py * f.W + px) &= ~lsdw_kUsed;
           f.reg[i] = f.reg[m - 1];
           f.reg[m - 1] = c;
           --m;
@@ -337,6 +404,9 @@ __device__ bool reduce_region_radius(const Frame& f, int& n, double reg_angle, d
     n = __shfl_sync(kFull, n, 0);
     __syncwarp();
     if (n < 2) return false;
+    if (n <= kRing)
+      for (int i = lane; i < n; i += 32) f.ring[i] = f.reg[i];
+    __syncwarp();
     region2rect(f, n, reg_angle, prec, rec, lane);
     density = density_of(n, rec);
   }
@@ -356,11 +426,12 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
     double a = 0, a2 = 0;   // points outside the radius add +0.0, which leaves the sums unchanged
     bool in = false;
     if (i < n) {
-      const uint32_t c = f.reg[i];
+      const uint32_t c = reg_at(f, i, n);
       const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
-      f.used[py * f.W + px] = 0;
+      const float4 r = f.pix[py * f.W + px];
+      *flags_of(f, py * f.W + px) = __float_as_int(r.w) & ~lsdw_kUsed;
       if (sqrt(lsd::dist_sq(xc, yc, (double)px, (double)py)) < rec.width) {
-        a = lsd::angle_diff_signed((double)f.pix[py * f.W + px].x * kDegToRad, ang_c);
+        a = lsd::angle_diff_signed((double)r.x * kDegToRad, ang_c);
         a2 = a * a;
         in = true;
       }
@@ -385,11 +456,15 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
 
 }  // namespace lsdw
 
-__global__ void __launch_bounds__(32)
-    lsd_core_kernel(LineBuffers L, uint32_t* __restrict__ status) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never synchronise with each other)
+
+__global__ void __launch_bounds__(kCoreWarps * 32)
+    lsd_core_kernel(LineBuffers L, int nb, uint32_t* __restrict__ status) {
+  __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
+  const int wid = threadIdx.x >> 5, b = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
+  if (b >= nb) return;
   const size_t npx = (size_t)L.Ws * L.Hs;
-  lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.used + b * npx, L.reg + b * npx};
+  lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.reg + b * npx, ring[wid]};
   const uint32_t* seeds = L.val_out + b * npx;
   const int n_seeds = L.n_def[b];
   float* out = L.raw + (size_t)b * L.raw_cap * 4;
@@ -398,12 +473,12 @@ __global__ void __launch_bounds__(32)
   for (int s0 = 0; s0 < n_seeds; s0 += 32) {
     const int my = s0 + lane < n_seeds ? (int)seeds[s0 + lane] : -1;
     // a pixel that is USED now stays USED (only the pixels of the region being refined are ever released)
-    unsigned todo = __ballot_sync(lsdw::kFull, my >= 0 && f.used[my] == 0);
+    unsigned todo = __ballot_sync(lsdw::kFull, my >= 0 && !(*lsdw::flags_of(f, my >= 0 ? my : 0) & lsdw_kUsed));
     while (todo) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
       const int seed = __shfl_sync(lsdw::kFull, my, l);
-      if (f.used[seed] != 0) continue;
+      if (*lsdw::flags_of(f, seed) & lsdw_kUsed) continue;
       double reg_angle;
       int n = lsdw::region_grow(f, seed, reg_angle, prec, lane);
       if (n < L.min_reg_size) continue;
@@ -446,7 +521,7 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
   cudaMemsetAsync(L.max_n2, 0xFF, (size_t)nb * sizeof(int32_t), st);  // -1
   const double rho = 2.0 / sin(lsd::kPi * lsd::kAngTh / 180);
   dim3 rows((L.Hs + 3) / 4, nb);
-  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.pix, L.used, L.max_n2, L.row_cnt, rho);
+  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.pix, L.max_n2, L.row_cnt, rho);
   lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, npx, L.n_def, L.seg_begin, L.seg_end);
   lsd_keys_kernel<<<rows, 128, 0, st>>>(L.pix, L.Ws, L.Hs, L.max_n2, L.row_cnt, L.key_in, L.val_in);
 }
@@ -460,7 +535,7 @@ void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st) {
 }
 
 void launch_lsd_core(const LineBuffers& L, int nb, uint32_t* status, cudaStream_t st) {
-  lsd_core_kernel<<<nb, 32, 0, st>>>(L, status);
+  lsd_core_kernel<<<(nb + kCoreWarps - 1) / kCoreWarps, kCoreWarps * 32, 0, st>>>(L, nb, status);
 }
 
 }  // namespace psl

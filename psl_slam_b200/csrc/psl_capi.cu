@@ -279,9 +279,12 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
     ctx->quota[L - 1] = std::max(cfg->orb_nfeatures - sum, 0);
   }
   ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 256;
-  ctx->line_chunk = cfg->line_chunk_frames > 0 ? cfg->line_chunk_frames : 1024;
+  ctx->line_chunk = cfg->line_chunk_frames > 0 ? cfg->line_chunk_frames : std::min(std::max(cfg->max_batch, 64), 4096);
   ctx->pool_cap = cfg->orb_max_candidates > 0 ? cfg->orb_max_candidates : std::max(16384, 32 * cfg->orb_nfeatures);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc(&ctx->d_geo, sizeof(OrbGeometry)) == cudaSuccess &&
             cudaMalloc(&ctx->d_status, sizeof(uint32_t)) == cudaSuccess &&
             cudaMemset(ctx->d_status, 0, sizeof(uint32_t)) == cudaSuccess &&
@@ -297,6 +300,7 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
 void psl_destroy(psl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_geometry(ctx);
   free_line_geometry(ctx);
@@ -313,6 +317,9 @@ void psl_destroy(psl_ctx* ctx) {
     cudaFree(b->p);
   for (DevBuf& b : ctx->m_misc) cudaFree(b.p);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -16,6 +16,8 @@ struct DevBuf {
 struct psl_ctx {
   psl_config cfg{};
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;          // the line path of the combined front end runs beside the point path
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   int chunk = 0;
   int pool_cap = 0;

@@ -67,7 +67,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   uint8_t* tmp = nullptr;
   bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
             lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx) &&
-            lalloc(ctx, L.used, C * npx) && lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
+            lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
             lalloc(ctx, L.key_out, C * npx) && lalloc(ctx, L.val_in, C * npx) && lalloc(ctx, L.val_out, C * npx) &&
             lalloc(ctx, L.seg_begin, C) && lalloc(ctx, L.seg_end, C) && lalloc(ctx, tmp, L.sort_tmp_bytes) &&

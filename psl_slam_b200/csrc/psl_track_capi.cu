@@ -133,14 +133,31 @@ int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gr
       o->line_cap > kMaxLinesPerFrame)
     return fail(ctx, PSL_E_INVALID, "bad line output block");
   if (B <= 0) return B == 0 ? PSL_OK : fail(ctx, PSL_E_INVALID, "bad argument");
-  int rc = psl_track_orb_batch_dev(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px,
-                                   depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, o->kps, o->desc, o->n, o->u_right, o->z,
-                                   o->assign, o->nmatches, o->cap);
-  if (rc) return rc;
+  // The line path (latency-bound: one warp walks one frame) and the point path (bandwidth / ALU-bound) are
+  // independent until the matchers, so they run on two streams and share the SMs; with per-stage profiling on
+  // they are serialised so that the stage timings stay meaningful.
   const int lc = o->line_cap;
+  cudaStream_t main_st = ctx->stream;
+  const bool overlap = !ctx->prof;
+  int rc;
+  if (overlap) {
+    PSL_CK(cudaSetDevice(ctx->cfg.device));
+    PSL_CK(cudaEventRecord(ctx->ev_fork, main_st));
+    PSL_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    ctx->stream = ctx->stream2;
+  }
   rc = psl_line_extract_batch_dev(ctx, d_gray, B, w, h, gray_stride, gray_frame_stride, o->kl, o->ldesc, o->lineeq, nullptr,
                                   lc, o->nl);
+  ctx->stream = main_st;
+  if (overlap && !rc) {
+    PSL_CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  }
   if (rc) return rc;
+  rc = psl_track_orb_batch_dev(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px,
+                               depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, o->kps, o->desc, o->n, o->u_right, o->z,
+                               o->assign, o->nmatches, o->cap);
+  if (rc) return rc;
+  if (overlap) PSL_CK(cudaStreamWaitEvent(main_st, ctx->ev_join, 0));
   // SearchByGeomNApearance(frame b, frame b-1): the Last set is the same [B][line_cap] block shifted by one frame
   cudaStream_t st = ctx->stream;
   if ((rc = ensure(ctx, ctx->m_misc[9], (size_t)B * lc * 8))) return rc;

@@ -8,8 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=1024)
-    ap.add_argument("--chunk", type=int, default=1024)
+    ap.add_argument("--frames", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--distinct", type=int, default=8)
     ap.add_argument("--lowtex", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
