@@ -198,7 +198,8 @@ def workload_config(frames_per_gpu):
                         "consecutive synthetic textured 640x480 RGB-D frames (ICL intrinsics)",
             "frames_per_step_per_gpu": frames_per_gpu, "width": W, "height": H,
             "l2_policy": "inputs larger than L2 (frames_per_step x 307 KB >> 126 MB), no flush",
-            "parallelism": "frames sharded across GPUs, no collective"}
+            "parallelism": "one sequence of frames_per_step_per_gpu x n_gpus frames in contiguous shards (one-frame "
+                           "halo re-extracted per shard), no collective"}
 
 
 def main():
@@ -234,18 +235,24 @@ def main():
 
     F = args.frames
     cfg = default_config()
-    cfg.device, cfg.max_width, cfg.max_height, cfg.max_batch = local, W, H, F
+    cfg.device, cfg.max_width, cfg.max_height, cfg.max_batch = local, W, H, F + 1
     cfg.orb_nfeatures, cfg.orb_scale_factor, cfg.orb_nlevels = ORB["nfeatures"], ORB["scale"], ORB["nlevels"]
     cfg.orb_ini_th_fast, cfg.orb_min_th_fast = ORB["ini"], ORB["mn"]
-    cfg.chunk_frames, cfg.line_chunk_frames, cfg.line_nfeatures = args.chunk, args.line_chunk, LINE["nfeatures"]
+    cfg.chunk_frames, cfg.line_nfeatures = args.chunk, LINE["nfeatures"]
+    cfg.line_chunk_frames = args.line_chunk or min(F + 1, 4100)
     ex = ORBextractor(ctx=Context(cfg))
     cap, lcap = ex.cap, LINE["nfeatures"]
     from psl_slam_b200 import make_camera, make_track_params, synth, track_frontend_batch_dev
     K = synth.ICL
     cam = make_camera(K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], K["depth_factor"])
     tprm = make_track_params(TRACK["th"], TRACK["nn_ratio"], TRACK["ori"])
-    base_g, base_d, base_T = synth_frames(16, seed=4 + rank)      # distinct synthetic sequence per rank
-    idx = torch.from_numpy(ping_pong(16, F)).cuda()
+    # cfg 4: one long sequence (F frames per GPU, F x N in total) in contiguous shards; ranks > 0 re-extract the
+    # frame before their range (one-frame halo) so that every owned frame is matched against its predecessor
+    from psl_slam_b200.shard import shard_with_halo
+    base_g, base_d, base_T = synth_frames(16, seed=4)
+    s0, s1, halo = shard_with_halo(F * world, rank, world)
+    idx = torch.from_numpy(ping_pong(16, F * world)[s0:s1]).cuda()
+    F_own, F = F, s1 - s0                                         # F now counts the halo frame too
     d_gray = torch.from_numpy(base_g).cuda()[idx].contiguous()    # [F,H,W] u8 resident in HBM
     d_depth = torch.from_numpy(base_d.view(np.int16)).cuda()[idx].contiguous()  # u16 bits
     d_T = torch.from_numpy(base_T).cuda()[idx].contiguous()
@@ -304,7 +311,7 @@ def main():
     n_kp = int(d_n.sum().item())
     n_match = int(d_nm.sum().item())
     n_lines, n_lmatch = int(d_nl.sum().item()), int(d_lnm.sum().item())
-    value = world * F * args.steps / (ms * 1e-3)
+    value = world * F_own * args.steps / (ms * 1e-3)
 
     # ---- per-stage pass (same steps, events between stages) -> roofline ----------------------
     ex.ctx.profile(True)
@@ -383,7 +390,7 @@ def main():
         t = torch.tensor([dt], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    e2e = {"value": world * F * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": F * (W * H * 3 + 48),
+    e2e = {"value": world * F_own * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": F * (W * H * 3 + 48),
            "d2h_bytes_per_step": F * (cap * (28 + 32 + 12) + lcap * (68 + 32 + 24 + 4) + 16), "steps": e2e_steps,
            "results_equal_device_path": int(h_n.sum().item()) == n_kp and int(h_nm.sum().item()) == n_match and
            int(h_nl.sum().item()) == n_lines and int(h_lnm.sum().item()) == n_lmatch}
@@ -396,7 +403,7 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-               "config": workload_config(F), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+               "config": workload_config(F_own), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
                "keypoints_per_frame": n_kp / F, "matches_per_frame": n_match / max(F - 1, 1),
                "lines_per_frame": n_lines / F, "line_matches_per_frame": n_lmatch / max(F - 1, 1)}

@@ -137,6 +137,17 @@ __global__ void __launch_bounds__(128)
 // done 27-wide.  The fp64 running sums of region2rect / refine are added in the reference's order
 // (one lane-ordered shuffle chain), the extents are exact min/max reductions.
 // ---------------------------------------------------------------------------------------------------
+#ifdef PSL_LSD_STATS
+__device__ unsigned long long g_lsd_stats[16];
+#define LSD_STAT(i, v) do { const unsigned long long v__ = (unsigned long long)(v); if (lane == 0) atomicAdd(&g_lsd_stats[i], v__); } while (0)
+#define LSD_T0(t) long long t = clock64()
+#define LSD_T1(i, t) do { LSD_STAT(i, clock64() - t); } while (0)
+#else
+#define LSD_STAT(i, v) do { } while (0)
+#define LSD_T0(t) do { } while (0)
+#define LSD_T1(i, t) do { } while (0)
+#endif
+
 namespace lsdw {
 
 using lsd::kDegToRad;
@@ -181,6 +192,20 @@ struct Nbr {
   bool cand;      // unused and with a defined angle when it was loaded
 };
 
+__device__ __forceinline__ Nbr load_nbr_at(const Frame& f, bool active, uint32_t c, int ox, int oy) {
+  Nbr b{-1, 0u, make_float4(kNotDefDeg, 0.f, 0.f, 0.f), false};
+  if (active) {
+    const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
+    if (xx >= 0 && xx < f.W && yy >= 0 && yy < f.H) {
+      b.nidx = yy * f.W + xx;
+      b.npk = ((uint32_t)yy << 16) | (uint32_t)xx;
+      b.rec = f.pix[b.nidx];
+      b.cand = !(__float_as_int(b.rec.w) & lsdw_kUsed) && b.rec.x != kNotDefDeg;
+    }
+  }
+  return b;
+}
+
 __device__ __forceinline__ Nbr load_nbr(const Frame& f, int first, int m, int n, int p, int ox, int oy) {
   Nbr b{-1, 0u, make_float4(kNotDefDeg, 0.f, 0.f, 0.f), false};
   if (p < m) {
@@ -204,16 +229,85 @@ __device__ __forceinline__ Nbr load_nbr(const Frame& f, int first, int m, int n,
 //    (cos_i * sumdx + sin_i * sumdy against cos(prec -/+ 0.5 deg) * |sum|): fastAtan2 is within 0.01 deg of the
 //    true angle and the fp32 dot product within 1e-6, so outside the +/- 0.5 deg band the outcome is certain;
 //    only a neighbour inside the band takes the exact path (fastAtan2 of the sums + the fp64 comparison);
-//  * the records of the next region points are loaded while the current ones are being decided; a pixel
-//    accepted in between is struck from the prefetched set by index.
+//  * a whole step (<= 27 tests) is decided at once when that is provably what the scalar loop would do:
+//    guess the accepted set A from the sums before the step, give every lane the sums it would see in the
+//    scalar loop (the prefix over the lanes of A before it), and re-test; if every lane's outcome under its own
+//    prefix is certain and reproduces A, then A is the scalar loop's result by induction over the lanes.  The
+//    prefix only feeds the certain / uncertain classification; the running sums themselves are then advanced
+//    by the accepted terms in lane order, i.e. with the reference's fp32 rounding.  Any other step replays the
+//    scalar loop.
+struct Grow {
+  float sumdx, sumdy, s2;
+  double reg_angle;
+  bool angle_valid;
+  int n;
+};
+
+__device__ __forceinline__ void accept_terms(const Frame& f, Grow& g, const Nbr& cur, unsigned A, int lane,
+                                             Nbr* nxt = nullptr) {
+  if (g.n == 1) {  // first accept of the region: the exact seed terms (see region_grow)
+    g.sumdx = (float)cos(g.reg_angle);
+    g.sumdy = (float)sin(g.reg_angle);
+  }
+  if (A >> lane & 1u) {
+    const int at = g.n + __popc(A & ((1u << lane) - 1u));
+    *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
+    f.reg[at] = cur.npk;
+    f.ring[at & (kRing - 1)] = cur.npk;
+  }
+  g.n += __popc(A);
+  for (unsigned a = A; a; a &= a - 1) {  // lane order = the reference's order of additions
+    const int j = __ffs(a) - 1;
+    g.sumdx += __shfl_sync(kFull, cur.rec.y, j);
+    g.sumdy += __shfl_sync(kFull, cur.rec.z, j);
+    if (nxt) {  // records loaded before this step's flag stores: strike what has just become USED
+      const int aidx = __shfl_sync(kFull, cur.nidx, j);
+      if (nxt->nidx == aidx) nxt->cand = false;
+    }
+  }
+  g.s2 = g.sumdx * g.sumdx + g.sumdy * g.sumdy;
+  g.angle_valid = false;
+}
+
+// the scalar loop over the lanes of one step
+__device__ void step_sequential(const Frame& f, Grow& g, Nbr& cur, double prec, bool quick, float chi2, float clo2,
+                                int lane) {
+  unsigned mask = __ballot_sync(kFull, cur.cand);
+  while (mask) {
+    const float dot = cur.rec.y * g.sumdx + cur.rec.z * g.sumdy, dot2 = dot * dot;
+    const bool sure = quick && g.s2 > 1e-6f;   // opposing gradients cancelled: no direction to test against
+    bool ok = cur.cand && sure && dot > 0.f && dot2 >= chi2 * g.s2;
+    const bool maybe = cur.cand && !ok && (!sure || (dot > 0.f && dot2 > clo2 * g.s2));
+    if (__ballot_sync(kFull, maybe) & mask) {
+      if (!g.angle_valid) {
+        g.reg_angle = (double)lsd::fast_atan2(g.sumdy, g.sumdx) * kDegToRad;
+        g.angle_valid = true;
+      }
+      if (maybe) ok = aligned_deg(cur.rec.x, g.reg_angle, prec);
+    }
+    const unsigned am = __ballot_sync(kFull, ok) & mask;
+    if (!am) break;
+    const int j = __ffs(am) - 1;
+    const int aidx = __shfl_sync(kFull, cur.nidx, j);
+    accept_terms(f, g, cur, 1u << j, lane);
+    if (cur.nidx == aidx) cur.cand = false;   // the same pixel seen from another centre is now USED
+    mask &= ~((2u << j) - 1u);                // tests before j were made (and failed) with the older sums
+  }
+}
+
 __device__ int region_grow(const Frame& f, int seed, double& reg_angle, double prec, int lane) {
   const int W = f.W;
   const float4 srec = f.pix[seed];
-  reg_angle = (double)srec.x * kDegToRad;
+  Grow g;
+  g.reg_angle = (double)srec.x * kDegToRad;
   // The reference seeds the sums with (float)cos(reg_angle) of the fp64 angle; that value only matters once a
   // second pixel joins (most seeds grow nothing), so it is evaluated at the first accept.  Until then the
   // quick test runs on the record's cos / sin (same direction to 1e-7) and the exact test on reg_angle itself.
-  float sumdx = srec.y, sumdy = srec.z;
+  g.sumdx = srec.y;
+  g.sumdy = srec.z;
+  g.s2 = g.sumdx * g.sumdx + g.sumdy * g.sumdy;
+  g.angle_valid = true;
+  g.n = 1;
   const int sy = seed / W, sx = seed - sy * W;
   if (lane == 0) {
     const uint32_t c = ((uint32_t)sy << 16) | (uint32_t)sx;
@@ -227,66 +321,87 @@ __device__ int region_grow(const Frame& f, int seed, double& reg_angle, double p
   const float chi = quick ? (float)cos(prec - band) : 2.f;   // dot >= chi * |sum|: aligned for sure
   const float clo = quick ? (float)cos(prec + band) : 0.f;   // dot <= clo * |sum|: not aligned for sure
   const float chi2 = chi * chi, clo2 = clo * clo;
-  float s2 = sumdx * sumdx + sumdy * sumdy;
-  bool angle_valid = true;
-  int n = 1;
   const int p = lane / 9, k = lane - 9 * p;
   const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
+  const unsigned lt = (1u << lane) - 1u;
+  // Software pipeline: the records of the next step's neighbours are requested as soon as the accepted set of
+  // the current step is known (its region points are the next entries of the list), i.e. before the flag /
+  // list stores and the ordered sum update of the current step; pixels accepted in the current step are
+  // struck from the prefetched set by index.
   int i = 0, m = 1;
   Nbr cur = load_nbr(f, 0, 1, 1, p, ox, oy);
   while (true) {
-    // prefetch the neighbours of the region points that already exist beyond the current ones
-    const int m2 = min(3, n - (i + m));
-    Nbr nxt = load_nbr(f, i + m, m2, n, p, ox, oy);
-    unsigned mask = __ballot_sync(kFull, cur.cand);
-    while (mask) {
-      const float dot = cur.rec.y * sumdx + cur.rec.z * sumdy, dot2 = dot * dot;
-      const bool sure = quick && s2 > 1e-6f;   // opposing gradients cancelled: no direction to test against
-      bool ok = cur.cand && sure && dot > 0.f && dot2 >= chi2 * s2;
-      const bool maybe = cur.cand && !ok && (!sure || (dot > 0.f && dot2 > clo2 * s2));
-      if (__ballot_sync(kFull, maybe) & mask) {
-        if (!angle_valid) {
-          reg_angle = (double)lsd::fast_atan2(sumdy, sumdx) * kDegToRad;
-          angle_valid = true;
+    i += m;                       // first region point of the next step
+    const unsigned cm = __ballot_sync(kFull, cur.cand);
+    bool batched = false;
+    unsigned A = 0;
+    if (!cm) {
+      batched = true;
+    } else if (quick && g.s2 > 1e-6f) {
+      // guess: the lanes that pass under the sums before the step (first lane of every repeated pixel)
+      const float dot = cur.rec.y * g.sumdx + cur.rec.z * g.sumdy;
+      const bool yes0 = cur.cand && dot > 0.f && dot * dot >= chi2 * g.s2;
+      A = __ballot_sync(kFull, yes0);
+      unsigned same = 1u << lane;   // cand lanes holding the same pixel (only possible across centres)
+      if (m > 1) {
+        if (cur.cand) same = __match_any_sync(cm, cur.nidx);
+        A = __ballot_sync(kFull, yes0 && !(same & A & lt));
+      }
+      if (A == 0) {
+        // nobody passes under the current sums; certain for all only if no lane sits in the band
+        const bool maybe0 = cur.cand && !yes0 && dot > 0.f && dot * dot > clo2 * g.s2;
+        batched = !__any_sync(kFull, maybe0);
+      } else {
+        // the sums every lane would see in the scalar loop: exclusive prefix over A (for classification only)
+        const bool inA = A >> lane & 1u;
+        float px = inA ? cur.rec.y : 0.f, py = inA ? cur.rec.z : 0.f;
+        const float ownx = px, owny = py;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float ux = __shfl_up_sync(kFull, px, d), uy = __shfl_up_sync(kFull, py, d);
+          if (lane >= d) { px += ux; py += uy; }
         }
-        if (maybe) ok = aligned_deg(cur.rec.x, reg_angle, prec);
+        // (at the first accept the exact seed terms replace the record's: same to 1e-7, far inside the band)
+        const float Px = g.sumdx + (px - ownx), Py = g.sumdy + (py - owny);
+        const float d1 = cur.rec.y * Px + cur.rec.z * Py, q1 = Px * Px + Py * Py;
+        const bool sure1 = q1 > 1e-6f;
+        const bool yes1 = cur.cand && sure1 && d1 > 0.f && d1 * d1 >= chi2 * q1;
+        const bool no1 = !cur.cand || (sure1 && (d1 <= 0.f || d1 * d1 <= clo2 * q1));
+        const bool taken = (same & A & lt) != 0;       // an earlier lane of A holds this pixel: USED by then
+        const bool expect = yes1 && !taken;
+        const bool certain = taken || yes1 || no1;
+        const unsigned E = __ballot_sync(kFull, expect);
+        batched = __all_sync(kFull, certain) && E == A;
       }
-      const unsigned am = __ballot_sync(kFull, ok) & mask;
-      if (!am) break;
-      const int j = __ffs(am) - 1;
-      const int aidx = __shfl_sync(kFull, cur.nidx, j);
-      if (n == 1) {  // first accept: the exact seed terms
-        sumdx = (float)cos(reg_angle);
-        sumdy = (float)sin(reg_angle);
-      }
-      sumdx += __shfl_sync(kFull, cur.rec.y, j);
-      sumdy += __shfl_sync(kFull, cur.rec.z, j);
-      if (lane == j) {
-        *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
-        f.reg[n] = cur.npk;
-        f.ring[n & (kRing - 1)] = cur.npk;
-      }
-      ++n;
-      s2 = sumdx * sumdx + sumdy * sumdy;
-      angle_valid = false;
-      if (cur.nidx == aidx) cur.cand = false;   // the same pixel seen from another centre is now USED
-      if (nxt.nidx == aidx) nxt.cand = false;
-      mask &= ~((2u << j) - 1u);                // tests before j were made (and failed) with the older sums
     }
-    i += m;
-    if (i >= n) break;
-    __syncwarp();
-    if (m2 > 0) {
+    if (batched) {
+      const int n_old = g.n, n_new = n_old + __popc(A);
+      if (i >= n_new) break;      // the list is exhausted (A is empty here)
+      // region points i .. i+2: from the list while they exist, else the lanes of A in order
+      const int m2 = min(3, n_new - i), idx = i + p;
+      uint32_t c = 0;
+      const unsigned A1 = A & (A - 1), A2 = A1 & (A1 - 1);
+      const int r = idx - n_old;  // >= 0: the r-th accepted lane of this step
+      const int src = r <= 0 ? __ffs(A) - 1 : (r == 1 ? __ffs(A1) - 1 : __ffs(A2) - 1);
+      const uint32_t fromA = __shfl_sync(kFull, cur.npk, src < 0 ? 0 : src);
+      if (p < m2) c = idx < n_old ? reg_at(f, idx, n_old) : fromA;
+      Nbr nxt = load_nbr_at(f, p < m2, c, ox, oy);
+      if (A) accept_terms(f, g, cur, A, lane, &nxt);
       cur = nxt;
       m = m2;
-    } else {  // the next points were appended during this step
-      m = min(3, n - i);
-      cur = load_nbr(f, i, m, n, p, ox, oy);
+    } else {
+      step_sequential(f, g, cur, prec, quick, chi2, clo2, lane);
+      if (i >= g.n) break;
+      __syncwarp();
+      m = min(3, g.n - i);
+      cur = load_nbr(f, i, m, g.n, p, ox, oy);
     }
+    __syncwarp();
   }
-  if (!angle_valid) reg_angle = (double)lsd::fast_atan2(sumdy, sumdx) * kDegToRad;
+  if (!g.angle_valid) g.reg_angle = (double)lsd::fast_atan2(g.sumdy, g.sumdx) * kDegToRad;
+  reg_angle = g.reg_angle;
   __syncwarp();
-  return n;
+  return g.n;
 }
 
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy; };
@@ -458,7 +573,7 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
 
 constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never synchronise with each other)
 
-__global__ void __launch_bounds__(kCoreWarps * 32)
+__global__ void __launch_bounds__(kCoreWarps * 32, 7)
     lsd_core_kernel(LineBuffers L, int nb, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
   const int wid = threadIdx.x >> 5, b = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
@@ -470,6 +585,7 @@ __global__ void __launch_bounds__(kCoreWarps * 32)
   float* out = L.raw + (size_t)b * L.raw_cap * 4;
   const double prec = lsd::kPi * lsd::kAngTh / 180;
   int nseg = 0;
+  LSD_T0(t_all);
   for (int s0 = 0; s0 < n_seeds; s0 += 32) {
     const int my = s0 + lane < n_seeds ? (int)seeds[s0 + lane] : -1;
     // a pixel that is USED now stays USED (only the pixels of the region being refined are ever released)
@@ -480,11 +596,19 @@ __global__ void __launch_bounds__(kCoreWarps * 32)
       const int seed = __shfl_sync(lsdw::kFull, my, l);
       if (*lsdw::flags_of(f, seed) & lsdw_kUsed) continue;
       double reg_angle;
+      LSD_T0(t_g);
       int n = lsdw::region_grow(f, seed, reg_angle, prec, lane);
+      LSD_T1(10, t_g);
+      LSD_STAT(13, 1);
       if (n < L.min_reg_size) continue;
       lsdw::Rect rec;
+      LSD_T0(t_r);
       lsdw::region2rect(f, n, reg_angle, prec, rec, lane);
-      if (!lsdw::refine(f, n, reg_angle, prec, rec, lane)) continue;
+      LSD_T1(11, t_r);
+      LSD_T0(t_f);
+      const bool okr = lsdw::refine(f, n, reg_angle, prec, rec, lane);
+      LSD_T1(12, t_f);
+      if (!okr) continue;
       rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
       rec.x1 /= lsd::kScale; rec.y1 /= lsd::kScale; rec.x2 /= lsd::kScale; rec.y2 /= lsd::kScale;
       if (lane == 0 && nseg < L.raw_cap) {
@@ -494,11 +618,21 @@ __global__ void __launch_bounds__(kCoreWarps * 32)
       ++nseg;
     }
   }
+  LSD_T1(14, t_all);
   if (lane == 0) {
     L.n_raw[b] = nseg < L.raw_cap ? nseg : L.raw_cap;
     if (nseg > L.raw_cap) atomicOr(status, kStatLineRaw);
   }
 }
+
+#ifdef PSL_LSD_STATS
+extern "C" void psl_lsd_stats(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_lsd_stats, sizeof(g_lsd_stats));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_lsd_stats, z, sizeof(z));
+}
+#endif
 
 size_t lsd_sort_temp_bytes(int items_per_frame, int frames) {
   size_t bytes = 0;

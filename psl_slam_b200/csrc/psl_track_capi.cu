@@ -124,10 +124,20 @@ int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth
 }
 
 
-int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
-                                 const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
-                                 int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
-                                 const psl_track_params* prm, float line_desc_th, const psl_frontend_out* o) {
+}  // extern "C"
+
+namespace {
+struct Copy { void* dst; const void* src; size_t bytes; };
+
+// The combined front end on device-resident data.  `late_in` are host->device copies of inputs only the point
+// path needs (depth, poses) and `early_out` device->host copies of the point results: the host-pointer entry
+// point uses them so that the line path (which needs the gray frames only and is the longer of the two) starts
+// right after the gray upload and the point results travel back while it is still running.
+int frontend_core(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                  const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px, int32_t B,
+                  int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam, const psl_track_params* prm,
+                  float line_desc_th, const psl_frontend_out* o, const Copy* late_in, int n_in, const Copy* early_out,
+                  int n_out) {
   if (!ctx) return PSL_E_INVALID;
   if (!o || !o->kl || !o->ldesc || !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || o->line_cap < 1 ||
       o->line_cap > kMaxLinesPerFrame)
@@ -153,10 +163,14 @@ int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gr
     PSL_CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
   }
   if (rc) return rc;
+  for (int i = 0; i < n_in; ++i)
+    PSL_CK(cudaMemcpyAsync(late_in[i].dst, late_in[i].src, late_in[i].bytes, cudaMemcpyHostToDevice, main_st));
   rc = psl_track_orb_batch_dev(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px,
                                depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, o->kps, o->desc, o->n, o->u_right, o->z,
                                o->assign, o->nmatches, o->cap);
   if (rc) return rc;
+  for (int i = 0; i < n_out; ++i)
+    PSL_CK(cudaMemcpyAsync(early_out[i].dst, early_out[i].src, early_out[i].bytes, cudaMemcpyDeviceToHost, main_st));
   if (overlap) PSL_CK(cudaStreamWaitEvent(main_st, ctx->ev_join, 0));
   // SearchByGeomNApearance(frame b, frame b-1): the Last set is the same [B][line_cap] block shifted by one frame
   cudaStream_t st = ctx->stream;
@@ -174,6 +188,17 @@ int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gr
   prof_span(ctx, 15, e, 2);
   PSL_CK(cudaGetLastError());
   return PSL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                                 const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                                 int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                                 const psl_track_params* prm, float line_desc_th, const psl_frontend_out* o) {
+  return frontend_core(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px, depth_frame_stride_px, B, w,
+                       h, d_Tcw, cam, prm, line_desc_th, o, nullptr, 0, nullptr, 0);
 }
 
 int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
@@ -204,24 +229,19 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
   if ((rc = ensure(ctx, ctx->l_n, nl * 4))) return rc;  // line_assign
   cudaStream_t st = ctx->stream;
   PSL_CK(cudaMemcpyAsync(M[0].p, gray, px * B, cudaMemcpyHostToDevice, st));
-  PSL_CK(cudaMemcpyAsync(M[1].p, depth, px * B * 2, cudaMemcpyHostToDevice, st));
-  PSL_CK(cudaMemcpyAsync(M[2].p, Tcw, (size_t)B * 48, cudaMemcpyHostToDevice, st));
+  const Copy late_in[2] = {{M[1].p, depth, px * B * 2}, {M[2].p, Tcw, (size_t)B * 48}};
   int32_t* d_n = M[5].as<int32_t>();
   psl_frontend_out d = *o;
   d.kps = M[3].as<psl_keypoint>(); d.desc = M[4].as<uint8_t>(); d.n = d_n; d.nmatches = d_n + B;
   d.u_right = M[6].as<float>(); d.z = M[7].as<float>(); d.assign = M[8].as<int32_t>();
   d.kl = ctx->l_kl.as<psl_keyline>(); d.ldesc = ctx->l_desc.as<uint8_t>(); d.lineeq = ctx->l_eq.as<double>();
   d.nl = d_n + 2 * B; d.line_nmatches = d_n + 3 * B; d.line_assign = ctx->l_n.as<int32_t>();
-  rc = psl_track_frontend_batch_dev(ctx, M[0].as<uint8_t>(), w, (int64_t)px, M[1].as<uint16_t>(), w, (int64_t)px, B, w, h,
-                                    M[2].as<float>(), cam, prm, line_desc_th, &d);
+  const Copy early_out[7] = {{o->kps, d.kps, nk * sizeof(psl_keypoint)}, {o->desc, d.desc, nk * 32},
+                             {o->n, d.n, (size_t)B * 4},  {o->nmatches, d.nmatches, (size_t)B * 4},
+                             {o->u_right, d.u_right, nk * 4}, {o->z, d.z, nk * 4}, {o->assign, d.assign, nk * 4}};
+  rc = frontend_core(ctx, M[0].as<uint8_t>(), w, (int64_t)px, M[1].as<uint16_t>(), w, (int64_t)px, B, w, h,
+                     M[2].as<float>(), cam, prm, line_desc_th, &d, late_in, 2, early_out, 7);
   if (rc) return rc;
-  PSL_CK(cudaMemcpyAsync(o->kps, d.kps, nk * sizeof(psl_keypoint), cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(o->desc, d.desc, nk * 32, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(o->n, d.n, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(o->nmatches, d.nmatches, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(o->u_right, d.u_right, nk * 4, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(o->z, d.z, nk * 4, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(o->assign, d.assign, nk * 4, cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(o->kl, d.kl, nl * sizeof(psl_keyline), cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(o->ldesc, d.ldesc, nl * 32, cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(o->lineeq, d.lineeq, nl * 24, cudaMemcpyDeviceToHost, st));

@@ -38,6 +38,17 @@ def main():
         tot = float(ms[10:15].sum())
         print(f"rep {r}: total {tot:.1f} ms  {a.frames / tot * 1e3:.0f} frames/s  prologue={ms[10]:.2f} order={ms[11]:.2f} "
               f"core={ms[12]:.2f} post={ms[13]:.2f} lbd={ms[14]:.2f}  lines/frame={n.float().mean().item():.1f}", flush=True)
+        _stats()
+
+
+def _stats():
+    import ctypes as C
+    from psl_slam_b200 import _lib
+    L = _lib.lib()
+    if hasattr(L, "psl_lsd_stats"):
+        z = (C.c_ulonglong * 16)()
+        L.psl_lsd_stats(z)
+        print("lsd stats [0 steps, 1 cyc guess, 2 cyc verify, 3 cyc accept, 4 cyc sync, 5 cyc seq, 6 -, 7 nseq | cyc: 8 load, 9 decide, 10 grow, 11 rect, 12 refine, 13 regions, 14 total]:", list(z)[:15])
 
 
 if __name__ == "__main__":
