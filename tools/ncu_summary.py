@@ -2,6 +2,7 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches_r01.csv profiles/r01_launches.md
     python tools/ncu_summary.py kernel   gpurun_out/prof_fast_r01.ncu-rep profiles/r01_fast_cells_ncu.md
+    python tools/ncu_summary.py kernels  gpurun_out/prof_line_r01.ncu-rep profiles/r01_line_kernels_ncu.md
 """
 import collections
 import csv
@@ -55,5 +56,27 @@ def kernel(src, dst):
                 f.write(f"| {k} | {units[i]} | " + " | ".join(d[i] for d in data) + " |\n")
 
 
+def kernels(src, dst):
+    """One column per distinct kernel of the report (its last captured launch)."""
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    name_i = hdr.index("Kernel Name")
+    last = {}
+    for d in data:
+        last[re.sub(r"\(.*", "", d[name_i]).split("::")[-1]] = d
+    names = list(last)
+    extra = ["lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+             "smsp__thread_inst_executed_per_inst_executed.ratio"]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none: {src}\n\n")
+        f.write("| metric | unit | " + " | ".join(f"`{n}`" for n in names) + " |\n")
+        f.write("|---|---|" + "---:|" * len(names) + "\n")
+        for k in KEYS + extra:
+            if k in hdr:
+                i = hdr.index(k)
+                f.write(f"| {k} | {units[i]} | " + " | ".join(last[n][i] for n in names) + " |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "kernels": kernels}[sys.argv[1]](sys.argv[2], sys.argv[3])
