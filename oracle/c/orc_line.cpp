@@ -409,11 +409,12 @@ int orc_line_extract(const uint8_t* gray, int w, int h, int stride, int nfeature
                      double* lineeq, float* lbd72, int cap, int* n_out) {
   *n_out = 0;
   if (w <= 0 || h <= 0) return 0;
-  std::vector<float> raw(4 * 8192), merged(4 * 8192);
-  int nr = orc_lsd_detect(gray, w, h, stride, 1, raw.data(), 8192);
-  if (nr > 8192) return PSL_E_CAPACITY;
+  const int kCap = 65536;
+  std::vector<float> raw(4 * (size_t)kCap), merged(4 * (size_t)kCap);
+  int nr = orc_lsd_detect(gray, w, h, stride, 1, raw.data(), kCap);
+  if (nr > kCap) return PSL_E_CAPACITY;
   orc_clamp_segments(raw.data(), nr, w, h);
-  int nm = orc_merge_lines_lsd(raw.data(), nr, merged.data(), 8192);
+  int nm = orc_merge_lines_lsd(raw.data(), nr, merged.data(), kCap);
   std::vector<psl_keyline> k(std::max(nm, 1));
   int n = orc_make_keylines(merged.data(), nm, w, h, nfeatures, k.data());
   if (n > cap) return PSL_E_CAPACITY;

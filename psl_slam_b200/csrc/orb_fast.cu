@@ -103,77 +103,86 @@ __global__ void __launch_bounds__(kFastThreads)
   if (tid == 0) s_nlist = 0;
   __syncthreads();
 
-  // ---- A: compass reject.  Any 9-arc contains one pixel of each antipodal pair, so a corner needs
-  // (p0 or p8) and (p4 or p12) outside [v-t, v+t].  Compared on pixel values, never on differences
-  // (nvcc 12.9 mis-packs min/max/abs of u8 differences for sm_100a).
-  const int t_lo = min(ini_th, min_th);
-  for (int i = tid; i < npx; i += kFastThreads) {
-    const int y = PSL_DIV(i, rcp_iw), x = i - y * iw;
-    const uint8_t* c = &s_tile[y + 3][x + 3 + ax];
-    const int v = *c, hi = v + t_lo, lo = v - t_lo;
-    const int q0 = c[3 * kTilePitch], q8 = c[-3 * kTilePitch];
-    if (q0 >= lo && q0 <= hi && q8 >= lo && q8 <= hi) continue;
-    const int q4 = c[3], q12 = c[-3];
-    if (q4 >= lo && q4 <= hi && q12 >= lo && q12 <= hi) continue;
-    s_list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
-  }
-  __syncthreads();
-
-  // ---- B: exact scores, two survivors per thread on u16x2 lanes -----------------------------------
-  const int nlist = s_nlist;
-  for (int k = 2 * tid; k < nlist; k += 2 * kFastThreads) {
-    const int ia = s_list[k], ib = s_list[min(k + 1, nlist - 1)];
-    const int ya = PSL_DIV(ia, rcp_iw), xa = ia - ya * iw;
-    const int yb = PSL_DIV(ib, rcp_iw), xb = ib - yb * iw;
-    const unsigned sc = fast_score_pair<kTilePitch>(&s_tile[ya + 3][xa + 3 + ax], &s_tile[yb + 3][xb + 3 + ax]);
-    const unsigned sa = sc & 0xFFFFu, sb = sc >> 16;
-    s_score[ya + 1][xa + 1] = (uint8_t)(sa >= (unsigned)t_lo ? sa : 0u);
-    s_score[yb + 1][xb + 1] = (uint8_t)(sb >= (unsigned)t_lo ? sb : 0u);
-  }
-  __syncthreads();
-
-  // ---- C: NMS over the survivors, two keep-bitmaps ----------------------------------------------------
-  for (int k = tid; k < nlist; k += kFastThreads) {
-    const int i = s_list[k];
-    const int y = PSL_DIV(i, rcp_iw), x = i - y * iw;
-    const unsigned s = s_score[y + 1][x + 1];
-    if (!s) continue;
-    const uint8_t* r0 = &s_score[y][x];
-    const uint8_t* r1 = &s_score[y + 1][x];
-    const uint8_t* r2 = &s_score[y + 2][x];
-    const unsigned m = max(max(max((unsigned)r0[0], (unsigned)r0[1]), max((unsigned)r0[2], (unsigned)r1[0])),
-                           max(max((unsigned)r1[2], (unsigned)r2[0]), max((unsigned)r2[1], (unsigned)r2[2])));
-    if (s > m) {
-      if (s >= (unsigned)ini_th) atomicOr(&s_keep[0][i >> 5], 1u << (i & 31));
-      if (s >= (unsigned)min_th) atomicOr(&s_keep[1][i >> 5], 1u << (i & 31));
-    }
-  }
-  __syncthreads();
-
-  // ---- D: threshold fallback + raster-ordered compaction (thread t owns bitmap word t) -----------
-  const int nwords = (npx + 31) >> 5;
-  const uint32_t w_ini = tid < nwords ? s_keep[0][tid] : 0u, w_lo = tid < nwords ? s_keep[1][tid] : 0u;
+  // The exact scores are the expensive part and only the pixels that pass the compass test need one.  At
+  // iniThFAST far fewer pixels pass than at minThFAST, and a textured cell almost always has a corner at
+  // iniThFAST, so the cell is first done at iniThFAST alone; only a cell that comes out empty is redone at
+  // minThFAST (:812-816).  Scores and the NMS verdict do not depend on the threshold (see the header), so the
+  // second pass simply extends the first.
   const int lane = tid & 31, wid = tid >> 5;
-  const int c_ini = __popc(w_ini), c_lo = __popc(w_lo);
-  int i_ini = c_ini, i_lo = c_lo;
+  const int nwords = (npx + 31) >> 5;
+  uint32_t keep = 0;
+  int total = 0, pos = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int t_cur = pass == 0 ? ini_th : min_th;
+    if (pass == 1) {
+      if (min_th >= ini_th) break;  // nothing new can appear
+      if (tid == 0) s_nlist = 0;
+      __syncthreads();
+    }
+    // ---- A: compass reject.  Any 9-arc contains one pixel of each antipodal pair, so a corner needs
+    // (p0 or p8) and (p4 or p12) outside [v-t, v+t].  Compared on pixel values, never on differences
+    // (nvcc 12.9 mis-packs min/max/abs of u8 differences for sm_100a).
+    for (int i = tid; i < npx; i += kFastThreads) {
+      const int y = PSL_DIV(i, rcp_iw), x = i - y * iw;
+      const uint8_t* c = &s_tile[y + 3][x + 3 + ax];
+      const int v = *c, hi = v + t_cur, lo = v - t_cur;
+      const int q0 = c[3 * kTilePitch], q8 = c[-3 * kTilePitch];
+      if (q0 >= lo && q0 <= hi && q8 >= lo && q8 <= hi) continue;
+      const int q4 = c[3], q12 = c[-3];
+      if (q4 >= lo && q4 <= hi && q12 >= lo && q12 <= hi) continue;
+      s_list[atomicAdd(&s_nlist, 1)] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // ---- B: exact scores, two survivors per thread on u16x2 lanes ---------------------------------
+    const int nlist = s_nlist;
+    for (int k = 2 * tid; k < nlist; k += 2 * kFastThreads) {
+      const int ia = s_list[k], ib = s_list[min(k + 1, nlist - 1)];
+      const int ya = PSL_DIV(ia, rcp_iw), xa = ia - ya * iw;
+      const int yb = PSL_DIV(ib, rcp_iw), xb = ib - yb * iw;
+      const unsigned sc = fast_score_pair<kTilePitch>(&s_tile[ya + 3][xa + 3 + ax], &s_tile[yb + 3][xb + 3 + ax]);
+      const unsigned sa = sc & 0xFFFFu, sb = sc >> 16;
+      s_score[ya + 1][xa + 1] = (uint8_t)(sa >= (unsigned)t_cur ? sa : 0u);
+      s_score[yb + 1][xb + 1] = (uint8_t)(sb >= (unsigned)t_cur ? sb : 0u);
+    }
+    __syncthreads();
+
+    // ---- C: NMS over the survivors -> keep-bitmap ---------------------------------------------------
+    for (int k = tid; k < nlist; k += kFastThreads) {
+      const int i = s_list[k];
+      const int y = PSL_DIV(i, rcp_iw), x = i - y * iw;
+      const unsigned sc = s_score[y + 1][x + 1];
+      if (!sc) continue;
+      const uint8_t* r0 = &s_score[y][x];
+      const uint8_t* r1 = &s_score[y + 1][x];
+      const uint8_t* r2 = &s_score[y + 2][x];
+      const unsigned m = max(max(max((unsigned)r0[0], (unsigned)r0[1]), max((unsigned)r0[2], (unsigned)r1[0])),
+                             max(max((unsigned)r1[2], (unsigned)r2[0]), max((unsigned)r2[1], (unsigned)r2[2])));
+      if (sc > m) atomicOr(&s_keep[0][i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+
+    // ---- D: count + raster-ordered positions (thread t owns bitmap word t) -----------------------
+    keep = tid < nwords ? s_keep[0][tid] : 0u;
+    const int cnt = __popc(keep);
+    int inc = cnt;
 #pragma unroll
-  for (int dlt = 1; dlt < 32; dlt <<= 1) {
-    const int a = __shfl_up_sync(0xffffffffu, i_ini, dlt), bb = __shfl_up_sync(0xffffffffu, i_lo, dlt);
-    if (lane >= dlt) { i_ini += a; i_lo += bb; }
-  }
-  if (lane == 31) { s_warp[0][wid] = i_ini; s_warp[1][wid] = i_lo; }
-  __syncthreads();
-  int base_ini = 0, base_lo = 0, tot_ini = 0, tot_lo = 0;
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, inc, dlt);
+      if (lane >= dlt) inc += a;
+    }
+    if (lane == 31) s_warp[pass][wid] = inc;
+    __syncthreads();
+    int base_w = 0;
+    total = 0;
 #pragma unroll
-  for (int w = 0; w < kFastThreads / 32; ++w) {
-    if (w < wid) { base_ini += s_warp[0][w]; base_lo += s_warp[1][w]; }
-    tot_ini += s_warp[0][w];
-    tot_lo += s_warp[1][w];
+    for (int w = 0; w < kFastThreads / 32; ++w) {
+      if (w < wid) base_w += s_warp[pass][w];
+      total += s_warp[pass][w];
+    }
+    pos = base_w + inc - cnt;
+    if (total > 0) break;  // :812-816 retry with minThFAST only when the cell is empty
   }
-  const bool use_ini = tot_ini > 0;  // :812-816 retry with minThFAST only when the cell is empty
-  const int total = use_ini ? tot_ini : tot_lo;
-  uint32_t keep = use_ini ? w_ini : w_lo;
-  int pos = use_ini ? base_ini + i_ini - c_ini : base_lo + i_lo - c_lo;
   if (tid == 0) {
     uint32_t base = 0;
     if (total) base = atomicAdd(pool_count + b, (uint32_t)total);
