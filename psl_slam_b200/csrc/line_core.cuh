@@ -52,6 +52,7 @@ struct MergeScratch {
   uint16_t* loc;     // [cap] position inside the sorted cluster
   uint8_t* flag;     // [cap] frontier bitmap / `clustered`
   int overflow;      // set when a neighbour list overflows
+  float* sangles;    // [cap] angles in scan order (warp-cooperative kernel only)
 };
 
 PSL_LN_HD float point_line_distance(const Seg& l, float x0, float y0) {  // uselongline.cpp:5-15

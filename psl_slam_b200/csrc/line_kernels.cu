@@ -20,6 +20,21 @@ namespace psl {
 //     fp64-heavy folds (:231-262) run one sub-cluster per lane;
 //   * stable index sorts are rank computations (position = number of elements that sort before).
 // ---------------------------------------------------------------------------------------------------
+#ifdef PSL_LSD_STATS
+__device__ unsigned long long g_post_stats[16];
+#define POST_T0(t) long long t = clock64()
+#define POST_T1(i, t) do { const unsigned long long v__ = (unsigned long long)(clock64() - t); if (lane == 0) atomicAdd(&g_post_stats[i], v__); } while (0)
+extern "C" void psl_post_stats(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_post_stats, sizeof(g_post_stats));
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_post_stats, z, sizeof(z));
+}
+#else
+#define POST_T0(t) do { } while (0)
+#define POST_T1(i, t) do { } while (0)
+#endif
+
 namespace linew {
 
 using line::kNbCap;
@@ -45,6 +60,7 @@ __device__ void rank_sort(const uint16_t* idx, uint16_t* out, int n, const float
 __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, float distance_thr, float endpoint_threshold,
                            MergeScratch& S, int lane) {
   if (n <= 0) return 0;
+  POST_T0(t_sort);
   for (int i = lane; i < n; i += 32) {
     const float dx = __fsub_rn(src[i].v[2], src[i].v[0]), dy = __fsub_rn(src[i].v[3], src[i].v[1]);
     S.angles[i] = (float)atan((double)__fdiv_rn(dy, dx));
@@ -55,13 +71,24 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   }
   __syncwarp();
   rank_sort(S.tmp16, S.order, n, S.angles, false, lane);
+  // segments and angles in scan order, so that the pair scan reads them with plain coalesced loads instead of a
+  // chain of dependent gathers (dst is free until the folds at the end)
+  Seg* sseg = dst;
+  for (int j = lane; j < n; j += 32) {
+    const int id = S.order[j];
+    sseg[j] = src[id];
+    S.sangles[j] = S.angles[id];
+  }
+  __syncwarp();
+  POST_T1(0, t_sort);
+  POST_T0(t_scan);
   const float ep_thr = __fmul_rn(endpoint_threshold, endpoint_threshold);
   const float quater_PI = (float)(line::kPi / 4.0);
   for (int i = 0; i < n; ++i) {
     const int idx1 = S.order[i];
-    const Seg s1 = src[idx1];
+    const Seg s1 = sseg[i];
     float x11 = s1.v[0], y11 = s1.v[1], x12 = s1.v[2], y12 = s1.v[3];
-    const float angle1 = S.angles[idx1];
+    const float angle1 = S.sangles[i];
     const bool sx = fabsf(angle1) < quater_PI;
     if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
     const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
@@ -72,11 +99,10 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
       bool far = false, to_merge = false;
       int idx2 = 0;
       if (j < n) {
-        idx2 = S.order[j];
-        const Seg s2 = src[idx2];
+        const Seg s2 = sseg[j];
         float x21 = s2.v[0], y21 = s2.v[1], x22 = s2.v[2], y22 = s2.v[3];
         if ((sx && (x22 < x21)) || ((!sx) && y22 < y21)) { float t = x21; x21 = x22; x22 = t; t = y21; y21 = y22; y22 = t; }
-        far = line::angle_diff(angle1, S.angles[idx2]) > angle_thr;
+        far = line::angle_diff(angle1, S.sangles[j]) > angle_thr;
         if (!far) {
           const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
           if (!(line::point_line_distance(s2, mx1, my1) > distance_thr && line::point_line_distance(s1, mx2, my2) > distance_thr)) {
@@ -96,6 +122,7 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
       const unsigned live = brk ? ((1u << (__ffs(brk) - 1)) - 1u) : kFull;
       const unsigned mm = __ballot_sync(kFull, to_merge) & live;
       if (mm >> lane & 1u) {
+        idx2 = S.order[j];
         const int pos = cnt1 + __popc(mm & ((1u << lane) - 1u));
         const int c2 = S.nb_cnt[idx2];
         if (pos < kNbCap && c2 < kNbCap) {
@@ -109,11 +136,27 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
       cnt1 = min(cnt1 + __popc(mm), kNbCap);
       __syncwarp();
       if (brk) break;
+      if (!can_break && __any_sync(kFull, far)) {
+        // A near-vertical segment `continue`s past partners whose angle gap is too large instead of stopping.
+        // In the angle-sorted order those form one contiguous run: |a2 - a1| grows with j, pi + a1 - a2 (the
+        // wrap-around branch of AngleDiff) shrinks, so only the partners right after i and the ones at the far
+        // end of the list (the other vertical direction) can pass.  Skip the run: first j past this batch whose
+        // gap is small again, found by bisection on the same fp32 predicate.
+        int lo = min(j0 + 32, n), hi = n;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (line::angle_diff(angle1, S.sangles[mid]) > angle_thr) lo = mid + 1;
+          else hi = mid;
+        }
+        j0 = lo - 32;  // the loop increment brings it to lo
+      }
     }
     if (lane == 0) S.nb_cnt[idx1] = (uint16_t)cnt1;
     __syncwarp();
   }
   S.overflow = __any_sync(kFull, S.overflow) ? 1 : 0;
+  POST_T1(1, t_scan);
+  POST_T0(t_bfs);
   // connected components (:153-190) and sub-clusters (:193-229): heads of the output lines, in output order
   uint16_t* heads = S.order;  // the angle order is no longer needed
   int nd = 0;
@@ -159,6 +202,8 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   }
   nd = __shfl_sync(kFull, nd, 0);
   __syncwarp();
+  POST_T1(2, t_bfs);
+  POST_T0(t_fold);
   for (int o = lane; o < nd; o += 32) {  // folded MergeTwoLines (:243-255), one sub-cluster per lane
     const int li = heads[o];
     Seg nl = line::merge_two(src[li], src[li]);
@@ -166,6 +211,7 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
     dst[o] = nl;
   }
   __syncwarp();
+  POST_T1(3, t_fold);
   return nd;
 }
 
@@ -238,10 +284,12 @@ __global__ void __launch_bounds__(kPostWarps * 32)
   if (b >= nb) return;
   const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
   line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
-                       L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0};
+                       L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o};
   line::Seg* raw = reinterpret_cast<line::Seg*>(L.raw) + o;
+  POST_T0(t_all);
   const int n = linew::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,
                                    lineeq + (size_t)b * cap * 3, cap, lane);
+  POST_T1(4, t_all);
   if (lane == 0) {
     if (S.overflow) atomicOr(status, kStatLineNeighbours);
     if (n < 0) atomicOr(status, kStatOutOverflow);

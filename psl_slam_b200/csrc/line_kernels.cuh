@@ -34,6 +34,7 @@ struct LineBuffers {
   line::Seg* t2;       // [C][raw_cap]
   float* m_angles;     // merge scratch, [C][raw_cap] each
   float* m_length;
+  float* m_sangles;
   uint16_t* m_order;
   uint16_t* m_tmp16;
   uint16_t* m_nb;      // [C][raw_cap][kNbCap]

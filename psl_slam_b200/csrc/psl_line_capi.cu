@@ -72,7 +72,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
             lalloc(ctx, L.key_out, C * npx) && lalloc(ctx, L.val_in, C * npx) && lalloc(ctx, L.val_out, C * npx) &&
             lalloc(ctx, L.seg_begin, C) && lalloc(ctx, L.seg_end, C) && lalloc(ctx, tmp, L.sort_tmp_bytes) &&
             lalloc(ctx, L.raw, C * R * 4) && lalloc(ctx, L.n_raw, C) && lalloc(ctx, L.t1, C * R) &&
-            lalloc(ctx, L.t2, C * R) && lalloc(ctx, L.m_angles, C * R) && lalloc(ctx, L.m_length, C * R) &&
+            lalloc(ctx, L.t2, C * R) && lalloc(ctx, L.m_angles, C * R) && lalloc(ctx, L.m_length, C * R) && lalloc(ctx, L.m_sangles, C * R) &&
             lalloc(ctx, L.m_order, C * R) && lalloc(ctx, L.m_tmp16, C * R) &&
             lalloc(ctx, L.m_nb, C * R * line::kNbCap) && lalloc(ctx, L.m_nb_cnt, C * R) &&
             lalloc(ctx, L.m_code, C * R) && lalloc(ctx, L.m_check, C * R) && lalloc(ctx, L.m_loc, C * R) &&

@@ -15,7 +15,7 @@ extern "C" int emu_frame_lines(const float* raw4, int n_raw, int w, int h, int n
   std::vector<int16_t> code(cap);
   std::vector<uint8_t> flag(cap, 0);
   MergeScratch S{cap, angles.data(), length.data(), order.data(), tmp16.data(), nb.data(), nb_cnt.data(), code.data(),
-                 check.data(), loc.data(), flag.data(), 0};
+                 check.data(), loc.data(), flag.data(), 0, nullptr};
   int n = frame_lines(raw.data(), n_raw, t1.data(), t2.data(), w, h, nfeatures, S, kl, eq, kl_cap);
   *overflow = S.overflow;
   return n;
