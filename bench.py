@@ -339,8 +339,16 @@ def main():
                        "achieved_gbs": gbs, "frac": gbs / peak})
     dom = max(stages, key=lambda s: s["ms_per_step"])
     nl = max(dom["launches_per_step"], 1)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom["stage"])
+        if tj and tj.get("dram_bytes_per_frame"):
+            traffic = tj["dram_bytes_per_frame"] * F / nl
+            traffic_src = f'{tj["kernel"]}: {tj["source"]}'
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom["stage"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom["alg_bytes_per_frame"] * F / nl,
                 "avg_launch_ms": dom["ms_per_step"] / nl,
                 "note": "achieved = algorithmic bytes of the stage x frames / CUDA-event time of the stage"}

@@ -331,19 +331,49 @@ __device__ __forceinline__ int reflect101_1(int i, int n) {  // one reflection i
   return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);
 }
 
-// cv::Sobel(CV_16SC1, 3x3, BORDER_REFLECT_101) of the blurred image, dx and dy interleaved (:374-399)
-__global__ void __launch_bounds__(256)
+// cv::Sobel(CV_16SC1, 3x3, BORDER_REFLECT_101) of the blurred image, dx and dy interleaved (:374-399).
+// A thread owns 4 adjacent pixels: three aligned words per row (left, own, right) give the 6 bytes it needs,
+// and the four (dx, dy) pairs leave as one 16-byte store.  Threads on the left / right image edge take the
+// per-pixel path with the reflected column.
+__device__ __forceinline__ void sobel_px(const uint8_t* r0, const uint8_t* r1, const uint8_t* r2, int x, int w, short2* out) {
+  const int xm = reflect101_1(x - 1, w), xp = reflect101_1(x + 1, w);
+  const int dx = ((int)r0[xp] - (int)r0[xm]) + 2 * ((int)r1[xp] - (int)r1[xm]) + ((int)r2[xp] - (int)r2[xm]);
+  const int dy = ((int)r2[xm] + 2 * (int)r2[x] + (int)r2[xp]) - ((int)r0[xm] + 2 * (int)r0[x] + (int)r0[xp]);
+  *out = make_short2((short)dx, (short)dy);
+}
+
+__global__ void __launch_bounds__(128)
     sobel_kernel(const uint8_t* __restrict__ img, int pitch, int64_t fs, int w, int h, short2* __restrict__ gxy) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, b = blockIdx.z;
   if (x >= w) return;
   const uint8_t* base = img + (size_t)b * fs;
   const uint8_t* r0 = base + (size_t)reflect101_1(y - 1, h) * pitch;
   const uint8_t* r1 = base + (size_t)y * pitch;
   const uint8_t* r2 = base + (size_t)reflect101_1(y + 1, h) * pitch;
-  const int xm = reflect101_1(x - 1, w), xp = reflect101_1(x + 1, w);
-  const int dx = ((int)r0[xp] - (int)r0[xm]) + 2 * ((int)r1[xp] - (int)r1[xm]) + ((int)r2[xp] - (int)r2[xm]);
-  const int dy = ((int)r2[xm] + 2 * (int)r2[x] + (int)r2[xp]) - ((int)r0[xm] + 2 * (int)r0[x] + (int)r0[xp]);
-  gxy[((size_t)b * h + y) * w + x] = make_short2((short)dx, (short)dy);
+  short2* out = gxy + ((size_t)b * h + y) * w + x;
+  if (x == 0 || x + 4 >= w || (w & 3)) {
+    for (int k = 0; k < 4 && x + k < w; ++k) sobel_px(r0, r1, r2, x + k, w, out + k);
+    return;
+  }
+  // bytes x-1 .. x+4 of each row
+  unsigned p[3][6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const uint8_t* row = r == 0 ? r0 : (r == 1 ? r1 : r2);
+    const unsigned wl = *reinterpret_cast<const unsigned*>(row + x - 4), wc = *reinterpret_cast<const unsigned*>(row + x),
+                   wr = *reinterpret_cast<const unsigned*>(row + x + 4);
+    p[r][0] = wl >> 24;
+    p[r][1] = wc & 0xFFu; p[r][2] = (wc >> 8) & 0xFFu; p[r][3] = (wc >> 16) & 0xFFu; p[r][4] = wc >> 24;
+    p[r][5] = wr & 0xFFu;
+  }
+  short2 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dx = ((int)p[0][k + 2] - (int)p[0][k]) + 2 * ((int)p[1][k + 2] - (int)p[1][k]) + ((int)p[2][k + 2] - (int)p[2][k]);
+    const int dy = ((int)p[2][k] + 2 * (int)p[2][k + 1] + (int)p[2][k + 2]) - ((int)p[0][k] + 2 * (int)p[0][k + 1] + (int)p[0][k + 2]);
+    o[k] = make_short2((short)dx, (short)dy);
+  }
+  *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(o);
 }
 
 // computeLBD for one line (:1074-1330) + binaryConversion (:402-413, :655-668).  Block = one line:
@@ -460,8 +490,8 @@ void launch_lbd(const LineBuffers& L, ImgBatch in, int nb, int nfeatures, const 
                 int cap, uint8_t* ldesc, float* lbd72, cudaStream_t st) {
   ImgBatchMut bl{L.blur, L.pitch, (int64_t)L.pitch * L.h, L.w, L.h};
   launch_blur7(in, bl, 0, 14, 62, 104, nb, st);  // GaussianBlur(5x5, sigma 1), computeGaussianPyramid :351-371
-  dim3 g1((L.w + 255) / 256, L.h, nb);
-  sobel_kernel<<<g1, 256, 0, st>>>(L.blur, L.pitch, (int64_t)L.pitch * L.h, L.w, L.h, L.gxy);
+  dim3 g1(((L.w + 3) / 4 + 127) / 128, L.h, nb);
+  sobel_kernel<<<g1, 128, 0, st>>>(L.blur, L.pitch, (int64_t)L.pitch * L.h, L.w, L.h, L.gxy);
   dim3 g2(nfeatures < cap ? nfeatures : cap, nb);
   lbd_kernel<<<g2, 64, 0, st>>>(L.gxy, L.w, L.h, kl, n_kl, cap, ldesc, lbd72);
 }

@@ -15,6 +15,7 @@ struct LineBuffers {
   const short2* ytab;  // [Hs]
   uint8_t* blur;       // [C][h][pitch]   7x7 sigma 0.75 (LSD) and, later, 5x5 sigma 1 (LBD)
   uint8_t* scaled;     // [C][Hs][Ws]
+  const float4* lut;   // [1021*1021] pixel record of every integer gradient (gx, gy)
   float4* pix;         // [C][Hs*Ws]  (angle in degrees | cos | sin | int bits: squared gradient norm + USED flag)
   uint32_t* reg;       // [C][Hs*Ws]
   int32_t* max_n2;     // [C]
@@ -47,6 +48,8 @@ struct LineBuffers {
 };
 
 size_t lsd_sort_temp_bytes(int items_per_frame, int frames);
+size_t lsd_lut_bytes();
+void launch_lsd_lut(float4* lut, cudaStream_t st);
 
 // LSD for `nb` frames (cv::LineSegmentDetector behind LineExtractor.cpp:336-337), three stages:
 // blur + 0.8x resize + gradient + seed keys (6 launches); stable seed ordering (cub segmented radix sort, counted as 1);

@@ -38,9 +38,35 @@ constexpr int lsdw_kUsed = 0x40000000;    // region membership flag, kept in the
 // neighbour: cos / sin are the fp32 values region_grow adds to its running sums, (float)cos((double)(float)angle)
 // (the reference calls cos(float) -> pinned to fp64 evaluation), computed here in parallel instead
 // of inside the sequential loop.
+// The record of a pixel depends on its integer gradient (gx, gy) only, |gx|, |gy| <= 510: all 1021^2 records are
+// tabulated once per context (16.7 MB, L2-resident) so that the per-frame gradient kernel is a gather instead of
+// fastAtan2 + fp64 cos / sin per pixel.
+constexpr int kLutSide = 1021, kLutOff = 510;
+
+__device__ __forceinline__ float4 lsd_record(int gx, int gy, double rho) {
+  float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, 0.f);
+  const int q = gx * gx + gy * gy;
+  rec.w = __int_as_float(q);
+  if (!(sqrt((double)q / 4.0) <= rho)) {
+    rec.x = lsd::fast_atan2((float)gx, (float)-gy);
+    const double a = (double)(float)((double)rec.x * lsd::kDegToRad);
+    rec.y = (float)cos(a);
+    rec.z = (float)sin(a);
+  }
+  return rec;
+}
+
+__global__ void __launch_bounds__(256) lsd_lut_kernel(float4* __restrict__ lut, double rho) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kLutSide * kLutSide) return;
+  const int gy = i / kLutSide - kLutOff, gx = i - (gy + kLutOff) * kLutSide - kLutOff;
+  lut[i] = lsd_record(gx, gy, rho);
+}
+
 __global__ void __launch_bounds__(128)
-    lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, float4* __restrict__ pix,
-                        int32_t* __restrict__ max_n2, int32_t* __restrict__ row_cnt, double rho) {
+    lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, const float4* __restrict__ lut,
+                        float4* __restrict__ pix, int32_t* __restrict__ max_n2, int32_t* __restrict__ row_cnt,
+                        int q_undef) {
   const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
   if (y >= Hs) return;
   const uint8_t* r0 = scaled + ((size_t)b * Hs + y) * Ws;
@@ -54,11 +80,8 @@ __global__ void __launch_bounds__(128)
       const int gx = DA + BC, gy = DA - BC;
       const int q = gx * gx + gy * gy;
       rec.w = __int_as_float(q);
-      if (!(sqrt((double)q / 4.0) <= rho)) {
-        rec.x = lsd::fast_atan2((float)gx, (float)-gy);
-        const double a = (double)(float)((double)rec.x * lsd::kDegToRad);
-        rec.y = (float)cos(a);
-        rec.z = (float)sin(a);
+      if (q > q_undef) {  // sqrt(q / 4) > rho  <=>  q > q_undef (largest q with sqrt(q / 4.0) <= rho, found on the host)
+        rec = __ldg(lut + (gy + kLutOff) * kLutSide + (gx + kLutOff));
         ++cnt;
         mx = max(mx, q);
       }
@@ -75,6 +98,12 @@ __global__ void __launch_bounds__(128)
     if (mx >= 0) atomicMax(max_n2 + b, mx);
   }
 }
+
+void launch_lsd_lut(float4* lut, cudaStream_t st) {
+  const double rho = 2.0 / sin(lsd::kPi * lsd::kAngTh / 180);
+  lsd_lut_kernel<<<(kLutSide * kLutSide + 255) / 256, 256, 0, st>>>(lut, rho);
+}
+size_t lsd_lut_bytes() { return (size_t)kLutSide * kLutSide * sizeof(float4); }
 
 // exclusive scan of the per-row counts of every frame (one warp per frame)
 __global__ void __launch_bounds__(32)
@@ -653,9 +682,12 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
                                               L.ytab);
   }
   cudaMemsetAsync(L.max_n2, 0xFF, (size_t)nb * sizeof(int32_t), st);  // -1
+  // largest q = gx^2 + gy^2 whose modulus sqrt(q / 4.0) is still <= rho (the same fp64 comparison as ll_angle)
   const double rho = 2.0 / sin(lsd::kPi * lsd::kAngTh / 180);
+  int q_undef = 0;
+  while (sqrt((double)(q_undef + 1) / 4.0) <= rho) ++q_undef;
   dim3 rows((L.Hs + 3) / 4, nb);
-  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.pix, L.max_n2, L.row_cnt, rho);
+  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.lut, L.pix, L.max_n2, L.row_cnt, q_undef);
   lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, npx, L.n_def, L.seg_begin, L.seg_end);
   lsd_keys_kernel<<<rows, 128, 0, st>>>(L.pix, L.Ws, L.Hs, L.max_n2, L.row_cnt, L.key_in, L.val_in);
 }

@@ -63,9 +63,10 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   exact_axis(w, L.Ws, xt);
   exact_axis(h, L.Hs, yt);
   short2 *dx = nullptr, *dy = nullptr;
+  uint8_t* lut = nullptr;
   L.sort_tmp_bytes = lsd_sort_temp_bytes((int)npx, (int)C);
   uint8_t* tmp = nullptr;
-  bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
+  bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
             lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx) &&
             lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
@@ -82,6 +83,8 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
     return fail(ctx, PSL_E_CUDA, "line buffers: out of device memory (lower psl_config.line_chunk_frames)");
   }
   L.sort_tmp = tmp;
+  L.lut = reinterpret_cast<const float4*>(lut);
+  launch_lsd_lut(reinterpret_cast<float4*>(lut), ctx->stream);
   L.xtab = dx;
   L.ytab = dy;
   PSL_CK(cudaMemcpyAsync(dx, xt.data(), xt.size() * sizeof(short2), cudaMemcpyHostToDevice, ctx->stream));
