@@ -63,31 +63,25 @@ __global__ void __launch_bounds__(256) lsd_lut_kernel(float4* __restrict__ lut, 
   lut[i] = lsd_record(gx, gy, rho);
 }
 
+// pass 1 over the 0.8x image: seed-capable pixels per row and the frame's largest squared gradient
 __global__ void __launch_bounds__(128)
-    lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, const float4* __restrict__ lut,
-                        float4* __restrict__ pix, int32_t* __restrict__ max_n2, int32_t* __restrict__ row_cnt,
-                        int q_undef) {
+    lsd_count_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, int32_t* __restrict__ max_n2,
+                     int32_t* __restrict__ row_cnt, int q_undef) {
   const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
   if (y >= Hs) return;
   const uint8_t* r0 = scaled + ((size_t)b * Hs + y) * Ws;
   const uint8_t* r1 = r0 + Ws;
-  const size_t base = ((size_t)b * Hs + y) * Ws;
   int cnt = 0, mx = -1;
-  for (int x = lane; x < Ws; x += 32) {
-    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(0));
-    if (y < Hs - 1 && x < Ws - 1) {
+  if (y < Hs - 1)
+    for (int x = lane; x < Ws - 1; x += 32) {
       const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
       const int gx = DA + BC, gy = DA - BC;
       const int q = gx * gx + gy * gy;
-      rec.w = __int_as_float(q);
-      if (q > q_undef) {  // sqrt(q / 4) > rho  <=>  q > q_undef (largest q with sqrt(q / 4.0) <= rho, found on the host)
-        rec = __ldg(lut + (gy + kLutOff) * kLutSide + (gx + kLutOff));
+      if (q > q_undef) {
         ++cnt;
         mx = max(mx, q);
       }
     }
-    pix[base + x] = rec;
-  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -96,6 +90,48 @@ __global__ void __launch_bounds__(128)
   if (lane == 0) {
     row_cnt[(size_t)b * Hs + y] = cnt;
     if (mx >= 0) atomicMax(max_n2 + b, mx);
+  }
+}
+
+// pass 2: the pixel records (a gather from the table) and, with the row offsets and the frame maximum known, the
+// (bin, pixel) pairs of the seed-capable pixels in raster order (ordered compaction, one warp per row)
+__global__ void __launch_bounds__(128)
+    lsd_gradient_kernel(const uint8_t* __restrict__ scaled, int Ws, int Hs, const float4* __restrict__ lut,
+                        float4* __restrict__ pix, const int32_t* __restrict__ max_n2,
+                        const int32_t* __restrict__ row_off, uint16_t* __restrict__ key, uint32_t* __restrict__ val,
+                        int q_undef) {
+  const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
+  if (y >= Hs) return;
+  const uint8_t* r0 = scaled + ((size_t)b * Hs + y) * Ws;
+  const uint8_t* r1 = r0 + Ws;
+  const size_t npx = (size_t)Ws * Hs, base = (size_t)b * npx + (size_t)y * Ws;
+  const int m = max_n2[b];
+  const double max_grad = m >= 0 ? sqrt((double)m / 4.0) : -1.0;
+  const double bin_coef = max_grad > 0 ? 1023.0 / max_grad : 0.0;
+  int pos = row_off[(size_t)b * Hs + y];
+  for (int x0 = 0; x0 < Ws; x0 += 32) {
+    const int x = x0 + lane;
+    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(0));
+    bool def = false;
+    int q = 0;
+    if (y < Hs - 1 && x < Ws - 1) {
+      const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
+      const int gx = DA + BC, gy = DA - BC;
+      q = gx * gx + gy * gy;
+      rec.w = __int_as_float(q);
+      if (q > q_undef) {  // sqrt(q / 4) > rho  <=>  q > q_undef (largest q with sqrt(q / 4.0) <= rho, found on the host)
+        rec = __ldg(lut + (gy + kLutOff) * kLutSide + (gx + kLutOff));
+        def = true;
+      }
+    }
+    if (x < Ws) pix[base + x] = rec;
+    const unsigned bal = __ballot_sync(0xffffffffu, def);
+    if (def) {
+      const int p = pos + __popc(bal & ((1u << lane) - 1u));
+      key[(size_t)b * npx + p] = (uint16_t)(int)(sqrt((double)q / 4.0) * bin_coef);
+      val[(size_t)b * npx + p] = (uint32_t)(y * Ws + x);
+    }
+    pos += __popc(bal);
   }
 }
 
@@ -127,32 +163,6 @@ __global__ void __launch_bounds__(32)
     n_def[b] = carry;
     seg_begin[b] = b * npx;
     seg_end[b] = b * npx + carry;
-  }
-}
-
-// (bin, pixel) pairs of the seed-capable pixels in raster order (ordered compaction, one warp per row)
-__global__ void __launch_bounds__(128)
-    lsd_keys_kernel(const float4* __restrict__ pix, int Ws, int Hs, const int32_t* __restrict__ max_n2,
-                    const int32_t* __restrict__ row_off, uint16_t* __restrict__ key, uint32_t* __restrict__ val) {
-  const int lane = threadIdx.x & 31, y = blockIdx.x * 4 + (threadIdx.x >> 5), b = blockIdx.y;
-  if (y >= Hs - 1) return;
-  const size_t npx = (size_t)Ws * Hs, base = (size_t)b * npx + (size_t)y * Ws;
-  const int m = max_n2[b];
-  const double max_grad = m >= 0 ? sqrt((double)m / 4.0) : -1.0;
-  const double bin_coef = max_grad > 0 ? 1023.0 / max_grad : 0.0;
-  int pos = row_off[(size_t)b * Hs + y];
-  for (int x0 = 0; x0 < Ws - 1; x0 += 32) {
-    const int x = x0 + lane;
-    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, 0.f);
-    if (x < Ws - 1) rec = pix[base + x];
-    const bool def = rec.x != lsd::kNotDefDeg;
-    const unsigned bal = __ballot_sync(0xffffffffu, def);
-    if (def) {
-      const int p = pos + __popc(bal & ((1u << lane) - 1u));
-      key[(size_t)b * npx + p] = (uint16_t)(int)(sqrt((double)(__float_as_int(rec.w) & lsdw_kN2Mask) / 4.0) * bin_coef);
-      val[(size_t)b * npx + p] = (uint32_t)(y * Ws + x);
-    }
-    pos += __popc(bal);
   }
 }
 
@@ -687,9 +697,10 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
   int q_undef = 0;
   while (sqrt((double)(q_undef + 1) / 4.0) <= rho) ++q_undef;
   dim3 rows((L.Hs + 3) / 4, nb);
-  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.lut, L.pix, L.max_n2, L.row_cnt, q_undef);
+  lsd_count_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.max_n2, L.row_cnt, q_undef);
   lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, npx, L.n_def, L.seg_begin, L.seg_end);
-  lsd_keys_kernel<<<rows, 128, 0, st>>>(L.pix, L.Ws, L.Hs, L.max_n2, L.row_cnt, L.key_in, L.val_in);
+  lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.lut, L.pix, L.max_n2, L.row_cnt, L.key_in, L.val_in,
+                                            q_undef);
 }
 
 // stable: bins descending, raster order inside a bin (identical to cv2 4.13 on every golden)
