@@ -76,7 +76,7 @@ typedef struct psl_config {
   int32_t orb_min_th_fast; /* ORBextractor.minThFAST   (7)    */
   int32_t orb_max_candidates; /* FAST candidate pool per frame; 0 = auto (the reference only
                                  reserves nfeatures*10 as a hint, ORBextractor.cc:779) */
-  int32_t chunk_frames;    /* frames processed together so a chunk's pyramid stays in L2; 0 = auto */
+  int32_t chunk_frames;    /* frames per launch of the ORB stages; 0 = auto (512; ~2.4 MB of HBM per frame at 640x480) */
   int32_t line_nfeatures;  /* LINEextractor.nFeatures  (200)  */
   float line_scale_factor; /* LINEextractor.scaleFactor (1.2; truncated to int 1 by the reference) */
   int32_t line_nlevels;    /* LINEextractor.nLevels    (1)    */

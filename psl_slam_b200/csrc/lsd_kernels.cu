@@ -334,9 +334,8 @@ __device__ void step_sequential(const Frame& f, Grow& g, Nbr& cur, double prec, 
   }
 }
 
-__device__ int region_grow(const Frame& f, int seed, double& reg_angle, double prec, int lane) {
+__device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_angle, double prec, int lane) {
   const int W = f.W;
-  const float4 srec = f.pix[seed];
   Grow g;
   g.reg_angle = (double)srec.x * kDegToRad;
   // The reference seeds the sums with (float)cos(reg_angle) of the fp64 angle; that value only matters once a
@@ -348,10 +347,16 @@ __device__ int region_grow(const Frame& f, int seed, double& reg_angle, double p
   g.angle_valid = true;
   g.n = 1;
   const int sy = seed / W, sx = seed - sy * W;
+  const uint32_t c0 = ((uint32_t)sy << 16) | (uint32_t)sx;
+  const int p = lane / 9, k = lane - 9 * p;
+  const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
+  // the seed's neighbours are requested before the seed is written back (none of them is the seed's own record
+  // as a candidate: the centre lane is struck below)
+  Nbr cur = load_nbr_at(f, p == 0, c0, ox, oy);
+  if (cur.nidx == seed) cur.cand = false;
   if (lane == 0) {
-    const uint32_t c = ((uint32_t)sy << 16) | (uint32_t)sx;
-    f.reg[0] = c;
-    f.ring[0] = c;
+    f.reg[0] = c0;
+    f.ring[0] = c0;
     *flags_of(f, seed) = __float_as_int(srec.w) | lsdw_kUsed;
   }
   __syncwarp();
@@ -360,15 +365,12 @@ __device__ int region_grow(const Frame& f, int seed, double& reg_angle, double p
   const float chi = quick ? (float)cos(prec - band) : 2.f;   // dot >= chi * |sum|: aligned for sure
   const float clo = quick ? (float)cos(prec + band) : 0.f;   // dot <= clo * |sum|: not aligned for sure
   const float chi2 = chi * chi, clo2 = clo * clo;
-  const int p = lane / 9, k = lane - 9 * p;
-  const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
   const unsigned lt = (1u << lane) - 1u;
   // Software pipeline: the records of the next step's neighbours are requested as soon as the accepted set of
   // the current step is known (its region points are the next entries of the list), i.e. before the flag /
   // list stores and the ordered sum update of the current step; pixels accepted in the current step are
   // struck from the prefetched set by index.
   int i = 0, m = 1;
-  Nbr cur = load_nbr(f, 0, 1, 1, p, ox, oy);
   while (true) {
     i += m;                       // first region point of the next step
     const unsigned cm = __ballot_sync(kFull, cur.cand);
@@ -600,7 +602,7 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
   __syncwarp();
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(f, sy * f.W + sx, reg_angle, tau, lane);
+  n = region_grow(f, sy * f.W + sx, f.pix[sy * f.W + sx], reg_angle, tau, lane);
   if (n < 2) return false;
   region2rect(f, n, reg_angle, prec, rec, lane);
   density = density_of(n, rec);
@@ -633,10 +635,11 @@ __global__ void __launch_bounds__(kCoreWarps * 32, 7)
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
       const int seed = __shfl_sync(lsdw::kFull, my, l);
-      if (*lsdw::flags_of(f, seed) & lsdw_kUsed) continue;
+      const float4 srec = f.pix[seed];
+      if (__float_as_int(srec.w) & lsdw_kUsed) continue;
       double reg_angle;
       LSD_T0(t_g);
-      int n = lsdw::region_grow(f, seed, reg_angle, prec, lane);
+      int n = lsdw::region_grow(f, seed, srec, reg_angle, prec, lane);
       LSD_T1(10, t_g);
       LSD_STAT(13, 1);
       if (n < L.min_reg_size) continue;

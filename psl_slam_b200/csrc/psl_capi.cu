@@ -278,7 +278,7 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
     }
     ctx->quota[L - 1] = std::max(cfg->orb_nfeatures - sum, 0);
   }
-  ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 256;
+  ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 512;
   ctx->line_chunk = cfg->line_chunk_frames > 0 ? cfg->line_chunk_frames : std::min(std::max(cfg->max_batch, 64), 4096);
   ctx->pool_cap = cfg->orb_max_candidates > 0 ? cfg->orb_max_candidates : std::max(16384, 32 * cfg->orb_nfeatures);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
