@@ -122,6 +122,21 @@ int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, in
                               int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
                               int32_t* d_n);
 
+/* Tracking::GrabImageRGBD input conversion (src/Tracking.cc:219-235; SURVEY "next" row N3, kernel K0):
+ *   cvtColor(RGB|BGR|RGBA|BGRA -> GRAY)  Y = (R*9798 + G*19235 + B*3735 + 16384) >> 15   (OpenCV 4.x Q15 arithmetic)
+ *   imDepth.convertTo(CV_32F, mDepthMapFactor)
+ * Batched, DEVICE pointers, asynchronous.  color: B frames of h rows, `channels` (3 or 4) interleaved bytes per
+ * pixel, `color_stride` bytes per row, frames `color_frame_stride` bytes apart; rgb_order != 0 for mbRGB (R first).
+ * gray: [B][h][gray_stride] u8.  depth_in u16 (strides in pixels) -> depth_out float [B][h][w]; either half of the
+ * call may be skipped by passing NULL. */
+int psl_convert_rgbd_dev(psl_ctx* ctx, const uint8_t* d_color, int32_t channels, int32_t rgb_order, int32_t color_stride,
+                         int64_t color_frame_stride, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                         const uint16_t* d_depth_in, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                         float depth_factor, float* d_depth_out, int32_t B, int32_t w, int32_t h);
+/* HOST pointers, tightly packed frames ([B][h][w][channels] -> [B][h][w]). */
+int psl_convert_rgbd(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32_t rgb_order, uint8_t* gray,
+                     const uint16_t* depth_in, float depth_factor, float* depth_out, int32_t B, int32_t w, int32_t h);
+
 /* LINEextractor::operator()(image, mask, keylines, descriptors, lineVec2d)
  * (add_src/LineExtractor.cpp:325-366; called from Frame::ExtractLSD, src/Frame.cc:494):
  *   LSDDetector::detect(img, kl, scale -> int 1, numOctaves 1)   :336-337  (cv::LineSegmentDetector, REFINE_STD)

@@ -8,5 +8,5 @@ from .orb import Context, ORBextractor  # noqa: F401
 from .line import LINEextractor  # noqa: F401
 from .line_matcher import InsectLineMatch, LineFrameData, LSDmatcher  # noqa: F401
 from .matcher import FrameData, ORBmatcher, hamming_knn2  # noqa: F401
-from .tracking import (make_camera, make_track_params, track_frontend_batch, track_frontend_batch_dev,  # noqa: F401
+from .tracking import (convert_rgbd, make_camera, make_track_params, track_frontend_batch, track_frontend_batch_dev,  # noqa: F401
                        track_orb_batch, track_orb_batch_dev)

@@ -115,4 +115,63 @@ void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* 
   query_build_kernel<<<grid, 128, 0, st>>>(kps, z, n, cap, Tcw, first, cam, prm, q, nq);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K0: input conversion of Tracking::GrabImageRGBD (Tracking.cc:219-235).  Pure streaming: a thread
+// converts 4 adjacent pixels (12 or 16 colour bytes in, one gray word out).
+// ---------------------------------------------------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(256)
+    color_to_gray_kernel(const uint8_t* __restrict__ color, int r_first, int color_stride, int64_t color_fs,
+                         uint8_t* __restrict__ gray, int gray_stride, int64_t gray_fs, int w) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, b = blockIdx.z;
+  if (x >= w) return;
+  const uint8_t* src = color + (size_t)b * color_fs + (size_t)y * color_stride + (size_t)x * CH;
+  uint8_t* dst = gray + (size_t)b * gray_fs + (size_t)y * gray_stride + x;
+  const int n = min(4, w - x);
+  uint8_t px[4 * CH];
+  const bool vec = n == 4 && ((uintptr_t)src & 3) == 0;
+  if (vec) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) reinterpret_cast<uint32_t*>(px)[k] = __ldg(reinterpret_cast<const uint32_t*>(src) + k);
+  } else {
+    for (int k = 0; k < n * CH; ++k) px[k] = __ldg(src + k);
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) {
+      const uint32_t c0 = px[k * CH], c1 = px[k * CH + 1], c2 = px[k * CH + 2];
+      const uint32_t R = r_first ? c0 : c2, B = r_first ? c2 : c0;
+      out |= ((R * 9798u + c1 * 19235u + B * 3735u + 16384u) >> 15) << (8 * k);
+    }
+  }
+  if (n == 4 && ((uintptr_t)dst & 3) == 0) *reinterpret_cast<uint32_t*>(dst) = out;
+  else
+    for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
+}
+
+void launch_color_to_gray(const uint8_t* color, int channels, int rgb_order, int color_stride, int64_t color_fs,
+                          uint8_t* gray, int gray_stride, int64_t gray_fs, int B, int w, int h, cudaStream_t st) {
+  dim3 grid(((w + 3) / 4 + 255) / 256, h, B);
+  if (channels == 3)
+    color_to_gray_kernel<3><<<grid, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w);
+  else
+    color_to_gray_kernel<4><<<grid, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w);
+}
+
+__global__ void __launch_bounds__(256)
+    depth_to_float_kernel(const uint16_t* __restrict__ in, int stride_px, int64_t fs_px, float factor,
+                          float* __restrict__ out, int w, int h) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= w) return;
+  // cv::Mat::convertTo(CV_32F, alpha): saturate_cast<float>(src * alpha) evaluated in fp32 for 16U sources
+  out[((size_t)b * h + y) * w + x] = __fmul_rn((float)__ldg(in + (size_t)b * fs_px + (size_t)y * stride_px + x), factor);
+}
+
+void launch_depth_to_float(const uint16_t* in, int stride_px, int64_t fs_px, float factor, float* out, int B, int w,
+                           int h, cudaStream_t st) {
+  dim3 grid((w + 255) / 256, h, B);
+  depth_to_float_kernel<<<grid, 256, 0, st>>>(in, stride_px, fs_px, factor, out, w, h);
+}
+
 }  // namespace psl

@@ -17,4 +17,10 @@ void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* 
                         const psl_camera& cam, const QueryBuildParams& prm, psl_proj_query* q, int32_t* nq, int B,
                         cudaStream_t st);
 
+// K0: cvtColor(... -> GRAY) in OpenCV 4.x Q15 arithmetic and depth.convertTo(CV_32F, factor) (Tracking.cc:219-235)
+void launch_color_to_gray(const uint8_t* color, int channels, int rgb_order, int color_stride, int64_t color_fs,
+                          uint8_t* gray, int gray_stride, int64_t gray_fs, int B, int w, int h, cudaStream_t st);
+void launch_depth_to_float(const uint16_t* in, int stride_px, int64_t fs_px, float factor, float* out, int B, int w,
+                           int h, cudaStream_t st);
+
 }  // namespace psl

@@ -251,4 +251,61 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
   return check_status(ctx);
 }
 
+
+int psl_convert_rgbd_dev(psl_ctx* ctx, const uint8_t* d_color, int32_t channels, int32_t rgb_order, int32_t color_stride,
+                         int64_t color_frame_stride, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                         const uint16_t* d_depth_in, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                         float depth_factor, float* d_depth_out, int32_t B, int32_t w, int32_t h) {
+  if (!ctx) return PSL_E_INVALID;
+  const bool do_color = d_color || d_gray, do_depth = d_depth_in || d_depth_out;
+  if (B < 0 || w <= 0 || h <= 0 || (do_color && (!d_color || !d_gray || (channels != 3 && channels != 4) ||
+      color_stride < w * channels || gray_stride < w)) || (do_depth && (!d_depth_in || !d_depth_out || depth_stride_px < w)))
+    return fail(ctx, PSL_E_INVALID, "bad argument (3 or 4 channels)");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  size_t e = prof_mark(ctx);
+  if (do_color)
+    launch_color_to_gray(d_color, channels, rgb_order, color_stride, color_frame_stride, d_gray, gray_stride,
+                         gray_frame_stride, B, w, h, ctx->stream);
+  if (do_depth)
+    launch_depth_to_float(d_depth_in, depth_stride_px, depth_frame_stride_px, depth_factor, d_depth_out, B, w, h,
+                          ctx->stream);
+  prof_span(ctx, 6, e, (int)do_color + (int)do_depth);
+  PSL_CK(cudaGetLastError());
+  return PSL_OK;
+}
+
+int psl_convert_rgbd(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32_t rgb_order, uint8_t* gray,
+                     const uint16_t* depth_in, float depth_factor, float* depth_out, int32_t B, int32_t w, int32_t h) {
+  if (!ctx) return PSL_E_INVALID;
+  if (B < 0 || w <= 0 || h <= 0 || (channels != 3 && channels != 4)) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const size_t px = (size_t)w * h * B;
+  DevBuf* M = ctx->m_misc;
+  cudaStream_t st = ctx->stream;
+  int rc;
+  const bool do_color = color && gray, do_depth = depth_in && depth_out;
+  if ((color || gray) && !do_color) return fail(ctx, PSL_E_INVALID, "color and gray must be given together");
+  if ((depth_in || depth_out) && !do_depth) return fail(ctx, PSL_E_INVALID, "depth_in and depth_out must be given together");
+  if (do_color) {
+    if ((rc = ensure(ctx, M[0], px * channels))) return rc;
+    if ((rc = ensure(ctx, M[1], px))) return rc;
+    PSL_CK(cudaMemcpyAsync(M[0].p, color, px * channels, cudaMemcpyHostToDevice, st));
+  }
+  if (do_depth) {
+    if ((rc = ensure(ctx, M[2], px * 2))) return rc;
+    if ((rc = ensure(ctx, M[3], px * 4))) return rc;
+    PSL_CK(cudaMemcpyAsync(M[2].p, depth_in, px * 2, cudaMemcpyHostToDevice, st));
+  }
+  rc = psl_convert_rgbd_dev(ctx, do_color ? M[0].as<uint8_t>() : nullptr, channels, rgb_order, w * channels,
+                            (int64_t)w * h * channels, do_color ? M[1].as<uint8_t>() : nullptr, w, (int64_t)w * h,
+                            do_depth ? M[2].as<uint16_t>() : nullptr, w, (int64_t)w * h, depth_factor,
+                            do_depth ? M[3].as<float>() : nullptr, B, w, h);
+  if (rc) return rc;
+  if (do_color) PSL_CK(cudaMemcpyAsync(gray, M[1].p, px, cudaMemcpyDeviceToHost, st));
+  if (do_depth) PSL_CK(cudaMemcpyAsync(depth_out, M[3].p, px * 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
 }  // extern "C"

@@ -86,3 +86,23 @@ def track_frontend_batch_dev(ex: ORBextractor, d_gray: int, d_depth: int, B: int
     ex.ctx.check(_lib.lib().psl_track_frontend_batch_dev(ex.ctx.handle, d_gray, W, W * H, d_depth, W, W * H, B, W, H,
                                                          d_Tcw, C.addressof(cam), C.addressof(prm),
                                                          C.c_float(line_desc_th), C.byref(fo)))
+
+
+def convert_rgbd(ctx, color: np.ndarray | None, rgb_order: bool, depth: np.ndarray | None, depth_map_factor: float = 5000.0):
+    """Input conversion of Tracking::GrabImageRGBD (src/Tracking.cc:219-235): colour [B,H,W,3|4] u8 -> gray [B,H,W] u8
+    (cvtColor RGB/BGR/RGBA/BGRA2GRAY) and depth [B,H,W] u16 -> float32 * (1/DepthMapFactor).  HOST arrays."""
+    gray = dep = None
+    B = H = W = ch = 0
+    if color is not None:
+        color = np.ascontiguousarray(color, np.uint8)
+        B, H, W, ch = color.shape
+        gray = np.empty((B, H, W), np.uint8)
+    if depth is not None:
+        depth = np.ascontiguousarray(depth, np.uint16)
+        B, H, W = depth.shape
+        dep = np.empty((B, H, W), np.float32)
+    f = np.float32(1.0) / np.float32(depth_map_factor)
+    ctx.check(_lib.lib().psl_convert_rgbd(ctx.handle, None if color is None else _ptr(color), ch or 3, int(rgb_order),
+                                          None if gray is None else _ptr(gray), None if depth is None else _ptr(depth),
+                                          C.c_float(f), None if dep is None else _ptr(dep), B, W, H))
+    return gray, dep

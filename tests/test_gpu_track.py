@@ -97,3 +97,21 @@ def test_combined_frontend_vs_oracle_chain(orc):
     n2, nm2, nl2, lnm2 = orc.frontend_batch_mt(gray, depth, T[:, :3, :4].reshape(len(T), 12), cam6, nthreads=2)
     assert np.array_equal(n2, out["n"]) and np.array_equal(nm2, out["nmatches"])
     assert np.array_equal(nl2, out["nl"]) and np.array_equal(lnm2, out["line_nmatches"])
+
+
+def test_input_conversion_vs_cv2_golden():
+    """Tracking::GrabImageRGBD's cvtColor / convertTo (K0) against real cv2 4.13 outputs."""
+    from conftest import load_golden
+    from psl_slam_b200 import Context, convert_rgbd, default_config, synth
+    g = load_golden("convert_rgbd")
+    ctx = Context(default_config())
+    for key, arr, order in (("gray_rgb", g["rgb"], True), ("gray_bgr", g["rgb"], False), ("gray_rgba", g["rgba"], True),
+                            ("gray_bgra", g["rgba"], False)):
+        gray, dep = convert_rgbd(ctx, np.stack([arr, arr[::-1].copy()]), order, np.stack([g["depth"], g["depth"]]))
+        assert np.array_equal(gray[0], g[key]) and np.array_equal(gray[1], g[key][::-1])
+        assert np.array_equal(dep[0], g["depth_f"])
+    # the synthetic generator's gray frames are this conversion of its RGB renders
+    poster = synth.make_poster(3, 512, 200)
+    rgb, _ = synth.render(poster, synth.trajectory(1, 3)[0], 320, 240)
+    gray, _ = convert_rgbd(ctx, rgb[None], True, None)
+    assert np.array_equal(gray[0], synth.rgb_to_gray(rgb))

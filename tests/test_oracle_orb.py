@@ -79,3 +79,14 @@ def test_orb_extract_end_to_end(orc, name):
 def test_empty_image(orc):
     kps, desc = orc.orb_extract(np.zeros((0, 0), np.uint8).reshape(0, 0))
     assert len(kps) == 0 and desc.shape == (0, 32)
+
+
+def test_gray_conversion_formula_vs_cv2_golden():
+    """The Q15 RGB->Y restatement used by the synthetic generator against real cv2.cvtColor."""
+    from conftest import load_golden
+    from psl_slam_b200 import synth
+    g = load_golden("convert_rgbd")
+    assert np.array_equal(synth.rgb_to_gray(g["rgb"]), g["gray_rgb"])
+    assert np.array_equal(synth.rgb_to_gray(g["rgb"][..., ::-1]), g["gray_bgr"])
+    assert np.array_equal(synth.rgb_to_gray(g["rgba"][..., :3]), g["gray_rgba"])
+    assert np.array_equal((g["depth"].astype(np.float32) * g["factor"]).astype(np.float32), g["depth_f"])
