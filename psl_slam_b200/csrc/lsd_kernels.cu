@@ -202,6 +202,7 @@ struct Frame {
   float4* pix;
   uint32_t* reg;    // region points in HBM, packed y << 16 | x
   uint32_t* ring;   // the last kRing of them in shared memory
+  double* terms;    // [3][32] staging of the fp64 terms that are summed in list order
 };
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -282,8 +283,7 @@ struct Grow {
   int n;
 };
 
-__device__ __forceinline__ void accept_terms(const Frame& f, Grow& g, const Nbr& cur, unsigned A, int lane,
-                                             Nbr* nxt = nullptr) {
+__device__ __forceinline__ void accept_terms(const Frame& f, Grow& g, const Nbr& cur, unsigned A, int lane) {
   if (g.n == 1) {  // first accept of the region: the exact seed terms (see region_grow)
     g.sumdx = (float)cos(g.reg_angle);
     g.sumdy = (float)sin(g.reg_angle);
@@ -299,10 +299,6 @@ __device__ __forceinline__ void accept_terms(const Frame& f, Grow& g, const Nbr&
     const int j = __ffs(a) - 1;
     g.sumdx += __shfl_sync(kFull, cur.rec.y, j);
     g.sumdy += __shfl_sync(kFull, cur.rec.z, j);
-    if (nxt) {  // records loaded before this step's flag stores: strike what has just become USED
-      const int aidx = __shfl_sync(kFull, cur.nidx, j);
-      if (nxt->nidx == aidx) nxt->cand = false;
-    }
   }
   g.s2 = g.sumdx * g.sumdx + g.sumdy * g.sumdy;
   g.angle_valid = false;
@@ -376,6 +372,7 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
     const unsigned cm = __ballot_sync(kFull, cur.cand);
     bool batched = false;
     unsigned A = 0;
+    float new_dx = 0.f, new_dy = 0.f;
     if (!cm) {
       batched = true;
     } else if (quick && g.s2 > 1e-6f) {
@@ -393,17 +390,18 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
         const bool maybe0 = cur.cand && !yes0 && dot > 0.f && dot * dot > clo2 * g.s2;
         batched = !__any_sync(kFull, maybe0);
       } else {
-        // the sums every lane would see in the scalar loop: exclusive prefix over A (for classification only)
-        const bool inA = A >> lane & 1u;
-        float px = inA ? cur.rec.y : 0.f, py = inA ? cur.rec.z : 0.f;
-        const float ownx = px, owny = py;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const float ux = __shfl_up_sync(kFull, px, d), uy = __shfl_up_sync(kFull, py, d);
-          if (lane >= d) { px += ux; py += uy; }
+        // the sums every lane would see in the scalar loop: the running sums advanced by the lanes of A before
+        // it, added in lane order with the reference's fp32 rounding (lane 31 ends with the sums after the step)
+        float Px = g.sumdx, Py = g.sumdy;
+        if (g.n == 1) {  // first accept of the region: the exact seed terms (see above)
+          Px = (float)cos(g.reg_angle);
+          Py = (float)sin(g.reg_angle);
         }
-        // (at the first accept the exact seed terms replace the record's: same to 1e-7, far inside the band)
-        const float Px = g.sumdx + (px - ownx), Py = g.sumdy + (py - owny);
+        for (unsigned a = A; a; a &= a - 1) {
+          const int j = __ffs(a) - 1;
+          const float vx = __shfl_sync(kFull, cur.rec.y, j), vy = __shfl_sync(kFull, cur.rec.z, j);
+          if (lane > j) { Px += vx; Py += vy; }
+        }
         const float d1 = cur.rec.y * Px + cur.rec.z * Py, q1 = Px * Px + Py * Py;
         const bool sure1 = q1 > 1e-6f;
         const bool yes1 = cur.cand && sure1 && d1 > 0.f && d1 * d1 >= chi2 * q1;
@@ -413,6 +411,10 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
         const bool certain = taken || yes1 || no1;
         const unsigned E = __ballot_sync(kFull, expect);
         batched = __all_sync(kFull, certain) && E == A;
+        if (batched) {
+          new_dx = __shfl_sync(kFull, Px, 31);
+          new_dy = __shfl_sync(kFull, Py, 31);
+        }
       }
     }
     if (batched) {
@@ -427,7 +429,23 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
       const uint32_t fromA = __shfl_sync(kFull, cur.npk, src < 0 ? 0 : src);
       if (p < m2) c = idx < n_old ? reg_at(f, idx, n_old) : fromA;
       Nbr nxt = load_nbr_at(f, p < m2, c, ox, oy);
-      if (A) accept_terms(f, g, cur, A, lane, &nxt);
+      if (A) {
+        if (A >> lane & 1u) {
+          const int at = n_old + __popc(A & lt);
+          *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
+          f.reg[at] = cur.npk;
+          f.ring[at & (kRing - 1)] = cur.npk;
+        }
+        for (unsigned a = A; a; a &= a - 1) {  // records loaded before these flag stores: strike what just became USED
+          const int aidx = __shfl_sync(kFull, cur.nidx, __ffs(a) - 1);
+          if (nxt.nidx == aidx) nxt.cand = false;
+        }
+        g.n = n_new;
+        g.sumdx = new_dx;
+        g.sumdy = new_dy;
+        g.s2 = new_dx * new_dx + new_dy * new_dy;
+        g.angle_valid = false;
+      }
       cur = nxt;
       m = m2;
     } else {
@@ -464,11 +482,16 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
       tx = (double)px * w;
       ty = (double)py * w;
     }
+    // ordered sums: the 32 terms go through shared memory and every lane adds them in list order (a broadcast
+    // read + one add per term, instead of a shuffle chain)
     const int cnt = min(32, n - base);
+    __syncwarp();
+    f.terms[lane] = tx; f.terms[32 + lane] = ty; f.terms[64 + lane] = w;
+    __syncwarp();
     for (int k = 0; k < cnt; ++k) {
-      x += shfl_d(tx, k);
-      y += shfl_d(ty, k);
-      sum += shfl_d(w, k);
+      x += f.terms[k];
+      y += f.terms[32 + k];
+      sum += f.terms[64 + k];
     }
   }
   x /= sum;
@@ -487,10 +510,13 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
       t3 = dx * dy * w;
     }
     const int cnt = min(32, n - base);
+    __syncwarp();
+    f.terms[lane] = t1; f.terms[32 + lane] = t2; f.terms[64 + lane] = t3;
+    __syncwarp();
     for (int k = 0; k < cnt; ++k) {
-      Ixx += shfl_d(t1, k);
-      Iyy += shfl_d(t2, k);
-      Ixy -= shfl_d(t3, k);
+      Ixx += f.terms[k];
+      Iyy += f.terms[32 + k];
+      Ixy -= f.terms[64 + k];
     }
   }
   const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
@@ -594,9 +620,12 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
     }
     cnt += __popc(__ballot_sync(kFull, in));
     const int c32 = min(32, n - base);
+    __syncwarp();
+    f.terms[lane] = a; f.terms[32 + lane] = a2;
+    __syncwarp();
     for (int k = 0; k < c32; ++k) {
-      sum += shfl_d(a, k);
-      s_sum += shfl_d(a2, k);
+      sum += f.terms[k];
+      s_sum += f.terms[32 + k];
     }
   }
   __syncwarp();
@@ -617,10 +646,11 @@ constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never 
 __global__ void __launch_bounds__(kCoreWarps * 32, 7)
     lsd_core_kernel(LineBuffers L, int nb, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
+  __shared__ double terms[kCoreWarps][96];
   const int wid = threadIdx.x >> 5, b = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
   if (b >= nb) return;
   const size_t npx = (size_t)L.Ws * L.Hs;
-  lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.reg + b * npx, ring[wid]};
+  lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.reg + b * npx, ring[wid], terms[wid]};
   const uint32_t* seeds = L.val_out + b * npx;
   const int n_seeds = L.n_def[b];
   float* out = L.raw + (size_t)b * L.raw_cap * 4;
