@@ -39,6 +39,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 constexpr int kDescWarps = 8;
+constexpr int kWinPitch = 44;  // staged window row: 11 words cover x-19 .. x+19 from a word-aligned start
 
 __global__ void __launch_bounds__(kDescWarps * 32)
     describe_kernel(const OrbGeometry* __restrict__ geo, ImgBatch in0, const uint32_t* __restrict__ sel,
@@ -78,19 +79,52 @@ __global__ void __launch_bounds__(kDescWarps * 32)
     img = geo->level[lvl].ptr + (size_t)b * geo->level[lvl].frame_stride;
     pitch = geo->level[lvl].pitch;
   }
+  // Both stages gather single bytes around the keypoint (31 patch rows, then 512 rotated pattern points within
+  // 19 px): straight from HBM/L2 that is one 32-byte sector per byte.  The warp first copies the two windows
+  // into shared memory with row-contiguous word loads (~80 sectors instead of ~540) and gathers from there.
+  __shared__ __align__(16) uint8_t s_blur[kDescWarps][39][kWinPitch];
+  __shared__ __align__(16) uint8_t s_raw[kDescWarps][31][kWinPitch];
+  const uint8_t* blur_img = geo->blur[lvl].ptr + (size_t)b * geo->blur[lvl].frame_stride;
+  const int bp = geo->blur[lvl].pitch;
+  const bool aligned = (((uintptr_t)img | (uintptr_t)blur_img) & 3) == 0 && ((pitch | bp) & 3) == 0;
+  const int xs = (x - kEdge) & ~3;            // first staged column (word aligned), x - 19 >= 0
+  const int nw = ((x + kEdge - xs) >> 2) + 1;  // words per row (<= 11)
+  if (aligned) {
+    for (int k = lane; k < 39 * nw; k += 32) {
+      const int r = k / nw, c = k - r * nw;
+      reinterpret_cast<uint32_t*>(&s_blur[warp][r][0])[c] =
+          __ldg(reinterpret_cast<const uint32_t*>(blur_img + (size_t)(y - kEdge + r) * bp + xs) + c);
+    }
+    for (int k = lane; k < 31 * nw; k += 32) {
+      const int r = k / nw, c = k - r * nw;
+      reinterpret_cast<uint32_t*>(&s_raw[warp][r][0])[c] =
+          __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y - kHalfPatch + r) * pitch + xs) + c);
+    }
+    __syncwarp();
+  }
+  const int xo = x - xs;  // column of the keypoint inside the staged rows
   // ---- IC_Angle: lane r owns patch row v = r - 15 -------------------------------------------
   int m10 = 0, m01 = 0;
   if (lane < 31) {
     const int v = lane - kHalfPatch;
     const int d = g_umax[v < 0 ? -v : v];
-    const uint8_t* row = img + (size_t)(y + v) * pitch + x;
-    int s = 0;
-    for (int u = -d; u <= d; ++u) {
-      const int val = __ldg(row + u);
-      s += val;
-      m10 += u * val;
+    int sum = 0;
+    if (aligned) {
+      const uint8_t* row = &s_raw[warp][lane][xo];
+      for (int u = -d; u <= d; ++u) {
+        const int val = row[u];
+        sum += val;
+        m10 += u * val;
+      }
+    } else {
+      const uint8_t* row = img + (size_t)(y + v) * pitch + x;
+      for (int u = -d; u <= d; ++u) {
+        const int val = __ldg(row + u);
+        sum += val;
+        m10 += u * val;
+      }
     }
-    m01 = v * s;
+    m01 = v * sum;
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
@@ -103,8 +137,8 @@ __global__ void __launch_bounds__(kDescWarps * 32)
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);  // :107
   const float rad = __fmul_rn(angle, factorPI);
   const float a = (float)cos((double)rad), bsin = (float)sin((double)rad);
-  const uint8_t* bl = geo->blur[lvl].ptr + (size_t)b * geo->blur[lvl].frame_stride + (size_t)y * geo->blur[lvl].pitch + x;
-  const int bp = geo->blur[lvl].pitch;
+  const uint8_t* bl = aligned ? &s_blur[warp][kEdge][xo] : blur_img + (size_t)y * bp + x;
+  const int bpp = aligned ? kWinPitch : bp;
   const char4* pat = reinterpret_cast<const char4*>(g_pattern) + lane * 8;
   uint32_t byte = 0;
 #pragma unroll
@@ -115,7 +149,7 @@ __global__ void __launch_bounds__(kDescWarps * 32)
     const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, bsin)));
     const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, bsin), __fmul_rn(y1, a)));
     const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, bsin)));
-    const int t0 = __ldg(bl + r0 * bp + c0), t1 = __ldg(bl + r1 * bp + c1);
+    const int t0 = bl[r0 * bpp + c0], t1 = bl[r1 * bpp + c1];
     byte |= (t0 < t1 ? 1u : 0u) << t;
   }
   desc[((size_t)b * cap + i) * 32 + lane] = (uint8_t)byte;
