@@ -405,9 +405,10 @@ __global__ void __launch_bounds__(64)
     float sCorX = sCorX0, sCorY = sCorY0;
     float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
     for (short wID = 0; wID < lengthOfLSP; ++wID) {
-      short q = (short)round((double)sCorX);
+      // round() of the reference (half away from zero, on the float promoted to double) == roundf on the float
+      short q = (short)roundf(sCorX);
       const short xCor = (q < 0) ? (short)0 : (q > imageWidth) ? imageWidth : q;
-      q = (short)round((double)sCorY);
+      q = (short)roundf(sCorY);
       const short yCor = (q < 0) ? (short)0 : (q > imageHeight) ? imageHeight : q;
       const short2 gg = __ldg(g + (int)yCor * w + (int)xCor);
       const float gDL = (float)gg.x * dL0 + (float)gg.y * dL1, gDO = (float)gg.x * dO0 + (float)gg.y * dO1;
