@@ -57,7 +57,8 @@ def algorithmic_bytes(w, h, nlevels, scale, nfeat):
         # line stages (LSD works on the 0.8x image, Ws x Hs = lrint(.8 w) x lrint(.8 h))
         "lsd_prologue": 2 * w * h + (w * h + LS(w, h)) + LS(w, h) * (1 + 4 + 4 + 1) + LS(w, h) * (8 + 6),
         #                 blur R+W    resize R + W        gradient R u8, W deg/n2/used   seed keys R, W (key, idx)
-        "lsd_order": 2 * LS(w, h) * 6 * 2,            # two radix passes over (u16 key, u32 idx) pairs, R + W
+        "lsd_order": 2 * int(0.3 * LS(w, h)) * 6 * 2,  # two radix passes over the (u16 key, u32 idx) pairs of the seed-capable
+        #                                                pixels (~30 % of the 0.8x image on the textured frames), R + W
         "lsd_grow": LS(w, h) * (4 + 4 + 1 + 1) + LS(w, h) * 4,  # deg, n2, used R+W once each + the seed list
         "line_merge": 4096 * 16 * 4,                  # raw segments through two merge passes (bound by the raw cap)
         "lbd": 2 * w * h + w * h + w * h * 4 + 200 * 63 * 120 * 4,  # blur R+W, Sobel R + W short2, 63 x len gathers/line
