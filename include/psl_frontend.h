@@ -237,6 +237,30 @@ int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, c
                   const psl_feature_vector* f_fv, float nn_ratio, int32_t th_low, int32_t check_orientation,
                   int32_t* match_f, int32_t* nmatches);
 
+/* What the KeyFrame-to-KeyFrame matchers read from a KeyFrame (include/KeyFrame.h): mvKeysUn, mvuRight (< 0 = no
+ * stereo observation), mDescriptors and, per keypoint, whether GetMapPoint(i) is non-null. */
+typedef struct psl_keyframe_view {
+  int32_t n;
+  const psl_keypoint* kps_un;
+  const float* u_right;
+  const uint8_t* desc;
+  const uint8_t* has_mappoint;
+} psl_keyframe_view;
+
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) (ORBmatcher.cc:657-823; "next" row
+ * N1, called by LocalMapping::CreateNewMapPoints, LocalMapping.cc:336): within equal vocabulary nodes, for every
+ * KF1 keypoint without a MapPoint the KF2 keypoint without a MapPoint of smallest Hamming distance <= th_low that
+ * is far enough from the epipole (mono-mono only, :739-745) and within 3.84 sigma^2 of the epipolar line
+ * (CheckDistEpipolarLine, :140-157); the last candidate wins distance ties (`dist > bestDist` skips); rotation
+ * histogram as elsewhere.  F12: 3x3 row-major; (ex, ey): epipole in image 2 (:663-670, computed by the caller from
+ * the poses); scale_factors2 / level_sigma2_2: pKF2->mvScaleFactors / mvLevelSigma2.
+ * matches12[kf1.n] = KF2 index or -1 (vMatchedPairs = the non-negative entries in index order); *nmatches = return. */
+int psl_match_triangulation(psl_ctx* ctx, const psl_keyframe_view* kf1, const psl_feature_vector* fv1,
+                            const psl_keyframe_view* kf2, const psl_feature_vector* fv2, const float* F12, float ex,
+                            float ey, const float* scale_factors2, const float* level_sigma2_2, int32_t nlevels,
+                            int32_t only_stereo, int32_t check_orientation, int32_t th_low, int32_t* matches12,
+                            int32_t* nmatches);
+
 /* ------------------------------------------------------------------------------------------------
  * Line matching (add_src/LSDmatcher.cpp, add_src/InsectlineMatch.cpp).  As for points, MapLine / InsectLine
  * objects stay with the caller; plain arrays cross the boundary.  All pointers HOST.

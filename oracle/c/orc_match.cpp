@@ -220,4 +220,74 @@ int orc_match_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* 
   return 0;
 }
 
+
+// ORBmatcher::SearchForTriangulation, ORBmatcher.cc:657-823 (+ CheckDistEpipolarLine :140-157).  vbMatched2 is
+// declared but never set by the reference, so KF2 keypoints can be matched more than once; kept.
+int orc_match_triangulation(const psl_keyframe_view* kf1, const psl_feature_vector* fv1, const psl_keyframe_view* kf2,
+                            const psl_feature_vector* fv2, const float* F12, float ex, float ey,
+                            const float* scale_factors2, const float* level_sigma2_2, int only_stereo,
+                            int check_orientation, int th_low, int32_t* matches12, int32_t* nmatches) {
+  for (int i = 0; i < kf1->n; ++i) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nm = 0, a = 0, b = 0;
+  while (a < fv1->n_nodes && b < fv2->n_nodes) {
+    if (fv1->node_id[a] == fv2->node_id[b]) {
+      for (int i1 = fv1->offs[a]; i1 < fv1->offs[a + 1]; ++i1) {
+        const int idx1 = (int)fv1->idx[i1];
+        if (kf1->has_mappoint[idx1]) continue;
+        const bool bStereo1 = kf1->u_right[idx1] >= 0;
+        if (only_stereo && !bStereo1) continue;
+        const psl_keypoint& kp1 = kf1->kps_un[idx1];
+        const uint8_t* d1 = kf1->desc + 32 * (size_t)idx1;
+        int bestDist = th_low, bestIdx2 = -1;
+        for (int i2 = fv2->offs[b]; i2 < fv2->offs[b + 1]; ++i2) {
+          const int idx2 = (int)fv2->idx[i2];
+          if (kf2->has_mappoint[idx2]) continue;
+          const bool bStereo2 = kf2->u_right[idx2] >= 0;
+          if (only_stereo && !bStereo2) continue;
+          const int dist = desc_dist(d1, kf2->desc + 32 * (size_t)idx2);
+          if (dist > th_low || dist > bestDist) continue;
+          const psl_keypoint& kp2 = kf2->kps_un[idx2];
+          if (!bStereo1 && !bStereo2) {
+            const float distex = ex - kp2.x, distey = ey - kp2.y;
+            if (distex * distex + distey * distey < 100 * scale_factors2[kp2.octave]) continue;
+          }
+          // CheckDistEpipolarLine
+          const float ea = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+          const float eb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+          const float ec = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+          const float num = ea * kp2.x + eb * kp2.y + ec;
+          const float den = ea * ea + eb * eb;
+          if (den == 0) continue;
+          const float dsqr = num * num / den;
+          if (dsqr < 3.84 * level_sigma2_2[kp2.octave]) {
+            bestIdx2 = idx2;
+            bestDist = dist;
+          }
+        }
+        if (bestIdx2 >= 0) {
+          matches12[idx1] = bestIdx2;
+          ++nm;
+          if (check_orientation) rotHist[rot_bin(kp1.angle, kf2->kps_un[bestIdx2].angle)].push_back(idx1);
+        }
+      }
+      ++a; ++b;
+    } else if (fv1->node_id[a] < fv2->node_id[b]) {
+      while (a < fv1->n_nodes && fv1->node_id[a] < fv2->node_id[b]) ++a;
+    } else {
+      while (b < fv2->n_nodes && fv2->node_id[b] < fv1->node_id[a]) ++b;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { matches12[idx] = -1; --nm; }
+    }
+  }
+  *nmatches = nm;
+  return 0;
+}
+
 }  // extern "C"

@@ -59,6 +59,11 @@ int orc_match_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* 
                   const psl_feature_vector* ffv, float nn_ratio, int th_low, int check_orientation, int32_t* match_f,
                   int32_t* nmatches);
 
+int orc_match_triangulation(const psl_keyframe_view* kf1, const psl_feature_vector* fv1, const psl_keyframe_view* kf2,
+                            const psl_feature_vector* fv2, const float* F12, float ex, float ey,
+                            const float* scale_factors2, const float* level_sigma2_2, int only_stereo,
+                            int check_orientation, int th_low, int32_t* matches12, int32_t* nmatches);
+
 /* ---- Frame bookkeeping (orc_frame.cpp): Frame.cc:1342-1381, ORBmatcher.cc:1339-1393 ---- */
 void orc_stereo_from_rgbd(const psl_keypoint* kps, int n, const uint16_t* depth, int w, int h, int stride_px,
                           float depth_factor, float bf, float* u_right, float* z);

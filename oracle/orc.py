@@ -258,6 +258,22 @@ def frontend_batch_mt(gray, depth, Tcw12, cam6, p: OrbParams | None = None, th=1
     return n, nm, nl, lnm
 
 
+def match_triangulation(kf1, fv1, kf2, fv2, F12, ex, ey, scale2, sigma2, only_stereo=False, check_ori=True, th_low=50):
+    """kf* = (kps_un, u_right, desc, has_mappoint), fv* = (node ids, offs, idx)."""
+    from psl_slam_b200._lib import make_feature_vector, make_keyframe_view
+    a, k1 = make_keyframe_view(*kf1)
+    b, k2 = make_keyframe_view(*kf2)
+    f1, k3 = make_feature_vector(*fv1)
+    f2, k4 = make_feature_vector(*fv2)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sc, s2 = np.ascontiguousarray(scale2, np.float32), np.ascontiguousarray(sigma2, np.float32)
+    m12 = np.zeros(max(a.n, 1), np.int32)
+    nm = C.c_int32()
+    lib().orc_match_triangulation(C.byref(a), C.byref(f1), C.byref(b), C.byref(f2), _p(F), C.c_float(ex), C.c_float(ey),
+                                  _p(sc), _p(s2), int(only_stereo), int(check_ori), th_low, _p(m12), C.byref(nm))
+    return m12[: a.n].copy(), nm.value
+
+
 # ---- lines ------------------------------------------------------------------------------------------
 from psl_slam_b200._lib import KEYLINE_DTYPE  # noqa: E402  (ABI struct only)
 

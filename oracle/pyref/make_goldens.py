@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|line|linematch|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|line|linematch|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -125,6 +125,59 @@ def make_match():
         print(f"match_pair{pair}: queries {int((q['flags'] & 1).sum())} proj-matches {nm} / mode1 {nm1} / bow {nmb}")
 
 
+def make_triangulation():
+    """N1 fixture: SearchForTriangulation between two keyframes of the synthetic sequence (fake 64-node vocabulary,
+    F12 from the true poses as LocalMapping::ComputeF12 does)."""
+    from oracle import orc
+    from oracle.pyref import frame_py, match_py
+    K = synth.ICL
+    gray, depth, T = synth.sequence(3, 6)
+    P = orb_cv2.OrbParams()
+    scale = np.array(P.scale, np.float32)
+    sigma2 = (scale * scale).astype(np.float32)
+    rng = np.random.default_rng(31)
+    for case, (i1, i2, only_stereo) in enumerate([(5, 0, False), (4, 1, True)]):
+        views = []
+        for i in (i1, i2):
+            kps, desc = orc.orb_extract(gray[i])
+            xy = np.stack([kps["x"], kps["y"]], 1)
+            ur, _ = frame_py.stereo_from_rgbd(xy, frame_py.depth_to_float(depth[i]), K["bf"])
+            ur = np.where(rng.random(len(ur)) < 0.5, ur, -1.0).astype(np.float32)  # half the points "monocular"
+            has_mp = rng.random(len(kps)) < 0.4
+            node = (desc[:, 0] & 0x3F).astype(np.uint32)
+            fv = {}
+            for k, nd in enumerate(node):
+                if nd % 7 != (3 if i == i1 else 5):
+                    fv.setdefault(int(nd), []).append(k)
+            views.append((kps, ur, desc, has_mp, fv))
+        # ComputeF12 (LocalMapping.cc): F12 = K1^-T [t12]x R12 K2^-1 in float32
+        T1, T2 = T[i1].astype(np.float32), T[i2].astype(np.float32)
+        R1w, t1w, R2w, t2w = T1[:3, :3], T1[:3, 3], T2[:3, :3], T2[:3, 3]
+        R12 = (R1w @ R2w.T).astype(np.float32)
+        t12 = (-R1w @ R2w.T @ t2w + t1w).astype(np.float32)
+        tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]], np.float32)
+        Km = np.array([[K["fx"], 0, K["cx"]], [0, K["fy"], K["cy"]], [0, 0, 1]], np.float32)
+        F12 = (np.linalg.inv(Km).T @ tx @ R12 @ np.linalg.inv(Km)).astype(np.float32)
+        Cw = -(R1w.T @ t1w)                                   # camera centre of KF1
+        C2 = (R2w @ Cw + t2w).astype(np.float32)
+        invz = np.float32(1.0) / C2[2]
+        ex = np.float32(np.float32(np.float32(K["fx"]) * C2[0]) * invz + np.float32(K["cx"]))
+        ey = np.float32(np.float32(np.float32(K["fy"]) * C2[1]) * invz + np.float32(K["cy"]))
+        (k1, u1, d1, h1, f1), (k2, u2, d2, h2, f2) = views
+        m12, nm = match_py.search_for_triangulation(k1, u1, d1, h1, f1, k2, u2, d2, h2, f2, F12, ex, ey, scale, sigma2,
+                                                    only_stereo, True, 50)
+        def csr(d):
+            ids = sorted(d)
+            offs = np.cumsum([0] + [len(d[k]) for k in ids]).astype(np.int32)
+            return np.array(ids, np.uint32), offs, np.array([i for k in ids for i in d[k]], np.uint32)
+        c1, c2 = csr(f1), csr(f2)
+        np.savez_compressed(os.path.join(OUT, f"triang_pair{case}.npz"), kps1=k1, ur1=u1, desc1=d1, has_mp1=h1.astype(np.uint8),
+                            kps2=k2, ur2=u2, desc2=d2, has_mp2=h2.astype(np.uint8), nodes1=c1[0], offs1=c1[1], idx1=c1[2],
+                            nodes2=c2[0], offs2=c2[1], idx2=c2[2], F12=F12, ex=ex, ey=ey, scale=scale, sigma2=sigma2,
+                            only_stereo=np.int32(only_stereo), matches12=m12, nmatches=np.int32(nm))
+        print(f"triang_pair{case}: n {len(k1)}/{len(k2)} matches {nm}")
+
+
 def make_line():
     """cfg-3 shaped fixtures: LSD (real cv2) -> merge -> top-N -> LBD (real cv2 blur/Sobel) -> line equations."""
     from oracle.pyref import line_py
@@ -237,6 +290,8 @@ if __name__ == "__main__":
         make_orb()
     if what in ("match", "all"):
         make_match()
+    if what in ("triang", "all"):
+        make_triangulation()
     if what in ("line", "all"):
         make_line()
     if what in ("linematch", "all"):

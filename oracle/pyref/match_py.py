@@ -189,3 +189,61 @@ def knn2_cv2(q, t):
         for k, e in enumerate(row):
             idx[i, k], dist[i, k] = e.trainIdx, int(e.distance)
     return idx, dist
+
+
+def search_for_triangulation(kps1, ur1, desc1, has_mp1, fv1, kps2, ur2, desc2, has_mp2, fv2, F12, ex, ey, scale2,
+                             sigma2_2, only_stereo=False, check_ori=True, th_low=50):
+    """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:657-823) + CheckDistEpipolarLine (:140-157).
+    kps*: structured keypoints; fv*: dict node -> list of indices; F12 float32 3x3.  Returns (matches12, count)."""
+    n1 = len(kps1)
+    m12 = np.full(n1, -1, np.int32)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    F = F12.astype(F32)
+    for node in sorted(set(fv1) & set(fv2)):
+        for idx1 in fv1[node]:
+            if has_mp1[idx1]:
+                continue
+            st1 = ur1[idx1] >= 0
+            if only_stereo and not st1:
+                continue
+            x1, y1 = F32(kps1["x"][idx1]), F32(kps1["y"][idx1])
+            best, bidx = th_low, -1
+            for idx2 in fv2[node]:
+                if has_mp2[idx2]:   # vbMatched2 is never set by the reference
+                    continue
+                st2 = ur2[idx2] >= 0
+                if only_stereo and not st2:
+                    continue
+                d = popcount_dist(desc1[idx1], desc2[idx2])
+                if d > th_low or d > best:
+                    continue
+                x2, y2, o2 = F32(kps2["x"][idx2]), F32(kps2["y"][idx2]), int(kps2["octave"][idx2])
+                if not st1 and not st2:
+                    dx, dy = F32(F32(ex) - x2), F32(F32(ey) - y2)
+                    if F32(F32(dx * dx) + F32(dy * dy)) < F32(F32(100) * F32(scale2[o2])):
+                        continue
+                a = F32(F32(F32(x1 * F[0, 0]) + F32(y1 * F[1, 0])) + F[2, 0])
+                b = F32(F32(F32(x1 * F[0, 1]) + F32(y1 * F[1, 1])) + F[2, 1])
+                c = F32(F32(F32(x1 * F[0, 2]) + F32(y1 * F[1, 2])) + F[2, 2])
+                num = F32(F32(F32(a * x2) + F32(b * y2)) + c)
+                den = F32(F32(a * a) + F32(b * b))
+                if den == 0:
+                    continue
+                dsqr = F32(F32(num * num) / den)
+                if float(dsqr) < 3.84 * float(F32(sigma2_2[o2])):
+                    bidx, best = idx2, d
+            if bidx >= 0:
+                m12[idx1] = bidx
+                nm += 1
+                if check_ori:
+                    hist[rot_bin(kps1["angle"][idx1], kps2["angle"][bidx])].append(idx1)
+    if check_ori:
+        keep = three_maxima([len(h) for h in hist])
+        for i in range(HISTO):
+            if i in keep:
+                continue
+            for idx in hist[i]:
+                m12[idx] = -1
+                nm -= 1
+    return m12, nm

@@ -93,6 +93,19 @@ class FrontendOut(C.Structure):  # psl_frontend_out
                 ("nl", C.c_void_p), ("line_assign", C.c_void_p), ("line_nmatches", C.c_void_p)]
 
 
+class KeyFrameView(C.Structure):  # psl_keyframe_view
+    _fields_ = [("n", C.c_int32), ("kps_un", C.c_void_p), ("u_right", C.c_void_p), ("desc", C.c_void_p),
+                ("has_mappoint", C.c_void_p)]
+
+
+def make_keyframe_view(kps_un, u_right, desc, has_mappoint):
+    kps_un = np.ascontiguousarray(kps_un, KP_DTYPE)
+    ur = np.ascontiguousarray(u_right, np.float32)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    mp = np.ascontiguousarray(has_mappoint, np.uint8)
+    return KeyFrameView(len(kps_un), kps_un.ctypes.data, ur.ctypes.data, desc.ctypes.data, mp.ctypes.data), (kps_un, ur, desc, mp)
+
+
 class FeatureVector(C.Structure):  # psl_feature_vector
     _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("offs", C.c_void_p), ("idx", C.c_void_p)]
 
@@ -124,7 +137,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
-           "psl_convert_rgbd_dev"]
+           "psl_convert_rgbd_dev", "psl_match_triangulation"]
 
 _lib = None
 
@@ -174,6 +187,7 @@ def lib():
         L.psl_track_frontend_batch.argtypes = [_p, _p, _p, _i, _i, _i, _p, _p, _p, _f, _p]
         L.psl_convert_rgbd.argtypes = [_p, _p, _i, _i, _p, _p, _f, _p, _i, _i, _i]
         L.psl_convert_rgbd_dev.argtypes = [_p, _p, _i, _i, _i, _l, _p, _i, _l, _p, _i, _l, _f, _p, _i, _i, _i]
+        L.psl_match_triangulation.argtypes = [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

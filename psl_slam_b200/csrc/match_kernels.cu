@@ -472,4 +472,101 @@ void launch_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf
   bow_finalize_kernel<<<1, 128, 0, st>>>(check_ori, match_f, hist, accepted, n_accepted, nmatches);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SearchForTriangulation (ORBmatcher.cc:657-823): one warp per pair of equal vocabulary nodes walks the
+// KF1 keypoints of the node; the lanes scan the KF2 keypoints.  The reference never sets vbMatched2, so the
+// KF1 keypoints are independent: best = smallest distance among the candidates that pass every gate, the
+// LAST one on ties (`dist > bestDist` skips, an equal distance replaces).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    triang_kernel(const psl_keypoint* __restrict__ kps1, const float* __restrict__ ur1, const uint4* __restrict__ desc1,
+                  const uint8_t* __restrict__ mp1, const int32_t* __restrict__ offs1, const uint32_t* __restrict__ idx1,
+                  const psl_keypoint* __restrict__ kps2, const float* __restrict__ ur2, const uint4* __restrict__ desc2,
+                  const uint8_t* __restrict__ mp2, const int32_t* __restrict__ offs2, const uint32_t* __restrict__ idx2,
+                  const int2* __restrict__ pairs, int npairs, const float* __restrict__ F12, float ex, float ey,
+                  const float* __restrict__ scale2, const float* __restrict__ sigma2, int only_stereo, int th_low,
+                  int check_ori, int32_t* __restrict__ m12, int32_t* __restrict__ hist, int32_t* __restrict__ nmatches) {
+  const int lane = threadIdx.x & 31, g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= npairs) return;
+  const int2 pr = pairs[g];
+  const int s1 = offs1[pr.x], e1 = offs1[pr.x + 1], s2 = offs2[pr.y], e2 = offs2[pr.y + 1];
+  const float f00 = F12[0], f01 = F12[1], f02 = F12[2], f10 = F12[3], f11 = F12[4], f12 = F12[5], f20 = F12[6],
+              f21 = F12[7], f22 = F12[8];
+  int nm = 0;
+  for (int i1 = s1; i1 < e1; ++i1) {
+    const int a = (int)idx1[i1];
+    if (mp1[a]) continue;
+    const bool st1 = ur1[a] >= 0.f;
+    if (only_stereo && !st1) continue;
+    const psl_keypoint kp1 = kps1[a];
+    const uint4 q0 = __ldg(desc1 + 2 * a), q1 = __ldg(desc1 + 2 * a + 1);
+    // epipolar line l = x1' F12 (CheckDistEpipolarLine :142-145), no contraction
+    const float ea = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, f00), __fmul_rn(kp1.y, f10)), f20);
+    const float eb = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, f01), __fmul_rn(kp1.y, f11)), f21);
+    const float ec = __fadd_rn(__fadd_rn(__fmul_rn(kp1.x, f02), __fmul_rn(kp1.y, f12)), f22);
+    const float den = __fadd_rn(__fmul_rn(ea, ea), __fmul_rn(eb, eb));
+    unsigned best = 0xFFFFFFFFu;
+    for (int j = s2 + lane; j < e2; j += 32) {
+      const int b = (int)idx2[j];
+      if (mp2[b]) continue;
+      const bool st2 = ur2[b] >= 0.f;
+      if (only_stereo && !st2) continue;
+      const int dist = hamming256(q0, q1, __ldg(desc2 + 2 * b), __ldg(desc2 + 2 * b + 1));
+      if (dist > th_low) continue;
+      const psl_keypoint kp2 = kps2[b];
+      if (!st1 && !st2) {
+        const float dx = __fsub_rn(ex, kp2.x), dy = __fsub_rn(ey, kp2.y);
+        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, scale2[kp2.octave])) continue;
+      }
+      if (den == 0.f) continue;
+      const float num = __fadd_rn(__fadd_rn(__fmul_rn(ea, kp2.x), __fmul_rn(eb, kp2.y)), ec);
+      const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+      if (!((double)dsqr < 3.84 * (double)sigma2[kp2.octave])) continue;
+      const unsigned key = ((unsigned)dist << 16) | (unsigned)(0xFFFF - (j - s2));  // later position = smaller key
+      best = min(best, key);
+    }
+    best = warp_min_u32(best);
+    if (best == 0xFFFFFFFFu) continue;
+    const int b = (int)idx2[s2 + (0xFFFF - (int)(best & 0xFFFFu))];
+    if (lane == 0) {
+      m12[a] = b;
+      if (check_ori) atomicAdd(&hist[rot_bin(kp1.angle, kps2[b].angle)], 1);
+    }
+    ++nm;
+  }
+  if (lane == 0 && nm) atomicAdd(nmatches, nm);
+}
+
+// rotation-consistency filter (:792-808): drop the matches outside the three dominant bins
+__global__ void triang_filter_kernel(const psl_keypoint* __restrict__ kps1, const psl_keypoint* __restrict__ kps2, int n1,
+                                     const int32_t* __restrict__ hist, int32_t* __restrict__ m12,
+                                     int32_t* __restrict__ nmatches) {
+  int ind1 = -1, ind2 = -1, ind3 = -1;
+  three_maxima(hist, ind1, ind2, ind3);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1) return;
+  const int b = m12[i];
+  if (b < 0) return;
+  const int bin = rot_bin(kps1[i].angle, kps2[b].angle);
+  if (bin != ind1 && bin != ind2 && bin != ind3) {
+    m12[i] = -1;
+    atomicSub(nmatches, 1);
+  }
+}
+
+void launch_triangulation(const psl_keypoint* kps1, const float* ur1, const uint8_t* desc1, const uint8_t* mp1,
+                          const int32_t* offs1, const uint32_t* idx1, int n1, const psl_keypoint* kps2, const float* ur2,
+                          const uint8_t* desc2, const uint8_t* mp2, const int32_t* offs2, const uint32_t* idx2,
+                          const int2* pairs, int npairs, const float* F12, float ex, float ey, const float* scale2,
+                          const float* sigma2, int only_stereo, int th_low, int check_ori, int32_t* m12, int32_t* hist,
+                          int32_t* nmatches, cudaStream_t st) {
+  cudaMemsetAsync(m12, 0xFF, (size_t)n1 * sizeof(int32_t), st);
+  cudaMemsetAsync(hist, 0, 33 * sizeof(int32_t), st);  // hist[32] | nmatches
+  if (npairs > 0)
+    triang_kernel<<<(npairs + 3) / 4, 128, 0, st>>>(kps1, ur1, (const uint4*)desc1, mp1, offs1, idx1, kps2, ur2,
+                                                    (const uint4*)desc2, mp2, offs2, idx2, pairs, npairs, F12, ex, ey,
+                                                    scale2, sigma2, only_stereo, th_low, check_ori, m12, hist, nmatches);
+  if (check_ori && n1 > 0) triang_filter_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(kps1, kps2, n1, hist, m12, nmatches);
+}
+
 }  // namespace psl

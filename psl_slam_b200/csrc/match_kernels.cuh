@@ -49,4 +49,12 @@ void launch_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf
                 int32_t* match_f, int32_t* hist /*[32]*/, uint32_t* accepted, int32_t* n_accepted, int32_t* nmatches,
                 cudaStream_t st);
 
+// SearchForTriangulation: candidate scan per vocabulary-node pair + rotation filter.  hist: int32[33] (30 bins used, [32] = nmatches)
+void launch_triangulation(const psl_keypoint* kps1, const float* ur1, const uint8_t* desc1, const uint8_t* mp1,
+                          const int32_t* offs1, const uint32_t* idx1, int n1, const psl_keypoint* kps2, const float* ur2,
+                          const uint8_t* desc2, const uint8_t* mp2, const int32_t* offs2, const uint32_t* idx2,
+                          const int2* pairs, int npairs, const float* F12, float ex, float ey, const float* scale2,
+                          const float* sigma2, int only_stereo, int th_low, int check_ori, int32_t* m12, int32_t* hist,
+                          int32_t* nmatches, cudaStream_t st);
+
 }  // namespace psl

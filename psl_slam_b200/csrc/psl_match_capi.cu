@@ -152,4 +152,68 @@ int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, c
   return check_status(ctx);
 }
 
+
+int psl_match_triangulation(psl_ctx* ctx, const psl_keyframe_view* kf1, const psl_feature_vector* fv1,
+                            const psl_keyframe_view* kf2, const psl_feature_vector* fv2, const float* F12, float ex,
+                            float ey, const float* scale_factors2, const float* level_sigma2_2, int32_t nlevels,
+                            int32_t only_stereo, int32_t check_orientation, int32_t th_low, int32_t* matches12,
+                            int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!kf1 || !kf2 || !fv1 || !fv2 || !F12 || !scale_factors2 || !level_sigma2_2 || !nmatches || nlevels < 1 ||
+      nlevels > kMaxLevels || kf1->n < 0 || kf2->n < 0 || kf2->n > 65535 ||
+      (kf1->n > 0 && (!kf1->kps_un || !kf1->u_right || !kf1->desc || !kf1->has_mappoint || !matches12)) ||
+      (kf2->n > 0 && (!kf2->kps_un || !kf2->u_right || !kf2->desc || !kf2->has_mappoint)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  const int n1 = kf1->n, n2 = kf2->n;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return PSL_OK;
+  for (int i = 0; i < n2; ++i)
+    if (kf2->kps_un[i].octave < 0 || kf2->kps_un[i].octave >= nlevels) return fail(ctx, PSL_E_INVALID, "octave out of range");
+  std::vector<int2> pairs;
+  for (int a = 0, b = 0; a < fv1->n_nodes && b < fv2->n_nodes;) {
+    if (fv1->node_id[a] == fv2->node_id[b]) pairs.push_back(make_int2(a++, b++));
+    else if (fv1->node_id[a] < fv2->node_id[b]) ++a;
+    else ++b;
+  }
+  const size_t ni1 = fv1->n_nodes ? (size_t)fv1->offs[fv1->n_nodes] : 0, ni2 = fv2->n_nodes ? (size_t)fv2->offs[fv2->n_nodes] : 0;
+  for (size_t i = 0; i < ni1; ++i) if ((int)fv1->idx[i] >= n1) return fail(ctx, PSL_E_INVALID, "feature index out of range");
+  for (size_t i = 0; i < ni2; ++i) if ((int)fv2->idx[i] >= n2) return fail(ctx, PSL_E_INVALID, "feature index out of range");
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  DevBuf* M = ctx->m_misc;
+  PSL_UP(M[0], kf1->kps_un, (size_t)n1 * sizeof(psl_keypoint));
+  PSL_UP(M[1], kf1->u_right, (size_t)n1 * 4);
+  PSL_UP(ctx->m_qdesc, kf1->desc, (size_t)n1 * 32);
+  PSL_UP(M[2], kf1->has_mappoint, (size_t)n1);
+  PSL_UP(M[3], fv1->offs, (size_t)(fv1->n_nodes + 1) * 4);
+  PSL_UP(M[4], fv1->idx, ni1 * 4);
+  PSL_UP(M[5], kf2->kps_un, (size_t)n2 * sizeof(psl_keypoint));
+  PSL_UP(M[6], kf2->u_right, (size_t)n2 * 4);
+  PSL_UP(ctx->m_desc, kf2->desc, (size_t)n2 * 32);
+  PSL_UP(M[7], kf2->has_mappoint, (size_t)n2);
+  PSL_UP(M[8], fv2->offs, (size_t)(fv2->n_nodes + 1) * 4);
+  PSL_UP(M[9], fv2->idx, ni2 * 4);
+  PSL_UP(M[10], pairs.data(), pairs.size() * sizeof(int2));
+  float tab[9 + 2 * kMaxLevels] = {0};
+  std::memcpy(tab, F12, 36);
+  std::memcpy(tab + 9, scale_factors2, (size_t)nlevels * 4);
+  std::memcpy(tab + 9 + kMaxLevels, level_sigma2_2, (size_t)nlevels * 4);
+  PSL_UP(M[11], tab, sizeof(tab));
+  int rc;
+  if ((rc = ensure(ctx, ctx->m_assign, (size_t)n1 * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_nm, 33 * 4))) return rc;
+  const float* d_tab = M[11].as<float>();
+  int32_t* d_hist = ctx->m_nm.as<int32_t>();
+  launch_triangulation(M[0].as<psl_keypoint>(), M[1].as<float>(), ctx->m_qdesc.as<uint8_t>(), M[2].as<uint8_t>(),
+                       M[3].as<int32_t>(), M[4].as<uint32_t>(), n1, M[5].as<psl_keypoint>(), M[6].as<float>(),
+                       ctx->m_desc.as<uint8_t>(), M[7].as<uint8_t>(), M[8].as<int32_t>(), M[9].as<uint32_t>(),
+                       M[10].as<int2>(), (int)pairs.size(), d_tab, ex, ey, d_tab + 9, d_tab + 9 + kMaxLevels, only_stereo,
+                       th_low, check_orientation, ctx->m_assign.as<int32_t>(), d_hist, d_hist + 32, ctx->stream);
+  prof_span(ctx, 5, prof_mark(ctx), 2);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(matches12, ctx->m_assign.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(nmatches, d_hist + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
 }  // extern "C"

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view
+from ._lib import KP_DTYPE, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view, make_keyframe_view
 from .orb import Context, _ptr
 
 
@@ -87,6 +87,28 @@ class ORBmatcher:
                                                 C.byref(b), C.c_float(self.mfNNratio), self.TH_LOW,
                                                 int(self.mbCheckOrientation), _ptr(match), C.byref(nm)))
         return match, nm.value
+
+
+    def SearchForTriangulation(self, kf1, fv1, kf2, fv2, F12, epipole, scale_factors2, level_sigma2_2,
+                               bOnlyStereo=False):
+        """SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo) — ORBmatcher.cc:657-823.
+        kf* = (kps_un, u_right, desc, has_mappoint); fv* = CSR FeatureVector; epipole = (ex, ey) of KF1's centre in
+        image 2 (:663-670).  Returns (vMatchedPairs [m,2], matches12 [n1], count)."""
+        a, k1 = make_keyframe_view(*kf1)
+        b, k2 = make_keyframe_view(*kf2)
+        f1, k3 = make_feature_vector(*fv1)
+        f2, k4 = make_feature_vector(*fv2)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        sc = np.ascontiguousarray(scale_factors2, np.float32)
+        s2 = np.ascontiguousarray(level_sigma2_2, np.float32)
+        m12 = np.full(a.n, -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_match_triangulation(self.ctx.handle, C.byref(a), C.byref(f1), C.byref(b), C.byref(f2),
+                                                          _ptr(F), C.c_float(epipole[0]), C.c_float(epipole[1]), _ptr(sc),
+                                                          _ptr(s2), len(sc), int(bOnlyStereo),
+                                                          int(self.mbCheckOrientation), self.TH_LOW, _ptr(m12), C.byref(nm)))
+        idx = np.nonzero(m12 >= 0)[0]
+        return np.stack([idx, m12[idx]], 1).astype(np.int64), m12, nm.value
 
 
 def hamming_knn2(ctx: Context, q: np.ndarray, t: np.ndarray):

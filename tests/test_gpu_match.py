@@ -118,3 +118,22 @@ def test_empty_inputs(matcher):
     empty = FrameData(np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8), None, (0, 0, 640, 480))
     a, nm = matcher.SearchByProjectionLastFrame(empty, g["queries"], g["desc_last"])
     assert nm == 0 and len(a) == 0
+
+
+@pytest.mark.parametrize("name", golden_names("triang_"))
+def test_search_for_triangulation_vs_golden_and_oracle(orc, name):
+    from psl_slam_b200 import ORBmatcher
+    g = load_golden(name)
+    kf1 = (g["kps1"], g["ur1"], g["desc1"], g["has_mp1"])
+    kf2 = (g["kps2"], g["ur2"], g["desc2"], g["has_mp2"])
+    fv1, fv2 = (g["nodes1"], g["offs1"], g["idx1"]), (g["nodes2"], g["offs2"], g["idx2"])
+    m = ORBmatcher(0.6, True)
+    pairs, m12, nm = m.SearchForTriangulation(kf1, fv1, kf2, fv2, g["F12"], (float(g["ex"]), float(g["ey"])), g["scale"],
+                                              g["sigma2"], bool(g["only_stereo"]))
+    assert np.array_equal(m12, g["matches12"]) and nm == int(g["nmatches"]) and len(pairs) == nm
+    # without the rotation check, and with a shifted epipole: against the oracle
+    m2 = ORBmatcher(0.6, False)
+    for ex, ey, only in ((float(g["ex"]), float(g["ey"]), False), (320.0, 240.0, False), (100.0, 50.0, True)):
+        want, wn = orc.match_triangulation(kf1, fv1, kf2, fv2, g["F12"], ex, ey, g["scale"], g["sigma2"], only, False, 50)
+        _, got, gn = m2.SearchForTriangulation(kf1, fv1, kf2, fv2, g["F12"], (ex, ey), g["scale"], g["sigma2"], only)
+        assert np.array_equal(got, want) and gn == wn

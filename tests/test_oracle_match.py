@@ -58,3 +58,13 @@ def test_empty_inputs(orc):
     a, n = orc.match_projection(g["kps_cur"][:0], None, g["desc_cur"][:0], g["bounds"], g["queries"], g["desc_last"],
                                 None, 0)
     assert n == 0 and len(a) == 0
+
+
+@pytest.mark.parametrize("name", golden_names("triang_"))
+def test_search_for_triangulation(orc, name):
+    g = load_golden(name)
+    m12, nm = orc.match_triangulation((g["kps1"], g["ur1"], g["desc1"], g["has_mp1"]), (g["nodes1"], g["offs1"], g["idx1"]),
+                                      (g["kps2"], g["ur2"], g["desc2"], g["has_mp2"]), (g["nodes2"], g["offs2"], g["idx2"]),
+                                      g["F12"], float(g["ex"]), float(g["ey"]), g["scale"], g["sigma2"],
+                                      bool(g["only_stereo"]), True, 50)
+    assert np.array_equal(m12, g["matches12"]) and nm == int(g["nmatches"]) and nm > 20
