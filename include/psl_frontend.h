@@ -261,6 +261,28 @@ int psl_match_triangulation(psl_ctx* ctx, const psl_keyframe_view* kf1, const ps
                             int32_t only_stereo, int32_t check_orientation, int32_t th_low, int32_t* matches12,
                             int32_t* nmatches);
 
+/* One MapPoint projected into a KeyFrame by ORBmatcher::Fuse before its window search (ORBmatcher.cc:846-892):
+ * the caller keeps the MapPoint tests (isBad, IsInKeyFrame, depth, IsInImage, distance invariance, viewing angle)
+ * and PredictScale; flags = PSL_Q_VALID when all passed. */
+typedef struct psl_fuse_query {
+  float u, v;          /* projection */
+  float u_right;       /* u - bf * invz */
+  float radius;        /* th * mvScaleFactors[nPredictedLevel] */
+  int32_t pred_level;  /* nPredictedLevel */
+  uint32_t flags;
+} psl_fuse_query;
+
+/* The matching part of ORBmatcher::Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:825-981; "next" row N1, called by
+ * LocalMapping::SearchInNeighbors, LocalMapping.cc:796,821): per MapPoint the keypoint of KeyFrame::GetFeaturesInArea
+ * (KeyFrame.cc:685-724, no level gate) with the smallest Hamming distance among those at level pred-1..pred whose
+ * reprojection error passes the chi-square gate (7.8 stereo / 5.99 mono, :906-931); earliest candidate wins ties.
+ * best_idx[nq] = keypoint index if that distance <= th_low (TH_LOW = 50), else -1; best_dist[nq] (may be NULL).
+ * The replace-or-add bookkeeping on the MapPoint objects (:953-975) stays with the caller; every query is
+ * independent.  inv_level_sigma2: pKF->mvInvLevelSigma2 (nlevels entries). */
+int psl_match_fuse(psl_ctx* ctx, const psl_frame_view* kf, const psl_fuse_query* queries, const uint8_t* query_desc,
+                   int32_t nq, const float* inv_level_sigma2, int32_t nlevels, int32_t th_low, int32_t* best_idx,
+                   int32_t* best_dist);
+
 /* ------------------------------------------------------------------------------------------------
  * Line matching (add_src/LSDmatcher.cpp, add_src/InsectlineMatch.cpp).  As for points, MapLine / InsectLine
  * objects stay with the caller; plain arrays cross the boundary.  All pointers HOST.

@@ -290,4 +290,40 @@ int orc_match_triangulation(const psl_keyframe_view* kf1, const psl_feature_vect
   return 0;
 }
 
+
+// the window search of ORBmatcher::Fuse, ORBmatcher.cc:893-950 (KeyFrame::GetFeaturesInArea = the Frame version
+// without a level gate, KeyFrame.cc:685-724)
+int orc_match_fuse(const psl_frame_view* kf, const psl_fuse_query* qs, const uint8_t* qdesc, int nq,
+                   const float* inv_level_sigma2, int th_low, int32_t* best_idx, int32_t* best_dist) {
+  Grid g(*kf);
+  std::vector<int> cand;
+  for (int q = 0; q < nq; ++q) {
+    best_idx[q] = -1;
+    if (best_dist) best_dist[q] = 256;
+    const psl_fuse_query& Q = qs[q];
+    if (!(Q.flags & PSL_Q_VALID)) continue;
+    features_in_area(*kf, g, Q.u, Q.v, Q.radius, -1, -1, cand);
+    int bestDist = 256, bestIdx = -1;
+    for (int idx : cand) {
+      const psl_keypoint& kp = kf->kps_un[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < Q.pred_level - 1 || kpLevel > Q.pred_level) continue;
+      const float ex = Q.u - kp.x, ey = Q.v - kp.y;
+      if (kf->u_right && kf->u_right[idx] >= 0) {
+        const float er = Q.u_right - kf->u_right[idx];
+        const float e2 = ex * ex + ey * ey + er * er;
+        if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+      } else {
+        const float e2 = ex * ex + ey * ey;
+        if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+      }
+      const int dist = desc_dist(qdesc + 32 * (size_t)q, kf->desc + 32 * (size_t)idx);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    if (best_dist) best_dist[q] = bestDist;
+    if (bestDist <= th_low) best_idx[q] = bestIdx;
+  }
+  return 0;
+}
+
 }  // extern "C"

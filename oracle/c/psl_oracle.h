@@ -64,6 +64,9 @@ int orc_match_triangulation(const psl_keyframe_view* kf1, const psl_feature_vect
                             const float* scale_factors2, const float* level_sigma2_2, int only_stereo,
                             int check_orientation, int th_low, int32_t* matches12, int32_t* nmatches);
 
+int orc_match_fuse(const psl_frame_view* kf, const psl_fuse_query* qs, const uint8_t* qdesc, int nq,
+                   const float* inv_level_sigma2, int th_low, int32_t* best_idx, int32_t* best_dist);
+
 /* ---- Frame bookkeeping (orc_frame.cpp): Frame.cc:1342-1381, ORBmatcher.cc:1339-1393 ---- */
 void orc_stereo_from_rgbd(const psl_keypoint* kps, int n, const uint16_t* depth, int w, int h, int stride_px,
                           float depth_factor, float bf, float* u_right, float* z);

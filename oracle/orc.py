@@ -274,6 +274,18 @@ def match_triangulation(kf1, fv1, kf2, fv2, F12, ex, ey, scale2, sigma2, only_st
     return m12[: a.n].copy(), nm.value
 
 
+def match_fuse(kps_un, u_right, desc, bounds, queries, qdesc, inv_sigma2, th_low=50):
+    from psl_slam_b200._lib import FUSE_QUERY_DTYPE
+    fv, keep = make_frame_view(kps_un, u_right, desc, bounds)
+    queries = np.ascontiguousarray(queries, FUSE_QUERY_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    s2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    bi = np.zeros(max(len(queries), 1), np.int32)
+    bd = np.zeros(max(len(queries), 1), np.int32)
+    lib().orc_match_fuse(C.byref(fv), _p(queries), _p(qdesc), len(queries), _p(s2), th_low, _p(bi), _p(bd))
+    return bi[: len(queries)].copy(), bd[: len(queries)].copy()
+
+
 # ---- lines ------------------------------------------------------------------------------------------
 from psl_slam_b200._lib import KEYLINE_DTYPE  # noqa: E402  (ABI struct only)
 

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|line|linematch|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -178,6 +178,51 @@ def make_triangulation():
         print(f"triang_pair{case}: n {len(k1)}/{len(k2)} matches {nm}")
 
 
+def make_fuse():
+    """N1 fixture: the window search of ORBmatcher::Fuse — map points of a neighbour keyframe projected into a keyframe."""
+    from oracle import orc
+    from oracle.pyref import frame_py, match_py
+    from psl_slam_b200._lib import FUSE_QUERY_DTYPE
+    K = synth.ICL
+    gray, depth, T = synth.sequence(6, 4)
+    P = orb_cv2.OrbParams()
+    scale = np.array(P.scale, np.float32)
+    inv_sigma2 = (np.float32(1.0) / (scale * scale)).astype(np.float32)
+    bounds = (np.float32(0), np.float32(0), np.float32(640), np.float32(480))
+    rng = np.random.default_rng(41)
+    for case, (a, b) in enumerate([(0, 3), (2, 1)]):
+        ka, da = orc.orb_extract(gray[a])
+        kb, db = orc.orb_extract(gray[b])
+        xy = np.stack([ka["x"], ka["y"]], 1)
+        _, dep = frame_py.stereo_from_rgbd(xy, frame_py.depth_to_float(depth[a]), K["bf"])
+        world = frame_py.unproject(xy, dep, K, np.linalg.inv(T[a]))     # map points = keypoints of keyframe a
+        xyb = np.stack([kb["x"], kb["y"]], 1)
+        urb, _ = frame_py.stereo_from_rgbd(xyb, frame_py.depth_to_float(depth[b]), K["bf"])
+        urb = np.where(rng.random(len(urb)) < 0.6, urb, -1.0).astype(np.float32)
+        Tb = T[b].astype(np.float32)
+        q = np.zeros(len(ka), FUSE_QUERY_DTYPE)
+        for i in range(len(ka)):
+            if not np.isfinite(world[i]).all() or dep[i] <= 0:
+                continue
+            pc = (Tb[:3, :3].astype(np.float64) @ world[i] + Tb[:3, 3]).astype(np.float32)
+            if pc[2] < 0:
+                continue
+            invz = np.float32(1) / pc[2]
+            u = np.float32(np.float32(K["fx"]) * np.float32(pc[0] * invz) + np.float32(K["cx"]))
+            v = np.float32(np.float32(K["fy"]) * np.float32(pc[1] * invz) + np.float32(K["cy"]))
+            if not (0 <= u < 640 and 0 <= v < 480):
+                continue
+            lvl = int(np.clip(ka["octave"][i] + rng.integers(-1, 2), 0, 7))
+            q[i] = (u, v, np.float32(u - np.float32(K["bf"]) * invz), np.float32(3.0) * scale[lvl], lvl, 1)
+        kun = np.stack([kb["x"], kb["y"], kb["size"], kb["angle"], kb["response"]], 1).astype(np.float32)
+        fv = match_py.FrameView(kun, kb["octave"], urb, db, *bounds)
+        bi, bd = match_py.fuse_search(fv, q, da, inv_sigma2, 50)
+        np.savez_compressed(os.path.join(OUT, f"fuse_pair{case}.npz"), kps=kb, desc=db, u_right=urb,
+                            bounds=np.array(bounds, np.float32), queries=q, qdesc=da, inv_sigma2=inv_sigma2, best_idx=bi,
+                            best_dist=bd)
+        print(f"fuse_pair{case}: queries {int((q['flags'] & 1).sum())} fused {(bi >= 0).sum()}")
+
+
 def make_line():
     """cfg-3 shaped fixtures: LSD (real cv2) -> merge -> top-N -> LBD (real cv2 blur/Sobel) -> line equations."""
     from oracle.pyref import line_py
@@ -292,6 +337,8 @@ if __name__ == "__main__":
         make_match()
     if what in ("triang", "all"):
         make_triangulation()
+    if what in ("fuse", "all"):
+        make_fuse()
     if what in ("line", "all"):
         make_line()
     if what in ("linematch", "all"):

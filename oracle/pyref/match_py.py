@@ -247,3 +247,37 @@ def search_for_triangulation(kps1, ur1, desc1, has_mp1, fv1, kps2, ur2, desc2, h
                 m12[idx] = -1
                 nm -= 1
     return m12, nm
+
+
+def fuse_search(fv: FrameView, queries, qdesc, inv_sigma2, th_low=50):
+    """The window search of ORBmatcher::Fuse (src/ORBmatcher.cc:893-950).  queries: structured (u, v, u_right, radius,
+    pred_level, flags).  Returns (best_idx, best_dist)."""
+    nq = len(queries)
+    bi = np.full(nq, -1, np.int32)
+    bd = np.full(nq, 256, np.int32)
+    for q in range(nq):
+        Q = queries[q]
+        if not (Q["flags"] & 1):
+            continue
+        best, bidx = 256, -1
+        for i in fv.features_in_area(Q["u"], Q["v"], Q["radius"]):
+            lvl = int(fv.octave[i])
+            if lvl < Q["pred_level"] - 1 or lvl > Q["pred_level"]:
+                continue
+            ex, ey = F32(F32(Q["u"]) - fv.x[i]), F32(F32(Q["v"]) - fv.y[i])
+            if fv.u_right is not None and fv.u_right[i] >= 0:
+                er = F32(F32(Q["u_right"]) - fv.u_right[i])
+                e2 = F32(F32(F32(ex * ex) + F32(ey * ey)) + F32(er * er))
+                if float(F32(e2 * F32(inv_sigma2[lvl]))) > 7.8:
+                    continue
+            else:
+                e2 = F32(F32(ex * ex) + F32(ey * ey))
+                if float(F32(e2 * F32(inv_sigma2[lvl]))) > 5.99:
+                    continue
+            d = popcount_dist(qdesc[q], fv.desc[i])
+            if d < best:
+                best, bidx = d, i
+        bd[q] = best
+        if best <= th_low:
+            bi[q] = bidx
+    return bi, bd

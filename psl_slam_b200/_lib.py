@@ -43,6 +43,8 @@ QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("radius", "<f4"), ("min_lev
 LINE_QUERY_DTYPE = np.dtype([("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2", "<f4"), ("radius", "<f4"),
                              ("sx", "<f4"), ("sy", "<f4"), ("ex", "<f4"), ("ey", "<f4"), ("length", "<f4"),
                              ("normal", "<f8", (3,)), ("flags", "<u4"), ("pad_", "<u4")])  # psl_line_query, 72 B
+FUSE_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("u_right", "<f4"), ("radius", "<f4"), ("pred_level", "<i4"),
+                             ("flags", "<u4")])  # psl_fuse_query
 Q_VALID, Q_CLAIMS = 1, 2
 
 
@@ -137,7 +139,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
-           "psl_convert_rgbd_dev", "psl_match_triangulation"]
+           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse"]
 
 _lib = None
 
@@ -188,6 +190,7 @@ def lib():
         L.psl_convert_rgbd.argtypes = [_p, _p, _i, _i, _p, _p, _f, _p, _i, _i, _i]
         L.psl_convert_rgbd_dev.argtypes = [_p, _p, _i, _i, _i, _l, _p, _i, _l, _p, _i, _l, _f, _p, _i, _i, _i]
         L.psl_match_triangulation.argtypes = [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p, _p]
+        L.psl_match_fuse.argtypes = [_p, _p, _p, _p, _i, _p, _i, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

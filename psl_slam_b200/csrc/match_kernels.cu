@@ -569,4 +569,87 @@ void launch_triangulation(const psl_keypoint* kps1, const float* ur1, const uint
   if (check_ori && n1 > 0) triang_filter_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(kps1, kps2, n1, hist, m12, nmatches);
 }
 
+// ---------------------------------------------------------------------------------------------
+// The window search of ORBmatcher::Fuse (ORBmatcher.cc:893-950): warp per projected MapPoint, lanes over the
+// grid cells of KeyFrame::GetFeaturesInArea.  Queries are independent; best = smallest distance, earliest
+// candidate in the reference's enumeration (cell column-major, in-cell order) on ties ->
+// key = dist << 32 | cell rank << 16 | slot.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCandWarps * 32)
+    fuse_kernel(MatchFrames f, const psl_fuse_query* __restrict__ qs, const uint8_t* __restrict__ qdesc, int nq,
+                const int32_t* __restrict__ cell_start, const uint16_t* __restrict__ cell_items,
+                const float* __restrict__ inv_sigma2, int th_low, int32_t* __restrict__ best_idx,
+                int32_t* __restrict__ best_dist) {
+  const int lane = threadIdx.x & 31, qi = blockIdx.x * kCandWarps + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  const psl_fuse_query Q = qs[qi];
+  unsigned long long best = ~0ull;
+  if (Q.flags & PSL_Q_VALID) {
+    const float x = Q.u, y = Q.v, r = Q.radius;
+    const float dxm = __fsub_rn(x, f.min_x), dym = __fsub_rn(y, f.min_y);
+    const int c0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dxm, r), f.grid_w_inv)));
+    const int c1 = min(PSL_GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(dxm, r), f.grid_w_inv)));
+    const int r0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(dym, r), f.grid_h_inv)));
+    const int r1 = min(PSL_GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(dym, r), f.grid_h_inv)));
+    if (c0 < PSL_GRID_COLS && c1 >= 0 && r0 < PSL_GRID_ROWS && r1 >= 0) {
+      const uint4* qd = reinterpret_cast<const uint4*>(qdesc + (size_t)qi * 32);
+      const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+      const uint4* fdesc = reinterpret_cast<const uint4*>(f.desc);
+      const int ncy = r1 - r0 + 1, ncells = (c1 - c0 + 1) * ncy;
+      for (int c = lane; c < ncells; c += 32) {
+        const int ix = c0 + c / ncy, iy = r0 + c % ncy;
+        const int s = cell_start[ix * PSL_GRID_ROWS + iy], e = cell_start[ix * PSL_GRID_ROWS + iy + 1];
+        for (int k = s; k < e; ++k) {
+          const int i = cell_items[k];
+          const psl_keypoint kp = f.kps[i];
+          if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+          if (kp.octave < Q.pred_level - 1 || kp.octave > Q.pred_level) continue;
+          const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
+          const float kr = f.u_right ? f.u_right[i] : -1.f;
+          if (kr >= 0.f) {
+            const float er = __fsub_rn(Q.u_right, kr);
+            const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+            if ((double)__fmul_rn(e2, inv_sigma2[kp.octave]) > 7.8) continue;
+          } else {
+            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if ((double)__fmul_rn(e2, inv_sigma2[kp.octave]) > 5.99) continue;
+          }
+          const unsigned dist = (unsigned)hamming256(q0, q1, __ldg(fdesc + 2 * i), __ldg(fdesc + 2 * i + 1));
+          const unsigned long long key = ((unsigned long long)dist << 32) | ((unsigned long long)c << 16) | (unsigned)(k - s);
+          best = key < best ? key : best;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+        best = o < best ? o : best;
+      }
+      if (best != ~0ull) {
+        // recover the keypoint index from (cell rank, slot)
+        const int c = (int)((best >> 16) & 0xFFFFu), k = (int)(best & 0xFFFFu);
+        const int ix = c0 + c / ncy, iy = r0 + c % ncy;
+        const int i = cell_items[cell_start[ix * PSL_GRID_ROWS + iy] + k];
+        const int dist = (int)(best >> 32);
+        if (lane == 0) {
+          best_idx[qi] = dist <= th_low ? i : -1;
+          if (best_dist) best_dist[qi] = dist;
+        }
+        return;
+      }
+    }
+  }
+  if (lane == 0) {
+    best_idx[qi] = -1;
+    if (best_dist) best_dist[qi] = 256;
+  }
+}
+
+void launch_fuse(const MatchFrames& f, const psl_fuse_query* qs, const uint8_t* qdesc, int nq, const int32_t* cell_start,
+                 const uint16_t* cell_items, const float* inv_sigma2, int th_low, int32_t* best_idx, int32_t* best_dist,
+                 cudaStream_t st) {
+  if (nq <= 0) return;
+  fuse_kernel<<<(nq + kCandWarps - 1) / kCandWarps, kCandWarps * 32, 0, st>>>(f, qs, qdesc, nq, cell_start, cell_items,
+                                                                             inv_sigma2, th_low, best_idx, best_dist);
+}
+
 }  // namespace psl

@@ -49,6 +49,11 @@ void launch_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf
                 int32_t* match_f, int32_t* hist /*[32]*/, uint32_t* accepted, int32_t* n_accepted, int32_t* nmatches,
                 cudaStream_t st);
 
+// the window search of ORBmatcher::Fuse for one keyframe (f: B = 1 views; grid from launch_grid_build)
+void launch_fuse(const MatchFrames& f, const psl_fuse_query* qs, const uint8_t* qdesc, int nq, const int32_t* cell_start,
+                 const uint16_t* cell_items, const float* inv_sigma2, int th_low, int32_t* best_idx, int32_t* best_dist,
+                 cudaStream_t st);
+
 // SearchForTriangulation: candidate scan per vocabulary-node pair + rotation filter.  hist: int32[33] (30 bins used, [32] = nmatches)
 void launch_triangulation(const psl_keypoint* kps1, const float* ur1, const uint8_t* desc1, const uint8_t* mp1,
                           const int32_t* offs1, const uint32_t* idx1, int n1, const psl_keypoint* kps2, const float* ur2,

@@ -216,4 +216,50 @@ int psl_match_triangulation(psl_ctx* ctx, const psl_keyframe_view* kf1, const ps
   return check_status(ctx);
 }
 
+
+int psl_match_fuse(psl_ctx* ctx, const psl_frame_view* kf, const psl_fuse_query* queries, const uint8_t* query_desc,
+                   int32_t nq, const float* inv_level_sigma2, int32_t nlevels, int32_t th_low, int32_t* best_idx,
+                   int32_t* best_dist) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!kf || nq < 0 || kf->n < 0 || kf->n > 65535 || nlevels < 1 || nlevels > kMaxLevels || !inv_level_sigma2 ||
+      (kf->n > 0 && (!kf->kps_un || !kf->desc)) || (nq > 0 && (!queries || !query_desc || !best_idx)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (nq == 0) return PSL_OK;
+  const int n = kf->n;
+  if (n == 0) {
+    for (int i = 0; i < nq; ++i) { best_idx[i] = -1; if (best_dist) best_dist[i] = 256; }
+    return PSL_OK;
+  }
+  for (int i = 0; i < n; ++i)
+    if (kf->kps_un[i].octave < 0 || kf->kps_un[i].octave >= nlevels) return fail(ctx, PSL_E_INVALID, "octave out of range");
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  DevBuf* M = ctx->m_misc;
+  PSL_UP(ctx->m_kps, kf->kps_un, (size_t)n * sizeof(psl_keypoint));
+  if (kf->u_right) PSL_UP(ctx->m_ur, kf->u_right, (size_t)n * 4);
+  PSL_UP(ctx->m_desc, kf->desc, (size_t)n * 32);
+  PSL_UP(M[0], queries, (size_t)nq * sizeof(psl_fuse_query));
+  PSL_UP(ctx->m_qdesc, query_desc, (size_t)nq * 32);
+  float tab[kMaxLevels] = {0};
+  std::memcpy(tab, inv_level_sigma2, (size_t)nlevels * 4);
+  PSL_UP(M[1], tab, sizeof(tab));
+  const int32_t nn[1] = {n};
+  PSL_UP(ctx->m_n, nn, sizeof(nn));
+  int rc;
+  if ((rc = ensure(ctx, ctx->m_cell_start, (size_t)(kGridCells + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_cell_items, (size_t)n * 2))) return rc;
+  if ((rc = ensure(ctx, ctx->m_assign, (size_t)nq * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->m_nm, (size_t)nq * 4))) return rc;
+  MatchFrames F{ctx->m_kps.as<psl_keypoint>(), kf->u_right ? ctx->m_ur.as<float>() : nullptr, ctx->m_desc.as<uint8_t>(),
+                ctx->m_n.as<int32_t>(), n, kf->min_x, kf->min_y, kf->grid_w_inv, kf->grid_h_inv};
+  launch_grid_build(F, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(), 1, ctx->stream);
+  launch_fuse(F, M[0].as<psl_fuse_query>(), ctx->m_qdesc.as<uint8_t>(), nq, ctx->m_cell_start.as<int32_t>(),
+              ctx->m_cell_items.as<uint16_t>(), M[1].as<float>(), th_low, ctx->m_assign.as<int32_t>(),
+              ctx->m_nm.as<int32_t>(), ctx->stream);
+  prof_span(ctx, 5, prof_mark(ctx), 2);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(best_idx, ctx->m_assign.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (best_dist) PSL_CK(cudaMemcpyAsync(best_dist, ctx->m_nm.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
 }  // extern "C"

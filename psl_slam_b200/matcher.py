@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view, make_keyframe_view
+from ._lib import FUSE_QUERY_DTYPE, KP_DTYPE, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view, make_keyframe_view
 from .orb import Context, _ptr
 
 
@@ -109,6 +109,20 @@ class ORBmatcher:
                                                           int(self.mbCheckOrientation), self.TH_LOW, _ptr(m12), C.byref(nm)))
         idx = np.nonzero(m12 >= 0)[0]
         return np.stack([idx, m12[idx]], 1).astype(np.int64), m12, nm.value
+
+
+    def FuseSearch(self, kf: FrameData, queries, mp_desc, inv_level_sigma2):
+        """The window search of Fuse(pKF, vpMapPoints, th) — ORBmatcher.cc:893-950.  Returns (best_idx [nq] = keypoint
+        to fuse with or -1, best_dist [nq]); the replace-or-add bookkeeping (:953-975) is the caller's."""
+        fv, keep = make_frame_view(kf.kps_un, kf.u_right, kf.desc, kf.bounds)
+        queries = np.ascontiguousarray(queries, FUSE_QUERY_DTYPE)
+        qd = np.ascontiguousarray(mp_desc, np.uint8)
+        s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        bi = np.full(len(queries), -1, np.int32)
+        bd = np.full(len(queries), 256, np.int32)
+        self.ctx.check(_lib.lib().psl_match_fuse(self.ctx.handle, C.byref(fv), _ptr(queries), _ptr(qd), len(queries),
+                                                 _ptr(s2), len(s2), self.TH_LOW, _ptr(bi), _ptr(bd)))
+        return bi, bd
 
 
 def hamming_knn2(ctx: Context, q: np.ndarray, t: np.ndarray):

@@ -137,3 +137,19 @@ def test_search_for_triangulation_vs_golden_and_oracle(orc, name):
         want, wn = orc.match_triangulation(kf1, fv1, kf2, fv2, g["F12"], ex, ey, g["scale"], g["sigma2"], only, False, 50)
         _, got, gn = m2.SearchForTriangulation(kf1, fv1, kf2, fv2, g["F12"], (ex, ey), g["scale"], g["sigma2"], only)
         assert np.array_equal(got, want) and gn == wn
+
+
+@pytest.mark.parametrize("name", golden_names("fuse_"))
+def test_fuse_search_vs_golden_and_oracle(orc, name):
+    from psl_slam_b200 import FrameData, ORBmatcher
+    g = load_golden(name)
+    m = ORBmatcher()
+    bi, bd = m.FuseSearch(FrameData(g["kps"], g["desc"], g["u_right"], tuple(g["bounds"])), g["queries"], g["qdesc"],
+                          g["inv_sigma2"])
+    assert np.array_equal(bi, g["best_idx"]) and np.array_equal(bd, g["best_dist"])
+    # mono keyframe (no right coordinates) and wider windows: against the oracle
+    q = g["queries"].copy()
+    q["radius"] *= 3
+    want_i, want_d = orc.match_fuse(g["kps"], None, g["desc"], tuple(g["bounds"]), q, g["qdesc"], g["inv_sigma2"], 50)
+    bi, bd = m.FuseSearch(FrameData(g["kps"], g["desc"], None, tuple(g["bounds"])), q, g["qdesc"], g["inv_sigma2"])
+    assert np.array_equal(bi, want_i) and np.array_equal(bd, want_d)

@@ -68,3 +68,10 @@ def test_search_for_triangulation(orc, name):
                                       g["F12"], float(g["ex"]), float(g["ey"]), g["scale"], g["sigma2"],
                                       bool(g["only_stereo"]), True, 50)
     assert np.array_equal(m12, g["matches12"]) and nm == int(g["nmatches"]) and nm > 20
+
+
+@pytest.mark.parametrize("name", golden_names("fuse_"))
+def test_fuse_search(orc, name):
+    g = load_golden(name)
+    bi, bd = orc.match_fuse(g["kps"], g["u_right"], g["desc"], tuple(g["bounds"]), g["queries"], g["qdesc"], g["inv_sigma2"], 50)
+    assert np.array_equal(bi, g["best_idx"]) and np.array_equal(bd, g["best_dist"]) and (bi >= 0).sum() > 100
