@@ -316,6 +316,14 @@ int psl_line_frame_bf_match(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, cons
 int psl_line_search_double(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const uint8_t* desc2, int32_t n2,
                            float nn_ratio, float th, int32_t* matches12, int32_t* nmatches);
 
+/* LSDmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs) (LSDmatcher.cpp:705-741, TH_LOW, mutual; called by
+ * LocalMapping::CreateNewMapLines2, LocalMapping.cc:580) and its vector form (:743-779: TH_HIGH, mutual check only
+ * when is_double): FrameBFMatch in both directions, then drop pairs where either line already has a MapLine
+ * (has_mapline1 / has_mapline2).  matches12[n1] = line of KF2 or -1; *nmatches = return value. */
+int psl_line_search_triangulation(psl_ctx* ctx, const uint8_t* desc1, const uint8_t* has_mapline1, int32_t n1,
+                                  const uint8_t* desc2, const uint8_t* has_mapline2, int32_t n2, float nn_ratio, float th,
+                                  int32_t is_double, int32_t* matches12, int32_t* nmatches);
+
 /* What LSDmatcher::SearchByProjection reads from the searched Frame (include/Frame.h): mvKeylinesUn, mLdesc,
  * mvKeyLineFunctions, mvLines3D (first/second endpoints, n x 6 doubles; only the map-line form needs it) and the
  * bounds of the 64x48 line grid (Frame::AssignFeaturesToGridForLine, Frame.cc:286-309; rebuilt by the library). */

@@ -229,6 +229,27 @@ int orc_line_search_double(const uint8_t* desc1, int n1, const uint8_t* desc2, i
   return nm;
 }
 
+// LSDmatcher::SearchForTriangulation, LSDmatcher.cpp:705-779 (pairs form: th = TH_LOW, is_double = 1)
+int orc_line_search_triangulation(const uint8_t* desc1, const uint8_t* has_ml1, int n1, const uint8_t* desc2,
+                                  const uint8_t* has_ml2, int n2, float nn_ratio, float th, int is_double,
+                                  int32_t* matches12) {
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<int32_t> m12(n1), m21(n2);
+  orc_line_frame_bf_match(desc1, n1, desc2, n2, nn_ratio, th, m12.data());
+  orc_line_frame_bf_match(desc2, n2, desc1, n1, nn_ratio, th, m21.data());
+  int nm = 0;
+  for (int i = 0; i < n1; ++i) {
+    const int j = m12[i];
+    if (j < 0) continue;
+    if (is_double && m21[j] != i) continue;
+    if (has_ml1[i] || has_ml2[j]) continue;
+    matches12[i] = j;
+    ++nm;
+  }
+  return nm;
+}
+
 int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,
                               const uint8_t* claimed_in, int mode, float nn_ratio, int32_t* assign) {
   LineGrid g(*f);

@@ -437,3 +437,11 @@ def plane_assoc(planes_cam, pts, Tcw, map_planes, map_bad, d_th, a_th, mode):
                               None if map_bad is None else _p(map_bad), len(map_planes), C.c_float(d_th),
                               C.c_float(a_th), mode, _p(out))
     return out[: len(planes_cam)].copy(), int(n)
+
+
+def line_search_triangulation(d1, ml1, d2, ml2, nn_ratio, th, is_double):
+    d1, d2, ml1, ml2 = _u8(d1), _u8(d2), _u8(ml1), _u8(ml2)
+    out = np.zeros(max(len(d1), 1), np.int32)
+    n = lib().orc_line_search_triangulation(_p(d1), _p(ml1), len(d1), _p(d2), _p(ml2), len(d2), C.c_float(nn_ratio),
+                                            C.c_float(th), int(is_double), _p(out))
+    return out[: len(d1)].copy(), int(n)

@@ -139,7 +139,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
-           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse"]
+           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation"]
 
 _lib = None
 
@@ -191,6 +191,7 @@ def lib():
         L.psl_convert_rgbd_dev.argtypes = [_p, _p, _i, _i, _i, _l, _p, _i, _l, _p, _i, _l, _f, _p, _i, _i, _i]
         L.psl_match_triangulation.argtypes = [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p, _p]
         L.psl_match_fuse.argtypes = [_p, _p, _p, _p, _i, _p, _i, _i, _p, _p]
+        L.psl_line_search_triangulation.argtypes = [_p, _p, _p, _i, _p, _p, _i, _f, _f, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

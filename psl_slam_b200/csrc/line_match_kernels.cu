@@ -171,6 +171,26 @@ __global__ void line_mutual_kernel(LineSet A, const int32_t* __restrict__ m21, i
   else atomicAdd(nmatches + b, 1);
 }
 
+// LSDmatcher::SearchForTriangulation (LSDmatcher.cpp:721-737, 759-775): mutual check (optional) + MapLine gates
+__global__ void line_triang_kernel(LineSet A, const int32_t* __restrict__ m21, int cap2, const uint8_t* __restrict__ ml1,
+                                   const uint8_t* __restrict__ ml2, int is_double, int32_t* __restrict__ m12,
+                                   int32_t* __restrict__ nmatches) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n[b]) return;
+  const int j = m12[(size_t)b * A.cap + i];
+  if (j < 0) return;
+  const bool drop = (is_double && m21[(size_t)b * cap2 + j] != i) || ml1[(size_t)b * A.cap + i] || ml2[(size_t)b * cap2 + j];
+  if (drop) m12[(size_t)b * A.cap + i] = -1;
+  else atomicAdd(nmatches + b, 1);
+}
+
+void launch_line_triang(const LineSet& A, const int32_t* m21, int cap2, const uint8_t* ml1, const uint8_t* ml2,
+                        int is_double, int32_t* m12, int32_t* nmatches, int B, cudaStream_t st) {
+  cudaMemsetAsync(nmatches, 0, (size_t)B * sizeof(int32_t), st);
+  dim3 grid((A.cap + 127) / 128, B);
+  line_triang_kernel<<<grid, 128, 0, st>>>(A, m21, cap2, ml1, ml2, is_double, m12, nmatches);
+}
+
 void launch_line_mutual(const LineSet& A, const int32_t* m21, int cap2, int32_t* m12, int32_t* nmatches, int B,
                         cudaStream_t st) {
   cudaMemsetAsync(nmatches, 0, (size_t)B * sizeof(int32_t), st);

@@ -24,6 +24,8 @@ void launch_line_bfmatch(const LineSet& Q, const LineSet& T, const uint2* knn, f
                          int32_t* matches, int B, cudaStream_t st);
 void launch_line_mutual(const LineSet& A, const int32_t* m21, int cap2, int32_t* m12, int32_t* nmatches, int B,
                         cudaStream_t st);
+void launch_line_triang(const LineSet& A, const int32_t* m21, int cap2, const uint8_t* ml1, const uint8_t* ml2,
+                        int is_double, int32_t* m12, int32_t* nmatches, int B, cudaStream_t st);
 // 3 launches: line grid cells, static keys, ordered resolve
 void launch_line_projection(const LineSet& F, const double* lineeq, const double* lines3d, const psl_line_query* queries,
                             const uint8_t* qdesc, const int32_t* nq, int qcap, int max_nq, float min_x, float min_y,

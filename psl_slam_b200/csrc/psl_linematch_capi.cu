@@ -143,6 +143,43 @@ int psl_line_search_double(psl_ctx* ctx, const uint8_t* desc1, int32_t n1, const
   return check_status(ctx);
 }
 
+int psl_line_search_triangulation(psl_ctx* ctx, const uint8_t* desc1, const uint8_t* has_mapline1, int32_t n1,
+                                  const uint8_t* desc2, const uint8_t* has_mapline2, int32_t n2, float nn_ratio, float th,
+                                  int32_t is_double, int32_t* matches12, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (bad_desc_args(desc1, n1, desc2, n2) || !nmatches || (n1 > 0 && (!matches12 || !has_mapline1)) || (n2 > 0 && !has_mapline2))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  if (n1 == 0) return PSL_OK;
+  if (n2 == 0) {  // LSDmatcher.cpp:714-715
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    return PSL_OK;
+  }
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  LineSet A, T;
+  int rc = stage_desc_pair(ctx, desc1, n1, desc2, n2, A, T);
+  if (rc) return rc;
+  PSL_UP(ctx->m_misc[0], has_mapline1, (size_t)n1);
+  PSL_UP(ctx->m_misc[1], has_mapline2, (size_t)n2);
+  PSL_ENS(ctx->m_best, (size_t)n1 * 8);
+  PSL_ENS(ctx->m_cand_count, (size_t)n2 * 8);
+  PSL_ENS(ctx->m_assign, (size_t)n1 * 4);
+  PSL_ENS(ctx->m_accepted, (size_t)n2 * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  cudaStream_t st = ctx->stream;
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(A, T, ctx->m_best.as<uint2>(), 1, st);
+  launch_line_bfmatch(A, T, ctx->m_best.as<uint2>(), nn_ratio, th, ctx->m_assign.as<int32_t>(), 1, st);
+  launch_line_knn2(T, A, ctx->m_cand_count.as<uint2>(), 1, st);
+  launch_line_bfmatch(T, A, ctx->m_cand_count.as<uint2>(), nn_ratio, th, ctx->m_accepted.as<int32_t>(), 1, st);
+  launch_line_triang(A, ctx->m_accepted.as<int32_t>(), T.cap, ctx->m_misc[0].as<uint8_t>(), ctx->m_misc[1].as<uint8_t>(),
+                     is_double, ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, st);
+  prof_span(ctx, 15, e, 5);
+  PSL_CK(cudaMemcpyAsync(matches12, ctx->m_assign.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
 int psl_line_match_projection(psl_ctx* ctx, const psl_line_frame_view* fv, const psl_line_query* queries,
                               const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in, int32_t mode,
                               float nn_ratio, int32_t* assign, int32_t* nmatches) {

@@ -87,6 +87,19 @@ class LSDmatcher:
                                                          C.byref(nm)))
         return out, nm.value
 
+    def SearchForTriangulation(self, ldesc1, has_mapline1, ldesc2, has_mapline2, as_pairs=True, isDouble=False):
+        """SearchForTriangulation(pKF1, pKF2, vMatchedPairs) — LSDmatcher.cpp:705-741 (as_pairs: TH_LOW, mutual) and the
+        vector<int> form :743-779 (TH_HIGH, mutual only when isDouble).  Returns (matches12 [n1], count)."""
+        d1, d2, m1, m2 = _u8(ldesc1), _u8(ldesc2), _u8(has_mapline1), _u8(has_mapline2)
+        out = np.full(len(d1), -1, np.int32)
+        nm = C.c_int32()
+        th = self.TH_LOW if as_pairs else self.TH_HIGH
+        self.ctx.check(_lib.lib().psl_line_search_triangulation(self.ctx.handle, _ptr(d1), _ptr(m1), len(d1), _ptr(d2),
+                                                                _ptr(m2), len(d2), C.c_float(self.mfNNratio),
+                                                                C.c_float(th), int(as_pairs or isDouble), _ptr(out),
+                                                                C.byref(nm)))
+        return out, nm.value
+
     def _project(self, frame: LineFrameData, queries, qdesc, claimed, mode):
         fv, keep = make_line_frame_view(frame.kl_un, frame.ldesc, frame.lineeq, frame.lines3d, frame.bounds)
         queries = np.ascontiguousarray(queries, LINE_QUERY_DTYPE)

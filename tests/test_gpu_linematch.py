@@ -122,3 +122,17 @@ def test_plane_assoc_vs_golden_and_oracle(orc):
             want, wn = orc.plane_assoc(pc, pts, np.eye(4), mp, None, 1.5, 0.5, mode)
             got, gn = m.__class__(1.5, 0.5, ctx=m.ctx)._run(pc, pts, np.eye(4), mp, None, mode)
             assert np.array_equal(got, want) and gn == wn
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_line_search_triangulation_vs_oracle(orc, name):
+    from psl_slam_b200 import LSDmatcher
+    g = load_golden(name)
+    rng = np.random.default_rng(5)
+    ml1 = (rng.random(len(g["desc_last"])) < 0.3).astype(np.uint8)
+    ml2 = (rng.random(len(g["desc_cur"])) < 0.3).astype(np.uint8)
+    m = LSDmatcher(0.95)
+    for as_pairs, dbl, th in ((True, True, 50), (False, False, 80), (False, True, 80)):
+        want, wn = orc.line_search_triangulation(g["desc_last"], ml1, g["desc_cur"], ml2, 0.95, th, as_pairs or dbl)
+        got, gn = m.SearchForTriangulation(g["desc_last"], ml1, g["desc_cur"], ml2, as_pairs, dbl)
+        assert np.array_equal(got, want) and gn == wn

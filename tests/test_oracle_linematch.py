@@ -60,3 +60,22 @@ def test_degenerate_inputs(orc):
     assert orc.line_search_double(d, three, 0.95, 50)[1] == 0
     a, n = orc.plane_assoc(np.zeros((0, 4)), np.zeros((0, 15)), np.eye(4), np.zeros((3, 4)), None, 0.1, 0.86, 0)
     assert n == 0 and len(a) == 0
+
+
+@pytest.mark.parametrize("name", PAIRS)
+def test_line_search_triangulation(orc, name):
+    """SearchForTriangulation = the SearchDouble result (pinned above against cv2) minus pairs that already own a MapLine."""
+    g = load_golden(name)
+    rng = np.random.default_rng(5)
+    ml1 = (rng.random(len(g["desc_last"])) < 0.3).astype(np.uint8)
+    ml2 = (rng.random(len(g["desc_cur"])) < 0.3).astype(np.uint8)
+    m, n = orc.line_search_triangulation(g["desc_last"], ml1, g["desc_cur"], ml2, 0.95, 50, True)
+    want = g["dbl"].copy()
+    for i, j in enumerate(want):
+        if j >= 0 and (ml1[i] or ml2[j]):
+            want[i] = -1
+    assert np.array_equal(m, want) and n == int((want >= 0).sum())
+    m2, n2 = orc.line_search_triangulation(g["desc_last"], ml1, g["desc_cur"], ml2, 0.95, 80, False)
+    bf = orc.line_frame_bf_match(g["desc_last"], g["desc_cur"], 0.95, 80)
+    want2 = np.where((bf >= 0) & (ml1 == 0) & (ml2[np.maximum(bf, 0)] == 0), bf, -1)
+    assert np.array_equal(m2, want2) and n2 == int((want2 >= 0).sum())
