@@ -229,6 +229,9 @@ def main():
         raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from psl_slam_b200 import Context, ORBextractor, default_config
