@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpsl_frontend.so")
+SO_PATH = os.environ.get("PSL_FRONTEND_SO") or os.path.join(_HERE, "libpsl_frontend.so")  # override: development A/B builds
 
 PSL_OK, PSL_E_INVALID, PSL_E_CUDA, PSL_E_CAPACITY, PSL_E_INTERNAL = 0, -1, -2, -3, -4
 

@@ -643,7 +643,10 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
 
 constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never synchronise with each other)
 
-__global__ void __launch_bounds__(kCoreWarps * 32, 7)
+#ifndef PSL_LSD_MINB
+#define PSL_LSD_MINB 7
+#endif
+__global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
     lsd_core_kernel(LineBuffers L, int nb, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
   __shared__ double terms[kCoreWarps][96];

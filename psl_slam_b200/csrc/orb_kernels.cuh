@@ -13,10 +13,25 @@ struct ResizeTables {
 // K1: level l from level l-1 (ORBextractor.cc:1120)
 void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTables& t, int B, cudaStream_t st);
 
-// K2: per-cell FAST + NMS + threshold fallback + ordered compaction (ORBextractor.cc:789-829)
+// Dense FAST path: the host side of its lookup tables (OrbGeometry::fast_tab) and of the TMA descriptors the
+// score kernel stages its pixel tiles with (one 3-D u8 tensor [frames][h][pitch] per level).
+struct alignas(64) FastMaps {
+  unsigned char m[kMaxLevels][128];  // CUtensorMap, opaque here
+  uint32_t valid;                    // bit l: level l has a descriptor
+};
+int fast_tile_count(const OrbGeometry& geo);                       // tiles per frame
+void fast_build_tab(const OrbGeometry& geo, uint32_t* host_tab);   // n_tiles + total_cells words
+// descriptor of one level; false when the layout cannot be described (base or strides not 16-byte aligned)
+bool fast_encode_map(FastMaps& maps, int level, const void* ptr, int w, int h, int pitch, int64_t frame_stride,
+                     int frames);
+constexpr int kFastLaunches = 4;  // memset + score tiles + collect + per-cell fallback
+
+// K2: per-cell FAST + NMS + threshold fallback + ordered compaction (ORBextractor.cc:789-829).
+// fb_list: [B * total_cells] u32 scratch (cells to redo at minThFAST), fb_count: one u32.
+// maps: descriptors of levels >= 1 (level 0 is encoded here from in0).
 void launch_fast_cells(const OrbGeometry* d_geo, const OrbGeometry& geo, ImgBatch in0, int ini_th, int min_th,
-                       uint32_t* pool, int pool_cap, uint32_t* pool_count, uint2* cell_tab, uint32_t* status, int B,
-                       cudaStream_t st);
+                       uint32_t* pool, int pool_cap, uint32_t* pool_count, uint2* cell_tab, uint32_t* fb_list,
+                       uint32_t* fb_count, FastMaps& maps, uint32_t* status, int B, cudaStream_t st);
 
 // K3: DistributeOctTree per (frame, level) (ORBextractor.cc:539-763)
 void launch_octree(const OrbGeometry* d_geo, const OrbGeometry& geo, const uint32_t* pool, int pool_cap,

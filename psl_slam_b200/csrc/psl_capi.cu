@@ -84,6 +84,8 @@ static void free_geometry(psl_ctx* c) {
   cudaFree(c->d_pool); c->d_pool = nullptr;
   cudaFree(c->d_pool_count); c->d_pool_count = nullptr;
   cudaFree(c->d_cell_tab); c->d_cell_tab = nullptr;
+  cudaFree(c->d_fb_list); c->d_fb_list = nullptr;
+  cudaFree(c->d_fast_tab); c->d_fast_tab = nullptr;
   cudaFree(c->d_key_scratch); c->d_key_scratch = nullptr;
   cudaFree(c->d_node_scratch); c->d_node_scratch = nullptr;
   cudaFree(c->d_sel); c->d_sel = nullptr;
@@ -170,12 +172,25 @@ static int set_geometry(psl_ctx* ctx, int w, int h) {
   PSL_CK(cudaMalloc(&ctx->d_pool, C * P * sizeof(uint32_t)));
   PSL_CK(cudaMalloc(&ctx->d_pool_count, C * sizeof(uint32_t)));
   PSL_CK(cudaMalloc(&ctx->d_cell_tab, C * cells * sizeof(uint2)));
+  PSL_CK(cudaMalloc(&ctx->d_fb_list, (C * cells + 1) * sizeof(uint32_t)));
   PSL_CK(cudaMalloc(&ctx->d_key_scratch, C * 2 * P * sizeof(uint32_t)));
   PSL_CK(cudaMalloc(&ctx->d_node_scratch, C * 2 * P * sizeof(uint16_t)));
   PSL_CK(cudaMalloc(&ctx->d_sel, C * sel * sizeof(uint32_t)));
   PSL_CK(cudaMalloc(&ctx->d_sel_count, C * L * sizeof(int32_t)));
+  // dense FAST path: tile / cell lookup tables and the TMA descriptors of our own levels
+  g.n_tiles = fast_tile_count(g);
+  std::vector<uint32_t> ftab((size_t)g.n_tiles + cells);
+  fast_build_tab(g, ftab.data());
+  PSL_CK(cudaMalloc(&ctx->d_fast_tab, ftab.size() * sizeof(uint32_t)));
+  PSL_CK(cudaMemcpyAsync(ctx->d_fast_tab, ftab.data(), ftab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                         ctx->stream));
+  g.fast_tab = ctx->d_fast_tab;
+  ctx->fast_maps.valid = 0;
+  for (int l = 1; l < L; ++l)
+    fast_encode_map(ctx->fast_maps, l, g.level[l].ptr, g.level[l].w, g.level[l].h, g.level[l].pitch,
+                    g.level[l].frame_stride, ctx->chunk);
   PSL_CK(cudaMemcpyAsync(ctx->d_geo, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
-  PSL_CK(cudaStreamSynchronize(ctx->stream));  // `all` and `g` are host temporaries
+  PSL_CK(cudaStreamSynchronize(ctx->stream));  // `all`, `ftab` and `g` are host temporaries
   ctx->geo_w = w;
   ctx->geo_h = h;
   return PSL_OK;
@@ -196,8 +211,9 @@ static int run_chunk(psl_ctx* ctx, ImgBatch in0, int nb, psl_keypoint* d_kps, ui
   prof_span(ctx, 0, e, g.nlevels - 1);
   e = prof_mark(ctx);
   launch_fast_cells(ctx->d_geo, g, in0, ctx->cfg.orb_ini_th_fast, ctx->cfg.orb_min_th_fast, ctx->d_pool,
-                    ctx->pool_cap, ctx->d_pool_count, ctx->d_cell_tab, ctx->d_status, nb, st);
-  prof_span(ctx, 1, e, 1);
+                    ctx->pool_cap, ctx->d_pool_count, ctx->d_cell_tab, ctx->d_fb_list,
+                    ctx->d_fb_list + (size_t)ctx->chunk * g.total_cells, ctx->fast_maps, ctx->d_status, nb, st);
+  prof_span(ctx, 1, e, kFastLaunches);
   e = prof_mark(ctx);
   launch_octree(ctx->d_geo, g, ctx->d_pool, ctx->pool_cap, ctx->d_cell_tab, ctx->d_key_scratch, ctx->d_node_scratch,
                 ctx->d_sel, ctx->d_sel_count, ctx->d_status, nb, st);

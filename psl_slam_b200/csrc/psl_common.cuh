@@ -52,6 +52,10 @@ struct OrbGeometry {
   int32_t sel_off[kMaxLevels];  // offset of a level's selected list inside a frame's block
   float scale[kMaxLevels];      // mvScaleFactor
   float kp_size[kMaxLevels];    // (int)(31*scale)
+  // lookup tables of the dense FAST path (device memory): tile -> lvl<<24 | ty<<12 | tx for the n_tiles score
+  // tiles of a frame, then cell -> lvl<<24 | ci<<12 | cj for its total_cells cells
+  const uint32_t* fast_tab;
+  int32_t n_tiles;
 };
 
 // FAST candidate packing: x-16 (12 bit) | y-16 (12 bit) | score (8 bit)

@@ -36,6 +36,9 @@ struct psl_ctx {
   uint32_t* d_pool = nullptr;     // [chunk][pool_cap] FAST candidates
   uint32_t* d_pool_count = nullptr;
   uint2* d_cell_tab = nullptr;    // [chunk][total_cells] (offset,count)
+  uint32_t* d_fb_list = nullptr;  // [chunk * total_cells] cells to redo at minThFAST, + 1 counter at the end
+  uint32_t* d_fast_tab = nullptr; // OrbGeometry::fast_tab
+  psl::FastMaps fast_maps{};      // TMA descriptors of the pyramid levels
   uint32_t* d_key_scratch = nullptr;   // [chunk][2][pool_cap]
   uint16_t* d_node_scratch = nullptr;  // [chunk][2][pool_cap]
   uint32_t* d_sel = nullptr;      // [chunk][total_sel]

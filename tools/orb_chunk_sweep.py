@@ -4,7 +4,7 @@ from psl_slam_b200 import ORBextractor, synth
 F = 2048
 gray, _, _ = synth.sequence(4, 16)
 d = torch.from_numpy(gray).cuda()[torch.arange(F).cuda() % 16].contiguous()
-for chunk in (32, 64, 128, 256, 512, 1024):
+for chunk in ([int(a) for a in sys.argv[1:]] or (32, 64, 128, 256, 512, 1024)):
     ex = ORBextractor(chunk_frames=chunk)
     cap = ex.cap
     kps = torch.empty((F, cap, 28), dtype=torch.uint8, device='cuda'); desc = torch.empty((F, cap, 32), dtype=torch.uint8, device='cuda'); n = torch.zeros(F, dtype=torch.int32, device='cuda')
