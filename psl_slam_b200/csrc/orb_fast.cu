@@ -417,16 +417,20 @@ __global__ void __launch_bounds__(kScoreThreads)
 }
 
 constexpr int kCollectWarps = 8;
+constexpr int kCollectCap = (kInteriorMax * kInteriorMax + 3) / 4;  // NMS survivors of a cell: at most one per 2x2 block
 
-// A warp per cell.  The interior is read as whole words, `rows_per_it` rows per warp step (2 when a row has at
-// most 16 words); a lane always holds the same word column, so its byte mask is fixed.
+// A warp per cell, one pass: the interior is read as whole words, `rpi` rows per warp step (2 when a row has at
+// most 16 words; a lane always holds the same word column, so its byte mask is fixed), five steps in flight.
+// Corners go to a per-warp shared list in raster order (steps ascending, lanes ascending = row then word, bytes
+// ascending); the list is copied to the cell's slice of the pool once its length is known.
 __global__ void __launch_bounds__(kCollectWarps * 32)
     fast_collect_kernel(const OrbGeometry* __restrict__ geo, int redo_empty, uint32_t* __restrict__ pool, int pool_cap,
                         uint32_t* __restrict__ pool_count, uint2* __restrict__ cell_tab,
                         uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
                         uint32_t* __restrict__ status) {
-  const int lane = threadIdx.x & 31, b = blockIdx.y;
-  const int cell = blockIdx.x * kCollectWarps + (threadIdx.x >> 5);
+  __shared__ uint32_t s_out[kCollectWarps][kCollectCap];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, b = blockIdx.y;
+  const int cell = blockIdx.x * kCollectWarps + wid;
   const int cells = geo->total_cells;
   if (cell >= cells) return;
   const uint32_t ce = __ldg(geo->fast_tab + geo->n_tiles + cell);
@@ -450,15 +454,41 @@ __global__ void __launch_bounds__(kCollectWarps * 32)
   const uint32_t* __restrict__ col = reinterpret_cast<const uint32_t*>(
       geo->blur[lvl].ptr + (size_t)b * geo->blur[lvl].frame_stride + (size_t)(ya + sub) * mp) + w0 + min(wi, nw - 1);
   const int stride = rpi * (mp >> 2), nit = (ih + rpi - 1) / rpi;
-  int cnt = 0;
-  unsigned long long any = 0ull;  // bit it: warp step `it` holds a corner (nit <= 60)
-  for (int it = 0; it < nit; ++it) {
-    const uint32_t v = (it * rpi + sub < ih) ? (__ldg(col + (size_t)it * stride) & lmask) : 0u;
-    const uint32_t nz = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
-    cnt += __popc(nz);
-    if (__any_sync(0xffffffffu, nz != 0u)) any |= 1ull << it;
+  const uint32_t xy0 = pack_cand(4 * (w0 + wi) - kMinBorder, ya + sub - kMinBorder, 0);  // level coordinate - minBorder
+  uint32_t* list = s_out[wid];
+  int run = 0;
+  constexpr int kFlight = 5;
+  for (int it0 = 0; it0 < nit; it0 += kFlight) {
+    uint32_t v[kFlight];
+#pragma unroll
+    for (int k = 0; k < kFlight; ++k) {
+      const int it = it0 + k;
+      v[k] = (it * rpi + sub < ih) ? __ldg(col + (size_t)it * stride) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kFlight; ++k) {
+      const uint32_t vv = v[k] & lmask;
+      uint32_t nz = (((vv & 0x7f7f7f7fu) + 0x7f7f7f7fu) | vv) & 0x80808080u;
+      if (!__any_sync(0xffffffffu, nz != 0u)) continue;
+      const int c = __popc(nz);
+      int inc = c;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, inc, dlt);
+        if (lane >= dlt) inc += a;
+      }
+      int pos = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+      const uint32_t xy = xy0 + ((uint32_t)((it0 + k) * rpi) << 8);
+      while (nz) {
+        const int j = (__ffs(nz) - 1) >> 3;
+        nz &= nz - 1;
+        if (pos < kCollectCap) list[pos] = xy + ((uint32_t)j << 20) + ((vv >> (8 * j)) & 0xFFu);
+        ++pos;
+      }
+    }
   }
-  const int total = __reduce_add_sync(0xffffffffu, cnt);
+  const int total = run;
   if (total == 0) {
     if (lane == 0) {
       if (redo_empty) {
@@ -475,33 +505,13 @@ __global__ void __launch_bounds__(kCollectWarps * 32)
     base = atomicAdd(pool_count + b, (uint32_t)total);
     *tab = make_uint2(base, (uint32_t)total);
     if (base + total > (uint32_t)pool_cap) atomicOr(status, kStatCandOverflow);
+    if (total > kCollectCap) atomicOr(status, kStatNodeOverflow);  // cannot happen: NMS survivors are never adjacent
   }
   base = __shfl_sync(0xffffffffu, base, 0);
-  if (base + total > (uint32_t)pool_cap) return;
+  if (base + total > (uint32_t)pool_cap || total > kCollectCap) return;
+  __syncwarp();
   uint32_t* out = pool + (size_t)b * pool_cap + base;
-  int run = 0;
-  while (any) {  // raster order: steps ascending, lanes ascending (row, then word), bytes ascending
-    const int it = __ffsll((long long)any) - 1;
-    any &= any - 1;
-    const int row = it * rpi + sub;
-    const uint32_t v = row < ih ? (__ldg(col + (size_t)it * stride) & lmask) : 0u;
-    uint32_t nz = (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u;
-    const int c = __popc(nz);
-    int inc = c;
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, inc, dlt);
-      if (lane >= dlt) inc += a;
-    }
-    int pos = run + inc - c;
-    run += __shfl_sync(0xffffffffu, inc, 31);
-    while (nz) {
-      const int j = (__ffs(nz) - 1) >> 3;
-      nz &= nz - 1;
-      // level coordinate - minBorder (:820-825)
-      out[pos++] = pack_cand(4 * (w0 + wi) + j - kMinBorder, ya + row - kMinBorder, (v >> (8 * j)) & 0xFFu);
-    }
-  }
+  for (int i = lane; i < total; i += 32) out[i] = list[i];
 }
 
 #undef PSL_DIV
