@@ -8,7 +8,12 @@ namespace psl {
 struct ResizeTables {
   const short4* xt;  // [dw]  (sx, sx+1 clamped, a0, a1)
   const short4* yt;  // [dh]  (sy, sy+1 clamped, b0, b1)
+  // the x table again, per group of 4 adjacent outputs (null when a group's taps span more than 3 source words):
+  const uint4* xw;      // [ceil(dw/4)] weights a0 | a1 << 16 of the 4 outputs
+  const uint32_t* xo;   // [ceil(dw/4)] first source word | byte offsets of the 4 left taps from it, 4 bits each, << 16
 };
+// host side of xw / xo; false when the scale is too large for the 3-word window
+bool resize_group_tables(const short4* xt, int dw, uint4* xw, uint32_t* xo);
 
 // K1: level l from level l-1 (ORBextractor.cc:1120)
 void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTables& t, int B, cudaStream_t st);

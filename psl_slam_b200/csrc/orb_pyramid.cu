@@ -34,8 +34,102 @@ __global__ void __launch_bounds__(256) resize_kernel(ImgBatch src, ImgBatchMut d
   *reinterpret_cast<uint32_t*>(dst.ptr + (size_t)b * dst.frame_stride + (size_t)y * dst.pitch + x4) = packed;
 }
 
+// The same arithmetic with whole-word loads: a thread owns 4 adjacent output columns and walks down kRBand output
+// rows.  Per source row it loads the 3 aligned words that hold the taps of its 4 outputs, shifts each tap pair
+// (S[sx], S[sx+1]) into the low half of a register and makes the Q11 row pass with one IDP.2A (u16 weights x u8
+// pixels).  sx+1 is the right tap wherever its weight is non-zero (the clamped ends have a1 = 0), and the row
+// pass of a source row that serves two consecutive output rows (every row but one in six at 1.2x) is kept.
+constexpr int kRBand = 8;
+
+__global__ void __launch_bounds__(256) resize_words_kernel(ImgBatch src, ImgBatchMut dst, const uint4* __restrict__ xw,
+                                                           const uint32_t* __restrict__ xo,
+                                                           const short4* __restrict__ yt) {
+  const int n4 = (dst.w + 3) >> 2, nbands = (dst.h + kRBand - 1) / kRBand;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4 * nbands) return;
+  const int band = idx / n4, g = idx - band * n4, b = blockIdx.y;
+  const uint4 wt = __ldg(xw + g);
+  const uint32_t xo_g = __ldg(xo + g);
+  const int wb = (int)(xo_g & 0xFFFFu);
+  const int nwords = src.pitch >> 2;
+  const bool in1 = wb + 1 < nwords, in2 = wb + 2 < nwords;  // stay inside the row (the taps there have weight 0)
+  const uint32_t* __restrict__ S = reinterpret_cast<const uint32_t*>(src.ptr + (size_t)b * src.frame_stride) + wb;
+  uint8_t* __restrict__ D = dst.ptr + (size_t)b * dst.frame_stride + 4 * g;
+  const uint32_t w4[4] = {wt.x, wt.y, wt.z, wt.w};
+  int kept_row = -1;
+  int kept[4] = {0, 0, 0, 0};
+  const int y_end = min((band + 1) * kRBand, dst.h);
+  for (int y = band * kRBand; y < y_end; ++y) {
+    const short4 ty = __ldg(yt + y);
+    int r0[4], r1[4];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int sy = pass == 0 ? ty.x : ty.y;
+      int* r = pass == 0 ? r0 : r1;
+      if (pass == 0 && sy == kept_row) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = kept[k];
+        continue;
+      }
+      if (pass == 1 && sy == ty.x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = r0[k];
+        continue;
+      }
+      const uint32_t* row = S + (size_t)sy * nwords;
+      const uint32_t W0 = __ldg(row), W1 = in1 ? __ldg(row + 1) : 0u, W2 = in2 ? __ldg(row + 2) : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t off = (xo_g >> (16 + 4 * k)) & 0xFu;
+        const uint32_t lo = off < 4u ? W0 : W1, hi = off < 4u ? W1 : W2;
+        const uint32_t pair = __funnelshift_r(lo, hi, 8u * (off & 3u));
+        r[k] = (int)__dp2a_lo(w4[k], pair, 0u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) kept[k] = r1[k];
+    kept_row = ty.y;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = ((((int)ty.z * (r0[k] >> 4)) >> 16) + (((int)ty.w * (r1[k] >> 4)) >> 16) + 2) >> 2;
+      packed |= (uint32_t)(v & 0xFF) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(D + (size_t)y * dst.pitch) = packed;
+  }
+}
+
+bool resize_group_tables(const short4* xt, int dw, uint4* xw, uint32_t* xo) {
+  const int n4 = (dw + 3) >> 2;
+  for (int g = 0; g < n4; ++g) {
+    const int wb = xt[4 * g].x >> 2;
+    uint32_t w[4] = {0, 0, 0, 0}, offs = 0;
+    for (int k = 0; k < 4; ++k) {
+      const int x = 4 * g + k;
+      if (x >= dw) continue;
+      const short4 t = xt[x];
+      if (t.y != t.x + 1 && t.w != 0) return false;  // the right tap is not the next pixel
+      const int off = t.x - 4 * wb;
+      if (off < 0 || off + 1 > 11 || t.z < 0 || t.w < 0) return false;
+      w[k] = (uint32_t)(uint16_t)t.z | ((uint32_t)(uint16_t)t.w << 16);
+      offs |= (uint32_t)off << (4 * k);
+    }
+    if (wb > 0xFFFF) return false;
+    xw[g] = make_uint4(w[0], w[1], w[2], w[3]);
+    xo[g] = (uint32_t)wb | (offs << 16);
+  }
+  return true;
+}
+
 void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTables& t, int B, cudaStream_t st) {
   const int n4 = (dst.w + 3) >> 2;
+  const bool aligned = ((uintptr_t)src.ptr & 3) == 0 && (src.pitch & 3) == 0 && (src.frame_stride & 3) == 0;
+  if (t.xw && aligned) {
+    const int nbands = (dst.h + kRBand - 1) / kRBand;
+    dim3 grid((n4 * nbands + 255) / 256, B);
+    resize_words_kernel<<<grid, 256, 0, st>>>(src, dst, t.xw, t.xo, t.yt);
+    return;
+  }
   dim3 grid((n4 * dst.h + 255) / 256, B);
   resize_kernel<<<grid, 256, 0, st>>>(src, dst, t.xt, t.yt);
 }

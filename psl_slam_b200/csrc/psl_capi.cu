@@ -151,23 +151,45 @@ static int set_geometry(psl_ctx* ctx, int w, int h) {
     if (l) g.level[l].ptr = ctx->d_levels + lvl_off[l];
     g.blur[l].ptr = ctx->d_levels + blur_off[l];
   }
-  // resize tables
+  // resize tables: per-pixel (x, y) and, for the word kernel, the x table per group of 4 outputs
   std::vector<short4> all;
-  std::vector<size_t> xo(L), yo(L);
+  std::vector<size_t> xo(L), yo(L), go(L);
+  std::vector<uint8_t> grouped;  // per level: [n4] uint4 weights, then [n4] u32 offsets (16-byte aligned blocks)
+  std::vector<char> grouped_ok(L, 0);
   std::vector<short4> t;
   for (int l = 1; l < L; ++l) {
     resize_axis(g.level[l - 1].w, g.level[l].w, true, t);
     xo[l] = all.size();
     all.insert(all.end(), t.begin(), t.end());
+    const int n4 = (g.level[l].w + 3) >> 2;
+    const size_t blk = ((size_t)n4 * 20 + 15) & ~(size_t)15;
+    go[l] = grouped.size();
+    grouped.resize(grouped.size() + blk);
+    std::vector<uint4> xw(n4);
+    std::vector<uint32_t> xoff(n4);
+    if (resize_group_tables(t.data(), g.level[l].w, xw.data(), xoff.data())) {
+      grouped_ok[l] = 1;
+      std::memcpy(grouped.data() + go[l], xw.data(), (size_t)n4 * 16);
+      std::memcpy(grouped.data() + go[l] + (size_t)n4 * 16, xoff.data(), (size_t)n4 * 4);
+    }
     resize_axis(g.level[l - 1].h, g.level[l].h, false, t);
     yo[l] = all.size();
     all.insert(all.end(), t.begin(), t.end());
   }
-  PSL_CK(cudaMalloc(&ctx->d_tables, std::max<size_t>(all.size(), 1) * sizeof(short4)));
+  const size_t all_bytes = (all.size() * sizeof(short4) + 15) & ~(size_t)15;
+  PSL_CK(cudaMalloc(&ctx->d_tables, std::max<size_t>(all_bytes + grouped.size(), 16)));
   PSL_CK(cudaMemcpyAsync(ctx->d_tables, all.data(), all.size() * sizeof(short4), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->rtab.assign(L, ResizeTables{nullptr, nullptr});
-  for (int l = 1; l < L; ++l)
-    ctx->rtab[l] = ResizeTables{(const short4*)ctx->d_tables + xo[l], (const short4*)ctx->d_tables + yo[l]};
+  if (!grouped.empty())
+    PSL_CK(cudaMemcpyAsync((uint8_t*)ctx->d_tables + all_bytes, grouped.data(), grouped.size(), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  ctx->rtab.assign(L, ResizeTables{nullptr, nullptr, nullptr, nullptr});
+  for (int l = 1; l < L; ++l) {
+    const uint8_t* gb = (const uint8_t*)ctx->d_tables + all_bytes + go[l];
+    const int n4 = (g.level[l].w + 3) >> 2;
+    ctx->rtab[l] = ResizeTables{(const short4*)ctx->d_tables + xo[l], (const short4*)ctx->d_tables + yo[l],
+                                grouped_ok[l] ? (const uint4*)gb : nullptr,
+                                grouped_ok[l] ? (const uint32_t*)(gb + (size_t)n4 * 16) : nullptr};
+  }
   const size_t C = ctx->chunk, P = ctx->pool_cap;
   PSL_CK(cudaMalloc(&ctx->d_pool, C * P * sizeof(uint32_t)));
   PSL_CK(cudaMalloc(&ctx->d_pool_count, C * sizeof(uint32_t)));
@@ -190,7 +212,7 @@ static int set_geometry(psl_ctx* ctx, int w, int h) {
     fast_encode_map(ctx->fast_maps, l, g.level[l].ptr, g.level[l].w, g.level[l].h, g.level[l].pitch,
                     g.level[l].frame_stride, ctx->chunk);
   PSL_CK(cudaMemcpyAsync(ctx->d_geo, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
-  PSL_CK(cudaStreamSynchronize(ctx->stream));  // `all`, `ftab` and `g` are host temporaries
+  PSL_CK(cudaStreamSynchronize(ctx->stream));  // `all`, `grouped`, `ftab` and `g` are host temporaries
   ctx->geo_w = w;
   ctx->geo_h = h;
   return PSL_OK;
