@@ -586,8 +586,8 @@ __device__ bool reduce_region_radius(const Frame& f, int& n, double reg_angle, d
     n = __shfl_sync(kFull, n, 0);
     __syncwarp();
     if (n < 2) return false;
-    if (n <= kRing)
-      for (int i = lane; i < n; i += 32) f.ring[i] = f.reg[i];
+    // the reordered tail goes back to the shared mirror (reg_at reads the last kRing points from it)
+    for (int i = max(0, n - kRing) + lane; i < n; i += 32) f.ring[i & (kRing - 1)] = f.reg[i];
     __syncwarp();
     region2rect(f, n, reg_angle, prec, rec, lane);
     density = density_of(n, rec);
