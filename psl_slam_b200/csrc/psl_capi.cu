@@ -321,6 +321,7 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
   ctx->pool_cap = cfg->orb_max_candidates > 0 ? cfg->orb_max_candidates : std::max(16384, 32 * cfg->orb_nfeatures);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc(&ctx->d_geo, sizeof(OrbGeometry)) == cudaSuccess &&
@@ -339,6 +340,7 @@ void psl_destroy(psl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  if (ctx->stream_copy) cudaStreamSynchronize(ctx->stream_copy);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_geometry(ctx);
   free_line_geometry(ctx);
@@ -358,6 +360,8 @@ void psl_destroy(psl_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
+  for (cudaEvent_t ev : ctx->ev_slice) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

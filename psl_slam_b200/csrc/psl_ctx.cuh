@@ -17,7 +17,9 @@ struct psl_ctx {
   psl_config cfg{};
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;          // the line path of the combined front end runs beside the point path
+  cudaStream_t stream_copy = nullptr;      // host->device uploads of the host-pointer combined entry point
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_slice;       // one per uploaded slice of gray frames (+ one for depth and poses)
   std::string err;
   int chunk = 0;
   int pool_cap = 0;

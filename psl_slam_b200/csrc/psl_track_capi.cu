@@ -10,6 +10,13 @@
 
 using namespace psl;
 
+namespace psl {
+int track_after_extract(psl_ctx* ctx, const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                        int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                        const psl_track_params* prm, psl_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, float* d_u_right,
+                        float* d_z, int32_t* d_assign, int32_t* d_nmatches, int32_t cap);
+}
+
 extern "C" {
 
 int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
@@ -24,6 +31,20 @@ int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_st
   if (B == 0) return PSL_OK;
   int rc = psl_orb_extract_batch_dev(ctx, d_gray, B, w, h, gray_stride, gray_frame_stride, d_kps, d_desc, cap, d_n);
   if (rc) return rc;
+  return psl::track_after_extract(ctx, d_depth, depth_stride_px, depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, d_kps,
+                                  d_desc, d_n, d_u_right, d_z, d_assign, d_nmatches, cap);
+}
+
+}  // extern "C"
+
+namespace psl {
+// Everything of the batched point front end that follows the extraction: ComputeStereoFromRGBD and
+// SearchByProjection against the previous frame (arguments as psl_track_orb_batch_dev, already validated).
+int track_after_extract(psl_ctx* ctx, const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
+                        int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
+                        const psl_track_params* prm, psl_keypoint* d_kps, uint8_t* d_desc, int32_t* d_n, float* d_u_right,
+                        float* d_z, int32_t* d_assign, int32_t* d_nmatches, int32_t cap) {
+  int rc;
   cudaStream_t st = ctx->stream;
   size_t e = prof_mark(ctx);
   launch_stereo(d_kps, d_n, cap, d_depth, depth_stride_px, depth_frame_stride_px, cam->depth_factor, cam->bf, d_u_right,
@@ -82,6 +103,10 @@ int psl_track_orb_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_st
   return PSL_OK;
 }
 
+}  // namespace psl
+
+extern "C" {
+
 int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
                         const float* Tcw, const psl_camera* cam, const psl_track_params* prm, psl_keypoint* kps,
                         uint8_t* desc, int32_t* n, float* u_right, float* z, int32_t* assign, int32_t* nmatches,
@@ -128,20 +153,26 @@ int psl_track_orb_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth
 
 namespace {
 struct Copy { void* dst; const void* src; size_t bytes; };
+// Host inputs of the host-pointer entry point (null members = data already in HBM)
+struct HostFeed { const uint8_t* gray; const uint16_t* depth; const float* Tcw; };
 
-// The combined front end on device-resident data.  `late_in` are host->device copies of inputs only the point
-// path needs (depth, poses) and `early_out` device->host copies of the point results: the host-pointer entry
-// point uses them so that the line path (which needs the gray frames only and is the longer of the two) starts
-// right after the gray upload and the point results travel back while it is still running.
-int frontend_core(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
-                  const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px, int32_t B,
-                  int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam, const psl_track_params* prm,
-                  float line_desc_th, const psl_frontend_out* o, const Copy* late_in, int n_in, const Copy* early_out,
+// The combined front end.  With `feed` the inputs come from host memory: the gray frames go up slice by slice
+// (one extraction chunk each) on a copy stream, the ORB extraction of a slice starts as soon as the slice has
+// landed, the line path (which needs all gray frames and is the longer of the two) starts after the last slice,
+// depth and poses follow behind the gray frames, and `early_out` (device->host copies of the point results)
+// travel back while the line path is still running.
+int frontend_core(psl_ctx* ctx, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                  uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px, int32_t B,
+                  int32_t w, int32_t h, float* d_Tcw, const psl_camera* cam, const psl_track_params* prm,
+                  float line_desc_th, const psl_frontend_out* o, const HostFeed* feed, const Copy* early_out,
                   int n_out) {
   if (!ctx) return PSL_E_INVALID;
   if (!o || !o->kl || !o->ldesc || !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || o->line_cap < 1 ||
       o->line_cap > kMaxLinesPerFrame)
     return fail(ctx, PSL_E_INVALID, "bad line output block");
+  if (!d_gray || !d_depth || !d_Tcw || !cam || !prm || !o->kps || !o->desc || !o->n || !o->u_right || !o->z ||
+      !o->assign || !o->nmatches || w <= 0 || h <= 0 || o->cap < 1 || o->cap > 65535 || depth_stride_px < w)
+    return fail(ctx, PSL_E_INVALID, "bad argument");
   if (B <= 0) return B == 0 ? PSL_OK : fail(ctx, PSL_E_INVALID, "bad argument");
   // The line path (latency-bound: one warp walks one frame) and the point path (bandwidth / ALU-bound) are
   // independent until the matchers, so they run on two streams and share the SMs; with per-stage profiling on
@@ -150,10 +181,37 @@ int frontend_core(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int6
   cudaStream_t main_st = ctx->stream;
   const bool overlap = !ctx->prof;
   int rc;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const int slice = ctx->chunk;
+  const int nslices = (B + slice - 1) / slice;
+  const bool sliced = feed && overlap;
+  if (feed && !sliced) {  // profiling: everything in order on one stream
+    PSL_CK(cudaMemcpyAsync(d_gray, feed->gray, (size_t)gray_frame_stride * B, cudaMemcpyHostToDevice, main_st));
+    PSL_CK(cudaMemcpyAsync(d_depth, feed->depth, (size_t)depth_frame_stride_px * 2 * B, cudaMemcpyHostToDevice, main_st));
+    PSL_CK(cudaMemcpyAsync(d_Tcw, feed->Tcw, (size_t)B * 48, cudaMemcpyHostToDevice, main_st));
+  }
+  if (overlap) PSL_CK(cudaEventRecord(ctx->ev_fork, main_st));
+  if (sliced) {
+    cudaStream_t cs = ctx->stream_copy;
+    while ((int)ctx->ev_slice.size() < nslices + 1) {
+      cudaEvent_t ev;
+      PSL_CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      ctx->ev_slice.push_back(ev);
+    }
+    PSL_CK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));  // earlier work on the main stream may still read the staging
+    for (int s0 = 0; s0 < nslices; ++s0) {
+      const int f0 = s0 * slice, nb = std::min(slice, B - f0);
+      PSL_CK(cudaMemcpyAsync(d_gray + (size_t)f0 * gray_frame_stride, feed->gray + (size_t)f0 * gray_frame_stride,
+                             (size_t)gray_frame_stride * nb, cudaMemcpyHostToDevice, cs));
+      PSL_CK(cudaEventRecord(ctx->ev_slice[s0], cs));
+    }
+    PSL_CK(cudaMemcpyAsync(d_depth, feed->depth, (size_t)depth_frame_stride_px * 2 * B, cudaMemcpyHostToDevice, cs));
+    PSL_CK(cudaMemcpyAsync(d_Tcw, feed->Tcw, (size_t)B * 48, cudaMemcpyHostToDevice, cs));
+    PSL_CK(cudaEventRecord(ctx->ev_slice[nslices], cs));
+  }
   if (overlap) {
-    PSL_CK(cudaSetDevice(ctx->cfg.device));
-    PSL_CK(cudaEventRecord(ctx->ev_fork, main_st));
     PSL_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    if (sliced) PSL_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_slice[nslices - 1], 0));
     ctx->stream = ctx->stream2;
   }
   rc = psl_line_extract_batch_dev(ctx, d_gray, B, w, h, gray_stride, gray_frame_stride, o->kl, o->ldesc, o->lineeq, nullptr,
@@ -163,11 +221,21 @@ int frontend_core(psl_ctx* ctx, const uint8_t* d_gray, int32_t gray_stride, int6
     PSL_CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
   }
   if (rc) return rc;
-  for (int i = 0; i < n_in; ++i)
-    PSL_CK(cudaMemcpyAsync(late_in[i].dst, late_in[i].src, late_in[i].bytes, cudaMemcpyHostToDevice, main_st));
-  rc = psl_track_orb_batch_dev(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px,
-                               depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, o->kps, o->desc, o->n, o->u_right, o->z,
-                               o->assign, o->nmatches, o->cap);
+  if (sliced) {
+    for (int s0 = 0; s0 < nslices; ++s0) {
+      const int f0 = s0 * slice, nb = std::min(slice, B - f0);
+      PSL_CK(cudaStreamWaitEvent(main_st, ctx->ev_slice[s0], 0));
+      rc = psl_orb_extract_batch_dev(ctx, d_gray + (size_t)f0 * gray_frame_stride, nb, w, h, gray_stride, gray_frame_stride,
+                                     o->kps + (size_t)f0 * o->cap, o->desc + (size_t)f0 * o->cap * 32, o->cap, o->n + f0);
+      if (rc) return rc;
+    }
+    PSL_CK(cudaStreamWaitEvent(main_st, ctx->ev_slice[nslices], 0));
+  } else {
+    rc = psl_orb_extract_batch_dev(ctx, d_gray, B, w, h, gray_stride, gray_frame_stride, o->kps, o->desc, o->cap, o->n);
+    if (rc) return rc;
+  }
+  rc = track_after_extract(ctx, d_depth, depth_stride_px, depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, o->kps, o->desc,
+                           o->n, o->u_right, o->z, o->assign, o->nmatches, o->cap);
   if (rc) return rc;
   for (int i = 0; i < n_out; ++i)
     PSL_CK(cudaMemcpyAsync(early_out[i].dst, early_out[i].src, early_out[i].bytes, cudaMemcpyDeviceToHost, main_st));
@@ -197,8 +265,9 @@ int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gr
                                  const uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px,
                                  int32_t B, int32_t w, int32_t h, const float* d_Tcw, const psl_camera* cam,
                                  const psl_track_params* prm, float line_desc_th, const psl_frontend_out* o) {
-  return frontend_core(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px, depth_frame_stride_px, B, w,
-                       h, d_Tcw, cam, prm, line_desc_th, o, nullptr, 0, nullptr, 0);
+  return frontend_core(ctx, const_cast<uint8_t*>(d_gray), gray_stride, gray_frame_stride, const_cast<uint16_t*>(d_depth),
+                       depth_stride_px, depth_frame_stride_px, B, w, h, const_cast<float*>(d_Tcw), cam, prm, line_desc_th, o,
+                       nullptr, nullptr, 0);
 }
 
 int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
@@ -228,8 +297,7 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
   if ((rc = ensure(ctx, ctx->l_eq, nl * 24))) return rc;
   if ((rc = ensure(ctx, ctx->l_n, nl * 4))) return rc;  // line_assign
   cudaStream_t st = ctx->stream;
-  PSL_CK(cudaMemcpyAsync(M[0].p, gray, px * B, cudaMemcpyHostToDevice, st));
-  const Copy late_in[2] = {{M[1].p, depth, px * B * 2}, {M[2].p, Tcw, (size_t)B * 48}};
+  const HostFeed feed{gray, depth, Tcw};
   int32_t* d_n = M[5].as<int32_t>();
   psl_frontend_out d = *o;
   d.kps = M[3].as<psl_keypoint>(); d.desc = M[4].as<uint8_t>(); d.n = d_n; d.nmatches = d_n + B;
@@ -240,7 +308,7 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
                              {o->n, d.n, (size_t)B * 4},  {o->nmatches, d.nmatches, (size_t)B * 4},
                              {o->u_right, d.u_right, nk * 4}, {o->z, d.z, nk * 4}, {o->assign, d.assign, nk * 4}};
   rc = frontend_core(ctx, M[0].as<uint8_t>(), w, (int64_t)px, M[1].as<uint16_t>(), w, (int64_t)px, B, w, h,
-                     M[2].as<float>(), cam, prm, line_desc_th, &d, late_in, 2, early_out, 7);
+                     M[2].as<float>(), cam, prm, line_desc_th, &d, &feed, early_out, 7);
   if (rc) return rc;
   PSL_CK(cudaMemcpyAsync(o->kl, d.kl, nl * sizeof(psl_keyline), cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(o->ldesc, d.ldesc, nl * 32, cudaMemcpyDeviceToHost, st));
