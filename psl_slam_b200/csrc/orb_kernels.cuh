@@ -29,7 +29,7 @@ void fast_build_tab(const OrbGeometry& geo, uint32_t* host_tab);   // n_tiles + 
 // descriptor of one level; false when the layout cannot be described (base or strides not 16-byte aligned)
 bool fast_encode_map(FastMaps& maps, int level, const void* ptr, int w, int h, int pitch, int64_t frame_stride,
                      int frames);
-constexpr int kFastLaunches = 4;  // memset + score tiles + collect + per-cell fallback
+constexpr int kFastLaunches = 3;  // score tiles + collect + per-cell fallback (the counter memset is not a kernel)
 
 // K2: per-cell FAST + NMS + threshold fallback + ordered compaction (ORBextractor.cc:789-829).
 // fb_list: [B * total_cells] u32 scratch (cells to redo at minThFAST), fb_count: one u32.
@@ -43,6 +43,7 @@ void launch_octree(const OrbGeometry* d_geo, const OrbGeometry& geo, const uint3
                    const uint2* cell_tab, uint32_t* key_scratch, uint16_t* node_scratch, uint32_t* sel,
                    int32_t* sel_count, uint32_t* status, int B, cudaStream_t st);
 
+constexpr int kBlurLaunches = 2;  // interior word columns + edge columns (word-aligned source)
 // generic separable 7-tap Q8 blur of one image batch (taps t0,t1,t2,t3=centre; dst pitch multiple of 4)
 void launch_blur7(const ImgBatch& src, const ImgBatchMut& dst, int t0, int t1, int t2, int t3, int B, cudaStream_t st);
 

@@ -151,15 +151,32 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i >= n ? 2 * (n - 1) - i : i;
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut dst, int t0, int t1, int t2, int t3) {
+// MODE 0: any layout; a warp covers 32 word columns, the edge columns (and every column of an image whose rows are
+//         not word aligned) read single bytes through the reflected index table.
+// MODE 1: the interior word columns [1, n_int] of a word-aligned image: 3 aligned words per row, the row pass of a
+//         pixel is two IDP.4A (taps as packed bytes) on the two funnel-shifted words that hold its 7 pixels.
+// MODE 2: the remaining (edge) word columns of such an image, one (band, column) per thread.
+template <int MODE>
+__global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut dst, int t0, int t1, int t2, int t3,
+                                                     int n_int) {
   const int lane = threadIdx.x, b = blockIdx.z;
-  const int xw = blockIdx.x * 32 + lane;              // output word (4 pixels)
-  const int y0 = (blockIdx.y * 4 + threadIdx.y) * kGBand;
   const int w = src.w, h = src.h;
+  int xw, y0;
+  if (MODE == 2) {
+    const int ne = ((w + 3) >> 2) - n_int, nbands = (h + kGBand - 1) / kGBand;
+    const int t = blockIdx.x * 128 + threadIdx.y * 32 + lane;
+    if (t >= ne * nbands) return;
+    const int band = t / ne, e = t - band * ne;
+    xw = e == 0 ? 0 : n_int + e;
+    y0 = band * kGBand;
+  } else {
+    xw = blockIdx.x * 32 + lane + (MODE == 1 ? 1 : 0);  // output word (4 pixels)
+    y0 = (blockIdx.y * 4 + threadIdx.y) * kGBand;
+    if (MODE == 1 && xw > n_int) return;
+  }
   if (y0 >= h || xw * 4 >= w) return;
   const int x = xw * 4;
-  const bool interior = ALIGNED && xw >= 1 && x + 7 < w;
+  const bool interior = MODE == 1;
   const uint8_t* __restrict__ S = src.ptr + (size_t)b * src.frame_stride;
   uint8_t* __restrict__ D = dst.ptr + (size_t)b * dst.frame_stride;
   int xi[10];
@@ -167,6 +184,8 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
 #pragma unroll
     for (int k = 0; k < 10; ++k) xi[k] = min(reflect101(x - 3 + k, w), w - 1);
   }
+  const uint32_t Ta = (uint32_t)t0 | ((uint32_t)t1 << 8) | ((uint32_t)t2 << 16) | ((uint32_t)t3 << 24);  // x-3 .. x
+  const uint32_t Tb = (uint32_t)t2 | ((uint32_t)t1 << 8) | ((uint32_t)t0 << 16);                         // x+1 .. x+3
   int ring[7][4];
 #pragma unroll
   for (int j = 0; j < 7; ++j)
@@ -190,20 +209,24 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
     for (int j = 0; j < 7; ++j) {
       const int yy = yb + j;
       if (yy >= y_end + 3) break;
-      int p[10];
       if (interior) {
         const uint32_t w0 = ld[j][0], w1 = ld[j][1], w2 = ld[j][2];
-        p[0] = (w0 >> 8) & 0xFF; p[1] = (w0 >> 16) & 0xFF; p[2] = w0 >> 24;
-        p[3] = w1 & 0xFF; p[4] = (w1 >> 8) & 0xFF; p[5] = (w1 >> 16) & 0xFF; p[6] = w1 >> 24;
-        p[7] = w2 & 0xFF; p[8] = (w2 >> 8) & 0xFF; p[9] = (w2 >> 16) & 0xFF;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // pixels x+k-3 .. x+k and x+k+1 .. x+k+4 (the tap of the last one is 0)
+          const uint32_t A = k == 3 ? w1 : __funnelshift_r(w0, w1, 8 * (k + 1));
+          const uint32_t Bw = k == 3 ? w2 : __funnelshift_r(w1, w2, 8 * (k + 1));
+          ring[j][k] = (int)__dp4a(A, Ta, __dp4a(Bw, Tb, 0u));
+        }
       } else {
+        int p[10];
         const uint8_t* row = S + (size_t)reflect101(yy, h) * src.pitch;
 #pragma unroll
         for (int k = 0; k < 10; ++k) p[k] = __ldg(row + xi[k]);
-      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        ring[j][k] = t0 * (p[k] + p[k + 6]) + t1 * (p[k + 1] + p[k + 5]) + t2 * (p[k + 2] + p[k + 4]) + t3 * p[k + 3];
+        for (int k = 0; k < 4; ++k)
+          ring[j][k] = t0 * (p[k] + p[k + 6]) + t1 * (p[k + 1] + p[k + 5]) + t2 * (p[k + 2] + p[k + 4]) + t3 * p[k + 3];
+      }
       const int yo = yy - 3;
       if (yo >= y0) {
         // newest row is slot j; the 7 rows yo-3..yo+3 sit in slots (j+1)%7 .. j
@@ -223,10 +246,19 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
 }
 
 void launch_blur7(const ImgBatch& src, const ImgBatchMut& dst, int t0, int t1, int t2, int t3, int B, cudaStream_t st) {
-  dim3 grid(((dst.w + 3) / 4 + 31) / 32, (dst.h + 4 * kGBand - 1) / (4 * kGBand), B), block(32, 4);
+  const int nwords = (dst.w + 3) / 4, nbands = (dst.h + kGBand - 1) / kGBand;
   const bool aligned = ((uintptr_t)src.ptr & 3) == 0 && (src.pitch & 3) == 0 && (src.frame_stride & 3) == 0;
-  if (aligned) gauss7_kernel<true><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3);
-  else gauss7_kernel<false><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3);
+  const int n_int = dst.w >= 12 ? (dst.w - 8) / 4 : 0;  // word columns xw in [1, n_int]: 4 xw + 7 < w
+  dim3 block(32, 4);
+  if (aligned && n_int > 0) {
+    dim3 grid((n_int + 31) / 32, (nbands + 3) / 4, B);
+    gauss7_kernel<1><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3, n_int);
+    dim3 egrid(((nwords - n_int) * nbands + 127) / 128, 1, B);
+    gauss7_kernel<2><<<egrid, block, 0, st>>>(src, dst, t0, t1, t2, t3, n_int);
+  } else {
+    dim3 grid((nwords + 31) / 32, (nbands + 3) / 4, B);
+    gauss7_kernel<0><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3, 0);
+  }
 }
 
 void launch_gauss7(const OrbGeometry& geo, ImgBatch in0, int B, cudaStream_t st) {

@@ -242,7 +242,7 @@ static int run_chunk(psl_ctx* ctx, ImgBatch in0, int nb, psl_keypoint* d_kps, ui
   prof_span(ctx, 2, e, 1);
   e = prof_mark(ctx);
   launch_gauss7(g, in0, nb, st);
-  prof_span(ctx, 3, e, g.nlevels);
+  prof_span(ctx, 3, e, kBlurLaunches * g.nlevels);
   e = prof_mark(ctx);
   launch_describe(ctx->d_geo, g, in0, ctx->d_sel, ctx->d_sel_count, d_kps, d_desc, cap, d_n, ctx->d_status, nb, st);
   prof_span(ctx, 4, e, 1);

@@ -104,7 +104,7 @@ static int run_line_chunk(psl_ctx* ctx, ImgBatch in, int nb, psl_keyline* d_kl, 
   const int nfeat = ctx->cfg.line_nfeatures;
   size_t e = prof_mark(ctx);
   launch_lsd_prologue(L, in, nb, st);
-  prof_span(ctx, 10, e, 6);
+  prof_span(ctx, 10, e, 5 + psl::kBlurLaunches);
   e = prof_mark(ctx);
   launch_lsd_order(L, nb, st);
   prof_span(ctx, 11, e, 1);
@@ -116,7 +116,7 @@ static int run_line_chunk(psl_ctx* ctx, ImgBatch in, int nb, psl_keyline* d_kl, 
   prof_span(ctx, 13, e, 1);
   e = prof_mark(ctx);
   launch_lbd(L, in, nb, nfeat, d_kl, d_n, cap, d_ldesc, d_lbd72, st);
-  prof_span(ctx, 14, e, 3);
+  prof_span(ctx, 14, e, 2 + psl::kBlurLaunches);
   PSL_CK(cudaGetLastError());
   return PSL_OK;
 }
