@@ -324,6 +324,30 @@ int psl_line_search_triangulation(psl_ctx* ctx, const uint8_t* desc1, const uint
                                   const uint8_t* desc2, const uint8_t* has_mapline2, int32_t n2, float nn_ratio, float th,
                                   int32_t is_double, int32_t* matches12, int32_t* nmatches);
 
+/* One MapLine projected into a KeyFrame by LSDmatcher::Fuse before its window search (LSDmatcher.cpp:862-918): the
+ * caller keeps the MapLine tests (isBad, IsInKeyFrame, IsInImage of both endpoints, distance invariance, viewing
+ * angle), the `return false` of the whole call on an endpoint behind the camera (:883-884), and PredictScale;
+ * flags = PSL_Q_VALID when all passed. */
+typedef struct psl_line_fuse_query {
+  float u1, v1, u2, v2;  /* projected endpoints */
+  float radius;          /* th * mvScaleFactorsLine[nPredictedLevel] */
+  int32_t pred_level;    /* nPredictedLevel */
+  uint32_t flags;
+} psl_line_fuse_query;
+
+/* The matching part of LSDmatcher::Fuse(pKF, vpMapLines, th) (LSDmatcher.cpp:847-984; "next" row N1, called by
+ * LocalMapping::SearchInNeighbors, LocalMapping.cc:846,872): per MapLine, KeyFrame::GetLinesInArea (KeyFrame.cc:857-891:
+ * every KeyLine whose midpoint lies within `radius` of the projected midpoint and whose 2-D direction has
+ * |cos| >= th_cos, default 0.998, in index order), the octave gate pred-1..pred, and the smallest Hamming distance;
+ * the earliest line wins ties.  kf_desc: the rows the reference compares against, which are those of
+ * pKF->mDescriptors (the ORB descriptor matrix) at the LINE index (:938), not of mLineDescriptors; it must have at
+ * least n_lines rows (the reference would throw beyond them).  best_idx[nq] = line index if that distance <= th_low
+ * (TH_LOW = 50), else -1; best_dist[nq] (may be NULL) = the smallest distance, 256 when no line qualified.  The
+ * replace-or-add bookkeeping on the MapLine objects (:955-978) stays with the caller; every query is independent. */
+int psl_line_fuse(psl_ctx* ctx, const psl_keyline* kl, int32_t n_lines, const uint8_t* kf_desc, int32_t n_desc,
+                  const psl_line_fuse_query* queries, const uint8_t* query_desc, int32_t nq, float th_cos, int32_t th_low,
+                  int32_t* best_idx, int32_t* best_dist);
+
 /* What LSDmatcher::SearchByProjection reads from the searched Frame (include/Frame.h): mvKeylinesUn, mLdesc,
  * mvKeyLineFunctions, mvLines3D (first/second endpoints, n x 6 doubles; only the map-line form needs it) and the
  * bounds of the 64x48 line grid (Frame::AssignFeaturesToGridForLine, Frame.cc:286-309; rebuilt by the library). */

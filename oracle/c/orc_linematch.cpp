@@ -250,6 +250,61 @@ int orc_line_search_triangulation(const uint8_t* desc1, const uint8_t* has_ml1, 
   return nm;
 }
 
+// KeyFrame::GetLinesInArea, KeyFrame.cc:857-891 (TH defaults to 0.998, KeyFrame.h:144): all KeyLines, index order.
+static std::vector<int> lines_in_area(const psl_keyline* kl, int n, float x1, float y1, float x2, float y2, float r,
+                                      float TH) {
+  std::vector<int> out;
+  float delta1x = x1 - x2, delta1y = y1 - y2;                                   // :863-864
+  const float norm_delta1 = sqrtf(delta1x * delta1x + delta1y * delta1y);        // :865
+  delta1x /= norm_delta1;                                                       // :866-867
+  delta1y /= norm_delta1;
+  for (int i = 0; i < n; ++i) {
+    const psl_keyline& k = kl[i];
+    // :873 the 0.5 literal makes the offsets and their squares double; the sum is stored in a float
+    const float distance = (float)((0.5 * (x1 + x2) - k.pt_x) * (0.5 * (x1 + x2) - k.pt_x) +
+                                   (0.5 * (y1 + y2) - k.pt_y) * (0.5 * (y1 + y2) - k.pt_y));
+    if (distance > r * r) continue;                                             // :874-875
+    float delta2x = k.start_x - k.end_x, delta2y = k.start_y - k.end_y;          // :877-878
+    const float norm_delta2 = sqrtf(delta2x * delta2x + delta2y * delta2y);
+    delta2x /= norm_delta2;
+    delta2y /= norm_delta2;
+    const float CosSita = fabsf(delta1x * delta2x + delta1y * delta2y);          // :882
+    if (CosSita < TH) continue;                                                 // :884-885 (NaN passes)
+    out.push_back(i);
+  }
+  return out;
+}
+
+// The window search of LSDmatcher::Fuse, LSDmatcher.cpp:916-953 (the caller did :862-914).  The descriptor rows it
+// compares against are pKF->mDescriptors.row(idx) (:938), passed as kf_desc.
+int orc_line_fuse(const psl_keyline* kl, int n_lines, const uint8_t* kf_desc, const psl_line_fuse_query* qs,
+                  const uint8_t* qdesc, int nq, float th_cos, int th_low, int32_t* best_idx, int32_t* best_dist) {
+  int fused = 0;
+  for (int q = 0; q < nq; ++q) {
+    best_idx[q] = -1;
+    if (best_dist) best_dist[q] = 256;
+    const psl_line_fuse_query& Q = qs[q];
+    if (!(Q.flags & PSL_Q_VALID)) continue;
+    const std::vector<int> cand = lines_in_area(kl, n_lines, Q.u1, Q.v1, Q.u2, Q.v2, Q.radius, th_cos);
+    int bestDist = 256, bestIdx = -1;                                           // :926-927
+    for (int idx : cand) {
+      const int kpLevel = kl[idx].octave;
+      if (kpLevel < Q.pred_level - 1 || kpLevel > Q.pred_level) continue;        // :936-937
+      const int dist = desc_dist(qdesc + 32 * (size_t)q, kf_desc + 32 * (size_t)idx);
+      if (dist < bestDist) {                                                    // :945-949
+        bestDist = dist;
+        bestIdx = idx;
+      }
+    }
+    if (best_dist) best_dist[q] = bestDist;
+    if (bestDist <= th_low && bestIdx >= 0) {                                    // :952
+      best_idx[q] = bestIdx;
+      ++fused;
+    }
+  }
+  return fused;
+}
+
 int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,
                               const uint8_t* claimed_in, int mode, float nn_ratio, int32_t* assign) {
   LineGrid g(*f);

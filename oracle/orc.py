@@ -439,6 +439,19 @@ def plane_assoc(planes_cam, pts, Tcw, map_planes, map_bad, d_th, a_th, mode):
     return out[: len(planes_cam)].copy(), int(n)
 
 
+def line_fuse(kl, kf_desc, queries, qdesc, th_cos=0.998, th_low=50):
+    """Window search of LSDmatcher::Fuse: (best_idx [nq], best_dist [nq], fused count)."""
+    from psl_slam_b200._lib import KEYLINE_DTYPE, LINE_FUSE_QUERY_DTYPE
+    kl = np.ascontiguousarray(kl, KEYLINE_DTYPE)
+    queries = np.ascontiguousarray(queries, LINE_FUSE_QUERY_DTYPE)
+    kf_desc, qdesc = _u8(kf_desc), _u8(qdesc)
+    nq = len(queries)
+    bi, bd = np.full(max(nq, 1), -1, np.int32), np.full(max(nq, 1), 256, np.int32)
+    n = lib().orc_line_fuse(_p(kl), len(kl), _p(kf_desc), _p(queries), _p(qdesc), nq, C.c_float(th_cos), int(th_low),
+                            _p(bi), _p(bd))
+    return bi[:nq].copy(), bd[:nq].copy(), int(n)
+
+
 def line_search_triangulation(d1, ml1, d2, ml2, nn_ratio, th, is_double):
     d1, d2, ml1, ml2 = _u8(d1), _u8(d2), _u8(ml1), _u8(ml2)
     out = np.zeros(max(len(d1), 1), np.int32)

@@ -267,3 +267,52 @@ def plane_assoc(planes_cam, pts, Tcw, map_planes, map_bad, d_th, a_th, mode):
         if mode == 0 and found:
             nm += 1
     return assign, nm
+
+
+# ---------------------------------------------------------------------------------------------------
+# LSDmatcher::Fuse window search (LSDmatcher.cpp:916-953) over KeyFrame::GetLinesInArea (KeyFrame.cc:857-891)
+# ---------------------------------------------------------------------------------------------------
+def lines_in_area(kl, x1, y1, x2, y2, r, TH=0.998):
+    """All KeyLines of the KeyFrame in index order; float / double mix as written in the reference."""
+    x1, y1, x2, y2, r, TH = F32(x1), F32(y1), F32(x2), F32(y2), F32(r), F32(TH)
+    out = []
+    with np.errstate(all="ignore"):
+        d1x, d1y = F32(x1 - x2), F32(y1 - y2)
+        n1 = F32(np.sqrt(F32(F32(d1x * d1x) + F32(d1y * d1y))))
+        d1x, d1y = F32(d1x / n1), F32(d1y / n1)
+        mx, my = 0.5 * float(F32(x1 + x2)), 0.5 * float(F32(y1 + y2))   # doubles
+        for i in range(len(kl)):
+            k = kl[i]
+            ex, ey = mx - float(k["pt_x"]), my - float(k["pt_y"])
+            distance = F32(ex * ex + ey * ey)
+            if distance > F32(r * r):
+                continue
+            d2x, d2y = F32(k["start_x"] - k["end_x"]), F32(k["start_y"] - k["end_y"])
+            n2 = F32(np.sqrt(F32(F32(d2x * d2x) + F32(d2y * d2y))))
+            d2x, d2y = F32(d2x / n2), F32(d2y / n2)
+            cs = F32(abs(F32(F32(d1x * d2x) + F32(d1y * d2y))))
+            if cs < TH:      # NaN (degenerate direction) passes, as in the reference
+                continue
+            out.append(i)
+    return out
+
+
+def line_fuse(kl, kf_desc, queries, qdesc, th_cos=0.998, th_low=50):
+    nq = len(queries)
+    bi, bd = np.full(nq, -1, np.int32), np.full(nq, 256, np.int32)
+    for q in range(nq):
+        Q = queries[q]
+        if not (int(Q["flags"]) & 1):
+            continue
+        best_d, best_i = 256, -1
+        for idx in lines_in_area(kl, Q["u1"], Q["v1"], Q["u2"], Q["v2"], Q["radius"], th_cos):
+            lvl = int(kl[idx]["octave"])
+            if lvl < int(Q["pred_level"]) - 1 or lvl > int(Q["pred_level"]):
+                continue
+            d = int(np.unpackbits(np.bitwise_xor(qdesc[q], kf_desc[idx])).sum())
+            if d < best_d:
+                best_d, best_i = d, idx
+        bd[q] = best_d
+        if best_d <= th_low and best_i >= 0:
+            bi[q] = best_i
+    return bi, bd

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|linefuse|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -328,6 +328,48 @@ def make_linematch():
     print("plane_assoc: mode0", n_0, a_0.tolist(), "mode1", n_1, a_1.tolist())
 
 
+def make_linefuse():
+    """LSDmatcher::Fuse window search: the lines of the linematch pairs as KeyFrame lines, the last frame's lines as
+    projected MapLines; kf_desc plays pKF->mDescriptors (rows near the line descriptors so that some fuse)."""
+    from oracle.pyref import linematch_py as lm
+    from psl_slam_b200._lib import LINE_FUSE_QUERY_DTYPE
+    for pair in (0, 1):
+        g = np.load(os.path.join(OUT, f"linematch_pair{pair}.npz"))
+        rng = np.random.default_rng(300 + pair)
+        kl = g["kl_cur"].copy()
+        kl["octave"] = rng.integers(0, 3, len(kl))          # exercise the level gate
+        n = len(kl)
+        kf_desc = rng.integers(0, 256, (max(n + 40, 64), 32), dtype=np.uint8)
+        flips = rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8) & \
+            rng.integers(0, 256, (n, 32), dtype=np.uint8)   # ~1/8 of the bits
+        kf_desc[:n] = g["desc_cur"] ^ np.where(rng.random((n, 1)) < 0.7, flips & rng.integers(0, 256, (n, 32), dtype=np.uint8), flips)
+        kl_l, d_l = g["kl_last"], g["desc_last"]
+        nq = len(kl_l)
+        q = np.zeros(nq, LINE_FUSE_QUERY_DTYPE)
+        jit = rng.normal(0, 2.0, (nq, 4)).astype(np.float32)
+        q["u1"], q["v1"] = kl_l["start_x"] + jit[:, 0], kl_l["start_y"] + jit[:, 1]
+        q["u2"], q["v2"] = kl_l["end_x"] + jit[:, 2], kl_l["end_y"] + jit[:, 3]
+        q["radius"] = (3.0 * np.float32(1.2) ** rng.integers(0, 3, nq)).astype(np.float32) * np.float32(4.0)
+        q["pred_level"] = rng.integers(-1, 4, nq)
+        q["flags"] = (rng.random(nq) < 0.9).astype(np.uint32)
+        if nq > 2:  # degenerate projection (both endpoints equal): NaN direction passes the cosine gate
+            q["u2"][1], q["v2"][1] = q["u1"][1], q["v1"][1]
+        qd = d_l.copy()
+        # some MapLine descriptors equal to the row the reference compares against
+        for i in range(0, min(nq, n), 5):
+            qd[i] = kf_desc[i % n]
+        bi, bd = lm.line_fuse(kl, kf_desc, q, qd, 0.998, 50)
+        bi2, bd2 = lm.line_fuse(kl, kf_desc, q, qd, 0.9, 80)
+        area = [np.array(lm.lines_in_area(kl, q["u1"][i], q["v1"][i], q["u2"][i], q["v2"][i], q["radius"][i], 0.998), np.int32)
+                for i in range(min(nq, 16))]
+        np.savez_compressed(os.path.join(OUT, f"linefuse_pair{pair}.npz"), kl=kl, kf_desc=kf_desc, queries=q, qdesc=qd,
+                            best_idx=bi, best_dist=bd, best_idx_loose=bi2, best_dist_loose=bd2,
+                            area_cat=np.concatenate(area) if area else np.zeros(0, np.int32),
+                            area_len=np.array([len(x) for x in area], np.int32))
+        print(f"linefuse_pair{pair}: lines {n} queries {int((q['flags'] & 1).sum())} fused {(bi >= 0).sum()} "
+              f"loose {(bi2 >= 0).sum()} with candidates {(bd < 256).sum()}")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(OUT, exist_ok=True)
@@ -343,3 +385,5 @@ if __name__ == "__main__":
         make_line()
     if what in ("linematch", "all"):
         make_linematch()
+    if what in ("linefuse", "all"):
+        make_linefuse()

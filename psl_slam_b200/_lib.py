@@ -45,6 +45,8 @@ LINE_QUERY_DTYPE = np.dtype([("x1", "<f4"), ("y1", "<f4"), ("x2", "<f4"), ("y2",
                              ("normal", "<f8", (3,)), ("flags", "<u4"), ("pad_", "<u4")])  # psl_line_query, 72 B
 FUSE_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("u_right", "<f4"), ("radius", "<f4"), ("pred_level", "<i4"),
                              ("flags", "<u4")])  # psl_fuse_query
+LINE_FUSE_QUERY_DTYPE = np.dtype([("u1", "<f4"), ("v1", "<f4"), ("u2", "<f4"), ("v2", "<f4"), ("radius", "<f4"),
+                                  ("pred_level", "<i4"), ("flags", "<u4")])  # psl_line_fuse_query, 28 B
 Q_VALID, Q_CLAIMS = 1, 2
 
 
@@ -139,7 +141,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
-           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation"]
+           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation", "psl_line_fuse"]
 
 _lib = None
 
@@ -192,6 +194,7 @@ def lib():
         L.psl_match_triangulation.argtypes = [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p, _p]
         L.psl_match_fuse.argtypes = [_p, _p, _p, _p, _i, _p, _i, _i, _p, _p]
         L.psl_line_search_triangulation.argtypes = [_p, _p, _p, _i, _p, _p, _i, _f, _f, _i, _p, _p]
+        L.psl_line_fuse.argtypes = [_p, _p, _i, _p, _i, _p, _p, _i, _f, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L
     return _lib

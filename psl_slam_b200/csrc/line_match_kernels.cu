@@ -184,6 +184,60 @@ __global__ void line_triang_kernel(LineSet A, const int32_t* __restrict__ m21, i
   else atomicAdd(nmatches + b, 1);
 }
 
+// LSDmatcher::Fuse window search (LSDmatcher.cpp:920-953) over KeyFrame::GetLinesInArea (KeyFrame.cc:857-891).
+// The float / double mix of the reference is kept: the midpoint offsets are formed and squared in double and their
+// sum is narrowed to float before the comparison with r * r; directions are normalised in float.  A degenerate
+// (zero-length) direction gives NaN, which fails `CosSita < TH` and therefore passes, as in the reference.
+__global__ void __launch_bounds__(128)
+    line_fuse_kernel(const psl_keyline* __restrict__ kl, int n_lines, const uint8_t* __restrict__ kf_desc,
+                     const psl_line_fuse_query* __restrict__ queries, const uint8_t* __restrict__ qdesc, int nq,
+                     float th_cos, int th_low, int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const psl_line_fuse_query Q = queries[q];
+  unsigned best = (256u << 16) | 0xFFFFu;  // distance << 16 | line: the minimum is the earliest smallest distance
+  if (Q.flags & PSL_Q_VALID) {
+    float d1x = __fsub_rn(Q.u1, Q.u2), d1y = __fsub_rn(Q.v1, Q.v2);
+    const float n1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
+    d1x = __fdiv_rn(d1x, n1);
+    d1y = __fdiv_rn(d1y, n1);
+    const double mx = 0.5 * (double)__fadd_rn(Q.u1, Q.u2), my = 0.5 * (double)__fadd_rn(Q.v1, Q.v2);
+    const float r2 = __fmul_rn(Q.radius, Q.radius);
+    const uint4* qd = reinterpret_cast<const uint4*>(qdesc) + 2 * (size_t)q;
+    const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+    for (int i = lane; i < n_lines; i += 32) {
+      const psl_keyline k = kl[i];
+      const double ex = mx - (double)k.pt_x, ey = my - (double)k.pt_y;
+      const float distance = (float)__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+      if (distance > r2) continue;
+      float d2x = __fsub_rn(k.start_x, k.end_x), d2y = __fsub_rn(k.start_y, k.end_y);
+      const float n2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+      d2x = __fdiv_rn(d2x, n2);
+      d2y = __fdiv_rn(d2y, n2);
+      const float cs = fabsf(__fadd_rn(__fmul_rn(d1x, d2x), __fmul_rn(d1y, d2y)));
+      if (cs < th_cos) continue;
+      if (k.octave < Q.pred_level - 1 || k.octave > Q.pred_level) continue;
+      const uint4* d = reinterpret_cast<const uint4*>(kf_desc) + 2 * (size_t)i;
+      const unsigned key = ((unsigned)ham256(q0, q1, __ldg(d), __ldg(d + 1)) << 16) | (unsigned)i;
+      best = min(best, key);
+    }
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  if (lane == 0) {
+    const int dist = (int)(best >> 16);
+    best_idx[q] = (dist <= th_low && (best & 0xFFFFu) != 0xFFFFu) ? (int)(best & 0xFFFFu) : -1;
+    if (best_dist) best_dist[q] = dist;
+  }
+}
+
+void launch_line_fuse(const psl_keyline* kl, int n_lines, const uint8_t* kf_desc, const psl_line_fuse_query* queries,
+                      const uint8_t* qdesc, int nq, float th_cos, int th_low, int32_t* best_idx, int32_t* best_dist,
+                      cudaStream_t st) {
+  if (nq <= 0) return;
+  line_fuse_kernel<<<(nq + 3) / 4, 128, 0, st>>>(kl, n_lines, kf_desc, queries, qdesc, nq, th_cos, th_low, best_idx,
+                                                 best_dist);
+}
+
 void launch_line_triang(const LineSet& A, const int32_t* m21, int cap2, const uint8_t* ml1, const uint8_t* ml2,
                         int is_double, int32_t* m12, int32_t* nmatches, int B, cudaStream_t st) {
   cudaMemsetAsync(nmatches, 0, (size_t)B * sizeof(int32_t), st);

@@ -26,6 +26,10 @@ void launch_line_mutual(const LineSet& A, const int32_t* m21, int cap2, int32_t*
                         cudaStream_t st);
 void launch_line_triang(const LineSet& A, const int32_t* m21, int cap2, const uint8_t* ml1, const uint8_t* ml2,
                         int is_double, int32_t* m12, int32_t* nmatches, int B, cudaStream_t st);
+// window search of LSDmatcher::Fuse: one warp per query over the n_lines KeyLines of one KeyFrame
+void launch_line_fuse(const psl_keyline* kl, int n_lines, const uint8_t* kf_desc, const psl_line_fuse_query* queries,
+                      const uint8_t* qdesc, int nq, float th_cos, int th_low, int32_t* best_idx, int32_t* best_dist,
+                      cudaStream_t st);
 // 3 launches: line grid cells, static keys, ordered resolve
 void launch_line_projection(const LineSet& F, const double* lineeq, const double* lines3d, const psl_line_query* queries,
                             const uint8_t* qdesc, const int32_t* nq, int qcap, int max_nq, float min_x, float min_y,

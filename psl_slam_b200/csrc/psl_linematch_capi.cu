@@ -180,6 +180,33 @@ int psl_line_search_triangulation(psl_ctx* ctx, const uint8_t* desc1, const uint
   return check_status(ctx);
 }
 
+int psl_line_fuse(psl_ctx* ctx, const psl_keyline* kl, int32_t n_lines, const uint8_t* kf_desc, int32_t n_desc,
+                  const psl_line_fuse_query* queries, const uint8_t* query_desc, int32_t nq, float th_cos, int32_t th_low,
+                  int32_t* best_idx, int32_t* best_dist) {
+  if (!ctx) return PSL_E_INVALID;
+  if (nq < 0 || n_lines < 0 || n_lines > 65534 || n_desc < n_lines || (n_lines > 0 && (!kl || !kf_desc)) ||
+      (nq > 0 && (!queries || !query_desc || !best_idx)))
+    return fail(ctx, PSL_E_INVALID, "bad argument (kf_desc needs a row per line: LSDmatcher.cpp:938)");
+  if (nq == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  PSL_UP(ctx->m_misc[0], kl, (size_t)n_lines * sizeof(psl_keyline));
+  PSL_UP(ctx->m_desc, kf_desc, (size_t)n_lines * 32);
+  PSL_UP(ctx->m_misc[3], queries, (size_t)nq * sizeof(psl_line_fuse_query));
+  PSL_UP(ctx->m_qdesc, query_desc, (size_t)nq * 32);
+  PSL_ENS(ctx->m_assign, (size_t)nq * 4);
+  PSL_ENS(ctx->m_accepted, (size_t)nq * 4);
+  cudaStream_t st = ctx->stream;
+  size_t e = prof_mark(ctx);
+  launch_line_fuse(ctx->m_misc[0].as<psl_keyline>(), n_lines, ctx->m_desc.as<uint8_t>(),
+                   ctx->m_misc[3].as<psl_line_fuse_query>(), ctx->m_qdesc.as<uint8_t>(), nq, th_cos, th_low,
+                   ctx->m_assign.as<int32_t>(), ctx->m_accepted.as<int32_t>(), st);
+  prof_span(ctx, 15, e, 1);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(best_idx, ctx->m_assign.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  if (best_dist) PSL_CK(cudaMemcpyAsync(best_dist, ctx->m_accepted.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
 int psl_line_match_projection(psl_ctx* ctx, const psl_line_frame_view* fv, const psl_line_query* queries,
                               const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in, int32_t mode,
                               float nn_ratio, int32_t* assign, int32_t* nmatches) {

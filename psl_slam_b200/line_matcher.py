@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import KEYLINE_DTYPE, LINE_QUERY_DTYPE, make_line_frame_view
+from ._lib import KEYLINE_DTYPE, LINE_FUSE_QUERY_DTYPE, LINE_QUERY_DTYPE, make_line_frame_view
 from .orb import Context, _ptr
 
 
@@ -99,6 +99,19 @@ class LSDmatcher:
                                                                 C.c_float(th), int(as_pairs or isDouble), _ptr(out),
                                                                 C.byref(nm)))
         return out, nm.value
+
+    def Fuse(self, keylines, kf_descriptors, queries, map_line_desc, th_cos=0.998):
+        """Window search of Fuse(pKF, vpMapLines, th) — LSDmatcher.cpp:847-984: per projected MapLine (queries:
+        LINE_FUSE_QUERY_DTYPE) the line of KeyFrame::GetLinesInArea (KeyFrame.cc:857-891) at level pred-1..pred with
+        the smallest Hamming distance to pKF->mDescriptors.row(idx) (:938).  Returns (best_idx [nq] or -1 when the
+        distance exceeds TH_LOW, best_dist [nq]); the replace-or-add bookkeeping stays with the caller."""
+        kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+        kd, qd = _u8(kf_descriptors), _u8(map_line_desc)
+        q = np.ascontiguousarray(queries, LINE_FUSE_QUERY_DTYPE)
+        bi, bd = np.full(len(q), -1, np.int32), np.full(len(q), 256, np.int32)
+        self.ctx.check(_lib.lib().psl_line_fuse(self.ctx.handle, _ptr(kl), len(kl), _ptr(kd), len(kd), _ptr(q), _ptr(qd),
+                                                len(q), C.c_float(th_cos), int(self.TH_LOW), _ptr(bi), _ptr(bd)))
+        return bi, bd
 
     def _project(self, frame: LineFrameData, queries, qdesc, claimed, mode):
         fv, keep = make_line_frame_view(frame.kl_un, frame.ldesc, frame.lineeq, frame.lines3d, frame.bounds)

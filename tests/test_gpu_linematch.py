@@ -136,3 +136,40 @@ def test_line_search_triangulation_vs_oracle(orc, name):
         want, wn = orc.line_search_triangulation(g["desc_last"], ml1, g["desc_cur"], ml2, 0.95, th, as_pairs or dbl)
         got, gn = m.SearchForTriangulation(g["desc_last"], ml1, g["desc_cur"], ml2, as_pairs, dbl)
         assert np.array_equal(got, want) and gn == wn
+
+
+@pytest.mark.parametrize("name", golden_names("linefuse_"))
+def test_line_fuse_vs_golden_and_oracle(orc, name):
+    from psl_slam_b200 import LSDmatcher, PslError
+    g = load_golden(name)
+    m = LSDmatcher(0.75)
+    bi, bd = m.Fuse(g["kl"], g["kf_desc"], g["queries"], g["qdesc"])
+    assert np.array_equal(bi, g["best_idx"]) and np.array_equal(bd, g["best_dist"])
+    bi, bd = m.Fuse(g["kl"], g["kf_desc"], g["queries"], g["qdesc"], th_cos=0.9)
+    want_i, want_d, _ = orc.line_fuse(g["kl"], g["kf_desc"], g["queries"], g["qdesc"], 0.9, 50)
+    assert np.array_equal(bi, want_i) and np.array_equal(bd, want_d)
+    # a larger synthetic case against the oracle: 1500 lines, 3000 queries, mixed levels, degenerate lines
+    rng = np.random.default_rng(11)
+    reps = 1500 // len(g["kl"]) + 1
+    kl = np.tile(g["kl"], reps)[:1500].copy()
+    for f in ("pt_x", "start_x", "end_x"):
+        kl[f] += np.repeat(rng.uniform(-40, 40, reps), len(g["kl"]))[:1500].astype(np.float32)
+    kl["end_x"][7], kl["end_y"][7] = kl["start_x"][7], kl["start_y"][7]
+    kd = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    q = np.tile(g["queries"], 3000 // len(g["queries"]) + 1)[:3000].copy()
+    q["radius"] = rng.uniform(5, 60, 3000).astype(np.float32)
+    q["pred_level"] = rng.integers(-1, 4, 3000)
+    qd = kd[rng.integers(0, 1500, 3000)] ^ (rng.integers(0, 256, (3000, 32), dtype=np.uint8) & rng.integers(0, 256, (3000, 32), dtype=np.uint8) & rng.integers(0, 256, (3000, 32), dtype=np.uint8))
+    near, _, _ = orc.line_fuse(kl, kd, q, qd, 0.95, 256)   # any candidate at all: make half of those queries fusable
+    hit = np.flatnonzero(near >= 0)[::2]
+    qd[hit] = kd[near[hit]] ^ (qd[hit] & rng.integers(0, 256, (len(hit), 32), dtype=np.uint8) & 0x11)
+    bi, bd = m.Fuse(kl, kd, q, qd, th_cos=0.95)
+    want_i, want_d, wn = orc.line_fuse(kl, kd, q, qd, 0.95, 50)
+    assert np.array_equal(bi, want_i) and np.array_equal(bd, want_d) and wn > 200
+    # empty inputs and the descriptor-row contract
+    bi, bd = m.Fuse(g["kl"][:0], g["kf_desc"], g["queries"], g["qdesc"])
+    assert (bi == -1).all() and (bd == 256).all()
+    bi, bd = m.Fuse(g["kl"], g["kf_desc"], g["queries"][:0], g["qdesc"][:0])
+    assert len(bi) == 0
+    with pytest.raises(PslError):
+        m.Fuse(g["kl"], g["kf_desc"][: len(g["kl"]) - 1], g["queries"], g["qdesc"])

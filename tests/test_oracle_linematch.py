@@ -79,3 +79,23 @@ def test_line_search_triangulation(orc, name):
     bf = orc.line_frame_bf_match(g["desc_last"], g["desc_cur"], 0.95, 80)
     want2 = np.where((bf >= 0) & (ml1 == 0) & (ml2[np.maximum(bf, 0)] == 0), bf, -1)
     assert np.array_equal(m2, want2) and n2 == int((want2 >= 0).sum())
+
+
+@pytest.mark.parametrize("name", golden_names("linefuse_"))
+def test_line_fuse(orc, name):
+    """LSDmatcher::Fuse window search (KeyFrame::GetLinesInArea + level gate + min Hamming vs pKF->mDescriptors rows)."""
+    g = load_golden(name)
+    bi, bd, n = orc.line_fuse(g["kl"], g["kf_desc"], g["queries"], g["qdesc"], 0.998, 50)
+    assert np.array_equal(bi, g["best_idx"]) and np.array_equal(bd, g["best_dist"]) and n == int((g["best_idx"] >= 0).sum())
+    assert n > 5
+    bi, bd, n = orc.line_fuse(g["kl"], g["kf_desc"], g["queries"], g["qdesc"], 0.9, 80)
+    assert np.array_equal(bi, g["best_idx_loose"]) and np.array_equal(bd, g["best_dist_loose"])
+    # edge cases: no lines, no queries, every query invalid
+    q = g["queries"].copy()
+    bi, bd, n = orc.line_fuse(g["kl"][:0], g["kf_desc"], q, g["qdesc"])
+    assert n == 0 and (bi == -1).all() and (bd == 256).all()
+    bi, bd, n = orc.line_fuse(g["kl"], g["kf_desc"], q[:0], g["qdesc"][:0])
+    assert n == 0 and len(bi) == 0
+    q["flags"] = 0
+    bi, bd, n = orc.line_fuse(g["kl"], g["kf_desc"], q, g["qdesc"])
+    assert n == 0 and (bi == -1).all()
