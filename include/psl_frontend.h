@@ -217,7 +217,12 @@ int psl_hamming_knn2(psl_ctx* ctx, const uint8_t* q, int32_t nq, const uint8_t* 
 /* ORBmatcher::SearchByProjection, both the Frame<-LastFrame form (ORBmatcher.cc:1328-1470, mode 0) and the
  * Frame<-local-map-points form (:45-129, mode 1).  claimed_in[n] (may be NULL) marks keypoints whose current
  * MapPoint has Observations()>0 before the call.  assign[n] = index of the query whose point ends up in
- * mvpMapPoints[i], or -1; *nmatches = the function's return value. */
+ * mvpMapPoints[i], or -1; *nmatches = the function's return value.
+ * The relocalization overload SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (:1472-1599,
+ * Tracking.cc:2142,2156) is mode 0 with other settings: frame->u_right = NULL (it has no right-coordinate gate),
+ * every valid query flagged PSL_Q_CLAIMS and claimed_in[i] = (CurrentFrame.mvpMapPoints[i] != NULL) (:1545-1546 skips
+ * any keypoint that holds a MapPoint, old or just assigned), levels pred-1 .. pred+1, angle = pKF->mvKeysUn[i].angle,
+ * th_dist = ORBdist (tests: reloc_* goldens, made by a restatement of that overload alone). */
 int psl_match_projection(psl_ctx* ctx, const psl_frame_view* frame, const psl_proj_query* queries,
                          const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in,
                          const psl_match_params* params, int32_t* assign, int32_t* nmatches);

@@ -123,6 +123,21 @@ def make_match():
                             kf_nodes=kcsr[0], kf_offs=kcsr[1], kf_idx=kcsr[2], f_nodes=fcsr[0], f_offs=fcsr[1],
                             f_idx=fcsr[2], bow_match=match, bow_nmatches=np.int32(nmb), knn_idx=idx2, knn_dist=dist2)
         print(f"match_pair{pair}: queries {int((q['flags'] & 1).sum())} proj-matches {nm} / mode1 {nm1} / bow {nmb}")
+        # relocalization overload (ORBmatcher.cc:1472-1599): the same points read as pKF's MapPoints, window
+        # pred-1..pred+1 (pred = the octave they were seen at, jittered), some keypoints already hold a MapPoint
+        rng2 = np.random.default_rng(500 + pair)
+        q2 = q.copy()
+        pred = np.clip(kl["octave"] + rng2.integers(-1, 2, n), 0, P.nlevels - 1)
+        q2["min_level"], q2["max_level"] = pred - 1, pred + 1
+        q2["radius"] = (np.float32(10.0 if pair == 0 else 20.0) * scale[pred]).astype(np.float32)
+        q2["flags"] = (has_mp & (rng2.random(n) < 0.85)).astype(np.uint32)      # not bad, not in sAlreadyFound
+        held = rng2.random(len(dc)) < 0.25
+        for orb_dist, tag in ((100, "a"), (64, "b")):
+            ar, nr = match_py.search_by_projection_keyframe(fv, q2, dl, held, orb_dist, True)
+            np.savez_compressed(os.path.join(OUT, f"reloc_pair{pair}{tag}.npz"), kps_cur=kc, desc_cur=dc,
+                                bounds=np.array(bounds, np.float32), queries=q2, desc_kf=dl,
+                                held=held.astype(np.uint8), orb_dist=np.int32(orb_dist), assign=ar, nmatches=np.int32(nr))
+            print(f"reloc_pair{pair}{tag}: queries {int((q2['flags'] & 1).sum())} matches {nr}")
 
 
 def make_triangulation():

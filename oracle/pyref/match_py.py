@@ -146,6 +146,44 @@ def search_by_projection(fv: FrameView, queries, qdesc, claimed_in, mode, th_dis
     return assign, nm
 
 
+def search_by_projection_keyframe(fv: FrameView, queries, kf_desc, has_mappoint_cur, orb_dist, check_ori=True):
+    """SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist) — ORBmatcher.cc:1472-1599,
+    written from that overload on its own (not through search_by_projection): candidates of
+    GetFeaturesInArea(u, v, radius, pred-1, pred+1) that hold no MapPoint yet (:1545-1546, which includes the ones
+    this call has just filled), smallest distance, accept <= ORBdist, rotation histogram on pKF's keypoint angle.
+    queries: (u, v, radius, min_level = pred-1, max_level = pred+1, -, angle = pKF->mvKeysUn[i].angle, flags & 1)."""
+    mp = [None if not h else -2 for h in has_mappoint_cur]      # mvpMapPoints: -2 = a MapPoint from before the call
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for qi, q in enumerate(queries):
+        if not (q["flags"] & 1):
+            continue
+        cand = fv.features_in_area(q["u"], q["v"], q["radius"], int(q["min_level"]), int(q["max_level"]))
+        if not cand:
+            continue
+        best, best_i = 256, -1
+        for i2 in cand:
+            if mp[i2] is not None:
+                continue
+            d = popcount_dist(kf_desc[qi], fv.desc[i2])
+            if d < best:
+                best, best_i = d, i2
+        if best <= orb_dist:
+            mp[best_i] = qi
+            nm += 1
+            if check_ori:
+                hist[rot_bin(q["angle"], fv.angle[best_i])].append(best_i)
+    if check_ori:
+        keep = three_maxima([len(h) for h in hist])
+        for b in range(HISTO):
+            if b not in keep:
+                for i in hist[b]:
+                    mp[i] = None
+                    nm -= 1
+    assign = np.array([m if (m is not None and m >= 0) else -1 for m in mp], np.int32)
+    return assign, nm
+
+
 def search_by_bow(kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv, nn_ratio=0.7, th_low=50, check_ori=True):
     """kf_fv / f_fv: dict node_id -> list of indices (DBoW2::FeatureVector)."""
     nf = len(f_desc)

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import FUSE_QUERY_DTYPE, KP_DTYPE, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view, make_keyframe_view
+from ._lib import FUSE_QUERY_DTYPE, KP_DTYPE, Q_CLAIMS, Q_VALID, QUERY_DTYPE, MatchParams, make_feature_vector, make_frame_view, make_keyframe_view
 from .orb import Context, _ptr
 
 
@@ -69,6 +69,19 @@ class ORBmatcher:
     def SearchByProjectionMapPoints(self, frame: FrameData, queries, mp_desc, claimed=None):
         """SearchByProjection(Frame &F, const vector<MapPoint*>&, th) — ORBmatcher.cc:45-129."""
         return self._project(frame, queries, mp_desc, claimed, 1, self.TH_HIGH, self.mfNNratio, False)
+
+    def SearchByProjectionKeyFrame(self, cur: FrameData, queries, kf_desc, has_mappoint_cur, ORBdist):
+        """SearchByProjection(Frame &CurrentFrame, KeyFrame *pKF, sAlreadyFound, th, ORBdist) — ORBmatcher.cc:1472-1599
+        (relocalization, Tracking.cc:2142, 2156).  It is the Frame<-LastFrame form with other settings, so it runs
+        through the same entry point (mode 0): no right-coordinate gate (u_right = NULL), every match claims its
+        keypoint (:1545-1546 skips any keypoint that holds a MapPoint, old or just assigned) and the threshold is
+        ORBdist.  queries: u, v, radius = th * mvScaleFactors[pred], levels pred-1 .. pred+1, angle of pKF's keypoint,
+        PSL_Q_VALID for the points that pass :1492-1525."""
+        q = np.ascontiguousarray(queries, QUERY_DTYPE).copy()
+        q["flags"] = np.where(q["flags"] & Q_VALID, Q_VALID | Q_CLAIMS, 0).astype(np.uint32)
+        view = FrameData(cur.kps_un, cur.desc, None, cur.bounds)
+        return self._project(view, q, kf_desc, has_mappoint_cur, 0, int(ORBdist), self.mfNNratio,
+                             self.mbCheckOrientation)
 
     def SearchByBoW(self, kf_desc, kf_angle, kf_valid, kf_fv, f_desc, f_angle, f_fv):
         """SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — ORBmatcher.cc:159-288.

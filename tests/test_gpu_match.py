@@ -153,3 +153,13 @@ def test_fuse_search_vs_golden_and_oracle(orc, name):
     want_i, want_d = orc.match_fuse(g["kps"], None, g["desc"], tuple(g["bounds"]), q, g["qdesc"], g["inv_sigma2"], 50)
     bi, bd = m.FuseSearch(FrameData(g["kps"], g["desc"], None, tuple(g["bounds"])), q, g["qdesc"], g["inv_sigma2"])
     assert np.array_equal(bi, want_i) and np.array_equal(bd, want_d)
+
+
+@pytest.mark.parametrize("name", golden_names("reloc_"))
+def test_search_by_projection_keyframe_vs_golden(name):
+    """SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) — ORBmatcher.cc:1472-1599."""
+    from psl_slam_b200 import FrameData, ORBmatcher
+    g = load_golden(name)
+    cur = FrameData(g["kps_cur"], g["desc_cur"], None, tuple(g["bounds"]))
+    a, n = ORBmatcher(0.9, True).SearchByProjectionKeyFrame(cur, g["queries"], g["desc_kf"], g["held"], int(g["orb_dist"]))
+    assert np.array_equal(a, g["assign"]) and n == int(g["nmatches"])

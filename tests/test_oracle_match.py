@@ -75,3 +75,16 @@ def test_fuse_search(orc, name):
     g = load_golden(name)
     bi, bd = orc.match_fuse(g["kps"], g["u_right"], g["desc"], tuple(g["bounds"]), g["queries"], g["qdesc"], g["inv_sigma2"], 50)
     assert np.array_equal(bi, g["best_idx"]) and np.array_equal(bd, g["best_dist"]) and (bi >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("name", golden_names("reloc_"))
+def test_search_by_projection_keyframe(orc, name):
+    """The relocalization overload (ORBmatcher.cc:1472-1599) is mode 0 of the projection matcher with no right-coordinate
+    gate, every match claiming its keypoint, the pre-filled keypoints as claimed_in and ORBdist as threshold; the golden
+    comes from a restatement written from that overload alone."""
+    g = load_golden(name)
+    q = g["queries"].copy()
+    q["flags"] = np.where(q["flags"] & 1, 3, 0).astype(np.uint32)
+    a, n = orc.match_projection(g["kps_cur"], None, g["desc_cur"], tuple(g["bounds"]), q, g["desc_kf"], g["held"], 0,
+                                int(g["orb_dist"]), 0.9, True)
+    assert np.array_equal(a, g["assign"]) and n == int(g["nmatches"]) and n > 100
