@@ -122,6 +122,25 @@ int psl_orb_extract_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t B, in
                               int64_t frame_stride, psl_keypoint* d_kps, uint8_t* d_desc, int32_t cap,
                               int32_t* d_n);
 
+/* Camera matrix and distortion of Tracking's settings (mK, mDistCoef: src/Tracking.cc:52-77): k1, k2, p1, p2, k3. */
+typedef struct psl_distortion {
+  float fx, fy, cx, cy;
+  float k1, k2, p1, p2, k3;
+} psl_distortion;
+
+/* Frame::UndistortKeyPoints (src/Frame.cc:1062-1092; SURVEY "next" row N3): mvKeysUn = mvKeys with pt replaced by
+ * cv::undistortPoints(pt, mK, mDistCoef, Mat(), mK) — OpenCV's five fixed-point iterations in double on the
+ * normalised coordinates, re-projected with mK and rounded to float; with k1 == 0 the keypoints are copied (:1064-1068).
+ * HOST pointers; kps_un may alias kps. */
+int psl_undistort_keypoints(psl_ctx* ctx, const psl_keypoint* kps, int32_t n, const psl_distortion* cam,
+                            psl_keypoint* kps_un);
+/* Batched, DEVICE pointers, asynchronous: frame b owns rows [b*cap, b*cap + d_n[b]) of both arrays. */
+int psl_undistort_keypoints_dev(psl_ctx* ctx, const psl_keypoint* d_kps, const int32_t* d_n, int32_t cap, int32_t B,
+                                const psl_distortion* cam, psl_keypoint* d_kps_un);
+/* Frame::ComputeImageBounds (src/Frame.cc:1135-1163): the undistorted image corners give
+ * bounds[4] = mnMinX, mnMinY, mnMaxX, mnMaxY (the order psl_frame_view uses); k1 == 0: 0, 0, cols, rows. */
+int psl_image_bounds(psl_ctx* ctx, int32_t cols, int32_t rows, const psl_distortion* cam, float* bounds);
+
 /* Tracking::GrabImageRGBD input conversion (src/Tracking.cc:219-235; SURVEY "next" row N3, kernel K0):
  *   cvtColor(RGB|BGR|RGBA|BGRA -> GRAY)  Y = (R*9798 + G*19235 + B*3735 + 16384) >> 15   (OpenCV 4.x Q15 arithmetic)
  *   imDepth.convertTo(CV_32F, mDepthMapFactor)
@@ -493,6 +512,28 @@ int64_t psl_launch_count(const psl_ctx* ctx);
  * *n = number of bytes (0,1,4) or entries (2,3,5) written. */
 int psl_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, int32_t level, void* out, int64_t cap_bytes,
                     int64_t* n);
+
+/* One entry of Frame::intersection_lines_plane (the junctions CPartiallyRecoverConnectivity / convertFansToKeyLines
+ * found, Frame.cc:504-511): the two line indices, the 2-D junction and its 3-D position in the camera frame. */
+typedef struct psl_line_junction {
+  int32_t l1, l2;
+  float cross2d_x, cross2d_y;
+  double cross3d[3];
+} psl_line_junction;
+
+/* The plane hypotheses Frame::ExtractLSD builds from coplanar intersecting line pairs (src/Frame.cc:512-645 with
+ * Frame::OldPlane :474-487; SURVEY "next" row N2, the producer of psl_plane_assoc's inputs).  Per junction, in order:
+ * le_l[i*6..] = the two normalised 2-D line equations sp x ep / sqrt(l0^2 + l1^2) (mvle_l, pushed for every junction);
+ * skipped if either line has mvLineEq == (0,0,0) or mvLines3D == 0 (Eigen isZero); normal = mvLineEq[l1] x mvLineEq[l2]
+ * normalised in float; the signed distances of the four 3-D endpoints and the junction must span <= 0.05; plane =
+ * (normal, -mean distance), flipped to d >= 0; dropped if OldPlane (|d - d'| <= 0.2 and |n.n'| >= 0.9397 against a plane
+ * already kept in this call).  kl_un: mvKeylinesUn; line_eq [n_lines*3] float: mvLineEq; lines3d [n_lines*6] double:
+ * mvLines3D first/second.  Outputs for the kept hypotheses, in order: planes [cap*4] (mvPlanes), normals [cap*3]
+ * (mvPlaneNormal), junction_of [cap] = index of the junction (gives mvPlaneLineNo, CrossPoint_3D, CrossPoint_2D);
+ * *n_planes = their number.  More than cap hypotheses: PSL_E_CAPACITY. */
+int psl_plane_hypotheses(psl_ctx* ctx, const psl_keyline* kl_un, const float* line_eq, const double* lines3d,
+                         int32_t n_lines, const psl_line_junction* junctions, int32_t n_junctions, double* le_l,
+                         float* planes, double* normals, int32_t* junction_of, int32_t cap, int32_t* n_planes);
 
 #ifdef __cplusplus
 }

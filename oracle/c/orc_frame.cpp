@@ -3,6 +3,7 @@
 // UnprojectStereo (src/Frame.cc:1342-1381), Frame::UpdatePoseMatrices (mRwc, mOw) and the per-point
 // prologue of ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (src/ORBmatcher.cc:1339-1393).
 // cv::Mat products of CV_32F matrices accumulate in double and round once (OpenCV gemm).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -19,6 +20,61 @@ inline void affine(const float* R, int rs, const float* x, const float* t, float
 }  // namespace
 
 extern "C" {
+
+// cv::undistortPoints(src, dst, K, D, noArray(), K) of one point (OpenCV 4.x cvUndistortPointsInternal, default
+// criteria = 5 iterations): double arithmetic on the float inputs; k4..k6, thin prism and tilt terms are zero here.
+static void undistort_point(float u_in, float v_in, const psl_distortion& c, float* out) {
+  const double fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy, k1 = c.k1, k2 = c.k2, p1 = c.p1, p2 = c.p2, k3 = c.k3;
+  const double ifx = 1. / fx, ify = 1. / fy;
+  const double u = u_in, v = v_in;
+  double x = (u - cx) * ifx, y = (v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+    if (icdist < 0) {
+      x = (u - cx) * ifx;
+      y = (v - cy) * ify;
+      break;
+    }
+    const double deltaX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+    const double deltaY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+    x = (x0 - deltaX) * icdist;
+    y = (y0 - deltaY) * icdist;
+  }
+  const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+  out[0] = (float)(xx * ww);
+  out[1] = (float)(yy * ww);
+}
+
+// Frame::UndistortKeyPoints, Frame.cc:1062-1092
+void orc_undistort_keypoints(const psl_keypoint* kps, int n, const psl_distortion* cam, psl_keypoint* kps_un) {
+  for (int i = 0; i < n; ++i) {
+    psl_keypoint k = kps[i];
+    if (cam->k1 != 0.f) {  // :1064
+      float p[2];
+      undistort_point(k.x, k.y, *cam, p);
+      k.x = p[0];
+      k.y = p[1];
+    }
+    kps_un[i] = k;
+  }
+}
+
+// Frame::ComputeImageBounds, Frame.cc:1135-1163; bounds = mnMinX, mnMinY, mnMaxX, mnMaxY
+void orc_image_bounds(int cols, int rows, const psl_distortion* cam, float* bounds) {
+  if (cam->k1 == 0.f) {
+    bounds[0] = 0.f; bounds[1] = 0.f; bounds[2] = (float)cols; bounds[3] = (float)rows;
+    return;
+  }
+  const float in[4][2] = {{0.f, 0.f}, {(float)cols, 0.f}, {0.f, (float)rows}, {(float)cols, (float)rows}};
+  float m[4][2];
+  for (int i = 0; i < 4; ++i) undistort_point(in[i][0], in[i][1], *cam, m[i]);
+  bounds[0] = std::min(m[0][0], m[2][0]);
+  bounds[2] = std::max(m[1][0], m[3][0]);
+  bounds[1] = std::min(m[0][1], m[1][1]);
+  bounds[3] = std::max(m[2][1], m[3][1]);
+}
 
 // mvuRight / mvDepth for every keypoint (zero distortion: mvKeysUn == mvKeys)
 void orc_stereo_from_rgbd(const psl_keypoint* kps, int n, const uint16_t* depth, int w, int h, int stride_px,

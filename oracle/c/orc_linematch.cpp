@@ -360,6 +360,78 @@ int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query
   return nmatches;
 }
 
+// The plane hypotheses of Frame::ExtractLSD, Frame.cc:512-645 (+ Frame::OldPlane :474-487).  Returns the number of
+// hypotheses (which may exceed cap; only the first cap are stored).
+int orc_plane_hypotheses(const psl_keyline* kl_un, const float* line_eq, const double* lines3d, int n_lines,
+                         const psl_line_junction* js, int nj, double* le_l, float* planes, double* normals,
+                         int32_t* junction_of, int cap) {
+  (void)n_lines;
+  std::vector<float> kept;  // mvPlanes, 4 floats each (all of them, also beyond cap: OldPlane reads them)
+  int np = 0;
+  auto is_zero3 = [](const double* v) {  // Eigen isZero(): |x| <= 1e-12 for every coefficient
+    return std::fabs(v[0]) <= 1e-12 && std::fabs(v[1]) <= 1e-12 && std::fabs(v[2]) <= 1e-12;
+  };
+  for (int i = 0; i < nj; ++i) {
+    const int l1 = js[i].l1, l2 = js[i].l2;
+    for (int s = 0; s < 2; ++s) {  // :522-528 le_l = sp x ep / sqrt(le0^2 + le1^2), homogeneous points (x, y, 1)
+      const psl_keyline& k = kl_un[s == 0 ? l1 : l2];
+      const double ax = k.start_x, ay = k.start_y, bx = k.end_x, by = k.end_y;
+      const double c0 = ay * 1.0 - 1.0 * by, c1 = 1.0 * bx - ax * 1.0, c2 = ax * by - ay * bx;
+      const double nrm = std::sqrt(c0 * c0 + c1 * c1);
+      le_l[6 * i + 3 * s] = c0 / nrm;
+      le_l[6 * i + 3 * s + 1] = c1 / nrm;
+      le_l[6 * i + 3 * s + 2] = c2 / nrm;
+    }
+    const float* e1 = line_eq + 3 * l1;
+    const float* e2 = line_eq + 3 * l2;
+    if (e1[0] == 0 && e1[1] == 0 && e1[2] == 0) continue;                     // :531-534
+    if (e2[0] == 0 && e2[1] == 0 && e2[2] == 0) continue;
+    const double* L1 = lines3d + 6 * l1;
+    const double* L2 = lines3d + 6 * l2;
+    if (is_zero3(L1) && is_zero3(L1 + 3)) continue;                            // :537-540
+    if (is_zero3(L2) && is_zero3(L2 + 3)) continue;
+    float pn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};  // :554
+    const float norm = sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);  // :572-573
+    pn[0] = pn[0] / norm;
+    pn[1] = pn[1] / norm;
+    pn[2] = pn[2] / norm;
+    double n_[3] = {pn[0], pn[1], pn[2]};                                      // :588
+    const double* P[5] = {L1, L1 + 3, L2, L2 + 3, js[i].cross3d};
+    float d[5];
+    for (int k = 0; k < 5; ++k) d[k] = (float)(n_[0] * P[k][0] + n_[1] * P[k][1] + n_[2] * P[k][2]);  // :597-602
+    float dmin = 10000, dmax = -10000;                                         // :609-622
+    for (int k = 0; k < 5; ++k) {
+      dmin = dmin < d[k] ? dmin : d[k];
+      dmax = dmax > d[k] ? dmax : d[k];
+    }
+    if (dmax - dmin > 0.05) continue;                                          // :628
+    const float planeDis = -(d[0] + d[1] + d[2] + d[3] + d[4]) / 5;            // :632
+    float pl[4] = {(float)n_[0], (float)n_[1], (float)n_[2], planeDis};
+    if (pl[3] < 0) {                                                           // :641-645
+      for (int k = 0; k < 4; ++k) pl[k] = -pl[k];
+      for (int k = 0; k < 3; ++k) n_[k] = -n_[k];
+    }
+    bool old = false;                                                          // OldPlane :474-487
+    for (size_t m = 0; m < kept.size(); m += 4) {
+      const float dd = pl[3] - kept[m + 3];
+      const float angle = pl[0] * kept[m] + pl[1] * kept[m + 1] + pl[2] * kept[m + 2];
+      if (dd > 0.2 || dd < -0.2) continue;
+      if (angle < 0.9397 && angle > -0.9397) continue;
+      old = true;
+      break;
+    }
+    if (old) continue;
+    kept.insert(kept.end(), pl, pl + 4);
+    if (np < cap) {
+      for (int k = 0; k < 4; ++k) planes[4 * np + k] = pl[k];
+      for (int k = 0; k < 3; ++k) normals[3 * np + k] = n_[k];
+      junction_of[np] = i;
+    }
+    ++np;
+  }
+  return np;
+}
+
 int orc_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
                     const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign) {
   int nmatches = 0;

@@ -68,6 +68,9 @@ int orc_match_fuse(const psl_frame_view* kf, const psl_fuse_query* qs, const uin
                    const float* inv_level_sigma2, int th_low, int32_t* best_idx, int32_t* best_dist);
 
 /* ---- Frame bookkeeping (orc_frame.cpp): Frame.cc:1342-1381, ORBmatcher.cc:1339-1393 ---- */
+/* Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:1062-1092, 1135-1163) over cv::undistortPoints */
+void orc_undistort_keypoints(const psl_keypoint* kps, int n, const psl_distortion* cam, psl_keypoint* kps_un);
+void orc_image_bounds(int cols, int rows, const psl_distortion* cam, float* bounds);
 void orc_stereo_from_rgbd(const psl_keypoint* kps, int n, const uint16_t* depth, int w, int h, int stride_px,
                           float depth_factor, float bf, float* u_right, float* z);
 void orc_queries_from_last_frame(const psl_keypoint* kps_last, const float* z_last, const uint8_t* valid_in,
@@ -107,6 +110,9 @@ int orc_line_fuse(const psl_keyline* kl, int n_lines, const uint8_t* kf_desc, co
                   const uint8_t* qdesc, int nq, float th_cos, int th_low, int32_t* best_idx, int32_t* best_dist);
 int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,
                               const uint8_t* claimed_in, int mode, float nn_ratio, int32_t* assign);
+int orc_plane_hypotheses(const psl_keyline* kl_un, const float* line_eq, const double* lines3d, int n_lines,
+                         const psl_line_junction* js, int nj, double* le_l, float* planes, double* normals,
+                         int32_t* junction_of, int cap);
 int orc_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
                     const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign);
 

@@ -193,6 +193,20 @@ def match_bow(kf_desc, kf_angle, kf_valid, kf_csr, f_desc, f_angle, f_csr, nn_ra
 
 
 # ---- Frame bookkeeping (oracle/c/orc_frame.cpp) -------------------------------------------------
+def undistort_keypoints(kps, cam):
+    """cam: psl_slam_b200._lib.Distortion.  Frame::UndistortKeyPoints."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.empty_like(kps)
+    lib().orc_undistort_keypoints(_p(kps), len(kps), C.byref(cam), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, cam):
+    b = np.zeros(4, np.float32)
+    lib().orc_image_bounds(int(cols), int(rows), C.byref(cam), _p(b))
+    return tuple(float(v) for v in b)
+
+
 def stereo_from_rgbd(kps, depth_u16, depth_factor, bf):
     kps = np.ascontiguousarray(kps, KP_DTYPE)
     depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
@@ -450,6 +464,22 @@ def line_fuse(kl, kf_desc, queries, qdesc, th_cos=0.998, th_low=50):
     n = lib().orc_line_fuse(_p(kl), len(kl), _p(kf_desc), _p(queries), _p(qdesc), nq, C.c_float(th_cos), int(th_low),
                             _p(bi), _p(bd))
     return bi[:nq].copy(), bd[:nq].copy(), int(n)
+
+
+def plane_hypotheses(kl_un, line_eq, lines3d, junctions, cap=None):
+    """Frame::ExtractLSD plane hypotheses: (le_l [nj,6], planes [np,4], normals [np,3], junction_of [np], count)."""
+    from psl_slam_b200._lib import JUNCTION_DTYPE, KEYLINE_DTYPE
+    kl = np.ascontiguousarray(kl_un, KEYLINE_DTYPE)
+    eq = np.ascontiguousarray(line_eq, np.float32).reshape(-1, 3)
+    l3 = np.ascontiguousarray(lines3d, np.float64).reshape(-1, 6)
+    js = np.ascontiguousarray(junctions, JUNCTION_DTYPE)
+    nj = len(js)
+    cap = nj if cap is None else cap
+    le = np.zeros((max(nj, 1), 6))
+    pl, nr, ow = np.zeros((max(cap, 1), 4), np.float32), np.zeros((max(cap, 1), 3)), np.zeros(max(cap, 1), np.int32)
+    n = lib().orc_plane_hypotheses(_p(kl), _p(eq), _p(l3), len(kl), _p(js), nj, _p(le), _p(pl), _p(nr), _p(ow), cap)
+    m = min(n, cap)
+    return le[:nj].copy(), pl[:m].copy(), nr[:m].copy(), ow[:m].copy(), int(n)
 
 
 def line_search_triangulation(d1, ml1, d2, ml2, nn_ratio, th, is_double):

@@ -316,3 +316,62 @@ def line_fuse(kl, kf_desc, queries, qdesc, th_cos=0.998, th_low=50):
         if best_d <= th_low and best_i >= 0:
             bi[q] = best_i
     return bi, bd
+
+
+# ---------------------------------------------------------------------------------------------------
+# Plane hypotheses of Frame::ExtractLSD (Frame.cc:512-645) with Frame::OldPlane (:474-487)
+# ---------------------------------------------------------------------------------------------------
+def plane_hypotheses(kl_un, line_eq, lines3d, junctions):
+    """junctions: structured (l1, l2, cross2d_x, cross2d_y, cross3d[3]).  Returns (le_l [nj,6] f64, planes [np,4] f32,
+    normals [np,3] f64, junction_of [np] i32).  numpy scalar arithmetic in the reference's types."""
+    F64 = np.float64
+    le = np.zeros((len(junctions), 6), F64)
+    planes, normals, owner = [], [], []
+    with np.errstate(all="ignore"):
+        for i, J in enumerate(junctions):
+            l1, l2 = int(J["l1"]), int(J["l2"])
+            for s_, l in enumerate((l1, l2)):
+                k = kl_un[l]
+                sp = np.array([F64(k["start_x"]), F64(k["start_y"]), F64(1.0)])
+                ep = np.array([F64(k["end_x"]), F64(k["end_y"]), F64(1.0)])
+                c = np.array([sp[1] * ep[2] - sp[2] * ep[1], sp[2] * ep[0] - sp[0] * ep[2], sp[0] * ep[1] - sp[1] * ep[0]])
+                le[i, 3 * s_:3 * s_ + 3] = c / np.sqrt(c[0] * c[0] + c[1] * c[1])
+            e1, e2 = line_eq[l1].astype(F32), line_eq[l2].astype(F32)
+            if (e1 == 0).all() or (e2 == 0).all():
+                continue
+            A, B = lines3d[l1].astype(F64), lines3d[l2].astype(F64)
+            if (np.abs(A) <= 1e-12).all() or (np.abs(B) <= 1e-12).all():
+                continue
+            pn = np.array([F32(F32(e1[1] * e2[2]) - F32(e1[2] * e2[1])), F32(F32(e1[2] * e2[0]) - F32(e1[0] * e2[2])),
+                           F32(F32(e1[0] * e2[1]) - F32(e1[1] * e2[0]))], F32)
+            norm = F32(np.sqrt(F32(F32(F32(pn[0] * pn[0]) + F32(pn[1] * pn[1])) + F32(pn[2] * pn[2]))))
+            pn = np.array([F32(pn[0] / norm), F32(pn[1] / norm), F32(pn[2] / norm)], F32)
+            n_ = pn.astype(F64)
+            pts = [A[:3], A[3:], B[:3], B[3:], np.asarray(J["cross3d"], F64)]
+            d = [F32(n_[0] * P[0] + n_[1] * P[1] + n_[2] * P[2]) for P in pts]
+            dmin, dmax = F32(10000), F32(-10000)
+            for v in d:
+                dmin = dmin if dmin < v else v
+                dmax = dmax if dmax > v else v
+            if F64(F32(dmax - dmin)) > 0.05:
+                continue
+            dis = F32(-F32(F32(F32(F32(d[0] + d[1]) + d[2]) + d[3]) + d[4]) / F32(5))
+            pl = np.array([pn[0], pn[1], pn[2], dis], F32)
+            if pl[3] < 0:
+                pl, n_ = -pl, -n_
+            old = False
+            for q in planes:
+                dd = F32(pl[3] - q[3])
+                ang = F32(F32(F32(pl[0] * q[0]) + F32(pl[1] * q[1])) + F32(pl[2] * q[2]))
+                if F64(dd) > 0.2 or F64(dd) < -0.2:
+                    continue
+                if F64(ang) < 0.9397 and F64(ang) > -0.9397:
+                    continue
+                old = True
+                break
+            if old:
+                continue
+            planes.append(pl)
+            normals.append(n_)
+            owner.append(i)
+    return (le, np.array(planes, F32).reshape(-1, 4), np.array(normals, F64).reshape(-1, 3), np.array(owner, np.int32))

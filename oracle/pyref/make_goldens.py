@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|linefuse|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|linefuse|undistort|planes|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -385,6 +385,99 @@ def make_linefuse():
               f"loose {(bi2 >= 0).sum()} with candidates {(bd < 256).sum()}")
 
 
+def make_undistort():
+    """Frame::UndistortKeyPoints / ComputeImageBounds: the real cv2.undistortPoints on the ORB keypoints of a golden
+    frame and on random points (inside, outside, on the corners), TUM1 / TUM2-like 5- and 4-coefficient cameras."""
+    import cv2
+    g = np.load(os.path.join(OUT, "orb_vga_seed1.npz"))
+    rng = np.random.default_rng(9)
+    pts_kp = np.ascontiguousarray(g["kps"][:, :2], np.float32)   # x, y of the final keypoints
+    pts_rnd = np.concatenate([rng.uniform(-80, 760, (4000, 2)), rng.uniform(0, 640, (2000, 2)) * [1, 0.75],
+                              [[0, 0], [640, 0], [0, 480], [640, 480], [318.64304, 255.31399]]]).astype(np.float32)
+    cams = {"tum1": (517.306408, 516.469215, 318.643040, 255.313989, 0.262383, -0.953104, -0.005358, 0.002628, 1.163314),
+            "tum2": (520.908620, 521.007327, 325.141442, 249.701764, 0.231222, -0.784899, -0.003257, -0.000105, 0.917205),
+            "k1only": (481.2, 480.0, 319.5, 239.5, -0.28, 0.0, 0.0, 0.0, 0.0),
+            "strong": (300.0, 300.0, 320.0, 240.0, -0.45, 0.25, 0.01, -0.008, 0.0)}
+    out = {"pts_kp": pts_kp, "pts_rnd": pts_rnd}
+    for name, c in cams.items():
+        K = np.array([[c[0], 0, c[2]], [0, c[1], c[3]], [0, 0, 1]], np.float32)
+        D = np.array(c[4:], np.float32)
+        out[f"cam_{name}"] = np.array(c, np.float32)
+        out[f"kp_{name}"] = cv2.undistortPoints(pts_kp.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+        out[f"rnd_{name}"] = cv2.undistortPoints(pts_rnd.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+        corners = np.array([[0, 0], [640, 0], [0, 480], [640, 480]], np.float32)
+        m = cv2.undistortPoints(corners.reshape(-1, 1, 2), K, D, None, K).reshape(-1, 2)
+        out[f"bounds_{name}"] = np.array([min(m[0, 0], m[2, 0]), min(m[0, 1], m[1, 1]), max(m[1, 0], m[3, 0]),
+                                          max(m[2, 1], m[3, 1])], np.float32)   # Frame.cc:1150-1153 as (minX, minY, maxX, maxY)
+        print(f"undistort {name}: max shift {np.abs(out[f'rnd_{name}'] - pts_rnd).max():.2f} px, bounds {out[f'bounds_{name}']}")
+    np.savez_compressed(os.path.join(OUT, "undistort.npz"), **out)
+
+
+def make_planes():
+    """Frame::ExtractLSD plane hypotheses: synthetic structural lines on a few 3-D planes in the camera frame (coplanar
+    intersecting pairs, repeated planes for OldPlane, skew pairs, lines without 3-D, parallel directions -> NaN)."""
+    from oracle.pyref import linematch_py as lm
+    from psl_slam_b200._lib import JUNCTION_DTYPE, KEYLINE_DTYPE
+    K = synth.ICL
+    for case in (0, 1, 2):
+        rng = np.random.default_rng(700 + min(case, 1))   # case 2 = case 1 with the degenerate pair first
+        n_planes, per = (5, 6) if case == 0 else (9, 8)
+        kl, eq, l3, js = [], [], [], []
+        def project(P):
+            return K["fx"] * P[0] / P[2] + K["cx"], K["fy"] * P[1] / P[2] + K["cy"]
+        for pi in range(n_planes):
+            n = rng.normal(0, 1, 3); n /= np.linalg.norm(n)
+            c = np.array([rng.uniform(-1, 1), rng.uniform(-0.8, 0.8), rng.uniform(1.5, 4.0)])
+            u = np.cross(n, [0, 0, 1.0]); u /= np.linalg.norm(u)
+            v = np.cross(n, u)
+            first = len(kl)
+            for li in range(per):
+                a = rng.uniform(0, np.pi)
+                dirv = np.cos(a) * u + np.sin(a) * v
+                mid = c + rng.uniform(-0.3, 0.3) * u + rng.uniform(-0.3, 0.3) * v
+                noise = rng.normal(0, 0.004 if li % 3 else 0.03, (2, 3))    # some lines leave the plane by > 5 cm
+                A, B = mid - 0.4 * dirv + noise[0], mid + 0.4 * dirv + noise[1]
+                k = np.zeros((), KEYLINE_DTYPE)
+                (k["start_x"], k["start_y"]), (k["end_x"], k["end_y"]) = project(A), project(B)
+                kl.append(k)
+                d = (B - A).astype(np.float32)
+                eq.append(d / np.float32(np.sqrt(np.float32(d @ d))))
+                l3.append(np.concatenate([A, B]))
+            for a_ in range(first, first + per):
+                for b_ in range(a_ + 1, first + per):
+                    if rng.random() < 0.45:
+                        A1, B1, A2 = l3[a_][:3], l3[a_][3:], l3[b_][:3]
+                        X = A1 + rng.uniform(0, 1) * (B1 - A1) * 0.5 + 0.5 * (A2 - A1) * rng.uniform(0, 0.2)
+                        X = X + rng.normal(0, 0.003, 3)
+                        j = np.zeros((), JUNCTION_DTYPE)
+                        j["l1"], j["l2"] = a_, b_
+                        j["cross2d_x"], j["cross2d_y"] = project(X)
+                        j["cross3d"] = X
+                        js.append(j)
+        kl, eq, l3, js = np.array(kl), np.array(eq, np.float32), np.array(l3), np.array(js)
+        # lines without a 3-D fit (isLineGood left them at their initial values), a zeroed direction, a skew pair and a
+        # parallel pair (normal = 0 / 0)
+        eq[3] = (-1, -1, -1); l3[3] = 0
+        eq[7] = 0
+        extra = np.zeros(3, JUNCTION_DTYPE)
+        extra[0]["l1"], extra[0]["l2"] = 0, per + 1                      # lines of two different planes
+        extra[1]["l1"], extra[1]["l2"] = 1, 1                            # a line with itself: parallel
+        extra[2]["l1"], extra[2]["l2"] = 2, 3
+        for e in extra:
+            e["cross3d"] = l3[e["l1"]][:3]
+        js = np.concatenate([js[: len(js) // 2], extra, js[len(js) // 2:]])
+        js = js[rng.permutation(len(js))]
+        if case == 2:  # the degenerate pair first: with no plane kept yet its NaN plane is accepted (and then, failing
+            # every comparison of OldPlane, makes each later hypothesis look old) -- the reference does the same
+            par = int(np.flatnonzero((js["l1"] == 1) & (js["l2"] == 1))[0])
+            js = np.concatenate([js[par:par + 1], js[:par], js[par + 1:]])
+        le, pl, nr, ow = lm.plane_hypotheses(kl, eq, l3, js)
+        np.savez_compressed(os.path.join(OUT, f"planes_case{case}.npz"), kl=kl, line_eq=eq, lines3d=l3, junctions=js,
+                            le_l=le, planes=pl, normals=nr, junction_of=ow)
+        print(f"planes_case{case}: lines {len(kl)} junctions {len(js)} planes {len(pl)} "
+              f"(nan planes {int(np.isnan(pl).any(1).sum())})")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(OUT, exist_ok=True)
@@ -402,3 +495,7 @@ if __name__ == "__main__":
         make_linematch()
     if what in ("linefuse", "all"):
         make_linefuse()
+    if what in ("undistort", "all"):
+        make_undistort()
+    if what in ("planes", "all"):
+        make_planes()

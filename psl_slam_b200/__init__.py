@@ -6,7 +6,8 @@ include/psl_frontend.h (libpsl_frontend.so, hand-written sm_100a CUDA).  No CPU 
 from ._lib import KEYLINE_DTYPE, KP_DTYPE, PslError, default_config  # noqa: F401
 from .orb import Context, ORBextractor  # noqa: F401
 from .line import LINEextractor  # noqa: F401
-from .line_matcher import InsectLineMatch, LineFrameData, LSDmatcher  # noqa: F401
+from .line_matcher import InsectLineMatch, LineFrameData, LSDmatcher, plane_hypotheses  # noqa: F401
 from .matcher import FrameData, ORBmatcher, hamming_knn2  # noqa: F401
-from .tracking import (convert_rgbd, make_camera, make_track_params, track_frontend_batch, track_frontend_batch_dev,  # noqa: F401
-                       track_orb_batch, track_orb_batch_dev)
+from .tracking import (convert_rgbd, image_bounds, make_camera, make_distortion, make_track_params,  # noqa: F401
+                       track_frontend_batch, track_frontend_batch_dev, track_orb_batch, track_orb_batch_dev,
+                       undistort_keypoints)

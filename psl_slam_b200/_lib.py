@@ -47,7 +47,14 @@ FUSE_QUERY_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("u_right", "<f4"), ("r
                              ("flags", "<u4")])  # psl_fuse_query
 LINE_FUSE_QUERY_DTYPE = np.dtype([("u1", "<f4"), ("v1", "<f4"), ("u2", "<f4"), ("v2", "<f4"), ("radius", "<f4"),
                                   ("pred_level", "<i4"), ("flags", "<u4")])  # psl_line_fuse_query, 28 B
+JUNCTION_DTYPE = np.dtype([("l1", "<i4"), ("l2", "<i4"), ("cross2d_x", "<f4"), ("cross2d_y", "<f4"),
+                           ("cross3d", "<f8", (3,))])  # psl_line_junction, 40 B
 Q_VALID, Q_CLAIMS = 1, 2
+
+
+class Distortion(C.Structure):  # psl_distortion
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("k1", C.c_float),
+                ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
 
 
 class FrameView(C.Structure):  # psl_frame_view
@@ -141,7 +148,8 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_extract", "psl_line_extract_batch", "psl_line_extract_batch_dev", "psl_line_match_nnr",
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
-           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation", "psl_line_fuse"]
+           "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation", "psl_line_fuse",
+           "psl_undistort_keypoints", "psl_undistort_keypoints_dev", "psl_image_bounds", "psl_plane_hypotheses"]
 
 _lib = None
 
@@ -194,6 +202,10 @@ def lib():
         L.psl_match_triangulation.argtypes = [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p, _p]
         L.psl_match_fuse.argtypes = [_p, _p, _p, _p, _i, _p, _i, _i, _p, _p]
         L.psl_line_search_triangulation.argtypes = [_p, _p, _p, _i, _p, _p, _i, _f, _f, _i, _p, _p]
+        L.psl_undistort_keypoints.argtypes = [_p, _p, _i, _p, _p]
+        L.psl_undistort_keypoints_dev.argtypes = [_p, _p, _p, _i, _i, _p, _p]
+        L.psl_image_bounds.argtypes = [_p, _i, _i, _p, _p]
+        L.psl_plane_hypotheses.argtypes = [_p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p]
         L.psl_line_fuse.argtypes = [_p, _p, _i, _p, _i, _p, _p, _i, _f, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
         _lib = L

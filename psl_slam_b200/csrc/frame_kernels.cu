@@ -174,4 +174,60 @@ void launch_depth_to_float(const uint16_t* in, int stride_px, int64_t fs_px, flo
   depth_to_float_kernel<<<grid, 256, 0, st>>>(in, stride_px, fs_px, factor, out, w, h);
 }
 
+// cv::undistortPoints(src, dst, K, D, noArray(), K) for one point, OpenCV 4.x cvUndistortPointsInternal with its
+// default criteria (5 iterations, no epsilon test): everything in double from the float inputs, no contraction.
+// The rational terms k4..k6, the thin-prism terms and the tilt are zero for the 4/5-coefficient models PSL-SLAM
+// reads (Tracking.cc:66-77); their additions of +0.0 are kept out, which leaves every value unchanged.
+__device__ __forceinline__ float2 undistort_point(float u_in, float v_in, const psl_distortion& c) {
+  const double fx = (double)c.fx, fy = (double)c.fy, cx = (double)c.cx, cy = (double)c.cy;
+  const double k1 = (double)c.k1, k2 = (double)c.k2, p1 = (double)c.p1, p2 = (double)c.p2, k3 = (double)c.k3;
+  const double ifx = __ddiv_rn(1.0, fx), ify = __ddiv_rn(1.0, fy);
+  const double u = (double)u_in, v = (double)v_in;
+  double x = __dmul_rn(__dsub_rn(u, cx), ifx), y = __dmul_rn(__dsub_rn(v, cy), ify);
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
+    const double icdist = __ddiv_rn(1.0, den);
+    if (icdist < 0) {
+      x = x0;
+      y = y0;
+      break;
+    }
+    // deltaX = 2*p1*x*y + p2*(r2 + 2*x*x);  deltaY = p1*(r2 + 2*y*y) + 2*p2*x*y   (left to right)
+    const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y),
+                                __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+    const double dY = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dX), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+  }
+  // RR = P * I: xx = fx*x + 0*y + cx, yy = 0*x + fy*y + cy, ww = 1 / (0*x + 0*y + 1)
+  const double xx = __dadd_rn(__dadd_rn(__dmul_rn(fx, x), __dmul_rn(0.0, y)), cx);
+  const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(fy, y)), cy);
+  const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(0.0, y)), 1.0));
+  return make_float2((float)__dmul_rn(xx, ww), (float)__dmul_rn(yy, ww));
+}
+
+__global__ void __launch_bounds__(128)
+    undistort_kernel(const psl_keypoint* __restrict__ kps, const int32_t* __restrict__ n, int cap, psl_distortion cam,
+                     psl_keypoint* __restrict__ kps_un) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n[b]) return;
+  psl_keypoint k = kps[(size_t)b * cap + i];
+  if (cam.k1 != 0.f) {  // Frame.cc:1064
+    const float2 p = undistort_point(k.x, k.y, cam);
+    k.x = p.x;
+    k.y = p.y;
+  }
+  kps_un[(size_t)b * cap + i] = k;
+}
+
+void launch_undistort(const psl_keypoint* kps, const int32_t* n, int cap, const psl_distortion& cam, psl_keypoint* kps_un,
+                      int B, cudaStream_t st) {
+  if (B <= 0 || cap <= 0) return;
+  dim3 grid((cap + 127) / 128, B);
+  undistort_kernel<<<grid, 128, 0, st>>>(kps, n, cap, cam, kps_un);
+}
+
 }  // namespace psl

@@ -17,6 +17,10 @@ void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* 
                         const psl_camera& cam, const QueryBuildParams& prm, psl_proj_query* q, int32_t* nq, int B,
                         cudaStream_t st);
 
+// Frame::UndistortKeyPoints (Frame.cc:1062-1092): kps_un[b][i] = kps[b][i] with cv::undistortPoints applied to pt
+void launch_undistort(const psl_keypoint* kps, const int32_t* n, int cap, const psl_distortion& cam, psl_keypoint* kps_un,
+                      int B, cudaStream_t st);
+
 // K0: cvtColor(... -> GRAY) in OpenCV 4.x Q15 arithmetic and depth.convertTo(CV_32F, factor) (Tracking.cc:219-235)
 void launch_color_to_gray(const uint8_t* color, int channels, int rgb_order, int color_stride, int64_t color_fs,
                           uint8_t* gray, int gray_stride, int64_t gray_fs, int B, int w, int h, cudaStream_t st);

@@ -487,6 +487,124 @@ __global__ void plane_assoc_kernel(const float* planes_cam, const double* pts, i
   }
 }
 
+// Plane hypotheses from coplanar intersecting line pairs (Frame.cc:512-645, OldPlane :474-487).  One warp: the lanes
+// evaluate 32 junctions at a time (everything but the duplicate test is independent), then the candidates are taken
+// in junction order and each is compared, 32 kept planes at a time, with the planes kept so far.  The float / double
+// mix follows the reference statement by statement; a degenerate pair (parallel directions) yields NaNs that fail
+// the span test's `>` and pass on, as there.
+__global__ void __launch_bounds__(32)
+    plane_hypotheses_kernel(const psl_keyline* __restrict__ kl_un, const float* __restrict__ line_eq,
+                            const double* __restrict__ lines3d, const psl_line_junction* __restrict__ js, int nj,
+                            double* __restrict__ le_l, float* planes, double* __restrict__ normals,
+                            int32_t* __restrict__ junction_of, int cap, int32_t* __restrict__ n_planes,
+                            float* kept /* [nj*4] scratch: every kept plane, also beyond cap */) {
+  const int lane = threadIdx.x;
+  int np = 0;
+  for (int base = 0; base < nj; base += 32) {
+    const int i = base + lane;
+    bool cand = false;
+    float pl[4] = {0.f, 0.f, 0.f, 0.f};
+    double nd[3] = {0., 0., 0.};
+    if (i < nj) {
+      const psl_line_junction J = js[i];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const psl_keyline k = kl_un[s == 0 ? J.l1 : J.l2];
+        const double ax = (double)k.start_x, ay = (double)k.start_y, bx = (double)k.end_x, by = (double)k.end_y;
+        const double c0 = __dsub_rn(ay, by), c1 = __dsub_rn(bx, ax), c2 = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+        const double nrm = __dsqrt_rn(__dadd_rn(__dmul_rn(c0, c0), __dmul_rn(c1, c1)));
+        le_l[6 * i + 3 * s] = __ddiv_rn(c0, nrm);
+        le_l[6 * i + 3 * s + 1] = __ddiv_rn(c1, nrm);
+        le_l[6 * i + 3 * s + 2] = __ddiv_rn(c2, nrm);
+      }
+      const float* e1 = line_eq + 3 * J.l1;
+      const float* e2 = line_eq + 3 * J.l2;
+      const double* L1 = lines3d + 6 * J.l1;
+      const double* L2 = lines3d + 6 * J.l2;
+      auto zero3 = [](const double* v) { return fabs(v[0]) <= 1e-12 && fabs(v[1]) <= 1e-12 && fabs(v[2]) <= 1e-12; };
+      const bool skip = (e1[0] == 0.f && e1[1] == 0.f && e1[2] == 0.f) || (e2[0] == 0.f && e2[1] == 0.f && e2[2] == 0.f) ||
+                        (zero3(L1) && zero3(L1 + 3)) || (zero3(L2) && zero3(L2 + 3));
+      if (!skip) {
+        float pn0 = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
+        float pn1 = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
+        float pn2 = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
+        const float norm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(pn0, pn0), __fmul_rn(pn1, pn1)), __fmul_rn(pn2, pn2)));
+        pn0 = __fdiv_rn(pn0, norm);
+        pn1 = __fdiv_rn(pn1, norm);
+        pn2 = __fdiv_rn(pn2, norm);
+        nd[0] = (double)pn0; nd[1] = (double)pn1; nd[2] = (double)pn2;
+        const double* P[5] = {L1, L1 + 3, L2, L2 + 3, J.cross3d};
+        float d[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+          d[k] = (float)__dadd_rn(__dadd_rn(__dmul_rn(nd[0], P[k][0]), __dmul_rn(nd[1], P[k][1])), __dmul_rn(nd[2], P[k][2]));
+        float dmin = 10000.f, dmax = -10000.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          dmin = dmin < d[k] ? dmin : d[k];
+          dmax = dmax > d[k] ? dmax : d[k];
+        }
+        if (!((double)__fsub_rn(dmax, dmin) > 0.05)) {
+          const float sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(d[0], d[1]), d[2]), d[3]), d[4]);
+          pl[0] = pn0; pl[1] = pn1; pl[2] = pn2;
+          pl[3] = __fdiv_rn(-sum, 5.f);
+          if (pl[3] < 0.f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pl[k] = -pl[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) nd[k] = -nd[k];
+          }
+          cand = true;
+        }
+      }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, cand);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      float q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = __shfl_sync(0xffffffffu, pl[k], j);
+      bool old = false;
+      for (int m0 = 0; m0 < np; m0 += 32) {  // OldPlane: any kept plane close in distance and direction
+        const int m = m0 + lane;
+        bool hit = false;
+        if (m < np) {
+          const float dd = __fsub_rn(q[3], kept[4 * m + 3]);
+          const float angle = __fadd_rn(__fadd_rn(__fmul_rn(q[0], kept[4 * m]), __fmul_rn(q[1], kept[4 * m + 1])),
+                                        __fmul_rn(q[2], kept[4 * m + 2]));
+          const bool far = (double)dd > 0.2 || (double)dd < -0.2;
+          const bool oblique = (double)angle < 0.9397 && (double)angle > -0.9397;
+          hit = !far && !oblique;
+        }
+        if (__any_sync(0xffffffffu, hit)) { old = true; break; }
+      }
+      if (old) continue;
+      if (lane == j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) kept[4 * np + k] = pl[k];
+        if (np < cap) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) planes[4 * np + k] = pl[k];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) normals[3 * np + k] = nd[k];
+          junction_of[np] = base + j;
+        }
+      }
+      ++np;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) *n_planes = np;
+}
+
+void launch_plane_hypotheses(const psl_keyline* kl_un, const float* line_eq, const double* lines3d,
+                             const psl_line_junction* js, int nj, double* le_l, float* planes, double* normals,
+                             int32_t* junction_of, int cap, int32_t* n_planes, float* kept, cudaStream_t st) {
+  plane_hypotheses_kernel<<<1, 32, 0, st>>>(kl_un, line_eq, lines3d, js, nj, le_l, planes, normals, junction_of, cap,
+                                            n_planes, kept);
+}
+
 void launch_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
                         const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign,
                         int32_t* nmatches, cudaStream_t st) {

@@ -36,6 +36,10 @@ void launch_line_projection(const LineSet& F, const double* lineeq, const double
                             float w_inv, float h_inv, int mode, float nn_ratio, const uint8_t* claimed_in,
                             uint16_t* cells, uint8_t* ncell, unsigned long long* keys, uint8_t* claimed, int32_t* assign,
                             int32_t* nmatches, int B, cudaStream_t st);
+// Frame::ExtractLSD plane hypotheses (Frame.cc:512-645): one warp; n_planes counts every kept hypothesis (> cap = overflow)
+void launch_plane_hypotheses(const psl_keyline* kl_un, const float* line_eq, const double* lines3d,
+                             const psl_line_junction* js, int nj, double* le_l, float* planes, double* normals,
+                             int32_t* junction_of, int cap, int32_t* n_planes, float* kept_scratch, cudaStream_t st);
 void launch_plane_assoc(const float* planes_cam, const double* pts, int n_ljl, const float* Tcw, const float* map_planes,
                         const uint8_t* map_bad, int n_map, float d_th, float a_th, int mode, int32_t* assign,
                         int32_t* nmatches, cudaStream_t st);

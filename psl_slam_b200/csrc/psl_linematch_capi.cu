@@ -276,4 +276,52 @@ int psl_plane_assoc(psl_ctx* ctx, const float* planes_cam, const double* pts, in
   return check_status(ctx);
 }
 
+int psl_plane_hypotheses(psl_ctx* ctx, const psl_keyline* kl_un, const float* line_eq, const double* lines3d,
+                         int32_t n_lines, const psl_line_junction* junctions, int32_t n_junctions, double* le_l,
+                         float* planes, double* normals, int32_t* junction_of, int32_t cap, int32_t* n_planes) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!n_planes || n_lines < 0 || n_junctions < 0 || cap < 0 ||
+      (n_junctions > 0 && (!kl_un || !line_eq || !lines3d || !junctions || !le_l || n_lines < 1)) ||
+      (cap > 0 && (!planes || !normals || !junction_of)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *n_planes = 0;
+  if (n_junctions == 0) return PSL_OK;
+  for (int i = 0; i < n_junctions; ++i)
+    if (junctions[i].l1 < 0 || junctions[i].l1 >= n_lines || junctions[i].l2 < 0 || junctions[i].l2 >= n_lines)
+      return fail(ctx, PSL_E_INVALID, "junction refers to a line outside [0, n_lines)");
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const int ocap = std::max(cap, 1);
+  PSL_UP(ctx->m_misc[0], kl_un, (size_t)n_lines * sizeof(psl_keyline));
+  PSL_UP(ctx->m_misc[1], line_eq, (size_t)n_lines * 12);
+  PSL_UP(ctx->m_misc[2], lines3d, (size_t)n_lines * 48);
+  PSL_UP(ctx->m_misc[3], junctions, (size_t)n_junctions * sizeof(psl_line_junction));
+  PSL_ENS(ctx->m_misc[4], (size_t)n_junctions * 48);   // le_l
+  PSL_ENS(ctx->m_misc[5], (size_t)ocap * 16);          // planes
+  PSL_ENS(ctx->m_misc[6], (size_t)ocap * 24);          // normals
+  PSL_ENS(ctx->m_assign, (size_t)ocap * 4);            // junction_of
+  PSL_ENS(ctx->m_misc[7], (size_t)n_junctions * 16);   // every kept plane (OldPlane reads them)
+  PSL_ENS(ctx->m_nm, 4);
+  cudaStream_t st = ctx->stream;
+  size_t e = prof_mark(ctx);
+  launch_plane_hypotheses(ctx->m_misc[0].as<psl_keyline>(), ctx->m_misc[1].as<float>(), ctx->m_misc[2].as<double>(),
+                          ctx->m_misc[3].as<psl_line_junction>(), n_junctions, ctx->m_misc[4].as<double>(),
+                          ctx->m_misc[5].as<float>(), ctx->m_misc[6].as<double>(), ctx->m_assign.as<int32_t>(), cap,
+                          ctx->m_nm.as<int32_t>(), ctx->m_misc[7].as<float>(), st);
+  prof_span(ctx, 15, e, 1);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(le_l, ctx->m_misc[4].p, (size_t)n_junctions * 48, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(n_planes, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, st));
+  int rc = check_status(ctx);  // synchronises: *n_planes is valid now
+  if (rc) return rc;
+  const int np = std::min(*n_planes, cap);
+  if (np > 0) {
+    PSL_CK(cudaMemcpyAsync(planes, ctx->m_misc[5].p, (size_t)np * 16, cudaMemcpyDeviceToHost, st));
+    PSL_CK(cudaMemcpyAsync(normals, ctx->m_misc[6].p, (size_t)np * 24, cudaMemcpyDeviceToHost, st));
+    PSL_CK(cudaMemcpyAsync(junction_of, ctx->m_assign.p, (size_t)np * 4, cudaMemcpyDeviceToHost, st));
+    PSL_CK(cudaStreamSynchronize(st));
+  }
+  if (*n_planes > cap) return fail(ctx, PSL_E_CAPACITY, "more plane hypotheses than `cap`");
+  return PSL_OK;
+}
+
 }  // extern "C"

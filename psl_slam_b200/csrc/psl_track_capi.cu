@@ -376,4 +376,57 @@ int psl_convert_rgbd(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32
   return check_status(ctx);
 }
 
+int psl_undistort_keypoints_dev(psl_ctx* ctx, const psl_keypoint* d_kps, const int32_t* d_n, int32_t cap, int32_t B,
+                                const psl_distortion* cam, psl_keypoint* d_kps_un) {
+  if (!ctx) return PSL_E_INVALID;
+  if (B < 0 || cap < 1 || !cam || (B > 0 && (!d_kps || !d_n || !d_kps_un))) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  size_t e = prof_mark(ctx);
+  launch_undistort(d_kps, d_n, cap, *cam, d_kps_un, B, ctx->stream);
+  prof_span(ctx, 6, e, 1);
+  PSL_CK(cudaGetLastError());
+  return PSL_OK;
+}
+
+int psl_undistort_keypoints(psl_ctx* ctx, const psl_keypoint* kps, int32_t n, const psl_distortion* cam,
+                            psl_keypoint* kps_un) {
+  if (!ctx) return PSL_E_INVALID;
+  if (n < 0 || !cam || (n > 0 && (!kps || !kps_un))) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (n == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  DevBuf* M = ctx->m_misc;
+  int rc;
+  if ((rc = ensure(ctx, M[0], (size_t)n * sizeof(psl_keypoint)))) return rc;
+  if ((rc = ensure(ctx, M[1], (size_t)n * sizeof(psl_keypoint)))) return rc;
+  if ((rc = ensure(ctx, M[2], 4))) return rc;
+  cudaStream_t st = ctx->stream;
+  PSL_CK(cudaMemcpyAsync(M[0].p, kps, (size_t)n * sizeof(psl_keypoint), cudaMemcpyHostToDevice, st));
+  PSL_CK(cudaMemcpyAsync(M[2].p, &n, 4, cudaMemcpyHostToDevice, st));
+  rc = psl_undistort_keypoints_dev(ctx, M[0].as<psl_keypoint>(), M[2].as<int32_t>(), n, 1, cam, M[1].as<psl_keypoint>());
+  if (rc) return rc;
+  PSL_CK(cudaMemcpyAsync(kps_un, M[1].p, (size_t)n * sizeof(psl_keypoint), cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
+int psl_image_bounds(psl_ctx* ctx, int32_t cols, int32_t rows, const psl_distortion* cam, float* bounds) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!cam || !bounds || cols <= 0 || rows <= 0) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (cam->k1 == 0.f) {  // Frame.cc:1156-1162
+    bounds[0] = 0.f; bounds[1] = 0.f; bounds[2] = (float)cols; bounds[3] = (float)rows;
+    return PSL_OK;
+  }
+  psl_keypoint c[4] = {};  // :1139-1143
+  c[1].x = (float)cols;
+  c[2].y = (float)rows;
+  c[3].x = (float)cols; c[3].y = (float)rows;
+  const int rc = psl_undistort_keypoints(ctx, c, 4, cam, c);
+  if (rc) return rc;
+  bounds[0] = std::min(c[0].x, c[2].x);  // mnMinX :1150
+  bounds[2] = std::max(c[1].x, c[3].x);  // mnMaxX
+  bounds[1] = std::min(c[0].y, c[1].y);  // mnMinY
+  bounds[3] = std::max(c[2].y, c[3].y);  // mnMaxY
+  return PSL_OK;
+}
+
 }  // extern "C"

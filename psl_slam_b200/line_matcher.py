@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import KEYLINE_DTYPE, LINE_FUSE_QUERY_DTYPE, LINE_QUERY_DTYPE, make_line_frame_view
+from ._lib import JUNCTION_DTYPE, KEYLINE_DTYPE, LINE_FUSE_QUERY_DTYPE, LINE_QUERY_DTYPE, make_line_frame_view
 from .orb import Context, _ptr
 
 
@@ -163,3 +163,21 @@ class InsectLineMatch:
     def AssociatePlanesByBoundary(self, planes_cam, pts, Tcw, map_planes):
         """Map::AssociatePlanesByBoundary(Frame&, dTh, aTh) — src/Map.cc:204-272 (the live twin)."""
         return self._run(planes_cam, pts, Tcw, map_planes, None, 1)
+
+
+def plane_hypotheses(ctx: Context, kl_un, line_eq, lines3d, junctions, cap: int | None = None):
+    """The plane hypotheses Frame::ExtractLSD builds from coplanar intersecting line pairs (Frame.cc:512-645, OldPlane
+    :474-487).  junctions: JUNCTION_DTYPE (intersection_lines_plane).  Returns (mvle_l [nj,6] f64, mvPlanes [np,4] f32,
+    mvPlaneNormal [np,3] f64, junction index of each plane [np])."""
+    kl = np.ascontiguousarray(kl_un, KEYLINE_DTYPE)
+    eq = np.ascontiguousarray(line_eq, np.float32).reshape(-1, 3)
+    l3 = np.ascontiguousarray(lines3d, np.float64).reshape(-1, 6)
+    js = np.ascontiguousarray(junctions, JUNCTION_DTYPE)
+    nj = len(js)
+    cap = nj if cap is None else cap
+    le = np.zeros((max(nj, 1), 6))
+    pl, nr, ow = np.zeros((max(cap, 1), 4), np.float32), np.zeros((max(cap, 1), 3)), np.zeros(max(cap, 1), np.int32)
+    n = C.c_int32()
+    ctx.check(_lib.lib().psl_plane_hypotheses(ctx.handle, _ptr(kl), _ptr(eq), _ptr(l3), len(kl), _ptr(js), nj, _ptr(le),
+                                              _ptr(pl), _ptr(nr), _ptr(ow), cap, C.byref(n)))
+    return le[:nj], pl[: n.value], nr[: n.value], ow[: n.value]

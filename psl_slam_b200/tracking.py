@@ -106,3 +106,23 @@ def convert_rgbd(ctx, color: np.ndarray | None, rgb_order: bool, depth: np.ndarr
                                           None if gray is None else _ptr(gray), None if depth is None else _ptr(depth),
                                           C.c_float(f), None if dep is None else _ptr(dep), B, W, H))
     return gray, dep
+
+
+def make_distortion(fx, fy, cx, cy, k1=0.0, k2=0.0, p1=0.0, p2=0.0, k3=0.0):
+    """mK and mDistCoef of Tracking's settings (Tracking.cc:52-77)."""
+    return _lib.Distortion(fx, fy, cx, cy, k1, k2, p1, p2, k3)
+
+
+def undistort_keypoints(ctx, kps: np.ndarray, cam) -> np.ndarray:
+    """Frame::UndistortKeyPoints (Frame.cc:1062-1092): KP_DTYPE [n] -> mvKeysUn."""
+    kps = np.ascontiguousarray(kps, _lib.KP_DTYPE)
+    out = np.empty_like(kps)
+    ctx.check(_lib.lib().psl_undistort_keypoints(ctx.handle, _ptr(kps), len(kps), C.byref(cam), _ptr(out)))
+    return out
+
+
+def image_bounds(ctx, cols: int, rows: int, cam):
+    """Frame::ComputeImageBounds (Frame.cc:1135-1163): (mnMinX, mnMinY, mnMaxX, mnMaxY)."""
+    b = np.zeros(4, np.float32)
+    ctx.check(_lib.lib().psl_image_bounds(ctx.handle, int(cols), int(rows), C.byref(cam), _ptr(b)))
+    return tuple(float(v) for v in b)

@@ -83,3 +83,36 @@ def test_capacity_errors_are_loud():
     assert e.value.code == -3
     with pytest.raises(PslError):
         LINEextractor(max_width=320, max_height=240)(gray[0])
+
+
+def test_unaligned_device_frames_vs_oracle(orc):
+    """Device-pointer entry with an odd base address and row stride: the byte-load form of the blur kernel (LSD
+    prologue, LBD) must reproduce the word form and the oracle."""
+    import torch
+
+    from psl_slam_b200 import KEYLINE_DTYPE, LINEextractor, synth
+    frames = np.stack([synth.sequence(8, 1)[0][0], synth.make_lowtex(31)])
+    B, (H, W) = len(frames), frames.shape[1:]
+    stride, off = W + 3, 1
+    fs = stride * H + 5
+    host = np.zeros(B * fs + 16, np.uint8)
+    for b in range(B):
+        for y in range(H):
+            s = off + b * fs + y * stride
+            host[s:s + W] = frames[b, y]
+    buf = torch.from_numpy(host).cuda()
+    ex = LINEextractor(chunk_frames=4)
+    cap = ex.cap
+    kl = torch.zeros((B, cap, 68), dtype=torch.uint8, device="cuda")
+    ld = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    eq = torch.zeros((B, cap, 3), dtype=torch.float64, device="cuda")
+    n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ex.extract_batch_dev(buf.data_ptr() + off, B, W, H, stride, fs, kl.data_ptr(), ld.data_ptr(), eq.data_ptr(), None,
+                         n.data_ptr())
+    ex.ctx.sync()
+    n_h = n.cpu().numpy()
+    for b in range(B):
+        okl, old, oeq, _ = orc.line_extract(frames[b], 200)
+        assert n_h[b] == len(okl) and n_h[b] > 5
+        assert kl[b, : n_h[b]].cpu().numpy().tobytes() == okl.tobytes()
+        assert np.array_equal(ld[b, : n_h[b]].cpu().numpy(), old) and np.array_equal(eq[b, : n_h[b]].cpu().numpy(), oeq)

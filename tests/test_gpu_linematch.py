@@ -173,3 +173,37 @@ def test_line_fuse_vs_golden_and_oracle(orc, name):
     assert len(bi) == 0
     with pytest.raises(PslError):
         m.Fuse(g["kl"], g["kf_desc"][: len(g["kl"]) - 1], g["queries"], g["qdesc"])
+
+
+@pytest.mark.parametrize("name", golden_names("planes_"))
+def test_plane_hypotheses_vs_golden_and_oracle(orc, name):
+    from psl_slam_b200 import Context, PslError, default_config, plane_hypotheses
+    g = load_golden(name)
+    ctx = Context(default_config())
+    le, pl, nr, ow = plane_hypotheses(ctx, g["kl"], g["line_eq"], g["lines3d"], g["junctions"])
+    same = lambda a, b: a.shape == b.shape and np.array_equal(a, b, equal_nan=True)  # noqa: E731  a degenerate pair yields NaNs
+    # (their payload bits are the only thing that may differ between the CPU and the GPU)
+    assert same(le, g["le_l"]) and same(pl, g["planes"]) and same(nr, g["normals"]) and np.array_equal(ow, g["junction_of"])
+    # many junctions (several 32-wide rounds, > 32 kept planes): tiled copies with every copy on its own plane offset
+    reps = 12
+    kl = np.tile(g["kl"], reps)
+    eq = np.tile(g["line_eq"], (reps, 1))
+    l3 = np.tile(g["lines3d"], (reps, 1)).copy()
+    js = np.tile(g["junctions"], reps).copy()
+    for r in range(reps):
+        sl = slice(r * len(g["kl"]), (r + 1) * len(g["kl"]))
+        l3[sl, 2::3] += 0.37 * r
+        jsl = slice(r * len(g["junctions"]), (r + 1) * len(g["junctions"]))
+        js["l1"][jsl] += r * len(g["kl"])
+        js["l2"][jsl] += r * len(g["kl"])
+        js["cross3d"][jsl, 2] += 0.37 * r
+    want = orc.plane_hypotheses(kl, eq, l3, js)
+    le, pl, nr, ow = plane_hypotheses(ctx, kl, eq, l3, js)
+    assert same(le, want[0]) and same(pl, want[1]) and same(nr, want[2]) and np.array_equal(ow, want[3])
+    if name != "planes_case2":
+        assert len(pl) > 32
+        with pytest.raises(PslError) as e:
+            plane_hypotheses(ctx, kl, eq, l3, js, cap=3)
+        assert e.value.code == -3
+    le, pl, nr, ow = plane_hypotheses(ctx, g["kl"], g["line_eq"], g["lines3d"], g["junctions"][:0])
+    assert len(pl) == 0 and len(le) == 0

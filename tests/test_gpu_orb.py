@@ -122,3 +122,36 @@ def test_stages_vs_golden(name):
         sel = ex.debug_fetch(3, 0, l)
         gs = g[f"sel_{l}"]
         assert np.array_equal(sel[:, :2] + 16, gs[:, :2]) and np.array_equal(sel[:, 2], gs[:, 2]), f"octree level {l}"
+
+
+def test_unaligned_device_frames_vs_oracle(orc):
+    """Device-pointer entry with a base address and row stride that are not multiples of 4 (nor 16): the byte-load
+    forms of the pyramid / blur kernels and the FAST tiles without a TMA descriptor must give the same result as the
+    aligned forms (and the oracle).  Low-texture frames also send most cells through the minThFAST fallback list."""
+    import torch
+
+    from psl_slam_b200 import KP_DTYPE, ORBextractor, synth
+    frames = np.stack([synth.sequence(8, 1)[0][0], synth.make_lowtex(31), synth.sequence(9, 1)[0][0]])
+    B, (H, W) = len(frames), frames.shape[1:]
+    stride, off = W + 3, 1
+    fs = stride * H + 5
+    buf = torch.zeros(B * fs + 16, dtype=torch.uint8, device="cuda")
+    host = np.zeros(B * fs + 16, np.uint8)
+    for b in range(B):
+        for y in range(H):
+            s = off + b * fs + y * stride
+            host[s:s + W] = frames[b, y]
+    buf.copy_(torch.from_numpy(host))
+    ex = ORBextractor(chunk_frames=2)
+    cap = ex.cap
+    kps = torch.zeros((B, cap, 28), dtype=torch.uint8, device="cuda")
+    desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ex.extract_batch_dev(buf.data_ptr() + off, B, W, H, stride, fs, kps.data_ptr(), desc.data_ptr(), n.data_ptr())
+    ex.ctx.sync()
+    n_h, kps_h, desc_h = n.cpu().numpy(), kps.cpu().numpy(), desc.cpu().numpy()
+    for b in range(B):
+        okps, odesc = orc.orb_extract(frames[b])
+        got = kps_h[b, : n_h[b]].copy().view(KP_DTYPE).reshape(-1)
+        _same(got, desc_h[b, : n_h[b]], okps, odesc)
+    assert n_h[1] < n_h[0]  # the low-texture frame is the sparse one

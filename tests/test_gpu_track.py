@@ -115,3 +115,49 @@ def test_input_conversion_vs_cv2_golden():
     rgb, _ = synth.render(poster, synth.trajectory(1, 3)[0], 320, 240)
     gray, _ = convert_rgbd(ctx, rgb[None], True, None)
     assert np.array_equal(gray[0], synth.rgb_to_gray(rgb))
+
+
+@pytest.mark.parametrize("cam", ["tum1", "tum2", "k1only", "strong"])
+def test_undistort_keypoints_vs_cv2_golden(orc, cam):
+    """Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:1062-1092, 1135-1163) against real cv2.undistortPoints."""
+    import ctypes as C
+
+    import torch
+    from conftest import load_golden
+
+    from psl_slam_b200 import Context, _lib, default_config, image_bounds, make_distortion, undistort_keypoints
+    from psl_slam_b200._lib import KP_DTYPE
+    g = load_golden("undistort")
+    d = make_distortion(*[float(v) for v in g[f"cam_{cam}"]])
+    ctx = Context(default_config())
+
+    def kp_array(xy):
+        k = np.zeros(len(xy), KP_DTYPE)
+        k["x"], k["y"] = xy[:, 0], xy[:, 1]
+        k["size"], k["angle"], k["octave"], k["class_id"] = 31.0, 12.5, 2, -1
+        return k
+
+    for src, want in ((g["pts_kp"], g[f"kp_{cam}"]), (g["pts_rnd"], g[f"rnd_{cam}"])):
+        k = kp_array(src)
+        out = undistort_keypoints(ctx, k, d)
+        assert np.array_equal(np.stack([out["x"], out["y"]], 1), want)
+        assert out.tobytes() == orc.undistort_keypoints(k, d).tobytes()
+    assert np.array_equal(np.array(image_bounds(ctx, 640, 480, d), np.float32), g[f"bounds_{cam}"])
+    z = make_distortion(500, 500, 320, 240, 0.0, 0.3, 0.01, 0.01, 0.1)
+    k = kp_array(g["pts_rnd"])
+    assert undistort_keypoints(ctx, k, z).tobytes() == k.tobytes()
+    assert image_bounds(ctx, 640, 480, z) == (0.0, 0.0, 640.0, 480.0)
+    assert len(undistort_keypoints(ctx, k[:0], d)) == 0
+    # batched device form: 3 frames with different counts, rows beyond a frame's count are left alone
+    cap, ns = 900, [900, 0, 417]
+    k3 = np.stack([kp_array(g["pts_rnd"][i * 900:(i + 1) * 900]) for i in range(3)])
+    dk = torch.from_numpy(k3.view(np.uint8).reshape(3, cap, 28)).cuda()
+    dn = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    do = torch.full((3, cap, 28), 0xAB, dtype=torch.uint8, device="cuda")
+    ctx.check(_lib.lib().psl_undistort_keypoints_dev(ctx.handle, dk.data_ptr(), dn.data_ptr(), cap, 3, C.byref(d), do.data_ptr()))
+    ctx.sync()
+    got = do.cpu().numpy()
+    for b, n in enumerate(ns):
+        want = orc.undistort_keypoints(k3[b, :n], d)
+        assert got[b, :n].tobytes() == want.tobytes()
+        assert (got[b, n:] == 0xAB).all()

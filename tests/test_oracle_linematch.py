@@ -99,3 +99,24 @@ def test_line_fuse(orc, name):
     q["flags"] = 0
     bi, bd, n = orc.line_fuse(g["kl"], g["kf_desc"], q, g["qdesc"])
     assert n == 0 and (bi == -1).all()
+
+
+def _same_planes(got, g):
+    le, pl, nr, ow = got[:4]
+    eq = lambda a, b: a.shape == b.shape and np.array_equal(a, b, equal_nan=True)  # noqa: E731  a degenerate pair yields NaNs
+    assert eq(le, g["le_l"]) and eq(pl, g["planes"]) and eq(nr, g["normals"])
+    assert np.array_equal(ow, g["junction_of"])
+
+
+@pytest.mark.parametrize("name", golden_names("planes_"))
+def test_plane_hypotheses(orc, name):
+    """Frame::ExtractLSD plane hypotheses + OldPlane against the independent numpy restatement."""
+    g = load_golden(name)
+    got = orc.plane_hypotheses(g["kl"], g["line_eq"], g["lines3d"], g["junctions"])
+    _same_planes(got, g)
+    assert got[4] == len(g["planes"]) >= 1
+    # capacity smaller than the result: the count is still reported, the first `cap` are stored
+    le, pl, nr, ow, n = orc.plane_hypotheses(g["kl"], g["line_eq"], g["lines3d"], g["junctions"], cap=1)
+    assert n == len(g["planes"]) and np.array_equal(pl, g["planes"][:1], equal_nan=True)
+    le, pl, nr, ow, n = orc.plane_hypotheses(g["kl"], g["line_eq"], g["lines3d"], g["junctions"][:0])
+    assert n == 0 and len(le) == 0

@@ -88,3 +88,31 @@ def test_search_by_projection_keyframe(orc, name):
     a, n = orc.match_projection(g["kps_cur"], None, g["desc_cur"], tuple(g["bounds"]), q, g["desc_kf"], g["held"], 0,
                                 int(g["orb_dist"]), 0.9, True)
     assert np.array_equal(a, g["assign"]) and n == int(g["nmatches"]) and n > 100
+
+
+def _kp_array(xy):
+    from psl_slam_b200._lib import KP_DTYPE
+    k = np.zeros(len(xy), KP_DTYPE)
+    k["x"], k["y"] = xy[:, 0], xy[:, 1]
+    k["size"], k["angle"], k["octave"], k["class_id"] = 31.0, 12.5, 2, -1
+    return k
+
+
+@pytest.mark.parametrize("cam", ["tum1", "tum2", "k1only", "strong"])
+def test_undistort_keypoints_vs_cv2_golden(orc, cam):
+    """Frame::UndistortKeyPoints / ComputeImageBounds against the real cv2.undistortPoints (bit-exact floats)."""
+    from psl_slam_b200 import make_distortion
+    g = load_golden("undistort")
+    d = make_distortion(*[float(v) for v in g[f"cam_{cam}"]])
+    for src, want in ((g["pts_kp"], g[f"kp_{cam}"]), (g["pts_rnd"], g[f"rnd_{cam}"])):
+        k = _kp_array(src)
+        out = orc.undistort_keypoints(k, d)
+        assert np.array_equal(np.stack([out["x"], out["y"]], 1), want)
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(out[f], k[f])
+    assert np.array_equal(np.array(orc.image_bounds(640, 480, d), np.float32), g[f"bounds_{cam}"])
+    # k1 == 0: copied keypoints, image rectangle (Frame.cc:1064-1068, 1156-1162)
+    z = make_distortion(500, 500, 320, 240, 0.0, 0.3, 0.01, 0.01, 0.1)
+    k = _kp_array(g["pts_rnd"])
+    assert orc.undistort_keypoints(k, z).tobytes() == k.tobytes()
+    assert orc.image_bounds(640, 480, z) == (0.0, 0.0, 640.0, 480.0)

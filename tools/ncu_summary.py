@@ -57,14 +57,14 @@ def kernel(src, dst):
 
 
 def kernels(src, dst):
-    """One column per distinct kernel of the report (its last captured launch)."""
+    """One column per distinct kernel of the report (its first captured launch: the largest pyramid level)."""
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     name_i = hdr.index("Kernel Name")
     last = {}
     for d in data:
-        last[re.sub(r"\(.*", "", d[name_i]).split("::")[-1]] = d
+        last.setdefault(re.sub(r"\(.*", "", d[name_i]).split("::")[-1], d)
     names = list(last)
     extra = ["lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
              "smsp__thread_inst_executed_per_inst_executed.ratio"]
