@@ -143,7 +143,8 @@ void launch_resize(const ImgBatch& src, const ImgBatchMut& dst, const ResizeTabl
 // three aligned words (coalesced across the warp, neighbours hit L1), makes the 4 horizontal
 // sums, and emits one uchar4 of the row 3 above.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGBand = 28;  // output rows per warp (4 ring turns of 7)
+constexpr int kGBand = 28;  // output rows per thread (4 ring turns of 7)
+constexpr int kGEdgeBand = 7;  // the edge columns are few and latency-bound: shorter bands, four times the threads
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   // valid for -n < i < 2n-1, which holds for a 3-px halo on any level the extractor accepts
@@ -161,14 +162,15 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
                                                      int n_int) {
   const int lane = threadIdx.x, b = blockIdx.z;
   const int w = src.w, h = src.h;
+  constexpr int kBand = MODE == 2 ? kGEdgeBand : kGBand;
   int xw, y0;
   if (MODE == 2) {
-    const int ne = ((w + 3) >> 2) - n_int, nbands = (h + kGBand - 1) / kGBand;
+    const int ne = ((w + 3) >> 2) - n_int, nbands = (h + kBand - 1) / kBand;
     const int t = blockIdx.x * 128 + threadIdx.y * 32 + lane;
     if (t >= ne * nbands) return;
     const int band = t / ne, e = t - band * ne;
     xw = e == 0 ? 0 : n_int + e;
-    y0 = band * kGBand;
+    y0 = band * kBand;
   } else {
     xw = blockIdx.x * 32 + lane + (MODE == 1 ? 1 : 0);  // output word (4 pixels)
     y0 = (blockIdx.y * 4 + threadIdx.y) * kGBand;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(128) gauss7_kernel(ImgBatch src, ImgBatchMut d
   for (int j = 0; j < 7; ++j)
 #pragma unroll
     for (int k = 0; k < 4; ++k) ring[j][k] = 0;
-  const int y_end = min(y0 + kGBand, h);
+  const int y_end = min(y0 + kBand, h);
   for (int yb = y0 - 3; yb < y_end + 3; yb += 7) {
     // issue the loads of seven rows before touching any of them (memory-level parallelism)
     uint32_t ld[7][3];
@@ -253,7 +255,8 @@ void launch_blur7(const ImgBatch& src, const ImgBatchMut& dst, int t0, int t1, i
   if (aligned && n_int > 0) {
     dim3 grid((n_int + 31) / 32, (nbands + 3) / 4, B);
     gauss7_kernel<1><<<grid, block, 0, st>>>(src, dst, t0, t1, t2, t3, n_int);
-    dim3 egrid(((nwords - n_int) * nbands + 127) / 128, 1, B);
+    const int ebands = (dst.h + kGEdgeBand - 1) / kGEdgeBand;
+    dim3 egrid(((nwords - n_int) * ebands + 127) / 128, 1, B);
     gauss7_kernel<2><<<egrid, block, 0, st>>>(src, dst, t0, t1, t2, t3, n_int);
   } else {
     dim3 grid((nwords + 31) / 32, (nbands + 3) / 4, B);
