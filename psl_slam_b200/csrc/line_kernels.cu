@@ -404,16 +404,40 @@ __global__ void __launch_bounds__(64)
     }
     float sCorX = sCorX0, sCorY = sCorY0;
     float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
-    for (short wID = 0; wID < lengthOfLSP; ++wID) {
-      // round() of the reference (half away from zero, on the float promoted to double) == roundf on the float
-      short q = (short)roundf(sCorX);
+    // One sample: round() of the reference (half away from zero, on the float promoted to double) == roundf on the
+    // float; the coordinates step in fp32 independently of the gradients, so the gathers of kAhead samples are issued
+    // together and the four sums then take them in the reference's order.
+    auto sample_addr = [&](float sx, float sy) -> int {
+      short q = (short)roundf(sx);
       const short xCor = (q < 0) ? (short)0 : (q > imageWidth) ? imageWidth : q;
-      q = (short)roundf(sCorY);
+      q = (short)roundf(sy);
       const short yCor = (q < 0) ? (short)0 : (q > imageHeight) ? imageHeight : q;
-      const short2 gg = __ldg(g + (int)yCor * w + (int)xCor);
+      return (int)yCor * w + (int)xCor;
+    };
+    auto accumulate = [&](short2 gg) {
       const float gDL = (float)gg.x * dL0 + (float)gg.y * dL1, gDO = (float)gg.x * dO0 + (float)gg.y * dO1;
       if (gDL > 0) pgdL += gDL; else ngdL -= gDL;
       if (gDO > 0) pgdO += gDO; else ngdO -= gDO;
+    };
+    int wID = 0;
+    const int len = (int)lengthOfLSP;
+    constexpr int kAhead = 8;
+    for (; wID + kAhead <= len; wID += kAhead) {
+      int a[kAhead];
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) {
+        a[u] = sample_addr(sCorX, sCorY);
+        sCorX += dL0;
+        sCorY += dL1;
+      }
+      short2 gv[kAhead];
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) gv[u] = __ldg(g + a[u]);
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) accumulate(gv[u]);
+    }
+    for (; wID < len; ++wID) {
+      accumulate(__ldg(g + sample_addr(sCorX, sCorY)));
       sCorX += dL0;
       sCorY += dL1;
     }
