@@ -13,6 +13,8 @@ struct LineBuffers {
   int raw_cap;         // raw LSD segments kept per frame
   const short2* xtab;  // [Ws] exact-resize taps (src index, Q8 weight of the right tap or -1)
   const short2* ytab;  // [Hs]
+  const uint4* xw4;     // xtab per group of 4 outputs for the word kernel (weights 256-f | f << 16), null if unusable
+  const uint32_t* xo4;  // first source word | 4-bit byte offsets of the 4 left taps << 16
   uint8_t* blur;       // [C][h][pitch]   7x7 sigma 0.75 (LSD) and, later, 5x5 sigma 1 (LBD)
   uint8_t* scaled;     // [C][Hs][Ws]
   const float4* lut;   // [1021*1021] pixel record of every integer gradient (gx, gy)

@@ -29,6 +29,73 @@ __global__ void __launch_bounds__(256)
   dst[((size_t)b * Hs + y) * Ws + x] = (uint8_t)((v + 32768u) >> 16);
 }
 
+// The same arithmetic with whole-word loads (the pyramid's resize_words_kernel, orb_pyramid.cu, with the exact
+// variant's Q8 weights and rounding): a thread owns 4 adjacent outputs and walks kXBand output rows; per source row
+// the 3 aligned words that hold its taps, one IDP.2A per output for the row pass; a source row that serves two
+// consecutive output rows (three in four at 0.8x) is interpolated once.
+constexpr int kXBand = 8;
+
+__global__ void __launch_bounds__(256)
+    resize_exact_words_kernel(const uint8_t* __restrict__ src, int pitch, int64_t fs, uint8_t* __restrict__ dst, int Ws,
+                              int Hs, const uint4* __restrict__ xw, const uint32_t* __restrict__ xo,
+                              const short2* __restrict__ ytab) {
+  const int n4 = Ws >> 2, nbands = (Hs + kXBand - 1) / kXBand;   // Ws is a multiple of 4 here
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n4 * nbands) return;
+  const int band = idx / n4, g = idx - band * n4, b = blockIdx.y;
+  const uint4 wt = __ldg(xw + g);
+  const uint32_t xo_g = __ldg(xo + g);
+  const int wb = (int)(xo_g & 0xFFFFu), nwords = pitch >> 2;
+  const bool in1 = wb + 1 < nwords, in2 = wb + 2 < nwords;
+  const uint32_t* __restrict__ S = reinterpret_cast<const uint32_t*>(src + (size_t)b * fs) + wb;
+  uint8_t* __restrict__ D = dst + (size_t)b * Hs * Ws + 4 * g;
+  const uint32_t w4[4] = {wt.x, wt.y, wt.z, wt.w};
+  int kept_row = -1;
+  uint32_t kept[4] = {0, 0, 0, 0};
+  const int y_end = min((band + 1) * kXBand, Hs);
+  for (int y = band * kXBand; y < y_end; ++y) {
+    const short2 ty = __ldg(ytab + y);
+    uint32_t h0[4], h1[4];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      uint32_t* hh = pass == 0 ? h0 : h1;
+      const int sy = ty.x + pass;
+      if (pass == 1 && ty.y < 0) break;       // no lower tap: v = h0 * 256
+      if (pass == 0 && sy == kept_row) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hh[k] = kept[k];
+        continue;
+      }
+      const uint32_t* row = S + (size_t)sy * nwords;
+      const uint32_t W0 = __ldg(row), W1 = in1 ? __ldg(row + 1) : 0u, W2 = in2 ? __ldg(row + 2) : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t off = (xo_g >> (16 + 4 * k)) & 0xFu;
+        const uint32_t lo = off < 4u ? W0 : W1, hi = off < 4u ? W1 : W2;
+        hh[k] = __dp2a_lo(w4[k], __funnelshift_r(lo, hi, 8u * (off & 3u)), 0u);
+      }
+    }
+    uint32_t packed = 0;
+    if (ty.y >= 0) {
+      const uint32_t fy = (uint32_t)ty.y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        packed |= ((h0[k] * (256u - fy) + h1[k] * fy + 32768u) >> 16) << (8 * k);
+        kept[k] = h1[k];
+      }
+      kept_row = ty.x + 1;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        packed |= ((h0[k] * 256u + 32768u) >> 16) << (8 * k);
+        kept[k] = h0[k];
+      }
+      kept_row = ty.x;
+    }
+    *reinterpret_cast<uint32_t*>(D + (size_t)y * Ws) = packed;
+  }
+}
+
 constexpr int lsdw_kN2Mask = 0x000FFFFF;  // gx^2 + gy^2 <= 2 * 510^2 < 2^20
 constexpr int lsdw_kUsed = 0x40000000;    // region membership flag, kept in the same word
 
@@ -722,7 +789,12 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
   const int npx = L.Ws * L.Hs;
   ImgBatchMut bl{L.blur, L.pitch, (int64_t)L.pitch * L.h, L.w, L.h};
   launch_blur7(in, bl, 0, 4, 56, 136, nb, st);  // GaussianBlur(7x7, sigma = 0.6 / 0.8)
-  {
+  if (L.xw4 && (L.Ws & 3) == 0 && (L.pitch & 3) == 0) {
+    const int nbands = (L.Hs + kXBand - 1) / kXBand;
+    dim3 grid(((L.Ws >> 2) * nbands + 255) / 256, nb);
+    resize_exact_words_kernel<<<grid, 256, 0, st>>>(L.blur, L.pitch, (int64_t)L.pitch * L.h, L.scaled, L.Ws, L.Hs, L.xw4,
+                                                    L.xo4, L.ytab);
+  } else {
     dim3 grid((L.Ws + 255) / 256, L.Hs, nb);
     resize_exact_kernel<<<grid, 256, 0, st>>>(L.blur, L.pitch, (int64_t)L.pitch * L.h, L.scaled, L.Ws, L.Hs, L.xtab,
                                               L.ytab);

@@ -64,9 +64,20 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   exact_axis(h, L.Hs, yt);
   short2 *dx = nullptr, *dy = nullptr;
   uint8_t* lut = nullptr;
+  // the x taps once more, per group of 4 outputs, for the word-based resize kernel
+  const int n4 = (L.Ws + 3) >> 2;
+  std::vector<short4> xt4(xt.size());
+  for (size_t i = 0; i < xt.size(); ++i)
+    xt4[i] = xt[i].y >= 0 ? make_short4(xt[i].x, (short)(xt[i].x + 1), (short)(256 - xt[i].y), xt[i].y)
+                          : make_short4(xt[i].x, xt[i].x, 256, 0);
+  std::vector<uint4> xw4(n4);
+  std::vector<uint32_t> xo4(n4);
+  const bool grouped = resize_group_tables(xt4.data(), L.Ws, xw4.data(), xo4.data());
+  uint4* dxw = nullptr;
+  uint32_t* dxo = nullptr;
   L.sort_tmp_bytes = lsd_sort_temp_bytes((int)npx, (int)C);
   uint8_t* tmp = nullptr;
-  bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
+  bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, dxw, (size_t)n4) && lalloc(ctx, dxo, (size_t)n4) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
             lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx) &&
             lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
@@ -87,6 +98,10 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   launch_lsd_lut(reinterpret_cast<float4*>(lut), ctx->stream);
   L.xtab = dx;
   L.ytab = dy;
+  L.xw4 = grouped ? dxw : nullptr;
+  L.xo4 = grouped ? dxo : nullptr;
+  PSL_CK(cudaMemcpyAsync(dxw, xw4.data(), xw4.size() * sizeof(uint4), cudaMemcpyHostToDevice, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(dxo, xo4.data(), xo4.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   PSL_CK(cudaMemcpyAsync(dx, xt.data(), xt.size() * sizeof(short2), cudaMemcpyHostToDevice, ctx->stream));
   PSL_CK(cudaMemcpyAsync(dy, yt.data(), yt.size() * sizeof(short2), cudaMemcpyHostToDevice, ctx->stream));
   upload_lbd_tables();
