@@ -42,17 +42,30 @@ using line::MergeScratch;
 using line::Seg;
 constexpr unsigned kFull = 0xffffffffu;
 
-// stable rank sort of idx[0..n) by key[idx] ascending (desc = false) or descending; result in out[]
+// stable rank sort of 0..n-1 by key ascending (desc = false) or descending; out[rank] = index.  Every caller sorts
+// the identity permutation, so the keys are read in place, four per load (the same address for all lanes: one
+// broadcast transaction); an element's rank = the keys that come before it + the equal ones with a smaller index.
 __device__ void rank_sort(const uint16_t* idx, uint16_t* out, int n, const float* key, bool desc, int lane) {
+  (void)idx;
+  const bool vec = (reinterpret_cast<uintptr_t>(key) & 15) == 0;
   for (int a = lane; a < n; a += 32) {
-    const float ka = key[idx[a]];
+    const float ka = key[a];
     int r = 0;
-    for (int b = 0; b < n; ++b) {
-      const float kb = key[idx[b]];
+    auto count = [&](float kb, int b) {
       const bool before = desc ? (kb > ka) : (kb < ka);
       r += (before || (!(desc ? (ka > kb) : (ka < kb)) && b < a)) ? 1 : 0;
-    }
-    out[r] = idx[a];
+    };
+    int b = 0;
+    if (vec)
+      for (; b + 4 <= n; b += 4) {
+        const float4 k4 = *reinterpret_cast<const float4*>(key + b);
+        count(k4.x, b);
+        count(k4.y, b + 1);
+        count(k4.z, b + 2);
+        count(k4.w, b + 3);
+      }
+    for (; b < n; ++b) count(key[b], b);
+    out[r] = (uint16_t)a;
   }
   __syncwarp();
 }

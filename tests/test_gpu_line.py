@@ -116,3 +116,17 @@ def test_unaligned_device_frames_vs_oracle(orc):
         assert n_h[b] == len(okl) and n_h[b] > 5
         assert kl[b, : n_h[b]].cpu().numpy().tobytes() == okl.tobytes()
         assert np.array_equal(ld[b, : n_h[b]].cpu().numpy(), old) and np.array_equal(eq[b, : n_h[b]].cpu().numpy(), oeq)
+
+
+def test_odd_sizes_vs_oracle(orc):
+    """Widths that are not multiples of 4 (image and its 0.8x copy): the per-pixel forms of the exact resize and the
+    Sobel kernels, and the edge columns of the blur."""
+    from psl_slam_b200 import LINEextractor, synth
+    base = synth.make_lowtex(41)
+    for (w, h) in ((322, 241), (431, 303)):
+        img = np.ascontiguousarray(base[:h, :w])
+        ex = LINEextractor(max_width=w, max_height=h)
+        kl, ld, eq = ex(img)
+        okl, old, oeq, _ = orc.line_extract(img, 200)
+        assert len(kl) == len(okl) and len(kl) > 3
+        assert kl.tobytes() == okl.tobytes() and np.array_equal(ld, old) and np.array_equal(eq, oeq)
