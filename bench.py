@@ -228,10 +228,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
+    json_fd = 1
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line.  NCCL writes its version banner to the C-level stdout when the
+        # communicator comes up (NCCL_DEBUG=VERSION and above), so file descriptor 1 points at stderr for the rest of
+        # the run and the JSON line goes to a duplicate of the original stdout.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from psl_slam_b200 import Context, ORBextractor, default_config
@@ -419,7 +423,7 @@ def main():
                "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
                "keypoints_per_frame": n_kp / F, "matches_per_frame": n_match / max(F - 1, 1),
                "lines_per_frame": n_lines / F, "line_matches_per_frame": n_lmatch / max(F - 1, 1)}
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
