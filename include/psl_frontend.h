@@ -513,6 +513,24 @@ int64_t psl_launch_count(const psl_ctx* ctx);
 int psl_debug_fetch(psl_ctx* ctx, int32_t what, int32_t frame, int32_t level, void* out, int64_t cap_bytes,
                     int64_t* n);
 
+/* Frame::isLineGood (src/Frame.cc:662-750; SURVEY "next" row N2): the 3-D line of every KeyLine from the depth image.
+ * Per line: min((int)length, 20) + 1 samples along it, nearest-pixel depth (> 0.01 m) back-projected with Frame's
+ * fx, fy, cx, cy; at least 5 points; each point's covariance (LINEextractor::compPt3dCov, depth noise model of
+ * LineExtractor.cpp:27-38) whitened through cv::SVD; a RANSAC of at most 10 draws under the Mahalanobis point-to-line
+ * distance (< 3) with the 10-cell support test (extract3dline_mahdist, verify3dLine), the SVD refit loop
+ * (computeLine3d_svd) and the two extreme inliers as end points; kept if they are more than 2 cm apart.
+ * depth: CV_32F metres (the output of psl_convert_rgbd).  lines3d [n*6] = mvLines3D first / second (zeros when there is
+ * no line), line_eq [n*3] = mvLineEq (unit direction as float; (-1,-1,-1) when there is no line).
+ * rand() of random_unique (LineExtractor.h:25-37) is pinned to the ANSI C example generator, re-seeded per line with
+ * seed * 1000003 + line index + 1 (the reference draws from the process-wide stream).  HOST pointers. */
+int psl_lines_3d(psl_ctx* ctx, const psl_keyline* kl_un, int32_t n, const float* depth, int32_t w, int32_t h, float fx,
+                 float fy, float cx, float cy, uint32_t seed, double* lines3d, float* line_eq);
+/* Batched, DEVICE pointers, asynchronous: frame b owns rows [b*cap, b*cap + d_n[b]) of d_kl / d_lines3d / d_line_eq and
+ * the depth image at d_depth + b * depth_frame_stride_px (row stride depth_stride_px floats). */
+int psl_lines_3d_dev(psl_ctx* ctx, const psl_keyline* d_kl, const int32_t* d_n, int32_t cap, int32_t B, const float* d_depth,
+                     int32_t w, int32_t h, int32_t depth_stride_px, int64_t depth_frame_stride_px, float fx, float fy,
+                     float cx, float cy, uint32_t seed, double* d_lines3d, float* d_line_eq);
+
 /* One entry of Frame::intersection_lines_plane (the junctions CPartiallyRecoverConnectivity / convertFansToKeyLines
  * found, Frame.cc:504-511): the two line indices, the 2-D junction and its 3-D position in the camera frame. */
 typedef struct psl_line_junction {

@@ -110,6 +110,9 @@ int orc_line_fuse(const psl_keyline* kl, int n_lines, const uint8_t* kf_desc, co
                   const uint8_t* qdesc, int nq, float th_cos, int th_low, int32_t* best_idx, int32_t* best_dist);
 int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,
                               const uint8_t* claimed_in, int mode, float nn_ratio, int32_t* assign);
+/* Frame::isLineGood (orc_line3d.cpp): Frame.cc:662-750, LineExtractor.cpp:27-323 */
+void orc_lines_3d(const psl_keyline* kl, int n, const float* depth, int w, int h, int stride, const float* cam,
+                  uint32_t seed, double* lines3d, float* line_eq);
 int orc_plane_hypotheses(const psl_keyline* kl_un, const float* line_eq, const double* lines3d, int n_lines,
                          const psl_line_junction* js, int nj, double* le_l, float* planes, double* normals,
                          int32_t* junction_of, int cap);

@@ -466,6 +466,18 @@ def line_fuse(kl, kf_desc, queries, qdesc, th_cos=0.998, th_low=50):
     return bi[:nq].copy(), bd[:nq].copy(), int(n)
 
 
+def lines_3d(kl, depth_f32, fx, fy, cx, cy, seed):
+    """Frame::isLineGood: (mvLines3D [n,6] f64, mvLineEq [n,3] f32)."""
+    from psl_slam_b200._lib import KEYLINE_DTYPE
+    kl = np.ascontiguousarray(kl, KEYLINE_DTYPE)
+    dep = np.ascontiguousarray(depth_f32, np.float32)
+    cam = np.array([fx, fy, cx, cy], np.float32)
+    n = len(kl)
+    l3, eq = np.zeros((max(n, 1), 6)), np.zeros((max(n, 1), 3), np.float32)
+    lib().orc_lines_3d(_p(kl), n, _p(dep), dep.shape[1], dep.shape[0], dep.shape[1], _p(cam), C.c_uint32(seed), _p(l3), _p(eq))
+    return l3[:n].copy(), eq[:n].copy()
+
+
 def plane_hypotheses(kl_un, line_eq, lines3d, junctions, cap=None):
     """Frame::ExtractLSD plane hypotheses: (le_l [nj,6], planes [np,4], normals [np,3], junction_of [np], count)."""
     from psl_slam_b200._lib import JUNCTION_DTYPE, KEYLINE_DTYPE

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|linefuse|undistort|planes|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|linefuse|undistort|planes|lines3d|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -478,6 +478,37 @@ def make_planes():
               f"(nan planes {int(np.isnan(pl).any(1).sum())})")
 
 
+def make_lines3d():
+    """Frame::isLineGood: the lines of the linematch pairs over the sequence's depth (clean, noisy, noisy with holes);
+    both SVDs are the real cv2.SVDecomp (oracle/pyref/line3d_py.py)."""
+    from oracle.pyref import line3d_py
+    K = synth.ICL
+    _, depth, _ = synth.sequence(2, 2)
+    low_kl = np.load(os.path.join(OUT, "linematch_pair1.npz"))["kl_cur"]
+    tex_kl = np.load(os.path.join(OUT, "linematch_pair0.npz"))["kl_cur"]
+    rng = np.random.default_rng(900)
+    base = (depth[1].astype(np.float32) * np.float32(1.0 / K["depth_factor"])).astype(np.float32)
+    cases = [("clean", tex_kl, 0.0, 0.0, 7), ("noisy", tex_kl, 0.01, 0.05, 8), ("holes", tex_kl, 0.03, 0.2, 9),
+             ("lowtex", low_kl, 0.02, 0.1, 10)]
+    for name, kl, noise, holes, seed in cases:
+        dep = (base * (1 + rng.normal(0, noise, base.shape))).astype(np.float32)
+        dep[rng.random(base.shape) < holes] = 0
+        if name == "lowtex":  # a depth step across the image: lines that straddle it need the RANSAC
+            dep[:, 320:] = (dep[:, 320:] * np.float32(1.35)).astype(np.float32)
+        # keep the fixture small: only the depth within 2 px of a line is ever read, the rest is zeroed
+        import cv2
+        mask = np.zeros(dep.shape, np.uint8)
+        for k in kl:
+            cv2.line(mask, (int(round(float(k["start_x"]))), int(round(float(k["start_y"])))),
+                     (int(round(float(k["end_x"]))), int(round(float(k["end_y"])))), 1, thickness=5)
+        dep = (dep * mask).astype(np.float32)
+        l3, eq = line3d_py.is_line_good(kl, dep, K["fx"], K["fy"], K["cx"], K["cy"], seed)
+        np.savez_compressed(os.path.join(OUT, f"lines3d_{name}.npz"), kl=kl, depth=dep,
+                            cam=np.array([K["fx"], K["fy"], K["cx"], K["cy"]], np.float32), seed=np.uint32(seed),
+                            lines3d=l3, line_eq=eq)
+        print(f"lines3d_{name}: lines {len(kl)} with a 3-D line {int((np.abs(l3).sum(1) > 0).sum())}")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(OUT, exist_ok=True)
@@ -499,3 +530,5 @@ if __name__ == "__main__":
         make_undistort()
     if what in ("planes", "all"):
         make_planes()
+    if what in ("lines3d", "all"):
+        make_lines3d()

@@ -149,7 +149,8 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_search_geom", "psl_line_frame_bf_match", "psl_line_search_double", "psl_line_match_projection",
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
            "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation", "psl_line_fuse",
-           "psl_undistort_keypoints", "psl_undistort_keypoints_dev", "psl_image_bounds", "psl_plane_hypotheses"]
+           "psl_undistort_keypoints", "psl_undistort_keypoints_dev", "psl_image_bounds", "psl_plane_hypotheses",
+           "psl_lines_3d", "psl_lines_3d_dev"]
 
 _lib = None
 
@@ -205,6 +206,8 @@ def lib():
         L.psl_undistort_keypoints.argtypes = [_p, _p, _i, _p, _p]
         L.psl_undistort_keypoints_dev.argtypes = [_p, _p, _p, _i, _i, _p, _p]
         L.psl_image_bounds.argtypes = [_p, _i, _i, _p, _p]
+        L.psl_lines_3d.argtypes = [_p, _p, _i, _p, _i, _i, _f, _f, _f, _f, C.c_uint32, _p, _p]
+        L.psl_lines_3d_dev.argtypes = [_p, _p, _p, _i, _i, _p, _i, _i, _i, _l, _f, _f, _f, _f, C.c_uint32, _p, _p]
         L.psl_plane_hypotheses.argtypes = [_p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p]
         L.psl_line_fuse.argtypes = [_p, _p, _i, _p, _i, _p, _p, _i, _f, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]

@@ -36,6 +36,10 @@ void launch_line_projection(const LineSet& F, const double* lineeq, const double
                             float w_inv, float h_inv, int mode, float nn_ratio, const uint8_t* claimed_in,
                             uint16_t* cells, uint8_t* ncell, unsigned long long* keys, uint8_t* claimed, int32_t* assign,
                             int32_t* nmatches, int B, cudaStream_t st);
+// Frame::isLineGood (Frame.cc:662-750): mvLines3D [B][cap][6] f64 and mvLineEq [B][cap][3] f32 of frame b's n_lines[b] KeyLines
+void launch_lines3d(const psl_keyline* kl, const int32_t* n_lines, int cap, const float* depth, int w, int h, int stride,
+                    int64_t frame_stride, float fx, float fy, float cx, float cy, uint32_t seed, double* lines3d,
+                    float* line_eq, int B, cudaStream_t st);
 // Frame::ExtractLSD plane hypotheses (Frame.cc:512-645): one warp; n_planes counts every kept hypothesis (> cap = overflow)
 void launch_plane_hypotheses(const psl_keyline* kl_un, const float* line_eq, const double* lines3d,
                              const psl_line_junction* js, int nj, double* le_l, float* planes, double* normals,

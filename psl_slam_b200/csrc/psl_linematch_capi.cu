@@ -324,4 +324,42 @@ int psl_plane_hypotheses(psl_ctx* ctx, const psl_keyline* kl_un, const float* li
   return PSL_OK;
 }
 
+int psl_lines_3d_dev(psl_ctx* ctx, const psl_keyline* d_kl, const int32_t* d_n, int32_t cap, int32_t B, const float* d_depth,
+                     int32_t w, int32_t h, int32_t depth_stride_px, int64_t depth_frame_stride_px, float fx, float fy,
+                     float cx, float cy, uint32_t seed, double* d_lines3d, float* d_line_eq) {
+  if (!ctx) return PSL_E_INVALID;
+  if (B < 0 || cap < 1 || w <= 0 || h <= 0 || depth_stride_px < w || !(fx != 0.f) || !(fy != 0.f) ||
+      (B > 0 && (!d_kl || !d_n || !d_depth || !d_lines3d || !d_line_eq)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  size_t e = prof_mark(ctx);
+  launch_lines3d(d_kl, d_n, cap, d_depth, w, h, depth_stride_px, depth_frame_stride_px, fx, fy, cx, cy, seed, d_lines3d,
+                 d_line_eq, B, ctx->stream);
+  prof_span(ctx, 15, e, 1);
+  PSL_CK(cudaGetLastError());
+  return PSL_OK;
+}
+
+int psl_lines_3d(psl_ctx* ctx, const psl_keyline* kl_un, int32_t n, const float* depth, int32_t w, int32_t h, float fx,
+                 float fy, float cx, float cy, uint32_t seed, double* lines3d, float* line_eq) {
+  if (!ctx) return PSL_E_INVALID;
+  if (n < 0 || w <= 0 || h <= 0 || !depth || (n > 0 && (!kl_un || !lines3d || !line_eq)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (n == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  PSL_UP(ctx->m_misc[0], kl_un, (size_t)n * sizeof(psl_keyline));
+  PSL_UP(ctx->m_misc[1], depth, (size_t)w * h * 4);
+  PSL_UP(ctx->m_n, &n, 4);
+  PSL_ENS(ctx->m_misc[2], (size_t)n * 48);
+  PSL_ENS(ctx->m_misc[3], (size_t)n * 12);
+  int rc = psl_lines_3d_dev(ctx, ctx->m_misc[0].as<psl_keyline>(), ctx->m_n.as<int32_t>(), n, 1, ctx->m_misc[1].as<float>(), w,
+                            h, w, (int64_t)w * h, fx, fy, cx, cy, seed, ctx->m_misc[2].as<double>(),
+                            ctx->m_misc[3].as<float>());
+  if (rc) return rc;
+  PSL_CK(cudaMemcpyAsync(lines3d, ctx->m_misc[2].p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(line_eq, ctx->m_misc[3].p, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_status(ctx);
+}
+
 }  // extern "C"

@@ -181,3 +181,15 @@ def plane_hypotheses(ctx: Context, kl_un, line_eq, lines3d, junctions, cap: int 
     ctx.check(_lib.lib().psl_plane_hypotheses(ctx.handle, _ptr(kl), _ptr(eq), _ptr(l3), len(kl), _ptr(js), nj, _ptr(le),
                                               _ptr(pl), _ptr(nr), _ptr(ow), cap, C.byref(n)))
     return le[:nj], pl[: n.value], nr[: n.value], ow[: n.value]
+
+
+def lines_3d(ctx: Context, kl_un, depth_f32, fx, fy, cx, cy, seed: int = 0):
+    """Frame::isLineGood (Frame.cc:662-750): (mvLines3D [n,6] f64, mvLineEq [n,3] f32) of the KeyLines from the CV_32F
+    depth image; `seed` pins random_unique's rand() (see include/psl_frontend.h)."""
+    kl = np.ascontiguousarray(kl_un, KEYLINE_DTYPE)
+    dep = np.ascontiguousarray(depth_f32, np.float32)
+    n = len(kl)
+    l3, eq = np.zeros((max(n, 1), 6)), np.zeros((max(n, 1), 3), np.float32)
+    ctx.check(_lib.lib().psl_lines_3d(ctx.handle, _ptr(kl), n, _ptr(dep), dep.shape[1], dep.shape[0], C.c_float(fx),
+                                      C.c_float(fy), C.c_float(cx), C.c_float(cy), C.c_uint32(seed), _ptr(l3), _ptr(eq)))
+    return l3[:n], eq[:n]

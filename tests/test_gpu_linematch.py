@@ -207,3 +207,49 @@ def test_plane_hypotheses_vs_golden_and_oracle(orc, name):
         assert e.value.code == -3
     le, pl, nr, ow = plane_hypotheses(ctx, g["kl"], g["line_eq"], g["lines3d"], g["junctions"][:0])
     assert len(pl) == 0 and len(le) == 0
+
+
+@pytest.mark.parametrize("name", golden_names("lines3d_"))
+def test_lines_3d_vs_golden_and_oracle(orc, name):
+    """Frame::isLineGood on CUDA against the cv2-SVD golden and the oracle, host and batched device forms."""
+    import ctypes as C
+
+    import torch
+
+    from psl_slam_b200 import KEYLINE_DTYPE, Context, _lib, default_config, lines_3d
+    g = load_golden(name)
+    cam = [float(v) for v in g["cam"]]
+    ctx = Context(default_config())
+    l3, eq = lines_3d(ctx, g["kl"], g["depth"], *cam, int(g["seed"]))
+    assert np.array_equal(l3, g["lines3d"]) and np.array_equal(eq, g["line_eq"])
+    for seed in (1, 2, 12345):
+        want = orc.lines_3d(g["kl"], g["depth"], *cam, seed)
+        got = lines_3d(ctx, g["kl"], g["depth"], *cam, seed)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    l3z, eqz = lines_3d(ctx, g["kl"], np.zeros_like(g["depth"]), *cam, 1)
+    assert not l3z.any() and (eqz == -1).all()
+    # batched device form: two frames (the second with half the lines and a shifted depth), strided depth rows
+    kl = np.ascontiguousarray(g["kl"], KEYLINE_DTYPE)
+    n, cap = len(kl), len(kl) + 3
+    h, w = g["depth"].shape
+    stride = w + 5
+    dep2 = np.zeros((2, h, stride), np.float32)
+    dep2[0, :, :w] = g["depth"]
+    dep2[1, :, :w] = g["depth"] * np.float32(1.1)
+    klb = np.zeros((2, cap), KEYLINE_DTYPE)
+    klb[0, :n] = kl
+    klb[1, : n // 2] = kl[: n // 2]
+    ns = [n, n // 2]
+    d_kl = torch.from_numpy(klb.view(np.uint8).reshape(2, cap, 68)).cuda()
+    d_n = torch.tensor(ns, dtype=torch.int32, device="cuda")
+    d_dep = torch.from_numpy(dep2).cuda()
+    d_l3 = torch.full((2, cap, 6), 7.0, dtype=torch.float64, device="cuda")
+    d_eq = torch.full((2, cap, 3), 7.0, dtype=torch.float32, device="cuda")
+    ctx.check(_lib.lib().psl_lines_3d_dev(ctx.handle, d_kl.data_ptr(), d_n.data_ptr(), cap, 2, d_dep.data_ptr(), w, h, stride,
+                                          h * stride, C.c_float(cam[0]), C.c_float(cam[1]), C.c_float(cam[2]),
+                                          C.c_float(cam[3]), C.c_uint32(5), d_l3.data_ptr(), d_eq.data_ptr()))
+    ctx.sync()
+    for b in range(2):
+        want = orc.lines_3d(klb[b, : ns[b]], np.ascontiguousarray(dep2[b, :, :w]), *cam, 5)
+        assert np.array_equal(d_l3[b, : ns[b]].cpu().numpy(), want[0]) and np.array_equal(d_eq[b, : ns[b]].cpu().numpy(), want[1])
+        assert (d_l3[b, ns[b]:].cpu().numpy() == 7.0).all()

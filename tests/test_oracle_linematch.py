@@ -120,3 +120,20 @@ def test_plane_hypotheses(orc, name):
     assert n == len(g["planes"]) and np.array_equal(pl, g["planes"][:1], equal_nan=True)
     le, pl, nr, ow, n = orc.plane_hypotheses(g["kl"], g["line_eq"], g["lines3d"], g["junctions"][:0])
     assert n == 0 and len(le) == 0
+
+
+@pytest.mark.parametrize("name", golden_names("lines3d_"))
+def test_lines_3d(orc, name):
+    """Frame::isLineGood: the oracle (own Jacobi SVD) against the restatement over the real cv2.SVDecomp."""
+    g = load_golden(name)
+    cam = [float(v) for v in g["cam"]]
+    l3, eq = orc.lines_3d(g["kl"], g["depth"], *cam, int(g["seed"]))
+    assert np.array_equal(l3, g["lines3d"]) and np.array_equal(eq, g["line_eq"])
+    assert (np.abs(l3).sum(1) > 0).sum() >= 20
+    # another seed draws other pairs: end points may change, the set of lines with a fit hardly does
+    l3b, _ = orc.lines_3d(g["kl"], g["depth"], *cam, int(g["seed"]) + 1)
+    assert abs(int((np.abs(l3b).sum(1) > 0).sum()) - int((np.abs(l3).sum(1) > 0).sum())) <= 6
+    # no depth at all / no lines
+    l3z, eqz = orc.lines_3d(g["kl"], np.zeros_like(g["depth"]), *cam, 1)
+    assert not l3z.any() and (eqz == -1).all()
+    assert len(orc.lines_3d(g["kl"][:0], g["depth"], *cam, 1)[0]) == 0
