@@ -236,11 +236,11 @@ __global__ void __launch_bounds__(32)
 // ---------------------------------------------------------------------------------------------------
 // The sequential core, one frame per warp.  Region growing is order dependent (every accepted pixel moves
 // the region angle the next neighbour is tested against), so the warp does not split the region; it
-// evaluates the next <= 27 neighbour tests of the reference's loop at once (the 3x3 neighbourhoods of up to
-// three consecutive region points, lane order = loop order), accepts the first aligned one, updates the
+// evaluates the next <= 32 neighbour tests of the reference's loop at once (the 8 neighbours of up to
+// four consecutive region points, lane order = loop order), accepts the first aligned one, updates the
 // angle, and re-evaluates only the lanes after it — exactly the sequence of decisions of the scalar loop
 // (lsd_core.cuh, which the CPU suite checks against the oracle) with the loads and the per-pixel arithmetic
-// done 27-wide.  The fp64 running sums of region2rect / refine are added in the reference's order
+// done 32-wide.  The fp64 running sums of region2rect / refine are added in the reference's order
 // (one lane-ordered shuffle chain), the extents are exact min/max reductions.
 // ---------------------------------------------------------------------------------------------------
 #ifdef PSL_LSD_STATS
@@ -291,7 +291,7 @@ __device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec
   return n_theta <= prec;
 }
 
-// the <= 27 neighbour tests of up to three consecutive region points, one per lane in loop order
+// the <= 32 neighbour tests of up to four consecutive region points, one per lane in loop order
 struct Nbr {
   int nidx;       // pixel index, -1 = outside the image / idle lane
   uint32_t npk;   // packed y << 16 | x
@@ -336,7 +336,7 @@ __device__ __forceinline__ Nbr load_nbr(const Frame& f, int first, int m, int n,
 //    (cos_i * sumdx + sin_i * sumdy against cos(prec -/+ 0.5 deg) * |sum|): fastAtan2 is within 0.01 deg of the
 //    true angle and the fp32 dot product within 1e-6, so outside the +/- 0.5 deg band the outcome is certain;
 //    only a neighbour inside the band takes the exact path (fastAtan2 of the sums + the fp64 comparison);
-//  * a whole step (<= 27 tests) is decided at once when that is provably what the scalar loop would do:
+//  * a whole step (<= 32 tests) is decided at once when that is provably what the scalar loop would do:
 //    guess the accepted set A from the sums before the step, give every lane the sums it would see in the
 //    scalar loop (the prefix over the lanes of A before it), and re-test; if every lane's outcome under its own
 //    prefix is certain and reproduces A, then A is the scalar loop's result by induction over the lanes.  The
@@ -411,7 +411,9 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
   g.n = 1;
   const int sy = seed / W, sx = seed - sy * W;
   const uint32_t c0 = ((uint32_t)sy << 16) | (uint32_t)sx;
-  const int p = lane / 9, k = lane - 9 * p;
+  // four region points per step, eight lanes each: the centre of a 3x3 neighbourhood is the region point itself
+  // (USED, never a candidate), so the loop's nine tests are the eight below in the same order
+  const int p = lane >> 3, k8 = lane & 7, k = k8 + (k8 >= 4);
   const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
   // the seed's neighbours are requested before the seed is written back (none of them is the seed's own record
   // as a candidate: the centre lane is struck below)
@@ -479,8 +481,10 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
         const unsigned E = __ballot_sync(kFull, expect);
         batched = __all_sync(kFull, certain) && E == A;
         if (batched) {
-          new_dx = __shfl_sync(kFull, Px, 31);
-          new_dy = __shfl_sync(kFull, Py, 31);
+          // lane 31's prefix misses its own term when it is accepted itself (the last addition of the step)
+          const bool last = (A >> 31) != 0u;
+          new_dx = __shfl_sync(kFull, last ? Px + cur.rec.y : Px, 31);
+          new_dy = __shfl_sync(kFull, last ? Py + cur.rec.z : Py, 31);
         }
       }
     }
@@ -488,11 +492,11 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
       const int n_old = g.n, n_new = n_old + __popc(A);
       if (i >= n_new) break;      // the list is exhausted (A is empty here)
       // region points i .. i+2: from the list while they exist, else the lanes of A in order
-      const int m2 = min(3, n_new - i), idx = i + p;
+      const int m2 = min(4, n_new - i), idx = i + p;
       uint32_t c = 0;
-      const unsigned A1 = A & (A - 1), A2 = A1 & (A1 - 1);
+      const unsigned A1 = A & (A - 1), A2 = A1 & (A1 - 1), A3 = A2 & (A2 - 1);
       const int r = idx - n_old;  // >= 0: the r-th accepted lane of this step
-      const int src = r <= 0 ? __ffs(A) - 1 : (r == 1 ? __ffs(A1) - 1 : __ffs(A2) - 1);
+      const int src = r <= 0 ? __ffs(A) - 1 : (r == 1 ? __ffs(A1) - 1 : (r == 2 ? __ffs(A2) - 1 : __ffs(A3) - 1));
       const uint32_t fromA = __shfl_sync(kFull, cur.npk, src < 0 ? 0 : src);
       if (p < m2) c = idx < n_old ? reg_at(f, idx, n_old) : fromA;
       Nbr nxt = load_nbr_at(f, p < m2, c, ox, oy);
@@ -519,7 +523,7 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
       step_sequential(f, g, cur, prec, quick, chi2, clo2, lane);
       if (i >= g.n) break;
       __syncwarp();
-      m = min(3, g.n - i);
+      m = min(4, g.n - i);
       cur = load_nbr(f, i, m, g.n, p, ox, oy);
     }
     __syncwarp();
