@@ -302,10 +302,55 @@ typedef struct psl_fuse_query {
  * reprojection error passes the chi-square gate (7.8 stereo / 5.99 mono, :906-931); earliest candidate wins ties.
  * best_idx[nq] = keypoint index if that distance <= th_low (TH_LOW = 50), else -1; best_dist[nq] (may be NULL).
  * The replace-or-add bookkeeping on the MapPoint objects (:953-975) stays with the caller; every query is
- * independent.  inv_level_sigma2: pKF->mvInvLevelSigma2 (nlevels entries). */
+ * independent.  inv_level_sigma2: pKF->mvInvLevelSigma2 (nlevels entries); NULL = no chi-square gate (the Sim3 form, below). */
 int psl_match_fuse(psl_ctx* ctx, const psl_frame_view* kf, const psl_fuse_query* queries, const uint8_t* query_desc,
                    int32_t nq, const float* inv_level_sigma2, int32_t nlevels, int32_t th_low, int32_t* best_idx,
                    int32_t* best_dist);
+
+/* The Sim3 form, ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:983-1100; "next" row N1, caller
+ * LoopClosing::SearchAndFuse, LoopClosing.cc:599), has the same window search without the chi-square gate (:1046-1075):
+ * call psl_match_fuse with inv_level_sigma2 = NULL (u_right of the queries and of kf is then not read).  Tests: the
+ * qfuse / fuse_idx arrays of the loop_pair* goldens.
+ *
+ * ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:290-403, caller
+ * LoopClosing::ComputeSim3, LoopClosing.cc:375) is psl_match_projection mode 0 with: frame->u_right = NULL,
+ * check_orientation = 0, th_dist = TH_LOW (50), every valid query flagged PSL_Q_CLAIMS, min_level = pred-1,
+ * max_level = pred (the loop's level test :376-379 selects the same keypoints in the same order as the level gate of
+ * Frame::GetFeaturesInArea), claimed_in[i] = (vpMatched[i] != NULL) (:370-371, which also skips the keypoints this call
+ * has just filled).  assign[i] = the query whose point this call wrote into vpMatched[i].  Tests: qproj / proj_assign. */
+
+/* ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) (ORBmatcher.cc:522-655; "next" row N1, caller
+ * LoopClosing::ComputeSim3, LoopClosing.cc:265).  As psl_match_bow, but both sides are keyframes: valid1 / valid2[i] != 0
+ * iff the keypoint holds a MapPoint that is not bad (:561-566, :580-586), the acceptance is `bestDist1 < th_low`
+ * (strict, :592) and the result is indexed by KF1: matches12[n1] = KF2 keypoint index or -1 (vpMatches12[idx1] =
+ * vpMapPoints2[matches12[idx1]]); *nmatches = the return value. */
+int psl_match_bow_kf(psl_ctx* ctx, const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int32_t n1,
+                     const psl_feature_vector* fv1, const uint8_t* desc2, const float* angle2, const uint8_t* valid2,
+                     int32_t n2, const psl_feature_vector* fv2, float nn_ratio, int32_t th_low,
+                     int32_t check_orientation, int32_t* matches12, int32_t* nmatches);
+
+/* ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (ORBmatcher.cc:1102-1326; "next" row N1, caller
+ * LoopClosing::ComputeSim3, LoopClosing.cc:323).  The caller keeps the MapPoint side (:1140-1186, :1220-1262: the point
+ * exists, is not bad, is not already matched, positive depth, IsInImage, distance invariance, PredictScale) and passes
+ * one psl_fuse_query per keypoint: q12[i1] = the MapPoint of KF1 keypoint i1 projected into KF2 with radius
+ * th * pKF2->mvScaleFactors[pred] (n = kf1->n queries, mp_desc1 = their descriptors), q21 likewise into KF1
+ * (kf2->n queries); u_right is not read.  Both window searches (smallest Hamming distance at level pred-1..pred, first
+ * candidate on ties, accepted if <= th_high = TH_HIGH) and the agreement test (:1306-1321) run on the device.
+ * matches12[kf1->n] = KF2 keypoint index for the pairs found in both directions, else -1; *nfound = the return value. */
+int psl_match_sim3(psl_ctx* ctx, const psl_frame_view* kf1, const psl_frame_view* kf2, const psl_fuse_query* q12,
+                   const uint8_t* mp_desc1, const psl_fuse_query* q21, const uint8_t* mp_desc2, int32_t th_high,
+                   int32_t* matches12, int32_t* nfound);
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:405-520; "next"
+ * row N1, caller Tracking::MonocularInitialization, Tracking.cc:696).  kps1_un / desc1: F1.mvKeysUn / mDescriptors
+ * (only level-0 keypoints search, :421-423); prev_matched [n1][2] = vbPrevMatched, read as the window centres and
+ * updated in place for the matched keypoints (:514-517); f2 = the searched frame (window of half-size window_size over
+ * its level-0 keypoints, :425).  The greedy loop is order dependent (vMatchedDistance / vnMatches21 un-match earlier
+ * pairs, :441-442, :461-470): the candidates and their distances are found in parallel, the loop itself is replayed in
+ * order by one warp.  matches12[n1] = F2 index or -1; *nmatches = the return value. */
+int psl_match_initialization(psl_ctx* ctx, const psl_keypoint* kps1_un, const uint8_t* desc1, int32_t n1,
+                             float* prev_matched, const psl_frame_view* f2, int32_t window_size, float nn_ratio,
+                             int32_t th_low, int32_t check_orientation, int32_t* matches12, int32_t* nmatches);
 
 /* ------------------------------------------------------------------------------------------------
  * Line matching (add_src/LSDmatcher.cpp, add_src/InsectlineMatch.cpp).  As for points, MapLine / InsectLine

@@ -3,6 +3,7 @@
 // (src/Frame.cc:269-284, 985-1050) on plain arrays.  Nothing here is used by the product.
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -309,7 +310,9 @@ int orc_match_fuse(const psl_frame_view* kf, const psl_fuse_query* qs, const uin
       const int kpLevel = kp.octave;
       if (kpLevel < Q.pred_level - 1 || kpLevel > Q.pred_level) continue;
       const float ex = Q.u - kp.x, ey = Q.v - kp.y;
-      if (kf->u_right && kf->u_right[idx] >= 0) {
+      if (!inv_level_sigma2) {
+        // the Sim3 form (ORBmatcher.cc:1046-1075) has no reprojection gate
+      } else if (kf->u_right && kf->u_right[idx] >= 0) {
         const float er = Q.u_right - kf->u_right[idx];
         const float e2 = ex * ex + ey * ey + er * er;
         if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
@@ -323,6 +326,152 @@ int orc_match_fuse(const psl_frame_view* kf, const psl_fuse_query* qs, const uin
     if (best_dist) best_dist[q] = bestDist;
     if (bestDist <= th_low) best_idx[q] = bestIdx;
   }
+  return 0;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), ORBmatcher.cc:522-655
+int orc_match_bow_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                     const psl_feature_vector* fv1, const uint8_t* desc2, const float* angle2, const uint8_t* valid2,
+                     int n2, const psl_feature_vector* fv2, float nn_ratio, int th_low, int check_orientation,
+                     int32_t* matches12, int32_t* nmatches) {
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  std::vector<char> vbMatched2((size_t)n2, 0);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int nm = 0, a = 0, b = 0;
+  while (a < fv1->n_nodes && b < fv2->n_nodes) {
+    if (fv1->node_id[a] == fv2->node_id[b]) {
+      for (int i1 = fv1->offs[a]; i1 < fv1->offs[a + 1]; ++i1) {
+        const int idx1 = (int)fv1->idx[i1];
+        if (!valid1[idx1]) continue;  // :561-566
+        const uint8_t* d1 = desc1 + 32 * (size_t)idx1;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int i2 = fv2->offs[b]; i2 < fv2->offs[b + 1]; ++i2) {
+          const int idx2 = (int)fv2->idx[i2];
+          if (vbMatched2[idx2] || !valid2[idx2]) continue;  // :580-586
+          const int dist = desc_dist(d1, desc2 + 32 * (size_t)idx2);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < th_low) {  // :592, strict
+          if ((float)bestDist1 < nn_ratio * (float)bestDist2) {
+            matches12[idx1] = bestIdx2;
+            vbMatched2[bestIdx2] = 1;
+            if (check_orientation) rotHist[rot_bin(angle1[idx1], angle2[bestIdx2])].push_back(idx1);
+            ++nm;
+          }
+        }
+      }
+      ++a; ++b;
+    } else if (fv1->node_id[a] < fv2->node_id[b]) {
+      while (a < fv1->n_nodes && fv1->node_id[a] < fv2->node_id[b]) ++a;
+    } else {
+      while (b < fv2->n_nodes && fv2->node_id[b] < fv1->node_id[a]) ++b;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { matches12[idx] = -1; --nm; }
+    }
+  }
+  *nmatches = nm;
+  return 0;
+}
+
+namespace {
+// one direction of SearchBySim3 after the projection, ORBmatcher.cc:1188-1216 / :1264-1296
+void sim3_direction(const psl_frame_view* kf, const psl_fuse_query* qs, const uint8_t* qdesc, int nq, int th_high,
+                    std::vector<int>& vnMatch) {
+  Grid g(*kf);
+  std::vector<int> cand;
+  vnMatch.assign((size_t)nq, -1);
+  for (int q = 0; q < nq; ++q) {
+    const psl_fuse_query& Q = qs[q];
+    if (!(Q.flags & PSL_Q_VALID)) continue;
+    features_in_area(*kf, g, Q.u, Q.v, Q.radius, -1, -1, cand);
+    int bestDist = INT32_MAX, bestIdx = -1;
+    for (int idx : cand) {
+      const psl_keypoint& kp = kf->kps_un[idx];
+      if (kp.octave < Q.pred_level - 1 || kp.octave > Q.pred_level) continue;
+      const int dist = desc_dist(qdesc + 32 * (size_t)q, kf->desc + 32 * (size_t)idx);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    if (bestDist <= th_high) vnMatch[q] = bestIdx;
+  }
+}
+}  // namespace
+
+// ORBmatcher::SearchBySim3, ORBmatcher.cc:1102-1326 (the MapPoint tests and the projections are the caller's)
+int orc_match_sim3(const psl_frame_view* kf1, const psl_frame_view* kf2, const psl_fuse_query* q12,
+                   const uint8_t* mp_desc1, const psl_fuse_query* q21, const uint8_t* mp_desc2, int th_high,
+                   int32_t* matches12, int32_t* nfound) {
+  std::vector<int> vnMatch1, vnMatch2;
+  sim3_direction(kf2, q12, mp_desc1, kf1->n, th_high, vnMatch1);
+  sim3_direction(kf1, q21, mp_desc2, kf2->n, th_high, vnMatch2);
+  int nFound = 0;
+  for (int i1 = 0; i1 < kf1->n; ++i1) {  // :1306-1321
+    matches12[i1] = -1;
+    const int idx2 = vnMatch1[i1];
+    if (idx2 >= 0) {
+      const int idx1 = vnMatch2[idx2];
+      if (idx1 == i1) { matches12[i1] = idx2; ++nFound; }
+    }
+  }
+  *nfound = nFound;
+  return 0;
+}
+
+// ORBmatcher::SearchForInitialization, ORBmatcher.cc:405-520
+int orc_match_initialization(const psl_keypoint* kps1_un, const uint8_t* desc1, int n1, float* prev_matched,
+                             const psl_frame_view* f2, int window_size, float nn_ratio, int th_low,
+                             int check_orientation, int32_t* matches12, int32_t* nmatches) {
+  int nm = 0;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  std::vector<int> vMatchedDistance((size_t)f2->n, INT32_MAX), vnMatches21((size_t)f2->n, -1);
+  Grid g(*f2);
+  std::vector<int> vIndices2;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    const int level1 = kps1_un[i1].octave;
+    if (level1 > 0) continue;
+    features_in_area(*f2, g, prev_matched[2 * i1], prev_matched[2 * i1 + 1], (float)window_size, level1, level1, vIndices2);
+    if (vIndices2.empty()) continue;
+    const uint8_t* d1 = desc1 + 32 * (size_t)i1;
+    int bestDist = INT32_MAX, bestDist2 = INT32_MAX, bestIdx2 = -1;
+    for (int i2 : vIndices2) {
+      const int dist = desc_dist(d1, f2->desc + 32 * (size_t)i2);
+      if (vMatchedDistance[i2] <= dist) continue;
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+      else if (dist < bestDist2) bestDist2 = dist;
+    }
+    if (bestDist <= th_low) {
+      if (bestDist < (float)bestDist2 * nn_ratio) {
+        if (vnMatches21[bestIdx2] >= 0) { matches12[vnMatches21[bestIdx2]] = -1; --nm; }
+        matches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        ++nm;
+        if (check_orientation) rotHist[rot_bin(kps1_un[i1].angle, f2->kps_un[bestIdx2].angle)].push_back(i1);
+      }
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (matches12[idx1] >= 0) { matches12[idx1] = -1; --nm; }
+    }
+  }
+  for (int i1 = 0; i1 < n1; ++i1)  // :514-517
+    if (matches12[i1] >= 0) {
+      prev_matched[2 * i1] = f2->kps_un[matches12[i1]].x;
+      prev_matched[2 * i1 + 1] = f2->kps_un[matches12[i1]].y;
+    }
+  *nmatches = nm;
   return 0;
 }
 

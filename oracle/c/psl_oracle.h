@@ -67,6 +67,18 @@ int orc_match_triangulation(const psl_keyframe_view* kf1, const psl_feature_vect
 int orc_match_fuse(const psl_frame_view* kf, const psl_fuse_query* qs, const uint8_t* qdesc, int nq,
                    const float* inv_level_sigma2, int th_low, int32_t* best_idx, int32_t* best_dist);
 
+/* loop closing / initialisation: ORBmatcher.cc:522-655, 1102-1326, 405-520 */
+int orc_match_bow_kf(const uint8_t* desc1, const float* angle1, const uint8_t* valid1, int n1,
+                     const psl_feature_vector* fv1, const uint8_t* desc2, const float* angle2, const uint8_t* valid2,
+                     int n2, const psl_feature_vector* fv2, float nn_ratio, int th_low, int check_orientation,
+                     int32_t* matches12, int32_t* nmatches);
+int orc_match_sim3(const psl_frame_view* kf1, const psl_frame_view* kf2, const psl_fuse_query* q12,
+                   const uint8_t* mp_desc1, const psl_fuse_query* q21, const uint8_t* mp_desc2, int th_high,
+                   int32_t* matches12, int32_t* nfound);
+int orc_match_initialization(const psl_keypoint* kps1_un, const uint8_t* desc1, int n1, float* prev_matched,
+                             const psl_frame_view* f2, int window_size, float nn_ratio, int th_low,
+                             int check_orientation, int32_t* matches12, int32_t* nmatches);
+
 /* ---- Frame bookkeeping (orc_frame.cpp): Frame.cc:1342-1381, ORBmatcher.cc:1339-1393 ---- */
 /* Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:1062-1092, 1135-1163) over cv::undistortPoints */
 void orc_undistort_keypoints(const psl_keypoint* kps, int n, const psl_distortion* cam, psl_keypoint* kps_un);

@@ -293,11 +293,56 @@ def match_fuse(kps_un, u_right, desc, bounds, queries, qdesc, inv_sigma2, th_low
     fv, keep = make_frame_view(kps_un, u_right, desc, bounds)
     queries = np.ascontiguousarray(queries, FUSE_QUERY_DTYPE)
     qdesc = np.ascontiguousarray(qdesc, np.uint8)
-    s2 = np.ascontiguousarray(inv_sigma2, np.float32)
+    s2 = None if inv_sigma2 is None else np.ascontiguousarray(inv_sigma2, np.float32)   # None: the Sim3 form
     bi = np.zeros(max(len(queries), 1), np.int32)
     bd = np.zeros(max(len(queries), 1), np.int32)
-    lib().orc_match_fuse(C.byref(fv), _p(queries), _p(qdesc), len(queries), _p(s2), th_low, _p(bi), _p(bd))
+    lib().orc_match_fuse(C.byref(fv), _p(queries), _p(qdesc), len(queries), None if s2 is None else _p(s2), th_low,
+                         _p(bi), _p(bd))
     return bi[: len(queries)].copy(), bd[: len(queries)].copy()
+
+
+def match_bow_kf(desc1, angle1, valid1, csr1, desc2, angle2, valid2, csr2, nn_ratio=0.75, th_low=50,
+                 check_orientation=True):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, ...): (matches12 [n1], nmatches)."""
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    angle1, angle2 = np.ascontiguousarray(angle1, np.float32), np.ascontiguousarray(angle2, np.float32)
+    valid1, valid2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+    f1, k1 = make_feature_vector(*csr1)
+    f2, k2 = make_feature_vector(*csr2)
+    m12 = np.zeros(max(len(desc1), 1), np.int32)
+    nm = C.c_int32()
+    lib().orc_match_bow_kf(_p(desc1), _p(angle1), _p(valid1), len(desc1), C.byref(f1), _p(desc2), _p(angle2), _p(valid2),
+                           len(desc2), C.byref(f2), C.c_float(nn_ratio), th_low, int(check_orientation), _p(m12),
+                           C.byref(nm))
+    return m12[: len(desc1)].copy(), nm.value
+
+
+def match_sim3(kf1, kf2, bounds, q12, mp_desc1, q21, mp_desc2, th_high=100):
+    """ORBmatcher::SearchBySim3 after the projections; kf* = (kps_un, desc): (matches12 [n1], nFound)."""
+    from psl_slam_b200._lib import FUSE_QUERY_DTYPE
+    a, ka = make_frame_view(kf1[0], None, kf1[1], bounds)
+    b, kb = make_frame_view(kf2[0], None, kf2[1], bounds)
+    q12, q21 = np.ascontiguousarray(q12, FUSE_QUERY_DTYPE), np.ascontiguousarray(q21, FUSE_QUERY_DTYPE)
+    d1, d2 = np.ascontiguousarray(mp_desc1, np.uint8), np.ascontiguousarray(mp_desc2, np.uint8)
+    assert len(q12) == a.n and len(q21) == b.n
+    m12 = np.zeros(max(a.n, 1), np.int32)
+    nf = C.c_int32()
+    lib().orc_match_sim3(C.byref(a), C.byref(b), _p(q12), _p(d1), _p(q21), _p(d2), th_high, _p(m12), C.byref(nf))
+    return m12[: a.n].copy(), nf.value
+
+
+def match_initialization(kps1_un, desc1, prev_matched, f2, bounds, window=100, nn_ratio=0.9, th_low=50,
+                         check_orientation=True):
+    """ORBmatcher::SearchForInitialization; f2 = (kps_un, desc): (matches12, nmatches, prev_matched after)."""
+    kps1 = np.ascontiguousarray(kps1_un, KP_DTYPE)
+    d1 = np.ascontiguousarray(desc1, np.uint8)
+    pm = np.array(prev_matched, np.float32, copy=True).reshape(-1, 2)
+    b, kb = make_frame_view(f2[0], None, f2[1], bounds)
+    m12 = np.zeros(max(len(kps1), 1), np.int32)
+    nm = C.c_int32()
+    lib().orc_match_initialization(_p(kps1), _p(d1), len(kps1), _p(pm), C.byref(b), int(window), C.c_float(nn_ratio),
+                                   th_low, int(check_orientation), _p(m12), C.byref(nm))
+    return m12[: len(kps1)].copy(), nm.value, pm
 
 
 # ---- lines ------------------------------------------------------------------------------------------

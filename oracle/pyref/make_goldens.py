@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|line|linematch|linefuse|undistort|planes|lines3d|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|line|linematch|linefuse|undistort|planes|lines3d|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -236,6 +236,105 @@ def make_fuse():
                             bounds=np.array(bounds, np.float32), queries=q, qdesc=da, inv_sigma2=inv_sigma2, best_idx=bi,
                             best_dist=bd)
         print(f"fuse_pair{case}: queries {int((q['flags'] & 1).sum())} fused {(bi >= 0).sum()}")
+
+
+def make_loop():
+    """N1 fixtures, second batch (loop closing + monocular initialisation): SearchByBoW(KF, KF), SearchBySim3, the Sim3
+    forms of Fuse and SearchByProjection, SearchForInitialization — two keyframe pairs of the synthetic sequence."""
+    from oracle import orc
+    from oracle.pyref import frame_py, match_py
+    from psl_slam_b200._lib import FUSE_QUERY_DTYPE
+    K = synth.ICL
+    gray, depth, T = synth.sequence(7, 4)
+    P = orb_cv2.OrbParams()
+    scale = np.array(P.scale, np.float32)
+    bounds = (np.float32(0), np.float32(0), np.float32(640), np.float32(480))
+    rng = np.random.default_rng(71)
+
+    def view(i):
+        kps, desc = orc.orb_extract(gray[i])
+        xy = np.stack([kps["x"], kps["y"]], 1)
+        _, dep = frame_py.stereo_from_rgbd(xy, frame_py.depth_to_float(depth[i]), K["bf"])
+        world = frame_py.unproject(xy, dep, K, np.linalg.inv(T[i]))
+        kun = np.stack([kps["x"], kps["y"], kps["size"], kps["angle"], kps["response"]], 1).astype(np.float32)
+        return kps, desc, dep, world, match_py.FrameView(kun, kps["octave"], None, desc, *bounds)
+
+    def project(world, dep, octave, Tcw, th, valid):
+        """the projection half of the Sim3 matchers (Scw already divided by its scale), float32 as cv::Mat"""
+        Tc = Tcw.astype(np.float32)
+        q = np.zeros(len(world), FUSE_QUERY_DTYPE)
+        for i in range(len(world)):
+            if not valid[i] or not np.isfinite(world[i]).all() or dep[i] <= 0:
+                continue
+            pc = (Tc[:3, :3].astype(np.float64) @ world[i] + Tc[:3, 3]).astype(np.float32)
+            if pc[2] < 0:
+                continue
+            invz = np.float32(1) / pc[2]
+            u = np.float32(np.float32(K["fx"]) * np.float32(pc[0] * invz) + np.float32(K["cx"]))
+            v = np.float32(np.float32(K["fy"]) * np.float32(pc[1] * invz) + np.float32(K["cy"]))
+            if not (0 <= u < 640 and 0 <= v < 480):
+                continue
+            lvl = int(np.clip(octave[i] + rng.integers(-1, 2), 0, P.nlevels - 1))
+            q[i] = (u, v, np.float32(u - np.float32(K["bf"]) * invz), np.float32(th) * scale[lvl], lvl, 1)
+        return q
+
+    def fvec(desc, drop):
+        node = (desc[:, 0] & 0x3F).astype(np.uint32)
+        d = {}
+        for i, nd in enumerate(node):
+            if nd % 7 != drop:
+                d.setdefault(int(nd), []).append(i)
+        return d
+
+    def csr(d):
+        ids = sorted(d)
+        offs = np.cumsum([0] + [len(d[k]) for k in ids]).astype(np.int32)
+        return np.array(ids, np.uint32), offs, np.array([i for k in ids for i in d[k]], np.uint32)
+
+    for case, (a, b) in enumerate([(0, 1), (3, 2)]):
+        ka, da, depa, wa, fva = view(a)
+        kb, db, depb, wb, fvb = view(b)
+        n1, n2 = len(ka), len(kb)
+        # the Sim3 estimate = the true relative pose, slightly off
+        Tb, Ta = T[b].copy(), T[a].copy()
+        Tb[:3, 3] += rng.normal(0, 0.003, 3)
+        Ta[:3, 3] += rng.normal(0, 0.003, 3)
+        # --- SearchByBoW(KF1, KF2)
+        v1, v2 = rng.random(n1) < 0.85, rng.random(n2) < 0.85
+        f1, f2 = fvec(da, 3), fvec(db, 5)
+        bow12, nbow = match_py.search_by_bow_kf(da, ka["angle"], v1, f1, db, kb["angle"], v2, f2, 0.75, 50, True)
+        bow12n, nbown = match_py.search_by_bow_kf(da, ka["angle"], v1, f1, db, kb["angle"], v2, f2, 0.9, 80, False)
+        c1, c2 = csr(f1), csr(f2)
+        # --- SearchBySim3 (th = 7.5, LoopClosing.cc): points of either keyframe not matched by the BoW pass
+        q12 = project(wa, depa, ka["octave"], Tb, 7.5, v1 & (bow12 < 0))
+        taken2 = np.zeros(n2, bool)
+        taken2[bow12[bow12 >= 0]] = True
+        q21 = project(wb, depb, kb["octave"], Ta, 7.5, v2 & ~taken2)
+        sim12, nsim = match_py.search_by_sim3(fva, fvb, q12, da, q21, db, 100)
+        # --- Fuse(pKF, Scw, vpPoints, th = 4) and SearchByProjection(pKF, Scw, vpPoints, vpMatched, th = 10)
+        qf = project(wa, depa, ka["octave"], Tb, 4.0, rng.random(n1) < 0.9)
+        fbi, fbd = match_py.fuse_search_sim3(fvb, qf, da, 50)
+        qp = project(wa, depa, ka["octave"], Tb, 10.0, rng.random(n1) < 0.9)
+        held = rng.random(n2) < 0.3
+        pas, npm = match_py.search_by_projection_sim3(fvb, qp, da, held, 50)
+        # --- SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, 100)
+        pm = np.stack([ka["x"], ka["y"]], 1).astype(np.float32)
+        if case == 1:   # a later attempt: some entries already moved to an earlier frame's matches
+            mv = rng.random(n1) < 0.4
+            pm[mv] += rng.normal(0, 6, (int(mv.sum()), 2)).astype(np.float32)
+        ini12, nini, pm_out = match_py.search_for_initialization(ka, da, pm, fvb, 100, 0.9, 50, True)
+        ini12n, ninin, pm_outn = match_py.search_for_initialization(ka, da, pm, fvb, 40, 0.8, 70, False)
+        np.savez_compressed(os.path.join(OUT, f"loop_pair{case}.npz"), kps1=ka, desc1=da, kps2=kb, desc2=db,
+                            bounds=np.array(bounds, np.float32), valid1=v1.astype(np.uint8), valid2=v2.astype(np.uint8),
+                            nodes1=c1[0], offs1=c1[1], idx1=c1[2], nodes2=c2[0], offs2=c2[1], idx2=c2[2],
+                            bow12=bow12, nbow=np.int32(nbow), bow12_noori=bow12n, nbow_noori=np.int32(nbown),
+                            q12=q12, q21=q21, sim12=sim12, nsim=np.int32(nsim),
+                            qfuse=qf, fuse_idx=fbi, fuse_dist=fbd,
+                            qproj=qp, held=held.astype(np.uint8), proj_assign=pas, nproj=np.int32(npm),
+                            prev_matched=pm, ini12=ini12, nini=np.int32(nini), prev_out=pm_out,
+                            ini12_b=ini12n, nini_b=np.int32(ninin), prev_out_b=pm_outn)
+        print(f"loop_pair{case}: n {n1}/{n2} bow {nbow}/{nbown} sim3 {nsim} (of {int((q12['flags'] & 1).sum())}/"
+              f"{int((q21['flags'] & 1).sum())}) fuse {(fbi >= 0).sum()} proj {npm} init {nini}/{ninin}")
 
 
 def make_line():
@@ -520,6 +619,8 @@ if __name__ == "__main__":
         make_triangulation()
     if what in ("fuse", "all"):
         make_fuse()
+    if what in ("loop", "all"):
+        make_loop()
     if what in ("line", "all"):
         make_line()
     if what in ("linematch", "all"):

@@ -319,3 +319,182 @@ def fuse_search(fv: FrameView, queries, qdesc, inv_sigma2, th_low=50):
         if best <= th_low:
             bi[q] = bidx
     return bi, bd
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Loop-closing / initialisation matchers ("next" row N1, second batch).  Each function below is written from its own
+# overload in src/ORBmatcher.cc, not through the functions above.
+# ---------------------------------------------------------------------------------------------------------------
+def search_by_bow_kf(desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2, nn_ratio=0.75, th_low=50, check_ori=True):
+    """ORBmatcher::SearchByBoW(pKF1, pKF2, vpMatches12) — src/ORBmatcher.cc:522-655.  valid*: the keypoint holds a
+    MapPoint that is not bad; fv*: dict node -> list of indices.  Returns (matches12 [n1] = KF2 index or -1, count)."""
+    n1, n2 = len(desc1), len(desc2)
+    m12 = np.full(n1, -1, np.int32)
+    matched2 = np.zeros(n2, bool)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for node in sorted(set(fv1) & set(fv2)):
+        for idx1 in fv1[node]:
+            if not valid1[idx1]:
+                continue
+            b1, bi, b2 = 256, -1, 256
+            for idx2 in fv2[node]:
+                if matched2[idx2] or not valid2[idx2]:
+                    continue
+                d = popcount_dist(desc1[idx1], desc2[idx2])
+                if d < b1:
+                    b2, b1, bi = b1, d, idx2
+                elif d < b2:
+                    b2 = d
+            if b1 < th_low and F32(b1) < F32(nn_ratio) * F32(b2):      # strict `<TH_LOW` here (:592), unlike :224
+                m12[idx1] = bi
+                matched2[bi] = True
+                if check_ori:
+                    hist[rot_bin(angle1[idx1], angle2[bi])].append(idx1)
+                nm += 1
+    if check_ori:
+        keep = three_maxima([len(h) for h in hist])
+        for b in range(HISTO):
+            if b not in keep:
+                for i in hist[b]:
+                    m12[i] = -1
+                    nm -= 1
+    return m12, nm
+
+
+def _window_best(fv: FrameView, Q, qd):
+    """min-distance keypoint of KeyFrame::GetFeaturesInArea(u, v, radius) at level pred-1..pred (first one on ties)."""
+    best, bidx = 2 ** 31 - 1, -1
+    for i in fv.features_in_area(Q["u"], Q["v"], Q["radius"]):
+        lvl = int(fv.octave[i])
+        if lvl < Q["pred_level"] - 1 or lvl > Q["pred_level"]:
+            continue
+        d = popcount_dist(qd, fv.desc[i])
+        if d < best:
+            best, bidx = d, i
+    return best, bidx
+
+
+def search_by_sim3(fv1: FrameView, fv2: FrameView, q12, qdesc1, q21, qdesc2, th_high=100):
+    """ORBmatcher::SearchBySim3 — src/ORBmatcher.cc:1102-1326 after the projections: q12[i1] = MapPoint of KF1 keypoint
+    i1 projected into KF2 (flags & 1 = it exists, is not bad, not already matched and passed the depth / image /
+    distance tests), q21 likewise.  Returns (matches12 [n1] = KF2 index or -1, nFound)."""
+    n1, n2 = len(q12), len(q21)
+    m1 = np.full(n1, -1, np.int32)
+    m2 = np.full(n2, -1, np.int32)
+    for i1 in range(n1):
+        if q12[i1]["flags"] & 1:
+            best, bidx = _window_best(fv2, q12[i1], qdesc1[i1])
+            if best <= th_high:
+                m1[i1] = bidx
+    for i2 in range(n2):
+        if q21[i2]["flags"] & 1:
+            best, bidx = _window_best(fv1, q21[i2], qdesc2[i2])
+            if best <= th_high:
+                m2[i2] = bidx
+    out = np.full(n1, -1, np.int32)
+    found = 0
+    for i1 in range(n1):
+        idx2 = m1[i1]
+        if idx2 >= 0 and m2[idx2] == i1:
+            out[i1] = idx2
+            found += 1
+    return out, found
+
+
+def fuse_search_sim3(fv: FrameView, queries, qdesc, th_low=50):
+    """The window search of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) — src/ORBmatcher.cc:1046-1075: as the
+    pose form but without the chi-square gate.  Returns (best_idx, best_dist)."""
+    nq = len(queries)
+    bi = np.full(nq, -1, np.int32)
+    bd = np.full(nq, 256, np.int32)
+    for q in range(nq):
+        if not (queries[q]["flags"] & 1):
+            continue
+        best, bidx = _window_best(fv, queries[q], qdesc[q])
+        if bidx >= 0:
+            bd[q] = best
+            if best <= th_low:
+                bi[q] = bidx
+    return bi, bd
+
+
+def search_by_projection_sim3(fv: FrameView, queries, qdesc, matched_in, th_low=50):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) — src/ORBmatcher.cc:290-403 after the
+    projection: queries (u, v, radius, pred_level, flags & 1); matched_in[i] = vpMatched[i] != NULL before the call.
+    Returns (assign [n] = query index written into vpMatched[i] by this call or -1, nmatches)."""
+    matched = matched_in.astype(bool).copy()
+    assign = np.full(fv.n, -1, np.int32)
+    nm = 0
+    for qi, Q in enumerate(queries):
+        if not (Q["flags"] & 1):
+            continue
+        best, bidx = 256, -1
+        for i in fv.features_in_area(Q["u"], Q["v"], Q["radius"]):
+            if matched[i]:
+                continue
+            lvl = int(fv.octave[i])
+            if lvl < Q["pred_level"] - 1 or lvl > Q["pred_level"]:
+                continue
+            d = popcount_dist(qdesc[qi], fv.desc[i])
+            if d < best:
+                best, bidx = d, i
+        if best <= th_low:
+            matched[bidx] = True
+            assign[bidx] = qi
+            nm += 1
+    return assign, nm
+
+
+def search_for_initialization(kps1, desc1, prev_matched, fv2: FrameView, window, nn_ratio=0.9, th_low=50,
+                              check_ori=True):
+    """ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:405-520.
+    kps1: structured keypoints of F1 (mvKeysUn); prev_matched [n1][2] float32.  Returns (matches12, nmatches,
+    prev_matched after the update)."""
+    n1, n2 = len(kps1), fv2.n
+    INT_MAX = 2 ** 31 - 1
+    m12 = np.full(n1, -1, np.int32)
+    m21 = np.full(n2, -1, np.int32)
+    mdist = np.full(n2, INT_MAX, np.int64)
+    hist = [[] for _ in range(HISTO)]
+    nm = 0
+    for i1 in range(n1):
+        level1 = int(kps1["octave"][i1])
+        if level1 > 0:
+            continue
+        cand = fv2.features_in_area(prev_matched[i1, 0], prev_matched[i1, 1], window, level1, level1)
+        if not cand:
+            continue
+        best, best2, bidx = INT_MAX, INT_MAX, -1
+        for i2 in cand:
+            d = popcount_dist(desc1[i1], fv2.desc[i2])
+            if mdist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bidx = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= th_low and F32(best) < F32(F32(best2) * F32(nn_ratio)):
+            if m21[bidx] >= 0:
+                m12[m21[bidx]] = -1
+                nm -= 1
+            m12[i1] = bidx
+            m21[bidx] = i1
+            mdist[bidx] = best
+            nm += 1
+            if check_ori:
+                hist[rot_bin(kps1["angle"][i1], fv2.angle[bidx])].append(i1)
+    if check_ori:
+        keep = three_maxima([len(h) for h in hist])
+        for b in range(HISTO):
+            if b in keep:
+                continue
+            for i in hist[b]:
+                if m12[i] >= 0:
+                    m12[i] = -1
+                    nm -= 1
+    pm = prev_matched.astype(F32).copy()
+    for i1 in range(n1):
+        if m12[i1] >= 0:
+            pm[i1, 0], pm[i1, 1] = fv2.x[m12[i1]], fv2.y[m12[i1]]
+    return m12, nm, pm

@@ -438,6 +438,8 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
   int i = 0, m = 1;
   while (true) {
     i += m;                       // first region point of the next step
+    LSD_STAT(0, 1);
+    LSD_STAT(1, m);
     const unsigned cm = __ballot_sync(kFull, cur.cand);
     bool batched = false;
     unsigned A = 0;
@@ -520,6 +522,7 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
       cur = nxt;
       m = m2;
     } else {
+      LSD_STAT(7, 1);
       step_sequential(f, g, cur, prec, quick, chi2, clo2, lane);
       if (i >= g.n) break;
       __syncwarp();
@@ -747,6 +750,8 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
       LSD_T1(10, t_g);
       LSD_STAT(13, 1);
       if (n < L.min_reg_size) continue;
+      LSD_STAT(2, 1);
+      LSD_STAT(3, n);
       lsdw::Rect rec;
       LSD_T0(t_r);
       lsdw::region2rect(f, n, reg_angle, prec, rec, lane);

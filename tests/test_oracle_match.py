@@ -116,3 +116,67 @@ def test_undistort_keypoints_vs_cv2_golden(orc, cam):
     k = _kp_array(g["pts_rnd"])
     assert orc.undistort_keypoints(k, z).tobytes() == k.tobytes()
     assert orc.image_bounds(640, 480, z) == (0.0, 0.0, 640.0, 480.0)
+
+
+# ---- N1, second batch: loop closing + monocular initialisation (loop_pair* goldens, oracle/pyref/match_py.py) ----
+LOOPS = golden_names("loop_pair")
+
+
+def loop_proj_queries(g):
+    """The qproj fuse-style queries of a loop golden as psl_proj_query records for mode 0 (see psl_frontend.h)."""
+    from psl_slam_b200._lib import QUERY_DTYPE
+    qp = g["qproj"]
+    q = np.zeros(len(qp), QUERY_DTYPE)
+    q["u"], q["v"], q["radius"] = qp["u"], qp["v"], qp["radius"]
+    q["min_level"], q["max_level"] = qp["pred_level"] - 1, qp["pred_level"]
+    q["flags"] = np.where(qp["flags"] & 1, 3, 0).astype(np.uint32)
+    return q
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_search_by_bow_keyframes(orc, name):
+    g = load_golden(name)
+    c1, c2 = (g["nodes1"], g["offs1"], g["idx1"]), (g["nodes2"], g["offs2"], g["idx2"])
+    m, n = orc.match_bow_kf(g["desc1"], g["kps1"]["angle"], g["valid1"], c1, g["desc2"], g["kps2"]["angle"], g["valid2"],
+                            c2, 0.75, 50, True)
+    assert np.array_equal(m, g["bow12"]) and n == int(g["nbow"]) and n > 100
+    m, n = orc.match_bow_kf(g["desc1"], g["kps1"]["angle"], g["valid1"], c1, g["desc2"], g["kps2"]["angle"], g["valid2"],
+                            c2, 0.9, 80, False)
+    assert np.array_equal(m, g["bow12_noori"]) and n == int(g["nbow_noori"])
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_search_by_sim3(orc, name):
+    g = load_golden(name)
+    m, n = orc.match_sim3((g["kps1"], g["desc1"]), (g["kps2"], g["desc2"]), tuple(g["bounds"]), g["q12"], g["desc1"],
+                          g["q21"], g["desc2"], 100)
+    assert np.array_equal(m, g["sim12"]) and n == int(g["nsim"]) and n > 100
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_fuse_and_projection_sim3_forms(orc, name):
+    g = load_golden(name)
+    bi, bd = orc.match_fuse(g["kps2"], None, g["desc2"], tuple(g["bounds"]), g["qfuse"], g["desc1"], None, 50)
+    assert np.array_equal(bi, g["fuse_idx"]) and np.array_equal(bd, g["fuse_dist"]) and (bi >= 0).sum() > 300
+    a, n = orc.match_projection(g["kps2"], None, g["desc2"], tuple(g["bounds"]), loop_proj_queries(g), g["desc1"],
+                                g["held"], 0, 50, 0.9, False)
+    assert np.array_equal(a, g["proj_assign"]) and n == int(g["nproj"]) and n > 200
+
+
+@pytest.mark.parametrize("name", LOOPS)
+def test_search_for_initialization(orc, name):
+    g = load_golden(name)
+    m, n, pm = orc.match_initialization(g["kps1"], g["desc1"], g["prev_matched"], (g["kps2"], g["desc2"]),
+                                        tuple(g["bounds"]), 100, 0.9, 50, True)
+    assert np.array_equal(m, g["ini12"]) and n == int(g["nini"]) and np.array_equal(pm, g["prev_out"]) and n > 100
+    m, n, pm = orc.match_initialization(g["kps1"], g["desc1"], g["prev_matched"], (g["kps2"], g["desc2"]),
+                                        tuple(g["bounds"]), 40, 0.8, 70, False)
+    assert np.array_equal(m, g["ini12_b"]) and n == int(g["nini_b"]) and np.array_equal(pm, g["prev_out_b"])
+    # no level-0 keypoint searches, nothing to search in
+    k = g["kps1"].copy()
+    k["octave"] = 1
+    m, n, pm = orc.match_initialization(k, g["desc1"], g["prev_matched"], (g["kps2"], g["desc2"]), tuple(g["bounds"]))
+    assert n == 0 and (m == -1).all() and np.array_equal(pm, g["prev_matched"])
+    m, n, pm = orc.match_initialization(g["kps1"], g["desc1"], g["prev_matched"], (g["kps2"][:0], g["desc2"][:0]),
+                                        tuple(g["bounds"]))
+    assert n == 0 and (m == -1).all()
