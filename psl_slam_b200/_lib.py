@@ -150,7 +150,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_plane_assoc", "psl_track_frontend_batch", "psl_track_frontend_batch_dev", "psl_convert_rgbd",
            "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation", "psl_line_fuse",
            "psl_undistort_keypoints", "psl_undistort_keypoints_dev", "psl_image_bounds", "psl_plane_hypotheses",
-           "psl_lines_3d", "psl_lines_3d_dev"]
+           "psl_lines_3d", "psl_lines_3d_dev", "psl_match_bow_kf", "psl_match_sim3", "psl_match_initialization"]
 
 _lib = None
 
@@ -211,6 +211,9 @@ def lib():
         L.psl_plane_hypotheses.argtypes = [_p, _p, _p, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p]
         L.psl_line_fuse.argtypes = [_p, _p, _i, _p, _i, _p, _p, _i, _f, _i, _p, _p]
         L.psl_debug_fetch.argtypes = [_p, _i, _i, _i, _p, _l, _p]
+        L.psl_match_bow_kf.argtypes = [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _f, _i, _i, _p, _p]
+        L.psl_match_sim3.argtypes = [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p]
+        L.psl_match_initialization.argtypes = [_p, _p, _p, _i, _p, _p, _i, _f, _i, _i, _p, _p]
         _lib = L
     return _lib
 

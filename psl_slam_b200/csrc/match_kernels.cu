@@ -5,6 +5,8 @@
 // into an embarrassingly parallel stage (ordered candidate lists with distances, one warp per query)
 // and an ordered resolve stage (one warp per frame walks the queries in order; the 32 lanes scan a
 // query's candidates together and pick the lexicographic minimum of (distance, position)).
+#include <climits>
+
 #include "match_kernels.cuh"
 
 namespace psl {
@@ -395,9 +397,10 @@ __global__ void __launch_bounds__(128)
     bow_kernel(const uint4* __restrict__ kf_desc, const float* __restrict__ kf_angle,
                const uint8_t* __restrict__ kf_valid, const int32_t* __restrict__ kf_offs,
                const uint32_t* __restrict__ kf_idx, const uint4* __restrict__ f_desc, const float* __restrict__ f_angle,
-               const int32_t* __restrict__ f_offs, const uint32_t* __restrict__ f_idx, const int2* __restrict__ pairs,
-               int npairs, float nn_ratio, int th_low, int check_ori, int32_t* match_f, int32_t* hist,
-               uint32_t* accepted, int32_t* n_accepted) {
+               const uint8_t* __restrict__ f_valid, const int32_t* __restrict__ f_offs,
+               const uint32_t* __restrict__ f_idx, const int2* __restrict__ pairs, int npairs, float nn_ratio,
+               int th_low, int strict, int check_ori, int32_t* match_f, int32_t* hist, uint32_t* accepted,
+               int32_t* n_accepted) {
   const int lane = threadIdx.x & 31, g = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (g >= npairs) return;
   const int2 pr = pairs[g];
@@ -409,7 +412,8 @@ __global__ void __launch_bounds__(128)
     unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
     for (int j = fs + lane; j < fe; j += 32) {
       const int rf = (int)f_idx[j];
-      if (match_f[rf] >= 0) continue;  // :209-210
+      if (match_f[rf] >= 0) continue;  // :209-210 (KF-KF form: vbMatched2, :583)
+      if (f_valid && !f_valid[rf]) continue;  // KF-KF form: the KF2 keypoint holds no good MapPoint (:583-587)
       const unsigned key = ((unsigned)hamming256(q0, q1, __ldg(f_desc + 2 * rf), __ldg(f_desc + 2 * rf + 1)) << 16) |
                            (unsigned)(j - fs);
       if (key < k1) { k2 = k1; k1 = key; }
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(128)
     if (best == 0xFFFFFFFFu) continue;
     const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
     const int d1 = (int)(best >> 16), d2 = second == 0xFFFFFFFFu ? 256 : (int)(second >> 16);
-    if (d1 <= th_low && (float)d1 < __fmul_rn(nn_ratio, (float)d2)) {
+    if ((strict ? d1 < th_low : d1 <= th_low) && (float)d1 < __fmul_rn(nn_ratio, (float)d2)) {  // :224 / :592
       const int rf = (int)f_idx[fs + (int)(best & 0xFFFFu)];
       if (lane == 0) {
         match_f[rf] = rk;
@@ -457,19 +461,29 @@ __global__ void bow_finalize_kernel(int check_ori, int32_t* match_f, const int32
   if (threadIdx.x == 0) *nmatches = n - s_drop;
 }
 
+__global__ void bow_invert_kernel(const int32_t* __restrict__ match_f, int nf, int32_t* __restrict__ m12) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nf && match_f[i] >= 0) m12[match_f[i]] = i;  // a KF1 keypoint is matched at most once
+}
+
 void launch_bow(const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid, const int32_t* kf_offs,
-                const uint32_t* kf_idx, const uint8_t* f_desc, const float* f_angle, const int32_t* f_offs,
-                const uint32_t* f_idx, const int2* pairs, int npairs, float nn_ratio, int th_low, int check_ori, int nf,
-                int32_t* match_f, int32_t* hist, uint32_t* accepted, int32_t* n_accepted, int32_t* nmatches,
-                cudaStream_t st) {
+                const uint32_t* kf_idx, const uint8_t* f_desc, const float* f_angle, const uint8_t* f_valid,
+                const int32_t* f_offs, const uint32_t* f_idx, const int2* pairs, int npairs, float nn_ratio, int th_low,
+                int strict, int check_ori, int nf, int32_t* match_f, int32_t* hist, uint32_t* accepted,
+                int32_t* n_accepted, int32_t* nmatches, int32_t* m12, int nkf, cudaStream_t st) {
   cudaMemsetAsync(match_f, 0xFF, (size_t)nf * sizeof(int32_t), st);
   cudaMemsetAsync(hist, 0, 32 * sizeof(int32_t), st);
   cudaMemsetAsync(n_accepted, 0, sizeof(int32_t), st);
   if (npairs > 0)
     bow_kernel<<<(npairs + 3) / 4, 128, 0, st>>>((const uint4*)kf_desc, kf_angle, kf_valid, kf_offs, kf_idx,
-                                                 (const uint4*)f_desc, f_angle, f_offs, f_idx, pairs, npairs, nn_ratio,
-                                                 th_low, check_ori, match_f, hist, accepted, n_accepted);
+                                                 (const uint4*)f_desc, f_angle, f_valid, f_offs, f_idx, pairs, npairs,
+                                                 nn_ratio, th_low, strict, check_ori, match_f, hist, accepted,
+                                                 n_accepted);
   bow_finalize_kernel<<<1, 128, 0, st>>>(check_ori, match_f, hist, accepted, n_accepted, nmatches);
+  if (m12) {  // KF-KF form: the result is indexed by the first keyframe (vpMatches12)
+    cudaMemsetAsync(m12, 0xFF, (size_t)nkf * sizeof(int32_t), st);
+    if (nf > 0) bow_invert_kernel<<<(nf + 127) / 128, 128, 0, st>>>(match_f, nf, m12);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -606,7 +620,9 @@ __global__ void __launch_bounds__(kCandWarps * 32)
           if (kp.octave < Q.pred_level - 1 || kp.octave > Q.pred_level) continue;
           const float ex = __fsub_rn(x, kp.x), ey = __fsub_rn(y, kp.y);
           const float kr = f.u_right ? f.u_right[i] : -1.f;
-          if (kr >= 0.f) {
+          if (!inv_sigma2) {
+            // the Sim3 forms (ORBmatcher.cc:1046-1075, 1188-1216) have no reprojection gate
+          } else if (kr >= 0.f) {
             const float er = __fsub_rn(Q.u_right, kr);
             const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
             if ((double)__fmul_rn(e2, inv_sigma2[kp.octave]) > 7.8) continue;
@@ -650,6 +666,124 @@ void launch_fuse(const MatchFrames& f, const psl_fuse_query* qs, const uint8_t* 
   if (nq <= 0) return;
   fuse_kernel<<<(nq + kCandWarps - 1) / kCandWarps, kCandWarps * 32, 0, st>>>(f, qs, qdesc, nq, cell_start, cell_items,
                                                                              inv_sigma2, th_low, best_idx, best_dist);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SearchBySim3 (ORBmatcher.cc:1102-1326): the two window searches are fuse_kernel launches without a gate; this is
+// the agreement test (:1306-1321).
+// ---------------------------------------------------------------------------------------------
+__global__ void sim3_agree_kernel(const int32_t* __restrict__ m1, int n1, const int32_t* __restrict__ m2,
+                                  int32_t* __restrict__ out, int32_t* __restrict__ nfound) {
+  const int i1 = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i1 < n1) {
+    const int idx2 = m1[i1];
+    ok = idx2 >= 0 && m2[idx2] == i1;
+    out[i1] = ok ? idx2 : -1;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(nfound, __popc(b));
+}
+
+void launch_sim3_agree(const int32_t* m1, int n1, const int32_t* m2, int32_t* out, int32_t* nfound, cudaStream_t st) {
+  cudaMemsetAsync(nfound, 0, sizeof(int32_t), st);
+  if (n1 > 0) sim3_agree_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(m1, n1, m2, out, nfound);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SearchForInitialization (ORBmatcher.cc:405-520): the greedy loop over the F1 keypoints, replayed in order by one
+// warp on the candidate lists of proj_candidates_kernel (window order, with distances).  A later keypoint may take
+// an F2 keypoint from an earlier one if it is strictly closer (vMatchedDistance, :441-442; the earlier pair is
+// dissolved, :461-465), so nothing about a list can be decided before its turn.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+    init_resolve_kernel(const uint32_t* __restrict__ cand, const int32_t* __restrict__ cand_count,
+                        const psl_keypoint* __restrict__ kps1, int n1, const psl_keypoint* __restrict__ kps2, int n2,
+                        float nn_ratio, int th_low, int check_ori, int32_t* mdist, int32_t* m21, uint32_t* accepted,
+                        int32_t* m12, float* prev_matched, int32_t* nmatches) {
+  __shared__ int s_hist[32];
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n2; i += 32) { mdist[i] = INT_MAX; m21[i] = -1; }
+  for (int i = lane; i < n1; i += 32) m12[i] = -1;
+  s_hist[lane] = 0;
+  __syncwarp();
+  int nm = 0, nacc = 0;
+  for (int base = 0; base < n1; base += 32) {
+    const int my_cnt = base + lane < n1 ? cand_count[base + lane] : 0;
+    unsigned todo = __ballot_sync(0xffffffffu, my_cnt > 0);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int i1 = base + j, cnt = __shfl_sync(0xffffffffu, my_cnt, j);
+      const uint32_t* cl = cand + (size_t)i1 * kCandCap;
+      unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+      for (int k = lane; k < cnt; k += 32) {
+        const uint32_t e = cl[k];
+        const int d = (int)(e & 0xFFFFu);
+        if (mdist[e >> 16] <= d) continue;  // :441-442
+        const unsigned key = ((unsigned)d << 16) | (unsigned)k;
+        if (key < k1) { k2 = k1; k1 = key; }
+        else if (key < k2) k2 = key;
+      }
+      const unsigned best = warp_min_u32(k1);
+      if (best == 0xFFFFFFFFu) continue;
+      const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
+      const int bestDist = (int)(best >> 16);
+      const float d2 = second == 0xFFFFFFFFu ? (float)INT_MAX : (float)(int)(second >> 16);
+      if (bestDist <= th_low && (float)bestDist < __fmul_rn(d2, nn_ratio)) {  // :456-458
+        const int i2 = (int)(cl[best & 0xFFFFu] >> 16);
+        const int old = __shfl_sync(0xffffffffu, lane == 0 ? m21[i2] : 0, 0);  // read by the lane that rewrites it
+        if (lane == 0) {
+          if (old >= 0) m12[old] = -1;
+          m12[i1] = i2;
+          m21[i2] = i1;
+          mdist[i2] = bestDist;
+          if (check_ori) {
+            const int bin = rot_bin(kps1[i1].angle, kps2[i2].angle);
+            s_hist[bin] += 1;  // a dissolved pair stays in its bin (rotHist is never shrunk, :461-465)
+            accepted[nacc] = ((uint32_t)i1 << 8) | (uint32_t)bin;
+          }
+        }
+        nm += old >= 0 ? 0 : 1;
+        ++nacc;
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+  if (check_ori) {
+    int b1, b2, b3;
+    three_maxima(s_hist, b1, b2, b3);
+    int dropped = 0;
+    for (int k = lane; k < nacc; k += 32) {
+      const uint32_t e = accepted[k];
+      const int bin = (int)(e & 0xFFu);
+      if (bin != b1 && bin != b2 && bin != b3 && m12[e >> 8] >= 0) {  // :499-503
+        m12[e >> 8] = -1;
+        ++dropped;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, d);
+    nm -= dropped;
+    __syncwarp();
+  }
+  for (int i = lane; i < n1; i += 32) {  // :514-517
+    const int i2 = m12[i];
+    if (i2 >= 0) {
+      prev_matched[2 * i] = kps2[i2].x;
+      prev_matched[2 * i + 1] = kps2[i2].y;
+    }
+  }
+  if (lane == 0) *nmatches = nm;
+}
+
+void launch_init_resolve(const uint32_t* cand, const int32_t* cand_count, const psl_keypoint* kps1, int n1,
+                         const psl_keypoint* kps2, int n2, float nn_ratio, int th_low, int check_ori, int32_t* mdist,
+                         int32_t* m21, uint32_t* accepted, int32_t* m12, float* prev_matched, int32_t* nmatches,
+                         cudaStream_t st) {
+  init_resolve_kernel<<<1, 32, 0, st>>>(cand, cand_count, kps1, n1, kps2, n2, nn_ratio, th_low, check_ori, mdist, m21,
+                                        accepted, m12, prev_matched, nmatches);
 }
 
 }  // namespace psl

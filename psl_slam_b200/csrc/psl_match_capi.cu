@@ -142,9 +142,9 @@ int psl_match_bow(psl_ctx* ctx, const uint8_t* kf_desc, const float* kf_angle, c
   int32_t* d_match = M[10].as<int32_t>();
   int32_t* d_hist = d_match + nf;
   launch_bow(M[0].as<uint8_t>(), M[1].as<float>(), M[2].as<uint8_t>(), M[3].as<int32_t>(), M[4].as<uint32_t>(),
-             M[5].as<uint8_t>(), M[6].as<float>(), M[7].as<int32_t>(), M[8].as<uint32_t>(), M[9].as<int2>(),
-             (int)pairs.size(), nn_ratio, th_low, check_orientation, nf, d_match, d_hist, M[11].as<uint32_t>(),
-             d_hist + 32, d_hist + 33, ctx->stream);
+             M[5].as<uint8_t>(), M[6].as<float>(), nullptr, M[7].as<int32_t>(), M[8].as<uint32_t>(), M[9].as<int2>(),
+             (int)pairs.size(), nn_ratio, th_low, 0, check_orientation, nf, d_match, d_hist, M[11].as<uint32_t>(),
+             d_hist + 32, d_hist + 33, nullptr, nkf, ctx->stream);
   prof_span(ctx, 5, prof_mark(ctx), 2);
   PSL_CK(cudaGetLastError());
   PSL_CK(cudaMemcpyAsync(match_f, d_match, (size_t)nf * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -221,7 +221,7 @@ int psl_match_fuse(psl_ctx* ctx, const psl_frame_view* kf, const psl_fuse_query*
                    int32_t nq, const float* inv_level_sigma2, int32_t nlevels, int32_t th_low, int32_t* best_idx,
                    int32_t* best_dist) {
   if (!ctx) return PSL_E_INVALID;
-  if (!kf || nq < 0 || kf->n < 0 || kf->n > 65535 || nlevels < 1 || nlevels > kMaxLevels || !inv_level_sigma2 ||
+  if (!kf || nq < 0 || kf->n < 0 || kf->n > 65535 || nlevels < 1 || nlevels > kMaxLevels ||
       (kf->n > 0 && (!kf->kps_un || !kf->desc)) || (nq > 0 && (!queries || !query_desc || !best_idx)))
     return fail(ctx, PSL_E_INVALID, "bad argument");
   if (nq == 0) return PSL_OK;
@@ -240,7 +240,7 @@ int psl_match_fuse(psl_ctx* ctx, const psl_frame_view* kf, const psl_fuse_query*
   PSL_UP(M[0], queries, (size_t)nq * sizeof(psl_fuse_query));
   PSL_UP(ctx->m_qdesc, query_desc, (size_t)nq * 32);
   float tab[kMaxLevels] = {0};
-  std::memcpy(tab, inv_level_sigma2, (size_t)nlevels * 4);
+  if (inv_level_sigma2) std::memcpy(tab, inv_level_sigma2, (size_t)nlevels * 4);  // NULL: the Sim3 form, no gate
   PSL_UP(M[1], tab, sizeof(tab));
   const int32_t nn[1] = {n};
   PSL_UP(ctx->m_n, nn, sizeof(nn));
@@ -253,7 +253,7 @@ int psl_match_fuse(psl_ctx* ctx, const psl_frame_view* kf, const psl_fuse_query*
                 ctx->m_n.as<int32_t>(), n, kf->min_x, kf->min_y, kf->grid_w_inv, kf->grid_h_inv};
   launch_grid_build(F, ctx->m_cell_start.as<int32_t>(), ctx->m_cell_items.as<uint16_t>(), 1, ctx->stream);
   launch_fuse(F, M[0].as<psl_fuse_query>(), ctx->m_qdesc.as<uint8_t>(), nq, ctx->m_cell_start.as<int32_t>(),
-              ctx->m_cell_items.as<uint16_t>(), M[1].as<float>(), th_low, ctx->m_assign.as<int32_t>(),
+              ctx->m_cell_items.as<uint16_t>(), inv_level_sigma2 ? M[1].as<float>() : nullptr, th_low, ctx->m_assign.as<int32_t>(),
               ctx->m_nm.as<int32_t>(), ctx->stream);
   prof_span(ctx, 5, prof_mark(ctx), 2);
   PSL_CK(cudaGetLastError());

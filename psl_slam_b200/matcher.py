@@ -130,12 +130,78 @@ class ORBmatcher:
         fv, keep = make_frame_view(kf.kps_un, kf.u_right, kf.desc, kf.bounds)
         queries = np.ascontiguousarray(queries, FUSE_QUERY_DTYPE)
         qd = np.ascontiguousarray(mp_desc, np.uint8)
-        s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        s2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
         bi = np.full(len(queries), -1, np.int32)
         bd = np.full(len(queries), 256, np.int32)
         self.ctx.check(_lib.lib().psl_match_fuse(self.ctx.handle, C.byref(fv), _ptr(queries), _ptr(qd), len(queries),
-                                                 _ptr(s2), len(s2), self.TH_LOW, _ptr(bi), _ptr(bd)))
+                                                 None if s2 is None else _ptr(s2), 1 if s2 is None else len(s2),
+                                                 self.TH_LOW, _ptr(bi), _ptr(bd)))
         return bi, bd
+
+    def FuseSearchSim3(self, kf: FrameData, queries, mp_desc):
+        """The window search of Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) — ORBmatcher.cc:1046-1075 (loop closing,
+        LoopClosing.cc:599): the pose form without the chi-square gate."""
+        return self.FuseSearch(FrameData(kf.kps_un, kf.desc, None, kf.bounds), queries, mp_desc, None)
+
+    def SearchByProjectionSim3(self, kf: FrameData, queries, mp_desc, matched):
+        """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) — ORBmatcher.cc:290-403 (LoopClosing.cc:375) after the
+        projection.  queries: psl_fuse_query records (u, v, radius = th * mvScaleFactors[pred], pred_level, PSL_Q_VALID);
+        matched[i] = vpMatched[i] != NULL.  Mode 0 of the projection matcher with the settings listed in the header.
+        Returns (assign [n] = query written into vpMatched[i] or -1, nmatches)."""
+        qf = np.ascontiguousarray(queries, FUSE_QUERY_DTYPE)
+        q = np.zeros(len(qf), QUERY_DTYPE)
+        q["u"], q["v"], q["radius"] = qf["u"], qf["v"], qf["radius"]
+        q["min_level"], q["max_level"] = qf["pred_level"] - 1, qf["pred_level"]
+        q["flags"] = np.where(qf["flags"] & Q_VALID, Q_VALID | Q_CLAIMS, 0).astype(np.uint32)
+        view = FrameData(kf.kps_un, kf.desc, None, kf.bounds)
+        return self._project(view, q, mp_desc, matched, 0, self.TH_LOW, self.mfNNratio, False)
+
+    def SearchByBoWKeyFrames(self, desc1, angle1, valid1, fv1, desc2, angle2, valid2, fv2):
+        """SearchByBoW(pKF1, pKF2, vpMatches12) — ORBmatcher.cc:522-655.  valid*: the keypoint holds a good MapPoint;
+        fv*: CSR FeatureVector.  Returns (matches12 [n1] = KF2 index or -1, nmatches)."""
+        desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+        angle1, angle2 = np.ascontiguousarray(angle1, np.float32), np.ascontiguousarray(angle2, np.float32)
+        valid1, valid2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+        a, k1 = make_feature_vector(*fv1)
+        b, k2 = make_feature_vector(*fv2)
+        m12 = np.full(len(desc1), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_match_bow_kf(self.ctx.handle, _ptr(desc1), _ptr(angle1), _ptr(valid1), len(desc1),
+                                                   C.byref(a), _ptr(desc2), _ptr(angle2), _ptr(valid2), len(desc2),
+                                                   C.byref(b), C.c_float(self.mfNNratio), self.TH_LOW,
+                                                   int(self.mbCheckOrientation), _ptr(m12), C.byref(nm)))
+        return m12, nm.value
+
+    def SearchBySim3(self, kf1: FrameData, kf2: FrameData, q12, mp_desc1, q21, mp_desc2):
+        """SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) — ORBmatcher.cc:1102-1326 after the projections
+        (one psl_fuse_query per keypoint of either keyframe).  Returns (matches12 [n1], nFound)."""
+        a, ka = make_frame_view(kf1.kps_un, None, kf1.desc, kf1.bounds)
+        b, kb = make_frame_view(kf2.kps_un, None, kf2.desc, kf2.bounds)
+        q12 = np.ascontiguousarray(q12, FUSE_QUERY_DTYPE)
+        q21 = np.ascontiguousarray(q21, FUSE_QUERY_DTYPE)
+        if len(q12) != a.n or len(q21) != b.n:
+            raise ValueError("SearchBySim3 takes one query per keypoint")
+        d1, d2 = np.ascontiguousarray(mp_desc1, np.uint8), np.ascontiguousarray(mp_desc2, np.uint8)
+        m12 = np.full(a.n, -1, np.int32)
+        nf = C.c_int32()
+        self.ctx.check(_lib.lib().psl_match_sim3(self.ctx.handle, C.byref(a), C.byref(b), _ptr(q12), _ptr(d1), _ptr(q21),
+                                                 _ptr(d2), self.TH_HIGH, _ptr(m12), C.byref(nf)))
+        return m12, nf.value
+
+    def SearchForInitialization(self, kps1_un, desc1, f2: FrameData, vbPrevMatched, windowSize=100):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) — ORBmatcher.cc:405-520.
+        Returns (vnMatches12 [n1], nmatches, vbPrevMatched after the update [n1, 2])."""
+        k1 = np.ascontiguousarray(kps1_un, _lib.KP_DTYPE)
+        d1 = np.ascontiguousarray(desc1, np.uint8)
+        pm = np.array(vbPrevMatched, np.float32, copy=True).reshape(-1, 2)
+        b, kb = make_frame_view(f2.kps_un, None, f2.desc, f2.bounds)
+        m12 = np.full(len(k1), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_match_initialization(self.ctx.handle, _ptr(k1), _ptr(d1), len(k1), _ptr(pm),
+                                                           C.byref(b), int(windowSize), C.c_float(self.mfNNratio),
+                                                           self.TH_LOW, int(self.mbCheckOrientation), _ptr(m12),
+                                                           C.byref(nm)))
+        return m12, nm.value, pm
 
 
 def hamming_knn2(ctx: Context, q: np.ndarray, t: np.ndarray):
