@@ -79,6 +79,11 @@ int orc_match_initialization(const psl_keypoint* kps1_un, const uint8_t* desc1, 
                              const psl_frame_view* f2, int window_size, float nn_ratio, int th_low,
                              int check_orientation, int32_t* matches12, int32_t* nmatches);
 
+/* ---- line junctions (orc_junction.cpp): PartiallyRecoverConnectivity.cpp:14-133, Frame.cc:380-472 ---- */
+int orc_line_junctions(const psl_keyline* kl_un, const double* lines3d, int n, int img_w, int img_h, float radius,
+                       float fan_thr, float* fans, psl_line_junction* junctions, int cap, int32_t* n_fans,
+                       int32_t* n_junctions);
+
 /* ---- Frame bookkeeping (orc_frame.cpp): Frame.cc:1342-1381, ORBmatcher.cc:1339-1393 ---- */
 /* Frame::UndistortKeyPoints / ComputeImageBounds (Frame.cc:1062-1092, 1135-1163) over cv::undistortPoints */
 void orc_undistort_keypoints(const psl_keypoint* kps, int n, const psl_distortion* cam, psl_keypoint* kps_un);

@@ -545,3 +545,17 @@ def line_search_triangulation(d1, ml1, d2, ml2, nn_ratio, th, is_double):
     n = lib().orc_line_search_triangulation(_p(d1), _p(ml1), len(d1), _p(d2), _p(ml2), len(d2), C.c_float(nn_ratio),
                                             C.c_float(th), int(is_double), _p(out))
     return out[: len(d1)].copy(), int(n)
+
+
+def line_junctions(kl_un, lines3d, img_w, img_h, radius=20.0, fan_thr=np.pi / 4, cap=4096):
+    """CPartiallyRecoverConnectivity + Frame::convertFansToKeyLines: (fans [m,4] f32, junctions [k] JUNCTION_DTYPE)."""
+    from psl_slam_b200._lib import JUNCTION_DTYPE
+    kl = np.ascontiguousarray(kl_un, KEYLINE_DTYPE)
+    l3 = None if lines3d is None else np.ascontiguousarray(lines3d, np.float64)
+    fans = np.zeros((cap, 4), np.float32)
+    js = np.zeros(cap, JUNCTION_DTYPE)
+    nf, nj = C.c_int32(), C.c_int32()
+    lib().orc_line_junctions(_p(kl), None if l3 is None else _p(l3), len(kl), int(img_w), int(img_h), C.c_float(radius),
+                             C.c_float(fan_thr), _p(fans), None if l3 is None else _p(js), cap, C.byref(nf), C.byref(nj))
+    assert nf.value <= cap
+    return fans[: nf.value].copy(), js[: nj.value].copy()

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|line|linematch|linefuse|undistort|planes|lines3d|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|undistort|planes|lines3d|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -577,6 +577,33 @@ def make_planes():
               f"(nan planes {int(np.isnan(pl).any(1).sum())})")
 
 
+def make_junctions():
+    """N2 fixture: the junction detection of Frame::ExtractLSD (CPartiallyRecoverConnectivity over the real cv2
+    primitives, oracle/pyref/junction_py.py) on the lines of the lines3d goldens; the 3-D cross points of
+    Frame::convertFansToKeyLines from numpy.linalg (tolerance check only: the reference solves with Eigen)."""
+    from oracle.pyref import junction_py
+    from psl_slam_b200._lib import JUNCTION_DTYPE
+    for case, (src, radius, thr) in enumerate([("lines3d_clean", 20.0, np.pi / 4), ("lines3d_noisy", 20.0, np.pi / 4),
+                                               ("lines3d_lowtex", 20.0, np.pi / 4), ("lines3d_holes", 35.0, np.pi / 6)]):
+        g = np.load(os.path.join(OUT, src + ".npz"))
+        kl, l3 = g["kl"], g["lines3d"]
+        L = np.stack([kl["start_x"], kl["start_y"], kl["end_x"], kl["end_y"]], 1).astype(np.float32)
+        fans, raw = junction_py.fans(L, radius, thr, 640, 480)
+        js = []
+        for f in fans:
+            i1, i2 = int(f[2]), int(f[3])
+            ok, X = junction_py.cross3d_numpy(l3[i1], l3[i2])
+            if ok and np.linalg.norm(X) > np.finfo(np.float64).eps:
+                j = np.zeros((), JUNCTION_DTYPE)
+                j["l1"], j["l2"], j["cross2d_x"], j["cross2d_y"], j["cross3d"] = i1, i2, f[0], f[1], X
+                js.append(j)
+        js = np.array(js, JUNCTION_DTYPE)
+        np.savez_compressed(os.path.join(OUT, f"junctions_case{case}.npz"), kl=kl, lines3d=l3, radius=np.float32(radius),
+                            fan_thr=np.float32(thr), size=np.array([640, 480], np.int32), fans=fans, fans_raw=raw,
+                            junctions=js)
+        print(f"junctions_case{case}: lines {len(kl)} raw fans {len(raw)} fans {len(fans)} junctions {len(js)}")
+
+
 def make_lines3d():
     """Frame::isLineGood: the lines of the linematch pairs over the sequence's depth (clean, noisy, noisy with holes);
     both SVDs are the real cv2.SVDecomp (oracle/pyref/line3d_py.py)."""
@@ -621,6 +648,7 @@ if __name__ == "__main__":
         make_fuse()
     if what in ("loop", "all"):
         make_loop()
+
     if what in ("line", "all"):
         make_line()
     if what in ("linematch", "all"):
@@ -633,3 +661,5 @@ if __name__ == "__main__":
         make_planes()
     if what in ("lines3d", "all"):
         make_lines3d()
+    if what in ("junctions", "all"):   # reads the lines3d fixtures
+        make_junctions()

@@ -137,3 +137,24 @@ def test_lines_3d(orc, name):
     l3z, eqz = orc.lines_3d(g["kl"], np.zeros_like(g["depth"]), *cam, 1)
     assert not l3z.any() and (eqz == -1).all()
     assert len(orc.lines_3d(g["kl"][:0], g["depth"], *cam, 1)[0]) == 0
+
+
+@pytest.mark.parametrize("name", golden_names("junctions_"))
+def test_line_junctions(orc, name):
+    """CPartiallyRecoverConnectivity (PartiallyRecoverConnectivity.cpp:14-133): the fans are bit-exact against the
+    restatement over the real cv2 primitives; the 3-D cross points of convertFansToKeyLines (Frame.cc:380-472) agree
+    with the independent numpy.linalg solution to 1e-9 (the reference solves the 2x2 system with Eigen's QR)."""
+    g = load_golden(name)
+    w, h = (int(v) for v in g["size"])
+    fans, js = orc.line_junctions(g["kl"], g["lines3d"], w, h, float(g["radius"]), float(g["fan_thr"]))
+    assert np.array_equal(fans, g["fans"]) and len(fans) > 20
+    want = g["junctions"]
+    assert len(js) == len(want)
+    for f in ("l1", "l2", "cross2d_x", "cross2d_y"):
+        assert np.array_equal(js[f], want[f]), f
+    assert np.allclose(js["cross3d"], want["cross3d"], rtol=1e-9, atol=1e-12)
+    # fans only (no 3-D lines), no lines, a tiny output capacity is reported through the counts
+    fans2, js2 = orc.line_junctions(g["kl"], None, w, h, float(g["radius"]), float(g["fan_thr"]))
+    assert np.array_equal(fans2, fans) and len(js2) == 0
+    fans3, js3 = orc.line_junctions(g["kl"][:0], g["lines3d"][:0], w, h)
+    assert len(fans3) == 0 and len(js3) == 0
