@@ -598,6 +598,30 @@ int psl_plane_hypotheses(psl_ctx* ctx, const psl_keyline* kl_un, const float* li
                          int32_t n_lines, const psl_line_junction* junctions, int32_t n_junctions, double* le_l,
                          float* planes, double* normals, int32_t* junction_of, int32_t cap, int32_t* n_planes);
 
+/* The junction detection of Frame::ExtractLSD (src/Frame.cc:504-507; SURVEY "next" row N2, the step between psl_lines_3d
+ * and psl_plane_hypotheses): CPartiallyRecoverConnectivity(mLines, expandWidth, fans, im, fanThr)
+ * (add_src/PartiallyRecoverConnectivity.cpp:14-133; radius = Frame::expandWidth = 20, fan_thr = Frame::fanThr = pi/4,
+ * include/Frame.h:217-218) followed by Frame::convertFansToKeyLines / Frame_shortestDistance (src/Frame.cc:380-472).
+ * kl_un: mvKeylinesUn (start / end points = Frame::keyLinesToMat); img_w / img_h: the image the lines come from.
+ * fans [cap*4] = the rows (x, y, i, j) of `fans` after the duplicate removal, in the reference's order (this is also
+ * LIL_gather: point + the two KeyLines i, j); *n_fans = their number (> cap: PSL_E_CAPACITY).
+ * junctions [cap] (may be NULL; needs lines3d = mvLines3D, n*6 doubles) = Frame::intersection_lines_plane, the fans
+ * whose two 3-D lines have a cross point (closest points of the two carrier lines, mid point; accepted if the mid-point
+ * test of :417-421 holds and |cross| > DBL_EPSILON), ready for psl_plane_hypotheses; *n_junctions = their number.
+ * Pinned: the cv::MatExpr of ptsDropInRotatedRect = one cv::addWeighted in double (cv2 4.13); the 2x2 system of
+ * Frame_shortestDistance follows Eigen's ColPivHouseholderQR step by step; the function's missing `return` (undefined
+ * behaviour when the mid-point test fails) reads "no cross point".  HOST pointers. */
+int psl_line_junctions(psl_ctx* ctx, const psl_keyline* kl_un, const double* lines3d, int32_t n, int32_t img_w,
+                       int32_t img_h, float radius, float fan_thr, float* fans, psl_line_junction* junctions,
+                       int32_t cap, int32_t* n_fans, int32_t* n_junctions);
+/* Batched, DEVICE pointers, asynchronous: frame b owns rows [b*line_cap, b*line_cap + d_n[b]) of d_kl / d_lines3d and
+ * rows [b*cap, ...) of d_fans / d_junctions; d_n_fans[b] / d_n_junctions[b] = the counts (a count above cap means the
+ * rows beyond cap were dropped).  d_lines3d and d_junctions are both NULL or both given. */
+int psl_line_junctions_dev(psl_ctx* ctx, const psl_keyline* d_kl, const int32_t* d_n, int32_t line_cap, int32_t B,
+                           const double* d_lines3d, int32_t img_w, int32_t img_h, float radius, float fan_thr,
+                           float* d_fans, psl_line_junction* d_junctions, int32_t cap, int32_t* d_n_fans,
+                           int32_t* d_n_junctions);
+
 #ifdef __cplusplus
 }
 #endif

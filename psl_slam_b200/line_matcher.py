@@ -183,6 +183,22 @@ def plane_hypotheses(ctx: Context, kl_un, line_eq, lines3d, junctions, cap: int 
     return le[:nj], pl[: n.value], nr[: n.value], ow[: n.value]
 
 
+def line_junctions(ctx: Context, kl_un, lines3d, img_w: int, img_h: int, radius: float = 20.0,
+                   fan_thr: float = float(np.float32(0.25 * np.pi)), cap: int = 4096):
+    """The junction detection of Frame::ExtractLSD (Frame.cc:504-507): CPartiallyRecoverConnectivity
+    (PartiallyRecoverConnectivity.cpp:14-133) + Frame::convertFansToKeyLines (Frame.cc:426-472).  lines3d = mvLines3D
+    [n,6] or None (fans only).  Returns (fans [m,4] f32 rows (x, y, i, j), intersection_lines_plane as JUNCTION_DTYPE)."""
+    kl = np.ascontiguousarray(kl_un, KEYLINE_DTYPE)
+    l3 = None if lines3d is None else np.ascontiguousarray(lines3d, np.float64).reshape(-1, 6)
+    fans = np.zeros((max(cap, 1), 4), np.float32)
+    js = np.zeros(max(cap, 1), JUNCTION_DTYPE)
+    nf, nj = C.c_int32(), C.c_int32()
+    ctx.check(_lib.lib().psl_line_junctions(ctx.handle, _ptr(kl), None if l3 is None else _ptr(l3), len(kl), int(img_w),
+                                            int(img_h), C.c_float(radius), C.c_float(fan_thr), _ptr(fans),
+                                            None if l3 is None else _ptr(js), cap, C.byref(nf), C.byref(nj)))
+    return fans[: nf.value], js[: nj.value]
+
+
 def lines_3d(ctx: Context, kl_un, depth_f32, fx, fy, cx, cy, seed: int = 0):
     """Frame::isLineGood (Frame.cc:662-750): (mvLines3D [n,6] f64, mvLineEq [n,3] f32) of the KeyLines from the CV_32F
     depth image; `seed` pins random_unique's rand() (see include/psl_frontend.h)."""

@@ -253,3 +253,67 @@ def test_lines_3d_vs_golden_and_oracle(orc, name):
         want = orc.lines_3d(klb[b, : ns[b]], np.ascontiguousarray(dep2[b, :, :w]), *cam, 5)
         assert np.array_equal(d_l3[b, : ns[b]].cpu().numpy(), want[0]) and np.array_equal(d_eq[b, : ns[b]].cpu().numpy(), want[1])
         assert (d_l3[b, ns[b]:].cpu().numpy() == 7.0).all()
+
+
+@pytest.mark.parametrize("name", golden_names("junctions_"))
+def test_line_junctions_vs_golden_and_oracle(orc, name):
+    """The junction detection of Frame::ExtractLSD (PartiallyRecoverConnectivity.cpp:14-133, Frame.cc:380-472): fans
+    bit-exact against the cv2-primitive golden; the junction records identical to the oracle's (same fp64 statements)
+    and within 1e-9 of the independent numpy.linalg cross points of the golden."""
+    import torch
+    from psl_slam_b200 import Context, PslError, default_config, line_junctions
+    from psl_slam_b200._lib import JUNCTION_DTYPE, KEYLINE_DTYPE, lib
+    g = load_golden(name)
+    ctx = Context(default_config())
+    w, h = (int(v) for v in g["size"])
+    r, t = float(g["radius"]), float(g["fan_thr"])
+    fans, js = line_junctions(ctx, g["kl"], g["lines3d"], w, h, r, t)
+    assert np.array_equal(fans, g["fans"])
+    ofans, ojs = orc.line_junctions(g["kl"], g["lines3d"], w, h, r, t)
+    assert np.array_equal(fans, ofans) and len(js) == len(ojs)
+    for f in ("l1", "l2", "cross2d_x", "cross2d_y", "cross3d"):
+        assert np.array_equal(js[f], ojs[f]), f
+    want = g["junctions"]
+    assert len(js) == len(want) and np.array_equal(js["l1"], want["l1"]) and np.array_equal(js["l2"], want["l2"])
+    assert np.allclose(js["cross3d"], want["cross3d"], rtol=1e-9, atol=1e-12)
+    # fans only; nothing; capacity
+    f2, j2 = line_junctions(ctx, g["kl"], None, w, h, r, t)
+    assert np.array_equal(f2, fans) and len(j2) == 0
+    f3, j3 = line_junctions(ctx, g["kl"][:0], g["lines3d"][:0], w, h, r, t)
+    assert len(f3) == 0 and len(j3) == 0
+    with pytest.raises(PslError):
+        line_junctions(ctx, g["kl"], g["lines3d"], w, h, r, t, cap=5)
+    # the chain isLineGood -> junctions -> plane hypotheses runs on the junction records as they are
+    from psl_slam_b200 import plane_hypotheses
+    eq = np.where(np.abs(g["lines3d"]).sum(1, keepdims=True) > 0,
+                  (g["lines3d"][:, 3:] - g["lines3d"][:, :3]) / np.maximum(
+                      np.linalg.norm(g["lines3d"][:, 3:] - g["lines3d"][:, :3], axis=1, keepdims=True), 1e-12),
+                  -1.0).astype(np.float32)
+    le, pl, nr, ow = plane_hypotheses(ctx, g["kl"], eq, g["lines3d"], js)
+    wle, wpl, wnr, wow = orc.plane_hypotheses(g["kl"], eq, g["lines3d"], js)
+    assert np.array_equal(pl, wpl, equal_nan=True) and np.array_equal(ow, wow)
+    # batched device form: three frames (the golden's lines, none, the first half) in one launch
+    n, cap, lc = len(g["kl"]), 512, len(g["kl"]) + 3
+    kl = np.zeros((3, lc), KEYLINE_DTYPE)
+    l3 = np.zeros((3, lc, 6))
+    kl[0, :n], l3[0, :n] = g["kl"], g["lines3d"]
+    kl[2, : n // 2], l3[2, : n // 2] = g["kl"][: n // 2], g["lines3d"][: n // 2]
+    d_kl = torch.from_numpy(kl.view(np.uint8).reshape(-1)).cuda()
+    d_l3 = torch.from_numpy(l3).cuda()
+    d_n = torch.tensor([n, 0, n // 2], dtype=torch.int32, device="cuda")
+    d_f = torch.zeros(3 * cap * 4, dtype=torch.float32, device="cuda")
+    d_j = torch.zeros(3 * cap * JUNCTION_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros(6, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.check(lib().psl_line_junctions_dev(ctx.handle, d_kl.data_ptr(), d_n.data_ptr(), lc, 3, d_l3.data_ptr(), w, h,
+                                           r, t, d_f.data_ptr(), d_j.data_ptr(), cap, d_c.data_ptr(),
+                                           d_c.data_ptr() + 12))
+    ctx.sync()
+    c = d_c.cpu().numpy()
+    bf = d_f.cpu().numpy().reshape(3, cap, 4)
+    bj = d_j.cpu().numpy().view(JUNCTION_DTYPE).reshape(3, cap)
+    assert c[0] == len(fans) and c[3] == len(js) and c[1] == 0 and c[4] == 0
+    assert np.array_equal(bf[0, : c[0]], fans) and np.array_equal(bj[0, : c[3]]["cross3d"], js["cross3d"])
+    hf, hj = orc.line_junctions(g["kl"][: n // 2], g["lines3d"][: n // 2], w, h, r, t)
+    assert c[2] == len(hf) and c[5] == len(hj) and np.array_equal(bf[2, : c[2]], hf)
+    assert np.array_equal(bj[2, : c[5]]["l1"], hj["l1"]) and np.array_equal(bj[2, : c[5]]["cross3d"], hj["cross3d"])
