@@ -133,9 +133,13 @@ class ORBmatcher:
         s2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
         bi = np.full(len(queries), -1, np.int32)
         bd = np.full(len(queries), 256, np.int32)
+        if s2 is not None:
+            nlevels = len(s2)
+        else:   # no table: nlevels only bounds the octaves
+            nlevels = int(kf.kps_un["octave"].max()) + 1 if fv.n else 1
         self.ctx.check(_lib.lib().psl_match_fuse(self.ctx.handle, C.byref(fv), _ptr(queries), _ptr(qd), len(queries),
-                                                 None if s2 is None else _ptr(s2), 1 if s2 is None else len(s2),
-                                                 self.TH_LOW, _ptr(bi), _ptr(bd)))
+                                                 None if s2 is None else _ptr(s2), nlevels, self.TH_LOW, _ptr(bi),
+                                                 _ptr(bd)))
         return bi, bd
 
     def FuseSearchSim3(self, kf: FrameData, queries, mp_desc):

@@ -290,7 +290,7 @@ def test_line_junctions_vs_golden_and_oracle(orc, name):
                       np.linalg.norm(g["lines3d"][:, 3:] - g["lines3d"][:, :3], axis=1, keepdims=True), 1e-12),
                   -1.0).astype(np.float32)
     le, pl, nr, ow = plane_hypotheses(ctx, g["kl"], eq, g["lines3d"], js)
-    wle, wpl, wnr, wow = orc.plane_hypotheses(g["kl"], eq, g["lines3d"], js)
+    wle, wpl, wnr, wow, _ = orc.plane_hypotheses(g["kl"], eq, g["lines3d"], js)
     assert np.array_equal(pl, wpl, equal_nan=True) and np.array_equal(ow, wow)
     # batched device form: three frames (the golden's lines, none, the first half) in one launch
     n, cap, lc = len(g["kl"]), 512, len(g["kl"]) + 3
