@@ -343,6 +343,23 @@ __device__ __forceinline__ Nbr load_nbr(const Frame& f, int first, int m, int n,
 //    prefix only feeds the certain / uncertain classification; the running sums themselves are then advanced
 //    by the accepted terms in lane order, i.e. with the reference's fp32 rounding.  Any other step replays the
 //    scalar loop.
+// thresholds of the quick alignment test for a precision `prec` (see region_grow)
+struct Quick {
+  bool quick;
+  float chi2, clo2;
+};
+
+__device__ __forceinline__ Quick make_quick(double prec) {
+  const double band = 0.5 * kDegToRad;
+  Quick q;
+  q.quick = prec + band < 1.5 && prec > band;   // both cosines positive: the test can be made on squares
+  const float chi = q.quick ? (float)cos(prec - band) : 2.f;   // dot >= chi * |sum|: aligned for sure
+  const float clo = q.quick ? (float)cos(prec + band) : 0.f;   // dot <= clo * |sum|: not aligned for sure
+  q.chi2 = chi * chi;
+  q.clo2 = clo * clo;
+  return q;
+}
+
 struct Grow {
   float sumdx, sumdy, s2;
   double reg_angle;
@@ -352,8 +369,10 @@ struct Grow {
 
 __device__ __forceinline__ void accept_terms(const Frame& f, Grow& g, const Nbr& cur, unsigned A, int lane) {
   if (g.n == 1) {  // first accept of the region: the exact seed terms (see region_grow)
-    g.sumdx = (float)cos(g.reg_angle);
-    g.sumdy = (float)sin(g.reg_angle);
+    double sd, cd;
+    sincos(g.reg_angle, &sd, &cd);   // one range reduction for both (same values as sin() / cos())
+    g.sumdx = (float)cd;
+    g.sumdy = (float)sd;
   }
   if (A >> lane & 1u) {
     const int at = g.n + __popc(A & ((1u << lane) - 1u));
@@ -397,7 +416,8 @@ __device__ void step_sequential(const Frame& f, Grow& g, Nbr& cur, double prec, 
   }
 }
 
-__device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_angle, double prec, int lane) {
+__device__ int region_grow(const Frame& f, int seed, int sx, int sy, float4 srec, double& reg_angle, double prec,
+                           const Quick qk, int lane) {
   const int W = f.W;
   Grow g;
   g.reg_angle = (double)srec.x * kDegToRad;
@@ -409,7 +429,6 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
   g.s2 = g.sumdx * g.sumdx + g.sumdy * g.sumdy;
   g.angle_valid = true;
   g.n = 1;
-  const int sy = seed / W, sx = seed - sy * W;
   const uint32_t c0 = ((uint32_t)sy << 16) | (uint32_t)sx;
   // four region points per step, eight lanes each: the centre of a 3x3 neighbourhood is the region point itself
   // (USED, never a candidate), so the loop's nine tests are the eight below in the same order
@@ -425,11 +444,8 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
     *flags_of(f, seed) = __float_as_int(srec.w) | lsdw_kUsed;
   }
   __syncwarp();
-  const double band = 0.5 * kDegToRad;
-  const bool quick = prec + band < 1.5 && prec > band;   // both cosines positive: the test can be made on squares
-  const float chi = quick ? (float)cos(prec - band) : 2.f;   // dot >= chi * |sum|: aligned for sure
-  const float clo = quick ? (float)cos(prec + band) : 0.f;   // dot <= clo * |sum|: not aligned for sure
-  const float chi2 = chi * chi, clo2 = clo * clo;
+  const bool quick = qk.quick;
+  const float chi2 = qk.chi2, clo2 = qk.clo2;
   const unsigned lt = (1u << lane) - 1u;
   // Software pipeline: the records of the next step's neighbours are requested as soon as the accepted set of
   // the current step is known (its region points are the next entries of the list), i.e. before the flag /
@@ -465,8 +481,10 @@ __device__ int region_grow(const Frame& f, int seed, float4 srec, double& reg_an
         // it, added in lane order with the reference's fp32 rounding (lane 31 ends with the sums after the step)
         float Px = g.sumdx, Py = g.sumdy;
         if (g.n == 1) {  // first accept of the region: the exact seed terms (see above)
-          Px = (float)cos(g.reg_angle);
-          Py = (float)sin(g.reg_angle);
+          double sd, cd;
+          sincos(g.reg_angle, &sd, &cd);
+          Px = (float)cd;
+          Py = (float)sd;
         }
         for (unsigned a = A; a; a &= a - 1) {
           const int j = __ffs(a) - 1;
@@ -600,7 +618,8 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
   double d = lsd::angle_diff_signed(theta, reg_angle);
   if (d < 0) d = -d;
   if (d > prec) theta += kPi;
-  const double dx = cos(theta), dy = sin(theta);
+  double dx, dy;
+  sincos(theta, &dy, &dx);
   // extents: `if (l > l_max) l_max = l; else if (l < l_min) l_min = l;` with both starting at 0 is an
   // independent max and min (a value above the running max is positive, so it cannot lower the min)
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
@@ -705,7 +724,7 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
   __syncwarp();
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(f, sy * f.W + sx, f.pix[sy * f.W + sx], reg_angle, tau, lane);
+  n = region_grow(f, sy * f.W + sx, sx, sy, f.pix[sy * f.W + sx], reg_angle, tau, make_quick(tau), lane);
   if (n < 2) return false;
   region2rect(f, n, reg_angle, prec, rec, lane);
   density = density_of(n, rec);
@@ -732,6 +751,8 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
   const int n_seeds = L.n_def[b];
   float* out = L.raw + (size_t)b * L.raw_cap * 4;
   const double prec = lsd::kPi * lsd::kAngTh / 180;
+  const lsdw::Quick qk = lsdw::make_quick(prec);
+  const float inv_w = 1.0f / (float)L.Ws;
   int nseg = 0;
   LSD_T0(t_all);
   for (int s0 = 0; s0 < n_seeds; s0 += 32) {
@@ -746,7 +767,11 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
       if (__float_as_int(srec.w) & lsdw_kUsed) continue;
       double reg_angle;
       LSD_T0(t_g);
-      int n = lsdw::region_grow(f, seed, srec, reg_angle, prec, lane);
+      // seed / W without the integer division: seed < 2^24 and W <= 4096, so the float quotient is off by at most one
+      int sy = (int)(((float)seed + 0.5f) * inv_w), sx = seed - sy * f.W;
+      if (sx < 0) { --sy; sx += f.W; }
+      else if (sx >= f.W) { ++sy; sx -= f.W; }
+      int n = lsdw::region_grow(f, seed, sx, sy, srec, reg_angle, prec, qk, lane);
       LSD_T1(10, t_g);
       LSD_STAT(13, 1);
       if (n < L.min_reg_size) continue;
