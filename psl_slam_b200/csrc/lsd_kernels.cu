@@ -416,9 +416,9 @@ __device__ void step_sequential(const Frame& f, Grow& g, Nbr& cur, double prec, 
   }
 }
 
+// reg_angle out is defined only for regions of at least min_n points (smaller ones are dropped by every caller)
 __device__ int region_grow(const Frame& f, int seed, int sx, int sy, float4 srec, double& reg_angle, double prec,
-                           const Quick qk, int lane) {
-  const int W = f.W;
+                           const Quick qk, int min_n, int lane) {
   Grow g;
   g.reg_angle = (double)srec.x * kDegToRad;
   // The reference seeds the sums with (float)cos(reg_angle) of the fp64 angle; that value only matters once a
@@ -549,7 +549,7 @@ __device__ int region_grow(const Frame& f, int seed, int sx, int sy, float4 srec
     }
     __syncwarp();
   }
-  if (!g.angle_valid) g.reg_angle = (double)lsd::fast_atan2(g.sumdy, g.sumdx) * kDegToRad;
+  if (!g.angle_valid && g.n >= min_n) g.reg_angle = (double)lsd::fast_atan2(g.sumdy, g.sumdx) * kDegToRad;
   reg_angle = g.reg_angle;
   __syncwarp();
   return g.n;
@@ -724,7 +724,7 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
   __syncwarp();
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(f, sy * f.W + sx, sx, sy, f.pix[sy * f.W + sx], reg_angle, tau, make_quick(tau), lane);
+  n = region_grow(f, sy * f.W + sx, sx, sy, f.pix[sy * f.W + sx], reg_angle, tau, make_quick(tau), 2, lane);
   if (n < 2) return false;
   region2rect(f, n, reg_angle, prec, rec, lane);
   density = density_of(n, rec);
@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
       int sy = (int)(((float)seed + 0.5f) * inv_w), sx = seed - sy * f.W;
       if (sx < 0) { --sy; sx += f.W; }
       else if (sx >= f.W) { ++sy; sx -= f.W; }
-      int n = lsdw::region_grow(f, seed, sx, sy, srec, reg_angle, prec, qk, lane);
+      int n = lsdw::region_grow(f, seed, sx, sy, srec, reg_angle, prec, qk, L.min_reg_size, lane);
       LSD_T1(10, t_g);
       LSD_STAT(13, 1);
       if (n < L.min_reg_size) continue;
@@ -795,6 +795,9 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
     }
   }
   LSD_T1(14, t_all);
+#ifdef PSL_LSD_STATS
+  if (lane == 0) atomicMax(&g_lsd_stats[15], (unsigned long long)(clock64() - t_all));   // slowest frame of the launch
+#endif
   if (lane == 0) {
     L.n_raw[b] = nseg < L.raw_cap ? nseg : L.raw_cap;
     if (nseg > L.raw_cap) atomicOr(status, kStatLineRaw);
