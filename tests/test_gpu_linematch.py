@@ -317,3 +317,34 @@ def test_line_junctions_vs_golden_and_oracle(orc, name):
     hf, hj = orc.line_junctions(g["kl"][: n // 2], g["lines3d"][: n // 2], w, h, r, t)
     assert c[2] == len(hf) and c[5] == len(hj) and np.array_equal(bf[2, : c[2]], hf)
     assert np.array_equal(bj[2, : c[5]]["l1"], hj["l1"]) and np.array_equal(bj[2, : c[5]]["cross3d"], hj["cross3d"])
+
+
+def test_line_junctions_random_large(orc):
+    """1100 random segments (more than 48 KB of per-frame line state in shared memory), with zero-length, vertical,
+    horizontal and duplicated segments, and 3-D lines that are parallel / identical / missing: against the oracle."""
+    from psl_slam_b200 import Context, default_config, line_junctions
+    from psl_slam_b200._lib import KEYLINE_DTYPE
+    rng = np.random.default_rng(77)
+    n = 1100
+    kl = np.zeros(n, KEYLINE_DTYPE)
+    c = rng.uniform([20, 20], [1900, 1060], (n, 2))
+    d = rng.normal(0, 60, (n, 2))
+    kl["start_x"], kl["start_y"] = (c - d)[:, 0], (c - d)[:, 1]
+    kl["end_x"], kl["end_y"] = (c + d)[:, 0], (c + d)[:, 1]
+    kl["end_x"][:20] = kl["start_x"][:20]                       # vertical
+    kl["end_y"][20:40] = kl["start_y"][20:40]                   # horizontal
+    kl["end_x"][40:50], kl["end_y"][40:50] = kl["start_x"][40:50], kl["start_y"][40:50]   # zero length
+    kl[50:60] = kl[60:70]                                       # duplicates
+    for f in ("start_x", "start_y", "end_x", "end_y"):
+        kl[f][100:200] = np.round(kl[f][100:200])               # integer coordinates: exact ties on the rectangle tests
+    l3 = rng.normal(0, 1, (n, 6)) + np.array([0, 0, 3, 0, 0, 3])
+    l3[:100] = 0                                                # no 3-D line
+    l3[100:150, 3:] = l3[100:150, :3] + (l3[150:200, 3:] - l3[150:200, :3])   # parallel to another line
+    l3[200:210] = l3[210:220]                                   # identical
+    ctx = Context(default_config())
+    fans, js = line_junctions(ctx, kl, l3, 1920, 1080, 20.0, float(np.float32(np.pi / 4)), cap=20000)
+    wf, wj = orc.line_junctions(kl, l3, 1920, 1080, 20.0, float(np.float32(np.pi / 4)), cap=20000)
+    assert len(fans) == len(wf) and len(fans) > 500
+    assert np.array_equal(fans, wf, equal_nan=True)
+    assert len(js) == len(wj) and np.array_equal(js["l1"], wj["l1"]) and np.array_equal(js["l2"], wj["l2"])
+    assert np.array_equal(js["cross3d"], wj["cross3d"])

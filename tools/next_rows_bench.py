@@ -102,6 +102,44 @@ def main():
         "gpu_ms_per_call": call_time(lambda: om.SearchByProjectionKeyFrame(cur, gr["queries"], gr["desc_kf"], gr["held"], 100)),
         "cpu_oracle_ms_per_call": cpu_time(lambda: orc.match_projection(gr["kps_cur"], None, gr["desc_cur"], tuple(gr["bounds"]), q,
                                                                         gr["desc_kf"], gr["held"], 0, 100, 0.9, True))}
+    # --- N2: junction detection, 1024 frames x 124 lines, device resident ---------------------------------------------
+    from psl_slam_b200._lib import JUNCTION_DTYPE
+    gj = load_golden("junctions_case1")
+    klj, l3j = np.ascontiguousarray(gj["kl"], KEYLINE_DTYPE), np.ascontiguousarray(gj["lines3d"], np.float64)
+    nj, capj = len(klj), 512
+    d_klj = torch.from_numpy(np.tile(klj.view(np.uint8).reshape(1, nj, 68), (B, 1, 1))).cuda()
+    d_l3j = torch.from_numpy(np.tile(l3j.reshape(1, nj, 6), (B, 1, 1))).cuda()
+    d_nj = torch.full((B,), nj, dtype=torch.int32, device="cuda")
+    d_f = torch.zeros((B, capj, 4), dtype=torch.float32, device="cuda")
+    d_j = torch.zeros((B, capj * JUNCTION_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros((2, B), dtype=torch.int32, device="cuda")
+    ms = ev_time(lambda: ctx.check(L.psl_line_junctions_dev(ctx.handle, d_klj.data_ptr(), d_nj.data_ptr(), nj, B, d_l3j.data_ptr(),
+                                                             640, 480, C.c_float(20.0), C.c_float(float(gj["fan_thr"])),
+                                                             d_f.data_ptr(), d_j.data_ptr(), capj, d_c.data_ptr(),
+                                                             d_c.data_ptr() + 4 * B)))
+    cpu = cpu_time(lambda: orc.line_junctions(klj, l3j, 640, 480, 20.0, float(gj["fan_thr"])))
+    out["line_junctions (CPartiallyRecoverConnectivity + cross points), 124 lines/frame"] = {
+        "gpu_us_per_frame": ms * 1e3 / B, "cpu_oracle_us_per_frame_1thread": cpu * 1e3}
+
+    # --- N1, second batch: loop-closing / initialisation matchers, single pair, host pointers ---------------------------
+    gl = load_golden("loop_pair0")
+    bnd = tuple(gl["bounds"])
+    k1, k2 = FrameData(gl["kps1"], gl["desc1"], None, bnd), FrameData(gl["kps2"], gl["desc2"], None, bnd)
+    c1, c2 = (gl["nodes1"], gl["offs1"], gl["idx1"]), (gl["nodes2"], gl["offs2"], gl["idx2"])
+    a1, a2 = gl["kps1"]["angle"], gl["kps2"]["angle"]
+    mb = ORBmatcher(0.75, True)
+    out["SearchByBoW(KF, KF), 1006 x 1008 kps"] = {
+        "gpu_ms_per_call": call_time(lambda: mb.SearchByBoWKeyFrames(gl["desc1"], a1, gl["valid1"], c1, gl["desc2"], a2, gl["valid2"], c2)),
+        "cpu_oracle_ms_per_call": cpu_time(lambda: orc.match_bow_kf(gl["desc1"], a1, gl["valid1"], c1, gl["desc2"], a2, gl["valid2"], c2))}
+    out["SearchBySim3, 1006 + 1008 queries"] = {
+        "gpu_ms_per_call": call_time(lambda: mb.SearchBySim3(k1, k2, gl["q12"], gl["desc1"], gl["q21"], gl["desc2"])),
+        "cpu_oracle_ms_per_call": cpu_time(lambda: orc.match_sim3((gl["kps1"], gl["desc1"]), (gl["kps2"], gl["desc2"]), bnd,
+                                                                  gl["q12"], gl["desc1"], gl["q21"], gl["desc2"], 100))}
+    mi = ORBmatcher(0.9, True)
+    out["SearchForInitialization, window 100"] = {
+        "gpu_ms_per_call": call_time(lambda: mi.SearchForInitialization(gl["kps1"], gl["desc1"], k2, gl["prev_matched"], 100)),
+        "cpu_oracle_ms_per_call": cpu_time(lambda: orc.match_initialization(gl["kps1"], gl["desc1"], gl["prev_matched"],
+                                                                            (gl["kps2"], gl["desc2"]), bnd, 100, 0.9, 50, True))}
     print(json.dumps(out, indent=1))
 
 
