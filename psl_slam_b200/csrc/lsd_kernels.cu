@@ -740,11 +740,15 @@ constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never 
 #define PSL_LSD_MINB 7
 #endif
 __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
-    lsd_core_kernel(LineBuffers L, int nb, uint32_t* __restrict__ status) {
+    lsd_core_kernel(LineBuffers L, int nb, uint32_t stride, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
   __shared__ double terms[kCoreWarps][96];
-  const int wid = threadIdx.x >> 5, b = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
-  if (b >= nb) return;
+  const int wid = threadIdx.x >> 5, slot = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
+  if (slot >= nb) return;
+  // frame of this warp: a fixed permutation of the batch (stride coprime to nb), so that the warps of one SM hold
+  // frames from all over the sequence — neighbouring frames cost about the same, and an SM that got only expensive
+  // ones would finish last
+  const int b = (int)(((uint64_t)slot * stride) % (uint32_t)nb);
   const size_t npx = (size_t)L.Ws * L.Hs;
   lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.reg + b * npx, ring[wid], terms[wid]};
   const uint32_t* seeds = L.val_out + b * npx;
@@ -857,7 +861,11 @@ void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st) {
 }
 
 void launch_lsd_core(const LineBuffers& L, int nb, uint32_t* status, cudaStream_t st) {
-  lsd_core_kernel<<<(nb + kCoreWarps - 1) / kCoreWarps, kCoreWarps * 32, 0, st>>>(L, nb, status);
+  auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+  uint32_t stride = (uint32_t)(0.6180339887 * nb) | 1u;   // golden-ratio stride, made coprime to nb
+  while (stride > 1 && gcd(stride, (uint32_t)nb) != 1) stride += 2;
+  if (nb < 3) stride = 1;
+  lsd_core_kernel<<<(nb + kCoreWarps - 1) / kCoreWarps, kCoreWarps * 32, 0, st>>>(L, nb, stride, status);
 }
 
 }  // namespace psl
