@@ -511,21 +511,19 @@ __device__ int region_grow(const Frame& f, int seed, int sx, int sy, float4 srec
     if (batched) {
       const int n_old = g.n, n_new = n_old + __popc(A);
       if (i >= n_new) break;      // the list is exhausted (A is empty here)
-      // region points i .. i+2: from the list while they exist, else the lanes of A in order
-      const int m2 = min(4, n_new - i), idx = i + p;
+      // the accepted points go to the shared mirror of the list first: the region points i .. i+3 of the next step
+      // are then read from it whether they are old entries or were accepted just now
+      const int at = n_old + __popc(A & lt);
+      if (A >> lane & 1u) f.ring[at & (kRing - 1)] = cur.npk;
+      __syncwarp();
+      const int m2 = min(4, n_new - i);
       uint32_t c = 0;
-      const unsigned A1 = A & (A - 1), A2 = A1 & (A1 - 1), A3 = A2 & (A2 - 1);
-      const int r = idx - n_old;  // >= 0: the r-th accepted lane of this step
-      const int src = r <= 0 ? __ffs(A) - 1 : (r == 1 ? __ffs(A1) - 1 : (r == 2 ? __ffs(A2) - 1 : __ffs(A3) - 1));
-      const uint32_t fromA = __shfl_sync(kFull, cur.npk, src < 0 ? 0 : src);
-      if (p < m2) c = idx < n_old ? reg_at(f, idx, n_old) : fromA;
+      if (p < m2) c = reg_at(f, i + p, n_new);
       Nbr nxt = load_nbr_at(f, p < m2, c, ox, oy);
       if (A) {
         if (A >> lane & 1u) {
-          const int at = n_old + __popc(A & lt);
           *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
           f.reg[at] = cur.npk;
-          f.ring[at & (kRing - 1)] = cur.npk;
         }
         for (unsigned a = A; a; a &= a - 1) {  // records loaded before these flag stores: strike what just became USED
           const int aidx = __shfl_sync(kFull, cur.nidx, __ffs(a) - 1);
