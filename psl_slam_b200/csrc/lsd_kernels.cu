@@ -303,7 +303,9 @@ __device__ __forceinline__ Nbr load_nbr_at(const Frame& f, bool active, uint32_t
   Nbr b{-1, 0u, make_float4(kNotDefDeg, 0.f, 0.f, 0.f), false};
   if (active) {
     const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
-    if (xx >= 0 && xx < f.W && yy >= 0 && yy < f.H) {
+    // a region point has a defined angle, so it is not in the last row / column (ll_angle leaves them NOTDEF):
+    // its neighbours can only leave the image at the top / left
+    if ((xx | yy) >= 0) {
       b.nidx = yy * f.W + xx;
       b.npk = ((uint32_t)yy << 16) | (uint32_t)xx;
       b.rec = f.pix[b.nidx];
@@ -560,8 +562,10 @@ __device__ __forceinline__ double modgrad(const Frame& f, int idx) {
 }
 
 __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec, Rect& rec, int lane) {
-  // weighted centroid: x += px * w ... in list order
-  double x = 0, y = 0, sum = 0;
+  // weighted centroid: x += px * w ... in list order.  The three running sums are independent chains: lane 0, 1 and 2
+  // each add one of them (one load + one add per term for the warp instead of three of each).
+  const double* chain = f.terms + 32 * (lane < 3 ? lane : 0);
+  double acc = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     double tx = 0, ty = 0, w = 0;
@@ -578,16 +582,14 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
     __syncwarp();
     f.terms[lane] = tx; f.terms[32 + lane] = ty; f.terms[64 + lane] = w;
     __syncwarp();
-    for (int k = 0; k < cnt; ++k) {
-      x += f.terms[k];
-      y += f.terms[32 + k];
-      sum += f.terms[64 + k];
-    }
+    for (int k = 0; k < cnt; ++k) acc += chain[k];
   }
+  double x = shfl_d(acc, 0), y = shfl_d(acc, 1);
+  const double sum = shfl_d(acc, 2);
   x /= sum;
   y /= sum;
   // get_theta: inertia matrix in list order
-  double Ixx = 0, Iyy = 0, Ixy = 0;
+  acc = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     double t1 = 0, t2 = 0, t3 = 0;
@@ -597,18 +599,15 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
       const double w = modgrad(f, py * f.W + px), dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * w;
       t2 = dx * dx * w;
-      t3 = dx * dy * w;
+      t3 = -(dx * dy * w);   // Ixy -= term  ==  Ixy += -term
     }
     const int cnt = min(32, n - base);
     __syncwarp();
     f.terms[lane] = t1; f.terms[32 + lane] = t2; f.terms[64 + lane] = t3;
     __syncwarp();
-    for (int k = 0; k < cnt; ++k) {
-      Ixx += f.terms[k];
-      Iyy += f.terms[32 + k];
-      Ixy -= f.terms[64 + k];
-    }
+    for (int k = 0; k < cnt; ++k) acc += chain[k];
   }
+  const double Ixx = shfl_d(acc, 0), Iyy = shfl_d(acc, 1), Ixy = shfl_d(acc, 2);
   const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
   double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lsd::fast_atan2((float)(lambda - Ixx), (float)Ixy)
                                          : (double)lsd::fast_atan2((float)Ixy, (float)(lambda - Iyy));
@@ -692,7 +691,8 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
   const uint32_t c0 = f.reg[0];
   const int sx = (int)(c0 & 0xFFFFu), sy = (int)(c0 >> 16);
   const double xc = (double)sx, yc = (double)sy, ang_c = (double)f.pix[sy * f.W + sx].x * kDegToRad;
-  double sum = 0, s_sum = 0;
+  const double* chain = f.terms + 32 * (lane < 2 ? lane : 0);   // lane 0: sum, lane 1: s_sum (see region2rect)
+  double acc = 0;
   int cnt = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
@@ -714,12 +714,10 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
     __syncwarp();
     f.terms[lane] = a; f.terms[32 + lane] = a2;
     __syncwarp();
-    for (int k = 0; k < c32; ++k) {
-      sum += f.terms[k];
-      s_sum += f.terms[32 + k];
-    }
+    for (int k = 0; k < c32; ++k) acc += chain[k];
   }
   __syncwarp();
+  const double sum = shfl_d(acc, 0), s_sum = shfl_d(acc, 1);
   const double mean_angle = sum / (double)cnt;
   const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
   n = region_grow(f, sy * f.W + sx, sx, sy, f.pix[sy * f.W + sx], reg_angle, tau, make_quick(tau), 2, lane);
