@@ -53,6 +53,8 @@ struct MergeScratch {
   uint8_t* flag;     // [cap] frontier bitmap / `clustered`
   int overflow;      // set when a neighbour list overflows
   float* sangles;    // [cap] angles in scan order (warp-cooperative kernel only)
+  uint16_t* fw;      // [cap][kNbCap] a row's own partners (warp-cooperative kernel only)
+  double* den;       // [cap] sqrt(a^2 + b^2) of PointLineDistance per line, scan order (warp-cooperative kernel only)
 };
 
 PSL_LN_HD float point_line_distance(const Seg& l, float x0, float y0) {  // uselongline.cpp:5-15

@@ -70,6 +70,14 @@ __device__ void rank_sort(const uint16_t* idx, uint16_t* out, int n, const float
   __syncwarp();
 }
 
+// line::point_line_distance with the line's denominator sqrt(a^2 + b^2) taken from the per-line table
+__device__ __forceinline__ float pld_den(const Seg& l, double den, float x0, float y0) {
+  const float x1 = l.v[0], y1 = l.v[1], x2 = l.v[2], y2 = l.v[3];
+  const float num = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(y2, y1), x0), __fmul_rn(__fsub_rn(x1, x2), y0)),
+                                    __fsub_rn(__fmul_rn(x2, y1), __fmul_rn(x1, y2))));
+  return (float)((double)num / den);
+}
+
 __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, float distance_thr, float endpoint_threshold,
                            MergeScratch& S, int lane) {
   if (n <= 0) return 0;
@@ -89,84 +97,107 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   Seg* sseg = dst;
   for (int j = lane; j < n; j += 32) {
     const int id = S.order[j];
-    sseg[j] = src[id];
+    const Seg sj = src[id];
+    sseg[j] = sj;
     S.sangles[j] = S.angles[id];
+    // the denominator of PointLineDistance (uselongline.cpp:5-15) depends on the line only
+    const double a = (double)__fsub_rn(sj.v[3], sj.v[1]), b = (double)__fsub_rn(sj.v[0], sj.v[2]);
+    S.den[j] = sqrt(a * a + b * b);
   }
   __syncwarp();
   POST_T1(0, t_sort);
   POST_T0(t_scan);
+  // Pair scan (:75-150).  The scalar loop walks the rows i in angle order and, for each, its partners j > i up to
+  // the first one whose angle gap is too large; every accepted pair appends each line to the other's neighbour list.
+  // Row i's list therefore ends up as: the rows before i that accepted i (ascending), then i's own partners
+  // (ascending) — i.e. all its neighbours in angle order, whatever the order of evaluation.  So the rows are
+  // independent: one row per lane (32 rows at a time, coalesced loads of the sorted copies, every lane busy with
+  // a partner that is inside its window), own partners into a forward list, the other side counted with an atomic
+  // and put in order afterwards.
   const float ep_thr = __fmul_rn(endpoint_threshold, endpoint_threshold);
   const float quater_PI = (float)(line::kPi / 4.0);
-  for (int i = 0; i < n; ++i) {
-    const int idx1 = S.order[i];
-    const Seg s1 = sseg[i];
-    float x11 = s1.v[0], y11 = s1.v[1], x12 = s1.v[2], y12 = s1.v[3];
-    const float angle1 = S.sangles[i];
-    const bool sx = fabsf(angle1) < quater_PI;
-    if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
-    const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
-    const float mx1 = (float)(0.5 * (double)__fadd_rn(s1.v[0], s1.v[2])), my1 = (float)(0.5 * (double)__fadd_rn(s1.v[1], s1.v[3]));
-    int cnt1 = S.nb_cnt[idx1];
-    for (int j0 = i + 1; j0 < n; j0 += 32) {
-      const int j = j0 + lane;
-      bool far = false, to_merge = false;
-      int idx2 = 0;
-      if (j < n) {
+  int* bcnt = reinterpret_cast<int*>(S.angles);   // the unsorted angles are dead from here on
+  for (int j = lane; j < n; j += 32) {
+    bcnt[j] = 0;
+    S.loc[S.order[j]] = (uint16_t)j;              // rank of a line in the angle order
+  }
+  __syncwarp();
+  int ovf = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    if (i < n) {
+      const int idx1 = S.order[i];
+      const Seg s1 = sseg[i];
+      float x11 = s1.v[0], y11 = s1.v[1], x12 = s1.v[2], y12 = s1.v[3];
+      const float angle1 = S.sangles[i];
+      const bool sx = fabsf(angle1) < quater_PI;
+      if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
+      const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
+      const float mx1 = (float)(0.5 * (double)__fadd_rn(s1.v[0], s1.v[2])), my1 = (float)(0.5 * (double)__fadd_rn(s1.v[1], s1.v[3]));
+      const double den1 = S.den[i];
+      int fc = 0;
+      for (int j = i + 1; j < n; ++j) {
+        if (line::angle_diff(angle1, S.sangles[j]) > angle_thr) {
+          if (can_break) break;   // the scalar loop stops at the first partner whose angle gap is too large
+          // A near-vertical segment `continue`s past such partners instead.  In the angle-sorted order they form one
+          // contiguous run: |a2 - a1| grows with j, pi + a1 - a2 (the wrap-around branch of AngleDiff) shrinks, so
+          // only the partners right after i and the ones at the far end of the list (the other vertical direction)
+          // can pass.  Skip the run: first j whose gap is small again, by bisection on the same fp32 predicate.
+          int lo = j + 1, hi = n;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (line::angle_diff(angle1, S.sangles[mid]) > angle_thr) lo = mid + 1;
+            else hi = mid;
+          }
+          j = lo - 1;  // the loop increment brings it to lo
+          continue;
+        }
         const Seg s2 = sseg[j];
         float x21 = s2.v[0], y21 = s2.v[1], x22 = s2.v[2], y22 = s2.v[3];
         if ((sx && (x22 < x21)) || ((!sx) && y22 < y21)) { float t = x21; x21 = x22; x22 = t; t = y21; y21 = y22; y22 = t; }
-        far = line::angle_diff(angle1, S.sangles[j]) > angle_thr;
-        if (!far) {
-          const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
-          if (!(line::point_line_distance(s2, mx1, my1) > distance_thr && line::point_line_distance(s1, mx2, my2) > distance_thr)) {
-            float cx12, cy12, cx21, cy21;
-            if ((sx && x12 > x22) || (!sx && y12 > y22)) { cx12 = x22; cy12 = y22; cx21 = x11; cy21 = y11; }
-            else { cx12 = x12; cy12 = y12; cx21 = x21; cy21 = y21; }
-            to_merge = ((sx && cx12 >= cx21) || (!sx && cy12 >= cy21));
-            if (!to_merge) {
-              const float ex = __fsub_rn(cx21, cx12), ey = __fsub_rn(cy21, cy12);
-              to_merge = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < ep_thr;
-            }
-          }
+        const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
+        if (pld_den(s2, S.den[j], mx1, my1) > distance_thr && pld_den(s1, den1, mx2, my2) > distance_thr) continue;
+        float cx12, cy12, cx21, cy21;
+        if ((sx && x12 > x22) || (!sx && y12 > y22)) { cx12 = x22; cy12 = y22; cx21 = x11; cy21 = y11; }
+        else { cx12 = x12; cy12 = y12; cx21 = x21; cy21 = y21; }
+        bool to_merge = ((sx && cx12 >= cx21) || (!sx && cy12 >= cy21));
+        if (!to_merge) {
+          const float ex = __fsub_rn(cx21, cx12), ey = __fsub_rn(cy21, cy12);
+          to_merge = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < ep_thr;
         }
-      }
-      // the scalar loop stops at the first partner whose angle gap is too large (unless near-vertical)
-      const unsigned brk = can_break ? __ballot_sync(kFull, far) : 0u;
-      const unsigned live = brk ? ((1u << (__ffs(brk) - 1)) - 1u) : kFull;
-      const unsigned mm = __ballot_sync(kFull, to_merge) & live;
-      if (mm >> lane & 1u) {
-        idx2 = S.order[j];
-        const int pos = cnt1 + __popc(mm & ((1u << lane) - 1u));
-        const int c2 = S.nb_cnt[idx2];
-        if (pos < kNbCap && c2 < kNbCap) {
-          S.nb[idx1 * kNbCap + pos] = (uint16_t)idx2;
-          S.nb[idx2 * kNbCap + c2] = (uint16_t)idx1;
-          S.nb_cnt[idx2] = (uint16_t)(c2 + 1);
+        if (!to_merge) continue;
+        const int idx2 = S.order[j];
+        const int b = atomicAdd(&bcnt[idx2], 1);   // slot in idx2's list of earlier rows (unordered until the pass below)
+        if (fc < kNbCap && b < kNbCap) {
+          S.fw[idx1 * kNbCap + fc] = (uint16_t)idx2;
+          S.nb[idx2 * kNbCap + b] = (uint16_t)idx1;
         } else {
-          S.overflow = 1;
+          ovf = 1;
         }
+        ++fc;
       }
-      cnt1 = min(cnt1 + __popc(mm), kNbCap);
-      __syncwarp();
-      if (brk) break;
-      if (!can_break && __any_sync(kFull, far)) {
-        // A near-vertical segment `continue`s past partners whose angle gap is too large instead of stopping.
-        // In the angle-sorted order those form one contiguous run: |a2 - a1| grows with j, pi + a1 - a2 (the
-        // wrap-around branch of AngleDiff) shrinks, so only the partners right after i and the ones at the far
-        // end of the list (the other vertical direction) can pass.  Skip the run: first j past this batch whose
-        // gap is small again, found by bisection on the same fp32 predicate.
-        int lo = min(j0 + 32, n), hi = n;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (line::angle_diff(angle1, S.sangles[mid]) > angle_thr) lo = mid + 1;
-          else hi = mid;
-        }
-        j0 = lo - 32;  // the loop increment brings it to lo
-      }
+      S.nb_cnt[idx1] = (uint16_t)min(fc, kNbCap);
     }
-    if (lane == 0) S.nb_cnt[idx1] = (uint16_t)cnt1;
-    __syncwarp();
   }
+  __syncwarp();
+  // neighbour list of a line = the earlier rows that accepted it, in angle order, then its own partners
+  for (int x = lane; x < n; x += 32) {
+    const int bc = min(bcnt[x], kNbCap), fc = S.nb_cnt[x];
+    uint16_t* nbx = S.nb + x * kNbCap;
+    for (int a = 1; a < bc; ++a) {   // insertion sort by rank (the lists hold a handful of entries)
+      const uint16_t v = nbx[a];
+      const uint16_t rv = S.loc[v];
+      int c = a - 1;
+      while (c >= 0 && S.loc[nbx[c]] > rv) { nbx[c + 1] = nbx[c]; --c; }
+      nbx[c + 1] = v;
+    }
+    int tot = bc + fc;
+    if (tot > kNbCap) { ovf = 1; tot = kNbCap; }
+    for (int k = 0; bc + k < tot; ++k) nbx[bc + k] = S.fw[x * kNbCap + k];
+    S.nb_cnt[x] = (uint16_t)tot;
+  }
+  if (ovf) S.overflow = 1;
+  __syncwarp();
   S.overflow = __any_sync(kFull, S.overflow) ? 1 : 0;
   POST_T1(1, t_scan);
   POST_T0(t_bfs);
@@ -290,14 +321,15 @@ __device__ int frame_lines(Seg* raw, int n_raw, Seg* t1, Seg* t2, int w, int h, 
 
 constexpr int kPostWarps = 4;  // frames per CTA (one per warp)
 
-__global__ void __launch_bounds__(kPostWarps * 32)
+__global__ void __launch_bounds__(kPostWarps * 32, 8)
     line_post_kernel(LineBuffers L, int nb, int nfeatures, psl_keyline* __restrict__ kl, double* __restrict__ lineeq,
                      int cap, int32_t* __restrict__ n_out, uint32_t* __restrict__ status) {
   const int b = blockIdx.x * kPostWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= nb) return;
   const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
   line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
-                       L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o};
+                       L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o,
+                       L.m_fw + o * line::kNbCap, L.m_den + o};
   line::Seg* raw = reinterpret_cast<line::Seg*>(L.raw) + o;
   POST_T0(t_all);
   const int n = linew::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,
