@@ -55,6 +55,7 @@ struct MergeScratch {
   float* sangles;    // [cap] angles in scan order (warp-cooperative kernel only)
   uint16_t* fw;      // [cap][kNbCap] a row's own partners (warp-cooperative kernel only)
   double* den;       // [cap] sqrt(a^2 + b^2) of PointLineDistance per line, scan order (warp-cooperative kernel only)
+  uint32_t* sort_cnt;  // bucket counters of the rank sort, shared memory (warp-cooperative kernel only)
 };
 
 PSL_LN_HD float point_line_distance(const Seg& l, float x0, float y0) {  // uselongline.cpp:5-15

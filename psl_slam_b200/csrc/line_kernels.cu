@@ -45,8 +45,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // stable rank sort of 0..n-1 by key ascending (desc = false) or descending; out[rank] = index.  Every caller sorts
 // the identity permutation, so the keys are read in place, four per load (the same address for all lanes: one
 // broadcast transaction); an element's rank = the keys that come before it + the equal ones with a smaller index.
-__device__ void rank_sort(const uint16_t* idx, uint16_t* out, int n, const float* key, bool desc, int lane) {
-  (void)idx;
+__device__ void rank_sort_quadratic(uint16_t* out, int n, const float* key, bool desc, int lane) {
   const bool vec = (reinterpret_cast<uintptr_t>(key) & 15) == 0;
   for (int a = lane; a < n; a += 32) {
     const float ka = key[a];
@@ -65,6 +64,77 @@ __device__ void rank_sort(const uint16_t* idx, uint16_t* out, int n, const float
         count(k4.w, b + 3);
       }
     for (; b < n; ++b) count(key[b], b);
+    out[r] = (uint16_t)a;
+  }
+  __syncwarp();
+}
+
+constexpr int kSortBuckets = 1024;
+
+// The same ranks through a monotone bucketing of the keys: an element's rank = the elements in earlier buckets + the
+// members of its own bucket that sort before it, so the quadratic part runs inside a bucket only.  cnt: kSortBuckets
+// counters of this warp in shared memory; bkt / members: u16 [n] scratch.
+__device__ void rank_sort(uint16_t* bkt, uint16_t* out, int n, const float* key, bool desc, int lane, uint32_t* cnt,
+                          uint16_t* members) {
+  float kmin = INFINITY, kmax = -INFINITY;
+  bool bad = false;
+  for (int a = lane; a < n; a += 32) {
+    const float k = key[a];
+    bad |= !(k == k) || fabsf(k) == INFINITY;
+    kmin = fminf(kmin, k);
+    kmax = fmaxf(kmax, k);
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    kmin = fminf(kmin, __shfl_xor_sync(kFull, kmin, d));
+    kmax = fmaxf(kmax, __shfl_xor_sync(kFull, kmax, d));
+  }
+  if (n < 128 || __any_sync(kFull, bad) || !(kmax > kmin)) {
+    rank_sort_quadratic(out, n, key, desc, lane);
+    return;
+  }
+  // monotone: subtraction of a constant, multiplication by a positive constant and truncation keep the order
+  const float scale = __fdiv_rn((float)(kSortBuckets - 1), __fsub_rn(kmax, kmin));
+  for (int b = lane; b < kSortBuckets; b += 32) cnt[b] = 0;
+  __syncwarp();
+  for (int a = lane; a < n; a += 32) {
+    int b = (int)__fmul_rn(__fsub_rn(key[a], kmin), scale);
+    b = min(max(b, 0), kSortBuckets - 1);
+    if (desc) b = kSortBuckets - 1 - b;
+    bkt[a] = (uint16_t)b;
+    atomicAdd(&cnt[b], 1u);
+  }
+  __syncwarp();
+  {  // exclusive prefix over the buckets: 32 consecutive counters per lane
+    uint32_t local = 0;
+    for (int k = 0; k < kSortBuckets / 32; ++k) local += cnt[lane * (kSortBuckets / 32) + k];
+    uint32_t inc = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(kFull, inc, d);
+      if (lane >= d) inc += o;
+    }
+    uint32_t run = inc - local;
+    for (int k = 0; k < kSortBuckets / 32; ++k) {
+      const uint32_t c = cnt[lane * (kSortBuckets / 32) + k];
+      cnt[lane * (kSortBuckets / 32) + k] = run;
+      run += c;
+    }
+  }
+  __syncwarp();
+  for (int a = lane; a < n; a += 32) members[atomicAdd(&cnt[bkt[a]], 1u)] = (uint16_t)a;   // cnt[b] becomes the bucket's end
+  __syncwarp();
+  for (int a = lane; a < n; a += 32) {
+    const int b = bkt[a];
+    const int s0 = b ? (int)cnt[b - 1] : 0, e0 = (int)cnt[b];
+    const float ka = key[a];
+    int r = s0;
+    for (int m = s0; m < e0; ++m) {
+      const int o = members[m];
+      const float kb = key[o];
+      const bool before = desc ? (kb > ka) : (kb < ka);
+      r += (before || (!(desc ? (ka > kb) : (ka < kb)) && o < a)) ? 1 : 0;
+    }
     out[r] = (uint16_t)a;
   }
   __syncwarp();
@@ -91,7 +161,7 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
     S.code[i] = -1;
   }
   __syncwarp();
-  rank_sort(S.tmp16, S.order, n, S.angles, false, lane);
+  rank_sort(S.tmp16, S.order, n, S.angles, false, lane, S.sort_cnt, S.check);
   // segments and angles in scan order, so that the pair scan reads them with plain coalesced loads instead of a
   // chain of dependent gathers (dst is free until the folds at the end)
   Seg* sseg = dst;
@@ -297,7 +367,7 @@ __device__ int frame_lines(Seg* raw, int n_raw, Seg* t1, Seg* t2, int w, int h, 
       S.tmp16[i] = (uint16_t)i;
     }
     __syncwarp();
-    rank_sort(S.tmp16, S.order, n2, S.length, true, lane);
+    rank_sort(S.tmp16, S.order, n2, S.length, true, lane, S.sort_cnt, S.check);
     n = nfeatures;
   } else {
     for (int i = lane; i < n2; i += 32) S.order[i] = (uint16_t)i;
@@ -324,12 +394,13 @@ constexpr int kPostWarps = 4;  // frames per CTA (one per warp)
 __global__ void __launch_bounds__(kPostWarps * 32, 8)
     line_post_kernel(LineBuffers L, int nb, int nfeatures, psl_keyline* __restrict__ kl, double* __restrict__ lineeq,
                      int cap, int32_t* __restrict__ n_out, uint32_t* __restrict__ status) {
+  __shared__ uint32_t sort_cnt[kPostWarps][linew::kSortBuckets];
   const int b = blockIdx.x * kPostWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= nb) return;
   const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
   line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
                        L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o,
-                       L.m_fw + o * line::kNbCap, L.m_den + o};
+                       L.m_fw + o * line::kNbCap, L.m_den + o, sort_cnt[threadIdx.x >> 5]};
   line::Seg* raw = reinterpret_cast<line::Seg*>(L.raw) + o;
   POST_T0(t_all);
   const int n = linew::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,
