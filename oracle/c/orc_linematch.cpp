@@ -250,6 +250,80 @@ int orc_line_search_triangulation(const uint8_t* desc1, const uint8_t* has_ml1, 
   return nm;
 }
 
+// ---- the epipolar-overlap variant: LSDmatcher::FrameBFMatchNew / mutualOverlap / SearchForTriangulationNew
+// (LSDmatcher.cpp:518-658, 783-824; nothing in the reference calls it) ----
+namespace {
+struct V3f { float v[3]; };
+
+V3f matvec3(const float* F, float x, float y) {  // cv::Mat(3x3 CV_32F) * (x, y, 1): double accumulation, one rounding
+  V3f r;
+  for (int k = 0; k < 3; ++k) r.v[k] = (float)((double)F[3 * k] * x + (double)F[3 * k + 1] * y + (double)F[3 * k + 2] * 1.0);
+  return r;
+}
+V3f cross3(const V3f& a, const V3f& b) {  // Mat::cross, CV_32F
+  return V3f{{a.v[1] * b.v[2] - a.v[2] * b.v[1], a.v[2] * b.v[0] - a.v[0] * b.v[2], a.v[0] * b.v[1] - a.v[1] * b.v[0]}};
+}
+float norm_diff(const V3f& a, const V3f& b) {  // (float) cv::norm(a - b): float differences, squares summed in double
+  const float d0 = a.v[0] - b.v[0], d1 = a.v[1] - b.v[1], d2 = a.v[2] - b.v[2];
+  return (float)std::sqrt((double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2);
+}
+float mutual_overlap(const V3f* p) {  // :583-658
+  float max_dist = 0.0f;
+  int outer1 = 0, outer2 = 3;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 4; ++j) {
+      const float dist = norm_diff(p[i], p[j]);
+      if (dist > max_dist) { max_dist = dist; outer1 = i; outer2 = j; }
+    }
+  if (max_dist < 1.0f) return 0.0f;
+  int inner[2], c = 0;
+  for (int k = 0; k < 4; ++k)
+    if (k != outer1 && k != outer2) inner[c++] = k;
+  return (float)(norm_diff(p[inner[0]], p[inner[1]]) / max_dist);
+}
+void frame_bf_match_new(const uint8_t* d1, const psl_keyline* kl1, int n1, const uint8_t* d2, const psl_keyline* kl2,
+                        const double* func2, int n2, const float* F, float th, float nn_ratio, int32_t* out) {  // :518-581
+  for (int i = 0; i < n1; ++i) out[i] = -1;
+  if (n1 == 0 || n2 < 2) return;  // with one train row knnMatch returns one entry and the loop `j < size() - 1` is empty
+  std::vector<int32_t> idx((size_t)n1 * 2), dist((size_t)n1 * 2);
+  orc_hamming_knn2(d1, n1, d2, n2, idx.data(), dist.data());
+  for (int q = 0; q < n1; ++q) {
+    const int t = idx[2 * q];
+    const V3f e1 = matvec3(F, kl1[q].start_x, kl1[q].start_y), e2 = matvec3(F, kl1[q].end_x, kl1[q].end_y);
+    const V3f l2{{(float)func2[3 * t], (float)func2[3 * t + 1], (float)func2[3 * t + 2]}};
+    V3f p1 = cross3(l2, e1), p2 = cross3(l2, e2);
+    if (!(std::fabs(p1.v[2]) > 1e-12 && std::fabs(p2.v[2]) > 1e-12)) continue;
+    const float s1 = (float)(1.0 / (double)p1.v[2]), s2 = (float)(1.0 / (double)p2.v[2]);  // Mat /= s -> convertTo(alpha = 1/s)
+    for (int k = 0; k < 3; ++k) { p1.v[k] = p1.v[k] * s1; p2.v[k] = p2.v[k] * s2; }
+    const V3f pts[4] = {p1, p2, V3f{{kl2[t].start_x, kl2[t].start_y, 1.0f}}, V3f{{kl2[t].end_x, kl2[t].end_y, 1.0f}}};
+    const float score = mutual_overlap(pts);
+    const float d0 = (float)dist[2 * q], dd1 = (float)dist[2 * q + 1];
+    if (d0 < th && score > 0.8 && d0 < nn_ratio * dd1) out[q] = t;
+  }
+}
+}  // namespace
+
+int orc_line_search_triangulation_new(const psl_keyline* kl1, const uint8_t* desc1, const double* func1,
+                                      const uint8_t* has_ml1, int n1, const psl_keyline* kl2, const uint8_t* desc2,
+                                      const double* func2, const uint8_t* has_ml2, int n2, const float* F21,
+                                      const float* F12, float nn_ratio, float th, int is_double, int32_t* pairs) {
+  for (int i = 0; i < n1; ++i) pairs[i] = -1;
+  if (n1 == 0 || n2 == 0) return 0;
+  std::vector<int32_t> m12((size_t)n1), m21((size_t)n2);
+  frame_bf_match_new(desc1, kl1, n1, desc2, kl2, func2, n2, F21, th, nn_ratio, m12.data());
+  frame_bf_match_new(desc2, kl2, n2, desc1, kl1, func1, n1, F12, th, nn_ratio, m21.data());
+  int nm = 0;
+  for (int i = 0; i < n1; ++i) {
+    const int j = m12[i];
+    if (j < 0) continue;
+    if (is_double && m21[j] != i) continue;
+    if (has_ml1[i] || has_ml2[j]) continue;
+    pairs[i] = j;
+    ++nm;
+  }
+  return nm;
+}
+
 // KeyFrame::GetLinesInArea, KeyFrame.cc:857-891 (TH defaults to 0.998, KeyFrame.h:144): all KeyLines, index order.
 static std::vector<int> lines_in_area(const psl_keyline* kl, int n, float x1, float y1, float x2, float y2, float r,
                                       float TH) {

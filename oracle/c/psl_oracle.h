@@ -123,6 +123,10 @@ int orc_line_search_double(const uint8_t* desc1, int n1, const uint8_t* desc2, i
 int orc_line_search_triangulation(const uint8_t* desc1, const uint8_t* has_ml1, int n1, const uint8_t* desc2,
                                   const uint8_t* has_ml2, int n2, float nn_ratio, float th, int is_double,
                                   int32_t* matches12);
+int orc_line_search_triangulation_new(const psl_keyline* kl1, const uint8_t* desc1, const double* func1,
+                                      const uint8_t* has_ml1, int n1, const psl_keyline* kl2, const uint8_t* desc2,
+                                      const double* func2, const uint8_t* has_ml2, int n2, const float* F21,
+                                      const float* F12, float nn_ratio, float th, int is_double, int32_t* pairs);
 int orc_line_fuse(const psl_keyline* kl, int n_lines, const uint8_t* kf_desc, const psl_line_fuse_query* qs,
                   const uint8_t* qdesc, int nq, float th_cos, int th_low, int32_t* best_idx, int32_t* best_dist);
 int orc_line_match_projection(const psl_line_frame_view* f, const psl_line_query* qs, const uint8_t* qdesc, int nq,

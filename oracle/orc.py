@@ -559,3 +559,17 @@ def line_junctions(kl_un, lines3d, img_w, img_h, radius=20.0, fan_thr=np.pi / 4,
                              C.c_float(fan_thr), _p(fans), None if l3 is None else _p(js), cap, C.byref(nf), C.byref(nj))
     assert nf.value <= cap
     return fans[: nf.value].copy(), js[: nj.value].copy()
+
+
+def line_search_triangulation_new(kl1, d1, func1, ml1, kl2, d2, func2, ml2, F21, F12, nn_ratio, th, is_double):
+    """LSDmatcher::SearchForTriangulationNew: (vMatchedPairs [n1], nmatches)."""
+    kl1, kl2 = np.ascontiguousarray(kl1, KEYLINE_DTYPE), np.ascontiguousarray(kl2, KEYLINE_DTYPE)
+    d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    f1, f2 = np.ascontiguousarray(func1, np.float64), np.ascontiguousarray(func2, np.float64)
+    m1, m2 = np.ascontiguousarray(ml1, np.uint8), np.ascontiguousarray(ml2, np.uint8)
+    A, B = np.ascontiguousarray(F21, np.float32).reshape(9), np.ascontiguousarray(F12, np.float32).reshape(9)
+    out = np.zeros(max(len(d1), 1), np.int32)
+    n = lib().orc_line_search_triangulation_new(_p(kl1), _p(d1), _p(f1), _p(m1), len(d1), _p(kl2), _p(d2), _p(f2), _p(m2),
+                                                len(d2), _p(A), _p(B), C.c_float(nn_ratio), C.c_float(th), int(is_double),
+                                                _p(out))
+    return out[: len(d1)].copy(), int(n)

@@ -15,6 +15,7 @@ import math
 import numpy as np
 
 F32 = np.float32
+F64 = np.float64
 COLS, ROWS = 64, 48
 
 
@@ -375,3 +376,88 @@ def plane_hypotheses(kl_un, line_eq, lines3d, junctions):
             normals.append(n_)
             owner.append(i)
     return (le, np.array(planes, F32).reshape(-1, 4), np.array(normals, F64).reshape(-1, 3), np.array(owner, np.int32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# LSDmatcher::FrameBFMatchNew / mutualOverlap / SearchForTriangulationNew (LSDmatcher.cpp:518-658, 783-824): the
+# epipolar-overlap variant of the line triangulation search (nothing in the reference calls it; "next" row N1)
+# ---------------------------------------------------------------------------------------------------
+def _matvec3_f32(F, x, y):
+    """cv::Mat(3x3, CV_32F) * (x, y, 1): double accumulation, one rounding (DESIGN.md, cv::Mat float products)."""
+    return [F32(F64(F[k, 0]) * F64(x) + F64(F[k, 1]) * F64(y) + F64(F[k, 2]) * F64(1.0)) for k in range(3)]
+
+
+def _cross_f32(a, b):
+    return [F32(F32(a[1] * b[2]) - F32(a[2] * b[1])), F32(F32(a[2] * b[0]) - F32(a[0] * b[2])),
+            F32(F32(a[0] * b[1]) - F32(a[1] * b[0]))]
+
+
+def _norm_diff(a, b):
+    """(float) cv::norm(a - b) for 3x1 CV_32F: float differences, squares accumulated in double."""
+    d = [F32(a[k] - b[k]) for k in range(3)]
+    return F32(math.sqrt(F64(d[0]) * F64(d[0]) + F64(d[1]) * F64(d[1]) + F64(d[2]) * F64(d[2])))
+
+
+def mutual_overlap(pts):
+    """LSDmatcher::mutualOverlap (:583-658) on four collinear homogeneous points."""
+    max_dist, o1, o2 = F32(0), 0, 3
+    for i in range(3):
+        for j in range(i + 1, 4):
+            d = _norm_diff(pts[i], pts[j])
+            if d > max_dist:
+                max_dist, o1, o2 = d, i, j
+    if max_dist < F32(1.0):
+        return F32(0)
+    inner = [k for k in range(4) if k != o1 and k != o2]
+    return F32(F64(_norm_diff(pts[inner[0]], pts[inner[1]])) / F64(max_dist))
+
+
+def frame_bf_match_new(d1, d2, kl1, kl2, func2, F, th, nn_ratio):
+    """LSDmatcher::FrameBFMatchNew (:518-581): the best knn match of a line of set 1 is kept if the projections of its end
+    points onto the matched line (along their epipolar lines F * p) overlap that line's segment by more than 0.8, its
+    distance is < th and passes the ratio test.  F: 3x3 float32."""
+    out = np.full(len(d1), -1, np.int32)
+    if len(d2) < 2:
+        return out          # knnMatch returns one entry: the loop `j < size() - 1` does not run
+    idx, dist = knn2_cv2(d1, d2)
+    F = np.asarray(F, F32)
+    with np.errstate(all="ignore"):
+        for q in range(len(d1)):
+            t = int(idx[q, 0])
+            e1 = _matvec3_f32(F, kl1["start_x"][q], kl1["start_y"][q])
+            e2 = _matvec3_f32(F, kl1["end_x"][q], kl1["end_y"][q])
+            l2 = [F32(func2[t, 0]), F32(func2[t, 1]), F32(func2[t, 2])]
+            p1, p2 = _cross_f32(l2, e1), _cross_f32(l2, e2)
+            if not (abs(float(p1[2])) > 1e-12 and abs(float(p2[2])) > 1e-12):
+                continue
+            s1, s2 = F32(1.0 / F64(p1[2])), F32(1.0 / F64(p2[2]))      # Mat /= s  ->  convertTo(alpha = 1 / s) in float
+            p1 = [F32(v * s1) for v in p1]
+            p2 = [F32(v * s2) for v in p2]
+            q1 = [F32(kl2["start_x"][t]), F32(kl2["start_y"][t]), F32(1)]
+            q2 = [F32(kl2["end_x"][t]), F32(kl2["end_y"][t]), F32(1)]
+            score = mutual_overlap([p1, p2, q1, q2])
+            d0, dd1 = F32(dist[q, 0]), F32(dist[q, 1])
+            if d0 < F32(th) and float(score) > 0.8 and d0 < F32(F32(nn_ratio) * dd1):
+                out[q] = t
+    return out
+
+
+def search_for_triangulation_new(d1, kl1, func1, ml1, d2, kl2, func2, ml2, F21, F12, nn_ratio, th, is_double):
+    """LSDmatcher::SearchForTriangulationNew (:783-824).  Returns (vMatchedPairs [n1], nmatches)."""
+    out = np.full(len(d1), -1, np.int32)
+    if len(d1) == 0 or len(d2) == 0:
+        return out, 0
+    t1 = frame_bf_match_new(d1, d2, kl1, kl2, func2, F21, th, nn_ratio)
+    t2 = frame_bf_match_new(d2, d1, kl2, kl1, func1, F12, th, nn_ratio)
+    n = 0
+    for i in range(len(d1)):
+        j = t1[i]
+        if j < 0:
+            continue
+        if is_double and t2[j] != i:
+            continue
+        if ml1[i] or ml2[j]:
+            continue
+        out[i] = j
+        n += 1
+    return out, n

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|undistort|planes|lines3d|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|linetriangnew|undistort|planes|lines3d|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -442,6 +442,37 @@ def make_linematch():
     print("plane_assoc: mode0", n_0, a_0.tolist(), "mode1", n_1, a_1.tolist())
 
 
+def make_linetriang_new():
+    """N1 fixture: LSDmatcher::SearchForTriangulationNew (epipolar-overlap variant) between two keyframes of the
+    synthetic sequence; F21 / F12 as LSDmatcher::ComputeF12 does (float32 cv::Mat products)."""
+    from oracle import orc
+    from oracle.pyref import linematch_py as lm
+    K = synth.ICL
+    Km = np.array([[K["fx"], 0, K["cx"]], [0, K["fy"], K["cy"]], [0, 0, 1]], np.float32)
+
+    def f12(T1, T2):   # LSDmatcher.cpp:826-845
+        T1, T2 = T1.astype(np.float32), T2.astype(np.float32)
+        R1w, t1w, R2w, t2w = T1[:3, :3], T1[:3, 3], T2[:3, :3], T2[:3, 3]
+        R12 = (R1w @ R2w.T).astype(np.float32)
+        t12 = (-R1w @ R2w.T @ t2w + t1w).astype(np.float32)
+        tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]], np.float32)
+        return (np.linalg.inv(Km).T @ tx @ R12 @ np.linalg.inv(Km)).astype(np.float32)
+
+    gray, _, T = synth.sequence(3, 6)
+    for case, (a, b, dbl, nnr) in enumerate([(0, 1, True, 0.95), (1, 4, False, 0.9)]):
+        rng = np.random.default_rng(300 + case)
+        k1, d1, e1, _ = orc.line_extract(gray[a], 200)
+        k2, d2, e2, _ = orc.line_extract(gray[b], 200)
+        ml1, ml2 = (rng.random(len(k1)) < 0.2).astype(np.uint8), (rng.random(len(k2)) < 0.2).astype(np.uint8)
+        F21, F12 = f12(T[b], T[a]), f12(T[a], T[b])
+        m, n = lm.search_for_triangulation_new(d1, k1, e1, ml1, d2, k2, e2, ml2, F21, F12, nnr, 50, dbl)
+        m2, n2 = lm.search_for_triangulation_new(d1, k1, e1, ml1, d2, k2, e2, ml2, F21, F12, 0.99, 90, not dbl)
+        np.savez_compressed(os.path.join(OUT, f"linetriangnew_pair{case}.npz"), kl1=k1, desc1=d1, func1=e1, ml1=ml1, kl2=k2,
+                            desc2=d2, func2=e2, ml2=ml2, F21=F21, F12=F12, nn_ratio=np.float32(nnr), is_double=np.int32(dbl),
+                            pairs=m, npairs=np.int32(n), pairs_b=m2, npairs_b=np.int32(n2))
+        print(f"linetriangnew_pair{case}: lines {len(k1)}/{len(k2)} pairs {n} / {n2}")
+
+
 def make_linefuse():
     """LSDmatcher::Fuse window search: the lines of the linematch pairs as KeyFrame lines, the last frame's lines as
     projected MapLines; kf_desc plays pKF->mDescriptors (rows near the line descriptors so that some fuse)."""
@@ -655,6 +686,8 @@ if __name__ == "__main__":
         make_linematch()
     if what in ("linefuse", "all"):
         make_linefuse()
+    if what in ("linetriangnew", "all"):
+        make_linetriang_new()
     if what in ("undistort", "all"):
         make_undistort()
     if what in ("planes", "all"):

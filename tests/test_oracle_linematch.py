@@ -158,3 +158,19 @@ def test_line_junctions(orc, name):
     assert np.array_equal(fans2, fans) and len(js2) == 0
     fans3, js3 = orc.line_junctions(g["kl"][:0], g["lines3d"][:0], w, h)
     assert len(fans3) == 0 and len(js3) == 0
+
+
+@pytest.mark.parametrize("name", golden_names("linetriangnew_"))
+def test_line_search_triangulation_new(orc, name):
+    """LSDmatcher::SearchForTriangulationNew (LSDmatcher.cpp:518-658, 783-824) against the independent Python restatement
+    over cv2.BFMatcher."""
+    g = load_golden(name)
+    args = (g["kl1"], g["desc1"], g["func1"], g["ml1"], g["kl2"], g["desc2"], g["func2"], g["ml2"], g["F21"], g["F12"])
+    m, n = orc.line_search_triangulation_new(*args, float(g["nn_ratio"]), 50, int(g["is_double"]))
+    assert np.array_equal(m, g["pairs"]) and n == int(g["npairs"]) and n > 20
+    m, n = orc.line_search_triangulation_new(*args, 0.99, 90, 1 - int(g["is_double"]))
+    assert np.array_equal(m, g["pairs_b"]) and n == int(g["npairs_b"])
+    # one line on the other side: knnMatch has no second neighbour, nothing matches; no lines at all
+    one = (g["kl1"], g["desc1"], g["func1"], g["ml1"], g["kl2"][:1], g["desc2"][:1], g["func2"][:1], g["ml2"][:1], g["F21"], g["F12"])
+    m, n = orc.line_search_triangulation_new(*one, 0.95, 50, 0)
+    assert n == 0 and (m == -1).all()
