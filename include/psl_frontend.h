@@ -393,6 +393,20 @@ int psl_line_search_triangulation(psl_ctx* ctx, const uint8_t* desc1, const uint
                                   const uint8_t* desc2, const uint8_t* has_mapline2, int32_t n2, float nn_ratio, float th,
                                   int32_t is_double, int32_t* matches12, int32_t* nmatches);
 
+/* LSDmatcher::SearchForTriangulationNew(pKF1, pKF2, vMatchedPairs, isDouble) over FrameBFMatchNew and mutualOverlap
+ * (add_src/LSDmatcher.cpp:518-658, 783-824; "next" row N1 — the epipolar-overlap variant of the search above; nothing in
+ * the reference calls it).  Per line of either keyframe: the best of cv::BFMatcher::knnMatch(k = 2) is kept if the
+ * projections of its end points onto the matched line, taken along their epipolar lines F * p, overlap that line's segment
+ * by more than 0.8 (mutualOverlap), its distance is < th and < nn_ratio * the second distance; then the mutual check
+ * (is_double) and the MapLine gates as in psl_line_search_triangulation.  kl*: mvKeyLines; func*: mvKeyLineFunctions
+ * (n*3 doubles); F21 = ComputeF12(pKF2, pKF1) maps points of KF1 to epipolar lines in KF2, F12 the reverse (3x3 row-major
+ * float, :804-805, computed by the caller from the poses).  matched_pairs[n1] = KF2 line or -1; *nmatches = return. */
+int psl_line_search_triangulation_new(psl_ctx* ctx, const psl_keyline* kl1, const uint8_t* desc1, const double* func1,
+                                      const uint8_t* has_mapline1, int32_t n1, const psl_keyline* kl2,
+                                      const uint8_t* desc2, const double* func2, const uint8_t* has_mapline2, int32_t n2,
+                                      const float* F21, const float* F12, float nn_ratio, float th, int32_t is_double,
+                                      int32_t* matched_pairs, int32_t* nmatches);
+
 /* One MapLine projected into a KeyFrame by LSDmatcher::Fuse before its window search (LSDmatcher.cpp:862-918): the
  * caller keeps the MapLine tests (isBad, IsInKeyFrame, IsInImage of both endpoints, distance invariance, viewing
  * angle), the `return false` of the whole call on an endpoint behind the camera (:883-884), and PredictScale;

@@ -263,23 +263,23 @@ V3f matvec3(const float* F, float x, float y) {  // cv::Mat(3x3 CV_32F) * (x, y,
 V3f cross3(const V3f& a, const V3f& b) {  // Mat::cross, CV_32F
   return V3f{{a.v[1] * b.v[2] - a.v[2] * b.v[1], a.v[2] * b.v[0] - a.v[0] * b.v[2], a.v[0] * b.v[1] - a.v[1] * b.v[0]}};
 }
-float norm_diff(const V3f& a, const V3f& b) {  // (float) cv::norm(a - b): float differences, squares summed in double
+double norm_diff(const V3f& a, const V3f& b) {  // cv::norm(a - b): float differences, squares summed in double
   const float d0 = a.v[0] - b.v[0], d1 = a.v[1] - b.v[1], d2 = a.v[2] - b.v[2];
-  return (float)std::sqrt((double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2);
+  return std::sqrt((double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2);
 }
 float mutual_overlap(const V3f* p) {  // :583-658
   float max_dist = 0.0f;
   int outer1 = 0, outer2 = 3;
   for (int i = 0; i < 3; ++i)
     for (int j = i + 1; j < 4; ++j) {
-      const float dist = norm_diff(p[i], p[j]);
+      const float dist = (float)norm_diff(p[i], p[j]);
       if (dist > max_dist) { max_dist = dist; outer1 = i; outer2 = j; }
     }
   if (max_dist < 1.0f) return 0.0f;
   int inner[2], c = 0;
   for (int k = 0; k < 4; ++k)
     if (k != outer1 && k != outer2) inner[c++] = k;
-  return (float)(norm_diff(p[inner[0]], p[inner[1]]) / max_dist);
+  return (float)(norm_diff(p[inner[0]], p[inner[1]]) / max_dist);  // double norm / float
 }
 void frame_bf_match_new(const uint8_t* d1, const psl_keyline* kl1, int n1, const uint8_t* d2, const psl_keyline* kl2,
                         const double* func2, int n2, const float* F, float th, float nn_ratio, int32_t* out) {  // :518-581

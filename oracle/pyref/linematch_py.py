@@ -393,9 +393,9 @@ def _cross_f32(a, b):
 
 
 def _norm_diff(a, b):
-    """(float) cv::norm(a - b) for 3x1 CV_32F: float differences, squares accumulated in double."""
+    """cv::norm(a - b) for 3x1 CV_32F (a double): float differences, squares accumulated in double."""
     d = [F32(a[k] - b[k]) for k in range(3)]
-    return F32(math.sqrt(F64(d[0]) * F64(d[0]) + F64(d[1]) * F64(d[1]) + F64(d[2]) * F64(d[2])))
+    return F64(math.sqrt(F64(d[0]) * F64(d[0]) + F64(d[1]) * F64(d[1]) + F64(d[2]) * F64(d[2])))
 
 
 def mutual_overlap(pts):
@@ -403,13 +403,13 @@ def mutual_overlap(pts):
     max_dist, o1, o2 = F32(0), 0, 3
     for i in range(3):
         for j in range(i + 1, 4):
-            d = _norm_diff(pts[i], pts[j])
+            d = F32(_norm_diff(pts[i], pts[j]))      # float dist = norm(...)
             if d > max_dist:
                 max_dist, o1, o2 = d, i, j
     if max_dist < F32(1.0):
         return F32(0)
     inner = [k for k in range(4) if k != o1 and k != o2]
-    return F32(F64(_norm_diff(pts[inner[0]], pts[inner[1]])) / F64(max_dist))
+    return F32(_norm_diff(pts[inner[0]], pts[inner[1]]) / F64(max_dist))     # double norm / float -> float
 
 
 def frame_bf_match_new(d1, d2, kl1, kl2, func2, F, th, nn_ratio):

@@ -151,7 +151,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_convert_rgbd_dev", "psl_match_triangulation", "psl_match_fuse", "psl_line_search_triangulation", "psl_line_fuse",
            "psl_undistort_keypoints", "psl_undistort_keypoints_dev", "psl_image_bounds", "psl_plane_hypotheses",
            "psl_lines_3d", "psl_lines_3d_dev", "psl_match_bow_kf", "psl_match_sim3", "psl_match_initialization",
-           "psl_line_junctions", "psl_line_junctions_dev"]
+           "psl_line_junctions", "psl_line_junctions_dev", "psl_line_search_triangulation_new"]
 
 _lib = None
 
@@ -215,6 +215,7 @@ def lib():
         L.psl_match_bow_kf.argtypes = [_p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _f, _i, _i, _p, _p]
         L.psl_match_sim3.argtypes = [_p, _p, _p, _p, _p, _p, _p, _i, _p, _p]
         L.psl_match_initialization.argtypes = [_p, _p, _p, _i, _p, _p, _i, _f, _i, _i, _p, _p]
+        L.psl_line_search_triangulation_new.argtypes = [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _f, _f, _i, _p, _p]
         L.psl_line_junctions.argtypes = [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _i, _p, _p]
         L.psl_line_junctions_dev.argtypes = [_p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _p, _p, _i, _p, _p]
         _lib = L

@@ -160,6 +160,70 @@ void launch_line_bfmatch(const LineSet& Q, const LineSet& T, const uint2* knn, f
   line_bfmatch_kernel<<<B, 256, 0, st>>>(Q, T, knn, nn_ratio, th, matches);
 }
 
+// LSDmatcher::FrameBFMatchNew + mutualOverlap (LSDmatcher.cpp:518-658): thread per query line.  The best knn match is
+// kept if the projections of the query's end points onto the matched line (along their epipolar lines F * p) overlap
+// that line's segment by more than 0.8 and the distance passes th and the ratio test.  cv::Mat float arithmetic as
+// pinned in DESIGN.md: 3x3 * 3x1 with double accumulation and one rounding, Mat::cross in float, `Mat /= s` =
+// convertTo(alpha = 1 / s) in float, cv::norm of a float difference with the squares summed in double.
+struct V3f { float v[3]; };
+__device__ __forceinline__ V3f matvec3(const float* F, float x, float y) {
+  V3f r;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) r.v[k] = (float)((double)F[3 * k] * x + (double)F[3 * k + 1] * y + (double)F[3 * k + 2] * 1.0);
+  return r;
+}
+__device__ __forceinline__ V3f cross3(const V3f& a, const V3f& b) {
+  return V3f{{a.v[1] * b.v[2] - a.v[2] * b.v[1], a.v[2] * b.v[0] - a.v[0] * b.v[2], a.v[0] * b.v[1] - a.v[1] * b.v[0]}};
+}
+__device__ __forceinline__ double norm_diff(const V3f& a, const V3f& b) {
+  const float d0 = a.v[0] - b.v[0], d1 = a.v[1] - b.v[1], d2 = a.v[2] - b.v[2];
+  return sqrt((double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2);
+}
+__device__ float mutual_overlap(const V3f* p) {
+  float max_dist = 0.0f;
+  int outer1 = 0, outer2 = 3;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 4; ++j) {
+      const float dist = (float)norm_diff(p[i], p[j]);   // float dist = norm(...)
+      if (dist > max_dist) { max_dist = dist; outer1 = i; outer2 = j; }
+    }
+  if (max_dist < 1.0f) return 0.0f;
+  int inner[2], c = 0;
+  for (int k = 0; k < 4; ++k)
+    if (k != outer1 && k != outer2) inner[c++] = k;
+  return (float)(norm_diff(p[inner[0]], p[inner[1]]) / (double)max_dist);   // double norm / float -> float
+}
+
+__global__ void line_bfmatch_new_kernel(LineSet Q, LineSet T, const double* __restrict__ funcT, const uint2* __restrict__ knn,
+                                        const float* __restrict__ F, float nn_ratio, float th, int32_t* __restrict__ matches) {
+  const int b = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q.n[b]) return;
+  int32_t* out = matches + (size_t)b * Q.cap;
+  out[q] = -1;
+  if (T.n[b] < 2) return;  // one train row: knnMatch has one entry and the loop `j < size() - 1` is empty
+  const uint2 kk = knn[(size_t)b * Q.cap + q];
+  const int t = (int)(kk.x & 0xFFFFu);
+  const psl_keyline k1 = Q.kl[(size_t)b * Q.cap + q], k2 = T.kl[(size_t)b * T.cap + t];
+  const double* f2 = funcT + ((size_t)b * T.cap + t) * 3;
+  const V3f e1 = matvec3(F, k1.start_x, k1.start_y), e2 = matvec3(F, k1.end_x, k1.end_y);
+  const V3f l2{{(float)f2[0], (float)f2[1], (float)f2[2]}};
+  V3f p1 = cross3(l2, e1), p2 = cross3(l2, e2);
+  if (!((double)fabsf(p1.v[2]) > 1e-12 && (double)fabsf(p2.v[2]) > 1e-12)) return;
+  const float s1 = (float)(1.0 / (double)p1.v[2]), s2 = (float)(1.0 / (double)p2.v[2]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { p1.v[k] = p1.v[k] * s1; p2.v[k] = p2.v[k] * s2; }
+  const V3f pts[4] = {p1, p2, V3f{{k2.start_x, k2.start_y, 1.0f}}, V3f{{k2.end_x, k2.end_y, 1.0f}}};
+  const float score = mutual_overlap(pts);
+  const float d0 = (float)(kk.x >> 16), d1 = (float)(kk.y >> 16);
+  if (d0 < th && (double)score > 0.8 && d0 < nn_ratio * d1) out[q] = t;
+}
+
+void launch_line_bfmatch_new(const LineSet& Q, const LineSet& T, const double* funcT, const uint2* knn, const float* F,
+                             float nn_ratio, float th, int32_t* matches, int B, cudaStream_t st) {
+  dim3 grid((Q.cap + 127) / 128, B);
+  line_bfmatch_new_kernel<<<grid, 128, 0, st>>>(Q, T, funcT, knn, F, nn_ratio, th, matches);
+}
+
 // mutual consistency of LSDmatcher::SearchDouble (LSDmatcher.cpp:474-487)
 __global__ void line_mutual_kernel(LineSet A, const int32_t* __restrict__ m21, int cap2, int32_t* __restrict__ m12,
                                    int32_t* __restrict__ nmatches) {

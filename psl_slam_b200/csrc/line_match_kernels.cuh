@@ -24,6 +24,9 @@ void launch_line_bfmatch(const LineSet& Q, const LineSet& T, const uint2* knn, f
                          int32_t* matches, int B, cudaStream_t st);
 void launch_line_mutual(const LineSet& A, const int32_t* m21, int cap2, int32_t* m12, int32_t* nmatches, int B,
                         cudaStream_t st);
+// FrameBFMatchNew: knn = launch_line_knn2(Q, T); Q.kl / T.kl and funcT (line equations of T, [B][cap][3]) are read
+void launch_line_bfmatch_new(const LineSet& Q, const LineSet& T, const double* funcT, const uint2* knn, const float* F,
+                             float nn_ratio, float th, int32_t* matches, int B, cudaStream_t st);
 void launch_line_triang(const LineSet& A, const int32_t* m21, int cap2, const uint8_t* ml1, const uint8_t* ml2,
                         int is_double, int32_t* m12, int32_t* nmatches, int B, cudaStream_t st);
 // window search of LSDmatcher::Fuse: one warp per query over the n_lines KeyLines of one KeyFrame

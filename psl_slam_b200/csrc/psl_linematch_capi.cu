@@ -180,6 +180,58 @@ int psl_line_search_triangulation(psl_ctx* ctx, const uint8_t* desc1, const uint
   return check_status(ctx);
 }
 
+int psl_line_search_triangulation_new(psl_ctx* ctx, const psl_keyline* kl1, const uint8_t* desc1, const double* func1,
+                                      const uint8_t* has_mapline1, int32_t n1, const psl_keyline* kl2,
+                                      const uint8_t* desc2, const double* func2, const uint8_t* has_mapline2, int32_t n2,
+                                      const float* F21, const float* F12, float nn_ratio, float th, int32_t is_double,
+                                      int32_t* matched_pairs, int32_t* nmatches) {
+  if (!ctx) return PSL_E_INVALID;
+  if (bad_desc_args(desc1, n1, desc2, n2) || !nmatches || !F21 || !F12 ||
+      (n1 > 0 && (!matched_pairs || !has_mapline1 || !kl1 || !func1)) || (n2 > 0 && (!has_mapline2 || !kl2 || !func2)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  *nmatches = 0;
+  if (n1 == 0) return PSL_OK;
+  for (int i = 0; i < n1; ++i) matched_pairs[i] = -1;
+  if (n2 == 0) return PSL_OK;  // LSDmatcher.cpp:792-793
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  LineSet A, T;
+  int rc = stage_desc_pair(ctx, desc1, n1, desc2, n2, A, T);
+  if (rc) return rc;
+  DevBuf* M = ctx->m_misc;
+  PSL_UP(M[0], has_mapline1, (size_t)n1);
+  PSL_UP(M[1], has_mapline2, (size_t)n2);
+  PSL_UP(M[2], kl1, (size_t)n1 * sizeof(psl_keyline));
+  PSL_UP(M[3], kl2, (size_t)n2 * sizeof(psl_keyline));
+  PSL_UP(M[4], func1, (size_t)n1 * 24);
+  PSL_UP(M[5], func2, (size_t)n2 * 24);
+  float FF[18];
+  std::memcpy(FF, F21, 36);
+  std::memcpy(FF + 9, F12, 36);
+  PSL_UP(M[6], FF, sizeof(FF));
+  A.kl = M[2].as<psl_keyline>();
+  T.kl = M[3].as<psl_keyline>();
+  PSL_ENS(ctx->m_best, (size_t)n1 * 8);
+  PSL_ENS(ctx->m_cand_count, (size_t)n2 * 8);
+  PSL_ENS(ctx->m_assign, (size_t)n1 * 4);
+  PSL_ENS(ctx->m_accepted, (size_t)n2 * 4);
+  PSL_ENS(ctx->m_nm, 4);
+  cudaStream_t st = ctx->stream;
+  size_t e = prof_mark(ctx);
+  launch_line_knn2(A, T, ctx->m_best.as<uint2>(), 1, st);
+  launch_line_bfmatch_new(A, T, M[5].as<double>(), ctx->m_best.as<uint2>(), M[6].as<float>(), nn_ratio, th,
+                          ctx->m_assign.as<int32_t>(), 1, st);   // thread12: F21 (:805)
+  launch_line_knn2(T, A, ctx->m_cand_count.as<uint2>(), 1, st);
+  launch_line_bfmatch_new(T, A, M[4].as<double>(), ctx->m_cand_count.as<uint2>(), M[6].as<float>() + 9, nn_ratio, th,
+                          ctx->m_accepted.as<int32_t>(), 1, st);  // thread21: F12 (:806)
+  launch_line_triang(A, ctx->m_accepted.as<int32_t>(), T.cap, M[0].as<uint8_t>(), M[1].as<uint8_t>(), is_double,
+                     ctx->m_assign.as<int32_t>(), ctx->m_nm.as<int32_t>(), 1, st);
+  prof_span(ctx, 15, e, 5);
+  PSL_CK(cudaGetLastError());
+  PSL_CK(cudaMemcpyAsync(matched_pairs, ctx->m_assign.p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, st));
+  PSL_CK(cudaMemcpyAsync(nmatches, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, st));
+  return check_status(ctx);
+}
+
 int psl_line_fuse(psl_ctx* ctx, const psl_keyline* kl, int32_t n_lines, const uint8_t* kf_desc, int32_t n_desc,
                   const psl_line_fuse_query* queries, const uint8_t* query_desc, int32_t nq, float th_cos, int32_t th_low,
                   int32_t* best_idx, int32_t* best_dist) {

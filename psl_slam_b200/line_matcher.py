@@ -100,6 +100,24 @@ class LSDmatcher:
                                                                 C.byref(nm)))
         return out, nm.value
 
+    def SearchForTriangulationNew(self, kf1, kf2, F21, F12, isDouble=False):
+        """SearchForTriangulationNew(pKF1, pKF2, vMatchedPairs, isDouble) — LSDmatcher.cpp:783-824 over FrameBFMatchNew
+        (:518-581) and mutualOverlap (:583-658).  kf* = (mvKeyLines, mLineDescriptors, mvKeyLineFunctions [n,3], has MapLine
+        [n]); F21 / F12 = ComputeF12(pKF2, pKF1) / ComputeF12(pKF1, pKF2), 3x3 float.  Returns (vMatchedPairs [n1], count)."""
+        k1, k2 = np.ascontiguousarray(kf1[0], KEYLINE_DTYPE), np.ascontiguousarray(kf2[0], KEYLINE_DTYPE)
+        d1, d2, m1, m2 = _u8(kf1[1]), _u8(kf2[1]), _u8(kf1[3]), _u8(kf2[3])
+        f1 = np.ascontiguousarray(kf1[2], np.float64).reshape(-1, 3)
+        f2 = np.ascontiguousarray(kf2[2], np.float64).reshape(-1, 3)
+        A = np.ascontiguousarray(F21, np.float32).reshape(9)
+        B = np.ascontiguousarray(F12, np.float32).reshape(9)
+        out = np.full(len(d1), -1, np.int32)
+        nm = C.c_int32()
+        self.ctx.check(_lib.lib().psl_line_search_triangulation_new(
+            self.ctx.handle, _ptr(k1), _ptr(d1), _ptr(f1), _ptr(m1), len(d1), _ptr(k2), _ptr(d2), _ptr(f2), _ptr(m2),
+            len(d2), _ptr(A), _ptr(B), C.c_float(self.mfNNratio), C.c_float(self.TH_LOW), int(isDouble), _ptr(out),
+            C.byref(nm)))
+        return out, nm.value
+
     def Fuse(self, keylines, kf_descriptors, queries, map_line_desc, th_cos=0.998):
         """Window search of Fuse(pKF, vpMapLines, th) — LSDmatcher.cpp:847-984: per projected MapLine (queries:
         LINE_FUSE_QUERY_DTYPE) the line of KeyFrame::GetLinesInArea (KeyFrame.cc:857-891) at level pred-1..pred with

@@ -348,3 +348,36 @@ def test_line_junctions_random_large(orc):
     assert np.array_equal(fans, wf, equal_nan=True)
     assert len(js) == len(wj) and np.array_equal(js["l1"], wj["l1"]) and np.array_equal(js["l2"], wj["l2"])
     assert np.array_equal(js["cross3d"], wj["cross3d"])
+
+
+@pytest.mark.parametrize("name", golden_names("linetriangnew_"))
+def test_line_search_triangulation_new(orc, name):
+    """LSDmatcher::SearchForTriangulationNew (LSDmatcher.cpp:518-658, 783-824)."""
+    from psl_slam_b200 import LSDmatcher
+    g = load_golden(name)
+    a = (g["kl1"], g["desc1"], g["func1"], g["ml1"])
+    b = (g["kl2"], g["desc2"], g["func2"], g["ml2"])
+    m, n = LSDmatcher(float(g["nn_ratio"])).SearchForTriangulationNew(a, b, g["F21"], g["F12"], bool(g["is_double"]))
+    assert np.array_equal(m, g["pairs"]) and n == int(g["npairs"])
+    mm = LSDmatcher(0.99)
+    mm.TH_LOW = 90
+    m, n = mm.SearchForTriangulationNew(a, b, g["F21"], g["F12"], not bool(g["is_double"]))
+    assert np.array_equal(m, g["pairs_b"]) and n == int(g["npairs_b"])
+    # perturbed geometry (other fundamental matrices, jittered end points): against the oracle
+    rng = np.random.default_rng(9)
+    k1 = g["kl1"].copy()
+    for f in ("start_x", "start_y", "end_x", "end_y"):
+        k1[f] += rng.normal(0, 4, len(k1)).astype(np.float32)
+    F21 = (g["F21"] * rng.uniform(0.8, 1.2, (3, 3))).astype(np.float32)
+    F12 = (g["F12"] * rng.uniform(0.8, 1.2, (3, 3))).astype(np.float32)
+    m, n = LSDmatcher(0.95).SearchForTriangulationNew((k1, g["desc1"], g["func1"], g["ml1"]), b, F21, F12, True)
+    wm, wn = orc.line_search_triangulation_new(k1, g["desc1"], g["func1"], g["ml1"], g["kl2"], g["desc2"], g["func2"], g["ml2"],
+                                               F21, F12, 0.95, 50, 1)
+    assert np.array_equal(m, wm) and n == wn
+    # a single line on the other side / none
+    one = (g["kl2"][:1], g["desc2"][:1], g["func2"][:1], g["ml2"][:1])
+    m, n = LSDmatcher(0.95).SearchForTriangulationNew(a, one, g["F21"], g["F12"], False)
+    assert n == 0 and (m == -1).all()
+    none = (g["kl2"][:0], g["desc2"][:0], g["func2"][:0], g["ml2"][:0])
+    m, n = LSDmatcher(0.95).SearchForTriangulationNew(a, none, g["F21"], g["F12"], False)
+    assert n == 0 and (m == -1).all()
