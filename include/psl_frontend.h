@@ -347,7 +347,8 @@ int psl_match_sim3(psl_ctx* ctx, const psl_frame_view* kf1, const psl_frame_view
  * updated in place for the matched keypoints (:514-517); f2 = the searched frame (window of half-size window_size over
  * its level-0 keypoints, :425).  The greedy loop is order dependent (vMatchedDistance / vnMatches21 un-match earlier
  * pairs, :441-442, :461-470): the candidates and their distances are found in parallel, the loop itself is replayed in
- * order by one warp.  matches12[n1] = F2 index or -1; *nmatches = the return value. */
+ * order by one warp.  matches12[n1] = F2 index or -1; *nmatches = the return value.  A window holding more than 256
+ * level-0 keypoints of F2 is refused with PSL_E_CAPACITY (nothing is written to the outputs). */
 int psl_match_initialization(psl_ctx* ctx, const psl_keypoint* kps1_un, const uint8_t* desc1, int32_t n1,
                              float* prev_matched, const psl_frame_view* f2, int32_t window_size, float nn_ratio,
                              int32_t th_low, int32_t check_orientation, int32_t* matches12, int32_t* nmatches);
