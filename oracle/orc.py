@@ -573,3 +573,19 @@ def line_search_triangulation_new(kl1, d1, func1, ml1, kl2, d2, func2, ml2, F21,
                                                 len(d2), _p(A), _p(B), C.c_float(nn_ratio), C.c_float(th), int(is_double),
                                                 _p(out))
     return out[: len(d1)].copy(), int(n)
+
+
+POSE_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("u_right", "<f4"), ("inv_sigma2", "<f4"), ("xw", "<f4"),
+                             ("yw", "<f4"), ("zw", "<f4"), ("flags", "<u4")])  # psl_pose_point, 32 B
+
+
+def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
+    """Optimizer::PoseOptimization, point edges only (UNPINNED restatement over the vendored g2o):
+    (Tcw after [4,4] f32, mvbOutlier [n] u8, nInitialCorrespondences - nBad)."""
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    p = np.ascontiguousarray(pts, POSE_POINT_DTYPE)
+    out = np.zeros(16, np.float32)
+    bad = np.zeros(max(len(p), 1), np.uint8)
+    n = lib().orc_pose_optimization(_p(T), _p(p), len(p), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                    C.c_float(bf), _p(out), _p(bad))
+    return out.reshape(4, 4), bad[: len(p)].copy(), int(n)

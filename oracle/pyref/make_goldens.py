@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|linetriangnew|undistort|planes|lines3d|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|linetriangnew|pose|undistort|planes|lines3d|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -635,6 +635,54 @@ def make_junctions():
         print(f"junctions_case{case}: lines {len(kl)} raw fans {len(raw)} fans {len(fans)} junctions {len(js)}")
 
 
+def make_pose():
+    """N4 fixture (oracle side only): Optimizer::PoseOptimization with point edges — synthetic map points seen from a known
+    pose with pixel noise, gross outliers and a perturbed pose prior; outputs of the independent numpy restatement
+    (oracle/pyref/pose_py.py)."""
+    from oracle import orc
+    from oracle.pyref import pose_py
+    K = synth.ICL
+    fx, fy, cx, cy, bf = K["fx"], K["fy"], K["cx"], K["cy"], K["bf"]
+
+    def rot(w):
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+    cases = [("pose_case0", 0, 600, 0.7, 0.10, 0.01, 0.03), ("pose_case1_mono", 1, 300, 0.0, 0.05, 0.02, 0.05),
+             ("pose_case2_far_prior", 2, 800, 0.9, 0.20, 0.06, 0.25), ("pose_case3_few", 3, 8, 0.5, 0.0, 0.01, 0.02),
+             ("pose_case4_two", 4, 2, 1.0, 0.0, 0.01, 0.02)]
+    for name, seed, n, p_stereo, p_out, rot_err, t_err in cases:
+        rng = np.random.default_rng(700 + seed)
+        Rt, tt = rot(rng.normal(0, 0.05, 3)), rng.normal(0, 0.1, 3)
+        Xc = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1, 1, n), rng.uniform(0.8, 6, n)], 1)
+        Xw = (Rt.T @ (Xc - tt).T).T
+        u = fx * Xc[:, 0] / Xc[:, 2] + cx + rng.normal(0, 0.6, n)
+        v = fy * Xc[:, 1] / Xc[:, 2] + cy + rng.normal(0, 0.6, n)
+        ur = u - bf / Xc[:, 2] + rng.normal(0, 0.6, n)
+        p = np.zeros(n + 5, orc.POSE_POINT_DTYPE)
+        p["u"][:n], p["v"][:n] = u, v
+        p["u_right"][:n] = np.where(rng.random(n) < p_stereo, ur, -1)
+        p["inv_sigma2"][:n] = 1 / 1.2 ** (2 * rng.integers(0, 8, n))
+        p["xw"][:n], p["yw"][:n], p["zw"][:n] = Xw[:, 0], Xw[:, 1], Xw[:, 2]
+        p["flags"][:n] = 1                                     # the last five keypoints have no MapPoint
+        bad = rng.random(n) < p_out
+        p["u"][:n][bad] += rng.normal(0, 25, int(bad.sum())).astype(np.float32)
+        p["v"][:n][bad] += rng.normal(0, 25, int(bad.sum())).astype(np.float32)
+        p = p[rng.permutation(len(p))]
+        T0 = np.eye(4, dtype=np.float32)
+        T0[:3, :3] = rot(rng.normal(0, rot_err, 3)) @ Rt
+        T0[:3, 3] = tt + rng.normal(0, t_err, 3)
+        T, outl, cnt = pose_py.pose_optimization(T0, p, fx, fy, cx, cy, bf)
+        Ttrue = np.eye(4)
+        Ttrue[:3, :3], Ttrue[:3, 3] = Rt, tt
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), Tcw0=T0, pts=p, cam=np.array([fx, fy, cx, cy, bf], np.float32),
+                            Tcw=T, outlier=outl, count=np.int32(cnt), Ttrue=Ttrue)
+        print(f"{name}: points {int((p['flags'] & 1).sum())} inliers {cnt} outliers {int(outl.sum())} "
+              f"|t - t_true| {np.abs(T[:3, 3] - tt).max():.2e} (prior {np.abs(T0[:3, 3] - tt).max():.2e})")
+
+
 def make_lines3d():
     """Frame::isLineGood: the lines of the linematch pairs over the sequence's depth (clean, noisy, noisy with holes);
     both SVDs are the real cv2.SVDecomp (oracle/pyref/line3d_py.py)."""
@@ -688,6 +736,8 @@ if __name__ == "__main__":
         make_linefuse()
     if what in ("linetriangnew", "all"):
         make_linetriang_new()
+    if what in ("pose", "all"):
+        make_pose()
     if what in ("undistort", "all"):
         make_undistort()
     if what in ("planes", "all"):
