@@ -637,6 +637,31 @@ int psl_line_junctions_dev(psl_ctx* ctx, const psl_keyline* d_kl, const int32_t*
                            float* d_fans, psl_line_junction* d_junctions, int32_t cap, int32_t* d_n_fans,
                            int32_t* d_n_junctions);
 
+/* Optimizer::PoseOptimization (src/Optimizer.cc:239-1023; SURVEY "next" row N4) for a frame without InsectLine
+ * observations: the pose-only Levenberg optimisation over the keypoints that hold a MapPoint — monocular / stereo
+ * reprojection edges (EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose of the vendored g2o) with Huber kernels
+ * (delta^2 = 5.991 / 7.815), four rounds of at most ten Levenberg iterations from the pose prior, the chi-square
+ * classification between rounds (outliers leave the system, :782-838), the kernels dropped after the third round.
+ * One record per keypoint: flags & 1 = mvpMapPoints[i] != NULL; u_right < 0 = monocular observation.  Tcw: 4x4
+ * row-major float (pFrame->mTcw in, the pose SetPose receives out); outlier[n] = mvbOutlier; *n_inliers = the return
+ * value (nInitialCorrespondences - nBad; 0 and no change with fewer than 3 correspondences).  fp64 on the device; the
+ * sums over the edges run in another order than g2o's, so the contract is a tolerance (pose to 1e-6, identical flags away
+ * from the thresholds), and the oracle is a restatement that g2o cannot pin here.  LIL edges (:504-590,
+ * :840-868) are not part of this entry point yet. */
+typedef struct psl_pose_point {
+  float u, v, u_right;   /* mvKeysUn[i].pt, mvuRight[i] */
+  float inv_sigma2;      /* mvInvLevelSigma2[mvKeysUn[i].octave] */
+  float xw, yw, zw;      /* pMP->GetWorldPos() */
+  uint32_t flags;
+} psl_pose_point;
+int psl_pose_optimization(psl_ctx* ctx, const float* Tcw_in, const psl_pose_point* pts, int32_t n, float fx, float fy,
+                          float cx, float cy, float bf, float* Tcw_out, uint8_t* outlier, int32_t* n_inliers);
+/* Batched, DEVICE pointers, asynchronous: frame b owns rows [b*cap, b*cap + d_n[b]) of d_pts / d_outlier and the 16
+ * floats at d_Tcw_in / d_Tcw_out + 16*b; one CTA per frame. */
+int psl_pose_optimization_dev(psl_ctx* ctx, const float* d_Tcw_in, const psl_pose_point* d_pts, const int32_t* d_n,
+                              int32_t cap, int32_t B, float fx, float fy, float cx, float cy, float bf, float* d_Tcw_out,
+                              uint8_t* d_outlier, int32_t* d_n_inliers);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,7 +114,7 @@ void compute_error(Edge& e, const Pose& p, const Cam& c) {
   quat_rotate(p.q, e.Xw, X);
   for (int i = 0; i < 3; ++i) X[i] += p.t[i];
   if (e.stereo) {  // EdgeStereoSE3ProjectXYZOnlyPose::cam_project: invz is a float
-    const float invz = 1.0f / (float)X[2];  // 1.0f / double -> double division, narrowed to float
+    const float invz = (float)(1.0 / X[2]);  // `const float invz = 1.0f / z`: double division, narrowed to float
     const double r0 = X[0] * invz * c.fx + c.cx, r1 = X[1] * invz * c.fy + c.cy;
     e.err[0] = e.obs[0] - r0; e.err[1] = e.obs[1] - r1; e.err[2] = e.obs[2] - (r0 - c.bf * invz);
   } else {         // project2d + intrinsics
@@ -207,7 +207,7 @@ int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n,
   const Cam cam{fx, fy, cx, cy, bf};
   std::vector<Edge> E;
   std::vector<int> idx;
-  const float deltaMono = sqrtf(5.991f), deltaStereo = sqrtf(7.815f);  // :276-277 (float sqrt of the double literal)
+  const float deltaMono = (float)std::sqrt(5.991), deltaStereo = (float)std::sqrt(7.815);  // :276-277
   for (int i = 0; i < n; ++i) {
     outlier[i] = 0;
     if (!(pts[i].flags & 1u)) continue;

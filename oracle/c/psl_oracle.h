@@ -85,12 +85,6 @@ int orc_line_junctions(const psl_keyline* kl_un, const double* lines3d, int n, i
                        int32_t* n_junctions);
 
 /* ---- pose-only optimisation (orc_pose.cpp): Optimizer.cc:239-1023 over the vendored g2o, point edges only; UNPINNED ---- */
-typedef struct psl_pose_point {
-  float u, v, u_right;   /* mvKeysUn[i].pt, mvuRight[i] (< 0: monocular edge) */
-  float inv_sigma2;      /* mvInvLevelSigma2[octave] */
-  float xw, yw, zw;      /* pMP->GetWorldPos() */
-  uint32_t flags;        /* 1: the keypoint has a MapPoint */
-} psl_pose_point;
 int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n, float fx, float fy, float cx, float cy,
                           float bf, float* Tcw_out, uint8_t* outlier);
 

@@ -87,8 +87,7 @@ def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
     obs = np.stack([pts["u"][sel], pts["v"][sel], np.where(stereo, pts["u_right"][sel], 0)], 1).astype(np.float64)
     Xw = np.stack([pts["xw"][sel], pts["yw"][sel], pts["zw"][sel]], 1).astype(np.float64)
     info = pts["inv_sigma2"][sel].astype(np.float64)
-    delta = np.where(stereo, float(F32(math.sqrt(F32(7.815)))), float(F32(math.sqrt(F32(5.991)))))
-    delta = np.where(stereo, float(np.sqrt(F32(7.815))), float(np.sqrt(F32(5.991))))
+    delta = np.where(stereo, float(F32(math.sqrt(7.815))), float(F32(math.sqrt(5.991))))   # const float delta = sqrt(5.991)
     level = np.zeros(len(sel), int)
     robust = np.ones(len(sel), bool)
     err = np.zeros((len(sel), 3))

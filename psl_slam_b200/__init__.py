@@ -11,3 +11,4 @@ from .matcher import FrameData, ORBmatcher, hamming_knn2  # noqa: F401
 from .tracking import (convert_rgbd, image_bounds, make_camera, make_distortion, make_track_params,  # noqa: F401
                        track_frontend_batch, track_frontend_batch_dev, track_orb_batch, track_orb_batch_dev,
                        undistort_keypoints)
+from .optimizer import PoseOptimization  # noqa: F401,E402
