@@ -140,6 +140,23 @@ def main():
         "gpu_ms_per_call": call_time(lambda: mi.SearchForInitialization(gl["kps1"], gl["desc1"], k2, gl["prev_matched"], 100)),
         "cpu_oracle_ms_per_call": cpu_time(lambda: orc.match_initialization(gl["kps1"], gl["desc1"], gl["prev_matched"],
                                                                             (gl["kps2"], gl["desc2"]), bnd, 100, 0.9, 50, True))}
+    # --- N4: pose-only optimisation (point edges), 1024 frames x 600 points, device resident ----------------------------
+    from psl_slam_b200._lib import POSE_POINT_DTYPE
+    gp4 = load_golden("pose_case0")
+    npt = len(gp4["pts"])
+    fxp, fyp, cxp, cyp, bfp = (float(v) for v in gp4["cam"])
+    d_pp = torch.from_numpy(np.tile(np.ascontiguousarray(gp4["pts"], POSE_POINT_DTYPE).view(np.uint8).reshape(1, -1), (B, 1))).cuda()
+    d_T0 = torch.from_numpy(np.tile(gp4["Tcw0"].reshape(1, 16), (B, 1))).cuda()
+    d_np = torch.full((B,), npt, dtype=torch.int32, device="cuda")
+    d_T1 = torch.zeros_like(d_T0)
+    d_ol = torch.zeros(B * npt, dtype=torch.uint8, device="cuda")
+    d_ci = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ms = ev_time(lambda: ctx.check(L.psl_pose_optimization_dev(ctx.handle, d_T0.data_ptr(), d_pp.data_ptr(), d_np.data_ptr(), npt, B,
+                                                                C.c_float(fxp), C.c_float(fyp), C.c_float(cxp), C.c_float(cyp),
+                                                                C.c_float(bfp), d_T1.data_ptr(), d_ol.data_ptr(), d_ci.data_ptr())))
+    cpu = cpu_time(lambda: orc.pose_optimization(gp4["Tcw0"], gp4["pts"], fxp, fyp, cxp, cyp, bfp))
+    out["PoseOptimization (point edges), 600 points/frame"] = {"gpu_us_per_frame": ms * 1e3 / B,
+                                                              "cpu_oracle_us_per_frame_1thread": cpu * 1e3}
     print(json.dumps(out, indent=1))
 
 
