@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(256)
 }
 
 constexpr int lsdw_kN2Mask = 0x000FFFFF;  // gx^2 + gy^2 <= 2 * 510^2 < 2^20
-constexpr int lsdw_kUsed = 0x40000000;    // region membership flag, kept in the same word
+constexpr int lsdw_kUnavail = (int)0x80000000;  // same word: not available to region growing (NOTDEF from the start, or USED)
 
 // ll_angle: gradient on the 2x2 stencil, angle in degrees (fastAtan2), squared norm, per-frame maximum
 // and the number of seed-capable pixels per row.  One warp per row.  Each pixel gets one 16-byte record
-// (angle in degrees | cos | sin | squared gradient norm + USED flag) so that region growing needs a single LDG.128 per
+// (angle in degrees | cos | sin | squared gradient norm + flag "not available": NOTDEF or USED) so that region growing needs a single LDG.128 per
 // neighbour: cos / sin are the fp32 values region_grow adds to its running sums, (float)cos((double)(float)angle)
 // (the reference calls cos(float) -> pinned to fp64 evaluation), computed here in parallel instead
 // of inside the sequential loop.
@@ -113,8 +113,9 @@ constexpr int kLutSide = 1021, kLutOff = 510;
 __device__ __forceinline__ float4 lsd_record(int gx, int gy, double rho) {
   float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, 0.f);
   const int q = gx * gx + gy * gy;
-  rec.w = __int_as_float(q);
+  rec.w = __int_as_float(q | lsdw_kUnavail);
   if (!(sqrt((double)q / 4.0) <= rho)) {
+    rec.w = __int_as_float(q);
     rec.x = lsd::fast_atan2((float)gx, (float)-gy);
     const double a = (double)(float)((double)rec.x * lsd::kDegToRad);
     rec.y = (float)cos(a);
@@ -178,14 +179,14 @@ __global__ void __launch_bounds__(128)
   int pos = row_off[(size_t)b * Hs + y];
   for (int x0 = 0; x0 < Ws; x0 += 32) {
     const int x = x0 + lane;
-    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(0));
+    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(lsdw_kUnavail));
     bool def = false;
     int q = 0;
     if (y < Hs - 1 && x < Ws - 1) {
       const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
       const int gx = DA + BC, gy = DA - BC;
       q = gx * gx + gy * gy;
-      rec.w = __int_as_float(q);
+      rec.w = __int_as_float(q | lsdw_kUnavail);
       if (q > q_undef) {  // sqrt(q / 4) > rho  <=>  q > q_undef (largest q with sqrt(q / 4.0) <= rho, found on the host)
         rec = __ldg(lut + (gy + kLutOff) * kLutSide + (gx + kLutOff));
         def = true;
@@ -237,11 +238,16 @@ __global__ void __launch_bounds__(32)
 // The sequential core, one frame per warp.  Region growing is order dependent (every accepted pixel moves
 // the region angle the next neighbour is tested against), so the warp does not split the region; it
 // evaluates the next <= 32 neighbour tests of the reference's loop at once (the 8 neighbours of up to
-// four consecutive region points, lane order = loop order), accepts the first aligned one, updates the
-// angle, and re-evaluates only the lanes after it — exactly the sequence of decisions of the scalar loop
-// (lsd_core.cuh, which the CPU suite checks against the oracle) with the loads and the per-pixel arithmetic
-// done 32-wide.  The fp64 running sums of region2rect / refine are added in the reference's order
-// (one lane-ordered shuffle chain), the extents are exact min/max reductions.
+// four consecutive region points, lane order = loop order) and commits a whole step when that is provably
+// what the scalar loop (lsd_core.cuh, which the CPU suite checks against the oracle) would have done; any
+// other step replays the scalar loop.  The fp64 running sums of region2rect / refine are added in the
+// reference's order, the extents are exact min/max reductions.
+//
+// The kernel is bound by instruction issue and instruction fetch (one warp per frame, about 27 warps per SM at
+// different places of the code), so it is written for few and compact instructions: every device function below has
+// exactly one inlined call site (the refine / reduce stages loop back into the same region_grow and region2rect),
+// and what runs rarely — the scalar replay of a step, the preparation of a re-grow, the radius reduction, the exact
+// seed terms — sits in __noinline__ functions outside the hot loops.
 // ---------------------------------------------------------------------------------------------------
 #ifdef PSL_LSD_STATS
 __device__ unsigned long long g_lsd_stats[16];
@@ -263,16 +269,15 @@ using lsd::kNotDefDeg;
 using lsd::kPi;
 
 constexpr int kRing = 1024;  // region points kept in shared memory (the BFS frontier and small regions)
+constexpr unsigned kFull = 0xffffffffu;
 
 struct Frame {
-  int W, H;
-  float4* pix;
+  int W;
+  float4* pix;      // records; W + 1 unavailable records precede the frame (the last row of the previous frame or the pad)
   uint32_t* reg;    // region points in HBM, packed y << 16 | x
   uint32_t* ring;   // the last kRing of them in shared memory
   double* terms;    // [3][32] staging of the fp64 terms that are summed in list order
 };
-
-constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
 __device__ __forceinline__ int* flags_of(const Frame& f, int idx) { return reinterpret_cast<int*>(f.pix + idx) + 3; }
@@ -280,6 +285,7 @@ __device__ __forceinline__ int* flags_of(const Frame& f, int idx) { return reint
 __device__ __forceinline__ uint32_t reg_at(const Frame& f, int i, int n) {
   return (n - i <= kRing) ? f.ring[i & (kRing - 1)] : f.reg[i];
 }
+__device__ __forceinline__ int lin_of(const Frame& f, uint32_t c) { return (int)(c >> 16) * f.W + (int)(c & 0xFFFFu); }
 
 __device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec) {
   double n_theta = theta - (double)deg * kDegToRad;
@@ -291,68 +297,42 @@ __device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec
   return n_theta <= prec;
 }
 
-// the <= 32 neighbour tests of up to four consecutive region points, one per lane in loop order
+// One neighbour test: the pixel `off` away from region point c.  A region point has a defined angle, so it is not in
+// the last row / column (ll_angle leaves them NOTDEF) and its neighbours can leave the image only at the top / left:
+// x = -1 lands on the last pixel of the row above and y = -1 on the row before the frame, all of them unavailable
+// records (NOTDEF carries the same flag as USED), so no bounds test is needed.
 struct Nbr {
-  int nidx;       // pixel index, -1 = outside the image / idle lane
-  uint32_t npk;   // packed y << 16 | x
+  int lin;        // pixel index
+  uint32_t npk;   // packed y << 16 | x (meaningless for a neighbour outside the image, which is never accepted)
   float4 rec;     // pixel record
-  bool cand;      // unused and with a defined angle when it was loaded
+  bool cand;      // available (not USED, defined angle) when it was loaded
 };
 
-__device__ __forceinline__ Nbr load_nbr_at(const Frame& f, bool active, uint32_t c, int ox, int oy) {
-  Nbr b{-1, 0u, make_float4(kNotDefDeg, 0.f, 0.f, 0.f), false};
+__device__ __forceinline__ Nbr load_nbr(const Frame& f, bool active, uint32_t c, int off, uint32_t offpk) {
+  Nbr b;
+  b.lin = lin_of(f, c) + off;
+  b.npk = c + offpk;
+  b.rec = make_float4(0.f, 0.f, 0.f, 0.f);
+  b.cand = false;
   if (active) {
-    const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
-    // a region point has a defined angle, so it is not in the last row / column (ll_angle leaves them NOTDEF):
-    // its neighbours can only leave the image at the top / left
-    if ((xx | yy) >= 0) {
-      b.nidx = yy * f.W + xx;
-      b.npk = ((uint32_t)yy << 16) | (uint32_t)xx;
-      b.rec = f.pix[b.nidx];
-      b.cand = !(__float_as_int(b.rec.w) & lsdw_kUsed) && b.rec.x != kNotDefDeg;
-    }
+    b.rec = f.pix[b.lin];
+    b.cand = __float_as_int(b.rec.w) >= 0;
   }
   return b;
 }
 
-__device__ __forceinline__ Nbr load_nbr(const Frame& f, int first, int m, int n, int p, int ox, int oy) {
-  Nbr b{-1, 0u, make_float4(kNotDefDeg, 0.f, 0.f, 0.f), false};
-  if (p < m) {
-    const uint32_t c = reg_at(f, first + p, n);
-    const int xx = (int)(c & 0xFFFFu) + ox, yy = (int)(c >> 16) + oy;
-    if (xx >= 0 && xx < f.W && yy >= 0 && yy < f.H) {
-      b.nidx = yy * f.W + xx;
-      b.npk = ((uint32_t)yy << 16) | (uint32_t)xx;
-      b.rec = f.pix[b.nidx];
-      b.cand = !(__float_as_int(b.rec.w) & lsdw_kUsed) && b.rec.x != kNotDefDeg;
-    }
-  }
-  return b;
-}
-
-// region_grow; returns the region size, reg_angle out.
-//
-// The serial chain of the reference is  accept -> sums -> reg_angle = fastAtan2(sums) -> test next neighbour.
-// Two things shorten it without changing a single decision:
-//  * the alignment test |angle_i - reg_angle| <= prec is first made on the sums themselves
-//    (cos_i * sumdx + sin_i * sumdy against cos(prec -/+ 0.5 deg) * |sum|): fastAtan2 is within 0.01 deg of the
-//    true angle and the fp32 dot product within 1e-6, so outside the +/- 0.5 deg band the outcome is certain;
-//    only a neighbour inside the band takes the exact path (fastAtan2 of the sums + the fp64 comparison);
-//  * a whole step (<= 32 tests) is decided at once when that is provably what the scalar loop would do:
-//    guess the accepted set A from the sums before the step, give every lane the sums it would see in the
-//    scalar loop (the prefix over the lanes of A before it), and re-test; if every lane's outcome under its own
-//    prefix is certain and reproduces A, then A is the scalar loop's result by induction over the lanes.  The
-//    prefix only feeds the certain / uncertain classification; the running sums themselves are then advanced
-//    by the accepted terms in lane order, i.e. with the reference's fp32 rounding.  Any other step replays the
-//    scalar loop.
-// thresholds of the quick alignment test for a precision `prec` (see region_grow)
+// thresholds of the quick alignment test for a precision `prec`.
+// The reference tests |angle_i - reg_angle| <= prec with reg_angle = fastAtan2(sums).  fastAtan2 is within 0.0096 deg
+// of the true angle (measured over 2e7 directions) and the fp32 dot product of a record's (cos, sin) with the sums is
+// good to 1e-6 relative, i.e. 2e-4 deg at 22.5 deg; with a band of +/- 0.03 deg around prec the outcome of the
+// reference's test is certain outside the band, and only a neighbour inside it takes the exact path.
 struct Quick {
   bool quick;
   float chi2, clo2;
 };
 
-__device__ __forceinline__ Quick make_quick(double prec) {
-  const double band = 0.5 * kDegToRad;
+__device__ __noinline__ Quick make_quick(double prec) {
+  const double band = 0.03 * kDegToRad;
   Quick q;
   q.quick = prec + band < 1.5 && prec > band;   // both cosines positive: the test can be made on squares
   const float chi = q.quick ? (float)cos(prec - band) : 2.f;   // dot >= chi * |sum|: aligned for sure
@@ -362,197 +342,191 @@ __device__ __forceinline__ Quick make_quick(double prec) {
   return q;
 }
 
-struct Grow {
-  float sumdx, sumdy, s2;
-  double reg_angle;
-  bool angle_valid;
+// The reference seeds the running sums with (float)cos(reg_angle), (float)sin(reg_angle) of the seed's fp64 angle.
+// Those values only matter once a second pixel joins (most seeds grow nothing), so they are evaluated at the first
+// accept; until then the quick test runs on the record's cos / sin (same direction to 1e-7).
+__device__ __noinline__ float2 seed_terms(float deg) {
+  double sd, cd;
+  sincos((double)deg * kDegToRad, &sd, &cd);   // same values as sin() / cos()
+  return make_float2((float)cd, (float)sd);
+}
+
+struct Sums {
+  float x, y;
   int n;
 };
 
-__device__ __forceinline__ void accept_terms(const Frame& f, Grow& g, const Nbr& cur, unsigned A, int lane) {
-  if (g.n == 1) {  // first accept of the region: the exact seed terms (see region_grow)
-    double sd, cd;
-    sincos(g.reg_angle, &sd, &cd);   // one range reduction for both (same values as sin() / cos())
-    g.sumdx = (float)cd;
-    g.sumdy = (float)sd;
-  }
-  if (A >> lane & 1u) {
-    const int at = g.n + __popc(A & ((1u << lane) - 1u));
-    *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
-    f.reg[at] = cur.npk;
-    f.ring[at & (kRing - 1)] = cur.npk;
-  }
-  g.n += __popc(A);
-  for (unsigned a = A; a; a &= a - 1) {  // lane order = the reference's order of additions
-    const int j = __ffs(a) - 1;
-    g.sumdx += __shfl_sync(kFull, cur.rec.y, j);
-    g.sumdy += __shfl_sync(kFull, cur.rec.z, j);
-  }
-  g.s2 = g.sumdx * g.sumdx + g.sumdy * g.sumdy;
-  g.angle_valid = false;
-}
-
-// the scalar loop over the lanes of one step
-__device__ void step_sequential(const Frame& f, Grow& g, Nbr& cur, double prec, bool quick, float chi2, float clo2,
-                                int lane) {
-  unsigned mask = __ballot_sync(kFull, cur.cand);
+// The scalar loop over the lanes of one step (the reference's order of tests), for the steps the batched decision cannot
+// prove.  Accepted pixels get their flag, list and ring entries here.  `exact` says whether the sums already are the
+// reference's (false until the first accept of the region).
+__device__ __noinline__ Sums step_sequential(Frame f, int lin, uint32_t npk, float4 rec, bool cand, Sums s, bool exact,
+                                             float seed_deg, double prec, Quick qk, int lane) {
+  unsigned mask = __ballot_sync(kFull, cand);
   while (mask) {
-    const float dot = cur.rec.y * g.sumdx + cur.rec.z * g.sumdy, dot2 = dot * dot;
-    const bool sure = quick && g.s2 > 1e-6f;   // opposing gradients cancelled: no direction to test against
-    bool ok = cur.cand && sure && dot > 0.f && dot2 >= chi2 * g.s2;
-    const bool maybe = cur.cand && !ok && (!sure || (dot > 0.f && dot2 > clo2 * g.s2));
+    const float s2 = s.x * s.x + s.y * s.y;
+    const float dot = rec.y * s.x + rec.z * s.y, dot2 = dot * dot;
+    const bool sure = qk.quick && s2 > 1e-6f;   // opposing gradients cancelled: no direction to test against
+    bool ok = cand && sure && dot > 0.f && dot2 >= qk.chi2 * s2;
+    const bool maybe = cand && !ok && (!sure || (dot > 0.f && dot2 > qk.clo2 * s2));
     if (__ballot_sync(kFull, maybe) & mask) {
-      if (!g.angle_valid) {
-        g.reg_angle = (double)lsd::fast_atan2(g.sumdy, g.sumdx) * kDegToRad;
-        g.angle_valid = true;
-      }
-      if (maybe) ok = aligned_deg(cur.rec.x, g.reg_angle, prec);
+      const double reg_angle = exact ? (double)lsd::fast_atan2(s.y, s.x) * kDegToRad : (double)seed_deg * kDegToRad;
+      if (maybe) ok = aligned_deg(rec.x, reg_angle, prec);
     }
     const unsigned am = __ballot_sync(kFull, ok) & mask;
     if (!am) break;
     const int j = __ffs(am) - 1;
-    const int aidx = __shfl_sync(kFull, cur.nidx, j);
-    accept_terms(f, g, cur, 1u << j, lane);
-    if (cur.nidx == aidx) cur.cand = false;   // the same pixel seen from another centre is now USED
+    if (!exact) {
+      const float2 e = seed_terms(seed_deg);
+      s.x = e.x;
+      s.y = e.y;
+      exact = true;
+    }
+    if (lane == j) {
+      *flags_of(f, lin) = __float_as_int(rec.w) | lsdw_kUnavail;
+      f.reg[s.n] = npk;
+      f.ring[s.n & (kRing - 1)] = npk;
+    }
+    s.n += 1;
+    s.x += __shfl_sync(kFull, rec.y, j);
+    s.y += __shfl_sync(kFull, rec.z, j);
+    const int alin = __shfl_sync(kFull, lin, j);
+    if (lin == alin) cand = false;            // the same pixel seen from another centre is now USED
     mask &= ~((2u << j) - 1u);                // tests before j were made (and failed) with the older sums
   }
+  return s;
 }
 
-// reg_angle out is defined only for regions of at least min_n points (smaller ones are dropped by every caller)
-__device__ int region_grow(const Frame& f, int seed, int sx, int sy, float4 srec, double& reg_angle, double prec,
-                           const Quick qk, int min_n, int lane) {
-  Grow g;
-  g.reg_angle = (double)srec.x * kDegToRad;
-  // The reference seeds the sums with (float)cos(reg_angle) of the fp64 angle; that value only matters once a
-  // second pixel joins (most seeds grow nothing), so it is evaluated at the first accept.  Until then the
-  // quick test runs on the record's cos / sin (same direction to 1e-7) and the exact test on reg_angle itself.
-  g.sumdx = srec.y;
-  g.sumdy = srec.z;
-  g.s2 = g.sumdx * g.sumdx + g.sumdy * g.sumdy;
-  g.angle_valid = true;
-  g.n = 1;
-  const uint32_t c0 = ((uint32_t)sy << 16) | (uint32_t)sx;
+// region_grow; returns the region size, reg_angle out (defined only for regions of at least min_n points; smaller
+// ones are dropped by every caller).
+//
+// The serial chain of the reference is  accept -> sums -> reg_angle = fastAtan2(sums) -> test next neighbour.
+//  * The alignment test is first made on the sums themselves (cos_i * sumdx + sin_i * sumdy against
+//    cos(prec -/+ band) * |sum|, see make_quick); only a neighbour inside the band needs the exact path.
+//  * A whole step (<= 32 tests) is decided at once when that is provably what the scalar loop would do: guess the
+//    accepted set A from the sums before the step, give every lane the sums it would see in the scalar loop (the
+//    prefix over the lanes of A before it) and re-test; if every lane's outcome under its own prefix is certain and
+//    reproduces A, then A is the scalar loop's result by induction over the lanes.  The prefix only feeds the
+//    certain / uncertain classification; the running sums themselves are advanced by the accepted terms in lane
+//    order, i.e. with the reference's fp32 rounding.
+//  * The guess is committed speculatively (flags, ring and list entries) and the records of the next step's
+//    neighbours are requested BEFORE the guess is verified, so the verification runs under the load latency and the
+//    next step needs no second look at what this step accepted (its loads already see the flags).  A refuted guess
+//    (a few percent of the steps) takes the flags back and replays the step with the scalar loop.
+__device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_t c0, float4 srec, double& reg_angle,
+                                           double prec, const Quick qk, int min_n, int lane) {
   // four region points per step, eight lanes each: the centre of a 3x3 neighbourhood is the region point itself
   // (USED, never a candidate), so the loop's nine tests are the eight below in the same order
   const int p = lane >> 3, k8 = lane & 7, k = k8 + (k8 >= 4);
   const int oy = k / 3 - 1, ox = k - 3 * (k / 3) - 1;
-  // the seed's neighbours are requested before the seed is written back (none of them is the seed's own record
-  // as a candidate: the centre lane is struck below)
-  Nbr cur = load_nbr_at(f, p == 0, c0, ox, oy);
-  if (cur.nidx == seed) cur.cand = false;
+  const int off = oy * f.W + ox;
+  const uint32_t offpk = (uint32_t)(oy * 65536 + ox);
+  const unsigned lt = (1u << lane) - 1u;
+  Sums s{srec.y, srec.z, 1};
+  bool exact = false;
   if (lane == 0) {
     f.reg[0] = c0;
     f.ring[0] = c0;
-    *flags_of(f, seed) = __float_as_int(srec.w) | lsdw_kUsed;
+    *flags_of(f, seed_lin) = __float_as_int(srec.w) | lsdw_kUnavail;
   }
+  Nbr cur = load_nbr(f, p == 0, c0, off, offpk);   // none of the eight is the seed itself
   __syncwarp();
-  const bool quick = qk.quick;
-  const float chi2 = qk.chi2, clo2 = qk.clo2;
-  const unsigned lt = (1u << lane) - 1u;
-  // Software pipeline: the records of the next step's neighbours are requested as soon as the accepted set of
-  // the current step is known (its region points are the next entries of the list), i.e. before the flag /
-  // list stores and the ordered sum update of the current step; pixels accepted in the current step are
-  // struck from the prefetched set by index.
   int i = 0, m = 1;
-  while (true) {
-    i += m;                       // first region point of the next step
+  for (;;) {
     LSD_STAT(0, 1);
     LSD_STAT(1, m);
-    const unsigned cm = __ballot_sync(kFull, cur.cand);
-    bool batched = false;
-    unsigned A = 0;
-    float new_dx = 0.f, new_dy = 0.f;
-    if (!cm) {
-      batched = true;
-    } else if (quick && g.s2 > 1e-6f) {
-      // guess: the lanes that pass under the sums before the step (first lane of every repeated pixel)
-      const float dot = cur.rec.y * g.sumdx + cur.rec.z * g.sumdy;
-      const bool yes0 = cur.cand && dot > 0.f && dot * dot >= chi2 * g.s2;
-      A = __ballot_sync(kFull, yes0);
-      unsigned same = 1u << lane;   // cand lanes holding the same pixel (only possible across centres)
-      if (m > 1) {
-        if (cur.cand) same = __match_any_sync(cm, cur.nidx);
-        A = __ballot_sync(kFull, yes0 && !(same & A & lt));
-      }
-      if (A == 0) {
-        // nobody passes under the current sums; certain for all only if no lane sits in the band
-        const bool maybe0 = cur.cand && !yes0 && dot > 0.f && dot * dot > clo2 * g.s2;
-        batched = !__any_sync(kFull, maybe0);
-      } else {
-        // the sums every lane would see in the scalar loop: the running sums advanced by the lanes of A before
-        // it, added in lane order with the reference's fp32 rounding (lane 31 ends with the sums after the step)
-        float Px = g.sumdx, Py = g.sumdy;
-        if (g.n == 1) {  // first accept of the region: the exact seed terms (see above)
-          double sd, cd;
-          sincos(g.reg_angle, &sd, &cd);
-          Px = (float)cd;
-          Py = (float)sd;
-        }
-        for (unsigned a = A; a; a &= a - 1) {
-          const int j = __ffs(a) - 1;
-          const float vx = __shfl_sync(kFull, cur.rec.y, j), vy = __shfl_sync(kFull, cur.rec.z, j);
-          if (lane > j) { Px += vx; Py += vy; }
-        }
-        const float d1 = cur.rec.y * Px + cur.rec.z * Py, q1 = Px * Px + Py * Py;
-        const bool sure1 = q1 > 1e-6f;
-        const bool yes1 = cur.cand && sure1 && d1 > 0.f && d1 * d1 >= chi2 * q1;
-        const bool no1 = !cur.cand || (sure1 && (d1 <= 0.f || d1 * d1 <= clo2 * q1));
-        const bool taken = (same & A & lt) != 0;       // an earlier lane of A holds this pixel: USED by then
-        const bool expect = yes1 && !taken;
-        const bool certain = taken || yes1 || no1;
-        const unsigned E = __ballot_sync(kFull, expect);
-        batched = __all_sync(kFull, certain) && E == A;
-        if (batched) {
-          // lane 31's prefix misses its own term when it is accepted itself (the last addition of the step)
-          const bool last = (A >> 31) != 0u;
-          new_dx = __shfl_sync(kFull, last ? Px + cur.rec.y : Px, 31);
-          new_dy = __shfl_sync(kFull, last ? Py + cur.rec.z : Py, 31);
-        }
-      }
+    const int i_next = i + m;   // first region point of the next step
+    const float s2 = s.x * s.x + s.y * s.y;
+    const bool fast = qk.quick && s2 > 1e-6f;
+    const float dot = cur.rec.y * s.x + cur.rec.z * s.y, dot2 = dot * dot;
+    const bool pos = cur.cand && dot > 0.f;
+    const bool yes0 = fast && pos && dot2 >= qk.chi2 * s2;
+    const bool unsure0 = cur.cand && !yes0 && (!fast || (pos && dot2 > qk.clo2 * s2));
+    const unsigned A0 = __ballot_sync(kFull, yes0), U0 = __ballot_sync(kFull, unsure0);
+    // guess: the lanes that pass under the sums before the step, first lane of every repeated pixel (the same pixel can
+    // only be seen from two centres; all its lanes hold the same record, so they pass together)
+    unsigned A = A0;
+    bool first = true;
+    if (A0 != 0u && m > 1) {
+      if (yes0) first = (__match_any_sync(A0, cur.lin) & lt) == 0u;
+      A = __ballot_sync(kFull, yes0 && first);
     }
-    if (batched) {
-      const int n_old = g.n, n_new = n_old + __popc(A);
-      if (i >= n_new) break;      // the list is exhausted (A is empty here)
-      // the accepted points go to the shared mirror of the list first: the region points i .. i+3 of the next step
-      // are then read from it whether they are old entries or were accepted just now
-      const int at = n_old + __popc(A & lt);
-      if (A >> lane & 1u) f.ring[at & (kRing - 1)] = cur.npk;
-      __syncwarp();
-      const int m2 = min(4, n_new - i);
-      uint32_t c = 0;
-      if (p < m2) c = reg_at(f, i + p, n_new);
-      Nbr nxt = load_nbr_at(f, p < m2, c, ox, oy);
-      if (A) {
-        if (A >> lane & 1u) {
-          *flags_of(f, cur.nidx) = __float_as_int(cur.rec.w) | lsdw_kUsed;
-          f.reg[at] = cur.npk;
-        }
-        for (unsigned a = A; a; a &= a - 1) {  // records loaded before these flag stores: strike what just became USED
-          const int aidx = __shfl_sync(kFull, cur.nidx, __ffs(a) - 1);
-          if (nxt.nidx == aidx) nxt.cand = false;
-        }
-        g.n = n_new;
-        g.sumdx = new_dx;
-        g.sumdy = new_dy;
-        g.s2 = new_dx * new_dx + new_dy * new_dy;
-        g.angle_valid = false;
-      }
-      cur = nxt;
-      m = m2;
-    } else {
-      LSD_STAT(7, 1);
-      step_sequential(f, g, cur, prec, quick, chi2, clo2, lane);
-      if (i >= g.n) break;
-      __syncwarp();
-      m = min(4, g.n - i);
-      cur = load_nbr(f, i, m, g.n, p, ox, oy);
+    const bool inA = (A >> lane) & 1u;
+    const int at = s.n + __popc(A & lt), n_spec = s.n + __popc(A);
+    if (inA) {   // speculative commit
+      *flags_of(f, cur.lin) = __float_as_int(cur.rec.w) | lsdw_kUnavail;
+      f.ring[at & (kRing - 1)] = cur.npk;
+      f.reg[at] = cur.npk;
     }
     __syncwarp();
+    const int m2 = min(4, n_spec - i_next);   // <= 0: the list ends with this step
+    Nbr nxt;
+    {
+      uint32_t c = 0;
+      if (p < m2) c = reg_at(f, i_next + p, n_spec);
+      nxt = load_nbr(f, p < m2, c, off, offpk);
+    }
+    // verification, under the latency of those loads
+    bool proven;
+    float nx = s.x, ny = s.y;
+    if (A == 0u) {
+      proven = U0 == 0u;   // nobody passes under the current sums; certain for all only if no lane sits in the band
+    } else {
+      // the sums every lane would see in the scalar loop: the running sums advanced by the lanes of A before it, added
+      // in lane order with the reference's fp32 rounding (lane 31 ends with the sums after the step)
+      float Px = s.x, Py = s.y;
+      if (!exact) {
+        const float2 e = seed_terms(srec.x);
+        Px = e.x;
+        Py = e.y;
+      }
+      for (unsigned a = A; a; a &= a - 1) {
+        const int j = __ffs(a) - 1;
+        const float vx = __shfl_sync(kFull, cur.rec.y, j), vy = __shfl_sync(kFull, cur.rec.z, j);
+        if (lane > j) { Px += vx; Py += vy; }
+      }
+      const float d1 = cur.rec.y * Px + cur.rec.z * Py, q1 = Px * Px + Py * Py;
+      const bool sure1 = q1 > 1e-6f;
+      const bool yes1 = sure1 && d1 > 0.f && d1 * d1 >= qk.chi2 * q1;
+      const bool no1 = sure1 && (d1 <= 0.f || d1 * d1 <= qk.clo2 * q1);
+      // an earlier lane of A holds this pixel: USED by the time the scalar loop gets here
+      const bool taken = yes0 && !first;
+      const bool lane_ok = !cur.cand || taken || (inA ? yes1 : no1);
+      proven = __all_sync(kFull, lane_ok);
+      // lane 31's prefix misses its own term when it is accepted itself (the last addition of the step)
+      const bool last = (A >> 31) != 0u;
+      nx = __shfl_sync(kFull, last ? Px + cur.rec.y : Px, 31);
+      ny = __shfl_sync(kFull, last ? Py + cur.rec.z : Py, 31);
+    }
+    if (proven) {
+      if (A != 0u) {
+        s.x = nx;
+        s.y = ny;
+        s.n = n_spec;
+        exact = true;
+      }
+      i = i_next;
+      if (m2 <= 0) break;
+      m = m2;
+      cur = nxt;
+    } else {
+      LSD_STAT(7, 1);
+      if (inA) *flags_of(f, cur.lin) = __float_as_int(cur.rec.w);   // take the guess back
+      __syncwarp();
+      s = step_sequential(f, cur.lin, cur.npk, cur.rec, cur.cand, s, exact, srec.x, prec, qk, lane);
+      exact = exact || s.n > 1;
+      i = i_next;
+      if (i >= s.n) break;
+      __syncwarp();
+      m = min(4, s.n - i);
+      uint32_t c = 0;
+      if (p < m) c = reg_at(f, i + p, s.n);
+      cur = load_nbr(f, p < m, c, off, offpk);
+    }
   }
-  if (!g.angle_valid && g.n >= min_n) g.reg_angle = (double)lsd::fast_atan2(g.sumdy, g.sumdx) * kDegToRad;
-  reg_angle = g.reg_angle;
+  if (s.n >= min_n)
+    reg_angle = exact ? (double)lsd::fast_atan2(s.y, s.x) * kDegToRad : (double)srec.x * kDegToRad;
   __syncwarp();
-  return g.n;
+  return s.n;
 }
 
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy; };
@@ -561,10 +535,23 @@ __device__ __forceinline__ double modgrad(const Frame& f, int idx) {
   return sqrt((double)(*flags_of(f, idx) & lsdw_kN2Mask) / 4.0);
 }
 
-__device__ void region2rect(const Frame& f, int n, double reg_angle, double prec, Rect& rec, int lane) {
-  // weighted centroid: x += px * w ... in list order.  The three running sums are independent chains: lane 0, 1 and 2
-  // each add one of them (one load + one add per term for the warp instead of three of each).
+// one ordered pass: the 32 terms of three running sums go through shared memory and lanes 0, 1, 2 each add one of
+// them in list order (a broadcast read + one add per term)
+__device__ __forceinline__ void ordered_add3(const Frame& f, double t0, double t1, double t2, int cnt, double& acc, int lane) {
+  __syncwarp();
+  f.terms[lane] = t0; f.terms[32 + lane] = t1; f.terms[64 + lane] = t2;
+  __syncwarp();
   const double* chain = f.terms + 32 * (lane < 3 ? lane : 0);
+  int k = 0;
+  for (; k + 4 <= cnt; k += 4) {
+    const double2 a = *reinterpret_cast<const double2*>(chain + k), b = *reinterpret_cast<const double2*>(chain + k + 2);
+    acc += a.x; acc += a.y; acc += b.x; acc += b.y;
+  }
+  for (; k < cnt; ++k) acc += chain[k];
+}
+
+__device__ __forceinline__ void region2rect(const Frame& f, int n, double reg_angle, double prec, Rect& rec, int lane) {
+  // weighted centroid: x += px * w ... in list order
   double acc = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
@@ -576,13 +563,7 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
       tx = (double)px * w;
       ty = (double)py * w;
     }
-    // ordered sums: the 32 terms go through shared memory and every lane adds them in list order (a broadcast
-    // read + one add per term, instead of a shuffle chain)
-    const int cnt = min(32, n - base);
-    __syncwarp();
-    f.terms[lane] = tx; f.terms[32 + lane] = ty; f.terms[64 + lane] = w;
-    __syncwarp();
-    for (int k = 0; k < cnt; ++k) acc += chain[k];
+    ordered_add3(f, tx, ty, w, min(32, n - base), acc, lane);
   }
   double x = shfl_d(acc, 0), y = shfl_d(acc, 1);
   const double sum = shfl_d(acc, 2);
@@ -601,11 +582,7 @@ __device__ void region2rect(const Frame& f, int n, double reg_angle, double prec
       t2 = dx * dx * w;
       t3 = -(dx * dy * w);   // Ixy -= term  ==  Ixy += -term
     }
-    const int cnt = min(32, n - base);
-    __syncwarp();
-    f.terms[lane] = t1; f.terms[32 + lane] = t2; f.terms[64 + lane] = t3;
-    __syncwarp();
-    for (int k = 0; k < cnt; ++k) acc += chain[k];
+    ordered_add3(f, t1, t2, t3, min(32, n - base), acc, lane);
   }
   const double Ixx = shfl_d(acc, 0), Iyy = shfl_d(acc, 1), Ixy = shfl_d(acc, 2);
   const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
@@ -647,51 +624,13 @@ __device__ __forceinline__ double density_of(int n, const Rect& rec) {
   return (double)n / (sqrt(lsd::dist_sq(rec.x1, rec.y1, rec.x2, rec.y2)) * rec.width);
 }
 
-// reduce_region_radius: the swap-with-last removal defines the order of the surviving points (and with it
-// the rounding of the next region2rect), so lane 0 replays it on the HBM list; the rectangle fits stay
-// cooperative.
-__device__ bool reduce_region_radius(const Frame& f, int& n, double reg_angle, double prec, Rect& rec, double density,
-                                     int lane) {
-  const uint32_t c0 = f.reg[0];
-  const double xc = (double)(int)(c0 & 0xFFFFu), yc = (double)(int)(c0 >> 16);
-  const double r1 = lsd::dist_sq(xc, yc, rec.x1, rec.y1), r2 = lsd::dist_sq(xc, yc, rec.x2, rec.y2);
-  double radSq = r1 > r2 ? r1 : r2;
-  while (density < lsd::kDensityTh) {
-    radSq *= 0.75 * 0.75;
-    if (lane == 0) {
-      int m = n;
-      for (int i = 0; i < m; ++i) {
-        const uint32_t c = f.reg[i];
-        const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
-        if (lsd::dist_sq(xc, yc, (double)px, (double)py) > radSq) {
-          *flags_of(f, py * f.W + px) &= ~lsdw_kUsed;
-          f.reg[i] = f.reg[m - 1];
-          f.reg[m - 1] = c;
-          --m;
-          --i;
-        }
-      }
-      n = m;
-    }
-    n = __shfl_sync(kFull, n, 0);
-    __syncwarp();
-    if (n < 2) return false;
-    // the reordered tail goes back to the shared mirror (reg_at reads the last kRing points from it)
-    for (int i = max(0, n - kRing) + lane; i < n; i += 32) f.ring[i & (kRing - 1)] = f.reg[i];
-    __syncwarp();
-    region2rect(f, n, reg_angle, prec, rec, lane);
-    density = density_of(n, rec);
-  }
-  return true;
-}
-
-__device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Rect& rec, int lane) {
-  double density = density_of(n, rec);
-  if (density >= lsd::kDensityTh) return true;
+// refine, first part (rare: the density of a region's first rectangle is below the threshold): release the region's
+// pixels and derive the tolerance tau of the re-grow from the angles near the seed.
+__device__ __noinline__ double refine_tolerance(Frame f, int n, double width, int lane) {
   const uint32_t c0 = f.reg[0];
   const int sx = (int)(c0 & 0xFFFFu), sy = (int)(c0 >> 16);
   const double xc = (double)sx, yc = (double)sy, ang_c = (double)f.pix[sy * f.W + sx].x * kDegToRad;
-  const double* chain = f.terms + 32 * (lane < 2 ? lane : 0);   // lane 0: sum, lane 1: s_sum (see region2rect)
+  const double* chain = f.terms + 32 * (lane < 2 ? lane : 0);   // lane 0: sum, lane 1: s_sum
   double acc = 0;
   int cnt = 0;
   for (int base = 0; base < n; base += 32) {
@@ -702,8 +641,8 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
       const uint32_t c = reg_at(f, i, n);
       const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
       const float4 r = f.pix[py * f.W + px];
-      *flags_of(f, py * f.W + px) = __float_as_int(r.w) & ~lsdw_kUsed;
-      if (sqrt(lsd::dist_sq(xc, yc, (double)px, (double)py)) < rec.width) {
+      *flags_of(f, py * f.W + px) = __float_as_int(r.w) & 0x7FFFFFFF;
+      if (sqrt(lsd::dist_sq(xc, yc, (double)px, (double)py)) < width) {
         a = lsd::angle_diff_signed((double)r.x * kDegToRad, ang_c);
         a2 = a * a;
         in = true;
@@ -719,13 +658,33 @@ __device__ bool refine(const Frame& f, int& n, double reg_angle, double prec, Re
   __syncwarp();
   const double sum = shfl_d(acc, 0), s_sum = shfl_d(acc, 1);
   const double mean_angle = sum / (double)cnt;
-  const double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-  n = region_grow(f, sy * f.W + sx, sx, sy, f.pix[sy * f.W + sx], reg_angle, tau, make_quick(tau), 2, lane);
-  if (n < 2) return false;
-  region2rect(f, n, reg_angle, prec, rec, lane);
-  density = density_of(n, rec);
-  if (density < lsd::kDensityTh) return reduce_region_radius(f, n, reg_angle, prec, rec, density, lane);
-  return true;
+  return 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+}
+
+// reduce_region_radius, one round (rare): the swap-with-last removal defines the order of the surviving points (and
+// with it the rounding of the next region2rect), so lane 0 replays it on the HBM list.  Returns the new size.
+__device__ __noinline__ int reduce_once(Frame f, int n, double xc, double yc, double radSq, int lane) {
+  if (lane == 0) {
+    int m = n;
+    for (int i = 0; i < m; ++i) {
+      const uint32_t c = f.reg[i];
+      const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
+      if (lsd::dist_sq(xc, yc, (double)px, (double)py) > radSq) {
+        *flags_of(f, py * f.W + px) &= 0x7FFFFFFF;
+        f.reg[i] = f.reg[m - 1];
+        f.reg[m - 1] = c;
+        --m;
+        --i;
+      }
+    }
+    n = m;
+  }
+  n = __shfl_sync(kFull, n, 0);
+  __syncwarp();
+  // the reordered tail goes back to the shared mirror (reg_at reads the last kRing points from it)
+  for (int i = max(0, n - kRing) + lane; i < n; i += 32) f.ring[i & (kRing - 1)] = f.reg[i];
+  __syncwarp();
+  return n;
 }
 
 }  // namespace lsdw
@@ -738,7 +697,7 @@ constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never 
 __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
     lsd_core_kernel(LineBuffers L, int nb, uint32_t stride, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
-  __shared__ double terms[kCoreWarps][96];
+  __shared__ __align__(16) double terms[kCoreWarps][96];
   const int wid = threadIdx.x >> 5, slot = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
   if (slot >= nb) return;
   // frame of this warp: a fixed permutation of the batch (stride coprime to nb), so that the warps of one SM hold
@@ -746,52 +705,89 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
   // ones would finish last
   const int b = (int)(((uint64_t)slot * stride) % (uint32_t)nb);
   const size_t npx = (size_t)L.Ws * L.Hs;
-  lsdw::Frame f{L.Ws, L.Hs, L.pix + b * npx, L.reg + b * npx, ring[wid], terms[wid]};
+  const lsdw::Frame f{L.Ws, L.pix + b * npx, L.reg + b * npx, ring[wid], terms[wid]};
   const uint32_t* seeds = L.val_out + b * npx;
   const int n_seeds = L.n_def[b];
   float* out = L.raw + (size_t)b * L.raw_cap * 4;
-  const double prec = lsd::kPi * lsd::kAngTh / 180;
-  const lsdw::Quick qk = lsdw::make_quick(prec);
+  const double prec0 = lsd::kPi * lsd::kAngTh / 180;
+  const lsdw::Quick qk0 = lsdw::make_quick(prec0);
   const float inv_w = 1.0f / (float)L.Ws;
   int nseg = 0;
   LSD_T0(t_all);
   for (int s0 = 0; s0 < n_seeds; s0 += 32) {
     const int my = s0 + lane < n_seeds ? (int)seeds[s0 + lane] : -1;
     // a pixel that is USED now stays USED (only the pixels of the region being refined are ever released)
-    unsigned todo = __ballot_sync(lsdw::kFull, my >= 0 && !(*lsdw::flags_of(f, my >= 0 ? my : 0) & lsdw_kUsed));
+    unsigned todo = __ballot_sync(lsdw::kFull, my >= 0 && *lsdw::flags_of(f, my >= 0 ? my : 0) >= 0);
+    LSD_STAT(4, __popc(todo));
     while (todo) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
       const int seed = __shfl_sync(lsdw::kFull, my, l);
       const float4 srec = f.pix[seed];
-      if (__float_as_int(srec.w) & lsdw_kUsed) continue;
-      double reg_angle;
-      LSD_T0(t_g);
+      if (__float_as_int(srec.w) < 0) { LSD_STAT(5, 1); continue; }
       // seed / W without the integer division: seed < 2^24 and W <= 4096, so the float quotient is off by at most one
       int sy = (int)(((float)seed + 0.5f) * inv_w), sx = seed - sy * f.W;
       if (sx < 0) { --sy; sx += f.W; }
       else if (sx >= f.W) { ++sy; sx -= f.W; }
-      int n = lsdw::region_grow(f, seed, sx, sy, srec, reg_angle, prec, qk, L.min_reg_size, lane);
-      LSD_T1(10, t_g);
-      LSD_STAT(13, 1);
-      if (n < L.min_reg_size) continue;
-      LSD_STAT(2, 1);
-      LSD_STAT(3, n);
-      lsdw::Rect rec;
-      LSD_T0(t_r);
-      lsdw::region2rect(f, n, reg_angle, prec, rec, lane);
-      LSD_T1(11, t_r);
-      LSD_T0(t_f);
-      const bool okr = lsdw::refine(f, n, reg_angle, prec, rec, lane);
-      LSD_T1(12, t_f);
-      if (!okr) continue;
-      rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
-      rec.x1 /= lsd::kScale; rec.y1 /= lsd::kScale; rec.x2 /= lsd::kScale; rec.y2 /= lsd::kScale;
-      if (lane == 0 && nseg < L.raw_cap) {
-        out[4 * nseg] = (float)rec.x1; out[4 * nseg + 1] = (float)rec.y1;
-        out[4 * nseg + 2] = (float)rec.x2; out[4 * nseg + 3] = (float)rec.y2;
+      const uint32_t c0 = ((uint32_t)sy << 16) | (uint32_t)sx;
+      // LineSegmentDetectorImpl::flsd for one seed, with refine (LSD_REFINE_STD) and reduce_region_radius folded into two
+      // loops around ONE region_grow and ONE region2rect:
+      //   stage 0  grow with the global tolerance; too small -> next seed; rectangle; dense enough -> segment
+      //   stage 1  (refine) release the pixels, re-grow with tolerance tau; < 2 points -> next seed; rectangle; dense -> segment
+      //   stage 2+ (reduce_region_radius) shrink the radius by 0.75, drop the points outside; < 2 -> next seed; rectangle; ...
+      double prec = prec0, reg_angle = 0, radSq = 0;
+      lsdw::Quick qk = qk0;
+      int stage = 0, n = 0;
+      bool emit = false;
+      for (;;) {
+        if (stage < 2) {
+          LSD_T0(t_g);
+          n = lsdw::region_grow(f, seed, c0, srec, reg_angle, prec, qk, stage == 0 ? L.min_reg_size : 2, lane);
+          LSD_T1(10, t_g);
+          if (stage == 0) {
+            LSD_STAT(13, 1);
+            if (n == 1) LSD_STAT(6, 1);
+            if (n < L.min_reg_size) { LSD_STAT(9, n); break; }
+            LSD_STAT(2, 1);
+            LSD_STAT(3, n);
+          } else if (n < 2) {
+            break;
+          }
+        }
+        lsdw::Rect rec;
+        LSD_T0(t_r);
+        lsdw::region2rect(f, n, reg_angle, prec0, rec, lane);
+        LSD_T1(11, t_r);
+        const double density = lsdw::density_of(n, rec);
+        if (density >= lsd::kDensityTh) {
+          rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+          rec.x1 /= lsd::kScale; rec.y1 /= lsd::kScale; rec.x2 /= lsd::kScale; rec.y2 /= lsd::kScale;
+          if (lane == 0 && nseg < L.raw_cap) {
+            out[4 * nseg] = (float)rec.x1; out[4 * nseg + 1] = (float)rec.y1;
+            out[4 * nseg + 2] = (float)rec.x2; out[4 * nseg + 3] = (float)rec.y2;
+          }
+          emit = true;
+          break;
+        }
+        LSD_T0(t_f);
+        if (stage == 0) {
+          prec = lsdw::refine_tolerance(f, n, rec.width, lane);
+          qk = lsdw::make_quick(prec);
+          stage = 1;
+        } else {
+          const double xc = (double)sx, yc = (double)sy;
+          if (stage == 1) {
+            const double r1 = lsd::dist_sq(xc, yc, rec.x1, rec.y1), r2 = lsd::dist_sq(xc, yc, rec.x2, rec.y2);
+            radSq = r1 > r2 ? r1 : r2;
+            stage = 2;
+          }
+          radSq *= 0.75 * 0.75;
+          n = lsdw::reduce_once(f, n, xc, yc, radSq, lane);
+          if (n < 2) { LSD_T1(12, t_f); break; }
+        }
+        LSD_T1(12, t_f);
       }
-      ++nseg;
+      if (emit) ++nseg;
     }
   }
   LSD_T1(14, t_all);

@@ -77,8 +77,11 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   uint32_t* dxo = nullptr;
   L.sort_tmp_bytes = lsd_sort_temp_bytes((int)npx, (int)C);
   uint8_t* tmp = nullptr;
+  // the records of the row above a frame must read "not available" (lsd_kernels.cu, load_nbr): for every frame but the
+  // first that row is the previous frame's last one (NOTDEF); the first frame gets Ws + 1 such records in front
+  const size_t pix_pad = ((size_t)L.Ws + 1 + 7) & ~(size_t)7;   // whole 128-byte lines, so the records stay line-aligned
   bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, dxw, (size_t)n4) && lalloc(ctx, dxo, (size_t)n4) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
-            lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx) &&
+            lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx + pix_pad) &&
             lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
             lalloc(ctx, L.key_out, C * npx) && lalloc(ctx, L.val_in, C * npx) && lalloc(ctx, L.val_out, C * npx) &&
@@ -94,6 +97,8 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
     return fail(ctx, PSL_E_CUDA, "line buffers: out of device memory (lower psl_config.line_chunk_frames)");
   }
   L.sort_tmp = tmp;
+  PSL_CK(cudaMemsetAsync(L.pix, 0xFF, pix_pad * sizeof(float4), ctx->stream));
+  L.pix += pix_pad;
   L.lut = reinterpret_cast<const float4*>(lut);
   launch_lsd_lut(reinterpret_cast<float4*>(lut), ctx->stream);
   L.xtab = dx;

@@ -52,7 +52,7 @@ def _stats():
             z2 = (C.c_ulonglong * 16)()
             L.psl_post_stats(z2)
             print("post stats cyc [sort, scan, cluster, fold, total]:", list(z2)[:5])
-        print("lsd stats [0 steps, 1 cyc guess, 2 cyc verify, 3 cyc accept, 4 cyc sync, 5 cyc seq, 6 -, 7 nseq | cyc: 8 load, 9 decide, 10 grow, 11 rect, 12 refine, 13 regions, 14 total]:", list(z)[:16])
+        print("lsd stats [0 steps, 1 region points visited, 2 regions>=min, 3 their pixels, 4 seeds unused at ballot, 5 of those used at their turn, 6 singleton regions, 7 sequential steps, 9 pixels of small regions | cyc: 10 grow, 11 rect, 12 refine, 13 regions grown, 14 total, 15 slowest frame]:", list(z)[:16])
 
 
 if __name__ == "__main__":
