@@ -468,6 +468,14 @@ def line_search_double(d1, d2, nn_ratio, th):
     return out, int(n)
 
 
+def line_grid_cells(view, line):
+    """Grid cells (cx * 48 + cy) a key line is registered in, Frame::AssignFeaturesToGridForLine order."""
+    out = np.zeros(4096, np.int32)
+    n = lib().orc_line_grid_cells(C.byref(view), int(line), _p(out), len(out))
+    assert n <= len(out)
+    return out[:n]
+
+
 def lines_in_area(view, x1, y1, x2, y2, r, TH):
     out = np.zeros(max(view.n, 1), np.int32)
     n = lib().orc_lines_in_area(C.byref(view), C.c_float(x1), C.c_float(y1), C.c_float(x2), C.c_float(y2),

@@ -18,7 +18,8 @@ struct LineBuffers {
   uint8_t* blur;       // [C][h][pitch]   7x7 sigma 0.75 (LSD) and, later, 5x5 sigma 1 (LBD)
   uint8_t* scaled;     // [C][Hs][Ws]
   const float4* lut;   // [1021*1021] pixel record of every integer gradient (gx, gy)
-  float4* pix;         // [C][Hs*Ws]  (angle in degrees | cos | sin | int bits: squared gradient norm + USED flag)
+  const float2* seed_lut;  // [1021*1021] (float)cos / (float)sin of the fp64 angle: the sums a region starts with
+  float4* pix;         // [C][Hs*Ws]  (angle in degrees | cos | sin | int bits: integer gradient + "not available" flag)
   uint32_t* reg;       // [C][Hs*Ws]
   int32_t* max_n2;     // [C]
   int32_t* row_cnt;    // [C][Hs]  defined pixels per row -> exclusive offsets
@@ -53,7 +54,8 @@ struct LineBuffers {
 
 size_t lsd_sort_temp_bytes(int items_per_frame, int frames);
 size_t lsd_lut_bytes();
-void launch_lsd_lut(float4* lut, cudaStream_t st);
+size_t lsd_seed_lut_bytes();
+void launch_lsd_lut(float4* lut, float2* seed_lut, cudaStream_t st);
 
 // LSD for `nb` frames (cv::LineSegmentDetector behind LineExtractor.cpp:336-337), three stages:
 // blur + 0.8x resize + gradient + seed keys (6 launches); stable seed ordering (cub segmented radix sort, counted as 1);

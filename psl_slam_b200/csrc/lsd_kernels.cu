@@ -96,12 +96,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-constexpr int lsdw_kN2Mask = 0x000FFFFF;  // gx^2 + gy^2 <= 2 * 510^2 < 2^20
+constexpr int lsdw_kGMask = 0x000FFFFF;   // the integer gradient of the pixel, (gy + 510) << 10 | (gx + 510)
 constexpr int lsdw_kUnavail = (int)0x80000000;  // same word: not available to region growing (NOTDEF from the start, or USED)
+__host__ __device__ __forceinline__ int lsdw_pack_g(int gx, int gy) { return ((gy + 510) << 10) | (gx + 510); }
+// gx^2 + gy^2 of a record's int word (modgrad = sqrt(that / 4.0))
+__device__ __forceinline__ int lsdw_n2(int w) {
+  const int gx = (w & 1023) - 510, gy = ((w >> 10) & 1023) - 510;
+  return gx * gx + gy * gy;
+}
 
 // ll_angle: gradient on the 2x2 stencil, angle in degrees (fastAtan2), squared norm, per-frame maximum
 // and the number of seed-capable pixels per row.  One warp per row.  Each pixel gets one 16-byte record
-// (angle in degrees | cos | sin | squared gradient norm + flag "not available": NOTDEF or USED) so that region growing needs a single LDG.128 per
+// (angle in degrees | cos | sin | integer gradient + flag "not available": NOTDEF or USED) so that region growing needs a single LDG.128 per
 // neighbour: cos / sin are the fp32 values region_grow adds to its running sums, (float)cos((double)(float)angle)
 // (the reference calls cos(float) -> pinned to fp64 evaluation), computed here in parallel instead
 // of inside the sequential loop.
@@ -110,25 +116,32 @@ constexpr int lsdw_kUnavail = (int)0x80000000;  // same word: not available to r
 // fastAtan2 + fp64 cos / sin per pixel.
 constexpr int kLutSide = 1021, kLutOff = 510;
 
-__device__ __forceinline__ float4 lsd_record(int gx, int gy, double rho) {
+__device__ __forceinline__ float4 lsd_record(int gx, int gy, double rho, float2& seed) {
   float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, 0.f);
   const int q = gx * gx + gy * gy;
-  rec.w = __int_as_float(q | lsdw_kUnavail);
+  rec.w = __int_as_float(lsdw_pack_g(gx, gy) | lsdw_kUnavail);
+  seed = make_float2(0.f, 0.f);
   if (!(sqrt((double)q / 4.0) <= rho)) {
-    rec.w = __int_as_float(q);
+    rec.w = __int_as_float(lsdw_pack_g(gx, gy));
     rec.x = lsd::fast_atan2((float)gx, (float)-gy);
     const double a = (double)(float)((double)rec.x * lsd::kDegToRad);
     rec.y = (float)cos(a);
     rec.z = (float)sin(a);
+    // what region_grow starts its running sums with when this pixel is the seed: cos / sin of the fp64 angle
+    double sd, cd;
+    sincos((double)rec.x * lsd::kDegToRad, &sd, &cd);
+    seed = make_float2((float)cd, (float)sd);
   }
   return rec;
 }
 
-__global__ void __launch_bounds__(256) lsd_lut_kernel(float4* __restrict__ lut, double rho) {
+__global__ void __launch_bounds__(256) lsd_lut_kernel(float4* __restrict__ lut, float2* __restrict__ seed_lut, double rho) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kLutSide * kLutSide) return;
   const int gy = i / kLutSide - kLutOff, gx = i - (gy + kLutOff) * kLutSide - kLutOff;
-  lut[i] = lsd_record(gx, gy, rho);
+  float2 sd;
+  lut[i] = lsd_record(gx, gy, rho, sd);
+  seed_lut[i] = sd;
 }
 
 // pass 1 over the 0.8x image: seed-capable pixels per row and the frame's largest squared gradient
@@ -179,14 +192,14 @@ __global__ void __launch_bounds__(128)
   int pos = row_off[(size_t)b * Hs + y];
   for (int x0 = 0; x0 < Ws; x0 += 32) {
     const int x = x0 + lane;
-    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(lsdw_kUnavail));
+    float4 rec = make_float4(lsd::kNotDefDeg, 0.f, 0.f, __int_as_float(lsdw_pack_g(0, 0) | lsdw_kUnavail));
     bool def = false;
     int q = 0;
     if (y < Hs - 1 && x < Ws - 1) {
       const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
       const int gx = DA + BC, gy = DA - BC;
       q = gx * gx + gy * gy;
-      rec.w = __int_as_float(q | lsdw_kUnavail);
+      rec.w = __int_as_float(lsdw_pack_g(gx, gy) | lsdw_kUnavail);
       if (q > q_undef) {  // sqrt(q / 4) > rho  <=>  q > q_undef (largest q with sqrt(q / 4.0) <= rho, found on the host)
         rec = __ldg(lut + (gy + kLutOff) * kLutSide + (gx + kLutOff));
         def = true;
@@ -203,11 +216,12 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-void launch_lsd_lut(float4* lut, cudaStream_t st) {
+void launch_lsd_lut(float4* lut, float2* seed_lut, cudaStream_t st) {
   const double rho = 2.0 / sin(lsd::kPi * lsd::kAngTh / 180);
-  lsd_lut_kernel<<<(kLutSide * kLutSide + 255) / 256, 256, 0, st>>>(lut, rho);
+  lsd_lut_kernel<<<(kLutSide * kLutSide + 255) / 256, 256, 0, st>>>(lut, seed_lut, rho);
 }
 size_t lsd_lut_bytes() { return (size_t)kLutSide * kLutSide * sizeof(float4); }
+size_t lsd_seed_lut_bytes() { return (size_t)kLutSide * kLutSide * sizeof(float2); }
 
 // exclusive scan of the per-row counts of every frame (one warp per frame)
 __global__ void __launch_bounds__(32)
@@ -269,6 +283,8 @@ using lsd::kNotDefDeg;
 using lsd::kPi;
 
 constexpr int kRing = 1024;  // region points kept in shared memory (the BFS frontier and small regions)
+// a refuted guess leaves up to 32 stale entries behind the end of the list, i.e. over the oldest entries of the ring
+constexpr int kRingValid = kRing - 32;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct Frame {
@@ -283,7 +299,8 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 __device__ __forceinline__ int* flags_of(const Frame& f, int idx) { return reinterpret_cast<int*>(f.pix + idx) + 3; }
 // region point i of a region of (current) size n
 __device__ __forceinline__ uint32_t reg_at(const Frame& f, int i, int n) {
-  return (n - i <= kRing) ? f.ring[i & (kRing - 1)] : f.reg[i];
+  if (n <= kRingValid) return f.ring[i & (kRing - 1)];   // the whole region is in the ring (uniform test, nearly always)
+  return (n - i <= kRingValid) ? f.ring[i & (kRing - 1)] : f.reg[i];
 }
 __device__ __forceinline__ int lin_of(const Frame& f, uint32_t c) { return (int)(c >> 16) * f.W + (int)(c & 0xFFFFu); }
 
@@ -343,14 +360,8 @@ __device__ __noinline__ Quick make_quick(double prec) {
 }
 
 // The reference seeds the running sums with (float)cos(reg_angle), (float)sin(reg_angle) of the seed's fp64 angle.
-// Those values only matter once a second pixel joins (most seeds grow nothing), so they are evaluated at the first
-// accept; until then the quick test runs on the record's cos / sin (same direction to 1e-7).
-__device__ __noinline__ float2 seed_terms(float deg) {
-  double sd, cd;
-  sincos((double)deg * kDegToRad, &sd, &cd);   // same values as sin() / cos()
-  return make_float2((float)cd, (float)sd);
-}
-
+// Those values (`sterm`, from the seed table of the integer gradient) only matter once a second pixel joins; until then
+// the quick test runs on the record's cos / sin (same direction to 1e-7).
 struct Sums {
   float x, y;
   int n;
@@ -359,8 +370,13 @@ struct Sums {
 // The scalar loop over the lanes of one step (the reference's order of tests), for the steps the batched decision cannot
 // prove.  Accepted pixels get their flag, list and ring entries here.  `exact` says whether the sums already are the
 // reference's (false until the first accept of the region).
-__device__ __noinline__ Sums step_sequential(Frame f, int lin, uint32_t npk, float4 rec, bool cand, Sums s, bool exact,
-                                             float seed_deg, double prec, Quick qk, int lane) {
+#ifdef PSL_V_SEQ_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+Sums step_sequential(Frame f, int lin, uint32_t npk, float4 rec, bool cand, Sums s, bool exact,
+                                             float seed_deg, float2 sterm, double prec, Quick qk, int lane) {
   unsigned mask = __ballot_sync(kFull, cand);
   while (mask) {
     const float s2 = s.x * s.x + s.y * s.y;
@@ -376,9 +392,8 @@ __device__ __noinline__ Sums step_sequential(Frame f, int lin, uint32_t npk, flo
     if (!am) break;
     const int j = __ffs(am) - 1;
     if (!exact) {
-      const float2 e = seed_terms(seed_deg);
-      s.x = e.x;
-      s.y = e.y;
+      s.x = sterm.x;
+      s.y = sterm.y;
       exact = true;
     }
     if (lane == j) {
@@ -412,8 +427,8 @@ __device__ __noinline__ Sums step_sequential(Frame f, int lin, uint32_t npk, flo
 //    neighbours are requested BEFORE the guess is verified, so the verification runs under the load latency and the
 //    next step needs no second look at what this step accepted (its loads already see the flags).  A refuted guess
 //    (a few percent of the steps) takes the flags back and replays the step with the scalar loop.
-__device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_t c0, float4 srec, double& reg_angle,
-                                           double prec, const Quick qk, int min_n, int lane) {
+__device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_t c0, float4 srec, float2 sterm,
+                                           double& reg_angle, double prec, const Quick qk, int min_n, int lane) {
   // four region points per step, eight lanes each: the centre of a 3x3 neighbourhood is the region point itself
   // (USED, never a candidate), so the loop's nine tests are the eight below in the same order
   const int p = lane >> 3, k8 = lane & 7, k = k8 + (k8 >= 4);
@@ -461,8 +476,8 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
     const int m2 = min(4, n_spec - i_next);   // <= 0: the list ends with this step
     Nbr nxt;
     {
-      uint32_t c = 0;
-      if (p < m2) c = reg_at(f, i_next + p, n_spec);
+      uint32_t c = f.ring[(i_next + p) & (kRing - 1)];
+      if (n_spec - i_next > kRingValid) c = f.reg[min(i_next + p, n_spec - 1)];   // a frontier longer than the ring (rare, uniform)
       nxt = load_nbr(f, p < m2, c, off, offpk);
     }
     // verification, under the latency of those loads
@@ -475,9 +490,8 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
       // in lane order with the reference's fp32 rounding (lane 31 ends with the sums after the step)
       float Px = s.x, Py = s.y;
       if (!exact) {
-        const float2 e = seed_terms(srec.x);
-        Px = e.x;
-        Py = e.y;
+        Px = sterm.x;
+        Py = sterm.y;
       }
       for (unsigned a = A; a; a &= a - 1) {
         const int j = __ffs(a) - 1;
@@ -512,7 +526,7 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
       LSD_STAT(7, 1);
       if (inA) *flags_of(f, cur.lin) = __float_as_int(cur.rec.w);   // take the guess back
       __syncwarp();
-      s = step_sequential(f, cur.lin, cur.npk, cur.rec, cur.cand, s, exact, srec.x, prec, qk, lane);
+      s = step_sequential(f, cur.lin, cur.npk, cur.rec, cur.cand, s, exact, srec.x, sterm, prec, qk, lane);
       exact = exact || s.n > 1;
       i = i_next;
       if (i >= s.n) break;
@@ -531,8 +545,14 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
 
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy; };
 
+__device__ __noinline__ double2 sincos_ni(double a) {
+  double s, c;
+  sincos(a, &s, &c);
+  return make_double2(s, c);
+}
+
 __device__ __forceinline__ double modgrad(const Frame& f, int idx) {
-  return sqrt((double)(*flags_of(f, idx) & lsdw_kN2Mask) / 4.0);
+  return sqrt((double)lsdw_n2(*flags_of(f, idx)) / 4.0);
 }
 
 // one ordered pass: the 32 terms of three running sums go through shared memory and lanes 0, 1, 2 each add one of
@@ -593,7 +613,11 @@ __device__ __forceinline__ void region2rect(const Frame& f, int n, double reg_an
   if (d < 0) d = -d;
   if (d > prec) theta += kPi;
   double dx, dy;
+#ifdef PSL_V_SINCOS_NI
+  { const double2 sc = sincos_ni(theta); dy = sc.x; dx = sc.y; }
+#else
   sincos(theta, &dy, &dx);
+#endif
   // extents: `if (l > l_max) l_max = l; else if (l < l_min) l_min = l;` with both starting at 0 is an
   // independent max and min (a value above the running max is positive, so it cannot lower the min)
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
@@ -682,7 +706,7 @@ __device__ __noinline__ int reduce_once(Frame f, int n, double xc, double yc, do
   n = __shfl_sync(kFull, n, 0);
   __syncwarp();
   // the reordered tail goes back to the shared mirror (reg_at reads the last kRing points from it)
-  for (int i = max(0, n - kRing) + lane; i < n; i += 32) f.ring[i & (kRing - 1)] = f.reg[i];
+  for (int i = max(0, n - kRingValid) + lane; i < n; i += 32) f.ring[i & (kRing - 1)] = f.reg[i];
   __syncwarp();
   return n;
 }
@@ -695,7 +719,7 @@ constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never 
 #define PSL_LSD_MINB 7
 #endif
 __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
-    lsd_core_kernel(LineBuffers L, int nb, uint32_t stride, uint32_t* __restrict__ status) {
+    lsd_core_kernel(const __grid_constant__ LineBuffers L, int nb, uint32_t stride, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
   __shared__ __align__(16) double terms[kCoreWarps][96];
   const int wid = threadIdx.x >> 5, slot = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
@@ -724,7 +748,10 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
       todo &= todo - 1;
       const int seed = __shfl_sync(lsdw::kFull, my, l);
       const float4 srec = f.pix[seed];
-      if (__float_as_int(srec.w) < 0) { LSD_STAT(5, 1); continue; }
+      const int sw = __float_as_int(srec.w);
+      if (sw < 0) { LSD_STAT(5, 1); continue; }
+      // the sums a region of this seed starts with once a second pixel joins (used by the first accept, far below)
+      const float2 sterm = __ldg(L.seed_lut + ((sw >> 10) & 1023) * kLutSide + (sw & 1023));
       // seed / W without the integer division: seed < 2^24 and W <= 4096, so the float quotient is off by at most one
       int sy = (int)(((float)seed + 0.5f) * inv_w), sx = seed - sy * f.W;
       if (sx < 0) { --sy; sx += f.W; }
@@ -742,7 +769,7 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
       for (;;) {
         if (stage < 2) {
           LSD_T0(t_g);
-          n = lsdw::region_grow(f, seed, c0, srec, reg_angle, prec, qk, stage == 0 ? L.min_reg_size : 2, lane);
+          n = lsdw::region_grow(f, seed, c0, srec, sterm, reg_angle, prec, qk, stage == 0 ? L.min_reg_size : 2, lane);
           LSD_T1(10, t_g);
           if (stage == 0) {
             LSD_STAT(13, 1);

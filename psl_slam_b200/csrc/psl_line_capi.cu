@@ -64,6 +64,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   exact_axis(h, L.Hs, yt);
   short2 *dx = nullptr, *dy = nullptr;
   uint8_t* lut = nullptr;
+  uint8_t* seed_lut = nullptr;
   // the x taps once more, per group of 4 outputs, for the word-based resize kernel
   const int n4 = (L.Ws + 3) >> 2;
   std::vector<short4> xt4(xt.size());
@@ -80,7 +81,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   // the records of the row above a frame must read "not available" (lsd_kernels.cu, load_nbr): for every frame but the
   // first that row is the previous frame's last one (NOTDEF); the first frame gets Ws + 1 such records in front
   const size_t pix_pad = ((size_t)L.Ws + 1 + 7) & ~(size_t)7;   // whole 128-byte lines, so the records stay line-aligned
-  bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, dxw, (size_t)n4) && lalloc(ctx, dxo, (size_t)n4) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
+  bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, dxw, (size_t)n4) && lalloc(ctx, dxo, (size_t)n4) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, seed_lut, lsd_seed_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
             lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx + pix_pad) &&
             lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
@@ -100,7 +101,8 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   PSL_CK(cudaMemsetAsync(L.pix, 0xFF, pix_pad * sizeof(float4), ctx->stream));
   L.pix += pix_pad;
   L.lut = reinterpret_cast<const float4*>(lut);
-  launch_lsd_lut(reinterpret_cast<float4*>(lut), ctx->stream);
+  L.seed_lut = reinterpret_cast<const float2*>(seed_lut);
+  launch_lsd_lut(reinterpret_cast<float4*>(lut), reinterpret_cast<float2*>(seed_lut), ctx->stream);
   L.xtab = dx;
   L.ytab = dy;
   L.xw4 = grouped ? dxw : nullptr;

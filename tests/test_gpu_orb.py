@@ -155,3 +155,34 @@ def test_unaligned_device_frames_vs_oracle(orc):
         got = kps_h[b, : n_h[b]].copy().view(KP_DTYPE).reshape(-1)
         _same(got, desc_h[b, : n_h[b]], okps, odesc)
     assert n_h[1] < n_h[0]  # the low-texture frame is the sparse one
+
+
+def test_cuda_equals_reference_build():
+    """The CUDA extractor against oracle/_ref: /root/reference/src/ORBextractor.cc compiled unchanged over the OpenCV
+    stand-in (tests/test_oracle_ref.py).  Prebuilt in the build container; travels with the snapshot."""
+    import ctypes as C
+    import os
+
+    from conftest import ROOT, golden_names, load_golden
+    from psl_slam_b200._lib import KP_DTYPE
+    path = os.path.join(ROOT, "oracle", "_ref", "libpsl_ref_orb.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built")
+    lib = C.CDLL(path)
+    lib.ref_orb_extract.restype = C.c_int
+    lib.ref_orb_extract.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_int]
+    for name in golden_names("orb_"):
+        g = load_golden(name)
+        nf, nl, ini, mn = [int(v) for v in g["params"]]
+        sf = float(g["scale_factor"])
+        img = np.ascontiguousarray(g["image"])
+        cap = nf + 64 * nl
+        rk = np.zeros(cap, KP_DTYPE)
+        rd = np.zeros((cap, 32), np.uint8)
+        n = lib.ref_orb_extract(nf, sf, nl, ini, mn, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                rk.ctypes.data, rd.ctypes.data, cap)
+        ex = _extractor(g)
+        kps, desc = ex(img)
+        assert len(kps) == n, name
+        assert kps.tobytes() == rk[:n].tobytes() and np.array_equal(desc, rd[:n]), name
