@@ -332,7 +332,7 @@ __device__ __forceinline__ Nbr load_nbr(const Frame& f, bool active, uint32_t c,
   b.rec = make_float4(0.f, 0.f, 0.f, 0.f);
   b.cand = false;
   if (active) {
-    b.rec = f.pix[b.lin];
+    b.rec = f.pix[b.lin];   // (ld.global.L2::128B / ::256B measured: no difference)
     b.cand = __float_as_int(b.rec.w) >= 0;
   }
   return b;
@@ -573,6 +573,7 @@ __device__ __forceinline__ void ordered_add3(const Frame& f, double t0, double t
 __device__ __forceinline__ void region2rect(const Frame& f, int n, double reg_angle, double prec, Rect& rec, int lane) {
   // weighted centroid: x += px * w ... in list order
   double acc = 0;
+  double w0 = 0, w1 = 0;   // the weights of the first 64 points (most regions are shorter) for the second pass
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     double tx = 0, ty = 0, w = 0;
@@ -583,6 +584,8 @@ __device__ __forceinline__ void region2rect(const Frame& f, int n, double reg_an
       tx = (double)px * w;
       ty = (double)py * w;
     }
+    if (base == 0) w0 = w;
+    if (base == 32) w1 = w;
     ordered_add3(f, tx, ty, w, min(32, n - base), acc, lane);
   }
   double x = shfl_d(acc, 0), y = shfl_d(acc, 1);
@@ -597,7 +600,8 @@ __device__ __forceinline__ void region2rect(const Frame& f, int n, double reg_an
     if (i < n) {
       const uint32_t c = reg_at(f, i, n);
       const int px = (int)(c & 0xFFFFu), py = (int)(c >> 16);
-      const double w = modgrad(f, py * f.W + px), dx = (double)px - x, dy = (double)py - y;
+      const double w = base == 0 ? w0 : base == 32 ? w1 : modgrad(f, py * f.W + px);
+      const double dx = (double)px - x, dy = (double)py - y;
       t1 = dy * dy * w;
       t2 = dx * dx * w;
       t3 = -(dx * dy * w);   // Ixy -= term  ==  Ixy += -term
@@ -722,14 +726,30 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
     lsd_core_kernel(const __grid_constant__ LineBuffers L, int nb, uint32_t stride, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
   __shared__ __align__(16) double terms[kCoreWarps][96];
+#ifndef PSL_NO_OPAQUE
+  // read once: under register pressure the compiler otherwise re-reads %tid (a slow special-register move) and rebuilds
+  // the shared-memory and frame pointers inside the step loop
+  unsigned tid_;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_));
+  const int wid = (int)(tid_ >> 5), slot = blockIdx.x * kCoreWarps + wid, lane = (int)(tid_ & 31u);
+#else
   const int wid = threadIdx.x >> 5, slot = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
+#endif
   if (slot >= nb) return;
   // frame of this warp: a fixed permutation of the batch (stride coprime to nb), so that the warps of one SM hold
   // frames from all over the sequence — neighbouring frames cost about the same, and an SM that got only expensive
   // ones would finish last
   const int b = (int)(((uint64_t)slot * stride) % (uint32_t)nb);
   const size_t npx = (size_t)L.Ws * L.Hs;
+#ifndef PSL_NO_OPAQUE
+  float4* pix_ = L.pix + b * npx;
+  uint32_t* reg_ = L.reg + b * npx;
+  uint32_t* ring_ = ring[wid];
+  asm volatile("" : "+l"(pix_), "+l"(reg_), "+l"(ring_));
+  const lsdw::Frame f{L.Ws, pix_, reg_, ring_, terms[wid]};
+#else
   const lsdw::Frame f{L.Ws, L.pix + b * npx, L.reg + b * npx, ring[wid], terms[wid]};
+#endif
   const uint32_t* seeds = L.val_out + b * npx;
   const int n_seeds = L.n_def[b];
   float* out = L.raw + (size_t)b * L.raw_cap * 4;
