@@ -646,8 +646,9 @@ int psl_line_junctions_dev(psl_ctx* ctx, const psl_keyline* d_kl, const int32_t*
  * row-major float (pFrame->mTcw in, the pose SetPose receives out); outlier[n] = mvbOutlier; *n_inliers = the return
  * value (nInitialCorrespondences - nBad; 0 and no change with fewer than 3 correspondences).  fp64 on the device; the
  * sums over the edges run in another order than g2o's, so the contract is a tolerance (pose to 1e-6, identical flags away
- * from the thresholds), and the oracle is a restatement that g2o cannot pin here.  LIL edges (:504-590,
- * :840-868) are not part of this entry point yet. */
+ * from the thresholds), and the oracle is a restatement that g2o cannot pin here.  This form carries no
+ * structural-line (LIL) edges, i.e. it is PoseOptimization for a frame with N_LJL = 0; psl_pose_optimization_lil below
+ * is the complete call. */
 typedef struct psl_pose_point {
   float u, v, u_right;   /* mvKeysUn[i].pt, mvuRight[i] */
   float inv_sigma2;      /* mvInvLevelSigma2[mvKeysUn[i].octave] */
@@ -661,6 +662,35 @@ int psl_pose_optimization(psl_ctx* ctx, const float* Tcw_in, const psl_pose_poin
 int psl_pose_optimization_dev(psl_ctx* ctx, const float* d_Tcw_in, const psl_pose_point* d_pts, const int32_t* d_n,
                               int32_t cap, int32_t B, float fx, float fy, float cx, float cy, float bf, float* d_Tcw_out,
                               uint8_t* d_outlier, int32_t* d_n_inliers);
+
+/* The complete Optimizer::PoseOptimization: the point edges above plus one EdgeLILSE3ProjectXYZ per structural line of the
+ * frame that holds a map InsectLine (src/Optimizer.cc:619-693; edge: add_inc/EdgeLIL.h:210-374).  The map InsectLine is a
+ * FIXED vertex (two 3-D segments and their cross point, :637-649), so the edge only adds to the pose block: a 6-dim
+ * error — the distances of the four projected end points to the two observed 2-D line equations and the reprojection
+ * error of the cross point — with identity information and a Huber kernel of delta^2 = 11.07.  The reference's
+ * Jacobian reads both end points of the second segment from the same three numbers (EdgeLIL.h:276-279); reproduced.
+ * Between rounds the LIL edges are classified like the points (chi2 > 11.07 -> mvbOutlier_Insec, level 1, :976-1007);
+ * lil_outlier[n_lil] receives mvbOutlier_Insec.  *n_inliers = nInitialCorrespondences - nBad, where the initial count
+ * includes the LIL edges and nBad only the point outliers (nLineBad is never incremented, :712, :1021). */
+typedef struct psl_pose_lil {
+  double line1[6]; /* pLIL->line1: start, end in world coordinates */
+  double line2[6]; /* pLIL->line2 */
+  double cross[3]; /* pLIL->crosspoint */
+  double obs1[3];  /* pFrame->mvle_l[i].first: the observed 2-D line equation of the first segment */
+  double obs2[3];  /* pFrame->mvle_l[i].second */
+  double ins[2];   /* pFrame->CrossPoint_2D[i] */
+  uint32_t flags;  /* & 1: mvpMapInsecs[i] != NULL and not bad */
+  uint32_t pad_;
+} psl_pose_lil;    /* 192 B */
+int psl_pose_optimization_lil(psl_ctx* ctx, const float* Tcw_in, const psl_pose_point* pts, int32_t n,
+                              const psl_pose_lil* lils, int32_t n_lil, float fx, float fy, float cx, float cy, float bf,
+                              float* Tcw_out, uint8_t* outlier, uint8_t* lil_outlier, int32_t* n_inliers);
+/* Batched, DEVICE pointers, asynchronous: frame b additionally owns rows [b*lil_cap, b*lil_cap + d_n_lil[b]) of d_lils /
+ * d_lil_outlier.  d_lils may be NULL with lil_cap = 0 (no structural lines). */
+int psl_pose_optimization_lil_dev(psl_ctx* ctx, const float* d_Tcw_in, const psl_pose_point* d_pts, const int32_t* d_n,
+                                  int32_t cap, const psl_pose_lil* d_lils, const int32_t* d_n_lil, int32_t lil_cap, int32_t B,
+                                  float fx, float fy, float cx, float cy, float bf, float* d_Tcw_out, uint8_t* d_outlier,
+                                  uint8_t* d_lil_outlier, int32_t* d_n_inliers);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
-// TEST INFRASTRUCTURE — CPU oracle of Optimizer::PoseOptimization ("next" row N4), point edges only.
-// Restates /root/reference/src/Optimizer.cc:239-1023 for a frame without InsectLine observations (N_LJL = 0: the LIL
-// block :504-590 adds nothing) over the vendored g2o it calls: EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose
+// TEST INFRASTRUCTURE — CPU oracle of Optimizer::PoseOptimization ("next" row N4): point edges and the structural-line
+// (LIL) edges.  Restates /root/reference/src/Optimizer.cc:239-1023 (the live LIL block is :619-693, its classification
+// :976-1007; the long blocks before them are commented-out code) and add_inc/EdgeLIL.h:210-374 over the vendored g2o it calls: EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose
 // (Thirdparty/g2o/g2o/types/types_six_dof_expmap.{h,cpp}), SE3Quat (types/se3quat.h), RobustKernelHuber
 // (core/robust_kernel_impl.cpp:78-98), BaseUnaryEdge::constructQuadraticForm (core/base_unary_edge.hpp:43-72),
 // OptimizationAlgorithmLevenberg::solve (core/optimization_algorithm_levenberg.cpp:61-190), SparseOptimizer::optimize
@@ -175,6 +175,89 @@ void build_system(const std::vector<Edge>& E, const Pose& p, const Cam& c, doubl
     }
   }
 }
+// ---- EdgeLILSE3ProjectXYZ (add_inc/EdgeLIL.h:210-374): a fixed VertexLIL (two 3-D segments + their cross point) seen from
+// the pose; 6-dim error = (distance of the projected end points of each segment to the observed 2-D line, 2 + 2, and
+// the reprojection error of the cross point, 2), information = identity (invSigma = 1, Optimizer.cc:241, :668)
+struct LilEdge { double Xw[15]; double l1[3], l2[3], ins[2]; int level; bool robust; double err[6]; };
+
+void map_point(const Pose& p, const double* xw, double X[3]) {  // SE3Quat::map
+  quat_rotate(p.q, xw, X);
+  for (int i = 0; i < 3; ++i) X[i] += p.t[i];
+}
+void lil_error(LilEdge& e, const Pose& p, const Cam& c) {  // computeError, EdgeLIL.h:220-259
+  double uv[5][2];
+  for (int k = 0; k < 5; ++k) {
+    double X[3];
+    map_point(p, e.Xw + 3 * k, X);
+    uv[k][0] = X[0] / X[2] * c.fx + c.cx;   // cam_project = project2d, then the intrinsics
+    uv[k][1] = X[1] / X[2] * c.fy + c.cy;
+  }
+  e.err[0] = uv[0][0] * e.l1[0] + uv[0][1] * e.l1[1] + 1.0 * e.l1[2];
+  e.err[1] = uv[1][0] * e.l1[0] + uv[1][1] * e.l1[1] + 1.0 * e.l1[2];
+  e.err[2] = uv[2][0] * e.l2[0] + uv[2][1] * e.l2[1] + 1.0 * e.l2[2];
+  e.err[3] = uv[3][0] * e.l2[0] + uv[3][1] * e.l2[1] + 1.0 * e.l2[2];
+  e.err[4] = e.ins[0] - uv[4][0];
+  e.err[5] = e.ins[1] - uv[4][1];
+}
+double lil_chi2(const LilEdge& e) {
+  double s = 0;
+  for (int k = 0; k < 6; ++k) s += e.err[k] * e.err[k];
+  return s;
+}
+// linearizeOplus, the pose block _jacobianOplusXj (:338-374).  The reference reads BOTH end points of the second segment
+// from estimate().segment<3>(9) (:276-279), so rows 2 and 3 are the derivative at the segment's END point; kept.
+void lil_jacobian(const LilEdge& e, const Pose& p, const Cam& c, double J[6][6]) {
+  const int src[4] = {0, 3, 9, 9};
+  for (int r = 0; r < 4; ++r) {
+    double X[3];
+    map_point(p, e.Xw + src[r], X);
+    const double x = X[0], y = X[1], invz = 1.0 / X[2], invz_2 = invz * invz;
+    const double l0 = r < 2 ? e.l1[0] : e.l2[0], l1 = r < 2 ? e.l1[1] : e.l2[1];
+    J[r][0] = -c.fx * x * y * invz_2 * l0 - c.fy * (1 + y * y * invz_2) * l1;
+    J[r][1] = c.fx * (1 + x * x * invz_2) * l0 + c.fy * x * y * invz_2 * l1;
+    J[r][2] = -c.fx * y * invz * l0 + c.fy * x * invz * l1;
+    J[r][3] = c.fx * invz * l0;
+    J[r][4] = c.fy * invz * l1;
+    J[r][5] = (-c.fx * x * l0 - c.fy * y * l1) * invz_2;
+  }
+  double X[3];
+  map_point(p, e.Xw + 12, X);
+  const double x = X[0], y = X[1], invz = 1.0 / X[2], invz_2 = invz * invz;
+  J[4][0] = x * y * invz_2 * c.fx; J[4][1] = -(1 + (x * x * invz_2)) * c.fx; J[4][2] = y * invz * c.fx;
+  J[4][3] = -c.fx * invz; J[4][4] = 0; J[4][5] = x * invz_2 * c.fx;
+  J[5][0] = (1 + y * y * invz_2) * c.fy; J[5][1] = -c.fy * x * y * invz_2; J[5][2] = -c.fy * x * invz;
+  J[5][3] = 0; J[5][4] = -c.fy * invz; J[5][5] = c.fy * y * invz_2;
+}
+// BaseBinaryEdge::constructQuadraticForm with the LIL vertex fixed (core/base_binary_edge.hpp:58-120): only the pose block
+void add_lil_edges(const std::vector<LilEdge>& E, const Pose& p, const Cam& c, double delta, double H[6][6], double b[6]) {
+  for (const LilEdge& e : E) {
+    if (e.level != 0) continue;
+    double J[6][6];
+    lil_jacobian(e, p, c, J);
+    double w = 1.0;
+    if (e.robust) { double rho[3]; huber(lil_chi2(e), delta, rho); w = rho[1]; }
+    for (int r = 0; r < 6; ++r) {
+      double s = 0;
+      for (int d = 0; d < 6; ++d) s += J[d][r] * e.err[d];
+      b[r] -= w * s;
+      for (int q = 0; q < 6; ++q) {
+        double h = 0;
+        for (int d = 0; d < 6; ++d) h += J[d][r] * w * J[d][q];
+        H[r][q] += h;
+      }
+    }
+  }
+}
+double lil_robust_chi2(const std::vector<LilEdge>& E, double delta) {
+  double s = 0;
+  for (const LilEdge& e : E) {
+    if (e.level != 0) continue;
+    const double c = lil_chi2(e);
+    if (e.robust) { double rho[3]; huber(c, delta, rho); s += rho[0]; } else s += c;
+  }
+  return s;
+}
+
 bool solve6(const double Hin[6][6], const double b[6], double x[6]) {  // LDL^T, fails unless positive (LinearSolverDense)
   double L[6][6] = {{0}}, D[6];
   for (int j = 0; j < 6; ++j) {
@@ -202,9 +285,25 @@ extern "C" {
 
 // pts: n records (u, v, u_right (< 0: monocular observation), inv_sigma2, Xw[3], valid) = the keypoints with a MapPoint.
 // Tcw: 4x4 row-major float in / out.  outlier[n] = mvbOutlier.  Returns nInitialCorrespondences - nBad (0 if < 3).
-int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n, float fx, float fy, float cx, float cy,
-                          float bf, float* Tcw_out, uint8_t* outlier) {
+// lils: n_lil records, one per structural line of the frame (flags & 1: it holds a map InsectLine that is not bad);
+// lil_outlier[n_lil] = mvbOutlier_Insec.  The return value does not subtract the LIL outliers (nLineBad stays 0, :712,1021).
+int orc_pose_optimization_lil(const float* Tcw_in, const psl_pose_point* pts, int n, const psl_pose_lil* lils, int n_lil,
+                              float fx, float fy, float cx, float cy, float bf, float* Tcw_out, uint8_t* outlier,
+                              uint8_t* lil_outlier) {
   const Cam cam{fx, fy, cx, cy, bf};
+  std::vector<LilEdge> L;
+  std::vector<int> lidx;
+  const double deltaLJL = (double)(float)std::sqrt(11.07);  // float deltaLJL = sqrt(11.07), :629
+  for (int i = 0; i < n_lil; ++i) {
+    lil_outlier[i] = 0;
+    if (!(lils[i].flags & 1u)) continue;
+    LilEdge e{};
+    for (int k = 0; k < 6; ++k) { e.Xw[k] = lils[i].line1[k]; e.Xw[6 + k] = lils[i].line2[k]; }
+    for (int k = 0; k < 3; ++k) { e.Xw[12 + k] = lils[i].cross[k]; e.l1[k] = lils[i].obs1[k]; e.l2[k] = lils[i].obs2[k]; }
+    e.ins[0] = lils[i].ins[0]; e.ins[1] = lils[i].ins[1];
+    e.level = 0; e.robust = true;
+    L.push_back(e); lidx.push_back(i);
+  }
   std::vector<Edge> E;
   std::vector<int> idx;
   const float deltaMono = (float)std::sqrt(5.991), deltaStereo = (float)std::sqrt(7.815);  // :276-277
@@ -221,7 +320,7 @@ int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n,
     E.push_back(e); idx.push_back(i);
   }
   std::memcpy(Tcw_out, Tcw_in, 16 * sizeof(float));
-  const int nInitial = (int)E.size();
+  const int nInitial = (int)E.size() + (int)L.size();
   if (nInitial < 3) return 0;
   double R0[3][3];
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R0[i][j] = Tcw_in[4 * i + j];
@@ -238,10 +337,12 @@ int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n,
     int nBadSteps = 0;
     for (int iter = 0; iter < 10; ++iter) {
       for (Edge& e : E) if (e.level == 0) compute_error(e, est, cam);
-      double currentChi = robust_chi2(E);
+      for (LilEdge& e : L) if (e.level == 0) lil_error(e, est, cam);
+      double currentChi = robust_chi2(E) + lil_robust_chi2(L, deltaLJL);
       const double iniChi = currentChi;
       double H[6][6], b[6];
       build_system(E, est, cam, H, b);
+      add_lil_edges(L, est, cam, deltaLJL, H, b);
       if (iter == 0) {
         double maxDiag = 0;
         for (int j = 0; j < 6; ++j) maxDiag = std::max(std::fabs(H[j][j]), maxDiag);
@@ -260,7 +361,8 @@ int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n,
         const bool ok2 = solve6(Hl, b, x);
         est = pose_exp_times(x, est);
         for (Edge& e : E) if (e.level == 0) compute_error(e, est, cam);
-          double tempChi = robust_chi2(E);
+        for (LilEdge& e : L) if (e.level == 0) lil_error(e, est, cam);
+        double tempChi = robust_chi2(E) + lil_robust_chi2(L, deltaLJL);
         if (!ok2) tempChi = std::numeric_limits<double>::max();
         rho = currentChi - tempChi;
         double scale = 0;
@@ -294,7 +396,15 @@ int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n,
       else { outlier[idx[k]] = 0; e.level = 0; }
       if (it == 2) e.robust = false;
     }
-    if (E.size() < 10) break;
+    for (size_t k = 0; k < L.size(); ++k) {  // :976-1007
+      LilEdge& e = L[k];
+      if (lil_outlier[lidx[k]]) lil_error(e, est, cam);
+      const float c2 = (float)lil_chi2(e);
+      if (c2 > 11.07f) { lil_outlier[lidx[k]] = 1; e.level = 1; }
+      else { lil_outlier[lidx[k]] = 0; e.level = 0; }
+      if (it == 2) e.robust = false;
+    }
+    if (E.size() + L.size() < 10) break;  // optimizer.edges().size() < 10
   }
   double R[3][3];
   quat_to_matrix(est.q, R);
@@ -305,6 +415,11 @@ int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n,
   Tcw_out[12] = Tcw_out[13] = Tcw_out[14] = 0.f;
   Tcw_out[15] = 1.f;
   return nInitial - nBad;
+}
+
+int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n, float fx, float fy, float cx, float cy,
+                          float bf, float* Tcw_out, uint8_t* outlier) {
+  return orc_pose_optimization_lil(Tcw_in, pts, n, nullptr, 0, fx, fy, cx, cy, bf, Tcw_out, outlier, nullptr);
 }
 
 }  // extern "C"

@@ -84,7 +84,10 @@ int orc_line_junctions(const psl_keyline* kl_un, const double* lines3d, int n, i
                        float fan_thr, float* fans, psl_line_junction* junctions, int cap, int32_t* n_fans,
                        int32_t* n_junctions);
 
-/* ---- pose-only optimisation (orc_pose.cpp): Optimizer.cc:239-1023 over the vendored g2o, point edges only; UNPINNED ---- */
+/* ---- pose-only optimisation (orc_pose.cpp): Optimizer.cc:239-1023 over the vendored g2o, point and LIL edges; UNPINNED ---- */
+int orc_pose_optimization_lil(const float* Tcw_in, const psl_pose_point* pts, int n, const psl_pose_lil* lils, int n_lil,
+                              float fx, float fy, float cx, float cy, float bf, float* Tcw_out, uint8_t* outlier,
+                              uint8_t* lil_outlier);
 int orc_pose_optimization(const float* Tcw_in, const psl_pose_point* pts, int n, float fx, float fy, float cx, float cy,
                           float bf, float* Tcw_out, uint8_t* outlier);
 

@@ -587,13 +587,24 @@ POSE_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("u_right", "<f4"), ("i
                              ("yw", "<f4"), ("zw", "<f4"), ("flags", "<u4")])  # psl_pose_point, 32 B
 
 
-def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
-    """Optimizer::PoseOptimization, point edges only (UNPINNED restatement over the vendored g2o):
-    (Tcw after [4,4] f32, mvbOutlier [n] u8, nInitialCorrespondences - nBad)."""
+POSE_LIL_DTYPE = np.dtype([("line1", "<f8", (6,)), ("line2", "<f8", (6,)), ("cross", "<f8", (3,)), ("obs1", "<f8", (3,)),
+                           ("obs2", "<f8", (3,)), ("ins", "<f8", (2,)), ("flags", "<u4"), ("pad_", "<u4")])  # psl_pose_lil, 192 B
+
+
+def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf, lils=None):
+    """Optimizer::PoseOptimization (UNPINNED restatement over the vendored g2o):
+    (Tcw after [4,4] f32, mvbOutlier [n] u8, nInitialCorrespondences - nBad) and, with `lils` (the structural-line edges),
+    additionally mvbOutlier_Insec [n_lil] u8."""
     T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
     p = np.ascontiguousarray(pts, POSE_POINT_DTYPE)
     out = np.zeros(16, np.float32)
     bad = np.zeros(max(len(p), 1), np.uint8)
-    n = lib().orc_pose_optimization(_p(T), _p(p), len(p), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
-                                    C.c_float(bf), _p(out), _p(bad))
-    return out.reshape(4, 4), bad[: len(p)].copy(), int(n)
+    if lils is None:
+        n = lib().orc_pose_optimization(_p(T), _p(p), len(p), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                        C.c_float(bf), _p(out), _p(bad))
+        return out.reshape(4, 4), bad[: len(p)].copy(), int(n)
+    l = np.ascontiguousarray(lils, POSE_LIL_DTYPE)
+    lbad = np.zeros(max(len(l), 1), np.uint8)
+    n = lib().orc_pose_optimization_lil(_p(T), _p(p), len(p), _p(l), len(l), C.c_float(fx), C.c_float(fy), C.c_float(cx),
+                                        C.c_float(cy), C.c_float(bf), _p(out), _p(bad), _p(lbad))
+    return out.reshape(4, 4), bad[: len(p)].copy(), int(n), lbad[: len(l)].copy()

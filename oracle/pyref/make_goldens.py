@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE — writes tests/golden/*.npz (run in the build container only; needs cv2).
 
-    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|linetriangnew|pose|undistort|planes|lines3d|all]
+    python -m oracle.pyref.make_goldens [orb|match|triang|fuse|loop|junctions|line|linematch|linefuse|linetriangnew|pose|pose_lil|undistort|planes|lines3d|all]
 
 Each fixture stores the seeded input bytes and the outputs of the cv2-primitive
 restatement of the reference (oracle/pyref), so that the tests never need cv2 or
@@ -683,6 +683,76 @@ def make_pose():
               f"|t - t_true| {np.abs(T[:3, 3] - tt).max():.2e} (prior {np.abs(T0[:3, 3] - tt).max():.2e})")
 
 
+def make_pose_lil():
+    """N4 with the structural-line edges: the point cases plus synthetic InsectLines — pairs of coplanar 3-D segments that meet
+    in a cross point, seen from the true pose; the observed 2-D line equations go through the noisy projections of the end
+    points (normalised as LINEextractor does, LineExtractor.cpp:352-363); some structural lines are gross outliers (wrong
+    association) and some records carry no map InsectLine.  Outputs of oracle/pyref/pose_py.py."""
+    from oracle import orc
+    from oracle.pyref import pose_py
+    K = synth.ICL
+    fx, fy, cx, cy, bf = K["fx"], K["fy"], K["cx"], K["cy"], K["bf"]
+
+    def rot(w):
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+    def proj(X):
+        return np.stack([fx * X[..., 0] / X[..., 2] + cx, fy * X[..., 1] / X[..., 2] + cy], -1)
+
+    # (name, seed, points, structural lines, share of outlier structural lines, prior rotation / translation error)
+    cases = [("pose_lil_case0", 0, 400, 12, 0.2, 0.01, 0.03), ("pose_lil_case1_lines_only", 1, 0, 9, 0.0, 0.01, 0.02),
+             ("pose_lil_case2_few_points", 2, 6, 20, 0.15, 0.02, 0.05), ("pose_lil_case3_far_prior", 3, 250, 16, 0.25, 0.05, 0.2)]
+    for name, seed, n, m, p_out, rot_err, t_err in cases:
+        rng = np.random.default_rng(900 + seed)
+        Rt, tt = rot(rng.normal(0, 0.05, 3)), rng.normal(0, 0.1, 3)
+        Xc = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1, 1, n), rng.uniform(0.8, 6, n)], 1)
+        Xw = (Rt.T @ (Xc - tt).T).T
+        p = np.zeros(n + 3, orc.POSE_POINT_DTYPE)
+        if n:
+            uv = proj(Xc) + rng.normal(0, 0.6, (n, 2))
+            p["u"][:n], p["v"][:n] = uv[:, 0], uv[:, 1]
+            p["u_right"][:n] = np.where(rng.random(n) < 0.7, uv[:, 0] - bf / Xc[:, 2] + rng.normal(0, 0.6, n), -1)
+            p["inv_sigma2"][:n] = 1 / 1.2 ** (2 * rng.integers(0, 8, n))
+            p["xw"][:n], p["yw"][:n], p["zw"][:n] = Xw[:, 0], Xw[:, 1], Xw[:, 2]
+            p["flags"][:n] = 1
+            bad = rng.random(n) < 0.08
+            p["u"][:n][bad] += rng.normal(0, 25, int(bad.sum())).astype(np.float32)
+        # structural lines in camera coordinates: cross point, two directions in a random plane through it
+        l = np.zeros(m + 2, orc.POSE_LIL_DTYPE)
+        for i in range(m):
+            c = np.array([rng.uniform(-1.2, 1.2), rng.uniform(-0.8, 0.8), rng.uniform(1.5, 5)])
+            d1, d2 = rng.normal(0, 1, 3), rng.normal(0, 1, 3)
+            d1, d2 = d1 / np.linalg.norm(d1), d2 / np.linalg.norm(d2)
+            P = np.stack([c + rng.uniform(-0.1, 0.05) * d1, c + rng.uniform(0.3, 0.9) * d1,
+                          c + rng.uniform(-0.1, 0.05) * d2, c + rng.uniform(0.3, 0.9) * d2, c])
+            Pw = (Rt.T @ (P - tt).T).T
+            l["line1"][i], l["line2"][i], l["cross"][i] = Pw[:2].reshape(6), Pw[2:4].reshape(6), Pw[4]
+            uv = proj(P) + rng.normal(0, 0.5, (5, 2))
+            if rng.random() < p_out:
+                uv += rng.normal(0, 30, 2)             # a wrong association: everything shifted
+            for key, a, b in (("obs1", uv[0], uv[1]), ("obs2", uv[2], uv[3])):
+                le = np.cross(np.append(a, 1.0), np.append(b, 1.0))
+                l[key][i] = le / np.sqrt(le[0] ** 2 + le[1] ** 2)
+            l["ins"][i] = uv[4]
+            l["flags"][i] = 1
+        l = l[rng.permutation(len(l))]
+        p = p[rng.permutation(len(p))]
+        T0 = np.eye(4, dtype=np.float32)
+        T0[:3, :3] = rot(rng.normal(0, rot_err, 3)) @ Rt
+        T0[:3, 3] = tt + rng.normal(0, t_err, 3)
+        T, outl, cnt, loutl = pose_py.pose_optimization(T0, p, fx, fy, cx, cy, bf, l)
+        Ttrue = np.eye(4)
+        Ttrue[:3, :3], Ttrue[:3, 3] = Rt, tt
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), Tcw0=T0, pts=p, lils=l, cam=np.array([fx, fy, cx, cy, bf], np.float32),
+                            Tcw=T, outlier=outl, lil_outlier=loutl, count=np.int32(cnt), Ttrue=Ttrue)
+        print(f"{name}: points {int((p['flags'] & 1).sum())} lils {int((l['flags'] & 1).sum())} count {cnt} point outliers "
+              f"{int(outl.sum())} lil outliers {int(loutl.sum())} |t - t_true| {np.abs(T[:3, 3] - tt).max():.2e} "
+              f"(prior {np.abs(T0[:3, 3] - tt).max():.2e})")
+
+
 def make_lines3d():
     """Frame::isLineGood: the lines of the linematch pairs over the sequence's depth (clean, noisy, noisy with holes);
     both SVDs are the real cv2.SVDecomp (oracle/pyref/line3d_py.py)."""
@@ -738,6 +808,8 @@ if __name__ == "__main__":
         make_linetriang_new()
     if what in ("pose", "all"):
         make_pose()
+    if what in ("pose_lil", "all"):
+        make_pose_lil()
     if what in ("undistort", "all"):
         make_undistort()
     if what in ("planes", "all"):

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE — golden-vector generator for Optimizer::PoseOptimization ("next" row N4), point edges only.
+"""TEST INFRASTRUCTURE — golden-vector generator for Optimizer::PoseOptimization ("next" row N4): point edges and the
+structural-line (LIL) edges of add_inc/EdgeLIL.h:210-374 (Optimizer.cc:619-693, :976-1007).
 
 Independent numpy restatement (written from src/Optimizer.cc:239-1023 and the vendored g2o sources it calls, not from
 oracle/c/orc_pose.cpp): rotations as matrices re-projected through a unit quaternion after every update (what
@@ -74,15 +75,83 @@ def _exp_times(x, q, t):
     return qn, V @ up + _rot(qe) @ t
 
 
-def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
-    """pts: structured (u, v, u_right, inv_sigma2, xw, yw, zw, flags).  Returns (Tcw [4,4] f32, outlier [n] u8, count)."""
+class _Lil:
+    """The LIL edges of a frame as arrays: world points P [m, 5, 3] (segment 1 start / end, segment 2 start / end, cross
+    point), observed line equations l1, l2 [m, 3], observed cross point ins [m, 2]."""
+
+    def __init__(self, lils, fx, fy, cx, cy):
+        self.sel = np.nonzero(lils["flags"] & 1)[0] if lils is not None and len(lils) else np.zeros(0, int)
+        a = lils[self.sel] if len(self.sel) else None
+        m = len(self.sel)
+        self.P = np.concatenate([a["line1"].reshape(m, 2, 3), a["line2"].reshape(m, 2, 3), a["cross"].reshape(m, 1, 3)], 1) \
+            if m else np.zeros((0, 5, 3))
+        self.l1 = a["obs1"].astype(np.float64) if m else np.zeros((0, 3))
+        self.l2 = a["obs2"].astype(np.float64) if m else np.zeros((0, 3))
+        self.ins = a["ins"].astype(np.float64) if m else np.zeros((0, 2))
+        self.K = (fx, fy, cx, cy)
+        self.level = np.zeros(m, int)
+        self.robust = np.ones(m, bool)
+        self.err = np.zeros((m, 6))
+        self.delta = float(F32(math.sqrt(11.07)))           # float deltaLJL = sqrt(11.07)
+
+    def errors(self, q, t, mask):
+        fx, fy, cx, cy = self.K
+        X = self.P[mask] @ _rot(q).T + t
+        u = X[..., 0] / X[..., 2] * fx + cx
+        v = X[..., 1] / X[..., 2] * fy + cy
+        l1, l2 = self.l1[mask], self.l2[mask]
+        e = np.zeros((int(mask.sum()), 6))
+        for r in range(2):
+            e[:, r] = u[:, r] * l1[:, 0] + v[:, r] * l1[:, 1] + l1[:, 2]
+            e[:, 2 + r] = u[:, 2 + r] * l2[:, 0] + v[:, 2 + r] * l2[:, 1] + l2[:, 2]
+        e[:, 4] = self.ins[mask][:, 0] - u[:, 4]
+        e[:, 5] = self.ins[mask][:, 1] - v[:, 4]
+        return e
+
+    def chi2(self, mask=slice(None)):
+        return (self.err[mask] ** 2).sum(1)
+
+    def jacobians(self, q, t, a):
+        """d error / d pose, [len(a), 6, 6].  Rows 2 and 3 both take the END point of the second segment: the reference
+        reads estimate().segment<3>(9) for its start as well (EdgeLIL.h:276-279)."""
+        fx, fy, cx, cy = self.K
+        X = self.P[a] @ _rot(q).T + t
+        J = np.zeros((len(a), 6, 6))
+        for r, (k, l) in enumerate(((0, self.l1), (1, self.l1), (3, self.l2), (3, self.l2))):
+            x, y, iz = X[:, k, 0], X[:, k, 1], 1.0 / X[:, k, 2]
+            iz2 = iz * iz
+            l0, l1 = l[a][:, 0], l[a][:, 1]
+            J[:, r] = np.stack([-fx * x * y * iz2 * l0 - fy * (1 + y * y * iz2) * l1,
+                                fx * (1 + x * x * iz2) * l0 + fy * x * y * iz2 * l1,
+                                -fx * y * iz * l0 + fy * x * iz * l1, fx * iz * l0, fy * iz * l1,
+                                (-fx * x * l0 - fy * y * l1) * iz2], 1)
+        x, y, iz = X[:, 4, 0], X[:, 4, 1], 1.0 / X[:, 4, 2]
+        iz2 = iz * iz
+        J[:, 4] = np.stack([x * y * iz2 * fx, -(1 + x * x * iz2) * fx, y * iz * fx, -fx * iz, 0 * x, x * iz2 * fx], 1)
+        J[:, 5] = np.stack([(1 + y * y * iz2) * fy, -fy * x * y * iz2, -fy * x * iz, 0 * x, -fy * iz, fy * y * iz2], 1)
+        return J
+
+
+def _huber(c, d):
+    big = c > d * d
+    s = np.sqrt(np.where(big, c, 1.0))
+    return np.where(big, 2 * s * d - d * d, c), np.where(big, d / s, 1.0)
+
+
+def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf, lils=None):
+    """pts: structured (u, v, u_right, inv_sigma2, xw, yw, zw, flags); lils: structured psl_pose_lil records or None.
+    Returns (Tcw [4,4] f32, outlier [n] u8, count) and, with lils, additionally lil_outlier [n_lil] u8."""
     fx, fy, cx, cy, bf = (float(F32(v)) for v in (fx, fy, cx, cy, bf))
     T0 = np.asarray(Tcw, F32).astype(np.float64)
     sel = np.nonzero(pts["flags"] & 1)[0]
     n = len(pts)
     outlier = np.zeros(n, np.uint8)
-    if len(sel) < 3:
-        return np.asarray(Tcw, F32).copy(), outlier, 0
+    LL = _Lil(lils, fx, fy, cx, cy)
+    lil_outlier = np.zeros(0 if lils is None else len(lils), np.uint8)
+    ret = (lambda T, o, c: (T, o, c)) if lils is None else (lambda T, o, c: (T, o, c, lil_outlier))
+    n_initial = len(sel) + len(LL.sel)
+    if n_initial < 3:
+        return ret(np.asarray(Tcw, F32).copy(), outlier, 0)
     stereo = ~(pts["u_right"][sel] < 0)
     obs = np.stack([pts["u"][sel], pts["v"][sel], np.where(stereo, pts["u_right"][sel], 0)], 1).astype(np.float64)
     Xw = np.stack([pts["xw"][sel], pts["yw"][sel], pts["zw"][sel]], 1).astype(np.float64)
@@ -118,7 +187,10 @@ def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
         a = level == 0
         c = chi2(a)
         r0, _ = rho_of(c, delta[a])
-        return float(np.where(robust[a], r0, c).sum())
+        al = LL.level == 0
+        cl = LL.chi2(al)
+        rl, _ = _huber(cl, LL.delta)
+        return float(np.where(robust[a], r0, c).sum()) + float(np.where(LL.robust[al], rl, cl).sum())
 
     def system(q, t):
         a = np.nonzero(level == 0)[0]
@@ -135,6 +207,13 @@ def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
         w = np.where(robust[a], w, 1.0)
         H = np.einsum("n,nij,nik->jk", w * info[a], J, J)
         b = -np.einsum("n,nij,ni->j", w * info[a], J, err[a])
+        al = np.nonzero(LL.level == 0)[0]
+        if len(al):
+            Jl = LL.jacobians(q, t, al)
+            _, wl = _huber(LL.chi2(al), LL.delta)
+            wl = np.where(LL.robust[al], wl, 1.0)
+            H = H + np.einsum("n,nij,nik->jk", wl, Jl, Jl)
+            b = b - np.einsum("n,nij,ni->j", wl, Jl, LL.err[al])
         return H, b
 
     nbad = 0
@@ -145,6 +224,8 @@ def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
         for iteration in range(10):
             act = level == 0
             err[act] = errors(q, t, act)
+            actl = LL.level == 0
+            LL.err[actl] = LL.errors(q, t, actl)
             cur = robust_chi()
             ini = cur
             H, b = system(q, t)
@@ -157,6 +238,7 @@ def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
                 x = np.linalg.solve(Hl, b) if ok else np.zeros(6)
                 qn, tn = _exp_times(x, q, t)
                 err[act] = errors(qn, tn, act)
+                LL.err[actl] = LL.errors(qn, tn, actl)
                 tmp = robust_chi() if ok else float(np.finfo(np.float64).max)
                 rho = (cur - tmp) / (float(x @ (lam * x + b)) + 1e-3)
                 if rho > 0 and math.isfinite(tmp):
@@ -184,12 +266,20 @@ def pose_optimization(Tcw, pts, fx, fy, cx, cy, bf):
         bad = c > thr
         level = bad.astype(int)
         nbad = int(bad.sum())
+        l1 = LL.level == 1
+        if l1.any():
+            LL.err[l1] = LL.errors(q, t, l1)
+        badl = LL.chi2().astype(F32) > F32(11.07)
+        LL.level = badl.astype(int)
         if it == 2:
             robust[:] = False
-        if len(sel) < 10:
+            LL.robust[:] = False
+        if n_initial < 10:
             break
     outlier[sel] = bad.astype(np.uint8)
+    if len(LL.sel):
+        lil_outlier[LL.sel] = badl.astype(np.uint8)
     T = np.eye(4, dtype=F32)
     T[:3, :3] = _rot(q).astype(F32)
     T[:3, 3] = t.astype(F32)
-    return T, outlier, len(sel) - nbad
+    return ret(T, outlier, n_initial - nbad)

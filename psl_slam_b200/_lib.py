@@ -51,6 +51,8 @@ JUNCTION_DTYPE = np.dtype([("l1", "<i4"), ("l2", "<i4"), ("cross2d_x", "<f4"), (
                            ("cross3d", "<f8", (3,))])  # psl_line_junction, 40 B
 POSE_POINT_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("u_right", "<f4"), ("inv_sigma2", "<f4"), ("xw", "<f4"),
                              ("yw", "<f4"), ("zw", "<f4"), ("flags", "<u4")])  # psl_pose_point, 32 B
+POSE_LIL_DTYPE = np.dtype([("line1", "<f8", (6,)), ("line2", "<f8", (6,)), ("cross", "<f8", (3,)), ("obs1", "<f8", (3,)),
+                           ("obs2", "<f8", (3,)), ("ins", "<f8", (2,)), ("flags", "<u4"), ("pad_", "<u4")])  # psl_pose_lil, 192 B
 Q_VALID, Q_CLAIMS = 1, 2
 
 
@@ -154,7 +156,8 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_undistort_keypoints", "psl_undistort_keypoints_dev", "psl_image_bounds", "psl_plane_hypotheses",
            "psl_lines_3d", "psl_lines_3d_dev", "psl_match_bow_kf", "psl_match_sim3", "psl_match_initialization",
            "psl_line_junctions", "psl_line_junctions_dev", "psl_line_search_triangulation_new",
-           "psl_pose_optimization", "psl_pose_optimization_dev"]
+           "psl_pose_optimization", "psl_pose_optimization_dev", "psl_pose_optimization_lil",
+           "psl_pose_optimization_lil_dev"]
 
 _lib = None
 
@@ -221,6 +224,8 @@ def lib():
         L.psl_line_search_triangulation_new.argtypes = [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _f, _f, _i, _p, _p]
         L.psl_pose_optimization.argtypes = [_p, _p, _p, _i, _f, _f, _f, _f, _f, _p, _p, _p]
         L.psl_pose_optimization_dev.argtypes = [_p, _p, _p, _p, _i, _i, _f, _f, _f, _f, _f, _p, _p, _p]
+        L.psl_pose_optimization_lil.argtypes = [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f, _f, _p, _p, _p, _p]
+        L.psl_pose_optimization_lil_dev.argtypes = [_p, _p, _p, _p, _i, _p, _p, _i, _i, _f, _f, _f, _f, _f, _p, _p, _p, _p]
         L.psl_line_junctions.argtypes = [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _i, _p, _p]
         L.psl_line_junctions_dev.argtypes = [_p, _p, _p, _i, _i, _p, _i, _i, _f, _f, _p, _p, _i, _p, _p]
         _lib = L

@@ -1,7 +1,8 @@
-// Optimizer::PoseOptimization ("next" row N4), point edges: the pose-only Levenberg optimisation of src/Optimizer.cc:239-1023
-// for frames without InsectLine observations, over what it calls in the vendored g2o (EdgeSE3ProjectXYZOnlyPose /
-// EdgeStereoSE3ProjectXYZOnlyPose, SE3Quat, RobustKernelHuber, BaseUnaryEdge::constructQuadraticForm,
-// OptimizationAlgorithmLevenberg::solve, SparseOptimizer::optimize).  One CTA per frame: the edges are spread over the
+// Optimizer::PoseOptimization ("next" row N4): the pose-only Levenberg optimisation of src/Optimizer.cc:239-1023 over what
+// it calls in the vendored g2o (EdgeSE3ProjectXYZOnlyPose / EdgeStereoSE3ProjectXYZOnlyPose, SE3Quat, RobustKernelHuber,
+// BaseUnaryEdge / BaseBinaryEdge::constructQuadraticForm, OptimizationAlgorithmLevenberg::solve, SparseOptimizer::optimize)
+// with the point edges and the structural-line edges EdgeLILSE3ProjectXYZ (add_inc/EdgeLIL.h:210-374; built at
+// Optimizer.cc:619-693, classified at :976-1007).  One CTA per frame: the edges are spread over the
 // threads, the 6x6 normal equations and the robust chi2 are block reductions (fixed order: per-thread partial sums in
 // index order, shuffle tree, warps in order), thread 0 runs the Levenberg control flow, the 6x6 LDL^T solve and the SE3
 // update.  fp64 throughout; the sums run in another order than g2o's edge loop, so the contract is a tolerance on the
@@ -144,10 +145,58 @@ __device__ void block_sum(double (&v)[K], double* s_part /*[8][K]*/, double* s_o
   __syncthreads();
 }
 
+// the five points of a LIL vertex seen from the pose (segment 1 start / end, segment 2 start / end, cross point)
+__device__ __forceinline__ void lil_map(const Pose& p, const psl_pose_lil& l, int k, double X[3]) {
+  const double* src = k < 2 ? l.line1 + 3 * k : k < 4 ? l.line2 + 3 * (k - 2) : l.cross;
+  const double xw[3] = {src[0], src[1], src[2]};
+  quat_rotate(p.q, xw, X);
+  X[0] += p.t[0]; X[1] += p.t[1]; X[2] += p.t[2];
+}
+// EdgeLILSE3ProjectXYZ::computeError (EdgeLIL.h:220-259)
+__device__ void lil_error(const Pose& p, const psl_pose_lil& l, const Cam& cam, double* e) {
+  double u[5], v[5];
+  for (int k = 0; k < 5; ++k) {
+    double X[3];
+    lil_map(p, l, k, X);
+    u[k] = X[0] / X[2] * cam.fx + cam.cx;
+    v[k] = X[1] / X[2] * cam.fy + cam.cy;
+  }
+  e[0] = u[0] * l.obs1[0] + v[0] * l.obs1[1] + 1.0 * l.obs1[2];
+  e[1] = u[1] * l.obs1[0] + v[1] * l.obs1[1] + 1.0 * l.obs1[2];
+  e[2] = u[2] * l.obs2[0] + v[2] * l.obs2[1] + 1.0 * l.obs2[2];
+  e[3] = u[3] * l.obs2[0] + v[3] * l.obs2[1] + 1.0 * l.obs2[2];
+  e[4] = l.ins[0] - u[4];
+  e[5] = l.ins[1] - v[4];
+}
+// row r of _jacobianOplusXj (EdgeLIL.h:338-374); rows 2 and 3 both take the END point of the second segment, as the
+// reference does (it reads estimate().segment<3>(9) for the start as well, :276-279)
+__device__ void lil_jacobian_row(const Pose& p, const psl_pose_lil& l, const Cam& cam, int r, double* J) {
+  double X[3];
+  lil_map(p, l, r == 0 ? 0 : r == 1 ? 1 : r < 4 ? 3 : 4, X);
+  const double x = X[0], y = X[1], invz = 1.0 / X[2], invz_2 = invz * invz;
+  if (r < 4) {
+    const double l0 = r < 2 ? l.obs1[0] : l.obs2[0], l1 = r < 2 ? l.obs1[1] : l.obs2[1];
+    J[0] = -cam.fx * x * y * invz_2 * l0 - cam.fy * (1 + y * y * invz_2) * l1;
+    J[1] = cam.fx * (1 + x * x * invz_2) * l0 + cam.fy * x * y * invz_2 * l1;
+    J[2] = -cam.fx * y * invz * l0 + cam.fy * x * invz * l1;
+    J[3] = cam.fx * invz * l0;
+    J[4] = cam.fy * invz * l1;
+    J[5] = (-cam.fx * x * l0 - cam.fy * y * l1) * invz_2;
+  } else if (r == 4) {
+    J[0] = x * y * invz_2 * cam.fx; J[1] = -(1 + (x * x * invz_2)) * cam.fx; J[2] = y * invz * cam.fx;
+    J[3] = -cam.fx * invz; J[4] = 0; J[5] = x * invz_2 * cam.fx;
+  } else {
+    J[0] = (1 + y * y * invz_2) * cam.fy; J[1] = -cam.fy * x * y * invz_2; J[2] = -cam.fy * x * invz;
+    J[3] = 0; J[4] = -cam.fy * invz; J[5] = cam.fy * y * invz_2;
+  }
+}
+
 __global__ void __launch_bounds__(kPoseThreads)
     pose_opt_kernel(const float* __restrict__ Tcw_in, const psl_pose_point* __restrict__ pts, const int32_t* __restrict__ n_pts,
-                    int cap, Cam cam, double* __restrict__ err_scratch, uint8_t* __restrict__ level_scratch,
-                    float* __restrict__ Tcw_out, uint8_t* __restrict__ outlier, int32_t* __restrict__ n_inliers) {
+                    int cap, const psl_pose_lil* __restrict__ lils, const int32_t* __restrict__ n_lils, int lil_cap, Cam cam,
+                    double* __restrict__ err_scratch, uint8_t* __restrict__ level_scratch, double* __restrict__ lil_err_scratch,
+                    uint8_t* __restrict__ lil_level_scratch, float* __restrict__ Tcw_out, uint8_t* __restrict__ outlier,
+                    uint8_t* __restrict__ lil_outlier, int32_t* __restrict__ n_inliers) {
   __shared__ double s_part[(kPoseThreads / 32) * 27];
   __shared__ double s_sum[27];
   __shared__ Pose s_est, s_init, s_backup;
@@ -162,12 +211,25 @@ __global__ void __launch_bounds__(kPoseThreads)
   const float* Tin = Tcw_in + (size_t)b * 16;
   float* Tout = Tcw_out + (size_t)b * 16;
   const double deltaMono = (double)(float)sqrt(5.991), deltaStereo = (double)(float)sqrt(7.815);   // const float delta = sqrt(5.991)
+  const double deltaLil = (double)(float)sqrt(11.07);   // float deltaLJL = sqrt(11.07), Optimizer.cc:629
+  // the structural-line edges of this frame (none when lils is NULL); they sit on the LAST threads of the block
+  const int nl = lils ? min(n_lils[b], lil_cap) : 0;
+  const psl_pose_lil* LL = lils + (size_t)b * lil_cap;
+  double* lerr = lil_err_scratch + (size_t)b * lil_cap * 6;
+  uint8_t* llevel = lil_level_scratch + (size_t)b * lil_cap;
+  uint8_t* lout = lil_outlier + (size_t)b * lil_cap;
+  const int ltid = kPoseThreads - 1 - tid;
 
   double cnt[1] = {0};
   for (int i = tid; i < n; i += kPoseThreads) {
     out[i] = 0;
     level[i] = (P[i].flags & 1u) ? 0 : 2;   // 2: no MapPoint, not an edge
     cnt[0] += (P[i].flags & 1u) ? 1.0 : 0.0;
+  }
+  for (int i = ltid; i < nl; i += kPoseThreads) {
+    lout[i] = 0;
+    llevel[i] = (LL[i].flags & 1u) ? 0 : 2;
+    cnt[0] += (LL[i].flags & 1u) ? 1.0 : 0.0;
   }
   block_sum<1>(cnt, s_part, s_sum);
   const int n_initial = (int)s_sum[0];
@@ -204,6 +266,13 @@ __global__ void __launch_bounds__(kPoseThreads)
         err[3 * i] = (double)pt.u - (px * cam.fx + cam.cx); err[3 * i + 1] = (double)pt.v - (py * cam.fy + cam.cy); err[3 * i + 2] = 0;
       }
     }
+    for (int i = ltid; i < nl; i += kPoseThreads)
+      if (llevel[i] == lvl) lil_error(p, LL[i], cam, lerr + 6 * i);
+  };
+  auto lil_chi2_of = [&](int i) {
+    double s2 = 0;
+    for (int k = 0; k < 6; ++k) s2 += lerr[6 * i + k] * lerr[6 * i + k];
+    return s2;   // information = identity
   };
   auto chi2_of = [&](int i) {
     return (err[3 * i] * err[3 * i] + err[3 * i + 1] * err[3 * i + 1] + err[3 * i + 2] * err[3 * i + 2]) * (double)P[i].inv_sigma2;
@@ -214,6 +283,12 @@ __global__ void __launch_bounds__(kPoseThreads)
       if (level[i] != 0) continue;
       const double e2 = chi2_of(i);
       if (robust) { double r0, r1; huber(e2, P[i].u_right < 0 ? deltaMono : deltaStereo, r0, r1); c[0] += r0; }
+      else c[0] += e2;
+    }
+    for (int i = ltid; i < nl; i += kPoseThreads) {
+      if (llevel[i] != 0) continue;
+      const double e2 = lil_chi2_of(i);
+      if (robust) { double r0, r1; huber(e2, deltaLil, r0, r1); c[0] += r0; }
       else c[0] += e2;
     }
     block_sum<1>(c, s_part, s_sum);
@@ -265,6 +340,25 @@ __global__ void __launch_bounds__(kPoseThreads)
         }
 #pragma unroll
         for (int r = 0; r < 6; ++r) acc[21 + r] -= w * ((J[0][r] * e0 + J[1][r] * e1 + J[2][r] * e2) * info);
+      }
+      // BaseBinaryEdge::constructQuadraticForm with the LIL vertex fixed: only the pose block (base_binary_edge.hpp:58-120)
+      for (int i = ltid; i < nl; i += kPoseThreads) {
+        if (llevel[i] != 0) continue;
+        double w = 1.0, r0;
+        if (robust) huber(lil_chi2_of(i), deltaLil, r0, w);
+        for (int d = 0; d < 6; ++d) {
+          double J[6];
+          lil_jacobian_row(p, LL[i], cam, d, J);
+          const double ed = lerr[6 * i + d];
+          int k = 0;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+#pragma unroll
+            for (int q = r; q < 6; ++q) acc[k++] += J[r] * w * J[q];
+          }
+#pragma unroll
+          for (int r = 0; r < 6; ++r) acc[21 + r] -= w * (J[r] * ed);
+        }
       }
       block_sum<27>(acc, s_part, s_sum);
       if (tid == 0) {
@@ -350,6 +444,12 @@ __global__ void __launch_bounds__(kPoseThreads)
       level[i] = bad ? 1 : 0;
       nb[0] += bad ? 1.0 : 0.0;
     }
+    for (int i = ltid; i < nl; i += kPoseThreads) {   // :976-1007; not counted in nBad (nLineBad stays 0)
+      if (llevel[i] > 1) continue;
+      const bool bad = (float)lil_chi2_of(i) > 11.07f;
+      lout[i] = bad ? 1 : 0;
+      llevel[i] = bad ? 1 : 0;
+    }
     block_sum<1>(nb, s_part, s_sum);
     n_bad = (int)s_sum[0];
     if (n_initial < 10) break;
@@ -375,57 +475,85 @@ using namespace psl;
 
 extern "C" {
 
-int psl_pose_optimization_dev(psl_ctx* ctx, const float* d_Tcw_in, const psl_pose_point* d_pts, const int32_t* d_n,
-                              int32_t cap, int32_t B, float fx, float fy, float cx, float cy, float bf, float* d_Tcw_out,
-                              uint8_t* d_outlier, int32_t* d_n_inliers) {
+int psl_pose_optimization_lil_dev(psl_ctx* ctx, const float* d_Tcw_in, const psl_pose_point* d_pts, const int32_t* d_n,
+                                  int32_t cap, const psl_pose_lil* d_lils, const int32_t* d_n_lil, int32_t lil_cap, int32_t B,
+                                  float fx, float fy, float cx, float cy, float bf, float* d_Tcw_out, uint8_t* d_outlier,
+                                  uint8_t* d_lil_outlier, int32_t* d_n_inliers) {
   if (!ctx) return PSL_E_INVALID;
-  if (B < 0 || cap < 1 || (B > 0 && (!d_Tcw_in || !d_pts || !d_n || !d_Tcw_out || !d_outlier || !d_n_inliers)))
+  if (B < 0 || cap < 1 || lil_cap < 0 ||
+      (B > 0 && (!d_Tcw_in || !d_pts || !d_n || !d_Tcw_out || !d_outlier || !d_n_inliers)) ||
+      (B > 0 && lil_cap > 0 && (!d_lils || !d_n_lil || !d_lil_outlier)))
     return fail(ctx, PSL_E_INVALID, "bad argument");
   if (B == 0) return PSL_OK;
   PSL_CK(cudaSetDevice(ctx->cfg.device));
   int rc;
   if ((rc = ensure(ctx, ctx->m_misc[10], (size_t)B * cap * 24))) return rc;
   if ((rc = ensure(ctx, ctx->m_misc[11], (size_t)B * cap))) return rc;
+  if ((rc = ensure(ctx, ctx->m_misc[12], (size_t)B * std::max(lil_cap, 1) * 48))) return rc;
+  if ((rc = ensure(ctx, ctx->m_misc[13], (size_t)B * std::max(lil_cap, 1)))) return rc;
   size_t e = prof_mark(ctx);
-  pose_opt_kernel<<<B, kPoseThreads, 0, ctx->stream>>>(d_Tcw_in, d_pts, d_n, cap, Cam{fx, fy, cx, cy, bf},
-                                                       ctx->m_misc[10].as<double>(), ctx->m_misc[11].as<uint8_t>(), d_Tcw_out,
-                                                       d_outlier, d_n_inliers);
+  pose_opt_kernel<<<B, kPoseThreads, 0, ctx->stream>>>(d_Tcw_in, d_pts, d_n, cap, lil_cap > 0 ? d_lils : nullptr, d_n_lil, lil_cap,
+                                                       Cam{fx, fy, cx, cy, bf}, ctx->m_misc[10].as<double>(),
+                                                       ctx->m_misc[11].as<uint8_t>(), ctx->m_misc[12].as<double>(),
+                                                       ctx->m_misc[13].as<uint8_t>(), d_Tcw_out, d_outlier, d_lil_outlier,
+                                                       d_n_inliers);
   prof_span(ctx, 15, e, 1);
   PSL_CK(cudaGetLastError());
   return PSL_OK;
 }
 
-int psl_pose_optimization(psl_ctx* ctx, const float* Tcw_in, const psl_pose_point* pts, int32_t n, float fx, float fy,
-                          float cx, float cy, float bf, float* Tcw_out, uint8_t* outlier, int32_t* n_inliers) {
+int psl_pose_optimization_dev(psl_ctx* ctx, const float* d_Tcw_in, const psl_pose_point* d_pts, const int32_t* d_n,
+                              int32_t cap, int32_t B, float fx, float fy, float cx, float cy, float bf, float* d_Tcw_out,
+                              uint8_t* d_outlier, int32_t* d_n_inliers) {
+  return psl_pose_optimization_lil_dev(ctx, d_Tcw_in, d_pts, d_n, cap, nullptr, nullptr, 0, B, fx, fy, cx, cy, bf, d_Tcw_out,
+                                       d_outlier, nullptr, d_n_inliers);
+}
+
+int psl_pose_optimization_lil(psl_ctx* ctx, const float* Tcw_in, const psl_pose_point* pts, int32_t n,
+                              const psl_pose_lil* lils, int32_t n_lil, float fx, float fy, float cx, float cy, float bf,
+                              float* Tcw_out, uint8_t* outlier, uint8_t* lil_outlier, int32_t* n_inliers) {
   if (!ctx) return PSL_E_INVALID;
-  if (!Tcw_in || !Tcw_out || !n_inliers || n < 0 || (n > 0 && (!pts || !outlier))) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (!Tcw_in || !Tcw_out || !n_inliers || n < 0 || n_lil < 0 || (n > 0 && (!pts || !outlier)) ||
+      (n_lil > 0 && (!lils || !lil_outlier)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
   *n_inliers = 0;
   for (int i = 0; i < 16; ++i) Tcw_out[i] = Tcw_in[i];
   for (int i = 0; i < n; ++i) outlier[i] = 0;
-  if (n == 0) return PSL_OK;
+  for (int i = 0; i < n_lil; ++i) lil_outlier[i] = 0;
+  if (n + n_lil == 0) return PSL_OK;
   PSL_CK(cudaSetDevice(ctx->cfg.device));
   DevBuf* M = ctx->m_misc;
   int rc;
 #define PSL_UPP(buf, src, nbytes)                                                                              \
   do {                                                                                                         \
     if ((rc = ensure(ctx, buf, (nbytes)))) return rc;                                                          \
-    PSL_CK(cudaMemcpyAsync((buf).p, (src), (nbytes), cudaMemcpyHostToDevice, ctx->stream));                    \
+    if ((nbytes) > 0) PSL_CK(cudaMemcpyAsync((buf).p, (src), (nbytes), cudaMemcpyHostToDevice, ctx->stream));  \
   } while (0)
+  const int cap = std::max(n, 1);
   PSL_UPP(M[0], Tcw_in, 64);
   PSL_UPP(M[1], pts, (size_t)n * sizeof(psl_pose_point));
-  const int32_t nn[1] = {n};
+  PSL_UPP(M[4], lils, (size_t)n_lil * sizeof(psl_pose_lil));
+  const int32_t nn[2] = {n, n_lil};
   PSL_UPP(ctx->m_n, nn, sizeof(nn));
   if ((rc = ensure(ctx, M[2], 64))) return rc;
-  if ((rc = ensure(ctx, M[3], (size_t)n))) return rc;
+  if ((rc = ensure(ctx, M[3], (size_t)cap))) return rc;
+  if ((rc = ensure(ctx, M[5], (size_t)std::max(n_lil, 1)))) return rc;
   if ((rc = ensure(ctx, ctx->m_nm, 4))) return rc;
-  rc = psl_pose_optimization_dev(ctx, M[0].as<float>(), M[1].as<psl_pose_point>(), ctx->m_n.as<int32_t>(), n, 1, fx, fy, cx,
-                                 cy, bf, M[2].as<float>(), M[3].as<uint8_t>(), ctx->m_nm.as<int32_t>());
+  rc = psl_pose_optimization_lil_dev(ctx, M[0].as<float>(), M[1].as<psl_pose_point>(), ctx->m_n.as<int32_t>(), cap,
+                                     M[4].as<psl_pose_lil>(), ctx->m_n.as<int32_t>() + 1, n_lil, 1, fx, fy, cx, cy, bf,
+                                     M[2].as<float>(), M[3].as<uint8_t>(), M[5].as<uint8_t>(), ctx->m_nm.as<int32_t>());
   if (rc) return rc;
   PSL_CK(cudaMemcpyAsync(Tcw_out, M[2].p, 64, cudaMemcpyDeviceToHost, ctx->stream));
-  PSL_CK(cudaMemcpyAsync(outlier, M[3].p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n > 0) PSL_CK(cudaMemcpyAsync(outlier, M[3].p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_lil > 0) PSL_CK(cudaMemcpyAsync(lil_outlier, M[5].p, (size_t)n_lil, cudaMemcpyDeviceToHost, ctx->stream));
   PSL_CK(cudaMemcpyAsync(n_inliers, ctx->m_nm.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
   return check_status(ctx);
 #undef PSL_UPP
+}
+
+int psl_pose_optimization(psl_ctx* ctx, const float* Tcw_in, const psl_pose_point* pts, int32_t n, float fx, float fy,
+                          float cx, float cy, float bf, float* Tcw_out, uint8_t* outlier, int32_t* n_inliers) {
+  return psl_pose_optimization_lil(ctx, Tcw_in, pts, n, nullptr, 0, fx, fy, cx, cy, bf, Tcw_out, outlier, nullptr, n_inliers);
 }
 
 }  // extern "C"

@@ -67,7 +67,7 @@ struct psl_ctx {
 
   // matcher scratch (single-pair host API and the batched pipeline)
   DevBuf m_kps, m_ur, m_desc, m_q, m_qdesc, m_claimed, m_n, m_cell_start, m_cell_items, m_cand, m_cand_count,
-      m_best, m_accepted, m_assign, m_nm, m_misc[12];
+      m_best, m_accepted, m_assign, m_nm, m_misc[16];
 
   // staging for the host-pointer entry points (grown on demand)
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
