@@ -76,7 +76,7 @@ typedef struct psl_config {
   int32_t orb_min_th_fast; /* ORBextractor.minThFAST   (7)    */
   int32_t orb_max_candidates; /* FAST candidate pool per frame; 0 = auto (the reference only
                                  reserves nfeatures*10 as a hint, ORBextractor.cc:779) */
-  int32_t chunk_frames;    /* frames per launch of the ORB stages; 0 = auto (512; ~2.4 MB of HBM per frame at 640x480) */
+  int32_t chunk_frames;    /* frames per launch of the ORB stages; 0 = auto (max_batch clamped to [1, 512]; ~2.4 MB of HBM per frame at 640x480) */
   int32_t line_nfeatures;  /* LINEextractor.nFeatures  (200)  */
   float line_scale_factor; /* LINEextractor.scaleFactor (1.2; truncated to int 1 by the reference) */
   int32_t line_nlevels;    /* LINEextractor.nLevels    (1)    */
@@ -546,6 +546,30 @@ int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gr
 /* HOST pointers (tightly packed frames); H2D and D2H copies are part of the call. */
 int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
                              const float* Tcw, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* out);
+
+/* Tracking::GrabImageRGBD for a batch (src/Tracking.cc:214-243): cvtColor RGB / BGR (A) -> GRAY on the device (the
+ * arithmetic of psl_convert_rgbd), then everything of psl_track_frontend_batch.  channels = 3 or 4; rgb_order != 0 for
+ * RGB(A) input (mbRGB, Tracking.cc:222-232), 0 for BGR(A).
+ *
+ * _dev: DEVICE pointers, asynchronous.
+ * Host form, one call: psl_track_rgbd_batch (tightly packed frames, width a multiple of 16).
+ * Host form, pipelined: psl_track_rgbd_batch_begin only enqueues the uploads of a batch into one of two staging sets and
+ * returns; psl_track_rgbd_batch_end runs the OLDEST begun batch and returns with its results in `out`.  Calling
+ * begin(k+1) before end(k) keeps the PCIe link busy while batch k is computed (at most two batches in flight; the host
+ * input buffers of a batch must stay valid and unchanged until its _end returns; pinned memory makes the copies
+ * asynchronous).  PSL_E_INVALID when a third batch is begun or none is in flight. */
+int psl_track_rgbd_batch_dev(psl_ctx* ctx, const uint8_t* d_color, int32_t channels, int32_t rgb_order, int32_t color_stride,
+                             int64_t color_frame_stride, const uint16_t* d_depth, int32_t depth_stride_px,
+                             int64_t depth_frame_stride_px, int32_t B, int32_t w, int32_t h, const float* d_Tcw,
+                             const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* out);
+int psl_track_rgbd_batch(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32_t rgb_order, const uint16_t* depth,
+                         int32_t B, int32_t w, int32_t h, const float* Tcw, const psl_camera* cam,
+                         const psl_track_params* prm, float line_desc_th, const psl_frontend_out* out);
+int psl_track_rgbd_batch_begin(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32_t rgb_order,
+                               const uint16_t* depth, int32_t B, int32_t w, int32_t h, const float* Tcw);
+int psl_track_rgbd_batch_end(psl_ctx* ctx, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
                              const psl_frontend_out* out);
 
 /* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).

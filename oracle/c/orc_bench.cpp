@@ -104,3 +104,37 @@ extern "C" int orc_frontend_batch_mt(const orc_orb_params* p, const uint8_t* gra
   });
   return err.load() ? -1 : 0;
 }
+
+// cvtColor RGB / BGR (A) -> GRAY as cv2 4.13 computes it: Y = (R 9798 + G 19235 + B 3735 + 2^14) >> 15;
+// what Tracking::GrabImageRGBD does before the Frame is built (src/Tracking.cc:219-232).
+extern "C" void orc_color_to_gray(const uint8_t* color, int channels, int rgb_order, uint8_t* gray, int64_t n_px) {
+  const int ri = rgb_order ? 0 : 2, bi = rgb_order ? 2 : 0;
+  for (int64_t i = 0; i < n_px; ++i) {
+    const uint8_t* c = color + i * channels;
+    gray[i] = (uint8_t)((c[ri] * 9798 + c[1] * 19235 + c[bi] * 3735 + 16384) >> 15);
+  }
+}
+
+// GrabImageRGBD for a batch: the conversion above, then orc_frontend_batch_mt (the CPU arm of bench.py with RGB-D input)
+extern "C" int orc_rgbd_frontend_batch_mt(const orc_orb_params* p, const uint8_t* color, int channels, int rgb_order,
+                                          const uint16_t* depth, int B, int w, int h, const float* Tcw, const float* cam,
+                                          float th, float nn_ratio, int check_ori, int line_nfeatures, float line_desc_th,
+                                          int nthreads, int32_t* n_out, int32_t* nmatches_out, int32_t* nl_out,
+                                          int32_t* line_nmatches_out) {
+  const size_t px = (size_t)w * h;
+  std::vector<uint8_t> gray(px * B);
+  std::atomic<int> next(0);
+  auto fn = [&]() {
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= B) break;
+      orc_color_to_gray(color + (size_t)b * px * channels, channels, rgb_order, &gray[(size_t)b * px], (int64_t)px);
+    }
+  };
+  std::vector<std::thread> th_;
+  for (int t = 1; t < nthreads; ++t) th_.emplace_back(fn);
+  fn();
+  for (auto& t : th_) t.join();
+  return orc_frontend_batch_mt(p, gray.data(), depth, B, w, h, Tcw, cam, th, nn_ratio, check_ori, line_nfeatures,
+                               line_desc_th, nthreads, n_out, nmatches_out, nl_out, line_nmatches_out);
+}

@@ -35,12 +35,39 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def build_native() -> str:
+    """-O3 -march=native build of the same sources ON THIS HOST, for the timed CPU baseline (the
+    reference builds with -O3 -march=native).  The portable x86-64-v3 build stays the checker of the tests."""
+    import hashlib
+    flags = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith(("flags", "model name")):
+                    flags += line
+                if line.strip() == "" and flags:
+                    break
+    except OSError:
+        pass
+    # one file per host CPU: a build made for another machine (e.g. in the build container) is never loaded here
+    so = os.path.join(_HERE, "_build", f"libpsl_oracle_native_{hashlib.sha1(flags.encode()).hexdigest()[:10]}.so")
+    subprocess.check_call(["make", "-s", "-C", _HERE, "native", f"NATIVE_OUT={so}"], stdout=subprocess.DEVNULL)
+    return so
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
+        so = _SO
+        if os.environ.get("PSL_ORACLE_NATIVE") == "1":
+            try:
+                so = build_native()
+            except Exception:   # no compiler on this host: the portable build
+                so = _SO
+        if so == _SO and not os.path.exists(_SO):
             build()
-        _lib = C.CDLL(_SO)
+        _lib = C.CDLL(so)
+        _lib.path = so
         _lib.orc_fast_atan2.restype = C.c_float
         _lib.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         _lib.orc_ic_angle.restype = C.c_float
@@ -270,6 +297,31 @@ def frontend_batch_mt(gray, depth, Tcw12, cam6, p: OrbParams | None = None, th=1
     if rc != 0:
         raise RuntimeError("orc_frontend_batch_mt failed")
     return n, nm, nl, lnm
+
+
+def rgbd_frontend_batch_mt(color, rgb_order, depth, Tcw12, cam6, p: OrbParams | None = None, th=15.0, nn_ratio=0.9,
+                           check_ori=True, line_nfeatures=200, line_desc_th=0.95, nthreads: int = 1):
+    """GrabImageRGBD for a batch: cvtColor -> GRAY (cv2 4.13 arithmetic), then frontend_batch_mt.  color [B,H,W,3|4] u8."""
+    p = p or params()
+    color = np.ascontiguousarray(color, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    B, H, W, ch = color.shape
+    T = np.ascontiguousarray(Tcw12, np.float32).reshape(B, 12)
+    cam = np.ascontiguousarray(cam6, np.float32)
+    n, nm, nl, lnm = (np.zeros(B, np.int32) for _ in range(4))
+    rc = lib().orc_rgbd_frontend_batch_mt(C.byref(p), _p(color), ch, int(bool(rgb_order)), _p(depth), B, W, H, _p(T), _p(cam),
+                                          C.c_float(th), C.c_float(nn_ratio), int(check_ori), int(line_nfeatures),
+                                          C.c_float(line_desc_th), int(nthreads), _p(n), _p(nm), _p(nl), _p(lnm))
+    if rc != 0:
+        raise RuntimeError(f"orc_rgbd_frontend_batch_mt rc={rc}")
+    return n, nm, nl, lnm
+
+
+def color_to_gray(color, rgb_order=True):
+    color = np.ascontiguousarray(color, np.uint8)
+    gray = np.empty(color.shape[:-1], np.uint8)
+    lib().orc_color_to_gray(_p(color), color.shape[-1], int(bool(rgb_order)), _p(gray), C.c_int64(gray.size))
+    return gray
 
 
 def match_triangulation(kf1, fv1, kf2, fv2, F12, ex, ey, scale2, sigma2, only_stereo=False, check_ori=True, th_low=50):

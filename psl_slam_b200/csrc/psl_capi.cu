@@ -316,7 +316,8 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
     }
     ctx->quota[L - 1] = std::max(cfg->orb_nfeatures - sum, 0);
   }
-  ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : 512;
+  // frames per extraction chunk: every per-chunk buffer is sized by it, so a context made for single frames stays small
+  ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : std::min(512, std::max(cfg->max_batch, 1));
   ctx->line_chunk = cfg->line_chunk_frames > 0 ? cfg->line_chunk_frames : std::min(std::max(cfg->max_batch, 64), 4096);
   ctx->pool_cap = cfg->orb_max_candidates > 0 ? cfg->orb_max_candidates : std::max(16384, 32 * cfg->orb_nfeatures);
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -356,6 +357,12 @@ void psl_destroy(psl_ctx* ctx) {
                     &ctx->m_assign, &ctx->m_nm})
     cudaFree(b->p);
   for (DevBuf& b : ctx->m_misc) cudaFree(b.p);
+  for (psl_ctx::FeedSlot& f : ctx->feed) {
+    cudaFree(f.color.p); cudaFree(f.depth.p); cudaFree(f.Tcw.p);
+    if (f.up_done) cudaEventDestroy(f.up_done);
+    if (f.free_ev) cudaEventDestroy(f.free_ev);
+  }
+  cudaFree(ctx->feed_gray.p);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

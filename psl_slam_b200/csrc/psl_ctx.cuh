@@ -69,6 +69,16 @@ struct psl_ctx {
   DevBuf m_kps, m_ur, m_desc, m_q, m_qdesc, m_claimed, m_n, m_cell_start, m_cell_items, m_cand, m_cand_count,
       m_best, m_accepted, m_assign, m_nm, m_misc[16];
 
+  // psl_track_rgbd_batch_begin / _end: two staging sets of the raw inputs (colour, depth, poses) + the gray frames
+  struct FeedSlot {
+    DevBuf color, depth, Tcw;
+    cudaEvent_t up_done = nullptr, free_ev = nullptr;
+    int B = 0, w = 0, h = 0, channels = 0, rgb_order = 0;
+    bool pending = false;
+  } feed[2];
+  int feed_head = 0, feed_tail = 0;
+  DevBuf feed_gray;
+
   // staging for the host-pointer entry points (grown on demand)
   uint8_t* d_in = nullptr; size_t d_in_bytes = 0;
   psl_keypoint* d_kps = nullptr; size_t d_kps_bytes = 0;

@@ -161,11 +161,11 @@ struct HostFeed { const uint8_t* gray; const uint16_t* depth; const float* Tcw; 
 // landed, the line path (which needs all gray frames and is the longer of the two) starts after the last slice,
 // depth and poses follow behind the gray frames, and `early_out` (device->host copies of the point results)
 // travel back while the line path is still running.
-int frontend_core(psl_ctx* ctx, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
-                  uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px, int32_t B,
-                  int32_t w, int32_t h, float* d_Tcw, const psl_camera* cam, const psl_track_params* prm,
-                  float line_desc_th, const psl_frontend_out* o, const HostFeed* feed, const Copy* early_out,
-                  int n_out) {
+int frontend_core_impl(psl_ctx* ctx, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
+                       uint16_t* d_depth, int32_t depth_stride_px, int64_t depth_frame_stride_px, int32_t B,
+                       int32_t w, int32_t h, float* d_Tcw, const psl_camera* cam, const psl_track_params* prm,
+                       float line_desc_th, const psl_frontend_out* o, const HostFeed* feed, const Copy* early_out,
+                       int n_out) {
   if (!ctx) return PSL_E_INVALID;
   if (!o || !o->kl || !o->ldesc || !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || o->line_cap < 1 ||
       o->line_cap > kMaxLinesPerFrame)
@@ -257,6 +257,24 @@ int frontend_core(psl_ctx* ctx, uint8_t* d_gray, int32_t gray_stride, int64_t gr
   PSL_CK(cudaGetLastError());
   return PSL_OK;
 }
+
+// An error after the fork leaves work on the line and copy streams that the main stream never joined; the next call
+// would reuse the staging those streams still read.  Drain them before reporting the error.
+int frontend_core(psl_ctx* ctx, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride, uint16_t* d_depth,
+                  int32_t depth_stride_px, int64_t depth_frame_stride_px, int32_t B, int32_t w, int32_t h, float* d_Tcw,
+                  const psl_camera* cam, const psl_track_params* prm, float line_desc_th, const psl_frontend_out* o,
+                  const HostFeed* feed, const Copy* early_out, int n_out) {
+  cudaStream_t main_st = ctx ? ctx->stream : nullptr;
+  const int rc = frontend_core_impl(ctx, d_gray, gray_stride, gray_frame_stride, d_depth, depth_stride_px,
+                                    depth_frame_stride_px, B, w, h, d_Tcw, cam, prm, line_desc_th, o, feed, early_out, n_out);
+  if (rc && ctx) {
+    ctx->stream = main_st;
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+    if (ctx->stream_copy) cudaStreamSynchronize(ctx->stream_copy);
+    cudaStreamSynchronize(main_st);
+  }
+  return rc;
+}
 }  // namespace
 
 extern "C" {
@@ -270,22 +288,18 @@ int psl_track_frontend_batch_dev(psl_ctx* ctx, const uint8_t* d_gray, int32_t gr
                        nullptr, nullptr, 0);
 }
 
-int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
-                             const float* Tcw, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
-                             const psl_frontend_out* o) {
-  if (!ctx) return PSL_E_INVALID;
-  if (!gray || !depth || !Tcw || !o || !o->kps || !o->desc || !o->n || !o->u_right || !o->z || !o->assign || !o->nmatches ||
-      !o->kl || !o->ldesc || !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || B < 0 || w <= 0 || h <= 0 ||
-      o->cap < 1 || o->line_cap < 1)
-    return fail(ctx, PSL_E_INVALID, "bad argument");
-  if (B == 0) return PSL_OK;
-  PSL_CK(cudaSetDevice(ctx->cfg.device));
+}  // extern "C"
+
+namespace {
+// The combined front end with HOST outputs: results are staged in HBM and copied back; the point results travel while
+// the line path is still running.  Inputs are either in HBM already (feed == nullptr) or come from `feed` (then
+// d_gray / d_depth / d_Tcw are the staging buffers they are uploaded to).  Synchronises before returning.
+int frontend_to_host(psl_ctx* ctx, uint8_t* d_gray, uint16_t* d_depth, float* d_Tcw, const HostFeed* feed, int32_t B,
+                     int32_t w, int32_t h, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                     const psl_frontend_out* o) {
   const size_t px = (size_t)w * h, nk = (size_t)B * o->cap, nl = (size_t)B * o->line_cap;
   DevBuf* M = ctx->m_misc;
   int rc;
-  if ((rc = ensure(ctx, M[0], px * B))) return rc;
-  if ((rc = ensure(ctx, M[1], px * B * 2))) return rc;
-  if ((rc = ensure(ctx, M[2], (size_t)B * 12 * 4))) return rc;
   if ((rc = ensure(ctx, M[3], nk * sizeof(psl_keypoint)))) return rc;
   if ((rc = ensure(ctx, M[4], nk * 32))) return rc;
   if ((rc = ensure(ctx, M[5], (size_t)B * 16))) return rc;  // n | nmatches | nl | line_nmatches
@@ -297,7 +311,6 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
   if ((rc = ensure(ctx, ctx->l_eq, nl * 24))) return rc;
   if ((rc = ensure(ctx, ctx->l_n, nl * 4))) return rc;  // line_assign
   cudaStream_t st = ctx->stream;
-  const HostFeed feed{gray, depth, Tcw};
   int32_t* d_n = M[5].as<int32_t>();
   psl_frontend_out d = *o;
   d.kps = M[3].as<psl_keypoint>(); d.desc = M[4].as<uint8_t>(); d.n = d_n; d.nmatches = d_n + B;
@@ -307,8 +320,8 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
   const Copy early_out[7] = {{o->kps, d.kps, nk * sizeof(psl_keypoint)}, {o->desc, d.desc, nk * 32},
                              {o->n, d.n, (size_t)B * 4},  {o->nmatches, d.nmatches, (size_t)B * 4},
                              {o->u_right, d.u_right, nk * 4}, {o->z, d.z, nk * 4}, {o->assign, d.assign, nk * 4}};
-  rc = frontend_core(ctx, M[0].as<uint8_t>(), w, (int64_t)px, M[1].as<uint16_t>(), w, (int64_t)px, B, w, h,
-                     M[2].as<float>(), cam, prm, line_desc_th, &d, &feed, early_out, 7);
+  rc = frontend_core(ctx, d_gray, w, (int64_t)px, d_depth, w, (int64_t)px, B, w, h, d_Tcw, cam, prm, line_desc_th, &d, feed,
+                     early_out, 7);
   if (rc) return rc;
   PSL_CK(cudaMemcpyAsync(o->kl, d.kl, nl * sizeof(psl_keyline), cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(o->ldesc, d.ldesc, nl * 32, cudaMemcpyDeviceToHost, st));
@@ -317,6 +330,126 @@ int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* 
   PSL_CK(cudaMemcpyAsync(o->line_nmatches, d.line_nmatches, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
   PSL_CK(cudaMemcpyAsync(o->line_assign, d.line_assign, nl * 4, cudaMemcpyDeviceToHost, st));
   return check_status(ctx);
+}
+
+bool bad_host_out(const psl_frontend_out* o) {
+  return !o || !o->kps || !o->desc || !o->n || !o->u_right || !o->z || !o->assign || !o->nmatches || !o->kl || !o->ldesc ||
+         !o->lineeq || !o->nl || !o->line_assign || !o->line_nmatches || o->cap < 1 || o->line_cap < 1;
+}
+}  // namespace
+
+extern "C" {
+
+int psl_track_frontend_batch(psl_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int32_t B, int32_t w, int32_t h,
+                             const float* Tcw, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* o) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!gray || !depth || !Tcw || bad_host_out(o) || B < 0 || w <= 0 || h <= 0) return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const size_t px = (size_t)w * h;
+  DevBuf* M = ctx->m_misc;
+  int rc;
+  if ((rc = ensure(ctx, M[0], px * B))) return rc;
+  if ((rc = ensure(ctx, M[1], px * B * 2))) return rc;
+  if ((rc = ensure(ctx, M[2], (size_t)B * 12 * 4))) return rc;
+  const HostFeed feed{gray, depth, Tcw};
+  return frontend_to_host(ctx, M[0].as<uint8_t>(), M[1].as<uint16_t>(), M[2].as<float>(), &feed, B, w, h, cam, prm,
+                          line_desc_th, o);
+}
+
+// ---- Tracking::GrabImageRGBD for a batch (src/Tracking.cc:214-243): colour -> gray on the device, then the combined
+// front end.  The host-pointer form is split in two so that a caller can keep the PCIe link busy: _begin only enqueues the
+// uploads of a batch into one of two staging sets, _end runs the oldest begun batch and returns its results; begin(k+1)
+// before end(k) overlaps the upload of batch k+1 with the kernels of batch k.
+int psl_track_rgbd_batch_dev(psl_ctx* ctx, const uint8_t* d_color, int32_t channels, int32_t rgb_order, int32_t color_stride,
+                             int64_t color_frame_stride, const uint16_t* d_depth, int32_t depth_stride_px,
+                             int64_t depth_frame_stride_px, int32_t B, int32_t w, int32_t h, const float* d_Tcw,
+                             const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* out) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!d_color || (channels != 3 && channels != 4) || B < 0 || w <= 0 || h <= 0 || color_stride < w * channels)
+    return fail(ctx, PSL_E_INVALID, "bad argument (3 or 4 channels)");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  const int gp = (w + 15) & ~15;
+  if ((rc = ensure(ctx, ctx->feed_gray, (size_t)gp * h * B))) return rc;
+  size_t e = prof_mark(ctx);
+  launch_color_to_gray(d_color, channels, rgb_order, color_stride, color_frame_stride, ctx->feed_gray.as<uint8_t>(), gp,
+                       (int64_t)gp * h, B, w, h, ctx->stream);
+  prof_span(ctx, 6, e, 1);
+  return frontend_core(ctx, ctx->feed_gray.as<uint8_t>(), gp, (int64_t)gp * h, const_cast<uint16_t*>(d_depth), depth_stride_px,
+                       depth_frame_stride_px, B, w, h, const_cast<float*>(d_Tcw), cam, prm, line_desc_th, out, nullptr,
+                       nullptr, 0);
+}
+
+int psl_track_rgbd_batch_begin(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32_t rgb_order,
+                               const uint16_t* depth, int32_t B, int32_t w, int32_t h, const float* Tcw) {
+  if (!ctx) return PSL_E_INVALID;
+  if (!color || !depth || !Tcw || (channels != 3 && channels != 4) || B < 1 || w <= 0 || h <= 0)
+    return fail(ctx, PSL_E_INVALID, "bad argument (3 or 4 channels)");
+  psl_ctx::FeedSlot& s = ctx->feed[ctx->feed_head];
+  if (s.pending) return fail(ctx, PSL_E_INVALID, "two batches are already in flight: call psl_track_rgbd_batch_end first");
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  const size_t px = (size_t)w * h;
+  int rc;
+  if ((rc = ensure(ctx, s.color, px * channels * B))) return rc;
+  if ((rc = ensure(ctx, s.depth, px * 2 * B))) return rc;
+  if ((rc = ensure(ctx, s.Tcw, (size_t)B * 48))) return rc;
+  if (!s.up_done) {
+    PSL_CK(cudaEventCreateWithFlags(&s.up_done, cudaEventDisableTiming));
+    PSL_CK(cudaEventCreateWithFlags(&s.free_ev, cudaEventDisableTiming));
+  } else {
+    PSL_CK(cudaStreamWaitEvent(ctx->stream_copy, s.free_ev, 0));   // the batch that used this set has been computed
+  }
+  cudaStream_t cs = ctx->stream_copy;
+  PSL_CK(cudaMemcpyAsync(s.color.p, color, px * channels * B, cudaMemcpyHostToDevice, cs));
+  PSL_CK(cudaMemcpyAsync(s.depth.p, depth, px * 2 * B, cudaMemcpyHostToDevice, cs));
+  PSL_CK(cudaMemcpyAsync(s.Tcw.p, Tcw, (size_t)B * 48, cudaMemcpyHostToDevice, cs));
+  PSL_CK(cudaEventRecord(s.up_done, cs));
+  s.B = B; s.w = w; s.h = h; s.channels = channels; s.rgb_order = rgb_order;
+  s.pending = true;
+  ctx->feed_head ^= 1;
+  return PSL_OK;
+}
+
+int psl_track_rgbd_batch_end(psl_ctx* ctx, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
+                             const psl_frontend_out* o) {
+  if (!ctx) return PSL_E_INVALID;
+  psl_ctx::FeedSlot& s = ctx->feed[ctx->feed_tail];
+  if (!s.pending) return fail(ctx, PSL_E_INVALID, "no batch in flight: call psl_track_rgbd_batch_begin first");
+  if (!cam || !prm || bad_host_out(o)) return fail(ctx, PSL_E_INVALID, "bad argument");
+  // frontend_to_host works on tightly packed device frames; the gray staging is written that way when w is a multiple of 16
+  if (s.w & 15) return fail(ctx, PSL_E_INVALID, "psl_track_rgbd_batch: width must be a multiple of 16");
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  s.pending = false;
+  ctx->feed_tail ^= 1;
+  int rc;
+  const int gp = (s.w + 15) & ~15;
+  if ((rc = ensure(ctx, ctx->feed_gray, (size_t)gp * s.h * s.B))) return rc;
+  PSL_CK(cudaStreamWaitEvent(ctx->stream, s.up_done, 0));
+  size_t e = prof_mark(ctx);
+  launch_color_to_gray(s.color.as<uint8_t>(), s.channels, s.rgb_order, s.w * s.channels, (int64_t)s.w * s.h * s.channels,
+                       ctx->feed_gray.as<uint8_t>(), gp, (int64_t)gp * s.h, s.B, s.w, s.h, ctx->stream);
+  prof_span(ctx, 6, e, 1);
+  rc = frontend_to_host(ctx, ctx->feed_gray.as<uint8_t>(), s.depth.as<uint16_t>(), s.Tcw.as<float>(), nullptr, s.B, s.w, s.h,
+                        cam, prm, line_desc_th, o);
+  // the set may be overwritten once everything enqueued so far has run (frontend_to_host synchronised on success)
+  cudaEventRecord(s.free_ev, ctx->stream);
+  return rc;
+}
+
+int psl_track_rgbd_batch(psl_ctx* ctx, const uint8_t* color, int32_t channels, int32_t rgb_order, const uint16_t* depth,
+                         int32_t B, int32_t w, int32_t h, const float* Tcw, const psl_camera* cam,
+                         const psl_track_params* prm, float line_desc_th, const psl_frontend_out* out) {
+  if (!ctx) return PSL_E_INVALID;
+  if (B == 0) return PSL_OK;
+  if (ctx->feed[0].pending || ctx->feed[1].pending)
+    return fail(ctx, PSL_E_INVALID, "a begun batch is in flight: finish it with psl_track_rgbd_batch_end");
+  const int rc = psl_track_rgbd_batch_begin(ctx, color, channels, rgb_order, depth, B, w, h, Tcw);
+  if (rc) return rc;
+  return psl_track_rgbd_batch_end(ctx, cam, prm, line_desc_th, out);
 }
 
 
