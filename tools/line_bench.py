@@ -16,12 +16,17 @@ def main():
     a = ap.parse_args()
     import torch
     from psl_slam_b200 import LINEextractor, synth, KEYLINE_DTYPE
+    idx = torch.from_numpy(np.arange(a.frames) % a.distinct).cuda()
     if a.lowtex:
         gray = np.stack([synth.make_lowtex(100 + i) for i in range(a.distinct)])
+        d = torch.from_numpy(gray).cuda()[idx].contiguous()
+    elif a.distinct > 32:   # the bench's frames: rendered on the device
+        import bench
+        rgb, _, _ = bench.render_sequence_cuda(4, a.distinct, 640, 480, torch.device("cuda"))
+        d = bench.gray_cuda(rgb)[idx].contiguous()
     else:
         gray, _, _ = synth.sequence(4, a.distinct)
-    idx = np.arange(a.frames) % a.distinct
-    d = torch.from_numpy(gray).cuda()[torch.from_numpy(idx).cuda()].contiguous()
+        d = torch.from_numpy(gray).cuda()[idx].contiguous()
     ex = LINEextractor(chunk_frames=a.chunk)
     cap = ex.cap
     kl = torch.zeros(a.frames * cap * 68, dtype=torch.uint8, device="cuda")
