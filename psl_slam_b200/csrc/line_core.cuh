@@ -39,6 +39,9 @@ constexpr double kPi = 3.14159265358979323846;
 struct Seg { float v[4]; };
 
 // Scratch of one frame (all arrays sized for `cap` segments).
+// pair-scan record of the warp-cooperative kernel: segment | angle | denominator of PointLineDistance
+struct alignas(16) ScanRec { Seg s; float angle, pad; double den; };
+
 struct MergeScratch {
   int cap;
   float* angles;     // [cap]
@@ -56,6 +59,7 @@ struct MergeScratch {
   uint16_t* fw;      // [cap][kNbCap] a row's own partners (warp-cooperative kernel only)
   double* den;       // [cap] sqrt(a^2 + b^2) of PointLineDistance per line, scan order (warp-cooperative kernel only)
   uint32_t* sort_cnt;  // bucket counters of the rank sort, shared memory (warp-cooperative kernel only)
+  ScanRec* scan;       // [cap] lines in scan order (warp-cooperative kernel only)
 };
 
 PSL_LN_HD float point_line_distance(const Seg& l, float x0, float y0) {  // uselongline.cpp:5-15

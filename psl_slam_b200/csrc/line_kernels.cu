@@ -40,6 +40,7 @@ namespace linew {
 using line::kNbCap;
 using line::MergeScratch;
 using line::Seg;
+using line::ScanRec;
 constexpr unsigned kFull = 0xffffffffu;
 
 // stable rank sort of 0..n-1 by key ascending (desc = false) or descending; out[rank] = index.  Every caller sorts
@@ -140,12 +141,20 @@ __device__ void rank_sort(uint16_t* bkt, uint16_t* out, int n, const float* key,
   __syncwarp();
 }
 
-// line::point_line_distance with the line's denominator sqrt(a^2 + b^2) taken from the per-line table
-__device__ __forceinline__ float pld_den(const Seg& l, double den, float x0, float y0) {
+// line::point_line_distance(l, x0, y0) > thr with the line's denominator sqrt(a^2 + b^2) taken from the per-line table.
+// The reference compares (float)((double)num / den) with thr; the fp64 division is about forty instructions and the
+// outcome is obvious for all but a sliver of the pairs, so the quotient is only formed when num is within 0.1 % of
+// thr * den (or den is not a positive finite number).
+__device__ __forceinline__ bool pld_exceeds(const Seg& l, double den, float x0, float y0, float thr) {
   const float x1 = l.v[0], y1 = l.v[1], x2 = l.v[2], y2 = l.v[3];
   const float num = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(y2, y1), x0), __fmul_rn(__fsub_rn(x1, x2), y0)),
                                     __fsub_rn(__fmul_rn(x2, y1), __fmul_rn(x1, y2))));
-  return (float)((double)num / den);
+  const double t = (double)thr * den, dn = (double)num;
+  if (den > 0.0 && t < 1e300) {
+    if (dn > t * 1.001) return true;
+    if (dn < t * 0.999) return false;
+  }
+  return (float)(dn / den) > thr;
 }
 
 __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, float distance_thr, float endpoint_threshold,
@@ -164,15 +173,20 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   rank_sort(S.tmp16, S.order, n, S.angles, false, lane, S.sort_cnt, S.check);
   // segments and angles in scan order, so that the pair scan reads them with plain coalesced loads instead of a
   // chain of dependent gathers (dst is free until the folds at the end)
-  Seg* sseg = dst;
+  // one 32-byte record per line: segment, angle, denominator of PointLineDistance (it depends on the line only,
+  // uselongline.cpp:5-15) — two 16-byte loads per partner off one pointer
+  ScanRec* srec = S.scan;
   for (int j = lane; j < n; j += 32) {
     const int id = S.order[j];
     const Seg sj = src[id];
-    sseg[j] = sj;
-    S.sangles[j] = S.angles[id];
-    // the denominator of PointLineDistance (uselongline.cpp:5-15) depends on the line only
     const double a = (double)__fsub_rn(sj.v[3], sj.v[1]), b = (double)__fsub_rn(sj.v[0], sj.v[2]);
-    S.den[j] = sqrt(a * a + b * b);
+    ScanRec r;
+    r.s = sj;
+    r.angle = S.angles[id];
+    r.pad = 0.f;
+    r.den = sqrt(a * a + b * b);
+    srec[j] = r;
+    S.sangles[j] = r.angle;   // (the bisection over a vertical line's far partners reads the angles alone)
   }
   __syncwarp();
   POST_T1(0, t_sort);
@@ -197,36 +211,49 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
     const int i = base + lane;
     if (i < n) {
       const int idx1 = S.order[i];
-      const Seg s1 = sseg[i];
+      const ScanRec r1 = srec[i];
+      const Seg s1 = r1.s;
       float x11 = s1.v[0], y11 = s1.v[1], x12 = s1.v[2], y12 = s1.v[3];
-      const float angle1 = S.sangles[i];
+      const float angle1 = r1.angle;
       const bool sx = fabsf(angle1) < quater_PI;
       if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
       const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
       const float mx1 = (float)(0.5 * (double)__fadd_rn(s1.v[0], s1.v[2])), my1 = (float)(0.5 * (double)__fadd_rn(s1.v[1], s1.v[3]));
-      const double den1 = S.den[i];
+      const double den1 = r1.den;
       int fc = 0;
-      for (int j = i + 1; j < n; ++j) {
-        if (line::angle_diff(angle1, S.sangles[j]) > angle_thr) {
+      // The partners are read one iteration ahead (angle, segment, denominator of the next j are requested before the
+      // current one is tested): the working set of the resident frames does not fit L1, so every partner is an L2 round
+      // trip that would otherwise sit in the loop's dependency chain.
+      int j = i + 1;
+      ScanRec r_nx = r1;
+      if (j < n) r_nx = srec[j];
+      while (j < n) {
+        const float angle2 = r_nx.angle;
+        const Seg s2 = r_nx.s;
+        const double den2 = r_nx.den;
+        const int jc = j;
+        ++j;
+        if (j < n) r_nx = srec[j];
+        if (line::angle_diff(angle1, angle2) > angle_thr) {
           if (can_break) break;   // the scalar loop stops at the first partner whose angle gap is too large
           // A near-vertical segment `continue`s past such partners instead.  In the angle-sorted order they form one
           // contiguous run: |a2 - a1| grows with j, pi + a1 - a2 (the wrap-around branch of AngleDiff) shrinks, so
           // only the partners right after i and the ones at the far end of the list (the other vertical direction)
           // can pass.  Skip the run: first j whose gap is small again, by bisection on the same fp32 predicate.
-          int lo = j + 1, hi = n;
+          int lo = jc + 1, hi = n;
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (line::angle_diff(angle1, S.sangles[mid]) > angle_thr) lo = mid + 1;
             else hi = mid;
           }
-          j = lo - 1;  // the loop increment brings it to lo
+          j = lo;
+          if (j < n) r_nx = srec[j];
           continue;
         }
-        const Seg s2 = sseg[j];
         float x21 = s2.v[0], y21 = s2.v[1], x22 = s2.v[2], y22 = s2.v[3];
         if ((sx && (x22 < x21)) || ((!sx) && y22 < y21)) { float t = x21; x21 = x22; x22 = t; t = y21; y21 = y22; y22 = t; }
         const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
-        if (pld_den(s2, S.den[j], mx1, my1) > distance_thr && pld_den(s1, den1, mx2, my2) > distance_thr) continue;
+        if (pld_exceeds(s2, den2, mx1, my1, distance_thr) && pld_exceeds(s1, den1, mx2, my2, distance_thr)) continue;
         float cx12, cy12, cx21, cy21;
         if ((sx && x12 > x22) || (!sx && y12 > y22)) { cx12 = x22; cy12 = y22; cx21 = x11; cy21 = y11; }
         else { cx12 = x12; cy12 = y12; cx21 = x21; cy21 = y21; }
@@ -236,7 +263,7 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
           to_merge = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < ep_thr;
         }
         if (!to_merge) continue;
-        const int idx2 = S.order[j];
+        const int idx2 = S.order[jc];
         const int b = atomicAdd(&bcnt[idx2], 1);   // slot in idx2's list of earlier rows (unordered until the pass below)
         if (fc < kNbCap && b < kNbCap) {
           S.fw[idx1 * kNbCap + fc] = (uint16_t)idx2;
@@ -274,47 +301,92 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   // connected components (:153-190) and sub-clusters (:193-229): heads of the output lines, in output order
   uint16_t* heads = S.order;  // the angle order is no longer needed
   int nd = 0;
-  if (lane == 0) {
-    for (int i = 0; i < n; ++i) {
-      if (S.code[i] >= 0) continue;
-      S.code[i] = 1;
+  // The scalar loop (one cluster at a time, breadth first; a round's frontier is the std::set of the uncoded neighbours of
+  // the previous one, i.e. ascending) with every inner loop spread over the lanes: the members of a round are appended
+  // in frontier order through a ballot prefix, their neighbours are flagged by all lanes, and the flagged range is
+  // swept 32 entries at a time into the next frontier.  Flags set for lines that join in the same round are dropped by
+  // the sweep exactly as the scalar code drops them.
+  const unsigned lt = (1u << lane) - 1u;
+  float* key2 = S.sangles;   // the scan-order angles are dead: sort keys of a cluster's members
+  uint16_t* sorted = reinterpret_cast<uint16_t*>(S.angles);   // (so are the unsorted angles / back counters)
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    for (;;) {
+      const int ii = i0 + lane;
+      const unsigned open = __ballot_sync(kFull, ii < n && S.code[ii] < 0);
+      if (!open) break;
+      const int i = i0 + __ffs(open) - 1;
       uint16_t* cl = S.tmp16;
-      int cs = 0, ncheck = 0;
-      cl[cs++] = (uint16_t)i;
-      for (int k = 0; k < S.nb_cnt[i]; ++k) S.check[ncheck++] = S.nb[i * kNbCap + k];
+      int cs = 1, ncheck = S.nb_cnt[i];
+      if (lane == 0) { S.code[i] = 1; cl[0] = (uint16_t)i; }
+      for (int k = lane; k < ncheck; k += 32) S.check[k] = S.nb[i * kNbCap + k];
+      __syncwarp();
       while (ncheck > 0) {
+        // (a) the frontier joins the cluster, in frontier order
+        for (int c0 = 0; c0 < ncheck; c0 += 32) {
+          const int c = c0 + lane;
+          const int j = c < ncheck ? S.check[c] : 0;
+          const bool join = c < ncheck && S.code[j] < 0;
+          const unsigned bal = __ballot_sync(kFull, join);
+          if (join) { S.code[j] = 1; cl[cs + __popc(bal & lt)] = (uint16_t)j; }
+          cs += __popc(bal);
+        }
+        __syncwarp();
+        // (b) flag the uncoded neighbours of the frontier
         int lo = n, hi = -1;
-        for (int c = 0; c < ncheck; ++c) {
+        for (int c = lane; c < ncheck; c += 32) {
           const int j = S.check[c];
-          if (S.code[j] < 0) { S.code[j] = 1; cl[cs++] = (uint16_t)j; }
-          for (int k = 0; k < S.nb_cnt[j]; ++k) {
+          const int cnt = S.nb_cnt[j];
+          for (int k = 0; k < cnt; ++k) {
             const int q = S.nb[j * kNbCap + k];
             if (S.code[q] < 0) { S.flag[q] = 1; lo = q < lo ? q : lo; hi = q > hi ? q : hi; }
           }
         }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+          lo = min(lo, __shfl_xor_sync(kFull, lo, d));
+          hi = max(hi, __shfl_xor_sync(kFull, hi, d));
+        }
+        __syncwarp();
+        // (c) the flagged lines, ascending, are the next frontier
         ncheck = 0;
-        for (int q = lo; q <= hi; ++q)
-          if (S.flag[q]) {
-            S.flag[q] = 0;
-            if (S.code[q] < 0) S.check[ncheck++] = (uint16_t)q;
-          }
+        for (int q0 = lo; q0 <= hi; q0 += 32) {
+          const int q = q0 + lane;
+          const bool f = q <= hi && S.flag[q] != 0;
+          if (f) S.flag[q] = 0;
+          const unsigned bal = __ballot_sync(kFull, f);   // (every flagged line is still uncoded: (a) ran before (b))
+          if (f) S.check[ncheck + __popc(bal & lt)] = (uint16_t)q;
+          ncheck += __popc(bal);
+        }
+        __syncwarp();
       }
       if (cs <= 2) {  // fold(cluster) == fold(head, neighbours(head)): the only possible neighbour is the other member
-        heads[nd++] = cl[0];
+        if (lane == 0) heads[nd] = cl[0];
+        ++nd;
         continue;
       }
-      line::stable_sort_idx(cl, S.check, cs, S.length, true);
-      for (int k = 0; k < cs; ++k) { S.loc[cl[k]] = (uint16_t)k; S.flag[k] = 0; }
-      for (int j = 0; j < cs; ++j) {
-        if (S.flag[j]) continue;
-        const int li = cl[j];
-        for (int k = 0; k < S.nb_cnt[li]; ++k) S.flag[S.loc[S.nb[li * kNbCap + k]]] = 1;
-        heads[nd++] = (uint16_t)li;
+      // sub-clusters (:193-229): members by length, descending and stable; every member not yet covered heads a
+      // sub-cluster and covers its neighbours (inherently sequential, a handful of steps)
+      for (int k = lane; k < cs; k += 32) key2[k] = S.length[cl[k]];
+      __syncwarp();
+      rank_sort_quadratic(S.check, cs, key2, true, lane);   // check[r] = position in cl of the r-th longest
+      for (int k = lane; k < cs; k += 32) sorted[k] = cl[S.check[k]];
+      __syncwarp();
+      for (int k = lane; k < cs; k += 32) { S.loc[sorted[k]] = (uint16_t)k; S.flag[k] = 0; }
+      __syncwarp();
+      if (lane == 0) {
+        for (int j = 0; j < cs; ++j) {
+          if (S.flag[j]) continue;
+          const int li = sorted[j];
+          for (int k = 0; k < S.nb_cnt[li]; ++k) S.flag[S.loc[S.nb[li * kNbCap + k]]] = 1;
+          heads[nd++] = (uint16_t)li;
+        }
       }
-      for (int k = 0; k < cs; ++k) S.flag[k] = 0;
+      nd = __shfl_sync(kFull, nd, 0);
+      __syncwarp();
+      for (int k = lane; k < cs; k += 32) S.flag[k] = 0;
+      __syncwarp();
     }
   }
-  nd = __shfl_sync(kFull, nd, 0);
   __syncwarp();
   POST_T1(2, t_bfs);
   POST_T0(t_fold);
@@ -400,7 +472,7 @@ __global__ void __launch_bounds__(kPostWarps * 32, 8)
   const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
   line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
                        L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o,
-                       L.m_fw + o * line::kNbCap, L.m_den + o, sort_cnt[threadIdx.x >> 5]};
+                       L.m_fw + o * line::kNbCap, L.m_den + o, sort_cnt[threadIdx.x >> 5], L.m_scan + o};
   line::Seg* raw = reinterpret_cast<line::Seg*>(L.raw) + o;
   POST_T0(t_all);
   const int n = linew::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,

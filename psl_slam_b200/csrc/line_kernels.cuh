@@ -44,6 +44,7 @@ struct LineBuffers {
   uint16_t* m_nb;      // [C][raw_cap][kNbCap]
   uint16_t* m_fw;      // [C][raw_cap][kNbCap]
   double* m_den;       // [C][raw_cap]
+  line::ScanRec* m_scan;  // [C][raw_cap]
   uint16_t* m_nb_cnt;
   int16_t* m_code;
   uint16_t* m_check;
