@@ -230,62 +230,68 @@ __global__ void __launch_bounds__(kFastThreads)
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Dense path (thresholds <= 127).
-//
-// score kernel: a CTA owns a 112 x 30 tile of a level's detection window.  The 144 x 38 pixel box the tile's
-// scores depend on is staged in shared memory by one TMA tensor copy (out-of-image bytes arrive as zeros); the
-// compass reject runs on 4 adjacent pixels per thread with byte-SIMD (VABSDIFF4 + a carry-free ">" on packed
-// bytes); the survivors are compacted, get exact scores two at a time on u16x2 lanes, and the per-cell NMS is
-// applied (a neighbour in another cell counts as 0, exactly as in the cell sub-images of the reference).
-// Output: the level's score map, u8 = score of a corner at iniThFAST that survives the NMS, else 0.  The map
-// lives in the level's blur buffer, which is not written until the blur stage that follows FAST and the octree.
-// collect kernel: a warp per cell turns the non-zero bytes of the cell's interior into the raster-ordered
-// candidate slice of the pool (popc prefix sums); a cell without any goes to the fallback list, which the
-// per-cell kernel above redoes at minThFAST (:812-816).
-// ---------------------------------------------------------------------------------------------
-constexpr int kTW = 112, kTH = 30;          // core tile (pixels whose map bytes this CTA writes); the TMA box must
-                                            // start on a 16-byte boundary of the row, hence a multiple of 16
-constexpr int kSW = 128, kSH = 32;          // scored region: core + 4 columns / 1 row of rim on each side (120 columns used)
-constexpr int kPR = kSH + 6;                // pixel rows staged
-constexpr int kPWords = 36, kPP = 144;      // pixel words per row used / row pitch in bytes (= TMA box width)
-constexpr int kScoreThreads = 256;
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#undef PSL_DIV
+
+// ---------------------------------------------------------------------------------------------
+// Fused dense path (thresholds <= 127): one kernel from pixels to the raster-ordered candidate slices.
+//
+// A CTA owns up to four neighbouring cells of one cell row.  Cell interiors tile the detection window without overlap
+// and the reference's non-maximum suppression never looks across a cell seam (every cv::FAST call sees its own
+// sub-image), so a tile made of whole cells needs no halo of scores at all — only the 3-pixel ring FAST itself reads.
+//   1. the (h_cell + 6) x 160 pixel box arrives by ONE TMA tensor copy (per-level descriptor; out-of-image bytes = 0);
+//   2. compass reject, 4 pixels per thread-row with byte SIMD; survivors compacted into a shared list;
+//   3. exact scores two at a time on u16x2 lanes -> shared score tile + list of corners at iniThFAST;
+//   4. NMS over the corners only (neighbours in another cell or outside the interior count as 0) -> keep bitmap;
+//   5. a warp per cell turns its rows of the bitmap into the cell's slice of the pool: popc prefix over the rows, one
+//      atomicAdd for the slice, entries written in raster order.  A cell without any corner goes to the fallback list
+//      that the per-cell kernel redoes at minThFAST (:812-816).
+// No score map in HBM, no second kernel reading it back.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRW = 128;                  // scored columns per tile (4 per lane)
+constexpr int kRP = 160;                  // pixel row pitch = TMA box width
+constexpr int kRHmax = kInteriorMax;      // interior rows of a cell
+constexpr int kRowsThreads = 256;
+
+__host__ __device__ inline int fast_group_cells(int w_cell) { return w_cell >= 63 ? 1 : (kRW - 3) / w_cell > 4 ? 4 : (kRW - 3) / w_cell; }
+
 template <bool ALIGNED>
-__global__ void __launch_bounds__(kScoreThreads)
-    fast_score_tiles_kernel(const OrbGeometry* __restrict__ geo, ImgBatch in0, const __grid_constant__ FastMaps maps,
-                            int ini_th) {
-  __shared__ __align__(128) uint8_t s_px[kPR][kPP];
-  __shared__ __align__(16) uint8_t s_sc[kSH][kSW];
-  __shared__ uint16_t s_list[kSH * kSW];
-  __shared__ uint16_t s_list2[kTH * kTW];
+__global__ void __launch_bounds__(kRowsThreads)
+    fast_rows_kernel(const OrbGeometry* __restrict__ geo, ImgBatch in0, const __grid_constant__ FastMaps maps, int ini_th,
+                     int redo_empty, uint32_t* __restrict__ pool, int pool_cap, uint32_t* __restrict__ pool_count,
+                     uint2* __restrict__ cell_tab, uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
+                     uint32_t* __restrict__ status) {
+  __shared__ __align__(128) uint8_t s_px[kRHmax + 6][kRP];
+  __shared__ __align__(16) uint8_t s_sc[kRHmax][kRW];
+  __shared__ uint32_t s_keep[kRHmax][kRW / 32];
+  __shared__ uint16_t s_list[kRHmax * kRW];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_n, s_n2;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.y;
   const uint32_t te = __ldg(geo->fast_tab + blockIdx.x);
-  const int lvl = (int)(te >> 24), ty = (int)((te >> 12) & 0xFFFu), tx = (int)(te & 0xFFFu);
-  const int cx0 = kMinBorder + kTW * tx, cy0 = kMinBorder + 3 + kTH * ty;
-  const int gx0 = cx0 - 16, gy0 = cy0 - 4;  // level coordinates of shared pixel (0, 0)
+  const int lvl = (int)(te >> 24), ci = (int)((te >> 14) & 0x3FFu), cj0 = (int)((te >> 4) & 0x3FFu), nc = (int)(te & 0xFu);
+  const CellGrid g = geo->grid[lvl];
+  // interiors: cell cj covers level x in [19 + cj * w_cell, ...) clipped at max_bx - 3; rows [ya, ya + ih)
+  const int xa0 = kMinBorder + 3 + cj0 * g.w_cell, ya = kMinBorder + 3 + ci * g.h_cell;
+  const int Wt = min(nc * g.w_cell, g.max_bx - 3 - xa0), ih = min(g.h_cell, g.max_by - 3 - ya);
+  const int X0 = (xa0 - 7) & ~15, Y0 = ya - 3;      // level coordinates of shared pixel (0, 0); X0 is the TMA box origin
+  const int c0 = xa0 - X0, c_lo = c0 & ~3;          // first interior column, first scored column (>= 4, a word boundary)
+  const int cofs = c0 - c_lo;                       // interior starts at scored column cofs (0..3)
   const bool tma = (maps.valid >> lvl) & 1u;
+  const int rows_px = g.h_cell + 6;
   if (tma && tid == 0) {
     const uint32_t bar = smem_u32(&s_bar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kPR * kPP) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(rows_px * kRP) : "memory");
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(&s_px[0][0])), "l"(reinterpret_cast<const void*>(&maps.m[lvl][0])), "r"(gx0), "r"(gy0), "r"(b),
+        ::"r"(smem_u32(&s_px[0][0])), "l"(reinterpret_cast<const void*>(&maps.m[lvl][0])), "r"(X0), "r"(Y0), "r"(b),
         "r"(bar)
         : "memory");
   }
-  const CellGrid g = geo->grid[lvl];
-  const int x_lo = kMinBorder + 3, x_hi = g.max_bx - 3, y_lo = kMinBorder + 3, y_hi = g.max_by - 3;
-  uint8_t* __restrict__ map = geo->blur[lvl].ptr + (size_t)b * geo->blur[lvl].frame_stride;
-  const int mp = geo->blur[lvl].pitch;
-
   if (!tma) {  // the layout has no descriptor (caller's image with odd strides): plain loads
     const uint8_t* __restrict__ img;
     int pitch, h, w;
@@ -296,11 +302,11 @@ __global__ void __launch_bounds__(kScoreThreads)
       img = geo->level[lvl].ptr + (size_t)b * geo->level[lvl].frame_stride;
       pitch = geo->level[lvl].pitch; w = geo->level[lvl].w; h = geo->level[lvl].h;
     }
-    for (int i = tid; i < kPR * kPWords; i += kScoreThreads) {
-      const int r = i / kPWords, wc = i - r * kPWords;
-      const int y = gy0 + r, x = gx0 + 4 * wc;
+    for (int i = tid; i < rows_px * (kRP / 4); i += kRowsThreads) {
+      const int r = i / (kRP / 4), wc = i - r * (kRP / 4);
+      const int y = Y0 + r, x = X0 + 4 * wc;
       uint32_t v = 0;
-      if (y < h) {
+      if (y >= 0 && y < h) {
         const uint8_t* p = img + (size_t)y * pitch + x;
         if (ALIGNED) {
           if (x + 4 <= pitch) v = __ldg(reinterpret_cast<const uint32_t*>(p));
@@ -313,14 +319,9 @@ __global__ void __launch_bounds__(kScoreThreads)
       reinterpret_cast<uint32_t*>(&s_px[r][0])[wc] = v;
     }
   }
-  reinterpret_cast<uint4*>(&s_sc[0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);  // 32 x 128 B = 256 x 16 B
+  for (int i = tid; i < ih * (kRW / 16); i += kRowsThreads) reinterpret_cast<uint4*>(&s_sc[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < ih * (kRW / 32); i += kRowsThreads) (&s_keep[0][0])[i] = 0u;
   if (tid == 0) { s_n = 0; s_n2 = 0; }
-  // the core of the map starts as zeros; the corners that survive are stored after the barriers below
-  for (int i = tid; i < kTH * (kTW / 8); i += kScoreThreads) {
-    const int r = i / (kTW / 8), c8 = i - r * (kTW / 8);
-    const int y = cy0 + r, x = cx0 + 8 * c8;
-    if (y < y_hi && x < x_hi) *reinterpret_cast<uint2*>(map + (size_t)y * mp + x) = make_uint2(0u, 0u);
-  }
   __syncthreads();
   if (tma) {
     const uint32_t bar = smem_u32(&s_bar);
@@ -332,196 +333,161 @@ __global__ void __launch_bounds__(kScoreThreads)
     }
   }
 
-  // ---- compass reject, 4 pixels per thread-row: a corner needs (up or down) and (left or right) further than
-  // t from the centre.  d > t on packed bytes: ((d & 0x7f) + (127 - t)) | d has bit 7 set.
+  // ---- compass reject, 4 pixels per thread-row: a corner needs (up or down) and (left or right) further than t from
+  // the centre.  d > t on packed bytes: ((d & 0x7f) + (127 - t)) | d has bit 7 set.
   {
-    const int x = cx0 - 4 + 4 * lane;
-    uint32_t vm = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (x + k >= x_lo && x + k < x_hi && lane < (kTW + 8) / 4) vm |= 0x80u << (8 * k);
-    const uint32_t K = (uint32_t)(127 - ini_th) * 0x01010101u;
-    uint32_t M = 0;  // bit 8 j + k: pixel j of this thread's group in its row k survives
+    uint32_t vm = 0;   // bytes of this lane's word that are interior columns
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int r = wid * 4 + k, y = cy0 - 1 + r;
-      const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_px[r + 3][0]) + 3 + lane;
-      const uint32_t wc = rc[0], wl = rc[-1], wr = rc[1];
-      const uint32_t wu = rc[-3 * (kPP / 4)], wd = rc[3 * (kPP / 4)];
-      const uint32_t left = __funnelshift_r(wl, wc, 8), right = __funnelshift_r(wc, wr, 24);  // x-3 / x+3
-      const uint32_t du = __vabsdiffu4(wc, wu), dd = __vabsdiffu4(wc, wd);
-      const uint32_t dl = __vabsdiffu4(wc, left), dr = __vabsdiffu4(wc, right);
-      const uint32_t ud = ((du & 0x7f7f7f7fu) + K) | ((dd & 0x7f7f7f7fu) + K) | du | dd;
-      const uint32_t lr = ((dl & 0x7f7f7f7fu) + K) | ((dr & 0x7f7f7f7fu) + K) | dl | dr;
-      const uint32_t m = (y >= y_lo && y < y_hi) ? (ud & lr & vm) : 0u;
-      M |= m >> (7 - k);
+      const int cc = 4 * lane + k - cofs;
+      if (cc >= 0 && cc < Wt) vm |= 0x80u << (8 * k);
     }
-    const int cnt = __popc(M);
-    int inc = cnt;
+    const uint32_t K = (uint32_t)(127 - ini_th) * 0x01010101u;
+    constexpr int kRT = 5;   // rows per thread and pass: 8 warps x 5 rows cover a cell row of up to 40 interior rows at once
+    for (int r0 = 0; r0 < ih; r0 += 8 * kRT) {
+      uint32_t M = 0;  // bit 8 j + k: pixel j of this thread's group in its row k survives
 #pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, inc, dlt);
-      if (lane >= dlt) inc += a;
-    }
-    int base = 0;
-    if (lane == 31 && inc) base = atomicAdd(&s_n, inc);
-    int pos = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-    const uint32_t e0 = ((uint32_t)(wid * 4) << 7) | (uint32_t)(4 * lane);  // entry = scored row << 7 | scored column
-    while (M) {
-      const uint32_t bit = (uint32_t)__ffs(M) - 1u;
-      M &= M - 1;
-      s_list[pos++] = (uint16_t)(e0 + ((bit & 7u) << 7) + (bit >> 3));
+      for (int k = 0; k < kRT; ++k) {
+        const int r = r0 + wid * kRT + k;
+        if (r < ih && vm) {
+          const uint32_t* rc = reinterpret_cast<const uint32_t*>(&s_px[r + 3][0]) + (c_lo >> 2) + lane;
+          const uint32_t wc = rc[0], wl = rc[-1], wr = rc[1];
+          const uint32_t wu = rc[-3 * (kRP / 4)], wd = rc[3 * (kRP / 4)];
+          const uint32_t left = __funnelshift_r(wl, wc, 8), right = __funnelshift_r(wc, wr, 24);  // x-3 / x+3
+          const uint32_t du = __vabsdiffu4(wc, wu), dd = __vabsdiffu4(wc, wd);
+          const uint32_t dl = __vabsdiffu4(wc, left), dr = __vabsdiffu4(wc, right);
+          const uint32_t ud = ((du & 0x7f7f7f7fu) + K) | ((dd & 0x7f7f7f7fu) + K) | du | dd;
+          const uint32_t lr = ((dl & 0x7f7f7f7fu) + K) | ((dr & 0x7f7f7f7fu) + K) | dl | dr;
+          M |= (ud & lr & vm) >> (7 - k);
+        }
+      }
+      // the order of the survivors does not matter (scores are per pixel, the NMS and the output work off bitmaps): one
+      // shared atomic per thread that has any
+      int pos = M ? atomicAdd(&s_n, __popc(M)) : 0;
+      const uint32_t e0 = ((uint32_t)(r0 + wid * kRT) << 7) | (uint32_t)(4 * lane);  // entry = row << 7 | scored column
+      while (M) {
+        const uint32_t bit = (uint32_t)__ffs(M) - 1u;
+        M &= M - 1;
+        s_list[pos++] = (uint16_t)(e0 + ((bit & 7u) << 7) + (bit >> 3));
+      }
     }
   }
   __syncthreads();
 
-  // ---- exact scores of the survivors, two per thread (scored (r, c) = shared pixel (r + 3, c + 12)) -------------
+  // ---- exact scores of the survivors, two per thread (scored (r, c) = shared pixel (r + 3, c_lo + c)) ---------------
   const int n = s_n;
-  for (int k = 2 * tid; k < n; k += 2 * kScoreThreads) {
+  constexpr int kHalf = kRHmax * kRW / 2;
+  const bool two_lists = n <= kHalf;
+  for (int k = 2 * tid; k < n; k += 2 * kRowsThreads) {
     const int ea = s_list[k], eb = s_list[min(k + 1, n - 1)];
     const int ra = ea >> 7, ca = ea & 127, rb = eb >> 7, cb = eb & 127;
-    const unsigned sc = fast_score_pair<kPP>(&s_px[ra + 3][ca + 12], &s_px[rb + 3][cb + 12]);
+    const unsigned sc = fast_score_pair<kRP>(&s_px[ra + 3][c_lo + ca], &s_px[rb + 3][c_lo + cb]);
     const unsigned sa = sc & 0xFFFFu, sb = sc >> 16;
-    if (sa >= (unsigned)ini_th) {
-      s_sc[ra][ca] = (uint8_t)sa;
-      if (ra >= 1 && ra <= kTH && ca >= 4 && ca < 4 + kTW) s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)ea;
-    }
-    if (k + 1 < n && sb >= (unsigned)ini_th) {
-      s_sc[rb][cb] = (uint8_t)sb;
-      if (rb >= 1 && rb <= kTH && cb >= 4 && cb < 4 + kTW) s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)eb;
+    const bool ka = sa >= (unsigned)ini_th, kb = k + 1 < n && sb >= (unsigned)ini_th;
+    if (ka) s_sc[ra][ca] = (uint8_t)sa;
+    if (kb) s_sc[rb][cb] = (uint8_t)sb;
+    if (two_lists && (ka || kb)) {   // the corners, for the NMS pass (upper half of the list array, free when n is small)
+      const int q = atomicAdd(&s_n2, (int)ka + (int)kb);
+      if (ka) s_list[kHalf + q] = (uint16_t)ea;
+      if (kb) s_list[kHalf + q + (int)ka] = (uint16_t)eb;
     }
   }
   __syncthreads();
 
-  // ---- NMS inside the cell the pixel belongs to ----------------------------------------------------------------
-  const int n2 = s_n2;
-  const float rcp_wc = __frcp_rn((float)g.w_cell), rcp_hc = __frcp_rn((float)g.h_cell);
-  for (int k = tid; k < n2; k += kScoreThreads) {
-    const int e = s_list2[k], r = e >> 7, c = e & 127;
-    const int x = cx0 - 4 + c, y = cy0 - 1 + r;
-    // position inside the cell: (x - x_lo) mod w_cell without an integer divide (quotient of values < 2^13 by
-    // a divisor <= 60: the true quotient + 0.5 / d is far from an integer compared with the fp32 error)
-    const int lx = (x - x_lo) - (int)(((float)(x - x_lo) + 0.5f) * rcp_wc) * g.w_cell;
-    const int ly = (y - y_lo) - (int)(((float)(y - y_lo) + 0.5f) * rcp_hc) * g.h_cell;
-    const unsigned ml = lx != 0 ? 0xFFu : 0u, mr = lx != g.w_cell - 1 ? 0xFFu : 0u;
-    const unsigned mu = ly != 0 ? 0xFFu : 0u, md = ly != g.h_cell - 1 ? 0xFFu : 0u;
-    const uint8_t* r0 = &s_sc[r - 1][c];
+  // ---- NMS inside the cell the corner belongs to -> keep bitmap -------------------------------------------------------
+  const float rcp_wc = __frcp_rn((float)g.w_cell);
+  const int n_nms = two_lists ? s_n2 : n;
+  const uint16_t* nms_list = two_lists ? s_list + kHalf : s_list;
+  for (int k = tid; k < n_nms; k += kRowsThreads) {
+    const int e = nms_list[k], r = e >> 7, c = e & 127;
+    if (!two_lists && s_sc[r][c] == 0) continue;
+    const int xt = c - cofs;                                  // column inside the tile's interior
+    // xt mod w_cell without an integer divide (values < 2^8, divisor <= 60: the quotient + 0.5 / d is far from an
+    // integer compared with the fp32 error)
+    const int cell = (int)(((float)xt + 0.5f) * rcp_wc), lx = xt - cell * g.w_cell;
+    const int iwk = min(g.w_cell, Wt - cell * g.w_cell);
+    const unsigned ml = lx != 0 ? 0xFFu : 0u, mr = lx != iwk - 1 ? 0xFFu : 0u;
+    const unsigned mu = r != 0 ? 0xFFu : 0u, md = r != ih - 1 ? 0xFFu : 0u;
+    const uint8_t* r0 = &s_sc[max(r - 1, 0)][c];
     const uint8_t* r1 = &s_sc[r][c];
-    const uint8_t* r2 = &s_sc[r + 1][c];
-    const unsigned up = max(max(r0[-1] & ml, (unsigned)r0[0]), r0[1] & mr) & mu;
-    const unsigned dn = max(max(r2[-1] & ml, (unsigned)r2[0]), r2[1] & mr) & md;
-    const unsigned mid = max(r1[-1] & ml, r1[1] & mr);
-    const unsigned sc = r1[0];
-    if (sc > max(max(up, dn), mid)) map[(size_t)y * mp + x] = (uint8_t)sc;
+    const uint8_t* r2 = &s_sc[min(r + 1, ih - 1)][c];
+    const int cm = max(c - 1, 0) - c, cp = min(c + 1, kRW - 1) - c;
+    const unsigned up = max(max(r0[cm] & ml, (unsigned)r0[0]), r0[cp] & mr) & mu;
+    const unsigned dn = max(max(r2[cm] & ml, (unsigned)r2[0]), r2[cp] & mr) & md;
+    const unsigned mid = max(r1[cm] & ml, r1[cp] & mr);
+    if ((unsigned)r1[0] > max(max(up, dn), mid)) atomicOr(&s_keep[r][c >> 5], 1u << (c & 31));
   }
-}
+  __syncthreads();
 
-constexpr int kCollectWarps = 8;
-constexpr int kCollectCap = (kInteriorMax * kInteriorMax + 3) / 4;  // NMS survivors of a cell: at most one per 2x2 block
-
-// A warp per cell, one pass: the interior is read as whole words, `rpi` rows per warp step (2 when a row has at
-// most 16 words; a lane always holds the same word column, so its byte mask is fixed), five steps in flight.
-// Corners go to a per-warp shared list in raster order (steps ascending, lanes ascending = row then word, bytes
-// ascending); the list is copied to the cell's slice of the pool once its length is known.
-__global__ void __launch_bounds__(kCollectWarps * 32)
-    fast_collect_kernel(const OrbGeometry* __restrict__ geo, int redo_empty, uint32_t* __restrict__ pool, int pool_cap,
-                        uint32_t* __restrict__ pool_count, uint2* __restrict__ cell_tab,
-                        uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
-                        uint32_t* __restrict__ status) {
-  __shared__ uint32_t s_out[kCollectWarps][kCollectCap];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, b = blockIdx.y;
-  const int cell = blockIdx.x * kCollectWarps + wid;
-  const int cells = geo->total_cells;
-  if (cell >= cells) return;
-  const uint32_t ce = __ldg(geo->fast_tab + geo->n_tiles + cell);
-  const int lvl = (int)(ce >> 24), ci = (int)((ce >> 12) & 0xFFFu), cj = (int)(ce & 0xFFFu);
-  const CellGrid g = geo->grid[lvl];
-  uint2* tab = cell_tab + (size_t)b * cells + cell;
-  // interior of the cell (:789-806): level x in [xa, xa + iw), y in [ya, ya + ih)
-  const int xa = kMinBorder + 3 + cj * g.w_cell, ya = kMinBorder + 3 + ci * g.h_cell;
-  const int iw = min(g.w_cell, g.max_bx - 3 - xa), ih = min(g.h_cell, g.max_by - 3 - ya);
-  if (iw <= 0 || ih <= 0) {
-    if (lane == 0) *tab = make_uint2(0u, 0u);
-    return;
-  }
-  const int mp = geo->blur[lvl].pitch;
-  const int w0 = xa >> 2, nw = ((xa + iw + 3) >> 2) - w0;
-  const int two = nw <= 16, wi = two ? (lane & 15) : lane, sub = two ? (lane >> 4) : 0, rpi = two ? 2 : 1;
-  // bytes of this lane's word column that belong to the interior
-  uint32_t lmask = wi < nw ? 0xFFFFFFFFu : 0u;
-  if (wi == 0) lmask &= 0xFFFFFFFFu << (8 * (xa & 3));
-  if (wi == nw - 1 && ((xa + iw) & 3)) lmask &= ~(0xFFFFFFFFu << (8 * ((xa + iw) & 3)));
-  const uint32_t* __restrict__ col = reinterpret_cast<const uint32_t*>(
-      geo->blur[lvl].ptr + (size_t)b * geo->blur[lvl].frame_stride + (size_t)(ya + sub) * mp) + w0 + min(wi, nw - 1);
-  const int stride = rpi * (mp >> 2), nit = (ih + rpi - 1) / rpi;
-  const uint32_t xy0 = pack_cand(4 * (w0 + wi) - kMinBorder, ya + sub - kMinBorder, 0);  // level coordinate - minBorder
-  uint32_t* list = s_out[wid];
-  int run = 0;
-  constexpr int kFlight = 5;
-  for (int it0 = 0; it0 < nit; it0 += kFlight) {
-    uint32_t v[kFlight];
-#pragma unroll
-    for (int k = 0; k < kFlight; ++k) {
-      const int it = it0 + k;
-      v[k] = (it * rpi + sub < ih) ? __ldg(col + (size_t)it * stride) : 0u;
+  // ---- a warp per cell: the cell's rows of the bitmap -> its slice of the pool, raster order -------------------------
+  if (wid < nc) {
+    const int cell = g.first_cell + ci * g.n_cols + cj0 + wid;
+    const int cells = geo->total_cells;
+    uint2* tab = cell_tab + (size_t)b * cells + cell;
+    const int cs = cofs + wid * g.w_cell;                    // first scored column of the cell
+    const int iwk = min(g.w_cell, Wt - wid * g.w_cell);
+    if (iwk <= 0 || ih <= 0) {
+      if (lane == 0) *tab = make_uint2(0u, 0u);
+      return;
     }
+    // bits of row r that belong to the cell, as a 64-bit mask starting at the cell's first column (iwk <= 60)
+    auto row_bits = [&](int r) -> unsigned long long {
+      const int w0 = cs >> 5, sh = cs & 31;
+      const unsigned long long lo = (unsigned long long)s_keep[r][w0] | ((unsigned long long)(w0 + 1 < kRW / 32 ? s_keep[r][w0 + 1] : 0u) << 32);
+      unsigned long long v = lo >> sh;
+      if (sh && w0 + 2 < kRW / 32) v |= (unsigned long long)s_keep[r][w0 + 2] << (64 - sh);
+      return v & ((1ull << iwk) - 1ull);
+    };
+    const unsigned long long m0 = lane < ih ? row_bits(lane) : 0ull;
+    const unsigned long long m1 = lane + 32 < ih ? row_bits(lane + 32) : 0ull;
+    const int c0n = __popcll(m0), c1n = __popcll(m1);
+    int i0 = c0n, i1 = c1n;
 #pragma unroll
-    for (int k = 0; k < kFlight; ++k) {
-      const uint32_t vv = v[k] & lmask;
-      uint32_t nz = (((vv & 0x7f7f7f7fu) + 0x7f7f7f7fu) | vv) & 0x80808080u;
-      if (!__any_sync(0xffffffffu, nz != 0u)) continue;
-      const int c = __popc(nz);
-      int inc = c;
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, inc, dlt);
-        if (lane >= dlt) inc += a;
-      }
-      int pos = run + inc - c;
-      run += __shfl_sync(0xffffffffu, inc, 31);
-      const uint32_t xy = xy0 + ((uint32_t)((it0 + k) * rpi) << 8);
-      while (nz) {
-        const int j = (__ffs(nz) - 1) >> 3;
-        nz &= nz - 1;
-        if (pos < kCollectCap) list[pos] = xy + ((uint32_t)j << 20) + ((vv >> (8 * j)) & 0xFFu);
-        ++pos;
-      }
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int a0 = __shfl_up_sync(0xffffffffu, i0, dlt), a1 = __shfl_up_sync(0xffffffffu, i1, dlt);
+      if (lane >= dlt) { i0 += a0; i1 += a1; }
     }
-  }
-  const int total = run;
-  if (total == 0) {
+    const int t0 = __shfl_sync(0xffffffffu, i0, 31), total = t0 + __shfl_sync(0xffffffffu, i1, 31);
+    if (total == 0) {
+      if (lane == 0) {
+        if (redo_empty) {
+          *tab = make_uint2(0xFFFFFFFFu, 0u);
+          fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)b * (uint32_t)cells + (uint32_t)cell;
+        } else {
+          *tab = make_uint2(0u, 0u);
+        }
+      }
+      return;
+    }
+    uint32_t base = 0;
     if (lane == 0) {
-      if (redo_empty) {
-        *tab = make_uint2(0xFFFFFFFFu, 0u);
-        fb_list[atomicAdd(fb_count, 1u)] = (uint32_t)b * (uint32_t)cells + (uint32_t)cell;
-      } else {
-        *tab = make_uint2(0u, 0u);
-      }
+      base = atomicAdd(pool_count + b, (uint32_t)total);
+      *tab = make_uint2(base, (uint32_t)total);
+      if (base + total > (uint32_t)pool_cap) atomicOr(status, kStatCandOverflow);
     }
-    return;
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + total > (uint32_t)pool_cap) return;
+    uint32_t* out = pool + (size_t)b * pool_cap + base;
+    // level coordinate - minBorder of the cell's first interior pixel
+    const uint32_t x_rel = (uint32_t)(xa0 + wid * g.w_cell - kMinBorder), y_rel = (uint32_t)(ya - kMinBorder);
+    auto emit = [&](unsigned long long m, int r, int pos) {
+      while (m) {
+        const int x = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        out[pos++] = pack_cand((int)x_rel + x, (int)y_rel + r, s_sc[r][cs + x]);
+      }
+    };
+    emit(m0, lane, i0 - c0n);
+    emit(m1, lane + 32, t0 + i1 - c1n);
   }
-  uint32_t base = 0;
-  if (lane == 0) {
-    base = atomicAdd(pool_count + b, (uint32_t)total);
-    *tab = make_uint2(base, (uint32_t)total);
-    if (base + total > (uint32_t)pool_cap) atomicOr(status, kStatCandOverflow);
-    if (total > kCollectCap) atomicOr(status, kStatNodeOverflow);  // cannot happen: NMS survivors are never adjacent
-  }
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (base + total > (uint32_t)pool_cap || total > kCollectCap) return;
-  __syncwarp();
-  uint32_t* out = pool + (size_t)b * pool_cap + base;
-  for (int i = lane; i < total; i += 32) out[i] = list[i];
 }
-
-#undef PSL_DIV
 
 int fast_tile_count(const OrbGeometry& geo) {
   int n = 0;
   for (int l = 0; l < geo.nlevels; ++l) {
     const CellGrid& cg = geo.grid[l];
-    const int ntx = (cg.max_bx - 3 - kMinBorder + kTW - 1) / kTW, nty = (cg.max_by - 3 - (kMinBorder + 3) + kTH - 1) / kTH;
-    n += (ntx > 0 && nty > 0) ? ntx * nty : 0;
+    const int G = fast_group_cells(cg.w_cell);
+    n += cg.n_rows * ((cg.n_cols + G - 1) / G);
   }
   return n;
 }
@@ -530,9 +496,10 @@ void fast_build_tab(const OrbGeometry& geo, uint32_t* tab) {
   int n = 0;
   for (int l = 0; l < geo.nlevels; ++l) {
     const CellGrid& cg = geo.grid[l];
-    const int ntx = (cg.max_bx - 3 - kMinBorder + kTW - 1) / kTW, nty = (cg.max_by - 3 - (kMinBorder + 3) + kTH - 1) / kTH;
-    for (int ty = 0; ty < nty; ++ty)
-      for (int tx = 0; tx < ntx; ++tx) tab[n++] = ((uint32_t)l << 24) | ((uint32_t)ty << 12) | (uint32_t)tx;
+    const int G = fast_group_cells(cg.w_cell);
+    for (int ci = 0; ci < cg.n_rows; ++ci)
+      for (int cj = 0; cj < cg.n_cols; cj += G)
+        tab[n++] = ((uint32_t)l << 24) | ((uint32_t)ci << 14) | ((uint32_t)cj << 4) | (uint32_t)std::min(G, cg.n_cols - cj);
   }
   for (int l = 0; l < geo.nlevels; ++l) {
     const CellGrid& cg = geo.grid[l];
@@ -547,7 +514,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 bool fast_encode_map(FastMaps& maps, int level, const void* ptr, int w, int h, int pitch, int64_t frame_stride,
-                     int frames) {
+                     int frames, int box_rows) {
   static_assert(sizeof(CUtensorMap) == 128, "FastMaps slot size");
   static EncodeTiledFn encode = [] {
     void* fn = nullptr;
@@ -558,10 +525,12 @@ bool fast_encode_map(FastMaps& maps, int level, const void* ptr, int w, int h, i
     return reinterpret_cast<EncodeTiledFn>(fn);
   }();
   maps.valid &= ~(1u << level);
-  if (!encode || ((uintptr_t)ptr & 15) || (pitch & 15) || (frame_stride & 15) || frames < 1) return false;
+  if (!encode || ((uintptr_t)ptr & 15) || (pitch & 15) || (frame_stride & 15) || frames < 1 || box_rows < 1 ||
+      box_rows > kRHmax + 6)
+    return false;
   const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
   const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
-  const cuuint32_t box[3] = {(cuuint32_t)kPP, (cuuint32_t)kPR, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)kRP, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = encode(reinterpret_cast<CUtensorMap*>(&maps.m[level][0]), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
                             const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -589,15 +558,16 @@ void launch_fast_cells(const OrbGeometry* d_geo, const OrbGeometry& geo, ImgBatc
                                                               pool, pool_cap, pool_count, cell_tab, status);
     return;
   }
-  fast_encode_map(maps, 0, in0.ptr, in0.w, in0.h, in0.pitch, in0.frame_stride, B);
+  fast_encode_map(maps, 0, in0.ptr, in0.w, in0.h, in0.pitch, in0.frame_stride, B, geo.grid[0].h_cell + 6);
   const int redo = min_th < ini_th;
   if (redo) cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
   dim3 tgrid(geo.n_tiles, B);
-  if (aligned) fast_score_tiles_kernel<true><<<tgrid, kScoreThreads, 0, st>>>(d_geo, in0, maps, ini_th);
-  else fast_score_tiles_kernel<false><<<tgrid, kScoreThreads, 0, st>>>(d_geo, in0, maps, ini_th);
-  dim3 cgrid((geo.total_cells + kCollectWarps - 1) / kCollectWarps, B);
-  fast_collect_kernel<<<cgrid, kCollectWarps * 32, 0, st>>>(d_geo, redo, pool, pool_cap, pool_count, cell_tab, fb_list,
-                                                            fb_count, status);
+  if (aligned)
+    fast_rows_kernel<true><<<tgrid, kRowsThreads, 0, st>>>(d_geo, in0, maps, ini_th, redo, pool, pool_cap, pool_count,
+                                                          cell_tab, fb_list, fb_count, status);
+  else
+    fast_rows_kernel<false><<<tgrid, kRowsThreads, 0, st>>>(d_geo, in0, maps, ini_th, redo, pool, pool_cap, pool_count,
+                                                           cell_tab, fb_list, fb_count, status);
   if (redo) {
     if (aligned)
       fast_cells_kernel<true><<<list_grid, kFastThreads, 0, st>>>(d_geo, in0, ini_th, min_th, 1, fb_list, fb_count, 0u,

@@ -28,8 +28,8 @@ int fast_tile_count(const OrbGeometry& geo);                       // tiles per 
 void fast_build_tab(const OrbGeometry& geo, uint32_t* host_tab);   // n_tiles + total_cells words
 // descriptor of one level; false when the layout cannot be described (base or strides not 16-byte aligned)
 bool fast_encode_map(FastMaps& maps, int level, const void* ptr, int w, int h, int pitch, int64_t frame_stride,
-                     int frames);
-constexpr int kFastLaunches = 3;  // score tiles + collect + per-cell fallback (the counter memset is not a kernel)
+                     int frames, int box_rows);
+constexpr int kFastLaunches = 2;  // fused rows kernel + per-cell fallback (the counter memset is not a kernel)
 
 // K2: per-cell FAST + NMS + threshold fallback + ordered compaction (ORBextractor.cc:789-829).
 // fb_list: [B * total_cells] u32 scratch (cells to redo at minThFAST), fb_count: one u32.

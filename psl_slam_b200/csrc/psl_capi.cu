@@ -210,7 +210,7 @@ static int set_geometry(psl_ctx* ctx, int w, int h) {
   ctx->fast_maps.valid = 0;
   for (int l = 1; l < L; ++l)
     fast_encode_map(ctx->fast_maps, l, g.level[l].ptr, g.level[l].w, g.level[l].h, g.level[l].pitch,
-                    g.level[l].frame_stride, ctx->chunk);
+                    g.level[l].frame_stride, ctx->chunk, g.grid[l].h_cell + 6);
   PSL_CK(cudaMemcpyAsync(ctx->d_geo, &g, sizeof(g), cudaMemcpyHostToDevice, ctx->stream));
   PSL_CK(cudaStreamSynchronize(ctx->stream));  // `all`, `grouped`, `ftab` and `g` are host temporaries
   ctx->geo_w = w;
