@@ -83,24 +83,20 @@ __global__ void __launch_bounds__(kDescWarps * 32)
   // 19 px): straight from HBM/L2 that is one 32-byte sector per byte.  The warp first copies the two windows
   // into shared memory with row-contiguous word loads (~80 sectors instead of ~540) and gathers from there.
   __shared__ __align__(16) uint8_t s_blur[kDescWarps][39][kWinPitch];
-  __shared__ __align__(16) uint8_t s_raw[kDescWarps][31][kWinPitch];
   const uint8_t* blur_img = geo->blur[lvl].ptr + (size_t)b * geo->blur[lvl].frame_stride;
   const int bp = geo->blur[lvl].pitch;
   const bool aligned = (((uintptr_t)img | (uintptr_t)blur_img) & 3) == 0 && ((pitch | bp) & 3) == 0;
   const int xs = (x - kEdge) & ~3;            // first staged column (word aligned), x - 19 >= 0
   const int nw = ((x + kEdge - xs) >> 2) + 1;  // words per row (<= 11)
   if (aligned) {
-    for (int k = lane; k < 39 * nw; k += 32) {
-      const int r = k / nw, c = k - r * nw;
-      reinterpret_cast<uint32_t*>(&s_blur[warp][r][0])[c] =
-          __ldg(reinterpret_cast<const uint32_t*>(blur_img + (size_t)(y - kEdge + r) * bp + xs) + c);
+    // two rows per step, a word column per lane (no index division): 20 steps for the 39 rows
+    const int c = lane & 15, rs = lane >> 4;
+    if (c < nw) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(blur_img + (size_t)(y - kEdge + rs) * bp + xs) + c;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&s_blur[warp][rs][0]) + c;
+#pragma unroll 4
+      for (int r = rs; r < 39; r += 2, src += (bp >> 1), dst += 2 * (kWinPitch / 4)) *dst = __ldg(src);
     }
-    for (int k = lane; k < 31 * nw; k += 32) {
-      const int r = k / nw, c = k - r * nw;
-      reinterpret_cast<uint32_t*>(&s_raw[warp][r][0])[c] =
-          __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y - kHalfPatch + r) * pitch + xs) + c);
-    }
-    __syncwarp();
   }
   const int xo = x - xs;  // column of the keypoint inside the staged rows
   // ---- IC_Angle: lane r owns patch row v = r - 15 -------------------------------------------
@@ -110,11 +106,23 @@ __global__ void __launch_bounds__(kDescWarps * 32)
     const int d = g_umax[v < 0 ? -v : v];
     int sum = 0;
     if (aligned) {
-      const uint8_t* row = &s_raw[warp][lane][xo];
-      for (int u = -d; u <= d; ++u) {
-        const int val = row[u];
-        sum += val;
-        m10 += u * val;
+      // the row's 2 d + 1 pixels straight from the level image as whole words; sum and first moment of a word are two
+      // byte dot products (pixels u8, offsets u = column - x as s8), bytes outside [-d, d] masked out
+      const int xr = (x - kHalfPatch) & ~3;                       // first word of the widest row
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(img + (size_t)(y + v) * pitch + xr);
+      const uint32_t dd = (uint32_t)d * 0x01010101u, lim = (uint32_t)(2 * d) * 0x01010101u;
+      uint32_t uw = __vadd4((uint32_t)((xr - x) & 0xFF) * 0x01010101u, 0x03020100u);   // u of the word's four bytes
+#pragma unroll
+      for (int w = 0; w < 9; ++w) {   // x - 15 .. x + 15 spans at most 9 aligned words
+        const uint32_t ok = __vcmpleu4(__vadd4(uw, dd), lim);      // 0xFF where -d <= u <= d
+        if (ok) {
+          const uint32_t px = __ldg(row + w) & ok;
+          int t;
+          asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(px), "r"(0x01010101), "r"(0));
+          sum += t;
+          asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(px), "r"(uw), "r"(m10));
+        }
+        uw = __vadd4(uw, 0x04040404u);
       }
     } else {
       const uint8_t* row = img + (size_t)(y + v) * pitch + x;
@@ -131,12 +139,15 @@ __global__ void __launch_bounds__(kDescWarps * 32)
     m10 += __shfl_xor_sync(0xffffffffu, m10, d);
     m01 += __shfl_xor_sync(0xffffffffu, m01, d);
   }
+  __syncwarp();   // the staged blur window is complete
   const float angle = fast_atan2_deg((float)m01, (float)m10);
 
   // ---- steered BRIEF: lane k makes descriptor byte k ----------------------------------------
   const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);  // :107
   const float rad = __fmul_rn(angle, factorPI);
-  const float a = (float)cos((double)rad), bsin = (float)sin((double)rad);
+  double sd, cd;
+  sincos((double)rad, &sd, &cd);   // same values as sin() / cos(), one range reduction
+  const float a = (float)cd, bsin = (float)sd;
   const uint8_t* bl = aligned ? &s_blur[warp][kEdge][xo] : blur_img + (size_t)y * bp + x;
   const int bpp = aligned ? kWinPitch : bp;
   const char4* pat = reinterpret_cast<const char4*>(g_pattern) + lane * 8;
