@@ -88,15 +88,16 @@ __global__ void __launch_bounds__(kDescWarps * 32)
   const bool aligned = (((uintptr_t)img | (uintptr_t)blur_img) & 3) == 0 && ((pitch | bp) & 3) == 0;
   const int xs = (x - kEdge) & ~3;            // first staged column (word aligned), x - 19 >= 0
   const int nw = ((x + kEdge - xs) >> 2) + 1;  // words per row (<= 11)
-  if (aligned) {
-    // two rows per step, a word column per lane (no index division): 20 steps for the 39 rows
-    const int c = lane & 15, rs = lane >> 4;
-    if (c < nw) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(blur_img + (size_t)(y - kEdge + rs) * bp + xs) + c;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(&s_blur[warp][rs][0]) + c;
-#pragma unroll 4
-      for (int r = rs; r < 39; r += 2, src += (bp >> 1), dst += 2 * (kWinPitch / 4)) *dst = __ldg(src);
-    }
+  // two rows per step, a word column per lane (no index division): 20 steps for the 39 rows.  All loads of the warp —
+  // these and the patch rows of IC_Angle below — are issued before anything is consumed: the kernel is bound by the
+  // latency of these L2 / HBM reads, not by instructions.
+  const int sc_ = lane & 15, rs = lane >> 4;
+  uint32_t bv[20];
+  if (aligned && sc_ < nw) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(blur_img + (size_t)(y - kEdge + rs) * bp + xs) + sc_;
+#pragma unroll
+    for (int k = 0; k < 20; ++k)
+      if (rs + 2 * k < 39) bv[k] = __ldg(src + (size_t)k * (bp >> 1));
   }
   const int xo = x - xs;  // column of the keypoint inside the staged rows
   // ---- IC_Angle: lane r owns patch row v = r - 15 -------------------------------------------
@@ -111,17 +112,30 @@ __global__ void __launch_bounds__(kDescWarps * 32)
       const int xr = (x - kHalfPatch) & ~3;                       // first word of the widest row
       const uint32_t* row = reinterpret_cast<const uint32_t*>(img + (size_t)(y + v) * pitch + xr);
       const uint32_t dd = (uint32_t)d * 0x01010101u, lim = (uint32_t)(2 * d) * 0x01010101u;
-      uint32_t uw = __vadd4((uint32_t)((xr - x) & 0xFF) * 0x01010101u, 0x03020100u);   // u of the word's four bytes
+      const uint32_t uw0 = __vadd4((uint32_t)((xr - x) & 0xFF) * 0x01010101u, 0x03020100u);   // u of the word's four bytes
+      uint32_t px[9], okm[9];
+      uint32_t uw = uw0;
 #pragma unroll
       for (int w = 0; w < 9; ++w) {   // x - 15 .. x + 15 spans at most 9 aligned words
-        const uint32_t ok = __vcmpleu4(__vadd4(uw, dd), lim);      // 0xFF where -d <= u <= d
-        if (ok) {
-          const uint32_t px = __ldg(row + w) & ok;
-          int t;
-          asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(px), "r"(0x01010101), "r"(0));
-          sum += t;
-          asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(px), "r"(uw), "r"(m10));
-        }
+        okm[w] = __vcmpleu4(__vadd4(uw, dd), lim);      // 0xFF where -d <= u <= d
+        px[w] = okm[w] ? __ldg(row + w) : 0u;
+        uw = __vadd4(uw, 0x04040404u);
+      }
+      // (the staged blur window goes to shared memory while those loads are in flight)
+      if (sc_ < nw) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_blur[warp][rs][0]) + sc_;
+#pragma unroll
+        for (int k = 0; k < 20; ++k)
+          if (rs + 2 * k < 39) dst[k * 2 * (kWinPitch / 4)] = bv[k];
+      }
+      uw = uw0;
+#pragma unroll
+      for (int w = 0; w < 9; ++w) {
+        const uint32_t p = px[w] & okm[w];
+        int t;
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(p), "r"(0x01010101), "r"(0));
+        sum += t;
+        asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(m10) : "r"(p), "r"(uw), "r"(m10));
         uw = __vadd4(uw, 0x04040404u);
       }
     } else {
@@ -133,6 +147,11 @@ __global__ void __launch_bounds__(kDescWarps * 32)
       }
     }
     m01 = v * sum;
+  } else if (aligned && sc_ < nw) {   // lane 31 has no patch row, only its share of the staging
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_blur[warp][rs][0]) + sc_;
+#pragma unroll
+    for (int k = 0; k < 20; ++k)
+      if (rs + 2 * k < 39) dst[k * 2 * (kWinPitch / 4)] = bv[k];
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
