@@ -177,40 +177,44 @@ __global__ void __launch_bounds__(kCandWarps * 32)
     return true;
   };
 
-  const int ncy = r1 - r0 + 1, ncells = (c1 - c0 + 1) * ncy;
+  // The CSR grid is cell-major with ix outer and iy inner, exactly the enumeration order of GetFeaturesInArea: the cells
+  // (ix, r0 .. r1) of one window column are one contiguous run of items.  A window is therefore a handful of runs
+  // (one per column); the lanes take the items of a run side by side, a ballot keeps the passing ones in order.
+  const int ncols = c1 - c0 + 1;
   int total = 0;
   unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;  // two smallest (dist << 16 | position) seen by this lane
-  for (int base = 0; base < ncells; base += 32) {
-    const int c = base + lane;
-    int s = 0, e = 0;
-    if (c < ncells) {
-      const int ix = c0 + c / ncy, iy = r0 + c % ncy;
-      s = start[ix * PSL_GRID_ROWS + iy];
-      e = start[ix * PSL_GRID_ROWS + iy + 1];
+  const unsigned lt = (1u << lane) - 1u;
+  for (int cb = 0; cb < ncols; cb += 32) {
+    int rs = 0, re = 0;   // run of window column cb + lane
+    if (cb + lane < ncols) {
+      const int ix = c0 + cb + lane;
+      rs = start[ix * PSL_GRID_ROWS + r0];
+      re = start[ix * PSL_GRID_ROWS + r1 + 1];
     }
-    int cnt = 0;
-    for (int k = s; k < e; ++k) cnt += passes(items[k]) ? 1 : 0;
-    int inc = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += o;
-    }
-    int pos = total + inc - cnt;
-    for (int k = s; k < e && cnt; ++k) {
-      const int i = items[k];
-      if (!passes(i)) continue;
-      if (pos < kCandCap) {
-        const uint4 d0 = __ldg(fdesc + 2 * i), d1 = __ldg(fdesc + 2 * i + 1);
-        const unsigned dist = (unsigned)hamming256(q0, q1, d0, d1);
-        out[pos] = ((uint32_t)i << 16) | dist;
-        const unsigned key = (dist << 16) | (unsigned)pos;
-        if (key < k1) { k2 = k1; k1 = key; }
-        else if (key < k2) k2 = key;
+    const int nc = min(32, ncols - cb);
+    for (int c = 0; c < nc; ++c) {
+      const int s = __shfl_sync(0xffffffffu, rs, c), e = __shfl_sync(0xffffffffu, re, c);
+      for (int k0 = s; k0 < e; k0 += 32) {
+        const int k = k0 + lane;
+        int i = 0;
+        bool ok = false;
+        if (k < e) {
+          i = items[k];
+          ok = passes(i);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int pos = total + __popc(bal & lt);
+        if (ok && pos < kCandCap) {
+          const uint4 d0 = __ldg(fdesc + 2 * i), d1 = __ldg(fdesc + 2 * i + 1);
+          const unsigned dist = (unsigned)hamming256(q0, q1, d0, d1);
+          out[pos] = ((uint32_t)i << 16) | dist;
+          const unsigned key = (dist << 16) | (unsigned)pos;
+          if (key < k1) { k2 = k1; k1 = key; }
+          else if (key < k2) k2 = key;
+        }
+        total += __popc(bal);
       }
-      ++pos;
     }
-    total += __shfl_sync(0xffffffffu, inc, 31);
   }
   const unsigned best = warp_min_u32(k1);
   const unsigned second = warp_min_u32(k1 == best ? k2 : k1);
