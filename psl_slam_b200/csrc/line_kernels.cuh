@@ -24,14 +24,9 @@ struct LineBuffers {
   int32_t* max_n2;     // [C]
   int32_t* row_cnt;    // [C][Hs]  defined pixels per row -> exclusive offsets
   int32_t* n_def;      // [C]
-  uint16_t* key_in;    // [C][Hs*Ws]
-  uint16_t* key_out;
-  uint32_t* val_in;    // [C][Hs*Ws]
-  uint32_t* val_out;
-  int32_t* seg_begin;  // [C] segment offsets for the segmented sort
-  int32_t* seg_end;    // [C]
-  void* sort_tmp;
-  size_t sort_tmp_bytes;
+  uint16_t* key_in;    // [C][Hs*Ws]  gradient bin of every seed-capable pixel, raster order
+  uint32_t* val_in;    // [C][Hs*Ws]  its pixel index
+  uint32_t* val_out;   // [C][Hs*Ws]  the pixel indices in seed order (bins descending, raster order inside a bin)
   float* raw;          // [C][raw_cap][4]
   int32_t* n_raw;      // [C]
   line::Seg* t1;       // [C][raw_cap]
@@ -53,13 +48,12 @@ struct LineBuffers {
   short2* gxy;         // [C][h][w] Sobel (dx, dy) of the sigma-1 blurred image
 };
 
-size_t lsd_sort_temp_bytes(int items_per_frame, int frames);
 size_t lsd_lut_bytes();
 size_t lsd_seed_lut_bytes();
 void launch_lsd_lut(float4* lut, float2* seed_lut, cudaStream_t st);
 
 // LSD for `nb` frames (cv::LineSegmentDetector behind LineExtractor.cpp:336-337), three stages:
-// blur + 0.8x resize + gradient + seed keys (6 launches); stable seed ordering (cub segmented radix sort, counted as 1);
+// blur + 0.8x resize + gradient + seed keys (6 launches); stable seed ordering (one counting pass, 1 launch);
 // the sequential region-growing core -> raw segments + counts (1 launch)
 void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t st);
 void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st);

@@ -1,7 +1,5 @@
 // LSD on the device: data-parallel prologue (7x7 sigma-0.75 blur, exact 0.8x resize, 2x2 gradient,
 // stable bin ordering of the seed pixels) and the sequential core (lsd_core.cuh), one frame per warp.
-#include <cub/device/device_segmented_radix_sort.cuh>
-
 #include "line_kernels.cuh"
 #include "lsd_core.cuh"
 #include "orb_kernels.cuh"
@@ -225,8 +223,7 @@ size_t lsd_seed_lut_bytes() { return (size_t)kLutSide * kLutSide * sizeof(float2
 
 // exclusive scan of the per-row counts of every frame (one warp per frame)
 __global__ void __launch_bounds__(32)
-    lsd_row_scan_kernel(int32_t* __restrict__ row_cnt, int Hs, int npx, int32_t* __restrict__ n_def,
-                        int32_t* __restrict__ seg_begin, int32_t* __restrict__ seg_end) {
+    lsd_row_scan_kernel(int32_t* __restrict__ row_cnt, int Hs, int32_t* __restrict__ n_def) {
   const int lane = threadIdx.x, b = blockIdx.x;
   int32_t* rc = row_cnt + (size_t)b * Hs;
   int carry = 0;
@@ -241,11 +238,7 @@ __global__ void __launch_bounds__(32)
     if (base + lane < Hs) rc[base + lane] = carry + inc - v;
     carry += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (lane == 0) {
-    n_def[b] = carry;
-    seg_begin[b] = b * npx;
-    seg_end[b] = b * npx + carry;
-  }
+  if (lane == 0) n_def[b] = carry;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -856,15 +849,6 @@ extern "C" void psl_lsd_stats(unsigned long long* out) {
 }
 #endif
 
-size_t lsd_sort_temp_bytes(int items_per_frame, int frames) {
-  size_t bytes = 0;
-  cub::DeviceSegmentedRadixSort::SortPairsDescending(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr,
-                                                     (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                     (int64_t)items_per_frame * frames, frames, (const int32_t*)nullptr,
-                                                     (const int32_t*)nullptr, 0, 10);
-  return bytes;
-}
-
 void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t st) {
   const int npx = L.Ws * L.Hs;
   ImgBatchMut bl{L.blur, L.pitch, (int64_t)L.pitch * L.h, L.w, L.h};
@@ -886,17 +870,99 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
   while (sqrt((double)(q_undef + 1) / 4.0) <= rho) ++q_undef;
   dim3 rows((L.Hs + 3) / 4, nb);
   lsd_count_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.max_n2, L.row_cnt, q_undef);
-  lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, npx, L.n_def, L.seg_begin, L.seg_end);
+  lsd_row_scan_kernel<<<nb, 32, 0, st>>>(L.row_cnt, L.Hs, L.n_def);
   lsd_gradient_kernel<<<rows, 128, 0, st>>>(L.scaled, L.Ws, L.Hs, L.lut, L.pix, L.max_n2, L.row_cnt, L.key_in, L.val_in,
                                             q_undef);
 }
 
-// stable: bins descending, raster order inside a bin (identical to cv2 4.13 on every golden)
+// ---------------------------------------------------------------------------------------------------
+// Seed order: the 1024-bin ordering of the seed-capable pixels (ll_angle's bucket lists), bins descending, raster
+// order inside a bin (stable: identical to cv2 4.13 on every golden).  One counting pass per frame, one CTA per frame:
+// the (bin, pixel) pairs arrive in raster order; warp w owns the w-th contiguous eighth of them.
+//   1. every warp counts its segment into its own 1024 counters (shared memory);
+//   2. a block scan turns them into start offsets, bins descending, segments in order inside a bin;
+//   3. every warp walks its segment again, 32 pairs per step: lanes with the same bin form a group (match.any), the
+//      group takes its slots from the warp's counter of that bin with one add, ranks inside a group are lane order.
+// Steps of a warp are sequential and segments are ordered, so equal bins keep the raster order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kOrdWarps = 32, kOrdBins = 1024;   // 128 KB of counters: one frame per SM, whose output (0.2 MB) stays in L2 while it fills
+
+__global__ void __launch_bounds__(kOrdWarps * 32)
+    lsd_seed_order_kernel(const uint16_t* __restrict__ key, const uint32_t* __restrict__ val, const int32_t* __restrict__ n_def,
+                          int npx, uint32_t* __restrict__ out) {
+  extern __shared__ uint32_t ord_smem[];
+  uint32_t (*hist)[kOrdBins] = reinterpret_cast<uint32_t (*)[kOrdBins]>(ord_smem);
+  __shared__ uint32_t wsum[kOrdWarps];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, b = blockIdx.x;
+  const int n = n_def[b];
+  const uint16_t* K = key + (size_t)b * npx;
+  const uint32_t* V = val + (size_t)b * npx;
+  uint32_t* O = out + (size_t)b * npx;
+  for (int i = tid; i < kOrdWarps * kOrdBins; i += kOrdWarps * 32) (&hist[0][0])[i] = 0u;
+  const int seg = (((n + kOrdWarps - 1) / kOrdWarps) + 31) & ~31;
+  const int lo = min(w * seg, n), hi = min(lo + seg, n);
+  __syncthreads();
+  for (int k0 = lo; k0 < hi; k0 += 32) {   // (low-gradient bins are crowded: one add per group of equal bins, not per lane)
+    const int k = k0 + lane;
+    const unsigned kk = k < hi ? (unsigned)K[k] : 0xFFFFu;
+    const unsigned grp = __match_any_sync(0xffffffffu, kk);
+    if (k < hi && lane == __ffs(grp) - 1) atomicAdd(&hist[w][kk], (uint32_t)__popc(grp));
+  }
+  __syncthreads();
+  {  // start offsets: position p = 1023 - bin; thread t owns p = kPer t .. kPer t + kPer - 1
+    constexpr int kPer = kOrdBins / (kOrdWarps * 32);
+    uint32_t tot = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int bin = kOrdBins - 1 - (kPer * tid + j);
+#pragma unroll
+      for (int ww = 0; ww < kOrdWarps; ++ww) tot += hist[ww][bin];
+    }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t run = inc - tot;
+    for (int ww = 0; ww < w; ++ww) run += wsum[ww];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int bin = kOrdBins - 1 - (kPer * tid + j);
+#pragma unroll
+      for (int ww = 0; ww < kOrdWarps; ++ww) {
+        const uint32_t c = hist[ww][bin];
+        hist[ww][bin] = run;
+        run += c;
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int k0 = lo; k0 < hi; k0 += 32) {
+    const int k = k0 + lane;
+    const bool act = k < hi;
+    const unsigned kk = act ? (unsigned)K[k] : 0xFFFFu;   // the idle lanes of the last step form a group of their own
+    const uint32_t v = act ? V[k] : 0u;
+    const unsigned grp = __match_any_sync(0xffffffffu, kk);
+    const int leader = __ffs(grp) - 1;
+    uint32_t base = 0;
+    if (act && lane == leader) base = atomicAdd(&hist[w][kk], (uint32_t)__popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (act) O[base + __popc(grp & lt)] = v;
+  }
+}
+
 void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st) {
-  const int npx = L.Ws * L.Hs;
-  size_t tmp = L.sort_tmp_bytes;
-  cub::DeviceSegmentedRadixSort::SortPairsDescending(L.sort_tmp, tmp, L.key_in, L.key_out, L.val_in, L.val_out,
-                                                     (int64_t)npx * nb, nb, L.seg_begin, L.seg_end, 0, 10, st);
+  constexpr int kSmem = kOrdWarps * kOrdBins * (int)sizeof(uint32_t);
+  static bool once = [] {
+    cudaFuncSetAttribute(lsd_seed_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    return true;
+  }();
+  (void)once;
+  lsd_seed_order_kernel<<<nb, kOrdWarps * 32, kSmem, st>>>(L.key_in, L.val_in, L.n_def, L.Ws * L.Hs, L.val_out);
 }
 
 void launch_lsd_core(const LineBuffers& L, int nb, uint32_t* status, cudaStream_t st) {

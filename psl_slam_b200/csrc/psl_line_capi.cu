@@ -76,8 +76,6 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   const bool grouped = resize_group_tables(xt4.data(), L.Ws, xw4.data(), xo4.data());
   uint4* dxw = nullptr;
   uint32_t* dxo = nullptr;
-  L.sort_tmp_bytes = lsd_sort_temp_bytes((int)npx, (int)C);
-  uint8_t* tmp = nullptr;
   // the records of the row above a frame must read "not available" (lsd_kernels.cu, load_nbr): for every frame but the
   // first that row is the previous frame's last one (NOTDEF); the first frame gets Ws + 1 such records in front
   const size_t pix_pad = ((size_t)L.Ws + 1 + 7) & ~(size_t)7;   // whole 128-byte lines, so the records stay line-aligned
@@ -85,8 +83,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
             lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx + pix_pad) &&
             lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
-            lalloc(ctx, L.key_out, C * npx) && lalloc(ctx, L.val_in, C * npx) && lalloc(ctx, L.val_out, C * npx) &&
-            lalloc(ctx, L.seg_begin, C) && lalloc(ctx, L.seg_end, C) && lalloc(ctx, tmp, L.sort_tmp_bytes) &&
+            lalloc(ctx, L.val_in, C * npx) && lalloc(ctx, L.val_out, C * npx) &&
             lalloc(ctx, L.raw, C * R * 4) && lalloc(ctx, L.n_raw, C) && lalloc(ctx, L.t1, C * R) &&
             lalloc(ctx, L.t2, C * R) && lalloc(ctx, L.m_angles, C * R) && lalloc(ctx, L.m_length, C * R) && lalloc(ctx, L.m_sangles, C * R) &&
             lalloc(ctx, L.m_order, C * R) && lalloc(ctx, L.m_tmp16, C * R) &&
@@ -97,7 +94,6 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
     free_line_geometry(ctx);
     return fail(ctx, PSL_E_CUDA, "line buffers: out of device memory (lower psl_config.line_chunk_frames)");
   }
-  L.sort_tmp = tmp;
   PSL_CK(cudaMemsetAsync(L.pix, 0xFF, pix_pad * sizeof(float4), ctx->stream));
   L.pix += pix_pad;
   L.lut = reinterpret_cast<const float4*>(lut);
