@@ -572,6 +572,16 @@ int psl_track_rgbd_batch_begin(psl_ctx* ctx, const uint8_t* color, int32_t chann
 int psl_track_rgbd_batch_end(psl_ctx* ctx, const psl_camera* cam, const psl_track_params* prm, float line_desc_th,
                              const psl_frontend_out* out);
 
+/* The second half of Tracking::TrackWithMotionModel (src/Tracking.cc:1193-1240) on the arrays psl_track_*_batch_dev left in
+ * HBM: for every frame b the keypoints that SearchByProjection matched (assign[b][i] = j >= 0) observe the MapPoint that
+ * frame b-1 created at its keypoint j — Last.UnprojectStereo(j), Frame.cc:1367-1381, from that keypoint, its depth z and
+ * the pose of frame b-1 — and Optimizer::PoseOptimization runs from the prior pose d_Tcw[b] (3x4 rows, as the batched
+ * front end takes them).  d_Tcw_out [B][16] 4x4 row-major, d_outlier [B][cap] = mvbOutlier, d_n_inliers [B] = the return
+ * value of PoseOptimization (0 and the prior pose for frame 0 and for frames with fewer than 3 matches).  Asynchronous. */
+int psl_track_pose_batch_dev(psl_ctx* ctx, const psl_keypoint* d_kps, const float* d_u_right, const float* d_z,
+                             const int32_t* d_assign, const int32_t* d_n, int32_t cap, int32_t B, const float* d_Tcw,
+                             const psl_camera* cam, float* d_Tcw_out, uint8_t* d_outlier, int32_t* d_n_inliers);
+
 /* Per-stage device timing (CUDA events on the ctx stream between the kernels of each stage).
  * Stages: 0 pyramid resize, 1 FAST cells, 2 octree selection, 3 Gaussian blur, 4 orientation+rBRIEF,
  * 5 single-pair matcher calls, 6 stereo + projection queries, 7 feature grid, 8 candidate lists,

@@ -158,7 +158,7 @@ EXPORTS = ["psl_default_config", "psl_create", "psl_destroy", "psl_last_error", 
            "psl_line_junctions", "psl_line_junctions_dev", "psl_line_search_triangulation_new",
            "psl_pose_optimization", "psl_pose_optimization_dev", "psl_pose_optimization_lil",
            "psl_pose_optimization_lil_dev", "psl_track_rgbd_batch_dev", "psl_track_rgbd_batch",
-           "psl_track_rgbd_batch_begin", "psl_track_rgbd_batch_end"]
+           "psl_track_rgbd_batch_begin", "psl_track_rgbd_batch_end", "psl_track_pose_batch_dev"]
 
 _lib = None
 
@@ -229,6 +229,7 @@ def lib():
         L.psl_track_rgbd_batch.argtypes = [_p, _p, _i, _i, _p, _i, _i, _i, _p, _p, _p, _f, _p]
         L.psl_track_rgbd_batch_begin.argtypes = [_p, _p, _i, _i, _p, _i, _i, _i, _p]
         L.psl_track_rgbd_batch_end.argtypes = [_p, _p, _p, _f, _p]
+        L.psl_track_pose_batch_dev.argtypes = [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]
         L.psl_pose_optimization_lil.argtypes = [_p, _p, _p, _i, _p, _i, _f, _f, _f, _f, _f, _p, _p, _p, _p]
         L.psl_pose_optimization_lil_dev.argtypes = [_p, _p, _p, _p, _i, _p, _p, _i, _i, _f, _f, _f, _f, _f, _p, _p, _p, _p]
         L.psl_line_junctions.argtypes = [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _i, _p, _p]

@@ -115,6 +115,63 @@ void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* 
   query_build_kernel<<<grid, 128, 0, st>>>(kps, z, n, cap, Tcw, first, cam, prm, q, nq);
 }
 
+// The correspondences PoseOptimization gets after SearchByProjection(Current, Last) in TrackWithMotionModel
+// (Tracking.cc:1193-1214): keypoint i of frame b matched to keypoint j = assign[b][i] of frame b-1 observes the
+// MapPoint that frame b-1 created at j, i.e. Last.UnprojectStereo(j) (Frame.cc:1367-1381) — the world point of the
+// synthetic sequence's "map".  One psl_pose_point per keypoint (flags = 0 without a match), plus the 4x4 prior pose.
+__global__ void pose_points_kernel(const psl_keypoint* __restrict__ kps, const float* __restrict__ u_right,
+                                   const float* __restrict__ z, const int32_t* __restrict__ assign,
+                                   const int32_t* __restrict__ n, int cap, const float* __restrict__ Tcw, psl_camera cam,
+                                   const float* __restrict__ inv_sigma2, psl_pose_point* __restrict__ pts,
+                                   float* __restrict__ T44) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16) {
+    const int r = i >> 2, c = i & 3;
+    T44[(size_t)b * 16 + i] = r < 3 ? Tcw[(size_t)b * 12 + i] : (c == 3 ? 1.f : 0.f);
+  }
+  if (i >= n[b]) return;
+  const psl_keypoint kp = kps[(size_t)b * cap + i];
+  psl_pose_point P;
+  P.u = kp.x; P.v = kp.y;
+  P.u_right = u_right[(size_t)b * cap + i];
+  P.inv_sigma2 = inv_sigma2[kp.octave];
+  P.xw = P.yw = P.zw = 0.f;
+  P.flags = 0;
+  const int j = b > 0 ? assign[(size_t)b * cap + i] : -1;
+  if (j >= 0) {
+    const float* Tl = Tcw + (size_t)(b - 1) * 12;
+    float Rwc[9], nRwc[9], Ow[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Rwc[r * 3 + k] = Tl[k * 4 + r];
+        nRwc[r * 3 + k] = -Tl[k * 4 + r];
+      }
+    const float tl[3] = {Tl[3], Tl[7], Tl[11]};
+    affine(nRwc, 3, tl, nullptr, Ow);   // mOw = -Rcw^T tcw
+    const psl_keypoint kl = kps[(size_t)(b - 1) * cap + j];
+    const float zz = z[(size_t)(b - 1) * cap + j];
+    if (zz > 0.f) {
+      const float invfx = __fdiv_rn(1.0f, cam.fx), invfy = __fdiv_rn(1.0f, cam.fy);
+      const float xc[3] = {__fmul_rn(__fmul_rn(__fsub_rn(kl.x, cam.cx), zz), invfx),
+                           __fmul_rn(__fmul_rn(__fsub_rn(kl.y, cam.cy), zz), invfy), zz};
+      float pw[3];
+      affine(Rwc, 3, xc, Ow, pw);  // UnprojectStereo
+      P.xw = pw[0]; P.yw = pw[1]; P.zw = pw[2];
+      P.flags = 1;
+    }
+  }
+  pts[(size_t)b * cap + i] = P;
+}
+
+void launch_pose_points(const psl_keypoint* kps, const float* u_right, const float* z, const int32_t* assign,
+                        const int32_t* n, int cap, const float* Tcw, const psl_camera& cam, const float* inv_sigma2,
+                        psl_pose_point* pts, float* T44, int B, cudaStream_t st) {
+  dim3 grid((cap + 127) / 128, B);
+  pose_points_kernel<<<grid, 128, 0, st>>>(kps, u_right, z, assign, n, cap, Tcw, cam, inv_sigma2, pts, T44);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K0: input conversion of Tracking::GrabImageRGBD (Tracking.cc:219-235).  Pure streaming: a thread
 // converts 4 adjacent pixels (12 or 16 colour bytes in, one gray word out).

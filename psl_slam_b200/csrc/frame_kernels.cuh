@@ -17,6 +17,11 @@ void launch_query_build(const psl_keypoint* kps, const float* z, const int32_t* 
                         const psl_camera& cam, const QueryBuildParams& prm, psl_proj_query* q, int32_t* nq, int B,
                         cudaStream_t st);
 
+// correspondences of PoseOptimization after SearchByProjection(Current, Last) + the 4x4 prior poses (Tracking.cc:1193-1214)
+void launch_pose_points(const psl_keypoint* kps, const float* u_right, const float* z, const int32_t* assign,
+                        const int32_t* n, int cap, const float* Tcw, const psl_camera& cam, const float* inv_sigma2,
+                        psl_pose_point* pts, float* T44, int B, cudaStream_t st);
+
 // Frame::UndistortKeyPoints (Frame.cc:1062-1092): kps_un[b][i] = kps[b][i] with cv::undistortPoints applied to pt
 void launch_undistort(const psl_keypoint* kps, const int32_t* n, int cap, const psl_distortion& cam, psl_keypoint* kps_un,
                       int B, cudaStream_t st);

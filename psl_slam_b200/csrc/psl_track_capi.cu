@@ -453,6 +453,33 @@ int psl_track_rgbd_batch(psl_ctx* ctx, const uint8_t* color, int32_t channels, i
 }
 
 
+// TrackWithMotionModel after the matcher (src/Tracking.cc:1193-1240): the matched keypoints of every frame, with the
+// MapPoints their partners in the previous frame created (Frame::UnprojectStereo), go through
+// Optimizer::PoseOptimization from the given prior pose; mvbOutlier and the inlier count come back.
+int psl_track_pose_batch_dev(psl_ctx* ctx, const psl_keypoint* d_kps, const float* d_u_right, const float* d_z,
+                             const int32_t* d_assign, const int32_t* d_n, int32_t cap, int32_t B, const float* d_Tcw,
+                             const psl_camera* cam, float* d_Tcw_out, uint8_t* d_outlier, int32_t* d_n_inliers) {
+  if (!ctx) return PSL_E_INVALID;
+  if (B < 0 || cap < 1 || !cam || (B > 0 && (!d_kps || !d_u_right || !d_z || !d_assign || !d_n || !d_Tcw || !d_Tcw_out ||
+      !d_outlier || !d_n_inliers)))
+    return fail(ctx, PSL_E_INVALID, "bad argument");
+  if (B == 0) return PSL_OK;
+  PSL_CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  DevBuf* M = ctx->m_misc;
+  if ((rc = ensure(ctx, M[14], (size_t)B * cap * sizeof(psl_pose_point)))) return rc;
+  if ((rc = ensure(ctx, M[15], (size_t)B * 64 + kMaxLevels * 4))) return rc;
+  float* d_T44 = M[15].as<float>();
+  float* d_is2 = d_T44 + (size_t)B * 16;
+  PSL_CK(cudaMemcpyAsync(d_is2, ctx->inv_sigma2.data(), (size_t)ctx->cfg.orb_nlevels * 4, cudaMemcpyHostToDevice, ctx->stream));
+  size_t e = prof_mark(ctx);
+  launch_pose_points(d_kps, d_u_right, d_z, d_assign, d_n, cap, d_Tcw, *cam, d_is2, M[14].as<psl_pose_point>(), d_T44, B,
+                     ctx->stream);
+  prof_span(ctx, 6, e, 1);
+  return psl_pose_optimization_dev(ctx, d_T44, M[14].as<psl_pose_point>(), d_n, cap, B, cam->fx, cam->fy, cam->cx, cam->cy,
+                                   cam->bf, d_Tcw_out, d_outlier, d_n_inliers);
+}
+
 int psl_convert_rgbd_dev(psl_ctx* ctx, const uint8_t* d_color, int32_t channels, int32_t rgb_order, int32_t color_stride,
                          int64_t color_frame_stride, uint8_t* d_gray, int32_t gray_stride, int64_t gray_frame_stride,
                          const uint16_t* d_depth_in, int32_t depth_stride_px, int64_t depth_frame_stride_px,

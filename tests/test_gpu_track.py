@@ -161,3 +161,63 @@ def test_undistort_keypoints_vs_cv2_golden(orc, cam):
         want = orc.undistort_keypoints(k3[b, :n], d)
         assert got[b, :n].tobytes() == want.tobytes()
         assert (got[b, n:] == 0xAB).all()
+
+
+def test_pose_after_matching_vs_oracle_chain(orc):
+    """The second half of TrackWithMotionModel (Tracking.cc:1193-1240) on the device arrays of the batched front end:
+    matches -> MapPoints of the previous frame (UnprojectStereo) -> PoseOptimization, against the same chain composed
+    from the oracle's pieces (pose to 1e-6, identical outlier flags and inlier counts)."""
+    import ctypes as C
+
+    import torch
+    from psl_slam_b200 import ORBextractor, make_camera, make_track_params, synth, track_orb_batch
+    from psl_slam_b200._lib import lib
+    K = synth.ICL
+    B = 5
+    gray, depth, T = synth.sequence(9, B)
+    T = T.astype(np.float32)
+    rng = np.random.default_rng(3)
+    T[1:, :3, 3] += rng.normal(0, 0.004, (B - 1, 3)).astype(np.float32)   # the motion model is never exact
+    ex = ORBextractor()
+    cam = make_camera(K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], K["depth_factor"])
+    out = track_orb_batch(ex, gray, depth, T, cam, make_track_params(15.0, 0.9, True))
+    cap = ex.cap
+    dev = {k: torch.from_numpy(np.ascontiguousarray(out[k]).view(np.uint8).reshape(-1)).cuda()
+           for k in ("kps", "u_right", "z", "assign", "n")}
+    T12 = np.ascontiguousarray(T[:, :3, :4].reshape(B, 12))
+    d_T = torch.from_numpy(T12).cuda()
+    d_To = torch.zeros((B, 16), dtype=torch.float32, device="cuda")
+    d_out = torch.zeros((B, cap), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ex.ctx.check(lib().psl_track_pose_batch_dev(ex.ctx.handle, dev["kps"].data_ptr(), dev["u_right"].data_ptr(),
+                                                dev["z"].data_ptr(), dev["assign"].data_ptr(), dev["n"].data_ptr(), cap, B,
+                                                d_T.data_ptr(), C.addressof(cam), d_To.data_ptr(), d_out.data_ptr(),
+                                                d_cnt.data_ptr()))
+    ex.ctx.sync()
+    To, outl, cnt = d_To.cpu().numpy().reshape(B, 4, 4), d_out.cpu().numpy(), d_cnt.cpu().numpy()
+    assert cnt[0] == 0 and np.array_equal(To[0], T[0])
+    fx, fy, cx, cy, bf = (np.float32(K[k]) for k in ("fx", "fy", "cx", "cy", "bf"))
+    inv_sigma2 = ex.GetInverseScaleSigmaSquares()
+    f32, f64 = np.float32, np.float64
+    for b in range(1, B):
+        n, nl = int(out["n"][b]), int(out["n"][b - 1])
+        kps, kl = out["kps"][b, :n], out["kps"][b - 1, :nl]
+        assign, zl = out["assign"][b, :n], out["z"][b - 1, :nl]
+        pts = np.zeros(n, orc.POSE_POINT_DTYPE)
+        pts["u"], pts["v"], pts["u_right"] = kps["x"], kps["y"], out["u_right"][b, :n]
+        pts["inv_sigma2"] = inv_sigma2[kps["octave"]]
+        m = np.nonzero(assign >= 0)[0]
+        j = assign[m]
+        assert (zl[j] > 0).all()
+        # Last.UnprojectStereo(j): fp32 steps, the 3x3 products accumulated in double and rounded once
+        Rcw, tcw = T[b - 1, :3, :3], T[b - 1, :3, 3]
+        Ow = (-(Rcw.T.astype(f64)) @ tcw.astype(f64)).astype(f32)
+        invfx, invfy = f32(1) / fx, f32(1) / fy
+        xc = np.stack([((kl["x"][j] - cx) * zl[j]) * invfx, ((kl["y"][j] - cy) * zl[j]) * invfy, zl[j]], 1).astype(f32)
+        Xw = (xc.astype(f64) @ Rcw.astype(f64) + Ow.astype(f64)).astype(f32)      # Rwc x = Rcw^T x
+        pts["xw"][m], pts["yw"][m], pts["zw"][m] = Xw[:, 0], Xw[:, 1], Xw[:, 2]
+        pts["flags"][m] = 1
+        wT, wout, wcnt = orc.pose_optimization(T[b], pts, fx, fy, cx, cy, bf)
+        assert cnt[b] == wcnt and wcnt > 200, (b, cnt[b], wcnt)
+        assert np.array_equal(outl[b, :n], wout), b
+        assert np.allclose(To[b], wT, rtol=0, atol=1e-6), b
