@@ -479,8 +479,8 @@ __global__ void __launch_bounds__(kPostWarps * 32, 8)
                                    lineeq + (size_t)b * cap * 3, cap, lane);
   POST_T1(4, t_all);
   if (lane == 0) {
-    if (S.overflow) atomicOr(status, kStatLineNeighbours);
-    if (n < 0) atomicOr(status, kStatOutOverflow);
+    if (S.overflow) { atomicOr(status, kStatLineNeighbours); atomicMax(status + 1, (uint32_t)b + 1u); }
+    if (n < 0) { atomicOr(status, kStatOutOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
     n_out[b] = n < 0 ? 0 : n;
   }
 }

@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
 #endif
   if (lane == 0) {
     L.n_raw[b] = nseg < L.raw_cap ? nseg : L.raw_cap;
-    if (nseg > L.raw_cap) atomicOr(status, kStatLineRaw);
+    if (nseg > L.raw_cap) { atomicOr(status, kStatLineRaw); atomicMax(status + 1, (uint32_t)b + 1u); }
   }
 }
 

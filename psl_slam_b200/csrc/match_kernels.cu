@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kCandWarps * 32)
   if (lane == 0) {
     *out_count = min(total, kCandCap);
     *out_best = make_uint2(best, second);
-    if (total > kCandCap) atomicOr(status, kStatCandOverflow);
+    if (total > kCandCap) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
   }
 }
 
@@ -346,6 +346,12 @@ __global__ void __launch_bounds__(32)
 void launch_proj_resolve(const MatchFrames& f, const MatchQueries& q, const uint32_t* cand, const int32_t* cand_count,
                          const uint2* cand_best, const uint8_t* claimed_in, psl_match_params prm,
                          uint32_t* accepted_scratch, int32_t* assign, int32_t* nmatches, int B, cudaStream_t st) {
+  // claimed[cap] bytes of dynamic shared memory: up to 65535 keypoints, i.e. beyond the 48 KB a kernel gets by default
+  static bool once = [] {
+    cudaFuncSetAttribute(proj_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    return true;
+  }();
+  (void)once;
   proj_resolve_kernel<<<B, 32, (size_t)f.cap, st>>>(f, q, cand, cand_count, cand_best, claimed_in, prm,
                                                     accepted_scratch, assign, nmatches);
 }

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kDescWarps * 32)
   const int n = __shfl_sync(0xffffffffu, inc, 31);
   if (i == 0 && lane == 0) {
     n_out[b] = n < cap ? n : cap;
-    if (n > cap) atomicOr(status, kStatOutOverflow);
+    if (n > cap) { atomicOr(status, kStatOutOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
   }
   if (i >= n || i >= cap) return;
   const uint32_t m = __ballot_sync(0xffffffffu, lane < nl && off <= i);

@@ -194,7 +194,7 @@ __device__ __forceinline__ void fast_cell_body(const OrbGeometry* __restrict__ g
     if (total) base = atomicAdd(pool_count + b, (uint32_t)total);
     s_base = base;
     *tab = make_uint2(base, (uint32_t)total);
-    if (base + total > (uint32_t)pool_cap) atomicOr(status, kStatCandOverflow);
+    if (base + total > (uint32_t)pool_cap) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
   }
   __syncthreads();
   const uint32_t base = s_base;
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kRowsThreads)
     if (lane == 0) {
       base = atomicAdd(pool_count + b, (uint32_t)total);
       *tab = make_uint2(base, (uint32_t)total);
-      if (base + total > (uint32_t)pool_cap) atomicOr(status, kStatCandOverflow);
+      if (base + total > (uint32_t)pool_cap) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + total > (uint32_t)pool_cap) return;

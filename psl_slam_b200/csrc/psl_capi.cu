@@ -26,18 +26,21 @@ int ensure_bytes(psl_ctx* ctx, void** p, size_t* have, size_t need) {
   return PSL_OK;
 }
 int check_status(psl_ctx* ctx) {
-  PSL_CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PSL_CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PSL_CK(cudaStreamSynchronize(ctx->stream));
-  const uint32_t s = *ctx->h_status;
+  const uint32_t s = ctx->h_status[0];
   if (!s) return PSL_OK;
-  PSL_CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(uint32_t), ctx->stream));
+  // word 1: 1 + the largest frame index (inside its launch chunk) that raised a flag, so that the caller of a batched
+  // entry point knows where to look; the other frames of the batch are complete
+  const std::string where = ctx->h_status[1] ? " (frame " + std::to_string(ctx->h_status[1] - 1) + " of its launch chunk)" : "";
+  PSL_CK(cudaMemsetAsync(ctx->d_status, 0, 2 * sizeof(uint32_t), ctx->stream));
   if (s & kStatBadRoot) return fail(ctx, PSL_E_INVALID, "octree: candidate outside the root nodes (aspect ratio)");
   if (s & kStatNodeOverflow) return fail(ctx, PSL_E_INTERNAL, "octree: node table bound violated");
   if (s & kStatCandOverflow)
-    return fail(ctx, PSL_E_CAPACITY, "FAST candidate pool overflow: raise psl_config.orb_max_candidates");
-  if (s & kStatOutOverflow) return fail(ctx, PSL_E_CAPACITY, "output capacity `cap` too small");
-  if (s & kStatLineRaw) return fail(ctx, PSL_E_CAPACITY, "LSD raw segment overflow: raise psl_config.line_max_raw");
-  if (s & kStatLineNeighbours) return fail(ctx, PSL_E_CAPACITY, "line merge: neighbour list bound violated");
+    return fail(ctx, PSL_E_CAPACITY, std::string("FAST candidate pool overflow: raise psl_config.orb_max_candidates") + where);
+  if (s & kStatOutOverflow) return fail(ctx, PSL_E_CAPACITY, std::string("output capacity `cap` too small") + where);
+  if (s & kStatLineRaw) return fail(ctx, PSL_E_CAPACITY, std::string("LSD raw segment overflow: raise psl_config.line_max_raw") + where);
+  if (s & kStatLineNeighbours) return fail(ctx, PSL_E_CAPACITY, std::string("line merge: neighbour list bound violated") + where);
   return fail(ctx, PSL_E_INTERNAL, "unknown device status");
 }
 
@@ -326,9 +329,9 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
             cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc(&ctx->d_geo, sizeof(OrbGeometry)) == cudaSuccess &&
-            cudaMalloc(&ctx->d_status, sizeof(uint32_t)) == cudaSuccess &&
-            cudaMemset(ctx->d_status, 0, sizeof(uint32_t)) == cudaSuccess &&
-            cudaMallocHost(&ctx->h_status, sizeof(uint32_t)) == cudaSuccess;
+            cudaMalloc(&ctx->d_status, 2 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMemset(ctx->d_status, 0, 2 * sizeof(uint32_t)) == cudaSuccess &&
+            cudaMallocHost(&ctx->h_status, 2 * sizeof(uint32_t)) == cudaSuccess;
   if (!ok) {
     psl_destroy(ctx);
     return PSL_E_CUDA;

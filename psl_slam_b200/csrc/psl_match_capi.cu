@@ -58,7 +58,8 @@ int psl_match_projection(psl_ctx* ctx, const psl_frame_view* fv, const psl_proj_
                          const uint8_t* query_desc, int32_t nq, const uint8_t* claimed_in,
                          const psl_match_params* prm, int32_t* assign, int32_t* nmatches) {
   if (!ctx) return PSL_E_INVALID;
-  if (!fv || !prm || !nmatches || nq < 0 || fv->n < 0 || fv->n > 65535 || (fv->n > 0 && (!fv->kps_un || !fv->desc || !assign)) ||
+  // the resolve stage packs an accepted match as query << 16 | keypoint: both sides are bounded by 65535
+  if (!fv || !prm || !nmatches || nq < 0 || nq > 65535 || fv->n < 0 || fv->n > 65535 || (fv->n > 0 && (!fv->kps_un || !fv->desc || !assign)) ||
       (nq > 0 && (!queries || !query_desc)) || (prm->mode != 0 && prm->mode != 1))
     return fail(ctx, PSL_E_INVALID, "bad argument");
   *nmatches = 0;
