@@ -126,6 +126,27 @@ PSL_LN_HD void stable_sort_idx(uint16_t* idx, uint16_t* tmp, int n, const float*
   }
 }
 
+// A segment with its end points ordered along the scan axis of a pair test: x when the row's line is closer to
+// horizontal than to vertical, else y (uselongline.cpp:84-99).
+struct AxisSeg { float ax, ay, bx, by; };  // a = first end along the axis, b = last
+PSL_LN_HD AxisSeg along_axis(const Seg& s, bool horiz) {
+  const bool flip = horiz ? (s.v[2] < s.v[0]) : (s.v[3] < s.v[1]);
+  AxisSeg r;
+  r.ax = flip ? s.v[2] : s.v[0]; r.ay = flip ? s.v[3] : s.v[1];
+  r.bx = flip ? s.v[0] : s.v[2]; r.by = flip ? s.v[1] : s.v[3];
+  return r;
+}
+// Two ordered segments overlap along the axis, or the gap between their facing end points is shorter than
+// sqrt(gap_sq_thr) (uselongline.cpp:123-143): the one that ends first supplies the tail, the other one the head.
+PSL_LN_HD bool ends_meet(const AxisSeg& p, const AxisSeg& q, bool horiz, float gap_sq_thr) {
+  const bool q_first = horiz ? (p.bx > q.bx) : (p.by > q.by);
+  const float tx = q_first ? q.bx : p.bx, ty = q_first ? q.by : p.by;
+  const float hx = q_first ? p.ax : q.ax, hy = q_first ? p.ay : q.ay;
+  if (horiz ? (tx >= hx) : (ty >= hy)) return true;
+  const float gx = PSL_LN_FSUB(hx, tx), gy = PSL_LN_FSUB(hy, ty);
+  return PSL_LN_FADD(PSL_LN_FMUL(gx, gx), PSL_LN_FMUL(gy, gy)) < gap_sq_thr;
+}
+
 // MergeLines (uselongline.cpp:24-264); returns the number of lines written to dst
 PSL_LN_HD int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, float distance_thr, float endpoint_threshold,
                           MergeScratch& S) {
@@ -139,18 +160,15 @@ PSL_LN_HD int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, floa
     S.code[i] = -1;
   }
   stable_sort_idx(S.order, S.tmp16, n, S.angles, false);
-  const float ep_thr = PSL_LN_FMUL(endpoint_threshold, endpoint_threshold);
-  const float quater_PI = (float)(kPi / 4.0);
+  const float gap_sq_thr = PSL_LN_FMUL(endpoint_threshold, endpoint_threshold);
+  const float quarter_turn = (float)(kPi / 4.0);
   for (int i = 0; i < n; ++i) {
     const int idx1 = S.order[i];
-    float x11 = src[idx1].v[0], y11 = src[idx1].v[1], x12 = src[idx1].v[2], y12 = src[idx1].v[3];
     const float angle1 = S.angles[idx1];
-    const bool sx = fabsf(angle1) < quater_PI;
-    if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
+    const bool horiz = fabsf(angle1) < quarter_turn;
+    const AxisSeg p = along_axis(src[idx1], horiz);
     for (int j = i + 1; j < n; ++j) {
       const int idx2 = S.order[j];
-      float x21 = src[idx2].v[0], y21 = src[idx2].v[1], x22 = src[idx2].v[2], y22 = src[idx2].v[3];
-      if ((sx && (x22 < x21)) || ((!sx) && y22 < y21)) { float t = x21; x21 = x22; x22 = t; t = y21; y21 = y22; y22 = t; }
       const float d_angle = angle_diff(angle1, S.angles[idx2]);
       if (d_angle > angle_thr) {
         if ((double)fabsf(angle1) < (kPi / 2 - (double)angle_thr)) break;
@@ -162,15 +180,7 @@ PSL_LN_HD int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, floa
       const float my2 = (float)(0.5 * (double)PSL_LN_FADD(src[idx2].v[1], src[idx2].v[3]));
       if (point_line_distance(src[idx2], mx1, my1) > distance_thr && point_line_distance(src[idx1], mx2, my2) > distance_thr)
         continue;
-      float cx12, cy12, cx21, cy21;
-      if ((sx && x12 > x22) || (!sx && y12 > y22)) { cx12 = x22; cy12 = y22; cx21 = x11; cy21 = y11; }
-      else { cx12 = x12; cy12 = y12; cx21 = x21; cy21 = y21; }
-      bool to_merge = ((sx && cx12 >= cx21) || (!sx && cy12 >= cy21));
-      if (!to_merge) {
-        const float ex = PSL_LN_FSUB(cx21, cx12), ey = PSL_LN_FSUB(cy21, cy12);
-        to_merge = PSL_LN_FADD(PSL_LN_FMUL(ex, ex), PSL_LN_FMUL(ey, ey)) < ep_thr;
-      }
-      if (to_merge) {
+      if (ends_meet(p, along_axis(src[idx2], horiz), horiz, gap_sq_thr)) {
         if (S.nb_cnt[idx1] < kNbCap && S.nb_cnt[idx2] < kNbCap) {
           S.nb[idx1 * kNbCap + S.nb_cnt[idx1]++] = (uint16_t)idx2;
           S.nb[idx2 * kNbCap + S.nb_cnt[idx2]++] = (uint16_t)idx1;

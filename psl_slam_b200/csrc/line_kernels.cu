@@ -198,8 +198,8 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   // independent: one row per lane (32 rows at a time, coalesced loads of the sorted copies, every lane busy with
   // a partner that is inside its window), own partners into a forward list, the other side counted with an atomic
   // and put in order afterwards.
-  const float ep_thr = __fmul_rn(endpoint_threshold, endpoint_threshold);
-  const float quater_PI = (float)(line::kPi / 4.0);
+  const float gap_sq_thr = __fmul_rn(endpoint_threshold, endpoint_threshold);
+  const float quarter_turn = (float)(line::kPi / 4.0);
   int* bcnt = reinterpret_cast<int*>(S.angles);   // the unsorted angles are dead from here on
   for (int j = lane; j < n; j += 32) {
     bcnt[j] = 0;
@@ -213,10 +213,9 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
       const int idx1 = S.order[i];
       const ScanRec r1 = srec[i];
       const Seg s1 = r1.s;
-      float x11 = s1.v[0], y11 = s1.v[1], x12 = s1.v[2], y12 = s1.v[3];
       const float angle1 = r1.angle;
-      const bool sx = fabsf(angle1) < quater_PI;
-      if ((sx && (x12 < x11)) || ((!sx) && y12 < y11)) { float t = x11; x11 = x12; x12 = t; t = y11; y11 = y12; y12 = t; }
+      const bool horiz = fabsf(angle1) < quarter_turn;
+      const line::AxisSeg p = line::along_axis(s1, horiz);
       const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
       const float mx1 = (float)(0.5 * (double)__fadd_rn(s1.v[0], s1.v[2])), my1 = (float)(0.5 * (double)__fadd_rn(s1.v[1], s1.v[3]));
       const double den1 = r1.den;
@@ -250,19 +249,9 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
           if (j < n) r_nx = srec[j];
           continue;
         }
-        float x21 = s2.v[0], y21 = s2.v[1], x22 = s2.v[2], y22 = s2.v[3];
-        if ((sx && (x22 < x21)) || ((!sx) && y22 < y21)) { float t = x21; x21 = x22; x22 = t; t = y21; y21 = y22; y22 = t; }
         const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
         if (pld_exceeds(s2, den2, mx1, my1, distance_thr) && pld_exceeds(s1, den1, mx2, my2, distance_thr)) continue;
-        float cx12, cy12, cx21, cy21;
-        if ((sx && x12 > x22) || (!sx && y12 > y22)) { cx12 = x22; cy12 = y22; cx21 = x11; cy21 = y11; }
-        else { cx12 = x12; cy12 = y12; cx21 = x21; cy21 = y21; }
-        bool to_merge = ((sx && cx12 >= cx21) || (!sx && cy12 >= cy21));
-        if (!to_merge) {
-          const float ex = __fsub_rn(cx21, cx12), ey = __fsub_rn(cy21, cy12);
-          to_merge = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)) < ep_thr;
-        }
-        if (!to_merge) continue;
+        if (!line::ends_meet(p, line::along_axis(s2, horiz), horiz, gap_sq_thr)) continue;
         const int idx2 = S.order[jc];
         const int b = atomicAdd(&bcnt[idx2], 1);   // slot in idx2's list of earlier rows (unordered until the pass below)
         if (fc < kNbCap && b < kNbCap) {

@@ -472,6 +472,18 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
       uint32_t c = f.ring[(i_next + p) & (kRing - 1)];
       if (n_spec - i_next > kRingValid) c = f.reg[min(i_next + p, n_spec - 1)];   // a frontier longer than the ring (rare, uniform)
       nxt = load_nbr(f, p < m2, c, off, offpk);
+#ifdef PSL_PF
+      // the record one pixel further in the same direction: where the step after the next one will look if this
+      // neighbour is accepted, requested a whole step ahead of its load
+      if (p < m2) {
+        const int far = nxt.lin + off;   // at most W + 1 records outside the frame: inside the pads of the batch array
+#if PSL_PF == 1
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(f.pix + far));
+#else
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(f.pix + far));
+#endif
+      }
+#endif
     }
     // verification, under the latency of those loads
     bool proven;

@@ -78,9 +78,11 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   uint32_t* dxo = nullptr;
   // the records of the row above a frame must read "not available" (lsd_kernels.cu, load_nbr): for every frame but the
   // first that row is the previous frame's last one (NOTDEF); the first frame gets Ws + 1 such records in front
-  const size_t pix_pad = ((size_t)L.Ws + 1 + 7) & ~(size_t)7;   // whole 128-byte lines, so the records stay line-aligned
+  const size_t pix_pad = (2 * ((size_t)L.Ws + 1) + 7) & ~(size_t)7;   // whole 128-byte lines, so the records stay line-aligned;
+  // one row + 1 of unavailable records before the first frame, twice that (and as much after the last frame) so that
+  // region growing's look-ahead prefetch stays inside the allocation
   bool ok = lalloc(ctx, dx, xt.size()) && lalloc(ctx, dy, yt.size()) && lalloc(ctx, dxw, (size_t)n4) && lalloc(ctx, dxo, (size_t)n4) && lalloc(ctx, lut, lsd_lut_bytes()) && lalloc(ctx, seed_lut, lsd_seed_lut_bytes()) && lalloc(ctx, L.blur, C * L.pitch * h) &&
-            lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx + pix_pad) &&
+            lalloc(ctx, L.scaled, C * npx) && lalloc(ctx, L.pix, C * npx + 2 * pix_pad) &&
             lalloc(ctx, L.reg, C * npx) && lalloc(ctx, L.max_n2, C) &&
             lalloc(ctx, L.row_cnt, C * L.Hs) && lalloc(ctx, L.n_def, C) && lalloc(ctx, L.key_in, C * npx) &&
             lalloc(ctx, L.val_in, C * npx) && lalloc(ctx, L.val_out, C * npx) &&
