@@ -314,20 +314,18 @@ __device__ __forceinline__ bool aligned_deg(float deg, double theta, double prec
 struct Nbr {
   int lin;        // pixel index
   uint32_t npk;   // packed y << 16 | x (meaningless for a neighbour outside the image, which is never accepted)
-  float4 rec;     // pixel record
-  bool cand;      // available (not USED, defined angle) when it was loaded
+  float4 rec;     // pixel record; rec.w < 0 (as an int): not available (USED, no defined angle, or an idle lane)
 };
+// Whether the pixel was available when it was loaded.  Deliberately NOT evaluated inside load_nbr: the first use of a
+// loaded register is where the warp waits for the load, and the step's verification is meant to run before that.
+__device__ __forceinline__ bool avail(const Nbr& b) { return __float_as_int(b.rec.w) >= 0; }
 
 __device__ __forceinline__ Nbr load_nbr(const Frame& f, bool active, uint32_t c, int off, uint32_t offpk) {
   Nbr b;
   b.lin = lin_of(f, c) + off;
   b.npk = c + offpk;
-  b.rec = make_float4(0.f, 0.f, 0.f, 0.f);
-  b.cand = false;
-  if (active) {
-    b.rec = f.pix[b.lin];   // (ld.global.L2::128B / ::256B measured: no difference)
-    b.cand = __float_as_int(b.rec.w) >= 0;
-  }
+  b.rec = make_float4(0.f, 0.f, 0.f, __int_as_float(lsdw_kUnavail));
+  if (active) b.rec = f.pix[b.lin];   // (ld.global.L2::128B / ::256B measured: no difference)
   return b;
 }
 
@@ -445,10 +443,11 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
     const int i_next = i + m;   // first region point of the next step
     const float s2 = s.x * s.x + s.y * s.y;
     const bool fast = qk.quick && s2 > 1e-6f;
+    const bool cand = avail(cur);
     const float dot = cur.rec.y * s.x + cur.rec.z * s.y, dot2 = dot * dot;
-    const bool pos = cur.cand && dot > 0.f;
+    const bool pos = cand && dot > 0.f;
     const bool yes0 = fast && pos && dot2 >= qk.chi2 * s2;
-    const bool unsure0 = cur.cand && !yes0 && (!fast || (pos && dot2 > qk.clo2 * s2));
+    const bool unsure0 = cand && !yes0 && (!fast || (pos && dot2 > qk.clo2 * s2));
     const unsigned A0 = __ballot_sync(kFull, yes0), U0 = __ballot_sync(kFull, unsure0);
     // guess: the lanes that pass under the sums before the step, first lane of every repeated pixel (the same pixel can
     // only be seen from two centres; all its lanes hold the same record, so they pass together)
@@ -472,18 +471,6 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
       uint32_t c = f.ring[(i_next + p) & (kRing - 1)];
       if (n_spec - i_next > kRingValid) c = f.reg[min(i_next + p, n_spec - 1)];   // a frontier longer than the ring (rare, uniform)
       nxt = load_nbr(f, p < m2, c, off, offpk);
-#ifdef PSL_PF
-      // the record one pixel further in the same direction: where the step after the next one will look if this
-      // neighbour is accepted, requested a whole step ahead of its load
-      if (p < m2) {
-        const int far = nxt.lin + off;   // at most W + 1 records outside the frame: inside the pads of the batch array
-#if PSL_PF == 1
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(f.pix + far));
-#else
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(f.pix + far));
-#endif
-      }
-#endif
     }
     // verification, under the latency of those loads
     bool proven;
@@ -509,7 +496,7 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
       const bool no1 = sure1 && (d1 <= 0.f || d1 * d1 <= qk.clo2 * q1);
       // an earlier lane of A holds this pixel: USED by the time the scalar loop gets here
       const bool taken = yes0 && !first;
-      const bool lane_ok = !cur.cand || taken || (inA ? yes1 : no1);
+      const bool lane_ok = !cand || taken || (inA ? yes1 : no1);
       proven = __all_sync(kFull, lane_ok);
       // lane 31's prefix misses its own term when it is accepted itself (the last addition of the step)
       const bool last = (A >> 31) != 0u;
@@ -531,7 +518,7 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
       LSD_STAT(7, 1);
       if (inA) *flags_of(f, cur.lin) = __float_as_int(cur.rec.w);   // take the guess back
       __syncwarp();
-      s = step_sequential(f, cur.lin, cur.npk, cur.rec, cur.cand, s, exact, srec.x, sterm, prec, qk, lane);
+      s = step_sequential(f, cur.lin, cur.npk, cur.rec, cand, s, exact, srec.x, sterm, prec, qk, lane);
       exact = exact || s.n > 1;
       i = i_next;
       if (i >= s.n) break;
@@ -766,8 +753,21 @@ __global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
   for (int s0 = 0; s0 < n_seeds; s0 += 32) {
     const int my = s0 + lane < n_seeds ? (int)seeds[s0 + lane] : -1;
     // a pixel that is USED now stays USED (only the pixels of the region being refined are ever released)
-    unsigned todo = __ballot_sync(lsdw::kFull, my >= 0 && *lsdw::flags_of(f, my >= 0 ? my : 0) >= 0);
+    const bool free_now = my >= 0 && *lsdw::flags_of(f, my >= 0 ? my : 0) >= 0;
+    unsigned todo = __ballot_sync(lsdw::kFull, free_now);
     LSD_STAT(4, __popc(todo));
+    // The eight neighbours of a seed that is about to be grown: the flag load brought in the sector of the seed's own
+    // record; ask for the rest now, so that all but the first region of the chunk find their first neighbourhood on
+    // the way (-1.5 % of the kernel).  x - 1 / y - 1 of a border seed land in the pad or the neighbouring row.
+    if (free_now) {
+      const float4* c = f.pix + my;
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(c - f.W - 1));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(c - f.W + 1));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(c - 1));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(c + 1));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(c + f.W - 1));
+      asm volatile("prefetch.global.L1 [%0];" :: "l"(c + f.W + 1));
+    }
     while (todo) {
       const int l = __ffs(todo) - 1;
       todo &= todo - 1;
