@@ -275,7 +275,7 @@ using lsd::kM32Pi;
 using lsd::kNotDefDeg;
 using lsd::kPi;
 
-constexpr int kRing = 1024;  // region points kept in shared memory (the BFS frontier and small regions)
+constexpr int kRing = 512;   // region points kept in shared memory (the BFS frontier and small regions)
 // a refuted guess leaves up to 32 stale entries behind the end of the list, i.e. over the oldest entries of the ring
 constexpr int kRingValid = kRing - 32;
 constexpr unsigned kFull = 0xffffffffu;
