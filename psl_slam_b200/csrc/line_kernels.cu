@@ -157,9 +157,13 @@ __device__ __forceinline__ bool pld_exceeds(const Seg& l, double den, float x0, 
   return (float)(dn / den) > thr;
 }
 
-__device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, float distance_thr, float endpoint_threshold,
-                           MergeScratch& S, int lane) {
-  if (n <= 0) return 0;
+// MergeLines (uselongline.cpp:24-264) in three phases, so that the pair scan -- two thirds of the work, independent per
+// row -- can run as a kernel of its own over (frame, block of 32 rows) instead of inside the one warp that owns the frame:
+//   merge_prepare    angles, angle order, the per-line scan records                       (one warp per frame)
+//   merge_scan_rows  the pair tests of 32 rows of the angle order                          (one warp per 32 rows)
+//   merge_finish     neighbour lists in order, clusters, sub-clusters, folded merges      (one warp per frame)
+__device__ void merge_prepare(const Seg* src, int n, MergeScratch& S, int lane) {
+  if (n <= 0) return;
   POST_T0(t_sort);
   for (int i = lane; i < n; i += 32) {
     const float dx = __fsub_rn(src[i].v[2], src[i].v[0]), dy = __fsub_rn(src[i].v[3], src[i].v[1]);
@@ -189,8 +193,19 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
     S.sangles[j] = r.angle;   // (the bisection over a vertical line's far partners reads the angles alone)
   }
   __syncwarp();
+  int* bcnt0 = reinterpret_cast<int*>(S.angles);   // the unsorted angles are dead from here on
+  for (int j = lane; j < n; j += 32) {
+    bcnt0[j] = 0;
+    S.loc[S.order[j]] = (uint16_t)j;              // rank of a line in the angle order
+  }
+  __syncwarp();
   POST_T1(0, t_sort);
-  POST_T0(t_scan);
+}
+
+// rows [base, base + 32) of the pair scan; returns whether a neighbour list overflowed
+__device__ int merge_scan_rows(int base, int n, float angle_thr, float distance_thr, float endpoint_threshold,
+                               MergeScratch& S, int lane) {
+  const ScanRec* srec = S.scan;
   // Pair scan (:75-150).  The scalar loop walks the rows i in angle order and, for each, its partners j > i up to
   // the first one whose angle gap is too large; every accepted pair appends each line to the other's neighbour list.
   // Row i's list therefore ends up as: the rows before i that accepted i (ascending), then i's own partners
@@ -200,14 +215,9 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
   // and put in order afterwards.
   const float gap_sq_thr = __fmul_rn(endpoint_threshold, endpoint_threshold);
   const float quarter_turn = (float)(line::kPi / 4.0);
-  int* bcnt = reinterpret_cast<int*>(S.angles);   // the unsorted angles are dead from here on
-  for (int j = lane; j < n; j += 32) {
-    bcnt[j] = 0;
-    S.loc[S.order[j]] = (uint16_t)j;              // rank of a line in the angle order
-  }
-  __syncwarp();
+  int* bcnt = reinterpret_cast<int*>(S.angles);   // back counters (merge_prepare zeroed them)
   int ovf = 0;
-  for (int base = 0; base < n; base += 32) {
+  {
     const int i = base + lane;
     if (i < n) {
       const int idx1 = S.order[i];
@@ -265,7 +275,15 @@ __device__ int merge_lines(const Seg* src, int n, Seg* dst, float angle_thr, flo
       S.nb_cnt[idx1] = (uint16_t)min(fc, kNbCap);
     }
   }
-  __syncwarp();
+  return __any_sync(kFull, ovf) ? 1 : 0;
+}
+
+// returns the number of lines written to dst
+__device__ int merge_finish(const Seg* src, int n, Seg* dst, MergeScratch& S, int lane) {
+  if (n <= 0) return 0;
+  POST_T0(t_scan);
+  int* bcnt = reinterpret_cast<int*>(S.angles);
+  int ovf = 0;
   // neighbour list of a line = the earlier rows that accepted it, in angle order, then its own partners
   for (int x = lane; x < n; x += 32) {
     const int bc = min(bcnt[x], kNbCap), fc = S.nb_cnt[x];
@@ -412,13 +430,16 @@ __device__ int filter_short(Seg* lines, int n, float length_thr, int lane) {
   return m;
 }
 
-__device__ int frame_lines(Seg* raw, int n_raw, Seg* t1, Seg* t2, int w, int h, int nfeatures, MergeScratch& S,
-                           psl_keyline* kl, double* lineeq, int kl_cap, int lane) {
-  for (int i = lane; i < n_raw; i += 32) line::clamp_segment(raw[i], w, h);
-  __syncwarp();
-  int n1 = merge_lines(raw, n_raw, t1, 0.05f, 5.f, 15.f, S, lane);   // uselongline.cpp:458
-  n1 = filter_short(t1, n1, 30.f, lane);
-  int n2 = merge_lines(t1, n1, t2, 0.03f, 3.f, 30.f, S, lane);       // :464
+// thresholds of the two MergeLines passes (uselongline.cpp:458, :464): angle, distance, end-point gap
+__device__ __forceinline__ void merge_pass_thresholds(int pass, float& angle_thr, float& distance_thr, float& endpoint_thr) {
+  angle_thr = pass == 0 ? 0.05f : 0.03f;
+  distance_thr = pass == 0 ? 5.f : 3.f;
+  endpoint_thr = pass == 0 ? 15.f : 30.f;
+}
+
+// last part of a frame: FilterShortLines of the second pass, top-N by response, key lines and line equations
+__device__ int frame_keylines(Seg* t2, int n2, int w, int h, int nfeatures, MergeScratch& S, psl_keyline* kl,
+                              double* lineeq, int kl_cap, int lane) {
   n2 = filter_short(t2, n2, 50.f, lane);
   int n = n2;
   if (n2 > nfeatures) {  // LineExtractor.cpp:342-348 (stable by response, descending)
@@ -452,31 +473,81 @@ __device__ int frame_lines(Seg* raw, int n_raw, Seg* t1, Seg* t2, int w, int h, 
 
 constexpr int kPostWarps = 4;  // frames per CTA (one per warp)
 
+__device__ __forceinline__ line::MergeScratch post_scratch(const LineBuffers& L, int b, uint32_t* sort_cnt) {
+  const size_t o = (size_t)b * (size_t)L.raw_cap;
+  return line::MergeScratch{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
+                            L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o,
+                            L.m_fw + o * line::kNbCap, L.m_den + o, sort_cnt, L.m_scan + o};
+}
+
+// The merge stage of a batch is five launches: [A] clamp + prepare pass 1, [scan 1], [B] finish pass 1 + filter +
+// prepare pass 2, [scan 2], [C] finish pass 2 + filter + top-N + key lines.  A, B, C run one warp per frame; the scans
+// run one warp per 32 rows of a frame's angle order.  L.m_cnt[b] = {lines of the current pass, overflow flags}.
+template <int STAGE>
 __global__ void __launch_bounds__(kPostWarps * 32, 8)
     line_post_kernel(LineBuffers L, int nb, int nfeatures, psl_keyline* __restrict__ kl, double* __restrict__ lineeq,
                      int cap, int32_t* __restrict__ n_out, uint32_t* __restrict__ status) {
   __shared__ uint32_t sort_cnt[kPostWarps][linew::kSortBuckets];
   const int b = blockIdx.x * kPostWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= nb) return;
-  const size_t rc = (size_t)L.raw_cap, o = (size_t)b * rc;
-  line::MergeScratch S{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
-                       L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o,
-                       L.m_fw + o * line::kNbCap, L.m_den + o, sort_cnt[threadIdx.x >> 5], L.m_scan + o};
+  const size_t o = (size_t)b * (size_t)L.raw_cap;
+  line::MergeScratch S = post_scratch(L, b, sort_cnt[threadIdx.x >> 5]);
   line::Seg* raw = reinterpret_cast<line::Seg*>(L.raw) + o;
+  line::Seg *t1 = L.t1 + o, *t2 = L.t2 + o;
+  int32_t* cnt = L.m_cnt + 2 * (size_t)b;
   POST_T0(t_all);
-  const int n = linew::frame_lines(raw, L.n_raw[b], L.t1 + o, L.t2 + o, L.w, L.h, nfeatures, S, kl + (size_t)b * cap,
-                                   lineeq + (size_t)b * cap * 3, cap, lane);
-  POST_T1(4, t_all);
-  if (lane == 0) {
-    if (S.overflow) { atomicOr(status, kStatLineNeighbours); atomicMax(status + 1, (uint32_t)b + 1u); }
-    if (n < 0) { atomicOr(status, kStatOutOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
-    n_out[b] = n < 0 ? 0 : n;
+  if (STAGE == 0) {
+    const int n_raw = L.n_raw[b];
+    for (int i = lane; i < n_raw; i += 32) line::clamp_segment(raw[i], L.w, L.h);
+    __syncwarp();
+    linew::merge_prepare(raw, n_raw, S, lane);
+    if (lane == 0) { cnt[0] = n_raw; cnt[1] = 0; }
+  } else if (STAGE == 1) {
+    int n1 = linew::merge_finish(raw, cnt[0], t1, S, lane);
+    n1 = linew::filter_short(t1, n1, 30.f, lane);
+    linew::merge_prepare(t1, n1, S, lane);
+    __syncwarp();
+    if (lane == 0) { cnt[0] = n1; if (S.overflow) cnt[1] = 1; }
+  } else {
+    const int n2 = linew::merge_finish(t1, cnt[0], t2, S, lane);
+    const int n = linew::frame_keylines(t2, n2, L.w, L.h, nfeatures, S, kl + (size_t)b * cap, lineeq + (size_t)b * cap * 3,
+                                        cap, lane);
+    if (lane == 0) {
+      if (S.overflow || cnt[1]) { atomicOr(status, kStatLineNeighbours); atomicMax(status + 1, (uint32_t)b + 1u); }
+      if (n < 0) { atomicOr(status, kStatOutOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
+      n_out[b] = n < 0 ? 0 : n;
+    }
   }
+  POST_T1(4, t_all);
+}
+
+constexpr int kScanWarps = 4;  // row blocks per CTA
+
+__global__ void __launch_bounds__(kScanWarps * 32)
+    line_scan_kernel(LineBuffers L, int nb, int pass) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int base = (blockIdx.x * kScanWarps + (threadIdx.x >> 5)) * 32;
+  int32_t* cnt = L.m_cnt + 2 * (size_t)b;
+  const int n = cnt[0];
+  if (base >= n) return;
+  line::MergeScratch S = post_scratch(L, b, nullptr);
+  float angle_thr, distance_thr, endpoint_thr;
+  linew::merge_pass_thresholds(pass, angle_thr, distance_thr, endpoint_thr);
+  POST_T0(t_scan);
+  const int ovf = linew::merge_scan_rows(base, n, angle_thr, distance_thr, endpoint_thr, S, lane);
+  POST_T1(1, t_scan);
+  if (ovf && lane == 0) cnt[1] = 1;
 }
 
 void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int cap,
                       int32_t* n_out, uint32_t* status, cudaStream_t st) {
-  line_post_kernel<<<(nb + kPostWarps - 1) / kPostWarps, kPostWarps * 32, 0, st>>>(L, nb, nfeatures, kl, lineeq, cap, n_out, status);
+  const int grid = (nb + kPostWarps - 1) / kPostWarps;
+  const dim3 sgrid((L.raw_cap + 32 * kScanWarps - 1) / (32 * kScanWarps), nb);
+  line_post_kernel<0><<<grid, kPostWarps * 32, 0, st>>>(L, nb, nfeatures, kl, lineeq, cap, n_out, status);
+  line_scan_kernel<<<sgrid, kScanWarps * 32, 0, st>>>(L, nb, 0);
+  line_post_kernel<1><<<grid, kPostWarps * 32, 0, st>>>(L, nb, nfeatures, kl, lineeq, cap, n_out, status);
+  line_scan_kernel<<<sgrid, kScanWarps * 32, 0, st>>>(L, nb, 1);
+  line_post_kernel<2><<<grid, kPostWarps * 32, 0, st>>>(L, nb, nfeatures, kl, lineeq, cap, n_out, status);
 }
 
 // ---------------------------------------------------------------------------------------------------

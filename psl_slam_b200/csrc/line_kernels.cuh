@@ -40,6 +40,7 @@ struct LineBuffers {
   uint16_t* m_fw;      // [C][raw_cap][kNbCap]
   double* m_den;       // [C][raw_cap]
   line::ScanRec* m_scan;  // [C][raw_cap]
+  int32_t* m_cnt;      // [C][2]  lines of the current merge pass | neighbour-list overflow
   uint16_t* m_nb_cnt;
   int16_t* m_code;
   uint16_t* m_check;
@@ -59,6 +60,7 @@ void launch_lsd_prologue(const LineBuffers& L, ImgBatch in, int nb, cudaStream_t
 void launch_lsd_order(const LineBuffers& L, int nb, cudaStream_t st);
 void launch_lsd_core(const LineBuffers& L, int nb, uint32_t* status, cudaStream_t st);
 // clamp + merge + top-N + keylines + line equations (LineExtractor.cpp:338-363); outputs are [nb][cap] blocks
+constexpr int kLinePostLaunches = 5;  // prepare, pair scan, finish + prepare, pair scan, finish + key lines
 void launch_line_post(const LineBuffers& L, int nb, int nfeatures, psl_keyline* kl, double* lineeq, int cap,
                       int32_t* n_out, uint32_t* status, cudaStream_t st);
 // LBD descriptors of the keylines (BinaryDescriptor::compute, LineExtractor.cpp:349-350); lbd72 optional.
