@@ -40,7 +40,7 @@ struct Seg { float v[4]; };
 
 // Scratch of one frame (all arrays sized for `cap` segments).
 // pair-scan record of the warp-cooperative kernel: segment | angle | denominator of PointLineDistance
-struct alignas(16) ScanRec { Seg s; float angle, pad; double den; };
+struct alignas(16) ScanRec { Seg s; float angle, tden; double den; };  // tden: (float)(distance threshold * den)
 
 struct MergeScratch {
   int cap;

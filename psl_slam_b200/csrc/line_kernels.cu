@@ -143,18 +143,27 @@ __device__ void rank_sort(uint16_t* bkt, uint16_t* out, int n, const float* key,
 
 // line::point_line_distance(l, x0, y0) > thr with the line's denominator sqrt(a^2 + b^2) taken from the per-line table.
 // The reference compares (float)((double)num / den) with thr; the fp64 division is about forty instructions and the
-// outcome is obvious for all but a sliver of the pairs, so the quotient is only formed when num is within 0.1 % of
-// thr * den (or den is not a positive finite number).
-__device__ __forceinline__ bool pld_exceeds(const Seg& l, double den, float x0, float y0, float thr) {
+// outcome is obvious for all but a sliver of the pairs, so the quotient is only formed when num is within 0.2 % of
+// thr * den (tden: that product rounded to fp32, from the line's scan record) or tden is not a positive finite number.
+__device__ __forceinline__ bool pld_exceeds(const Seg& l, double den, float tden, float x0, float y0, float thr) {
   const float x1 = l.v[0], y1 = l.v[1], x2 = l.v[2], y2 = l.v[3];
   const float num = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(__fsub_rn(y2, y1), x0), __fmul_rn(__fsub_rn(x1, x2), y0)),
                                     __fsub_rn(__fmul_rn(x2, y1), __fmul_rn(x1, y2))));
-  const double t = (double)thr * den, dn = (double)num;
-  if (den > 0.0 && t < 1e300) {
-    if (dn > t * 1.001) return true;
-    if (dn < t * 0.999) return false;
+  if (tden > 0.f && tden < 1e30f) {
+    if (num > tden * 1.002f) return true;
+    if (num < tden * 0.998f) return false;
   }
-  return (float)(dn / den) > thr;
+  return (float)((double)num / den) > thr;
+}
+
+// AngleDiff(a1, a2) > thr (uselongline.cpp:17-22: min(|a2 - a1|, pi + min - max), the second term through fp64) for
+// a threshold below 0.14 rad: the fp64 term is pi - |a2 - a1| up to rounding, so it only decides when the plain
+// difference is within 0.14 of pi.
+__device__ __forceinline__ bool angle_gap_exceeds(float a1, float a2, float thr) {
+  const float c1 = fabsf(__fsub_rn(a2, a1));
+  if (c1 <= thr) return false;
+  if (c1 < 3.0f && thr < 0.14f) return true;
+  return line::angle_diff(a1, a2) > thr;
 }
 
 // MergeLines (uselongline.cpp:24-264) in three phases, so that the pair scan -- two thirds of the work, independent per
@@ -162,7 +171,7 @@ __device__ __forceinline__ bool pld_exceeds(const Seg& l, double den, float x0, 
 //   merge_prepare    angles, angle order, the per-line scan records                       (one warp per frame)
 //   merge_scan_rows  the pair tests of 32 rows of the angle order                          (one warp per 32 rows)
 //   merge_finish     neighbour lists in order, clusters, sub-clusters, folded merges      (one warp per frame)
-__device__ void merge_prepare(const Seg* src, int n, MergeScratch& S, int lane) {
+__device__ void merge_prepare(const Seg* src, int n, float distance_thr, MergeScratch& S, int lane) {
   if (n <= 0) return;
   POST_T0(t_sort);
   for (int i = lane; i < n; i += 32) {
@@ -187,8 +196,8 @@ __device__ void merge_prepare(const Seg* src, int n, MergeScratch& S, int lane) 
     ScanRec r;
     r.s = sj;
     r.angle = S.angles[id];
-    r.pad = 0.f;
     r.den = sqrt(a * a + b * b);
+    r.tden = (float)((double)distance_thr * r.den);
     srec[j] = r;
     S.sangles[j] = r.angle;   // (the bisection over a vertical line's far partners reads the angles alone)
   }
@@ -227,8 +236,10 @@ __device__ int merge_scan_rows(int base, int n, float angle_thr, float distance_
       const bool horiz = fabsf(angle1) < quarter_turn;
       const line::AxisSeg p = line::along_axis(s1, horiz);
       const bool can_break = (double)fabsf(angle1) < (line::kPi / 2 - (double)angle_thr);
-      const float mx1 = (float)(0.5 * (double)__fadd_rn(s1.v[0], s1.v[2])), my1 = (float)(0.5 * (double)__fadd_rn(s1.v[1], s1.v[3]));
+      // midpoints: the reference's 0.5 * (x1 + x2) on floats; halving is exact, so the fp64 detour is not needed
+      const float mx1 = __fmul_rn(0.5f, __fadd_rn(s1.v[0], s1.v[2])), my1 = __fmul_rn(0.5f, __fadd_rn(s1.v[1], s1.v[3]));
       const double den1 = r1.den;
+      const float tden1 = r1.tden;
       int fc = 0;
       // The partners are read one iteration ahead (angle, segment, denominator of the next j are requested before the
       // current one is tested): the working set of the resident frames does not fit L1, so every partner is an L2 round
@@ -240,10 +251,11 @@ __device__ int merge_scan_rows(int base, int n, float angle_thr, float distance_
         const float angle2 = r_nx.angle;
         const Seg s2 = r_nx.s;
         const double den2 = r_nx.den;
+        const float tden2 = r_nx.tden;
         const int jc = j;
         ++j;
         if (j < n) r_nx = srec[j];
-        if (line::angle_diff(angle1, angle2) > angle_thr) {
+        if (angle_gap_exceeds(angle1, angle2, angle_thr)) {
           if (can_break) break;   // the scalar loop stops at the first partner whose angle gap is too large
           // A near-vertical segment `continue`s past such partners instead.  In the angle-sorted order they form one
           // contiguous run: |a2 - a1| grows with j, pi + a1 - a2 (the wrap-around branch of AngleDiff) shrinks, so
@@ -252,15 +264,15 @@ __device__ int merge_scan_rows(int base, int n, float angle_thr, float distance_
           int lo = jc + 1, hi = n;
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (line::angle_diff(angle1, S.sangles[mid]) > angle_thr) lo = mid + 1;
+            if (angle_gap_exceeds(angle1, S.sangles[mid], angle_thr)) lo = mid + 1;
             else hi = mid;
           }
           j = lo;
           if (j < n) r_nx = srec[j];
           continue;
         }
-        const float mx2 = (float)(0.5 * (double)__fadd_rn(s2.v[0], s2.v[2])), my2 = (float)(0.5 * (double)__fadd_rn(s2.v[1], s2.v[3]));
-        if (pld_exceeds(s2, den2, mx1, my1, distance_thr) && pld_exceeds(s1, den1, mx2, my2, distance_thr)) continue;
+        const float mx2 = __fmul_rn(0.5f, __fadd_rn(s2.v[0], s2.v[2])), my2 = __fmul_rn(0.5f, __fadd_rn(s2.v[1], s2.v[3]));
+        if (pld_exceeds(s2, den2, tden2, mx1, my1, distance_thr) && pld_exceeds(s1, den1, tden1, mx2, my2, distance_thr)) continue;
         if (!line::ends_meet(p, line::along_axis(s2, horiz), horiz, gap_sq_thr)) continue;
         const int idx2 = S.order[jc];
         const int b = atomicAdd(&bcnt[idx2], 1);   // slot in idx2's list of earlier rows (unordered until the pass below)
@@ -500,12 +512,12 @@ __global__ void __launch_bounds__(kPostWarps * 32, 8)
     const int n_raw = L.n_raw[b];
     for (int i = lane; i < n_raw; i += 32) line::clamp_segment(raw[i], L.w, L.h);
     __syncwarp();
-    linew::merge_prepare(raw, n_raw, S, lane);
+    linew::merge_prepare(raw, n_raw, 5.f, S, lane);
     if (lane == 0) { cnt[0] = n_raw; cnt[1] = 0; }
   } else if (STAGE == 1) {
     int n1 = linew::merge_finish(raw, cnt[0], t1, S, lane);
     n1 = linew::filter_short(t1, n1, 30.f, lane);
-    linew::merge_prepare(t1, n1, S, lane);
+    linew::merge_prepare(t1, n1, 3.f, S, lane);
     __syncwarp();
     if (lane == 0) { cnt[0] = n1; if (S.overflow) cnt[1] = 1; }
   } else {
