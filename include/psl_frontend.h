@@ -74,8 +74,11 @@ typedef struct psl_config {
   int32_t orb_nlevels;     /* ORBextractor.nLevels     (8)    */
   int32_t orb_ini_th_fast; /* ORBextractor.iniThFAST   (20)   */
   int32_t orb_min_th_fast; /* ORBextractor.minThFAST   (7)    */
-  int32_t orb_max_candidates; /* FAST candidate pool per frame; 0 = auto (the reference only
-                                 reserves nfeatures*10 as a hint, ORBextractor.cc:779) */
+  int32_t orb_max_candidates; /* FAST candidate pool per frame (the reference only reserves nfeatures*10 as a hint,
+                                 ORBextractor.cc:779).  > 0: hard bound, overflow = PSL_E_CAPACITY.  0 / < 0: starts at
+                                 max(16384, 32 nfeatures) / at |value| and doubles when a frame overflows it: the
+                                 host-pointer entry points then run the call again themselves, the device-pointer
+                                 ones return PSL_E_CAPACITY once and succeed when called again */
   int32_t chunk_frames;    /* frames per launch of the ORB stages; 0 = auto (max_batch clamped to [1, 512]; ~2.4 MB of HBM per frame at 640x480) */
   int32_t line_nfeatures;  /* LINEextractor.nFeatures  (200)  */
   float line_scale_factor; /* LINEextractor.scaleFactor (1.2; truncated to int 1 by the reference) */
@@ -85,7 +88,8 @@ typedef struct psl_config {
   int32_t line_chunk_frames; /* frames per launch of the line stages; 0 = auto (max_batch clamped to [64, 4096]).
                                 The LSD core runs one frame per warp, so the batch is its parallel axis;
                                 the line buffers take about 7.5 MB of HBM per frame of the chunk at 640x480 */
-  int32_t line_max_raw;    /* raw LSD segments kept per frame before the merge; 0 = auto (4096) */
+  int32_t line_max_raw;    /* raw LSD segments kept per frame before the merge: > 0 hard bound, 0 / < 0 starts at
+                              4096 / |value| and grows like orb_max_candidates (at most 65535) */
 } psl_config;
 
 void psl_default_config(psl_config* cfg);

@@ -193,8 +193,11 @@ __device__ __forceinline__ void fast_cell_body(const OrbGeometry* __restrict__ g
     uint32_t base = 0;
     if (total) base = atomicAdd(pool_count + b, (uint32_t)total);
     s_base = base;
-    *tab = make_uint2(base, (uint32_t)total);
-    if (base + total > (uint32_t)pool_cap) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
+    // a cell that does not fit keeps no candidates and says so in its table entry: the octree gathers through the
+    // table, and a level whose total still fits would otherwise read past the pool
+    const bool fits = base + total <= (uint32_t)pool_cap;
+    *tab = make_uint2(fits ? base : 0u, fits ? (uint32_t)total : 0u);
+    if (!fits) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
   }
   __syncthreads();
   const uint32_t base = s_base;
@@ -462,8 +465,9 @@ __global__ void __launch_bounds__(kRowsThreads)
     uint32_t base = 0;
     if (lane == 0) {
       base = atomicAdd(pool_count + b, (uint32_t)total);
-      *tab = make_uint2(base, (uint32_t)total);
-      if (base + total > (uint32_t)pool_cap) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
+      const bool fits = base + total <= (uint32_t)pool_cap;   // (see fast_cell_body)
+      *tab = make_uint2(fits ? base : 0u, fits ? (uint32_t)total : 0u);
+      if (!fits) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
     }
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + total > (uint32_t)pool_cap) return;

@@ -25,10 +25,14 @@ int ensure_bytes(psl_ctx* ctx, void** p, size_t* have, size_t need) {
   *have = need;
   return PSL_OK;
 }
+static void free_geometry(psl_ctx* c);
+
 int check_status(psl_ctx* ctx) {
   PSL_CK(cudaMemcpyAsync(ctx->h_status, ctx->d_status, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PSL_CK(cudaStreamSynchronize(ctx->stream));
   const uint32_t s = ctx->h_status[0];
+  ctx->last_flags = s;
+  ctx->grew = false;
   if (!s) return PSL_OK;
   // word 1: 1 + the largest frame index (inside its launch chunk) that raised a flag, so that the caller of a batched
   // entry point knows where to look; the other frames of the batch are complete
@@ -36,10 +40,15 @@ int check_status(psl_ctx* ctx) {
   PSL_CK(cudaMemsetAsync(ctx->d_status, 0, 2 * sizeof(uint32_t), ctx->stream));
   if (s & kStatBadRoot) return fail(ctx, PSL_E_INVALID, "octree: candidate outside the root nodes (aspect ratio)");
   if (s & kStatNodeOverflow) return fail(ctx, PSL_E_INTERNAL, "octree: node table bound violated");
+  // a capacity the context sizes itself is doubled right here: the call that hit it fails once (the host-pointer
+  // extractors run it again themselves), the next one has the room
+  ctx->grew = grow_capacity(ctx);
+  const std::string again = ctx->grew ? " -- capacity doubled, call again" : "";
   if (s & kStatCandOverflow)
-    return fail(ctx, PSL_E_CAPACITY, std::string("FAST candidate pool overflow: raise psl_config.orb_max_candidates") + where);
+    return fail(ctx, PSL_E_CAPACITY, std::string("FAST candidate pool overflow: raise psl_config.orb_max_candidates") + where + again);
   if (s & kStatOutOverflow) return fail(ctx, PSL_E_CAPACITY, std::string("output capacity `cap` too small") + where);
-  if (s & kStatLineRaw) return fail(ctx, PSL_E_CAPACITY, std::string("LSD raw segment overflow: raise psl_config.line_max_raw") + where);
+  if (s & kStatLineRaw)
+    return fail(ctx, PSL_E_CAPACITY, std::string("LSD raw segment overflow: raise psl_config.line_max_raw") + where + again);
   if (s & kStatLineNeighbours) return fail(ctx, PSL_E_CAPACITY, std::string("line merge: neighbour list bound violated") + where);
   return fail(ctx, PSL_E_INTERNAL, "unknown device status");
 }
@@ -94,6 +103,26 @@ static void free_geometry(psl_ctx* c) {
   cudaFree(c->d_sel); c->d_sel = nullptr;
   cudaFree(c->d_sel_count); c->d_sel_count = nullptr;
   c->geo_w = c->geo_h = 0;
+}
+
+// After a PSL_E_CAPACITY from check_status(): double the capacity that overflowed if the context owns it (auto mode)
+// and drop the buffers sized by it, so that the same call can simply be made again.  False: nothing to grow.
+bool grow_capacity(psl_ctx* ctx) {
+  const uint32_t s = ctx->last_flags;
+  bool grown = false;
+  if ((s & kStatCandOverflow) && ctx->pool_auto && ctx->pool_cap < (1 << 22)) {
+    ctx->pool_cap *= 2;
+    cudaStreamSynchronize(ctx->stream);
+    free_geometry(ctx);
+    grown = true;
+  }
+  if ((s & kStatLineRaw) && ctx->raw_auto && ctx->raw_cap < 65535) {
+    ctx->raw_cap = std::min(2 * ctx->raw_cap, 65535);
+    cudaStreamSynchronize(ctx->stream);
+    free_line_geometry(ctx);
+    grown = true;
+  }
+  return grown;
 }
 
 // Level sizes, cell grids, octree roots and device buffers for frames of w x h.
@@ -322,7 +351,14 @@ int psl_create(const psl_config* cfg, psl_ctx** out) {
   // frames per extraction chunk: every per-chunk buffer is sized by it, so a context made for single frames stays small
   ctx->chunk = cfg->chunk_frames > 0 ? cfg->chunk_frames : std::min(512, std::max(cfg->max_batch, 1));
   ctx->line_chunk = cfg->line_chunk_frames > 0 ? cfg->line_chunk_frames : std::min(std::max(cfg->max_batch, 64), 4096);
-  ctx->pool_cap = cfg->orb_max_candidates > 0 ? cfg->orb_max_candidates : std::max(16384, 32 * cfg->orb_nfeatures);
+  // capacities that depend on the image content: a positive value is a hard bound (overflow = PSL_E_CAPACITY), 0 or a
+  // negative value starts at the default / at |value| and grows when a frame overflows it (grow_capacity)
+  ctx->pool_cap = cfg->orb_max_candidates > 0   ? cfg->orb_max_candidates
+                  : cfg->orb_max_candidates < 0 ? -cfg->orb_max_candidates
+                                                : std::max(16384, 32 * cfg->orb_nfeatures);
+  ctx->pool_auto = cfg->orb_max_candidates <= 0;
+  ctx->raw_cap = cfg->line_max_raw > 0 ? cfg->line_max_raw : (cfg->line_max_raw < 0 ? -cfg->line_max_raw : 4096);
+  ctx->raw_auto = cfg->line_max_raw <= 0;
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream_copy, cudaStreamNonBlocking) == cudaSuccess &&
@@ -446,12 +482,15 @@ int psl_orb_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t 
   for (int b = 0; b < B; ++b)
     PSL_CK(cudaMemcpy2DAsync(ctx->d_in + b * fs, pitch, gray + (size_t)b * frame_stride, stride, w, h,
                              cudaMemcpyHostToDevice, ctx->stream));
-  rc = psl_orb_extract_batch_dev(ctx, ctx->d_in, B, w, h, pitch, (int64_t)fs, ctx->d_kps, ctx->d_desc, cap, ctx->d_n);
-  if (rc) return rc;
-  PSL_CK(cudaMemcpyAsync(n, ctx->d_n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
-  PSL_CK(cudaMemcpyAsync(kps, ctx->d_kps, sizeof(psl_keypoint) * (size_t)cap * B, cudaMemcpyDeviceToHost, ctx->stream));
-  PSL_CK(cudaMemcpyAsync(desc, ctx->d_desc, (size_t)32 * cap * B, cudaMemcpyDeviceToHost, ctx->stream));
-  return check_status(ctx);
+  for (;;) {   // (again with a larger candidate pool when a frame overflowed an auto-sized one)
+    rc = psl_orb_extract_batch_dev(ctx, ctx->d_in, B, w, h, pitch, (int64_t)fs, ctx->d_kps, ctx->d_desc, cap, ctx->d_n);
+    if (rc) return rc;
+    PSL_CK(cudaMemcpyAsync(n, ctx->d_n, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    PSL_CK(cudaMemcpyAsync(kps, ctx->d_kps, sizeof(psl_keypoint) * (size_t)cap * B, cudaMemcpyDeviceToHost, ctx->stream));
+    PSL_CK(cudaMemcpyAsync(desc, ctx->d_desc, (size_t)32 * cap * B, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = check_status(ctx);
+    if (rc != PSL_E_CAPACITY || !ctx->grew) return rc;
+  }
 }
 
 int psl_profile_enable(psl_ctx* ctx, int32_t on) {

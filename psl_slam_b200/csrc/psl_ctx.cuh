@@ -23,6 +23,11 @@ struct psl_ctx {
   std::string err;
   int chunk = 0;
   int pool_cap = 0;
+  bool pool_auto = false;   // orb_max_candidates <= 0: the pool grows when a frame overflows it
+  int raw_cap = 0;          // LSD raw segments per frame (LineBuffers::raw_cap of the next geometry)
+  bool raw_auto = false;    // line_max_raw <= 0: grows likewise
+  uint32_t last_flags = 0;  // device status word of the last check_status()
+  bool grew = false;        // ... and whether it doubled a capacity (grow_capacity)
 
   // ORBextractor ctor tables (ORBextractor.cc:410-446)
   std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
@@ -92,6 +97,7 @@ int cuda_fail(psl_ctx* c, cudaError_t e, const char* what);
 int ensure_bytes(psl_ctx* c, void** p, size_t* have, size_t need);
 inline int ensure(psl_ctx* c, DevBuf& b, size_t need) { return ensure_bytes(c, &b.p, &b.bytes, need ? need : 16); }
 void free_line_geometry(psl_ctx* c);
+bool grow_capacity(psl_ctx* ctx);
 int check_status(psl_ctx* c);  // sync + translate the device status word
 // RAII-free stage bracket: begin/end record events when profiling is on and count launches.
 size_t prof_mark(psl_ctx* c);

@@ -56,7 +56,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
   L.Hs = (int)lrint(h * 0.8);
   const double logNT = 5 * (log10((double)L.Ws) + log10((double)L.Hs)) / 2 + log10(11.0);
   L.min_reg_size = (int)(size_t)(-logNT / log10(22.5 / 180));
-  L.raw_cap = ctx->cfg.line_max_raw > 0 ? ctx->cfg.line_max_raw : 4096;
+  L.raw_cap = ctx->raw_cap;
   if (L.raw_cap > 65535) return fail(ctx, PSL_E_INVALID, "line_max_raw must be <= 65535");
   const size_t C = ctx->line_chunk, npx = (size_t)L.Ws * L.Hs, R = L.raw_cap;
   std::vector<short2> xt, yt;
@@ -198,17 +198,20 @@ int psl_line_extract_batch(psl_ctx* ctx, const uint8_t* gray, int32_t B, int32_t
   for (int b = 0; b < B; ++b)
     PSL_CK(cudaMemcpy2DAsync(ctx->l_in.as<uint8_t>() + b * fs, pitch, gray + (size_t)b * frame_stride, stride, w, h,
                              cudaMemcpyHostToDevice, ctx->stream));
-  rc = psl_line_extract_batch_dev(ctx, ctx->l_in.as<uint8_t>(), B, w, h, pitch, (int64_t)fs, ctx->l_kl.as<psl_keyline>(),
-                                  ctx->l_desc.as<uint8_t>(), ctx->l_eq.as<double>(), lbd72 ? ctx->l_lbd.as<float>() : nullptr,
-                                  cap, ctx->l_n.as<int32_t>());
-  if (rc) return rc;
-  cudaStream_t st = ctx->stream;
-  PSL_CK(cudaMemcpyAsync(n, ctx->l_n.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(kl, ctx->l_kl.p, sizeof(psl_keyline) * N, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(ldesc, ctx->l_desc.p, 32 * N, cudaMemcpyDeviceToHost, st));
-  PSL_CK(cudaMemcpyAsync(lineeq, ctx->l_eq.p, 24 * N, cudaMemcpyDeviceToHost, st));
-  if (lbd72) PSL_CK(cudaMemcpyAsync(lbd72, ctx->l_lbd.p, 288 * N, cudaMemcpyDeviceToHost, st));
-  return check_status(ctx);
+  for (;;) {   // (again with more room for raw segments when a frame overflowed an auto-sized bound)
+    rc = psl_line_extract_batch_dev(ctx, ctx->l_in.as<uint8_t>(), B, w, h, pitch, (int64_t)fs, ctx->l_kl.as<psl_keyline>(),
+                                    ctx->l_desc.as<uint8_t>(), ctx->l_eq.as<double>(), lbd72 ? ctx->l_lbd.as<float>() : nullptr,
+                                    cap, ctx->l_n.as<int32_t>());
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    PSL_CK(cudaMemcpyAsync(n, ctx->l_n.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+    PSL_CK(cudaMemcpyAsync(kl, ctx->l_kl.p, sizeof(psl_keyline) * N, cudaMemcpyDeviceToHost, st));
+    PSL_CK(cudaMemcpyAsync(ldesc, ctx->l_desc.p, 32 * N, cudaMemcpyDeviceToHost, st));
+    PSL_CK(cudaMemcpyAsync(lineeq, ctx->l_eq.p, 24 * N, cudaMemcpyDeviceToHost, st));
+    if (lbd72) PSL_CK(cudaMemcpyAsync(lbd72, ctx->l_lbd.p, 288 * N, cudaMemcpyDeviceToHost, st));
+    rc = check_status(ctx);
+    if (rc != PSL_E_CAPACITY || !ctx->grew) return rc;
+  }
 }
 
 int psl_line_extract(psl_ctx* ctx, const uint8_t* gray, int32_t w, int32_t h, int32_t stride, psl_keyline* kl,

@@ -85,6 +85,19 @@ def test_capacity_errors_are_loud():
         LINEextractor(max_width=320, max_height=240)(gray[0])
 
 
+def test_auto_capacity_grows_and_reruns():
+    """line_max_raw <= 0: the context owns the bound.  A frame with more raw segments than the starting value makes the
+    host-pointer call grow the buffers and run again by itself; the result is the one of a roomy context."""
+    from psl_slam_b200 import LINEextractor, synth
+    gray, _, _ = synth.sequence(6, 2)
+    kl0, ld0, eq0 = LINEextractor()(gray[0])
+    ex = LINEextractor(max_raw=-16, chunk_frames=2)
+    for g in gray:   # the second call starts with the grown bound
+        kl, ld, eq = ex(g)
+    kl, ld, eq = ex(gray[0])
+    assert kl.tobytes() == kl0.tobytes() and np.array_equal(ld, ld0) and np.array_equal(eq, eq0)
+
+
 def test_unaligned_device_frames_vs_oracle(orc):
     """Device-pointer entry with an odd base address and row stride: the byte-load form of the blur kernel (LSD
     prologue, LBD) must reproduce the word form and the oracle."""

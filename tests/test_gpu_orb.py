@@ -97,12 +97,26 @@ def test_candidate_pool_overflow_is_loud():
     from psl_slam_b200 import ORBextractor, PslError
     rng = np.random.default_rng(5)
     img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
-    ex = ORBextractor(max_candidates=1024)
-    with pytest.raises(PslError) as e:
-        ex(img)
-    assert e.value.code == -3
+    # 1024: the first level alone overflows; 32768: a level whose own total fits loses single cells to the other
+    # levels' appends (the gather of the octree must not follow the table entries of cells that were dropped)
+    for cap in (1024, 32768):
+        ex = ORBextractor(max_candidates=cap)
+        with pytest.raises(PslError) as e:
+            ex(img)
+        assert e.value.code == -3
     ex2 = ORBextractor(max_candidates=131072)
     assert len(ex2(img)[0]) >= 1000
+
+
+def test_auto_candidate_pool_grows_and_reruns():
+    """orb_max_candidates <= 0: the pool belongs to the context and doubles until the frame fits (the call is run again
+    inside the host-pointer entry point); same key points and descriptors as with a roomy fixed pool."""
+    from psl_slam_b200 import ORBextractor
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    k0, d0 = ORBextractor(max_candidates=131072)(img)
+    k1, d1 = ORBextractor(max_candidates=-1024)(img)
+    assert k0.tobytes() == k1.tobytes() and np.array_equal(d0, d1)
 
 
 @pytest.mark.parametrize("name", ORB)
