@@ -24,8 +24,8 @@ ncu -i $T/prof_core.ncu-rep --page source --print-source cuda,sass --csv 2>/dev/
 # full sets of the other kernels (the ORB kernels run 512 frames per launch in the bench as well; the line kernels are
 # captured at 512 frames per launch to keep ncu's save / restore between replay passes small)
 ncu --set full --clock-control none \
-    -k regex:"line_post|lbd_kernel|sobel|resize_exact|lsd_gradient|lsd_seed_order|fast_|octree|describe|proj_candidates|proj_resolve|color_to_gray" \
-    -c 22 -o $T/prof_main -f python bench.py --frames 512 --distinct 64 --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_main_${TAG}.log 2>&1
+    -k regex:"line_post|line_scan|lbd_kernel|sobel|resize_exact|lsd_gradient|lsd_seed_order|fast_|octree|describe|proj_candidates|proj_resolve|color_to_gray" \
+    -c 30 -o $T/prof_main -f python bench.py --frames 512 --distinct 64 --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_main_${TAG}.log 2>&1
 ncu --set full --clock-control none -k regex:"resize_words|gauss7" -c 3 -o $T/prof_stream -f \
     python bench.py --frames 512 --distinct 64 --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_stream_${TAG}.log 2>&1
 for r in main stream; do

@@ -50,7 +50,7 @@ for part, frames in (("core", 4096), ("main", 512), ("stream", 512)):
         name = re.sub(r"^void ", "", name)
         if name not in per_kernel:
             per_kernel[name] = ((float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]) / frames, frames)
-stage_kernel = {"lsd_grow": "lsd_core_kernel", "line_merge": "line_post_kernel", "lbd": "lbd_kernel",
+stage_kernel = {"lsd_grow": "lsd_core_kernel", "line_merge": "line_scan_kernel", "lbd": "lbd_kernel",
                 "fast": "fast_rows_kernel<1>", "describe": "describe_kernel", "blur": "gauss7_kernel<1>",
                 "pyramid": "resize_words_kernel", "candidates": "proj_candidates_kernel", "lsd_order": "lsd_seed_order_kernel"}
 traffic = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per frame of the stage's dominant kernel, from one `ncu --set full` "
