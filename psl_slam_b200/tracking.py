@@ -126,3 +126,44 @@ def image_bounds(ctx, cols: int, rows: int, cam):
     b = np.zeros(4, np.float32)
     ctx.check(_lib.lib().psl_image_bounds(ctx.handle, int(cols), int(rows), C.byref(cam), _ptr(b)))
     return tuple(float(v) for v in b)
+
+
+def extract_lsd_batch_dev(lex, d_gray: int, d_depth_u16: int, B: int, W: int, H: int, cam: Camera, seed: int = 0,
+                          gray_stride: int | None = None, junction_cap: int = 2048):
+    """Frame::ExtractLSD up to the plane hypotheses (src/Frame.cc:489-511) for B frames resident in HBM, chained on the
+    context's stream without a round trip to the host:
+
+        (*mpLSDextractorLeft)(im, mask, mvKeylinesUn, mLdesc, mvKeyLineFunctions)       psl_line_extract_batch_dev
+        imDepth.convertTo(CV_32F, mDepthMapFactor)           (Tracking.cc:232-235)      psl_convert_rgbd_dev
+        isLineGood(imGray, imDepth, K)                       (Frame.cc:662-750)         psl_lines_3d_dev
+        CPartiallyRecoverConnectivity + convertFansToKeyLines (Frame.cc:504-507)        psl_line_junctions_dev
+
+    d_gray: u8 [B][H][gray_stride], d_depth_u16: u16 [B][H][W] (device addresses).  Returns torch tensors on the device
+    (rows past the per-frame counts are unspecified): kl [B,cap] bytes of KEYLINE_DTYPE, ldesc [B,cap,32], lineeq
+    [B,cap,3] f64, n [B], depth [B,H,W] f32, lines3d [B,cap,6] f64, line_eq3 [B,cap,3] f32, fans [B,jcap,4] f32,
+    junctions [B,jcap] bytes of JUNCTION_DTYPE, n_fans [B], n_junctions [B].  psl_plane_hypotheses (host pointers, one
+    frame) takes rows of these arrays as they are."""
+    import torch
+
+    from ._lib import JUNCTION_DTYPE
+    ctx, L = lex.ctx, _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cap, gs = lex.cap, gray_stride or W
+    z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+    out = {"kl": z((B, cap, KEYLINE_DTYPE.itemsize), torch.uint8), "ldesc": z((B, cap, 32), torch.uint8),
+           "lineeq": z((B, cap, 3), torch.float64), "n": z((B,), torch.int32), "depth": z((B, H, W), torch.float32),
+           "lines3d": z((B, cap, 6), torch.float64), "line_eq3": z((B, cap, 3), torch.float32),
+           "fans": z((B, junction_cap, 4), torch.float32),
+           "junctions": z((B, junction_cap, JUNCTION_DTYPE.itemsize), torch.uint8), "n_fans": z((B,), torch.int32),
+           "n_junctions": z((B,), torch.int32)}
+    p = {k: v.data_ptr() for k, v in out.items()}
+    lex.extract_batch_dev(d_gray, B, W, H, gs, gs * H, p["kl"], p["ldesc"], p["lineeq"], None, p["n"])
+    ctx.check(L.psl_convert_rgbd_dev(ctx.handle, None, 3, 1, 0, 0, None, 0, 0, d_depth_u16, W, W * H,
+                                     C.c_float(cam.depth_factor), p["depth"], B, W, H))
+    ctx.check(L.psl_lines_3d_dev(ctx.handle, p["kl"], p["n"], cap, B, p["depth"], W, H, W, W * H, C.c_float(cam.fx),
+                                 C.c_float(cam.fy), C.c_float(cam.cx), C.c_float(cam.cy), C.c_uint32(seed), p["lines3d"],
+                                 p["line_eq3"]))
+    ctx.check(L.psl_line_junctions_dev(ctx.handle, p["kl"], p["n"], cap, B, p["lines3d"], W, H, C.c_float(20.0),
+                                       C.c_float(float(np.float32(0.25 * np.pi))), p["fans"], p["junctions"],
+                                       junction_cap, p["n_fans"], p["n_junctions"]))
+    return out

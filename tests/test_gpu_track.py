@@ -221,3 +221,48 @@ def test_pose_after_matching_vs_oracle_chain(orc):
         assert cnt[b] == wcnt and wcnt > 200, (b, cnt[b], wcnt)
         assert np.array_equal(outl[b, :n], wout), b
         assert np.allclose(To[b], wT, rtol=0, atol=1e-6), b
+
+
+def test_extract_lsd_chain_on_device_vs_oracle_pieces(orc):
+    """Frame::ExtractLSD (Frame.cc:489-645) chained on the device for a batch -- line extraction -> depth conversion ->
+    3-D lines -> junctions, nothing in between touching the host -- against the same chain composed from the oracle's
+    pieces on the frames one by one; the plane hypotheses (host entry point) then run on the rows of the device arrays."""
+    import torch
+
+    from psl_slam_b200 import LINEextractor, make_camera, plane_hypotheses, synth
+    from psl_slam_b200._lib import JUNCTION_DTYPE, KEYLINE_DTYPE
+    from psl_slam_b200.tracking import extract_lsd_batch_dev
+    K = synth.ICL
+    B = 3
+    gray, depth, _ = synth.sequence(11, B)
+    H, W = gray.shape[1:]
+    lex = LINEextractor()
+    cam = make_camera(K["fx"], K["fy"], K["cx"], K["cy"], K["bf"], K["depth_factor"])
+    d_gray, d_depth = torch.from_numpy(gray).cuda(), torch.from_numpy(depth.view(np.int16)).cuda()
+    out = extract_lsd_batch_dev(lex, d_gray.data_ptr(), d_depth.data_ptr(), B, W, H, cam, seed=7)
+    lex.ctx.sync()
+    n = out["n"].cpu().numpy()
+    kl_all = out["kl"].cpu().numpy().reshape(B, -1).view(KEYLINE_DTYPE)
+    js_all = out["junctions"].cpu().numpy().reshape(B, -1).view(JUNCTION_DTYPE)
+    planes_seen = 0
+    for b in range(B):
+        kl, ld, eq = orc.line_extract(gray[b])
+        assert n[b] == len(kl) and kl_all[b, : n[b]].tobytes() == kl.tobytes()
+        assert np.array_equal(out["ldesc"][b, : n[b]].cpu().numpy(), ld)
+        depf = depth[b].astype(np.float32) * np.float32(cam.depth_factor)   # convertTo(CV_32F, factor): one fp32 product
+        assert np.array_equal(out["depth"][b].cpu().numpy(), depf)
+        l3, eq3 = orc.lines_3d(kl, depf, cam.fx, cam.fy, cam.cx, cam.cy, 7)
+        assert np.array_equal(out["lines3d"][b, : n[b]].cpu().numpy(), l3)
+        assert np.array_equal(out["line_eq3"][b, : n[b]].cpu().numpy(), eq3)
+        fans, js = orc.line_junctions(kl, l3, W, H)
+        nf, nj = int(out["n_fans"][b]), int(out["n_junctions"][b])
+        assert nf == len(fans) and nj == len(js)
+        assert np.array_equal(out["fans"][b, :nf].cpu().numpy(), fans)
+        assert js_all[b, :nj].tobytes() == np.ascontiguousarray(js, JUNCTION_DTYPE).tobytes()
+        got = plane_hypotheses(lex.ctx, kl_all[b, : n[b]], out["line_eq3"][b, : n[b]].cpu().numpy(),
+                               out["lines3d"][b, : n[b]].cpu().numpy(), js_all[b, :nj])
+        want = orc.plane_hypotheses(kl, eq3, l3, js)
+        for g, w_ in zip(got, want):
+            assert np.array_equal(g, w_)
+        planes_seen += len(got[1])
+    assert n.min() > 10
