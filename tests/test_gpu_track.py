@@ -246,7 +246,7 @@ def test_extract_lsd_chain_on_device_vs_oracle_pieces(orc):
     js_all = out["junctions"].cpu().numpy().reshape(B, -1).view(JUNCTION_DTYPE)
     planes_seen = 0
     for b in range(B):
-        kl, ld, eq = orc.line_extract(gray[b])
+        kl, ld, eq, _ = orc.line_extract(gray[b])
         assert n[b] == len(kl) and kl_all[b, : n[b]].tobytes() == kl.tobytes()
         assert np.array_equal(out["ldesc"][b, : n[b]].cpu().numpy(), ld)
         depf = depth[b].astype(np.float32) * np.float32(cam.depth_factor)   # convertTo(CV_32F, factor): one fp32 product
