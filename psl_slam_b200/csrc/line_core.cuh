@@ -57,7 +57,6 @@ struct MergeScratch {
   int overflow;      // set when a neighbour list overflows
   float* sangles;    // [cap] angles in scan order (warp-cooperative kernel only)
   uint16_t* fw;      // [cap][kNbCap] a row's own partners (warp-cooperative kernel only)
-  double* den;       // [cap] sqrt(a^2 + b^2) of PointLineDistance per line, scan order (warp-cooperative kernel only)
   uint32_t* sort_cnt;  // bucket counters of the rank sort, shared memory (warp-cooperative kernel only)
   ScanRec* scan;       // [cap] lines in scan order (warp-cooperative kernel only)
 };

@@ -489,7 +489,7 @@ __device__ __forceinline__ line::MergeScratch post_scratch(const LineBuffers& L,
   const size_t o = (size_t)b * (size_t)L.raw_cap;
   return line::MergeScratch{L.raw_cap,      L.m_angles + o, L.m_length + o, L.m_order + o, L.m_tmp16 + o, L.m_nb + o * line::kNbCap,
                             L.m_nb_cnt + o, L.m_code + o,   L.m_check + o,  L.m_loc + o,   L.m_flag + o,  0, L.m_sangles + o,
-                            L.m_fw + o * line::kNbCap, L.m_den + o, sort_cnt, L.m_scan + o};
+                            L.m_fw + o * line::kNbCap, sort_cnt, L.m_scan + o};
 }
 
 // The merge stage of a batch is five launches: [A] clamp + prepare pass 1, [scan 1], [B] finish pass 1 + filter +

@@ -38,7 +38,6 @@ struct LineBuffers {
   uint16_t* m_tmp16;
   uint16_t* m_nb;      // [C][raw_cap][kNbCap]
   uint16_t* m_fw;      // [C][raw_cap][kNbCap]
-  double* m_den;       // [C][raw_cap]
   line::ScanRec* m_scan;  // [C][raw_cap]
   int32_t* m_cnt;      // [C][2]  lines of the current merge pass | neighbour-list overflow
   uint16_t* m_nb_cnt;

@@ -361,11 +361,7 @@ struct Sums {
 // The scalar loop over the lanes of one step (the reference's order of tests), for the steps the batched decision cannot
 // prove.  Accepted pixels get their flag, list and ring entries here.  `exact` says whether the sums already are the
 // reference's (false until the first accept of the region).
-#ifdef PSL_V_SEQ_INLINE
-__device__ __forceinline__
-#else
 __device__ __noinline__
-#endif
 Sums step_sequential(Frame f, int lin, uint32_t npk, float4 rec, bool cand, Sums s, bool exact,
                                              float seed_deg, float2 sterm, double prec, Quick qk, int lane) {
   unsigned mask = __ballot_sync(kFull, cand);
@@ -537,12 +533,6 @@ __device__ __forceinline__ int region_grow(const Frame& f, int seed_lin, uint32_
 
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy; };
 
-__device__ __noinline__ double2 sincos_ni(double a) {
-  double s, c;
-  sincos(a, &s, &c);
-  return make_double2(s, c);
-}
-
 __device__ __forceinline__ double modgrad(const Frame& f, int idx) {
   return sqrt((double)lsdw_n2(*flags_of(f, idx)) / 4.0);
 }
@@ -609,11 +599,7 @@ __device__ __forceinline__ void region2rect(const Frame& f, int n, double reg_an
   if (d < 0) d = -d;
   if (d > prec) theta += kPi;
   double dx, dy;
-#ifdef PSL_V_SINCOS_NI
-  { const double2 sc = sincos_ni(theta); dy = sc.x; dx = sc.y; }
-#else
   sincos(theta, &dy, &dx);
-#endif
   // extents: `if (l > l_max) l_max = l; else if (l < l_min) l_min = l;` with both starting at 0 is an
   // independent max and min (a value above the running max is positive, so it cannot lower the min)
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
@@ -711,37 +697,26 @@ __device__ __noinline__ int reduce_once(Frame f, int n, double xc, double yc, do
 
 constexpr int kCoreWarps = 4;  // frames per CTA (one per warp; the warps never synchronise with each other)
 
-#ifndef PSL_LSD_MINB
-#define PSL_LSD_MINB 7
-#endif
-__global__ void __launch_bounds__(kCoreWarps * 32, PSL_LSD_MINB)
+__global__ void __launch_bounds__(kCoreWarps * 32, 7)
     lsd_core_kernel(const __grid_constant__ LineBuffers L, int nb, uint32_t stride, uint32_t* __restrict__ status) {
   __shared__ uint32_t ring[kCoreWarps][lsdw::kRing];
   __shared__ __align__(16) double terms[kCoreWarps][96];
-#ifndef PSL_NO_OPAQUE
   // read once: under register pressure the compiler otherwise re-reads %tid (a slow special-register move) and rebuilds
   // the shared-memory and frame pointers inside the step loop
   unsigned tid_;
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_));
   const int wid = (int)(tid_ >> 5), slot = blockIdx.x * kCoreWarps + wid, lane = (int)(tid_ & 31u);
-#else
-  const int wid = threadIdx.x >> 5, slot = blockIdx.x * kCoreWarps + wid, lane = threadIdx.x & 31;
-#endif
   if (slot >= nb) return;
   // frame of this warp: a fixed permutation of the batch (stride coprime to nb), so that the warps of one SM hold
   // frames from all over the sequence — neighbouring frames cost about the same, and an SM that got only expensive
   // ones would finish last
   const int b = (int)(((uint64_t)slot * stride) % (uint32_t)nb);
   const size_t npx = (size_t)L.Ws * L.Hs;
-#ifndef PSL_NO_OPAQUE
   float4* pix_ = L.pix + b * npx;
   uint32_t* reg_ = L.reg + b * npx;
   uint32_t* ring_ = ring[wid];
   asm volatile("" : "+l"(pix_), "+l"(reg_), "+l"(ring_));
   const lsdw::Frame f{L.Ws, pix_, reg_, ring_, terms[wid]};
-#else
-  const lsdw::Frame f{L.Ws, L.pix + b * npx, L.reg + b * npx, ring[wid], terms[wid]};
-#endif
   const uint32_t* seeds = L.val_out + b * npx;
   const int n_seeds = L.n_def[b];
   float* out = L.raw + (size_t)b * L.raw_cap * 4;

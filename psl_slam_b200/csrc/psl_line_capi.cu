@@ -89,7 +89,7 @@ static int set_line_geometry(psl_ctx* ctx, int w, int h) {
             lalloc(ctx, L.raw, C * R * 4) && lalloc(ctx, L.n_raw, C) && lalloc(ctx, L.t1, C * R) &&
             lalloc(ctx, L.t2, C * R) && lalloc(ctx, L.m_angles, C * R) && lalloc(ctx, L.m_length, C * R) && lalloc(ctx, L.m_sangles, C * R) &&
             lalloc(ctx, L.m_order, C * R) && lalloc(ctx, L.m_tmp16, C * R) &&
-            lalloc(ctx, L.m_nb, C * R * line::kNbCap) && lalloc(ctx, L.m_fw, C * R * line::kNbCap) && lalloc(ctx, L.m_den, C * R) && lalloc(ctx, L.m_scan, C * R) && lalloc(ctx, L.m_cnt, C * 2) && lalloc(ctx, L.m_nb_cnt, C * R) &&
+            lalloc(ctx, L.m_nb, C * R * line::kNbCap) && lalloc(ctx, L.m_fw, C * R * line::kNbCap) && lalloc(ctx, L.m_scan, C * R) && lalloc(ctx, L.m_cnt, C * 2) && lalloc(ctx, L.m_nb_cnt, C * R) &&
             lalloc(ctx, L.m_code, C * R) && lalloc(ctx, L.m_check, C * R) && lalloc(ctx, L.m_loc, C * R) &&
             lalloc(ctx, L.m_flag, C * R, true) && lalloc(ctx, L.gxy, C * (size_t)w * h);
   if (!ok) {
