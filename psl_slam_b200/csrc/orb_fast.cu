@@ -255,20 +255,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 constexpr int kRW = 128;                  // scored columns per tile (4 per lane)
 constexpr int kRP = 160;                  // pixel row pitch = TMA box width
 constexpr int kRHmax = kInteriorMax;      // interior rows of a cell
-constexpr int kRowsThreads = 256;
+#ifndef PSL_ROWS_THREADS
+#define PSL_ROWS_THREADS 128
+#endif
+constexpr int kRowsThreads = PSL_ROWS_THREADS;
 
 __host__ __device__ inline int fast_group_cells(int w_cell) { return w_cell >= 63 ? 1 : (kRW - 3) / w_cell > 4 ? 4 : (kRW - 3) / w_cell; }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(kRowsThreads)
+__global__ void __launch_bounds__(kRowsThreads, 1024 / kRowsThreads)
     fast_rows_kernel(const OrbGeometry* __restrict__ geo, ImgBatch in0, const __grid_constant__ FastMaps maps, int ini_th,
                      int redo_empty, uint32_t* __restrict__ pool, int pool_cap, uint32_t* __restrict__ pool_count,
                      uint2* __restrict__ cell_tab, uint32_t* __restrict__ fb_list, uint32_t* __restrict__ fb_count,
-                     uint32_t* __restrict__ status) {
-  __shared__ __align__(128) uint8_t s_px[kRHmax + 6][kRP];
-  __shared__ __align__(16) uint8_t s_sc[kRHmax][kRW];
-  __shared__ uint32_t s_keep[kRHmax][kRW / 32];
-  __shared__ uint16_t s_list[kRHmax * kRW];
+                     uint32_t* __restrict__ status, int rh) {
+  // tiles sized by the tallest cell of this geometry (rh rows, 30..37 for the usual level sizes; kRHmax is the bound of
+  // the cell rule): fewer bytes per CTA, more CTAs per SM
+  extern __shared__ __align__(128) unsigned char rows_smem[];
+  uint8_t (*s_px)[kRP] = reinterpret_cast<uint8_t (*)[kRP]>(rows_smem);                                   // [rh + 6][kRP]
+  uint8_t (*s_sc)[kRW] = reinterpret_cast<uint8_t (*)[kRW]>(rows_smem + (size_t)(rh + 6) * kRP);           // [rh][kRW]
+  uint32_t (*s_keep)[kRW / 32] = reinterpret_cast<uint32_t (*)[kRW / 32]>(&s_sc[rh][0]);                   // [rh][kRW / 32]
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(&s_keep[rh][0]);                                          // [rh * kRW]
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_n, s_n2;
 
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(kRowsThreads)
     }
     const uint32_t K = (uint32_t)(127 - ini_th) * 0x01010101u;
     constexpr int kRT = 4;   // rows per thread and pass (5 measured slower: 5.32 against 5.19 ms per 2048 frames)
-    for (int r0 = 0; r0 < ih; r0 += 8 * kRT) {
+    for (int r0 = 0; r0 < ih; r0 += (kRowsThreads / 32) * kRT) {
       uint32_t M = 0;  // bit 8 j + k: pixel j of this thread's group in its row k survives
 #pragma unroll
       for (int k = 0; k < kRT; ++k) {
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(kRowsThreads)
 
   // ---- exact scores of the survivors, two per thread (scored (r, c) = shared pixel (r + 3, c_lo + c)) ---------------
   const int n = s_n;
-  constexpr int kHalf = kRHmax * kRW / 2;
+  const int kHalf = rh * kRW / 2;
   const bool two_lists = n <= kHalf;
   for (int k = 2 * tid; k < n; k += 2 * kRowsThreads) {
     const int ea = s_list[k], eb = s_list[min(k + 1, n - 1)];
@@ -423,15 +429,15 @@ __global__ void __launch_bounds__(kRowsThreads)
   __syncthreads();
 
   // ---- a warp per cell: the cell's rows of the bitmap -> its slice of the pool, raster order -------------------------
-  if (wid < nc) {
-    const int cell = g.first_cell + ci * g.n_cols + cj0 + wid;
+  for (int cw = wid; cw < nc; cw += kRowsThreads / 32) {
+    const int cell = g.first_cell + ci * g.n_cols + cj0 + cw;
     const int cells = geo->total_cells;
     uint2* tab = cell_tab + (size_t)b * cells + cell;
-    const int cs = cofs + wid * g.w_cell;                    // first scored column of the cell
-    const int iwk = min(g.w_cell, Wt - wid * g.w_cell);
+    const int cs = cofs + cw * g.w_cell;                     // first scored column of the cell
+    const int iwk = min(g.w_cell, Wt - cw * g.w_cell);
     if (iwk <= 0 || ih <= 0) {
       if (lane == 0) *tab = make_uint2(0u, 0u);
-      return;
+      continue;
     }
     // bits of row r that belong to the cell, as a 64-bit mask starting at the cell's first column (iwk <= 60)
     auto row_bits = [&](int r) -> unsigned long long {
@@ -460,7 +466,7 @@ __global__ void __launch_bounds__(kRowsThreads)
           *tab = make_uint2(0u, 0u);
         }
       }
-      return;
+      continue;
     }
     uint32_t base = 0;
     if (lane == 0) {
@@ -470,10 +476,10 @@ __global__ void __launch_bounds__(kRowsThreads)
       if (!fits) { atomicOr(status, kStatCandOverflow); atomicMax(status + 1, (uint32_t)b + 1u); }
     }
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + total > (uint32_t)pool_cap) return;
+    if (base + total > (uint32_t)pool_cap) continue;
     uint32_t* out = pool + (size_t)b * pool_cap + base;
     // level coordinate - minBorder of the cell's first interior pixel
-    const uint32_t x_rel = (uint32_t)(xa0 + wid * g.w_cell - kMinBorder), y_rel = (uint32_t)(ya - kMinBorder);
+    const uint32_t x_rel = (uint32_t)(xa0 + cw * g.w_cell - kMinBorder), y_rel = (uint32_t)(ya - kMinBorder);
     auto emit = [&](unsigned long long m, int r, int pos) {
       while (m) {
         const int x = __ffsll((long long)m) - 1;
@@ -566,12 +572,21 @@ void launch_fast_cells(const OrbGeometry* d_geo, const OrbGeometry& geo, ImgBatc
   const int redo = min_th < ini_th;
   if (redo) cudaMemsetAsync(fb_count, 0, sizeof(uint32_t), st);
   dim3 tgrid(geo.n_tiles, B);
+  int rh = 1;
+  for (int l = 0; l < geo.nlevels; ++l) rh = std::max(rh, geo.grid[l].h_cell);
+  rh = std::min(rh, kRHmax);
+  // pixels (+ 3 rows above / below) | scores | NMS bitmap | survivor list
+  const size_t smem = (size_t)(rh + 6) * kRP + (size_t)rh * kRW + (size_t)rh * (kRW / 32) * 4 + (size_t)rh * kRW * 2;
+  if (smem > 48 * 1024) {
+    cudaFuncSetAttribute(fast_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(fast_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   if (aligned)
-    fast_rows_kernel<true><<<tgrid, kRowsThreads, 0, st>>>(d_geo, in0, maps, ini_th, redo, pool, pool_cap, pool_count,
-                                                          cell_tab, fb_list, fb_count, status);
+    fast_rows_kernel<true><<<tgrid, kRowsThreads, smem, st>>>(d_geo, in0, maps, ini_th, redo, pool, pool_cap, pool_count,
+                                                             cell_tab, fb_list, fb_count, status, rh);
   else
-    fast_rows_kernel<false><<<tgrid, kRowsThreads, 0, st>>>(d_geo, in0, maps, ini_th, redo, pool, pool_cap, pool_count,
-                                                           cell_tab, fb_list, fb_count, status);
+    fast_rows_kernel<false><<<tgrid, kRowsThreads, smem, st>>>(d_geo, in0, maps, ini_th, redo, pool, pool_cap, pool_count,
+                                                              cell_tab, fb_list, fb_count, status, rh);
   if (redo) {
     if (aligned)
       fast_cells_kernel<true><<<list_grid, kFastThreads, 0, st>>>(d_geo, in0, ini_th, min_th, 1, fb_list, fb_count, 0u,
