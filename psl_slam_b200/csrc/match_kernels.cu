@@ -128,7 +128,8 @@ void launch_grid_build(const MatchFrames& f, int32_t* cell_start, uint16_t* cell
 // ---------------------------------------------------------------------------------------------
 constexpr int kCandWarps = 8;
 
-__global__ void __launch_bounds__(kCandWarps * 32)
+// (8 CTAs per SM: the kernel waits on its gathers, 64 resident warps at 32 registers beat 32 at 60: 5.4 -> 4.3 ms per 4096 frames)
+__global__ void __launch_bounds__(kCandWarps * 32, 8)
     proj_candidates_kernel(MatchFrames f, MatchQueries qs, const int32_t* __restrict__ cell_start,
                            const uint16_t* __restrict__ cell_items, uint32_t* __restrict__ cand,
                            int32_t* __restrict__ cand_count, uint2* __restrict__ cand_best,
