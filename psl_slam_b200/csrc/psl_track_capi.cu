@@ -53,7 +53,7 @@ int track_after_extract(psl_ctx* ctx, const uint16_t* d_depth, int32_t depth_str
 
   // The matching kernels are latency-bound per frame (one warp walks a frame's queries in order), so they
   // run over many more frames per launch than the L2-sized extraction chunks.
-  const int C = std::min(B, 1024);
+  const int C = std::min(B, 4096);   // frames per matching launch (the ordered resolve is one warp per frame: it wants them all)
   if ((rc = ensure(ctx, ctx->m_q, (size_t)C * cap * sizeof(psl_proj_query)))) return rc;
   if ((rc = ensure(ctx, ctx->m_n, (size_t)C * 4))) return rc;
   if ((rc = ensure(ctx, ctx->m_cell_start, (size_t)C * (kGridCells + 1) * 4))) return rc;
