@@ -266,3 +266,43 @@ def test_extract_lsd_chain_on_device_vs_oracle_pieces(orc):
             assert np.array_equal(g, w_)
         planes_seen += len(got[1])
     assert n.min() > 10
+
+
+def test_bench_sequence_both_extractors_vs_oracle(orc):
+    """Frames of the bench's own workload (the GPU-rendered cfg-4 sequence: ~1100 raw LSD segments and ~5 k FAST
+    candidates per frame, heavier than the goldens) through both batched extractors, every frame against the oracle."""
+    import os
+    import sys
+
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from psl_slam_b200 import KP_DTYPE, LINEextractor, ORBextractor
+    from psl_slam_b200._lib import KEYLINE_DTYPE
+    B, W, H = 40, 640, 480
+    rgb, _, _ = bench.render_sequence_cuda(4, B, W, H, torch.device("cuda"))
+    d_gray = bench.gray_cuda(rgb).contiguous()
+    gray = d_gray.cpu().numpy()
+    ex, lex = ORBextractor(), LINEextractor(chunk_frames=B)
+    cap, lcap = ex.cap, lex.cap
+    kps = torch.zeros((B, cap, KP_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device="cuda")
+    n = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ex.extract_batch_dev(d_gray.data_ptr(), B, W, H, W, W * H, kps.data_ptr(), desc.data_ptr(), n.data_ptr())
+    ex.ctx.sync()
+    kl = torch.zeros((B, lcap, KEYLINE_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    ld = torch.zeros((B, lcap, 32), dtype=torch.uint8, device="cuda")
+    eq = torch.zeros((B, lcap, 3), dtype=torch.float64, device="cuda")
+    nl = torch.zeros(B, dtype=torch.int32, device="cuda")
+    lex.extract_batch_dev(d_gray.data_ptr(), B, W, H, W, W * H, kl.data_ptr(), ld.data_ptr(), eq.data_ptr(), None, nl.data_ptr())
+    lex.ctx.sync()
+    n, nl = n.cpu().numpy(), nl.cpu().numpy()
+    kps, desc = kps.cpu().numpy().reshape(B, -1).view(KP_DTYPE), desc.cpu().numpy()
+    kl, ld, eq = kl.cpu().numpy().reshape(B, -1).view(KEYLINE_DTYPE), ld.cpu().numpy(), eq.cpu().numpy()
+    for b in range(0, B, 3):   # (the oracle takes ~50 ms per frame: every third frame keeps the test short)
+        wk, wd = orc.orb_extract(gray[b])
+        assert n[b] == len(wk) and kps[b, : n[b]].tobytes() == wk.tobytes() and np.array_equal(desc[b, : n[b]], wd), b
+        wl, wld, weq, _ = orc.line_extract(gray[b])
+        assert nl[b] == len(wl) and kl[b, : nl[b]].tobytes() == wl.tobytes(), b
+        assert np.array_equal(ld[b, : nl[b]], wld) and np.array_equal(eq[b, : nl[b]], weq), b
+    assert n.min() > 900 and nl.min() > 40
