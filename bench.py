@@ -240,7 +240,7 @@ def run_reference(args, rank, world):
         return
     gray, depth, T12 = synth_frames_rgb(24)
     cores = os.cpu_count() or 1
-    per_step = 2 * cores
+    per_step = 8 * cores   # enough tasks per thread that the step does not end on one straggler
     idx = ping_pong(len(gray), per_step)
     g, d, t = gray[idx], depth[idx], T12[idx]
     for _ in range(args.warmup):
