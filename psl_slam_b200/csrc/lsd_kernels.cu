@@ -151,16 +151,32 @@ __global__ void __launch_bounds__(128)
   const uint8_t* r0 = scaled + ((size_t)b * Hs + y) * Ws;
   const uint8_t* r1 = r0 + Ws;
   int cnt = 0, mx = -1;
-  if (y < Hs - 1)
-    for (int x = lane; x < Ws - 1; x += 32) {
-      const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
-      const int gx = DA + BC, gy = DA - BC;
-      const int q = gx * gx + gy * gy;
-      if (q > q_undef) {
-        ++cnt;
-        mx = max(mx, q);
-      }
+  auto px = [&](int a, int b1, int c, int d) {   // a = r0[x], b1 = r0[x + 1], c = r1[x], d = r1[x + 1]
+    const int DA = d - a, BC = b1 - c;
+    const int gx = DA + BC, gy = DA - BC;
+    const int q = gx * gx + gy * gy;
+    if (q > q_undef) {
+      ++cnt;
+      mx = max(mx, q);
     }
+  };
+  if (y < Hs - 1) {
+    if ((Ws & 3) == 0 && ((reinterpret_cast<uintptr_t>(scaled)) & 3) == 0) {
+      // whole words: a lane owns 4 adjacent pixels, the fifth byte of its window is the first of the next word
+      for (int x = 4 * lane; x < Ws; x += 128) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(r0 + x), c = *reinterpret_cast<const uint32_t*>(r1 + x);
+        const bool last = x + 4 >= Ws;
+        const uint32_t a4 = last ? 0u : (uint32_t)r0[x + 4], c4 = last ? 0u : (uint32_t)r1[x + 4];
+        const int A[5] = {(int)(a & 255u), (int)((a >> 8) & 255u), (int)((a >> 16) & 255u), (int)(a >> 24), (int)a4};
+        const int Cc[5] = {(int)(c & 255u), (int)((c >> 8) & 255u), (int)((c >> 16) & 255u), (int)(c >> 24), (int)c4};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (!(last && k == 3)) px(A[k], A[k + 1], Cc[k], Cc[k + 1]);   // the last column of a row has no gradient
+      }
+    } else {
+      for (int x = lane; x < Ws - 1; x += 32) px((int)r0[x], (int)r0[x + 1], (int)r1[x], (int)r1[x + 1]);
+    }
+  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
