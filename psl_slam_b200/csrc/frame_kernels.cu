@@ -179,9 +179,12 @@ void launch_pose_points(const psl_keypoint* kps, const float* u_right, const flo
 template <int CH>
 __global__ void __launch_bounds__(256)
     color_to_gray_kernel(const uint8_t* __restrict__ color, int r_first, int color_stride, int64_t color_fs,
-                         uint8_t* __restrict__ gray, int gray_stride, int64_t gray_fs, int w) {
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, b = blockIdx.z;
-  if (x >= w) return;
+                         uint8_t* __restrict__ gray, int gray_stride, int64_t gray_fs, int w, int h) {
+  // a thread owns 4 adjacent pixels; the groups of all rows are numbered through, so that no thread of a CTA idles on a
+  // row that is not a multiple of 1024 pixels wide
+  const int gpr = (w + 3) >> 2, idx = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  const int y = idx / gpr, x = (idx - y * gpr) * 4;
+  if (y >= h) return;
   const uint8_t* src = color + (size_t)b * color_fs + (size_t)y * color_stride + (size_t)x * CH;
   uint8_t* dst = gray + (size_t)b * gray_fs + (size_t)y * gray_stride + x;
   const int n = min(4, w - x);
@@ -207,13 +210,47 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < n; ++k) dst[k] = (uint8_t)(out >> (8 * k));
 }
 
+// The same for 3-channel images whose rows are whole 16-pixel groups on 16-byte boundaries: a thread owns 16 pixels,
+// three 16-byte loads in flight, one 16-byte store.
+__global__ void __launch_bounds__(256)
+    color3_to_gray16_kernel(const uint8_t* __restrict__ color, int r_first, int color_stride, int64_t color_fs,
+                            uint8_t* __restrict__ gray, int gray_stride, int64_t gray_fs, int w, int h) {
+  const int gpr = w >> 4, idx = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  const int y = idx / gpr, x = (idx - y * gpr) * 16;
+  if (y >= h) return;
+  const uint4* src = reinterpret_cast<const uint4*>(color + (size_t)b * color_fs + (size_t)y * color_stride + (size_t)x * 3);
+  const uint4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2);
+  const uint32_t wds[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+  uint32_t out[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {   // 4 pixels = 12 bytes = words 3g .. 3g + 2
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int byte0 = 12 * g + 3 * k;
+      auto byte_at = [&](int i) -> uint32_t { return (wds[i >> 2] >> (8 * (i & 3))) & 255u; };
+      const uint32_t c0 = byte_at(byte0), c1 = byte_at(byte0 + 1), c2 = byte_at(byte0 + 2);
+      const uint32_t R = r_first ? c0 : c2, B = r_first ? c2 : c0;
+      o |= ((R * 9798u + c1 * 19235u + B * 3735u + 16384u) >> 15) << (8 * k);
+    }
+    out[g] = o;
+  }
+  *reinterpret_cast<uint4*>(gray + (size_t)b * gray_fs + (size_t)y * gray_stride + x) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 void launch_color_to_gray(const uint8_t* color, int channels, int rgb_order, int color_stride, int64_t color_fs,
                           uint8_t* gray, int gray_stride, int64_t gray_fs, int B, int w, int h, cudaStream_t st) {
-  dim3 grid(((w + 3) / 4 + 255) / 256, h, B);
+  if (channels == 3 && (w & 15) == 0 && ((uintptr_t)color & 15) == 0 && (color_stride & 15) == 0 && (color_fs & 15) == 0 &&
+      ((uintptr_t)gray & 15) == 0 && (gray_stride & 15) == 0 && (gray_fs & 15) == 0) {
+    dim3 grid16(((w >> 4) * h + 255) / 256, B);
+    color3_to_gray16_kernel<<<grid16, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w, h);
+    return;
+  }
+  dim3 grid(((w + 3) / 4 * h + 255) / 256, B);
   if (channels == 3)
-    color_to_gray_kernel<3><<<grid, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w);
+    color_to_gray_kernel<3><<<grid, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w, h);
   else
-    color_to_gray_kernel<4><<<grid, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w);
+    color_to_gray_kernel<4><<<grid, 256, 0, st>>>(color, rgb_order, color_stride, color_fs, gray, gray_stride, gray_fs, w, h);
 }
 
 __global__ void __launch_bounds__(256)

@@ -115,6 +115,16 @@ def test_input_conversion_vs_cv2_golden():
     rgb, _ = synth.render(poster, synth.trajectory(1, 3)[0], 320, 240)
     gray, _ = convert_rgbd(ctx, rgb[None], True, None)
     assert np.array_equal(gray[0], synth.rgb_to_gray(rgb))
+    # both kernels (16 pixels per thread for rows of whole 16-pixel groups, 4 per thread otherwise), both channel orders
+    rng = np.random.default_rng(11)
+    for w in (64, 640, 52, 37):
+        img = rng.integers(0, 256, (3, 24, w, 3), dtype=np.uint8)
+        c = img.astype(np.uint32)
+        for order in (True, False):
+            r, b = (c[..., 0], c[..., 2]) if order else (c[..., 2], c[..., 0])
+            want = ((r * 9798 + c[..., 1] * 19235 + b * 3735 + 16384) >> 15).astype(np.uint8)
+            got, _ = convert_rgbd(ctx, img, order, None)
+            assert np.array_equal(got, want), (w, order)
 
 
 @pytest.mark.parametrize("cam", ["tum1", "tum2", "k1only", "strong"])
