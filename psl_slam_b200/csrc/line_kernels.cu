@@ -711,12 +711,12 @@ __global__ void __launch_bounds__(64)
     // One sample: round() of the reference (half away from zero, on the float promoted to double) == roundf on the
     // float; the coordinates step in fp32 independently of the gradients, so the gathers of kAhead samples are issued
     // together and the four sums then take them in the reference's order.
+    // (the reference rounds into a `short`; inside +/- 32767 the int below is that value, and coordinates beyond it --
+    // undefined behaviour there -- cannot occur for a support region of a line inside an image of at most 16384 pixels)
     auto sample_addr = [&](float sx, float sy) -> int {
-      short q = (short)roundf(sx);
-      const short xCor = (q < 0) ? (short)0 : (q > imageWidth) ? imageWidth : q;
-      q = (short)roundf(sy);
-      const short yCor = (q < 0) ? (short)0 : (q > imageHeight) ? imageHeight : q;
-      return (int)yCor * w + (int)xCor;
+      const int xCor = min(max((int)roundf(sx), 0), (int)imageWidth);
+      const int yCor = min(max((int)roundf(sy), 0), (int)imageHeight);
+      return yCor * w + xCor;
     };
     auto accumulate = [&](short2 gg) {
       const float gDL = (float)gg.x * dL0 + (float)gg.y * dL1, gDO = (float)gg.x * dO0 + (float)gg.y * dO1;
